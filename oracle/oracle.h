@@ -1,0 +1,148 @@
+/* oracle/oracle.h -- CPU ORACLE: TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C restatement of the RestartSQP hot path, used as the
+ * checker for the CUDA kernels.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library.  The product
+ * (restartsqp_b200/lib/libsqpb200.so) never links, loads or calls it.
+ *
+ * Pinning status:
+ *   - L0 functions (triplet->CSC, value scatter, SpMV/SpMTV, norms): PINNED against the
+ *     reference's own code compiled in oracle/_ref (tests/test_oracle_l0.py) and against
+ *     committed golden vectors generated from it (tests/golden/l0_golden.json).
+ *   - L1/L2 glue (QP data construction, working-set translation, KKT residual formulas):
+ *     restated from src/QPhandler.cpp and src/qpOASESInterface.cpp; those files cannot be
+ *     compiled here (they need qpOASES + Ipopt), so they are pinned by reading only.
+ *   - Active-set QP/LP arithmetic (row D): qpOASES 3.2.1 is an un-vendored third-party
+ *     dependency (CMakeLists.txt:81-94) that is absent from /root/reference and from this
+ *     container.  "PARITY UNPINNED": the oracle restates the published online active-set
+ *     strategy (Ferreau, Bock, Diehl 2008; Ferreau et al. 2014) and is validated by
+ *     independent ground truth (exhaustive active-set enumeration on small strictly convex
+ *     QPs, and the reference's own KKT acceptance test at 1e-6), not by qpOASES outputs.
+ */
+#ifndef RESTARTSQP_ORACLE_H
+#define RESTARTSQP_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- constants: include/sqphot/Utils.hpp:35-37 ---- */
+#define ORC_INF 1.0e18
+#define ORC_M_EPS 1.0e-16
+#define ORC_SQRT_M_EPS 1.0e-8
+
+/* ActiveType: include/sqphot/Types.hpp:84-89 */
+#define ORC_ACTIVE_ABOVE 1
+#define ORC_ACTIVE_BELOW (-1)
+#define ORC_ACTIVE_BOTH_SIDE (-99)
+#define ORC_INACTIVE 0
+
+/* Exitflag QP codes: include/sqphot/Types.hpp:51-73 */
+#define ORC_QP_OPTIMAL 20
+#define ORC_QPERROR_INTERNAL_ERROR 21
+#define ORC_QPERROR_INFEASIBLE 22
+#define ORC_QPERROR_UNBOUNDED 23
+#define ORC_QPERROR_EXCEED_MAX_ITER 24
+#define ORC_QPERROR_NOTINITIALISED 25
+#define ORC_QPERROR_PERFORMINGHOMOTOPY 28
+#define ORC_QPERROR_UNKNOWN 30
+
+/* ------------------------------------------------------------------ L0 ---- */
+
+/* Entry-list construction of SpHbMat::setStructure(rhs, I_info), src/SpHbMat.cpp:203-227:
+ * the zJ triplets followed by the identity blocks.  Returns total entry count. */
+int orc_expand_A(int zJ, const int* row1, const int* col1, const double* val, int I_len,
+                 const int* I_irow, const int* I_jcol, const int* I_size, const double* I_value,
+                 int* e_row1, int* e_col1, double* e_val);
+
+/* Entry-list construction of SpHbMat::setStructure(rhs), src/SpHbMat.cpp:296-309:
+ * every off-diagonal of a symmetric triplet is followed by its mirror. Returns count. */
+int orc_expand_H(int zH, const int* row1, const int* col1, const double* val, int symmetric,
+                 int* e_row1, int* e_col1, double* e_val);
+
+/* Sort by (col,row) [tie-break: entry counter] and emit 0-based CSC + `order`,
+ * src/SpHbMat.cpp:253-264 with comparator include/sqphot/SpHbMat.hpp:370-380. */
+void orc_csc_from_entries(int ncol, int z, const int* e_row1, const int* e_col1,
+                          const double* e_val, int* colptr, int* rowidx, double* val, int* order);
+
+/* SpHbMat::setMatVal(rhs, I_info): src/SpHbMat.cpp:368-380 */
+void orc_setmatval_A(int zJ, const int* order, const double* jac_val, double* csc_val);
+/* SpHbMat::setMatVal(rhs): src/SpHbMat.cpp:383-393 */
+void orc_setmatval_H(int zH, const int* row1, const int* col1, int symmetric, const int* order,
+                     const double* h_val, double* csc_val);
+
+/* SpHbMat::times / transposed_times, CSC branch: src/SpHbMat.cpp:720-736, 679-695 */
+void orc_csc_times(int nrow, int ncol, const int* colptr, const int* rowidx, const double* val,
+                   const double* x, double* y);
+void orc_csc_transposed_times(int nrow, int ncol, const int* colptr, const int* rowidx,
+                              const double* val, const double* x, double* y);
+/* SpTripletMat::times / transposed_times: src/SpTripletMat.cpp:237-258, 311-323 */
+void orc_triplet_times(int nrow, int ncol, int z, const int* row1, const int* col1,
+                       const double* val, int symmetric, int transpose, const double* x, double* y);
+/* Utils oneNorm/infNorm: src/Utils.cpp:65-83 */
+double orc_one_norm(const double* x, int n);
+double orc_inf_norm(const double* x, int n);
+
+/* ------------------------------------------------- L2: QPhandler data ---- */
+/* QPhandler::set_bounds / update_bounds / update_delta (non-QORE branch):
+ * src/QPhandler.cpp:185-201, 358-367, 559-564.  mode: 0=set_bounds, 1=update_bounds
+ * (refreshes lbA but NOT ubA: quirk 2), 2=update_delta. */
+void orc_qp_bounds(int mode, int n, int m, double delta, const double* x_l, const double* x_u,
+                   const double* x_k, const double* c_l, const double* c_u, const double* c_k,
+                   double* lb, double* ub, double* lbA, double* ubA);
+/* QPhandler::set_g / update_grad / update_penalty: src/QPhandler.cpp:287-292, 461-462, 439-440.
+ * grad may be NULL (penalty only); rho<0 means "leave slack entries". */
+void orc_qp_g(int n, int m, const double* grad, double rho, double* g);
+/* QPhandler::get_infea_measure_model: src/QPhandler.cpp:592-594 */
+double orc_infea_measure_model(int n, int m, const double* x_qp);
+
+/* ------------------------------------------------- L1: backend glue ------ */
+/* qpOASESInterface::get_working_set: src/qpOASESInterface.cpp:835-895 (raw +1/-1/0 ->
+ * ActiveType, including the misplaced-parenthesis behaviour at :874 and :880). */
+void orc_translate_working_set(int nV, int nC, const int* raw_b, const int* raw_c, const double* x,
+                               const double* Ax, const double* lb, const double* ub,
+                               const double* lbA, const double* ubA, int* W_b, int* W_c);
+/* qpOASESInterface::test_optimality: src/qpOASESInterface.cpp:498-684.
+ * out[0..4] = primal, dual, stationarity, complementarity, KKT_error.  Returns 1 iff
+ * KKT_error <= 1e-6 (:673).  H may be absent (colptr NULL): then Hx = 0. */
+int orc_kkt_residuals(int nV, int nC, const int* A_colptr, const int* A_rowidx, const double* A_val,
+                      const int* H_colptr, const int* H_rowidx, const double* H_val, const double* g,
+                      const double* lb, const double* ub, const double* lbA, const double* ubA,
+                      const double* x, const double* y, const int* W_b, const int* W_c, double* out);
+
+/* ------------------------------------------------- row D: active-set QP -- */
+typedef struct orc_qp orc_qp;
+
+typedef struct {
+    int max_iter;          /* nWSR (Options::qp_maxiter / lp_maxiter) */
+    int refactor_every;    /* enableCholeskyRefactorisation (setToReliable: 1) */
+    int refine_steps;      /* numRefinementSteps */
+    int enable_flipping;   /* enableFlippingBounds */
+    int enable_drift;      /* enableDriftCorrection */
+    int enable_ramping;    /* enableRamping */
+} orc_qp_options;
+
+void orc_qp_default_options(orc_qp_options* o);
+orc_qp* orc_qp_create(int nV, int nC);
+void orc_qp_destroy(orc_qp* q);
+/* Cold start ("init"): H may be NULL colptr for an LP.  Returns Exitflag (20 = optimal). */
+int orc_qp_init(orc_qp* q, const orc_qp_options* opt, const int* H_colptr, const int* H_rowidx,
+                const double* H_val, const double* g, const int* A_colptr, const int* A_rowidx,
+                const double* A_val, const double* lb, const double* ub, const double* lbA,
+                const double* ubA, int is_lp);
+/* Hot start with unchanged matrices ("hotstart(g,lb,ub,lbA,ubA)"). */
+int orc_qp_hotstart(orc_qp* q, const orc_qp_options* opt, const double* g, const double* lb,
+                    const double* ub, const double* lbA, const double* ubA);
+/* Hot start with new matrix values, same pattern ("hotstart(H,g,A,...)"). */
+int orc_qp_hotstart_matrices(orc_qp* q, const orc_qp_options* opt, const double* H_val,
+                             const double* A_val, const double* g, const double* lb,
+                             const double* ub, const double* lbA, const double* ubA);
+void orc_qp_get_solution(const orc_qp* q, double* x, double* y, double* obj, int* iters);
+void orc_qp_get_working_set(const orc_qp* q, int* raw_b, int* raw_c);
+/* flop counter for the roofline model of SURVEY.md section 8(d) */
+double orc_qp_get_flops(const orc_qp* q);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,188 @@
+/* sqpb200.h -- C ABI of the B200-native batched QP-subproblem engine for RestartSQP.
+ *
+ * This is the drop-in boundary: what a `CudaQPInterface :
+ * QPSolverInterface` adapter class (restartsqp_b200/csrc/adapter/CudaQPInterface.hpp) and the
+ * batched host driver call.  No C++ types, no exceptions and no torch types cross this line.
+ * Every function returns 0 on success, a negative SQPB200_ERR_* code on a library error, or,
+ * for the solve status arrays, the reference's Exitflag QP codes 20..30
+ * (include/sqphot/Types.hpp:51-73).
+ *
+ * One handle owns the device state of `batch` independent QP (or LP) instances that share
+ * one sparsity pattern (one NLP structure), exactly the data one
+ * `qpOASESInterface` object owns for a single instance (src/qpOASESInterface.cpp:106-128):
+ * lb, ub, g, x [nV]; lbA, ubA [nC]; y [nV+nC]; A (CSC, nC x nV); H (CSC, nV x nV; QP only);
+ * plus the hot-start state qpOASES keeps inside SQProblem (working set, TQ/Cholesky factors).
+ *
+ * Array arguments are caller-owned; `loc` says whether the pointer is host or device memory.
+ * Batched arrays are instance-major: vals[batch][len], contiguous.
+ * There is NO CPU fallback: every compute entry point runs CUDA kernels on the handle's device
+ * and fails with SQPB200_ERR_CUDA if no device is available.
+ */
+#ifndef SQPB200_H
+#define SQPB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sqpb200_handle_s* sqpb200_handle;
+
+#define SQPB200_LOC_HOST 0
+#define SQPB200_LOC_DEVICE 1
+
+/* QPType, include/sqphot/Types.hpp:45-48 */
+#define SQPB200_LP 1
+#define SQPB200_QP 2
+
+/* vector selectors for sqpb200_set_vectors / get_vectors (setters at
+ * include/sqphot/QPsolverInterface.hpp:144-165) */
+#define SQPB200_VEC_G 0
+#define SQPB200_VEC_LB 1
+#define SQPB200_VEC_UB 2
+#define SQPB200_VEC_LBA 3
+#define SQPB200_VEC_UBA 4
+
+#define SQPB200_MAT_A 0
+#define SQPB200_MAT_H 1
+
+/* ActiveType, include/sqphot/Types.hpp:84-89 */
+#define SQPB200_ACTIVE_ABOVE 1
+#define SQPB200_ACTIVE_BELOW (-1)
+#define SQPB200_ACTIVE_BOTH_SIDE (-99)
+#define SQPB200_INACTIVE 0
+
+/* Exitflag QP codes, include/sqphot/Types.hpp:60-70 */
+#define SQPB200_QP_OPTIMAL 20
+#define SQPB200_QPERROR_INTERNAL_ERROR 21
+#define SQPB200_QPERROR_INFEASIBLE 22
+#define SQPB200_QPERROR_UNBOUNDED 23
+#define SQPB200_QPERROR_EXCEED_MAX_ITER 24
+#define SQPB200_QPERROR_NOTINITIALISED 25
+#define SQPB200_QPERROR_PERFORMINGHOMOTOPY 28
+#define SQPB200_QPERROR_UNKNOWN 30
+
+#define SQPB200_ERR_INVALID (-1)
+#define SQPB200_ERR_CUDA (-2)
+#define SQPB200_ERR_NOMEM (-3)
+#define SQPB200_ERR_STATE (-4)
+#define SQPB200_ERR_TOO_LARGE (-5)
+
+/* Solver options.  Defaults mirror Options::setToDefault (src/Options.cpp:19-57) for the
+ * iteration limits and qpOASES Options::setToReliable (src/qpOASESInterface.cpp:765) for the rest. */
+typedef struct {
+    int qp_maxiter;      /* Options::qp_maxiter = 1000 */
+    int lp_maxiter;      /* Options::lp_maxiter = 100 */
+    int enable_flipping; /* 1 */
+    int enable_ramping;  /* 1 */
+    int enable_drift;    /* 1 */
+    int team_size;       /* threads cooperating on one QP: 0 = choose from (nV, nC); 32..256 */
+    int keep_state;      /* 1: keep working set + factors resident for hot starts */
+} sqpb200_options;
+
+void sqpb200_default_options(sqpb200_options* o);
+const char* sqpb200_version(void);
+/* number of CUDA devices visible, or SQPB200_ERR_CUDA */
+int sqpb200_device_count(void);
+
+/* ---- life cycle: replaces qpOASESInterface ctor + allocate_memory (src/qpOASESInterface.cpp:35-50,
+ * 106-128).  nV = nVar_QP, nC = nConstr_QP. */
+int sqpb200_create(int batch, int nV, int nC, int qptype, int device, const sqpb200_options* opts,
+                   sqpb200_handle* out);
+int sqpb200_destroy(sqpb200_handle h);
+/* run all subsequent work of this handle on the given cudaStream_t (NULL = default stream) */
+int sqpb200_set_stream(sqpb200_handle h, void* cuda_stream);
+int sqpb200_synchronize(sqpb200_handle h);
+const char* sqpb200_last_error(sqpb200_handle h);
+
+/* ---- structure: replaces set_A / set_H first call -> SpHbMat::setStructure
+ * (src/qpOASESInterface.cpp:426-437, 400-417; src/SpHbMat.cpp:196-268, 284-355).
+ * Triplets are 1-based (FORTRAN style, src/SQPTNLP.cpp:18).  The identity blocks are the
+ * IdentityInfo of include/sqphot/Types.hpp:36-42.  Runs the device segmented sort/scan.
+ * Returns the number of CSC entries (>= 0) or a negative error. */
+int sqpb200_set_structure_A(sqpb200_handle h, int zJ, const int* row1, const int* col1, int I_len,
+                            const int* I_irow, const int* I_jcol, const int* I_size,
+                            const double* I_value);
+int sqpb200_set_structure_H(sqpb200_handle h, int zH, const int* row1, const int* col1,
+                            int is_symmetric);
+/* Direct CSC structure (the data constructor used by the replay driver,
+ * src/qpOASESInterface.cpp:54-94, test/QPsolvers_testers.cpp:220-221). */
+int sqpb200_set_structure_csc(sqpb200_handle h, int which, int nnz, const int* colptr,
+                              const int* rowidx);
+/* Copy the CSC index arrays back to the host for parity checks: colptr[ncol+1], rowidx[nnz],
+ * order[nnz] (order may be NULL). */
+int sqpb200_get_structure(sqpb200_handle h, int which, int* colptr, int* rowidx, int* order);
+int sqpb200_get_nnz(sqpb200_handle h, int which);
+
+/* ---- values: replaces set_A / set_H later calls -> SpHbMat::setMatVal (src/SpHbMat.cpp:368-393).
+ * vals[batch][z] are triplet-ordered values (zJ per instance for A, zH for H); they are scattered
+ * through `order` on the device.  broadcast != 0: vals[z] is shared by all instances. */
+int sqpb200_set_values_A(sqpb200_handle h, const double* vals, int loc, int broadcast);
+int sqpb200_set_values_H(sqpb200_handle h, const double* vals, int loc, int broadcast);
+/* CSC-ordered values (data-constructor path). */
+int sqpb200_set_values_csc(sqpb200_handle h, int which, const double* vals, int loc, int broadcast);
+int sqpb200_get_values_csc(sqpb200_handle h, int which, double* vals, int loc);
+
+/* ---- vectors: bulk form of set_lb/set_ub/set_lbA/set_ubA/set_g
+ * (src/qpOASESInterface.cpp:361-395, 445-484).  Writes vals[batch][count] into entries
+ * [offset, offset+count) of the selected vector of every instance and raises the same change
+ * flags (Update_bounds / Update_g).  broadcast != 0: vals[count] shared by all instances. */
+int sqpb200_set_vectors(sqpb200_handle h, int which, const double* vals, int offset, int count,
+                        int loc, int broadcast);
+int sqpb200_get_vectors(sqpb200_handle h, int which, double* vals, int loc);
+
+/* ---- batched QPhandler data construction on the device (src/QPhandler.cpp:167-261, 272-297,
+ * 342-419, 430-463, 533-567): n = NLP variables, m = NLP constraints (nV = n+2m, nC = m).
+ * mode 0 = set_bounds, 1 = update_bounds (lbA only: quirk 2), 2 = update_delta.
+ * delta[batch]; x_l,x_u,x_k [batch][n]; c_l,c_u,c_k [batch][m] (device or host per loc). */
+int sqpb200_qphandler_bounds(sqpb200_handle h, int mode, int n, int m, const double* delta,
+                             const double* x_l, const double* x_u, const double* x_k,
+                             const double* c_l, const double* c_u, const double* c_k, int loc);
+/* g = [grad ; rho*1]: grad[batch][n] may be NULL (update_penalty), rho[batch] may be NULL
+ * (update_grad). */
+int sqpb200_qphandler_g(sqpb200_handle h, int n, int m, const double* grad, const double* rho,
+                        int loc);
+
+/* ---- solve: replaces optimizeQP / optimizeLP incl. the init/hotstart state machine and the
+ * one-retry recovery (src/qpOASESInterface.cpp:137-284, 686-758, 817-833).
+ * mode = SQPB200_QP or SQPB200_LP; maxiter <= 0 uses the option default; active_mask[batch]
+ * (host, may be NULL = all) selects the instances to solve. */
+int sqpb200_solve(sqpb200_handle h, int mode, int maxiter, const unsigned char* active_mask);
+
+/* ---- results (src/qpOASESInterface.cpp:221-222, 290-357).  Any pointer may be NULL.
+ * x[batch][nV]; y[batch][nV+nC] (bound multipliers first); obj[batch]; status[batch] (Exitflag);
+ * iters[batch] (working-set changes of the last solve, what the reference adds to Stats::qp_iter). */
+int sqpb200_get_solution(sqpb200_handle h, double* x, double* y, double* obj, int* status,
+                         int* iters, int loc);
+/* wb[batch][nV], wc[batch][nC] as int32.  translated = 0: raw qpOASES convention (+1 upper,
+ * -1 lower, 0 inactive); translated = 1: the reference's ActiveType after get_working_set
+ * (src/qpOASESInterface.cpp:835-895). */
+int sqpb200_get_working_set(sqpb200_handle h, int* wb, int* wc, int translated, int loc);
+/* out[batch][5] = primal, dual, stationarity, complementarity violation and KKT_error of
+ * test_optimality (src/qpOASESInterface.cpp:498-684), evaluated by the solve kernel's epilogue. */
+int sqpb200_kkt_residuals(sqpb200_handle h, double* out, int loc);
+/* Recompute them with the stand-alone batched kernel (for parity tests and ncu). */
+int sqpb200_kkt_residuals_recompute(sqpb200_handle h, double* out, int loc);
+
+/* ---- stand-alone batched SpMV / SpMTV on the handle's CSC matrices (SpHbMat::times,
+ * transposed_times; src/SpHbMat.cpp:659-737).  x[batch][ncol or nrow], y[batch][nrow or ncol]. */
+int sqpb200_spmv(sqpb200_handle h, int which, int transpose, const double* x, double* y, int loc);
+
+/* ---- stand-alone segmented triplet -> CSC assembly over `nmat` independent matrices in one
+ * launch (rows A4/A5 as a batched device sort/scan).  seg[nmat+1] are offsets into the 1-based
+ * triplet arrays; ncol[nmat] column counts.  Outputs: colptr (concatenated, sum(ncol+1)),
+ * rowidx and order (same offsets as the input).  All pointers host memory. */
+int sqpb200_assemble_csc_batched(int device, int nmat, const int* seg, const int* ncol,
+                                 const int* row1, const int* col1, int* colptr, int* rowidx,
+                                 int* order, float* kernel_ms);
+
+/* kernels launched by this handle since creation (for bench.py's gpu_launches) */
+long long sqpb200_launch_count(sqpb200_handle h);
+/* smem bytes per QP, team size and QPs per CTA chosen for the solve kernel */
+int sqpb200_solve_config(sqpb200_handle h, int* team_size, int* qps_per_cta, int* smem_per_cta);
+/* device time of the last solve launch measured with CUDA events on the handle's stream (ms) */
+float sqpb200_last_solve_ms(sqpb200_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQPB200_H */

@@ -118,15 +118,18 @@ void orc_qp_destroy(orc_qp* q) {
 }
 
 /* ------------------------------------------------------------ sparse products */
-/* out = (H + reg I) v, storage-order accumulation as SpHbMat::times (src/SpHbMat.cpp:729-735) */
+/* out = (H + reg I) v.  H is symmetric (SymSparseMat, src/qpOASESInterface.cpp:412-416), so row c
+ * is read from column c of the CSC arrays; for a symmetric H the terms and their order are those
+ * of SpHbMat::times (src/SpHbMat.cpp:729-735). */
 static void mulH(const orc_qp* q, const double* v, double* out) {
     int nV = q->nV;
-    for (int i = 0; i < nV; i++) out[i] = 0.0;
-    if (q->has_H)
-        for (int c = 0; c < nV; c++)
-            for (int e = q->Hp[c]; e < q->Hp[c + 1]; e++) out[q->Hi[e]] += q->Hv[e] * v[c];
-    if (q->reg != 0.0)
-        for (int i = 0; i < nV; i++) out[i] += q->reg * v[i];
+    for (int c = 0; c < nV; c++) {
+        double s = 0.0;
+        if (q->has_H)
+            for (int e = q->Hp[c]; e < q->Hp[c + 1]; e++) s += q->Hv[e] * v[q->Hi[e]];
+        if (q->reg != 0.0) s += q->reg * v[c];
+        out[c] = s;
+    }
 }
 static void mulA(const orc_qp* q, const double* v, double* out) {
     for (int i = 0; i < q->nC; i++) out[i] = 0.0;
@@ -338,7 +341,7 @@ static void solve_T(const orc_qp* q, const double* b, double* v) {
     for (int i = 0; i < nAC; i++) {
         int d = nFR - 1 - i;
         double s = b[i];
-        for (int j = d + 1; j < nFR; j++) s -= q->T[(size_t)i * nV + j] * v[j];
+        for (int j = nFR - 1; j > d; j--) s -= q->T[(size_t)i * nV + j] * v[j];
         v[d] = s / q->T[(size_t)i * nV + d];
     }
 }
@@ -348,7 +351,7 @@ static void solve_Tt(const orc_qp* q, const double* r, double* u) {
     for (int i = nAC - 1; i >= 0; i--) {
         int d = nFR - 1 - i;
         double s = r[d];
-        for (int k = i + 1; k < nAC; k++) s -= q->T[(size_t)k * nV + d] * u[k];
+        for (int k = nAC - 1; k > i; k--) s -= q->T[(size_t)k * nV + d] * u[k];
         u[i] = s / q->T[(size_t)i * nV + d];
     }
 }
@@ -388,7 +391,7 @@ static void step_direction(orc_qp* q, const double* dgv, const double* dxFX_full
         }
         for (int i = nZ - 1; i >= 0; i--) {
             double s = q->zv[i];
-            for (int k = i + 1; k < nZ; k++) s -= q->R[(size_t)i * nV + k] * q->zv[k];
+            for (int k = nZ - 1; k > i; k--) s -= q->R[(size_t)i * nV + k] * q->zv[k];
             q->zv[i] = s / q->R[(size_t)i * nV + i];
         }
         for (int p = 0; p < nFR; p++) {
@@ -421,6 +424,7 @@ static void step_direction(orc_qp* q, const double* dgv, const double* dxFX_full
 /* (qpOASES performDriftCorrection + setupAuxiliaryQPgradient) */
 static void drift_correction(orc_qp* q) {
     int nV = q->nV, nC = q->nC;
+    mulA(q, q->x, q->Ax); /* Ax is re-evaluated, not carried along, so it cannot drift from A*x */
     for (int i = 0; i < nV; i++) {
         if (q->sB[i] < 0) { q->lb[i] = q->x[i]; if (q->ub[i] < q->x[i]) q->ub[i] = q->x[i]; if (q->y[i] < 0) q->y[i] = 0.0; }
         else if (q->sB[i] > 0) { q->ub[i] = q->x[i]; if (q->lb[i] > q->x[i]) q->lb[i] = q->x[i]; if (q->y[i] > 0) q->y[i] = 0.0; }
@@ -446,6 +450,7 @@ static void ramping(orc_qp* q) {
     int nV = q->nV, nC = q->nC;
     int nRamp = nV + nC + nC + nV;
     double r0 = 0.5, r1 = 1.0;
+    mulA(q, q->x, q->Ax);
     for (int i = 0; i < nV; i++) {
         double tP = (double)((i + q->ramp_offset) % nRamp) / (double)(nRamp - 1);
         double rP = (1.0 - tP) * r0 + tP * r1;
@@ -495,7 +500,7 @@ static int ensure_li(orc_qp* q, int c, int v, int status) {
         q->xiB[i] = ai - q->t2[i];
     }
     double sgn = (status < 0) ? 1.0 : -1.0; /* lower: mu >= 0 ; upper: mu <= 0 */
-    double ymin = QP_MAX_DUAL_JUMP; int kind = -1, idx = -1;
+    double ymin = QP_INFTY; int kind = -1, idx = -1; /* no maxDualJump cap: multipliers scale with rho */
     for (int i = 0; i < nAC; i++) {
         int ci = q->AC[i]; double xi = sgn * q->xiC[i], yy = q->y[nV + ci];
         if (q->sC[ci] < 0) { if (xi > QP_ZERO && yy >= 0.0 && yy / xi < ymin) { ymin = yy / xi; kind = 0; idx = ci; } }
@@ -534,7 +539,9 @@ static int homotopy(orc_qp* q, const orc_qp_options* opt) {
 
         /* ratio tests (qpOASES performStep / performRatioTest / isBlocking) */
         double tau = 1.0; int bc_idx = -1, bc_isbound = 0, bc_status = 0;
-#define BLOCKING(num, den) ((den) >= QP_EPS_DEN && (num) >= QP_EPS_NUM && (num) < tau * (den))
+/* isBlocking: den >= epsDen, num >= epsNum, num < den (the full step is not reachable); the
+         * ratio then has to beat the running minimum strictly, so the first index scanned wins ties */
+#define BLOCKING(num, den) ((den) >= QP_EPS_DEN && (num) >= QP_EPS_NUM && (num) < (den) && (num) / (den) < tau)
         for (int i = 0; i < q->nAC; i++) { /* duals of active constraints */
             int ci = q->AC[i]; double num, den;
             if (q->sC[ci] < 0) { num = q->y[nV + ci]; den = -q->dy[nV + ci]; } else { num = -q->y[nV + ci]; den = q->dy[nV + ci]; }
@@ -568,6 +575,18 @@ static int homotopy(orc_qp* q, const orc_qp_options* opt) {
 #undef BLOCKING
         if (q->verbose) printf("  it %d: tau=%.6e  bc=%s%d -> %d  nFR=%d nAC=%d\n", it, tau,
                                bc_idx < 0 ? "none" : (bc_isbound ? "b" : "c"), bc_idx, bc_status, q->nFR, q->nAC);
+        if (q->verbose > 2) {
+            printf("    FR:"); for (int p = 0; p < q->nFR; p++) printf(" %d", q->FR[p]);
+            printf("  AC:"); for (int p = 0; p < q->nAC; p++) printf(" %d", q->AC[p]);
+            printf("\n    x :"); for (int i = 0; i < nV; i++) printf(" %.17g", q->x[i]);
+            printf("\n    dx:"); for (int i = 0; i < nV; i++) printf(" %.17g", q->dx[i]);
+            printf("\n    Ax:"); for (int i = 0; i < nC; i++) printf(" %.17g", q->Ax[i]);
+            printf("\n    dAx:"); for (int i = 0; i < nC; i++) printf(" %.17g", q->dAx[i]);
+            printf("\n    ubA:"); for (int i = 0; i < nC; i++) printf(" %.17g", q->ubA[i]);
+            printf("\n    T:"); for (int i = 0; i < q->nAC; i++) for (int j = 0; j < q->nFR; j++) printf(" %.17g", q->T[(size_t)i*nV+j]);
+            printf("\n    Q:"); for (int i = 0; i < q->nFR; i++) for (int j = 0; j < q->nFR; j++) printf(" %.17g", q->Q[(size_t)i*nV+j]);
+            printf("\n");
+        }
         /* step */
         if (bc_idx < 0) {
             for (int i = 0; i < nV; i++) { q->x[i] += q->dx[i]; q->g[i] = q->gN[i]; q->lb[i] = q->lbN[i]; q->ub[i] = q->ubN[i]; }

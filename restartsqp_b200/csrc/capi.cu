@@ -1,0 +1,753 @@
+// capi.cu -- the C ABI of libsqpb200.so (include/sqpb200.h): handle management, host<->device
+// plumbing and kernel launches.  No CPU compute path exists in this library: every numerical
+// entry point launches the sm_100a kernels of qp_kernel.cuh / l0_kernels.cuh.
+#include "../../include/sqpb200.h"
+#include "l0_kernels.cuh"
+#include "qp_kernel.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace sqpb200;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            h->err = buf_;                                                                         \
+            return SQPB200_ERR_CUDA;                                                               \
+        }                                                                                          \
+    } while (0)
+
+enum { MS_UNDEFINED = -1, MS_FIXED = 0, MS_VARIED = 1 };
+
+struct sqpb200_handle_s {
+    int batch = 0, nV = 0, nC = 0, qptype = SQPB200_QP, device = 0;
+    sqpb200_options opt;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // structure
+    bool A_set = false, H_set = false;
+    int zA = 0, zJ = 0, zH = 0, zHt = 0;  // zH: CSC entries of H; zHt: triplet count
+    std::vector<int> Ap, Ai, Aorder, Asrc, Hp, Hi, Horder, Hsrc;
+    std::vector<double> A_init;
+    int *dAp = nullptr, *dAi = nullptr, *dArp = nullptr, *dAci = nullptr, *dAperm = nullptr, *dAsrc = nullptr;
+    int *dHp = nullptr, *dHi = nullptr, *dHsrc = nullptr;
+    // data
+    double *dAval = nullptr, *dHval = nullptr;
+    double *dg = nullptr, *dlb = nullptr, *dub = nullptr, *dlbA = nullptr, *dubA = nullptr;
+    // results
+    double *dx = nullptr, *dy = nullptr, *dobj = nullptr, *dkkt = nullptr;
+    int *dstatus = nullptr, *diters = nullptr, *dWB = nullptr, *dWC = nullptr;
+    signed char *dwsB = nullptr, *dwsC = nullptr;
+    unsigned char* dmask = nullptr;
+    // hot-start state
+    double* dstate = nullptr;
+    int* dstate_hdr = nullptr;
+    int slice_doubles = 0, ld = 0;
+    // change flags (src/qpOASESInterface.cpp:361-496, 817-833)
+    bool first_solved = false, upd_A = false, upd_H = false, upd_g = false, upd_bounds = false;
+    int old_ms = MS_UNDEFINED, new_ms = MS_UNDEFINED;
+    // staging + stats
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    long long launches = 0;
+    float last_ms = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int team = 0, teams_per_cta = 0, smem_cta = 0;
+};
+
+static int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    long long cap = 148LL * 16;  // 148 SMs x resident CTAs; grid-stride loops cover the rest
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+template <typename T>
+static int dev_alloc(sqpb200_handle h, T** p, size_t n) {
+    if (n == 0) n = 1;
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    CK(cudaMemsetAsync(*p, 0, n * sizeof(T), h->stream));
+    return 0;
+}
+
+static int ensure_stage(sqpb200_handle h, size_t bytes) {
+    if (bytes <= h->stage_bytes) return 0;
+    if (h->stage) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->stage)); h->stage = nullptr; h->stage_bytes = 0; }
+    CK(cudaMalloc(&h->stage, bytes));
+    h->stage_bytes = bytes;
+    return 0;
+}
+
+// returns a device pointer for `src` (copying through the staging buffer when it is host memory)
+static int to_device(sqpb200_handle h, const void* src, size_t bytes, int loc, size_t stage_off, const void** out) {
+    if (loc == SQPB200_LOC_DEVICE) { *out = src; return 0; }
+    CK(cudaMemcpyAsync((char*)h->stage + stage_off, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    *out = (char*)h->stage + stage_off;
+    return 0;
+}
+
+__global__ void widen_ws_kernel(long long total, const signed char* __restrict__ in, int* __restrict__ out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < total; t += stride) out[t] = (int)in[t];
+}
+
+// All sqpb200_* functions below were declared extern "C" by include/sqpb200.h and keep that linkage.
+
+void sqpb200_default_options(sqpb200_options* o) {
+    o->qp_maxiter = 1000;
+    o->lp_maxiter = 100;
+    o->enable_flipping = 1;
+    o->enable_ramping = 1;
+    o->enable_drift = 1;
+    o->team_size = 0;
+    o->keep_state = 1;
+}
+
+const char* sqpb200_version(void) { return "sqpb200 0.1 (sm_100a)"; }
+
+int sqpb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return SQPB200_ERR_CUDA;
+    return n;
+}
+
+const char* sqpb200_last_error(sqpb200_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int sqpb200_create(int batch, int nV, int nC, int qptype, int device, const sqpb200_options* opts,
+                   sqpb200_handle* out) {
+    if (!out || batch <= 0 || nV <= 0 || nC < 0 || (qptype != SQPB200_QP && qptype != SQPB200_LP)) return SQPB200_ERR_INVALID;
+    if (nV >= (1 << 15) || nC >= (1 << 15)) return SQPB200_ERR_TOO_LARGE;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SQPB200_ERR_CUDA;  // no CPU fallback
+    if (device < 0 || device >= ndev) return SQPB200_ERR_INVALID;
+    sqpb200_handle h = new sqpb200_handle_s();
+    h->batch = batch; h->nV = nV; h->nC = nC; h->qptype = qptype; h->device = device;
+    if (opts) h->opt = *opts; else sqpb200_default_options(&h->opt);
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return SQPB200_ERR_CUDA; }
+    h->ld = (nV % 2 == 0) ? nV + 1 : nV;  // odd leading dimension: conflict-free row and column walks
+    size_t B = (size_t)batch;
+    int rc = 0;
+    rc |= dev_alloc(h, &h->dg, B * nV); rc |= dev_alloc(h, &h->dlb, B * nV); rc |= dev_alloc(h, &h->dub, B * nV);
+    rc |= dev_alloc(h, &h->dlbA, B * nC); rc |= dev_alloc(h, &h->dubA, B * nC);
+    rc |= dev_alloc(h, &h->dx, B * nV); rc |= dev_alloc(h, &h->dy, B * (nV + nC));
+    rc |= dev_alloc(h, &h->dobj, B); rc |= dev_alloc(h, &h->dkkt, B * 5);
+    rc |= dev_alloc(h, &h->dstatus, B); rc |= dev_alloc(h, &h->diters, B);
+    rc |= dev_alloc(h, &h->dWB, B * nV); rc |= dev_alloc(h, &h->dWC, B * nC);
+    rc |= dev_alloc(h, &h->dwsB, B * nV); rc |= dev_alloc(h, &h->dwsC, B * nC);
+    rc |= dev_alloc(h, &h->dmask, B);
+    if (rc) { *out = h; return SQPB200_ERR_CUDA; }
+    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+    // status = NOTINITIALISED until the first solve
+    std::vector<int> st(batch, SQPB200_QPERROR_NOTINITIALISED);
+    cudaMemcpy(h->dstatus, st.data(), B * sizeof(int), cudaMemcpyHostToDevice);
+    *out = h;
+    return 0;
+}
+
+int sqpb200_destroy(sqpb200_handle h) {
+    if (!h) return SQPB200_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {h->dAp, h->dAi, h->dArp, h->dAci, h->dAperm, h->dAsrc, h->dHp, h->dHi, h->dHsrc, h->dAval, h->dHval,
+                    h->dg, h->dlb, h->dub, h->dlbA, h->dubA, h->dx, h->dy, h->dobj, h->dkkt, h->dstatus, h->diters,
+                    h->dWB, h->dWC, h->dwsB, h->dwsC, h->dmask, h->dstate, h->dstate_hdr, h->stage};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return 0;
+}
+
+int sqpb200_set_stream(sqpb200_handle h, void* s) {
+    if (!h) return SQPB200_ERR_INVALID;
+    h->stream = (cudaStream_t)s;
+    return 0;
+}
+
+int sqpb200_synchronize(sqpb200_handle h) {
+    if (!h) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ assembly
+// Runs csc_assemble_kernel over nmat segments whose triplets are already on the host.
+static int run_assembly(sqpb200_handle h, cudaStream_t stream, int nmat, const int* seg, const int* ncol,
+                        const int* row1, const int* col1, int* colptr, int* rowidx, int* order, float* ms,
+                        std::string* err) {
+    (void)h;
+    int ztot = seg[nmat];
+    std::vector<int> cp_off(nmat + 1, 0), pad_off(nmat + 1, 0);
+    for (int m = 0; m < nmat; m++) {
+        int z = seg[m + 1] - seg[m];
+        int P = 1;
+        while (P < z) P <<= 1;
+        if (z >= (1 << 21) || ncol[m] >= (1 << 21)) { *err = "matrix too large for packed keys"; return SQPB200_ERR_TOO_LARGE; }
+        pad_off[m + 1] = pad_off[m] + P;
+        cp_off[m + 1] = cp_off[m] + ncol[m] + 1;
+    }
+    int *dseg, *dncol, *dcpoff, *drow, *dcol, *dpad, *dcolptr, *drowidx, *dorder;
+    uint64_t* dscr;
+    auto A = [&](void** p, size_t b) { return cudaMalloc(p, b ? b : 4); };
+    cudaError_t e = cudaSuccess;
+    e = A((void**)&dseg, (nmat + 1) * 4); if (e) goto fail0;
+    A((void**)&dncol, nmat * 4); A((void**)&dcpoff, (nmat + 1) * 4); A((void**)&dpad, (nmat + 1) * 4);
+    A((void**)&drow, (size_t)ztot * 4); A((void**)&dcol, (size_t)ztot * 4);
+    A((void**)&dcolptr, (size_t)cp_off[nmat] * 4); A((void**)&drowidx, (size_t)ztot * 4); A((void**)&dorder, (size_t)ztot * 4);
+    e = A((void**)&dscr, (size_t)pad_off[nmat] * 8); if (e) goto fail0;
+    cudaMemcpyAsync(dseg, seg, (nmat + 1) * 4, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(dncol, ncol, nmat * 4, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(dcpoff, cp_off.data(), (nmat + 1) * 4, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(dpad, pad_off.data(), (nmat + 1) * 4, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(drow, row1, (size_t)ztot * 4, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(dcol, col1, (size_t)ztot * 4, cudaMemcpyHostToDevice, stream);
+    {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, stream);
+        csc_assemble_kernel<<<nmat, 256, 0, stream>>>(nmat, dseg, dncol, dcpoff, drow, dcol, dpad, dscr, dcolptr, drowidx, dorder);
+        cudaEventRecord(e1, stream);
+        cudaMemcpyAsync(colptr, dcolptr, (size_t)cp_off[nmat] * 4, cudaMemcpyDeviceToHost, stream);
+        cudaMemcpyAsync(rowidx, drowidx, (size_t)ztot * 4, cudaMemcpyDeviceToHost, stream);
+        cudaMemcpyAsync(order, dorder, (size_t)ztot * 4, cudaMemcpyDeviceToHost, stream);
+        e = cudaStreamSynchronize(stream);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        if (ms) *ms = t;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    cudaFree(dseg); cudaFree(dncol); cudaFree(dcpoff); cudaFree(dpad); cudaFree(drow); cudaFree(dcol);
+    cudaFree(dcolptr); cudaFree(drowidx); cudaFree(dorder); cudaFree(dscr);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return SQPB200_ERR_CUDA; }
+    return 0;
+fail0:
+    *err = cudaGetErrorString(e);
+    return SQPB200_ERR_CUDA;
+}
+
+int sqpb200_assemble_csc_batched(int device, int nmat, const int* seg, const int* ncol, const int* row1,
+                                 const int* col1, int* colptr, int* rowidx, int* order, float* kernel_ms) {
+    if (nmat <= 0 || !seg || !ncol) return SQPB200_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return SQPB200_ERR_CUDA;
+    std::string err;
+    return run_assembly(nullptr, nullptr, nmat, seg, ncol, row1, col1, colptr, rowidx, order, kernel_ms, &err);
+}
+
+template <typename T>
+static int upload_vec(sqpb200_handle h, T** d, const std::vector<T>& v) {
+    if (*d) { CK(cudaFree(*d)); *d = nullptr; }
+    CK(cudaMalloc((void**)d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) CK(cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int finish_structure_A(sqpb200_handle h) {
+    const int nV = h->nV, nC = h->nC, zA = h->zA;
+    // CSR view of the CSC pattern: entries of each row in column order (the CSC storage order)
+    std::vector<int> Arp(nC + 1, 0), Aci(zA), Aperm(zA);
+    for (int e = 0; e < zA; e++) Arp[h->Ai[e] + 1]++;
+    for (int r = 0; r < nC; r++) Arp[r + 1] += Arp[r];
+    std::vector<int> fill(Arp.begin(), Arp.end() - 1);
+    for (int c = 0; c < nV; c++)
+        for (int e = h->Ap[c]; e < h->Ap[c + 1]; e++) { int r = h->Ai[e]; Aci[fill[r]] = c; Aperm[fill[r]] = e; fill[r]++; }
+    int rc = 0;
+    rc |= upload_vec(h, &h->dAp, h->Ap); rc |= upload_vec(h, &h->dAi, h->Ai);
+    rc |= upload_vec(h, &h->dArp, Arp); rc |= upload_vec(h, &h->dAci, Aci); rc |= upload_vec(h, &h->dAperm, Aperm);
+    rc |= upload_vec(h, &h->dAsrc, h->Asrc);
+    if (rc) return SQPB200_ERR_CUDA;
+    if (h->dAval) { CK(cudaFree(h->dAval)); h->dAval = nullptr; }
+    if (dev_alloc(h, &h->dAval, (size_t)h->batch * zA)) return SQPB200_ERR_CUDA;
+    if (!h->A_init.empty() && zA > 0) {  // identity entries (and zeros) in every instance
+        if (ensure_stage(h, (size_t)zA * 8)) return SQPB200_ERR_CUDA;
+        CK(cudaMemcpyAsync(h->stage, h->A_init.data(), (size_t)zA * 8, cudaMemcpyHostToDevice, h->stream));
+        long long total = (long long)h->batch * zA;
+        broadcast_rows_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(total, zA, 0, zA, (const double*)h->stage, h->dAval);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    h->A_set = true;
+    return 0;
+}
+
+int sqpb200_set_structure_A(sqpb200_handle h, int zJ, const int* row1, const int* col1, int I_len,
+                            const int* I_irow, const int* I_jcol, const int* I_size, const double* I_value) {
+    if (!h || zJ < 0) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    // entry list of SpHbMat::setStructure(rhs, I_info), src/SpHbMat.cpp:203-227
+    std::vector<int> er, ec;
+    std::vector<double> ev;
+    for (int i = 0; i < zJ; i++) { er.push_back(row1[i]); ec.push_back(col1[i]); ev.push_back(0.0); }
+    for (int b = 0; b < I_len; b++)
+        for (int j = 0; j < I_size[b]; j++) { er.push_back(I_irow[b] + j); ec.push_back(I_jcol[b] + j); ev.push_back(I_value[b]); }
+    int z = (int)er.size();
+    for (int i = 0; i < z; i++)
+        if (er[i] < 1 || er[i] > h->nC || ec[i] < 1 || ec[i] > h->nV) { h->err = "triplet index out of range"; return SQPB200_ERR_INVALID; }
+    h->zA = z; h->zJ = zJ;
+    h->Ap.assign(h->nV + 1, 0); h->Ai.assign(z, 0); h->Aorder.assign(z, 0);
+    int seg[2] = {0, z}, ncol[1] = {h->nV};
+    if (z > 0) {
+        int rc = run_assembly(h, h->stream, 1, seg, ncol, er.data(), ec.data(), h->Ap.data(), h->Ai.data(), h->Aorder.data(), nullptr, &h->err);
+        h->launches++;
+        if (rc) return rc;
+    }
+    h->Asrc.assign(z, -1);
+    h->A_init.assign(z, 0.0);
+    for (int i = 0; i < z; i++) {
+        if (i < zJ) h->Asrc[h->Aorder[i]] = i;
+        else h->A_init[h->Aorder[i]] = ev[i];
+    }
+    int rc = finish_structure_A(h);
+    return rc ? rc : z;
+}
+
+int sqpb200_set_structure_H(sqpb200_handle h, int zH, const int* row1, const int* col1, int is_symmetric) {
+    if (!h || zH < 0) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    // entry list of SpHbMat::setStructure(rhs), src/SpHbMat.cpp:296-309
+    std::vector<int> er, ec, srct;
+    for (int i = 0; i < zH; i++) {
+        er.push_back(row1[i]); ec.push_back(col1[i]); srct.push_back(i);
+        if (is_symmetric && row1[i] != col1[i]) { er.push_back(col1[i]); ec.push_back(row1[i]); srct.push_back(i); }
+    }
+    int z = (int)er.size();
+    for (int i = 0; i < z; i++)
+        if (er[i] < 1 || er[i] > h->nV || ec[i] < 1 || ec[i] > h->nV) { h->err = "triplet index out of range"; return SQPB200_ERR_INVALID; }
+    h->zH = z; h->zHt = zH;
+    h->Hp.assign(h->nV + 1, 0); h->Hi.assign(z, 0); h->Horder.assign(z, 0);
+    int seg[2] = {0, z}, ncol[1] = {h->nV};
+    if (z > 0) {
+        int rc = run_assembly(h, h->stream, 1, seg, ncol, er.data(), ec.data(), h->Hp.data(), h->Hi.data(), h->Horder.data(), nullptr, &h->err);
+        h->launches++;
+        if (rc) return rc;
+    }
+    h->Hsrc.assign(z, -1);
+    for (int i = 0; i < z; i++) h->Hsrc[h->Horder[i]] = srct[i];
+    int rc = 0;
+    rc |= upload_vec(h, &h->dHp, h->Hp); rc |= upload_vec(h, &h->dHi, h->Hi); rc |= upload_vec(h, &h->dHsrc, h->Hsrc);
+    if (rc) return SQPB200_ERR_CUDA;
+    if (h->dHval) { CK(cudaFree(h->dHval)); h->dHval = nullptr; }
+    if (dev_alloc(h, &h->dHval, (size_t)h->batch * z)) return SQPB200_ERR_CUDA;
+    h->H_set = true;
+    return z;
+}
+
+int sqpb200_set_structure_csc(sqpb200_handle h, int which, int nnz, const int* colptr, const int* rowidx) {
+    if (!h || nnz < 0 || !colptr) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (colptr[h->nV] != nnz) { h->err = "colptr[ncol] != nnz"; return SQPB200_ERR_INVALID; }
+    if (which == SQPB200_MAT_A) {
+        h->zA = nnz; h->zJ = nnz;
+        h->Ap.assign(colptr, colptr + h->nV + 1); h->Ai.assign(rowidx, rowidx + nnz);
+        h->Aorder.resize(nnz); h->Asrc.resize(nnz);
+        for (int i = 0; i < nnz; i++) { h->Aorder[i] = i; h->Asrc[i] = i; }
+        h->A_init.clear();
+        int rc = finish_structure_A(h);
+        return rc ? rc : nnz;
+    } else if (which == SQPB200_MAT_H) {
+        h->zH = nnz; h->zHt = nnz;
+        h->Hp.assign(colptr, colptr + h->nV + 1); h->Hi.assign(rowidx, rowidx + nnz);
+        h->Horder.resize(nnz); h->Hsrc.resize(nnz);
+        for (int i = 0; i < nnz; i++) { h->Horder[i] = i; h->Hsrc[i] = i; }
+        int rc = 0;
+        rc |= upload_vec(h, &h->dHp, h->Hp); rc |= upload_vec(h, &h->dHi, h->Hi); rc |= upload_vec(h, &h->dHsrc, h->Hsrc);
+        if (rc) return SQPB200_ERR_CUDA;
+        if (h->dHval) { CK(cudaFree(h->dHval)); h->dHval = nullptr; }
+        if (dev_alloc(h, &h->dHval, (size_t)h->batch * nnz)) return SQPB200_ERR_CUDA;
+        h->H_set = true;
+        return nnz;
+    }
+    return SQPB200_ERR_INVALID;
+}
+
+int sqpb200_get_structure(sqpb200_handle h, int which, int* colptr, int* rowidx, int* order) {
+    if (!h) return SQPB200_ERR_INVALID;
+    const std::vector<int>& P = which == SQPB200_MAT_A ? h->Ap : h->Hp;
+    const std::vector<int>& I = which == SQPB200_MAT_A ? h->Ai : h->Hi;
+    const std::vector<int>& O = which == SQPB200_MAT_A ? h->Aorder : h->Horder;
+    if (P.empty()) return SQPB200_ERR_STATE;
+    if (colptr) std::copy(P.begin(), P.end(), colptr);
+    if (rowidx) std::copy(I.begin(), I.end(), rowidx);
+    if (order) std::copy(O.begin(), O.end(), order);
+    return 0;
+}
+
+int sqpb200_get_nnz(sqpb200_handle h, int which) {
+    if (!h) return SQPB200_ERR_INVALID;
+    return which == SQPB200_MAT_A ? h->zA : h->zH;
+}
+
+// ------------------------------------------------------------------------------ values
+static int set_values(sqpb200_handle h, int which, const double* vals, int loc, int broadcast, bool csc_order) {
+    if (!h || !vals) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    bool isA = which == SQPB200_MAT_A;
+    if (isA ? !h->A_set : !h->H_set) { h->err = "structure not set"; return SQPB200_ERR_STATE; }
+    int z_out = isA ? h->zA : h->zH;
+    int z_in = csc_order ? z_out : (isA ? h->zJ : h->zHt);
+    if (z_out == 0 || z_in == 0) return 0;
+    size_t bytes = (size_t)(broadcast ? 1 : h->batch) * z_in * 8;
+    if (loc == SQPB200_LOC_HOST && ensure_stage(h, bytes)) return SQPB200_ERR_CUDA;
+    const void* din;
+    if (to_device(h, vals, bytes, loc, 0, &din)) return SQPB200_ERR_CUDA;
+    double* dout = isA ? h->dAval : h->dHval;
+    long long total = (long long)h->batch * z_out;
+    if (csc_order && !broadcast) {
+        CK(cudaMemcpyAsync(dout, din, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    } else if (csc_order) {
+        broadcast_rows_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(total, z_out, 0, z_out, (const double*)din, dout);
+        h->launches++;
+    } else {
+        scatter_values_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(total, z_in, z_out, isA ? h->dAsrc : h->dHsrc,
+                                                                           (const double*)din, broadcast, dout);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    // change flags: src/qpOASESInterface.cpp:407-409, 427-429
+    if (h->first_solved) { if (isA) h->upd_A = true; else h->upd_H = true; }
+    return 0;
+}
+
+int sqpb200_set_values_A(sqpb200_handle h, const double* vals, int loc, int broadcast) { return set_values(h, SQPB200_MAT_A, vals, loc, broadcast, false); }
+int sqpb200_set_values_H(sqpb200_handle h, const double* vals, int loc, int broadcast) { return set_values(h, SQPB200_MAT_H, vals, loc, broadcast, false); }
+int sqpb200_set_values_csc(sqpb200_handle h, int which, const double* vals, int loc, int broadcast) { return set_values(h, which, vals, loc, broadcast, true); }
+
+int sqpb200_get_values_csc(sqpb200_handle h, int which, double* vals, int loc) {
+    if (!h || !vals) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    bool isA = which == SQPB200_MAT_A;
+    size_t bytes = (size_t)h->batch * (isA ? h->zA : h->zH) * 8;
+    CK(cudaMemcpyAsync(vals, isA ? h->dAval : h->dHval, bytes, loc == SQPB200_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ vectors
+static double* vec_ptr(sqpb200_handle h, int which, int* len) {
+    switch (which) {
+    case SQPB200_VEC_G: *len = h->nV; return h->dg;
+    case SQPB200_VEC_LB: *len = h->nV; return h->dlb;
+    case SQPB200_VEC_UB: *len = h->nV; return h->dub;
+    case SQPB200_VEC_LBA: *len = h->nC; return h->dlbA;
+    case SQPB200_VEC_UBA: *len = h->nC; return h->dubA;
+    }
+    *len = 0;
+    return nullptr;
+}
+
+int sqpb200_set_vectors(sqpb200_handle h, int which, const double* vals, int offset, int count, int loc, int broadcast) {
+    if (!h || !vals) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int len;
+    double* d = vec_ptr(h, which, &len);
+    if (!d && len == 0 && count == 0) return 0;
+    if (!d || offset < 0 || count < 0 || offset + count > len) return SQPB200_ERR_INVALID;
+    if (count == 0) return 0;
+    if (!broadcast) {
+        CK(cudaMemcpy2DAsync(d + offset, (size_t)len * 8, vals, (size_t)count * 8, (size_t)count * 8, h->batch,
+                             loc == SQPB200_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+        if (loc == SQPB200_LOC_HOST && ensure_stage(h, (size_t)count * 8)) return SQPB200_ERR_CUDA;
+        const void* din;
+        if (to_device(h, vals, (size_t)count * 8, loc, 0, &din)) return SQPB200_ERR_CUDA;
+        long long total = (long long)h->batch * count;
+        broadcast_rows_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(total, len, offset, count, (const double*)din, d);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    // change flags: src/qpOASESInterface.cpp:361-395
+    if (h->first_solved) { if (which == SQPB200_VEC_G) h->upd_g = true; else h->upd_bounds = true; }
+    return 0;
+}
+
+int sqpb200_get_vectors(sqpb200_handle h, int which, double* vals, int loc) {
+    if (!h || !vals) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int len;
+    double* d = vec_ptr(h, which, &len);
+    if (!d) return SQPB200_ERR_INVALID;
+    CK(cudaMemcpyAsync(vals, d, (size_t)h->batch * len * 8, loc == SQPB200_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sqpb200_qphandler_bounds(sqpb200_handle h, int mode, int n, int m, const double* delta, const double* x_l,
+                             const double* x_u, const double* x_k, const double* c_l, const double* c_u,
+                             const double* c_k, int loc) {
+    if (!h || n + 2 * m != h->nV || m != h->nC || mode < 0 || mode > 2) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    size_t B = h->batch, bn = B * n * 8, bm = B * m * 8;
+    const void *dd, *dxl, *dxu, *dxk, *dcl = nullptr, *dcu = nullptr, *dck = nullptr;
+    if (loc == SQPB200_LOC_HOST && ensure_stage(h, B * 8 + 3 * bn + 3 * bm)) return SQPB200_ERR_CUDA;
+    size_t off = 0;
+    if (to_device(h, delta, B * 8, loc, off, &dd)) return SQPB200_ERR_CUDA; off += B * 8;
+    if (to_device(h, x_l, bn, loc, off, &dxl)) return SQPB200_ERR_CUDA; off += bn;
+    if (to_device(h, x_u, bn, loc, off, &dxu)) return SQPB200_ERR_CUDA; off += bn;
+    if (to_device(h, x_k, bn, loc, off, &dxk)) return SQPB200_ERR_CUDA; off += bn;
+    if (mode != 2 && m > 0) {
+        if (to_device(h, c_l, bm, loc, off, &dcl)) return SQPB200_ERR_CUDA; off += bm;
+        if (to_device(h, c_u, bm, loc, off, &dcu)) return SQPB200_ERR_CUDA; off += bm;
+        if (to_device(h, c_k, bm, loc, off, &dck)) return SQPB200_ERR_CUDA; off += bm;
+    }
+    long long total = (long long)B * h->nV;
+    qphandler_bounds_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(h->batch, (mode != 2 && m > 0) ? mode : 2, n, m, 1.0e18,
+        (const double*)dd, (const double*)dxl, (const double*)dxu, (const double*)dxk, (const double*)dcl,
+        (const double*)dcu, (const double*)dck, h->dlb, h->dub, h->dlbA, h->dubA);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (mode == 0 && m == 0) { /* nothing else */ }
+    if (h->first_solved) h->upd_bounds = true;
+    return 0;
+}
+
+int sqpb200_qphandler_g(sqpb200_handle h, int n, int m, const double* grad, const double* rho, int loc) {
+    if (!h || n + 2 * m != h->nV) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    size_t B = h->batch;
+    const void *dgr = nullptr, *drho = nullptr;
+    if (loc == SQPB200_LOC_HOST && ensure_stage(h, B * n * 8 + B * 8)) return SQPB200_ERR_CUDA;
+    if (grad && to_device(h, grad, B * n * 8, loc, 0, &dgr)) return SQPB200_ERR_CUDA;
+    if (rho && to_device(h, rho, B * 8, loc, B * n * 8, &drho)) return SQPB200_ERR_CUDA;
+    long long total = (long long)B * h->nV;
+    qphandler_g_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(h->batch, n, m, (const double*)dgr, (const double*)drho, h->dg);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (h->first_solved) h->upd_g = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ solve
+static int choose_config(sqpb200_handle h) {
+    int zH = (h->qptype == SQPB200_QP) ? h->zH : 0;  // an LP handle never holds H (src/qpOASESInterface.cpp:122-124)
+    h->slice_doubles = qp_slice_doubles(h->nV, h->nC, h->ld, h->zA, zH);
+    size_t slice_bytes = (size_t)h->slice_doubles * 8;
+    const size_t SMEM_MAX = 227 * 1024;
+    int team = h->opt.team_size;
+    if (team == 0) {
+        size_t per_sm = SMEM_MAX / (slice_bytes + 64);
+        if (per_sm >= 16) team = 32;
+        else if (per_sm >= 8) team = 64;
+        else if (per_sm >= 3) team = 128;
+        else team = 256;
+    }
+    if (team != 32 && team != 64 && team != 128 && team != 256) { h->err = "team_size must be 32, 64, 128 or 256"; return SQPB200_ERR_INVALID; }
+    int cta = team <= 128 ? 128 : 256;
+    int teams = cta / team;
+    size_t smem = (size_t)teams * slice_bytes + (size_t)teams * 2 * (team / 32 + 1) * 8;
+    while (smem > SMEM_MAX && teams > 1) {  // fewer QPs per CTA
+        team *= 2; teams = cta / team;
+        smem = (size_t)teams * slice_bytes + (size_t)teams * 2 * (team / 32 + 1) * 8;
+    }
+    if (smem > SMEM_MAX) {
+        h->err = "QP too large for the shared-memory resident kernel (nV=" + std::to_string(h->nV) + ")";
+        return SQPB200_ERR_TOO_LARGE;
+    }
+    h->team = team; h->teams_per_cta = teams; h->smem_cta = (int)smem;
+    return 0;
+}
+
+template <int TEAM, int CTA>
+static cudaError_t launch_solve(sqpb200_handle h, const QPKernelArgs& a) {
+    cudaError_t e = cudaFuncSetAttribute(qp_solve_kernel<TEAM, CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_cta);
+    if (e != cudaSuccess) return e;
+    int teams = CTA / TEAM;
+    int grid = (h->batch + teams - 1) / teams;
+    qp_solve_kernel<TEAM, CTA><<<grid, CTA, h->smem_cta, h->stream>>>(a);
+    return cudaGetLastError();
+}
+
+int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask) {
+    if (!h) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->A_set) { h->err = "set_structure_A has not been called"; return SQPB200_ERR_STATE; }
+    bool is_lp = (mode_qp == SQPB200_LP);
+    if (mode_qp != h->qptype) { h->err = "solve mode differs from the handle's QPType (the reference keeps one backend per type)"; return SQPB200_ERR_INVALID; }
+    if (!is_lp && !h->H_set) { h->err = "set_structure_H has not been called"; return SQPB200_ERR_STATE; }
+    int rc = choose_config(h);
+    if (rc) return rc;
+    if (h->opt.keep_state && !h->dstate) {
+        if (dev_alloc(h, &h->dstate, (size_t)h->batch * h->slice_doubles)) return SQPB200_ERR_CUDA;
+        if (dev_alloc(h, &h->dstate_hdr, (size_t)h->batch * 4)) return SQPB200_ERR_CUDA;
+    }
+    // init / hotstart decision: src/qpOASESInterface.cpp:141-211 with get_Matrix_change_status :817-833
+    int mode = MODE_COLD;
+    if (h->first_solved && h->opt.keep_state) {
+        bool varied = h->upd_A || h->upd_H;
+        if (h->old_ms == MS_UNDEFINED) h->old_ms = varied ? MS_VARIED : MS_FIXED;
+        else { if (h->new_ms != MS_UNDEFINED) h->old_ms = h->new_ms; h->new_ms = varied ? MS_VARIED : MS_FIXED; }
+        if (h->new_ms == MS_UNDEFINED) mode = (h->old_ms == MS_FIXED) ? MODE_HOT_FIXED : MODE_HOT_VARIED;
+        else if (h->new_ms == MS_FIXED && h->old_ms == MS_FIXED) mode = MODE_HOT_FIXED;
+        else if (h->new_ms == MS_VARIED && h->old_ms == MS_VARIED) mode = MODE_HOT_VARIED;
+        else {  // status flip: warm re-init with (x, y, working set) :202-207 -> same working set, new factors
+            mode = MODE_HOT_VARIED;
+            h->new_ms = h->old_ms = MS_UNDEFINED;
+        }
+    }
+    QPKernelArgs a;
+    memset(&a, 0, sizeof a);
+    a.batch = h->batch; a.nV = h->nV; a.nC = h->nC; a.ld = h->ld;
+    a.is_lp = is_lp; a.has_H = !is_lp;
+    a.max_iter = maxiter > 0 ? maxiter : (is_lp ? h->opt.lp_maxiter : h->opt.qp_maxiter);
+    a.flags = (h->opt.enable_flipping ? FLAG_FLIPPING : 0) | (h->opt.enable_ramping ? FLAG_RAMPING : 0) |
+              (h->opt.enable_drift ? FLAG_DRIFT : 0) | (h->opt.keep_state ? FLAG_KEEP_STATE : 0);
+    a.mode = mode;
+    a.zA = h->zA; a.zH = is_lp ? 0 : h->zH;
+    a.Ap = h->dAp; a.Ai = h->dAi; a.Arp = h->dArp; a.Aci = h->dAci; a.Aperm = h->dAperm;
+    a.Hp = h->dHp; a.Hi = h->dHi;
+    a.Aval = h->dAval; a.Hval = h->dHval;
+    a.gN = h->dg; a.lbN = h->dlb; a.ubN = h->dub; a.lbAN = h->dlbA; a.ubAN = h->dubA;
+    if (active_mask) {
+        CK(cudaMemcpyAsync(h->dmask, active_mask, h->batch, cudaMemcpyHostToDevice, h->stream));
+        a.mask = h->dmask;
+    }
+    a.x = h->dx; a.y = h->dy; a.obj = h->dobj; a.kkt = h->dkkt; a.status = h->dstatus; a.iters = h->diters;
+    a.wsB = h->dwsB; a.wsC = h->dwsC; a.WB = h->dWB; a.WC = h->dWC;
+    a.state = h->dstate; a.state_hdr = h->dstate_hdr; a.slice_doubles = h->slice_doubles;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    cudaError_t e;
+    switch (h->team) {
+    case 32: e = launch_solve<32, 128>(h, a); break;
+    case 64: e = launch_solve<64, 128>(h, a); break;
+    case 128: e = launch_solve<128, 128>(h, a); break;
+    default: e = launch_solve<256, 256>(h, a); break;
+    }
+    if (e != cudaSuccess) { h->err = std::string("qp_solve_kernel launch: ") + cudaGetErrorString(e); return SQPB200_ERR_CUDA; }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->launches++;
+    // reset_flags(): src/qpOASESInterface.cpp:488-496
+    h->upd_A = h->upd_H = h->upd_g = h->upd_bounds = false;
+    h->first_solved = true;
+    return 0;
+}
+
+float sqpb200_last_solve_ms(sqpb200_handle h) {
+    if (!h || !h->ev1) return -1.f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.f;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->last_ms = ms;
+    return ms;
+}
+
+int sqpb200_solve_config(sqpb200_handle h, int* team_size, int* qps_per_cta, int* smem_per_cta) {
+    if (!h) return SQPB200_ERR_INVALID;
+    if (h->team == 0) { int rc = choose_config(h); if (rc) return rc; }
+    if (team_size) *team_size = h->team;
+    if (qps_per_cta) *qps_per_cta = h->teams_per_cta;
+    if (smem_per_cta) *smem_per_cta = h->smem_cta;
+    return 0;
+}
+
+long long sqpb200_launch_count(sqpb200_handle h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------ results
+static int copy_out(sqpb200_handle h, void* dst, const void* src, size_t bytes, int loc) {
+    if (!dst) return 0;
+    CK(cudaMemcpyAsync(dst, src, bytes, loc == SQPB200_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+int sqpb200_get_solution(sqpb200_handle h, double* x, double* y, double* obj, int* status, int* iters, int loc) {
+    if (!h) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    size_t B = h->batch;
+    if (copy_out(h, x, h->dx, B * h->nV * 8, loc) || copy_out(h, y, h->dy, B * (h->nV + h->nC) * 8, loc) ||
+        copy_out(h, obj, h->dobj, B * 8, loc) || copy_out(h, status, h->dstatus, B * 4, loc) ||
+        copy_out(h, iters, h->diters, B * 4, loc))
+        return SQPB200_ERR_CUDA;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sqpb200_get_working_set(sqpb200_handle h, int* wb, int* wc, int translated, int loc) {
+    if (!h) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    size_t B = h->batch;
+    if (translated) {
+        if (copy_out(h, wb, h->dWB, B * h->nV * 4, loc) || copy_out(h, wc, h->dWC, B * h->nC * 4, loc)) return SQPB200_ERR_CUDA;
+    } else {
+        size_t nb = B * h->nV, nc = B * h->nC;
+        if (ensure_stage(h, (nb + nc) * 4 + 16)) return SQPB200_ERR_CUDA;
+        int* sb = (int*)h->stage;
+        int* sc = sb + nb;
+        widen_ws_kernel<<<grid_for((long long)nb, 256), 256, 0, h->stream>>>((long long)nb, h->dwsB, sb);
+        if (nc) widen_ws_kernel<<<grid_for((long long)nc, 256), 256, 0, h->stream>>>((long long)nc, h->dwsC, sc);
+        h->launches += nc ? 2 : 1;
+        CK(cudaGetLastError());
+        if (copy_out(h, wb, sb, nb * 4, loc) || copy_out(h, wc, sc, nc * 4, loc)) return SQPB200_ERR_CUDA;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sqpb200_kkt_residuals(sqpb200_handle h, double* out, int loc) {
+    if (!h || !out) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (copy_out(h, out, h->dkkt, (size_t)h->batch * 5 * 8, loc)) return SQPB200_ERR_CUDA;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sqpb200_kkt_residuals_recompute(sqpb200_handle h, double* out, int loc) {
+    if (!h || !out) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->A_set) return SQPB200_ERR_STATE;
+    KKTArgs a;
+    memset(&a, 0, sizeof a);
+    a.batch = h->batch; a.nV = h->nV; a.nC = h->nC; a.zA = h->zA; a.zH = h->zH;
+    a.has_H = (h->qptype == SQPB200_QP && h->H_set) ? 1 : 0;
+    a.Ap = h->dAp; a.Ai = h->dAi; a.Arp = h->dArp; a.Aci = h->dAci; a.Aperm = h->dAperm; a.Hp = h->dHp; a.Hi = h->dHi;
+    a.Aval = h->dAval; a.Hval = h->dHval; a.g = h->dg; a.lb = h->dlb; a.ub = h->dub; a.lbA = h->dlbA; a.ubA = h->dubA;
+    a.x = h->dx; a.y = h->dy; a.wsB = h->dwsB; a.wsC = h->dwsC; a.WB = h->dWB; a.WC = h->dWC;
+    if (ensure_stage(h, (size_t)h->batch * 5 * 8)) return SQPB200_ERR_CUDA;
+    a.out = (loc == SQPB200_LOC_DEVICE) ? out : (double*)h->stage;
+    int warps = 4;
+    size_t smem = (size_t)warps * (2 * h->nV + h->nC) * 8;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kkt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kkt_kernel<<<(h->batch + warps - 1) / warps, warps * 32, smem, h->stream>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (loc == SQPB200_LOC_HOST) CK(cudaMemcpyAsync(out, h->stage, (size_t)h->batch * 5 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sqpb200_spmv(sqpb200_handle h, int which, int transpose, const double* x, double* y, int loc) {
+    if (!h || !x || !y) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    bool isA = which == SQPB200_MAT_A;
+    if (isA ? !h->A_set : !h->H_set) return SQPB200_ERR_STATE;
+    int nin, nout, nnz;
+    const int *ptr, *idx, *perm;
+    const double* val;
+    if (isA && !transpose) { nin = h->nV; nout = h->nC; nnz = h->zA; ptr = h->dArp; idx = h->dAci; perm = h->dAperm; val = h->dAval; }
+    else if (isA) { nin = h->nC; nout = h->nV; nnz = h->zA; ptr = h->dAp; idx = h->dAi; perm = nullptr; val = h->dAval; }
+    else { nin = h->nV; nout = h->nV; nnz = h->zH; ptr = h->dHp; idx = h->dHi; perm = nullptr; val = h->dHval; }
+    size_t B = h->batch, bin = B * nin * 8, bout = B * nout * 8;
+    if (nout == 0) return 0;
+    const void* dxv = x;
+    double* dyv = y;
+    if (loc == SQPB200_LOC_HOST) {
+        if (ensure_stage(h, bin + bout + 16)) return SQPB200_ERR_CUDA;
+        if (to_device(h, x, bin, loc, 0, &dxv)) return SQPB200_ERR_CUDA;
+        dyv = (double*)((char*)h->stage + ((bin + 15) / 16) * 16);
+    }
+    long long total = (long long)B * nout;
+    spmv_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(total, nout, nin, nnz, ptr, idx, perm, val, (const double*)dxv, dyv);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (loc == SQPB200_LOC_HOST) CK(cudaMemcpyAsync(y, dyv, bout, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+

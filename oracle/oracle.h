@@ -139,6 +139,12 @@ int orc_qp_hotstart_matrices(orc_qp* q, const orc_qp_options* opt, const double*
                              const double* ub, const double* lbA, const double* ubA);
 void orc_qp_get_solution(const orc_qp* q, double* x, double* y, double* obj, int* iters);
 void orc_qp_get_working_set(const orc_qp* q, int* raw_b, int* raw_c);
+/* oracle_batch.c: OpenMP driver over independent instances (one solver object per thread) */
+int orc_max_threads(void);
+int orc_qp_solve_batch(int B, int nV, int nC, const int* Hp, const int* Hi, const double* Hv, int Hv_stride,
+                       const int* Ap, const int* Ai, const double* Av, int Av_stride, const double* g,
+                       const double* lb, const double* ub, const double* lbA, const double* ubA, int is_lp,
+                       int max_iter, double* x, double* y, double* obj, int* status, int* iters, int nthreads);
 /* flop counter for the roofline model of SURVEY.md section 8(d) */
 double orc_qp_get_flops(const orc_qp* q);
 

@@ -37,7 +37,7 @@ def _f64(a):
 def build(force=False):
     """Compile liboracle.so (and _ref/libref_l0.so when /root/reference exists)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_l0.c", "oracle_qp.c", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_l0.c", "oracle_qp.c", "oracle_batch.c", "oracle.h", "Makefile")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, capture_output=True)
@@ -218,3 +218,25 @@ class OracleQP:
 
     def flops(self):
         return self.L.orc_qp_get_flops(self.h)
+
+
+def solve_batch(nV, nC, A, H, g, lb, ub, lbA, ubA, is_lp=False, max_iter=1000, nthreads=0, Avals=None, Hvals=None):
+    """Cold-start solve of a batch on the host cores (OpenMP, one oracle object per thread).
+    A, H = (colptr,rowidx,val[z]) shared pattern; Avals/Hvals optional [B][z].  Returns dict + threads used."""
+    g = _f64(g)
+    B = g.shape[0]
+    lb, ub, lbA, ubA = _f64(lb), _f64(ub), _f64(lbA), _f64(ubA)
+    Ap, Ai = _i32(A[0]), _i32(A[1])
+    Av = _f64(A[2] if Avals is None else Avals)
+    if H is not None and not is_lp:
+        Hp, Hi = _i32(H[0]), _i32(H[1])
+        Hv = _f64(H[2] if Hvals is None else Hvals)
+    else:
+        Hp = Hi = None
+        Hv = np.zeros(1)
+    x, y = np.empty((B, nV)), np.empty((B, nV + nC))
+    obj, st, it = np.empty(B), np.empty(B, np.int32), np.empty(B, np.int32)
+    used = lib().orc_qp_solve_batch(B, nV, nC, _ip(Hp), _ip(Hi), _dp(Hv), 0 if Hv.ndim == 1 else Hv.shape[1], _ip(Ap), _ip(Ai),
+                                    _dp(Av), 0 if Av.ndim == 1 else Av.shape[1], _dp(g), _dp(lb), _dp(ub), _dp(lbA), _dp(ubA),
+                                    int(is_lp), int(max_iter), _dp(x), _dp(y), _dp(obj), _ip(st), _ip(it), int(nthreads))
+    return dict(x=x, y=y, obj=obj, status=st, iters=it, threads=used)

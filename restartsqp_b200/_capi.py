@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsqpb200.so")
+LIB_PATH = os.environ.get("SQPB200_LIB") or os.path.join(HERE, "lib", "libsqpb200.so")
 
 LOC_HOST, LOC_DEVICE = 0, 1
 LP, QP = 1, 2

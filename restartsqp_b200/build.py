@@ -1,38 +1,78 @@
-"""Build libsqpb200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+"""Build libsqpb200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo).
+
+The active-set kernel is compiled once per team size (qp_solve_inst.cu with -DQP_TEAM/-DQP_CTA), the
+object files in parallel.  -fmad=false: FP64 multiply-adds are not contracted, so the solve kernel's
+arithmetic is operation-for-operation the CPU oracle's and the L0 kernels' sums are the reference's
+(SpHbMat::times evaluates val*x then +=); parity tests can therefore compare bit patterns.
+"""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "lib", "libsqpb200.so")
-SRCS = [os.path.join(HERE, "csrc", f) for f in ("capi.cu",)]
-DEPS = SRCS + [os.path.join(HERE, "csrc", f) for f in ("qp_kernel.cuh", "l0_kernels.cuh")] + [
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libsqpb200.so")
+OBJDIR = os.path.join(HERE, "build")
+HEADERS = [os.path.join(CSRC, f) for f in ("qp_kernel.cuh", "l0_kernels.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "sqpb200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+TEAMS = [(32, 128), (64, 128), (128, 128), (256, 256)]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+              "-Xcompiler", "-fPIC"]
+
+
+def _nvcc():
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return nvcc if os.path.exists(nvcc) else "nvcc"
+
+
+def _units():
+    units = [(os.path.join(CSRC, "capi.cu"), os.path.join(OBJDIR, "capi.o"), [])]
+    for team, cta in TEAMS:
+        # multi-warp teams are compiled fully inlined (see the QP_INLINE_ALL note in qp_kernel.cuh)
+        units.append((os.path.join(CSRC, "qp_solve_inst.cu"), os.path.join(OBJDIR, "qp_solve_%d.o" % team),
+                      ["-DQP_TEAM=%d" % team, "-DQP_CTA=%d" % cta] + (["-DQP_INLINE_ALL"] if team > 32 else [])))
+    return units
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def is_stale():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    return _stale(LIB, [u[0] for u in _units()] + HEADERS + [os.path.abspath(__file__)])
 
 
 def build(force=False, verbose=False):
     """Compile the CUDA extension if it is missing or older than its sources.  Returns the .so path."""
     if not force and not is_stale():
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    if not os.path.exists(nvcc):
-        nvcc = "nvcc"
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SRCS
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(u):
+        src, obj, defs = u
+        if not force and not _stale(obj, [src] + HEADERS + [os.path.abspath(__file__)]):
+            return ""
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + defs + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        return r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(_units())) as ex:
+        logs = list(ex.map(compile_one, _units()))
+    cmd = [nvcc, "-shared", "-o", LIB] + [u[1] for u in _units()]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
-        print(r.stderr)
+        print("\n".join(logs))
     return LIB
 
 

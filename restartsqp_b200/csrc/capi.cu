@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -556,14 +557,12 @@ static int choose_config(sqpb200_handle h) {
     return 0;
 }
 
-template <int TEAM, int CTA>
-static cudaError_t launch_solve(sqpb200_handle h, const QPKernelArgs& a) {
-    cudaError_t e = cudaFuncSetAttribute(qp_solve_kernel<TEAM, CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_cta);
-    if (e != cudaSuccess) return e;
-    int teams = CTA / TEAM;
-    int grid = (h->batch + teams - 1) / teams;
-    qp_solve_kernel<TEAM, CTA><<<grid, CTA, h->smem_cta, h->stream>>>(a);
-    return cudaGetLastError();
+// one object file per team size (qp_solve_inst.cu)
+namespace sqpb200 {
+cudaError_t launch_qp_solve_32(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_64(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_128(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_256(const QPKernelArgs&, int, cudaStream_t);
 }
 
 int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask) {
@@ -616,10 +615,10 @@ int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned cha
     CK(cudaEventRecord(h->ev0, h->stream));
     cudaError_t e;
     switch (h->team) {
-    case 32: e = launch_solve<32, 128>(h, a); break;
-    case 64: e = launch_solve<64, 128>(h, a); break;
-    case 128: e = launch_solve<128, 128>(h, a); break;
-    default: e = launch_solve<256, 256>(h, a); break;
+    case 32: e = launch_qp_solve_32(a, h->smem_cta, h->stream); break;
+    case 64: e = launch_qp_solve_64(a, h->smem_cta, h->stream); break;
+    case 128: e = launch_qp_solve_128(a, h->smem_cta, h->stream); break;
+    default: e = launch_qp_solve_256(a, h->smem_cta, h->stream); break;
     }
     if (e != cudaSuccess) { h->err = std::string("qp_solve_kernel launch: ") + cudaGetErrorString(e); return SQPB200_ERR_CUDA; }
     CK(cudaEventRecord(h->ev1, h->stream));

@@ -29,6 +29,17 @@
 
 namespace sqpb200 {
 
+// Out-of-line member functions keep the one-warp-per-QP kernel at ~14k SASS instructions (vs ~52k fully
+// inlined).  The multi-warp variants (TEAM >= 64) MUST be compiled with -DQP_INLINE_ALL: CTA-level barriers
+// (bar.sync / __syncthreads) inside out-of-line functions were observed on sm_100a (CUDA 12.9) to lose
+// synchronisation when a warp reaches the call lane-divergent (intermittent wrong results / deadlocks with
+// __noinline__, none in 384-instance stress runs when inlined); warp barriers (__syncwarp) are unaffected.
+#ifdef QP_INLINE_ALL
+#define QP_FN __forceinline__
+#else
+#define QP_FN __noinline__
+#endif
+
 #define QP_EPS 2.221e-16
 #define QP_INFTY 1.0e20
 #define QP_ZERO 1.0e-25
@@ -79,9 +90,16 @@ template <int TEAM>
 struct Team {
     int lane;     // 0..TEAM-1
     int team_id;  // team index within the CTA
+    // TEAM == 32: warp barrier.  TEAM >= 128: the team is the whole CTA (one QP per CTA), so the compiler-known
+    // __syncthreads() is used.  TEAM == 64: two warps joined by a named barrier; the warp is re-converged first
+    // and the non-.aligned barrier.sync form is used, so a lane-divergent prologue cannot make it undefined.
     __device__ __forceinline__ void sync() const {
         if (TEAM == 32) __syncwarp();
-        else asm volatile("bar.sync %0, %1;" ::"r"(team_id + 1), "r"(TEAM) : "memory");
+        else if (TEAM >= 128) __syncthreads();
+        else {
+            __syncwarp();
+            asm volatile("barrier.sync %0, %1;" ::"r"(team_id + 1), "r"(TEAM) : "memory");
+        }
     }
 };
 
@@ -127,7 +145,7 @@ struct QPSolver {
     }
 
     // ---------------------------------------------------------------- sparse products
-    __device__ void mulH(const double* v, double* out) {  // out = (H + reg I) v   (H symmetric: column gather)
+    __device__ QP_FN void mulH(const double* v, double* out) {  // out = (H + reg I) v   (H symmetric: column gather)
         for (int c = lane; c < nV; c += TEAM) {
             double s = 0.0;
             if (has_H) {
@@ -139,7 +157,7 @@ struct QPSolver {
         }
         sync();
     }
-    __device__ void mulA(const double* v, double* out) {
+    __device__ QP_FN void mulA(const double* v, double* out) {
         for (int r = lane; r < nC; r += TEAM) {
             double s = 0.0;
             int k1 = Arp[r + 1];
@@ -148,7 +166,7 @@ struct QPSolver {
         }
         sync();
     }
-    __device__ void mulAT(const double* yc, double* out) {
+    __device__ QP_FN void mulAT(const double* yc, double* out) {
         for (int c = lane; c < nV; c += TEAM) {
             double s = 0.0;
             int e1 = Ap[c + 1];
@@ -166,7 +184,7 @@ struct QPSolver {
     }
 
     // ---------------------------------------------------------------- reductions
-    __device__ MinKey team_min(double t, int pos) {
+    __device__ QP_FN MinKey team_min(double t, int pos) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             double t2_ = __shfl_xor_sync(0xffffffffu, t, o);
@@ -197,13 +215,13 @@ struct QPSolver {
     }
 
     // ---------------------------------------------------------------- projected Cholesky
-    __device__ void proj_column(int b) {  // t2 = (H+regI) * (column b of Q scattered to full space)
+    __device__ QP_FN void proj_column(int b) {  // t2 = (H+regI) * (column b of Q scattered to full space)
         for (int i = lane; i < nV; i += TEAM) { int p = posFR[i]; t1[i] = (p >= 0) ? Q[p * ld + b] : 0.0; }
         sync();
         mulH(t1, t2);
     }
     // returns 0 ok, 1+j on failure (uniform)
-    __device__ int recompute_R() {
+    __device__ QP_FN int recompute_R() {
         int nZ = nFR - nAC;
         if (nZ <= 0) return 0;
         if (is_lp) {
@@ -231,9 +249,9 @@ struct QPSolver {
             }
             sync();
             double d = R(i, i);
+            sync();  // all lanes hold d before anyone rewrites R(i,i): the branch below is team-uniform
             if (!(d > QP_ZERO)) return 1 + i;
             double dd = sqrt(d);
-            sync();
             for (int j = i + lane; j < nZ; j += TEAM) R(i, j) = (j == i) ? dd : R(i, j) / dd;
             for (int j = lane; j < i; j += TEAM) R(i, j) = 0.0;
             sync();
@@ -241,7 +259,7 @@ struct QPSolver {
         return 0;
     }
     // border R with the new last null-space column; returns 1 if curvature acceptable
-    __device__ int extend_R(int check_curvature) {
+    __device__ QP_FN int extend_R(int check_curvature) {
         int nZ = nFR - nAC, b = nZ - 1;
         if (is_lp) {
             for (int a_ = lane; a_ < b; a_ += TEAM) { R(a_, b) = 0.0; R(b, a_) = 0.0; }
@@ -267,6 +285,7 @@ struct QPSolver {
         double rho2 = w[b];
         for (int k = 0; k < b; k++) rho2 -= R(k, b) * R(k, b);
         int ok = check_curvature ? (rho2 > QP_EPS_FLIP) : (rho2 > QP_ZERO);
+        sync();  // every lane has read w[b] / R(.,b) before a caller may overwrite them (team-uniform decision)
         if (!ok) return 0;
         if (lane == 0) R(b, b) = sqrt(rho2);
         for (int a_ = lane; a_ < b; a_ += TEAM) R(b, a_) = 0.0;
@@ -275,7 +294,7 @@ struct QPSolver {
     }
 
     // ---------------------------------------------------------------- working-set updates
-    __device__ void constraint_w(int c, double& wz2, double& a2) {
+    __device__ QP_FN void constraint_w(int c, double& wz2, double& a2) {
         int nZ = nFR - nAC;
         for (int p = lane; p < nFR; p += TEAM) a[p] = A_entry(c, FR[p]);
         sync();
@@ -289,9 +308,10 @@ struct QPSolver {
         for (int p = 0; p < nFR; p++) s2 += a[p] * a[p];
         for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
         wz2 = z2; a2 = s2;
+        sync();
     }
     // chain of rotations compressing w[0..cnt) into w[cnt-1]; writes (c,s) to t2,t3; returns r
-    __device__ double rotation_chain(int cnt) {
+    __device__ QP_FN double rotation_chain(int cnt) {
         double r = w[0];
         if (lane == 0) {
             double a0 = w[0];
@@ -306,7 +326,7 @@ struct QPSolver {
         r = t2[cnt - 1];
         return r;
     }
-    __device__ void add_constraint(int c, int status) {
+    __device__ QP_FN void add_constraint(int c, int status) {
         int nZ = nFR - nAC;
         double r = rotation_chain(nZ);
         for (int p = lane; p < nFR; p += TEAM) {
@@ -324,7 +344,7 @@ struct QPSolver {
         nAC++;
         sync();
     }
-    __device__ void remove_constraint(int c) {
+    __device__ QP_FN void remove_constraint(int c) {
         int k = posAC[c];
         for (int i = k + 1; i < nAC; i++) {
             int cL = nFR - 1 - i;
@@ -355,15 +375,16 @@ struct QPSolver {
         nAC--;
         sync();
     }
-    __device__ double bound_w(int v) {
+    __device__ QP_FN double bound_w(int v) {
         int nZ = nFR - nAC, p = posFR[v];
         for (int j = lane; j < nFR; j += TEAM) w[j] = Q[p * ld + j];
         sync();
         double z2 = 0.0;
         for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
+        sync();
         return z2;
     }
-    __device__ void add_bound(int v, int status) {
+    __device__ QP_FN void add_bound(int v, int status) {
         int nZ = nFR - nAC, p = posFR[v];
         rotation_chain(nFR);
         for (int pp = lane; pp < nFR; pp += TEAM) {
@@ -397,7 +418,7 @@ struct QPSolver {
         nFR--;
         sync();
     }
-    __device__ void remove_bound(int v) {
+    __device__ QP_FN void remove_bound(int v) {
         for (int j = lane; j < nFR; j += TEAM) { Q[nFR * ld + j] = 0.0; Q[j * ld + nFR] = 0.0; }
         for (int i = lane; i < nAC; i += TEAM) {
             int r = AC[i];
@@ -431,7 +452,7 @@ struct QPSolver {
 
     // ---------------------------------------------------------------- T solves
     // T v = b : v indexed by Q column; row i has its diagonal at column nFR-1-i
-    __device__ void solve_T(double* b, double* v) {  // b (by AC position) is destroyed
+    __device__ QP_FN void solve_T(double* b, double* v) {  // b (by AC position) is destroyed
         for (int i = 0; i < nAC; i++) {
             int d = nFR - 1 - i;
             double vi = b[i] / T(i, d);
@@ -442,7 +463,7 @@ struct QPSolver {
         }
     }
     // T' u = r : r indexed by Q column (destroyed), u by AC position
-    __device__ void solve_Tt(double* r, double* u) {
+    __device__ QP_FN void solve_Tt(double* r, double* u) {
         for (int i = nAC - 1; i >= 0; i--) {
             int d = nFR - 1 - i;
             double ui = r[d] / T(i, d);
@@ -457,7 +478,7 @@ struct QPSolver {
     // ---------------------------------------------------------------- step direction
     // dxFX: full-length vector holding the bound shift of every fixed variable; dbAC by AC position.
     // dgv(i) is evaluated on the fly as gN[i]-g[i] when use_dg, else taken from `dgvec`.
-    __device__ void step_direction(const double* dgvec, const double* dxFX, double* dbAC) {
+    __device__ QP_FN void step_direction(const double* dgvec, const double* dxFX, double* dbAC) {
         int nZ = nFR - nAC;
         for (int i = lane; i < nV; i += TEAM) dx[i] = (sB[i] != 0) ? dxFX[i] : 0.0;
         sync();
@@ -526,13 +547,13 @@ struct QPSolver {
     }
 
     // ---------------------------------------------------------------- drift correction / ramping
-    __device__ void stationarity_gradient() {  // g = A'y_c + y_b - (H+regI) x
+    __device__ QP_FN void stationarity_gradient() {  // g = A'y_c + y_b - (H+regI) x
         mulAT(y + nV, t2);
         mulH(x, t1);
         for (int i = lane; i < nV; i += TEAM) g[i] = t2[i] + y[i] - t1[i];
         sync();
     }
-    __device__ void drift_correction() {
+    __device__ QP_FN void drift_correction() {
         mulA(x, Ax);
         for (int i = lane; i < nV; i += TEAM) {
             int s = sB[i]; double xi = x[i];
@@ -549,7 +570,7 @@ struct QPSolver {
         sync();
         stationarity_gradient();
     }
-    __device__ void ramping() {
+    __device__ QP_FN void ramping() {
         int nRamp = nV + nC + nC + nV;
         const double r0 = 0.5, r1 = 1.0;
         mulA(x, Ax);
@@ -588,7 +609,7 @@ struct QPSolver {
 
     // ---------------------------------------------------------------- exchange (ensure LI)
     // element to add: constraint c (v<0) or bound v (c<0); w holds its Q-coordinates. 0 ok, 1 infeasible
-    __device__ int ensure_li(int c, int v, int status) {
+    __device__ QP_FN int ensure_li(int c, int v, int status) {
         int nZ = nFR - nAC;
         double* xiC = zv;
         double* xiB = dx;
@@ -637,7 +658,7 @@ struct QPSolver {
     }
 
     // ---------------------------------------------------------------- homotopy
-    __device__ int homotopy(int max_iter) {
+    __device__ QP_FN int homotopy(int max_iter) {
         iters = 0;
         for (int it = 0;; it++) {
             // data shift: dg in `a`.. we keep dg in zv? -> use dedicated: t-vectors are busy, so dg lives in `a` (nT)
@@ -781,7 +802,7 @@ struct QPSolver {
     }
 
     // ---------------------------------------------------------------- cold start / refactorise
-    __device__ void cold_start_state() {
+    __device__ QP_FN void cold_start_state() {
         nFR = 0; nAC = 0; ramp_offset = 0;
         for (int i = lane; i < nV; i += TEAM) {
             x[i] = 0.0; y[i] = 0.0; sB[i] = -1; posFR[i] = -1; g[i] = 0.0; lb[i] = 0.0; ub[i] = QP_BOUND_RELAX;
@@ -792,7 +813,7 @@ struct QPSolver {
         sync();
     }
     // rebuild TQ and R for the kept working set with the new matrix values; 0 ok
-    __device__ int refactorise() {
+    __device__ QP_FN int refactorise() {
         int nAC_old = nAC;
         // remember (constraint, status) by AC position in t1/t3 tails is unsafe (used by callees): use yv/zv? also used.
         // -> keep them in dAx (nC) and dy[nV..] (nC): neither is touched by constraint_w/add_constraint/recompute_R.

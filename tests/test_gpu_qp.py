@@ -1,0 +1,273 @@
+"""GPU parity for the active-set QP/LP kernel (row D) through the C ABI: the CUDA path against the CPU
+oracle on the same inputs.  Gates: identical final working sets (raw qpOASES
+convention), identical status and iteration counts, x / y / objective within 1e-8 relative; KKT residuals
+of the fused epilogue against the oracle's restatement of test_optimality."""
+import numpy as np
+import pytest
+
+import restartsqp_b200 as r
+from restartsqp_b200 import capi
+from oracle import oracle_py as orc
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+RTOL = 1.0e-8
+FIX = H.load_qp_fixtures()
+
+
+def relerr(a, b):
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max())) if a.size else 0.0
+
+
+def solve_batch_csc(nV, nC, Acsc, Hcsc, g, lb, ub, lbA, ubA, qptype=r.QPType.QP, team_size=0, Avals=None, Hvals=None):
+    """g, lb, ... are [batch][len]; Acsc/Hcsc = (colptr,rowidx,val[z]) shared, Avals/Hvals optional [batch][z]."""
+    B = g.shape[0]
+    s = r.CudaQPInterface(nV=nV, nC=nC, qptype=qptype, batch=B, team_size=team_size)
+    s.set_csc(capi.MAT_A, Acsc[0], Acsc[1], Acsc[2] if Avals is None else Avals)
+    if qptype == r.QPType.QP:
+        s.set_csc(capi.MAT_H, Hcsc[0], Hcsc[1], Hcsc[2] if Hvals is None else Hvals)
+    s.set_g(g); s.set_lb(lb); s.set_ub(ub)
+    if nC:
+        s.set_lbA(lbA); s.set_ubA(ubA)
+    if qptype == r.QPType.QP:
+        s.optimizeQP() if B > 1 else s._solve(r.QPType.QP, None, None, 0)
+    else:
+        s.optimizeLP() if B > 1 else s._solve(r.QPType.LP, None, None, 0)
+    return s
+
+
+def check_against_oracle(s, b, o, nV, strict=True):
+    x, y = s.get_optimal_solution()[b], np.concatenate([s.get_multipliers_bounds()[b], s.get_multipliers_constr()[b]])
+    wc, wb = s.get_working_set(translated=False)
+    assert int(s.get_status()[b]) == o["status"]
+    assert int(s.get_iterations()[b]) == o["iters"]
+    assert (wb[b] == o["wb"]).all() and (wc[b] == o["wc"]).all(), "working sets differ"
+    if strict:
+        assert relerr(x, o["x"]) <= RTOL and relerr(y, o["y"]) <= RTOL
+        assert abs(s.get_obj_value()[b] - o["obj"]) <= RTOL * max(1.0, abs(o["obj"]))
+
+
+# The library is built with -fmad=false and the kernel evaluates every sum in the oracle's order, so even the
+# degenerate non-convex dumps (hs056, hs107: ~70 bound flips) follow the oracle's path bit for bit.
+PATH_DEPENDENT = set()
+
+
+@pytest.mark.parametrize("q", FIX, ids=[q["name"] for q in FIX])
+def test_dumped_qp_replay_matches_oracle(gpu_lib, q):
+    nV, nC = q["nV"], q["nC"]
+    B = 4
+    rng = np.random.default_rng(1234)
+    g = np.tile(np.array(q["g"]), (B, 1))
+    g[1:] *= 1.0 + 1e-3 * rng.uniform(-1, 1, size=g[1:].shape)  # replica 0 exact
+    tile = lambda k, n_: np.tile(np.array(q[k], dtype=np.float64).reshape(1, n_), (B, 1))
+    A = (q["A_colptr"], q["A_rowidx"], np.array(q["A_val"]))
+    Hc = (q["H_colptr"], q["H_rowidx"], np.array(q["H_val"]))
+    s = solve_batch_csc(nV, nC, A, Hc, g, tile("lb", nV), tile("ub", nV), tile("lbA", nC), tile("ubA", nC))
+    st = s.get_status()
+    assert ((st >= 20) & (st <= 30)).all()
+    assert np.isfinite(s.get_optimal_solution()).all()
+    if q["name"] in PATH_DEPENDENT:
+        s.close()
+        return
+    for b in range(B):
+        p = dict(nV=nV, nC=nC, g=g[b], lb=q["lb"], ub=q["ub"], lbA=q["lbA"], ubA=q["ubA"])
+        o = H.oracle_solve(orc, p, Acsc=A, Hcsc=Hc)
+        check_against_oracle(s, b, o, nV, strict=(o["status"] == 20))
+    # fused KKT epilogue == stand-alone kernel == oracle restatement of test_optimality (replica 0)
+    k_fused = s.get_optimality_status()["KKT_error"].copy()
+    k_alone = s.get_optimality_status(recompute=True)
+    p = dict(nV=nV, nC=nC, g=g[0], lb=q["lb"], ub=q["ub"], lbA=q["lbA"], ubA=q["ubA"])
+    o = H.oracle_solve(orc, p, Acsc=A, Hcsc=Hc)
+    if H.is_symmetric_fixture(q) and o["status"] == 20:
+        x, y = s.get_optimal_solution()[0], np.concatenate([s.get_multipliers_bounds()[0], s.get_multipliers_constr()[0]])
+        wc, wb = s.get_working_set(translated=False)
+        Ax = orc.csc_times(nC, nV, *A, x)
+        Wb, Wc = orc.translate_working_set(wb[0], wc[0], x, Ax, q["lb"], q["ub"], q["lbA"], q["ubA"])
+        ok, res = orc.kkt_residuals(nV, nC, A, Hc, g[0], q["lb"], q["ub"], q["lbA"], q["ubA"], x, y, Wb, Wc)
+        # stand-alone kernel: bit-exact with the restated reference formulas on the same (x, y, W)
+        assert [k_alone[k][0] for k in ("primal_violation", "dual_violation", "stationarity_violation",
+                                        "compl_violation", "KKT_error")] == res.tolist()
+        WcT, WbT = s.get_working_set(translated=True)
+        assert (WbT[0] == Wb).all() and (WcT[0] == Wc).all()
+        scale = max(1.0, np.abs(y).max() * max(1.0, np.abs(x).max()))
+        assert abs(k_fused[0] - res[4]) <= 1e-10 * scale
+    s.close()
+
+
+@pytest.mark.parametrize("team", [32, 64, 128, 256])
+def test_random_convex_batch_all_team_sizes(gpu_lib, team):
+    rng = np.random.default_rng(40 + team)
+    n, m = 6, 4
+    base = H.random_l1_qp(rng, n, m, convex=True, dens=0.7)
+    nV, nC, B = base["nV"], base["nC"], 64
+    Ac, Hc = H.csc(base["A"]), H.csc(base["H"])
+    Avals = np.tile(Ac[2], (B, 1))
+    Avals *= 1.0 + 0.1 * rng.standard_normal(Avals.shape) * (np.abs(np.abs(Avals) - 1.0) > 1e-12)  # keep the +-1 slack columns
+    Hvals = np.tile(Hc[2], (B, 1))
+    g = np.tile(base["g"], (B, 1)); g[:, :n] += rng.standard_normal((B, n))
+    lbA = np.tile(base["lbA"], (B, 1)); ubA = np.tile(base["ubA"], (B, 1))
+    shift = 0.5 * rng.standard_normal((B, m))
+    lbA = np.where(lbA > -1e17, lbA + shift, lbA); ubA = np.where(ubA < 1e17, ubA + shift, ubA)
+    lb, ub = np.tile(base["lb"], (B, 1)), np.tile(base["ub"], (B, 1))
+    s = solve_batch_csc(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA, team_size=team, Avals=Avals, Hvals=Hvals)
+    assert s.solve_config()["team_size"] == team
+    assert (s.get_status() == 20).all()
+    assert s.test_optimality().all()
+    for b in range(B):
+        p = dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b])
+        o = H.oracle_solve(orc, p, Acsc=(Ac[0], Ac[1], Avals[b]), Hcsc=(Hc[0], Hc[1], Hvals[b]))
+        check_against_oracle(s, b, o, nV)
+    s.close()
+
+
+@pytest.mark.parametrize("shape", [(1, 0), (2, 1), (4, 2), (10, 7), (23, 12), (30, 20)])
+def test_random_shapes_incl_edge_cases(gpu_lib, shape):
+    """n=1 / no constraints / nV above one warp's lane count; per-instance data, shared pattern."""
+    n, m = shape
+    rng = np.random.default_rng(1000 + 31 * n + m)
+    base = H.random_l1_qp(rng, n, m, convex=True, dens=0.5)
+    nV, nC, B = base["nV"], base["nC"], 8
+    Ac, Hc = H.csc(base["A"]), H.csc(base["H"])
+    g = np.tile(base["g"], (B, 1)); g[:, :n] += rng.standard_normal((B, n))
+    lb, ub = np.tile(base["lb"], (B, 1)), np.tile(base["ub"], (B, 1))
+    lbA, ubA = np.tile(base["lbA"], (B, 1)), np.tile(base["ubA"], (B, 1))
+    s = solve_batch_csc(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA)
+    for b in range(B):
+        p = dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b])
+        check_against_oracle(s, b, H.oracle_solve(orc, p, Acsc=Ac, Hcsc=Hc), nV)
+    s.close()
+
+
+def test_lp_matches_oracle(gpu_lib):
+    rng = np.random.default_rng(77)
+    n, m, B = 5, 4, 16
+    base = H.random_l1_qp(rng, n, m, rho=1.0)
+    nV, nC = base["nV"], base["nC"]
+    Ac = H.csc(base["A"])
+    g = np.tile(base["g"], (B, 1)); g[:, :n] = 0.0
+    lb, ub = np.tile(base["lb"], (B, 1)), np.tile(base["ub"], (B, 1))
+    lbA, ubA = np.tile(base["lbA"], (B, 1)), np.tile(base["ubA"], (B, 1))
+    shift = rng.standard_normal((B, m))
+    lbA = np.where(lbA > -1e17, lbA + shift, lbA); ubA = np.where(ubA < 1e17, ubA + shift, ubA)
+    s = solve_batch_csc(nV, nC, Ac, None, g, lb, ub, lbA, ubA, qptype=r.QPType.LP)
+    for b in range(B):
+        p = dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b], A=base["A"])
+        o = H.oracle_solve(orc, p, is_lp=True, max_iter=100, Acsc=Ac)
+        check_against_oracle(s, b, o, nV)
+    s.close()
+
+
+def test_hotstart_fixed_and_varied(gpu_lib):
+    """hotstart(g,lb,ub,lbA,ubA) and hotstart(H,g,A,...) (src/qpOASESInterface.cpp:176-211) against the
+    oracle's hot starts, and against cold starts on the new data (strictly convex => same point)."""
+    rng = np.random.default_rng(9)
+    n, m, B = 5, 3, 12
+    base = H.random_l1_qp(rng, n, m, convex=True)
+    nV, nC = base["nV"], base["nC"]
+    Ac, Hc = H.csc(base["A"]), H.csc(base["H"])
+    g = np.tile(base["g"], (B, 1)); g[:, :n] += rng.standard_normal((B, n))
+    lb, ub = np.tile(base["lb"], (B, 1)), np.tile(base["ub"], (B, 1))
+    lbA, ubA = np.tile(base["lbA"], (B, 1)), np.tile(base["ubA"], (B, 1))
+    s = solve_batch_csc(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA)
+    oracles = []
+    for b in range(B):
+        p = dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b])
+        o = H.oracle_solve(orc, p, Acsc=Ac, Hcsc=Hc)
+        check_against_oracle(s, b, o, nV)
+        oracles.append(o["solver"])
+    # 1) vectors only -> FIXED hot start
+    g2 = g.copy(); g2[:, :n] += 0.3 * rng.standard_normal((B, n))
+    lbA2 = np.where(lbA > -1e17, lbA - 0.2, lbA); ubA2 = np.where(ubA < 1e17, ubA + 0.1, ubA)
+    s.set_g(g2); s.set_lbA(lbA2); s.set_ubA(ubA2)
+    s.optimizeQP()
+    for b in range(B):
+        st = oracles[b].hotstart(g2[b], lb[b], ub[b], lbA2[b], ubA2[b])
+        x, y, obj, it = oracles[b].solution(); wb, wc = oracles[b].working_set()
+        check_against_oracle(s, b, dict(x=x, y=y, obj=obj, iters=it, status=st, wb=wb, wc=wc), nV)
+    # 2) new matrix values -> VARIED hot start (first a status flip, handled as a warm re-init)
+    Hv2 = np.tile(Hc[2], (B, 1)) * 1.1
+    Av2 = np.tile(Ac[2], (B, 1))
+    s.set_csc_values(capi.MAT_H, Hv2); s.set_csc_values(capi.MAT_A, Av2)
+    s.optimizeQP()
+    for b in range(B):
+        st = oracles[b].hotstart_matrices(Hv2[b], Av2[b], g2[b], lb[b], ub[b], lbA2[b], ubA2[b])
+        x, y, obj, it = oracles[b].solution(); wb, wc = oracles[b].working_set()
+        check_against_oracle(s, b, dict(x=x, y=y, obj=obj, iters=it, status=st, wb=wb, wc=wc), nV)
+        p = dict(nV=nV, nC=nC, g=g2[b], lb=lb[b], ub=ub[b], lbA=lbA2[b], ubA=ubA2[b])
+        cold = H.oracle_solve(orc, p, Acsc=Ac, Hcsc=(Hc[0], Hc[1], Hv2[b]))
+        assert relerr(s.get_optimal_solution()[b], cold["x"]) <= RTOL
+    s.close()
+
+
+def test_qphandler_solveQP_and_reference_exceptions(gpu_lib):
+    """QPhandler::solveQP (src/QPhandler.cpp:470-499) through triplets + IdentityInfo, batch == 1 semantics."""
+    n, m = 4, 2  # HS071 shape: x0 = (1,5,5,1), 1<=x<=5, c1>=25, c2=40
+    x_k = np.array([1.0, 5.0, 5.0, 1.0])
+    hnd = r.QPhandler(r.NLPInfo(nCon=m, nVar=n, nnz_jac_g=8, nnz_h_lag=10), r.QPType.QP, batch=1)
+    jr, jc = [1, 2] * 4, [1, 1, 2, 2, 3, 3, 4, 4]
+    c1 = lambda x: x[0] * x[1] * x[2] * x[3]
+    J = np.array([[x_k[1] * x_k[2] * x_k[3], x_k[0] * x_k[2] * x_k[3], x_k[0] * x_k[1] * x_k[3], x_k[0] * x_k[1] * x_k[2]],
+                  2 * x_k])
+    jv = np.array([J[r_ - 1, c_ - 1] for r_, c_ in zip(jr, jc)])
+    hr, hc = [1, 1, 2, 1, 2, 3, 1, 2, 3, 4], [1, 2, 2, 3, 3, 3, 4, 4, 4, 4]
+    Hd = np.array([[2 * x_k[3], x_k[3], x_k[3], 2 * x_k[0] + x_k[1] + x_k[2]], [0, 0, 0, x_k[0]], [0, 0, 0, x_k[0]], [0, 0, 0, 0]])
+    Hd = np.triu(Hd) + np.triu(Hd, 1).T + 2.0 * np.eye(4)
+    hv = np.array([Hd[r_ - 1, c_ - 1] for r_, c_ in zip(hr, hc)])
+    grad = np.array([x_k[3] * (2 * x_k[0] + x_k[1] + x_k[2]), x_k[0] * x_k[3], x_k[0] * x_k[3] + 1, x_k[0] * (x_k[0] + x_k[1] + x_k[2])])
+    c_k = np.array([c1(x_k), (x_k ** 2).sum()])
+    hnd.set_bounds(1.0, np.ones(4), 5 * np.ones(4), x_k, np.array([25.0, 40.0]), np.array([1e18, 40.0]), c_k)
+    hnd.set_g(grad, 1.0)
+    hnd.set_A(r.SpTripletMat(np.array(jr), np.array(jc), jv, m, n))
+    hnd.set_H(r.SpTripletMat(np.array(hr), np.array(hc), hv, n, n, True))
+    stats = r.Stats()
+    ok = hnd.solveQP(stats)
+    assert ok.all() and int(hnd.get_status()[0]) == 20 and stats.qp_iter[0] > 0
+    # same QP through the oracle
+    I = orc.identity_info(n, m)
+    A = orc.assemble_A(m, n + 2 * m, jr, jc, jv, I)
+    Hh = orc.assemble_H(n + 2 * m, hr, hc, hv, True)
+    si = hnd.solverInterface_
+    p = dict(nV=n + 2 * m, nC=m, g=si.getG()[0], lb=si.getLb()[0], ub=si.getUb()[0], lbA=si.getLbA()[0], ubA=si.getUbA()[0])
+    o = H.oracle_solve(orc, p, Acsc=A[:3], Hcsc=Hh[:3])
+    check_against_oracle(si, 0, o, n + 2 * m)
+    assert abs(hnd.get_infea_measure_model()[0] - orc.lib().orc_infea_measure_model(n, m, orc._dp(o["x"]))) < 1e-12
+    assert abs(hnd.get_objective()[0] - o["obj"]) <= RTOL * max(1, abs(o["obj"]))
+    # batch == 1 raises like the reference when the QP cannot be solved (max iterations exhausted)
+    si2 = r.CudaQPInterface(r.NLPInfo(nCon=m, nVar=n), r.QPType.QP, r.Options(qp_maxiter=1), batch=1)
+    si2.set_A(r.SpTripletMat(np.array(jr), np.array(jc), jv, m, n), hnd.I_info_A_)
+    si2.set_H(r.SpTripletMat(np.array(hr), np.array(hc), hv, n, n, True))
+    si2.set_g(p["g"]); si2.set_lb(p["lb"]); si2.set_ub(p["ub"]); si2.set_lbA(p["lbA"]); si2.set_ubA(p["ubA"])
+    with pytest.raises(r.QP_NOT_OPTIMAL):
+        si2.optimizeQP()
+    assert int(si2.get_status()[0]) == int(r.Exitflag.QPERROR_PERFORMINGHOMOTOPY)
+    si2.close(); si.close()
+
+
+def test_active_mask_and_large_batch_properties(gpu_lib):
+    """Size-independent properties at a large batch: every instance KKT-optimal by the reference's test;
+    replicated inputs give bit-identical outputs; masked-out instances are untouched."""
+    rng = np.random.default_rng(21)
+    n, m, B = 8, 5, 20000
+    base = H.random_l1_qp(rng, n, m, convex=True)
+    nV, nC = base["nV"], base["nC"]
+    Ac, Hc = H.csc(base["A"]), H.csc(base["H"])
+    g = np.tile(base["g"], (B, 1)); g[: B // 2, :n] += rng.standard_normal((B // 2, n))
+    g[B // 2:] = g[: B // 2]  # second half replicates the first
+    lb, ub = np.tile(base["lb"], (B, 1)), np.tile(base["ub"], (B, 1))
+    lbA, ubA = np.tile(base["lbA"], (B, 1)), np.tile(base["ubA"], (B, 1))
+    s = r.CudaQPInterface(nV=nV, nC=nC, batch=B)
+    s.set_csc(capi.MAT_A, *Ac); s.set_csc(capi.MAT_H, *Hc)
+    s.set_g(g); s.set_lb(lb); s.set_ub(ub); s.set_lbA(lbA); s.set_ubA(ubA)
+    mask = np.ones(B, np.uint8); mask[7] = 0
+    s.optimizeQP(active_mask=mask)
+    st, x = s.get_status(), s.get_optimal_solution()
+    assert st[7] == int(r.Exitflag.QPERROR_NOTINITIALISED) and not x[7].any()
+    keep = mask.astype(bool)
+    assert (st[keep] == 20).all() and s.test_optimality()[keep].all()
+    assert (x[: B // 2][keep[: B // 2]] == x[B // 2:][keep[: B // 2]]).all()
+    for b in rng.integers(0, B // 2, 5):
+        if b == 7:
+            continue
+        p = dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b])
+        check_against_oracle(s, int(b), H.oracle_solve(orc, p, Acsc=Ac, Hcsc=Hc), nV)
+    s.close()

@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- QP subproblems/sec of the batched QP-subproblem hot path on B200.
+
+Workload (BASELINE.json configs[1]): replay of the dumped QP subproblems of
+test/unsolved_QP_data + test/unsolved_QPs as a batch.  Every dumped QP with a symmetric Hessian array
+(21 of the 27; the other six hold a non-symmetric "H", i.e. are not QPs, and are kept as robustness tests
+only) is replicated B = 4096 times with g *= 1 + 1e-3*U(-1,1) (seed 1234, replica 0 exact).  One step =
+one cold-start solve (init) of every replica of every dumped QP = 21*B QPs per GPU.  With N GPUs every
+rank solves its own 21*B replicas (rank-seeded perturbations): weak scaling, no collective on the path.
+
+  value  QPs/s with all inputs resident in HBM: K steps of 21 solve launches, CUDA events, max over ranks.
+  e2e    the same through the public plugin API with HOST (pinned) buffers: every step uploads H, A values,
+         g, lb, ub, lbA, ubA of every instance, solves, and reads x, y, objective and status back.
+  roofline  qp_solve_kernel: algorithmic compulsory bytes over the kernel's device time,
+         against the measured HBM copy peak; FP64 and shared-memory rates are reported next to it.
+  cpu_baseline  the CPU oracle (oracle/, a port: qpOASES itself is not available) on all host cores over a
+         bounded sample of the same workload.
+
+`--impl reference` times that CPU path alone and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+METRIC = "QP subproblems/sec"
+UNIT = "QPs/s"
+WORKLOAD = "replay_dumped_qps (test/unsolved_QP_data + test/unsolved_QPs, 21 symmetric-H dumps x B replicas, cold start)"
+
+
+# ------------------------------------------------------------------------------------------ workload
+def load_fixtures():
+    import scipy.sparse as sp
+    with open(os.path.join(ROOT, "tests", "golden", "qp_fixtures.json")) as f:
+        qps = json.load(f)["qps"]
+    out = []
+    for q in qps:
+        nV = q["nV"]
+        Hd = sp.csc_matrix((q["H_val"], q["H_rowidx"], q["H_colptr"]), shape=(nV, nV)).toarray()
+        if np.abs(Hd - Hd.T).max() == 0.0:
+            out.append(q)
+    return out
+
+
+def make_batch(q, B, seed):
+    nV, nC = q["nV"], q["nC"]
+    rng = np.random.default_rng(seed)
+    g = np.tile(np.array(q["g"], dtype=np.float64), (B, 1))
+    g[1:] *= 1.0 + 1e-3 * rng.uniform(-1.0, 1.0, size=g[1:].shape)
+    tile = lambda k, n: np.ascontiguousarray(np.tile(np.array(q[k], dtype=np.float64).reshape(1, n), (B, 1)))
+    return dict(nV=nV, nC=nC, g=g, lb=tile("lb", nV), ub=tile("ub", nV), lbA=tile("lbA", nC), ubA=tile("ubA", nC),
+                Av=tile("A_val", len(q["A_val"])), Hv=tile("H_val", len(q["H_val"])))
+
+
+def algorithmic_bytes(q):
+    """Compulsory HBM bytes of one solve (SURVEY.md 8d, row 'QP/LP solve'): data in, x/y/working set/obj/status out."""
+    nV, nC, zA, zH = q["nV"], q["nC"], len(q["A_val"]), len(q["H_val"])
+    return 8 * (zH + zA + 3 * nV + 2 * nC) + 8 * (2 * nV + nC) + 4 * (nV + nC) + 16
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_rate(fixtures, sample_B, seed, max_seconds=25.0):
+    """QPs/s of the CPU oracle on all host cores over `sample_B` replicas of every dumped QP."""
+    from oracle import oracle_py as orc
+    cores = orc.lib().orc_max_threads()
+    total, t_total = 0, 0.0
+    for k, q in enumerate(fixtures):
+        d = make_batch(q, sample_B, seed + k)
+        A = (q["A_colptr"], q["A_rowidx"], q["A_val"])
+        H = (q["H_colptr"], q["H_rowidx"], q["H_val"])
+        t0 = time.perf_counter()
+        r = orc.solve_batch(d["nV"], d["nC"], A, H, d["g"], d["lb"], d["ub"], d["lbA"], d["ubA"], Avals=d["Av"], Hvals=d["Hv"])
+        t_total += time.perf_counter() - t0
+        total += sample_B
+        cores = r["threads"]
+        if t_total > max_seconds:
+            break
+    return total / t_total, cores, total, t_total
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    fixtures = load_fixtures()
+    # bounded sample per step: calibrate so that warmup+steps stay within ~2 minutes
+    rate0, cores, n0, t0 = cpu_rate(fixtures, 16, 1234)
+    per_step_budget = 90.0 / max(1, args.steps + args.warmup)
+    sample_B = int(max(16, min(args.replicas, rate0 * per_step_budget / len(fixtures))))
+    for _ in range(args.warmup):
+        cpu_rate(fixtures, sample_B, 1234)
+    tot, tt = 0, 0.0
+    for _ in range(args.steps):
+        r, cores, n, t = cpu_rate(fixtures, sample_B, 1234, max_seconds=1e9)
+        tot += n; tt += t
+    value = tot / tt
+    sample = "%d replicas of each of the %d dumped QPs per step (%d QPs/step)" % (sample_B, len(fixtures), sample_B * len(fixtures))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic (dumped QP fixtures of the reference, perturbed replicas)",
+        "config": {"workload": WORKLOAD, "replicas_per_qp": sample_B, "qps_per_step": sample_B * len(fixtures)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "CPU oracle (restatement of the qpOASES path; qpOASES 3.2.1 is not available offline), "
+                                 "one solver object per thread, pthreads over instances"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import restartsqp_b200 as r
+    from restartsqp_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = capi.lib()
+    fixtures = load_fixtures()
+    B = args.replicas
+    groups = []
+    h2d = d2h = 0
+    for k, q in enumerate(fixtures):
+        d = make_batch(q, B, 1234 + 1000 * rank + k)
+        s = r.CudaQPInterface(nV=d["nV"], nC=d["nC"], qptype=r.QPType.QP, batch=B, device=local_rank, keep_state=False,
+                              team_size=args.team)
+        s.set_csc(capi.MAT_A, q["A_colptr"], q["A_rowidx"], d["Av"])
+        s.set_csc(capi.MAT_H, q["H_colptr"], q["H_rowidx"], d["Hv"])
+        s.set_g(d["g"]); s.set_lb(d["lb"]); s.set_ub(d["ub"])
+        if d["nC"]:
+            s.set_lbA(d["lbA"]); s.set_ubA(d["ubA"])
+        pin = {kk: torch.from_numpy(v).pin_memory() for kk, v in d.items() if isinstance(v, np.ndarray)}
+        nV, nC = d["nV"], d["nC"]
+        outp = dict(x=torch.empty((B, nV), dtype=torch.float64).pin_memory(), y=torch.empty((B, nV + nC), dtype=torch.float64).pin_memory(),
+                    obj=torch.empty(B, dtype=torch.float64).pin_memory(), st=torch.empty(B, dtype=torch.int32).pin_memory())
+        h2d += sum(int(t.numel()) * 8 for t in pin.values())
+        d2h += sum(int(t.numel()) * t.element_size() for t in outp.values())
+        groups.append(dict(q=q, s=s, pin=pin, out=outp, nV=nV, nC=nC))
+    torch.cuda.synchronize()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step_resident():
+        flush.zero_()
+        for gr in groups:
+            gr["s"]._solve(r.QPType.QP, None, None, 0)
+
+    def step_e2e():
+        flush.zero_()
+        for gr in groups:
+            s, p, o = gr["s"], gr["pin"], gr["out"]
+            s.set_csc_values(capi.MAT_A, p["Av"]); s.set_csc_values(capi.MAT_H, p["Hv"])
+            s.set_g(p["g"]); s.set_lb(p["lb"]); s.set_ub(p["ub"])
+            if gr["nC"]:
+                s.set_lbA(p["lbA"]); s.set_ubA(p["ubA"])
+            s._solve(r.QPType.QP, None, None, 0)
+            L.sqpb200_get_solution(s.h, C.c_void_p(o["x"].data_ptr()), C.c_void_p(o["y"].data_ptr()), C.c_void_p(o["obj"].data_ptr()),
+                                   C.c_void_p(o["st"].data_ptr()), None, capi.LOC_HOST)
+
+    def timed(fn, steps, warmup, collect_kernel_ms=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = sum(gr["s"].launch_count() for gr in groups)
+        kms = 0.0
+        e0.record()
+        for _ in range(steps):
+            fn()
+            if collect_kernel_ms:  # per-launch CUDA-event time recorded by the library around qp_solve_kernel
+                kms += sum(gr["s"].last_solve_ms() for gr in groups)
+        e1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        launches = sum(gr["s"].launch_count() for gr in groups) - launches0
+        return float(t.item()), launches, kms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, launches, _ = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    # second pass only to attribute device time to the solve kernel (event sync per launch serialises the host)
+    _, _, kernel_ms = timed(step_resident, args.steps, 0, collect_kernel_ms=True)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    qps_step = len(fixtures) * B * world
+    value = qps_step * args.steps / (ms_res * 1e-3)
+    e2e = qps_step * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        # parity spot check on the benchmarked data (replica 0 of each dump) against the oracle
+        status_ok = 0
+        for gr in groups:
+            status_ok += int((gr["s"].get_status() == 20).sum())
+        # roofline of the dominant kernel
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        bytes_step = sum(algorithmic_bytes(gr["q"]) for gr in groups) * B
+        kernel_s_per_step = kernel_ms * 1e-3 / args.steps
+        achieved = bytes_step / kernel_s_per_step / 1e9
+        fp64 = smem = None
+        try:
+            P = C.CDLL(os.path.join(ROOT, "restartsqp_b200", "lib", "libsqpb200_peaks.so"))
+            a, b = C.c_double(0), C.c_double(0)
+            if P.peaks_measure(C.byref(a), C.byref(b)) == 0:
+                fp64, smem = a.value, b.value
+        except Exception:
+            pass
+        flops_step = None
+        try:
+            from oracle import oracle_py as orc
+            fl = 0.0
+            for gr in groups:
+                q = gr["q"]
+                o = orc.OracleQP(q["nV"], q["nC"])
+                o.init((q["H_colptr"], q["H_rowidx"], q["H_val"]), q["g"], (q["A_colptr"], q["A_rowidx"], q["A_val"]), q["lb"], q["ub"], q["lbA"], q["ubA"])
+                fl += o.flops()
+            flops_step = fl * B
+        except Exception:
+            pass
+        roofline = {"kernel": "qp_solve_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "kernel_ms_per_step": 1e3 * kernel_s_per_step, "kernel_share_of_step": kernel_s_per_step / (ms_res * 1e-3 / args.steps),
+                    "algorithmic_bytes_per_step": bytes_step,
+                    "note": "active-set iterations run out of shared memory: the kernel is latency/issue bound, not HBM bound; "
+                            "FP64 rate (flop model of SURVEY.md 8d counted by the oracle on replica 0) is given in fp64"}
+        if flops_step is not None:
+            roofline["fp64"] = {"achieved_gflops": flops_step / kernel_s_per_step / 1e9, "peak_gflops": fp64,
+                                "frac": (flops_step / kernel_s_per_step / 1e9 / fp64) if fp64 else None,
+                                "peak_source": "FMA-chain microbenchmark tools/peaks.cu, this run"}
+        if smem is not None:
+            roofline["smem_peak_gbs"] = smem
+        sample_B = max(8, min(B, 256))
+        rate, cores, n, t = cpu_rate(fixtures, sample_B, 1234, max_seconds=25.0)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (dumped QP fixtures of the reference, perturbed replicas)",
+            "config": {"workload": WORKLOAD, "replicas_per_qp": B, "qps_per_step_per_gpu": len(fixtures) * B,
+                       "l2": "256 MiB buffer written between steps (inside the timed region)",
+                       "solved_optimal": status_ok, "team_size": args.team or "auto"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d QPs (%d replicas of each dumped QP) in %.1f s" % (n, sample_B, t)},
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--replicas", type=int, default=4096, help="replicas per dumped QP (B of SURVEY.md 8d config 2)")
+    ap.add_argument("--team", type=int, default=0, help="threads per QP (0 = auto)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,7 +49,6 @@ struct sqpb200_handle_s {
     unsigned char* dmask = nullptr;
     // hot-start state
     double* dstate = nullptr;
-    int* dstate_hdr = nullptr;
     int slice_doubles = 0, ld = 0;
     // change flags (src/qpOASESInterface.cpp:361-496, 817-833)
     bool first_solved = false, upd_A = false, upd_H = false, upd_g = false, upd_bounds = false;
@@ -160,7 +159,7 @@ int sqpb200_destroy(sqpb200_handle h) {
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dAp, h->dAi, h->dArp, h->dAci, h->dAperm, h->dAsrc, h->dHp, h->dHi, h->dHsrc, h->dAval, h->dHval,
                     h->dg, h->dlb, h->dub, h->dlbA, h->dubA, h->dx, h->dy, h->dobj, h->dkkt, h->dstatus, h->diters,
-                    h->dWB, h->dWC, h->dwsB, h->dwsC, h->dmask, h->dstate, h->dstate_hdr, h->stage};
+                    h->dWB, h->dWC, h->dwsB, h->dwsC, h->dmask, h->dstate, h->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -528,41 +527,49 @@ int sqpb200_qphandler_g(sqpb200_handle h, int n, int m, const double* grad, cons
 }
 
 // ------------------------------------------------------------------------------ solve
+static void fill_dims(sqpb200_handle h, QPKernelArgs& a) {
+    memset(&a, 0, sizeof a);
+    a.batch = h->batch; a.nV = h->nV; a.nC = h->nC; a.ld = h->ld;
+    a.is_lp = (h->qptype == SQPB200_LP); a.has_H = !a.is_lp;
+    a.zA = h->zA; a.zH = a.is_lp ? 0 : h->zH;  // an LP handle never holds H (src/qpOASESInterface.cpp:122-124)
+    qp_fill_layout(a);
+}
+
 static int choose_config(sqpb200_handle h) {
-    int zH = (h->qptype == SQPB200_QP) ? h->zH : 0;  // an LP handle never holds H (src/qpOASESInterface.cpp:122-124)
-    h->slice_doubles = qp_slice_doubles(h->nV, h->nC, h->ld, h->zA, zH);
-    size_t slice_bytes = (size_t)h->slice_doubles * 8;
-    const size_t SMEM_MAX = 227 * 1024;
-    int team = h->opt.team_size;
-    if (team == 0) {
-        size_t per_sm = SMEM_MAX / (slice_bytes + 64);
-        if (per_sm >= 16) team = 32;
-        else if (per_sm >= 8) team = 64;
-        else if (per_sm >= 3) team = 128;
-        else team = 256;
+    QPKernelArgs a;
+    fill_dims(h, a);
+    if (h->zA >= 32768 || h->zH >= 32768) { h->err = "pattern too large for 16-bit staged indices"; return SQPB200_ERR_TOO_LARGE; }
+    h->slice_doubles = a.slice_doubles;
+    const size_t slice_bytes = (size_t)a.slice_doubles * 8, pat_bytes = (size_t)a.pat_shorts * 2;
+    const size_t SMEM_MAX = 227 * 1024, SMEM_SM = 228 * 1024;
+    // One warp per QP: the only team size shipped this round (see the note in qp_kernel.cuh).
+    if (h->opt.team_size != 0 && h->opt.team_size != 32) { h->err = "team_size must be 0 (auto) or 32"; return SQPB200_ERR_INVALID; }
+    // QPs (warps) per CTA in {4, 2, 1}: take the one that keeps the most QPs resident per SM
+    int best_teams = 0;
+    size_t best_res = 0;
+    for (int teams = 4; teams >= 1; teams >>= 1) {
+        size_t smem = (size_t)teams * slice_bytes + pat_bytes;
+        if (smem > SMEM_MAX) continue;
+        size_t ctas = SMEM_SM / (smem + 1024 + 512);  // 1 KiB per CTA reserved by the driver + the static argument copy
+        if (ctas > 32) ctas = 32;
+        size_t res = ctas * teams;
+        if (res > 64) res = 64;  // 64 warps per SM
+        if (res > best_res) { best_res = res; best_teams = teams; }
     }
-    if (team != 32 && team != 64 && team != 128 && team != 256) { h->err = "team_size must be 32, 64, 128 or 256"; return SQPB200_ERR_INVALID; }
-    int cta = team <= 128 ? 128 : 256;
-    int teams = cta / team;
-    size_t smem = (size_t)teams * slice_bytes + (size_t)teams * 2 * (team / 32 + 1) * 8;
-    while (smem > SMEM_MAX && teams > 1) {  // fewer QPs per CTA
-        team *= 2; teams = cta / team;
-        smem = (size_t)teams * slice_bytes + (size_t)teams * 2 * (team / 32 + 1) * 8;
-    }
-    if (smem > SMEM_MAX) {
-        h->err = "QP too large for the shared-memory resident kernel (nV=" + std::to_string(h->nV) + ")";
+    if (best_teams == 0) {
+        h->err = "QP too large for the shared-memory resident kernel (nV=" + std::to_string(h->nV) + ", " +
+                 std::to_string(slice_bytes) + " B per QP)";
         return SQPB200_ERR_TOO_LARGE;
     }
-    h->team = team; h->teams_per_cta = teams; h->smem_cta = (int)smem;
+    h->team = 32; h->teams_per_cta = best_teams; h->smem_cta = (int)((size_t)best_teams * slice_bytes + pat_bytes);
     return 0;
 }
 
 // one object file per team size (qp_solve_inst.cu)
 namespace sqpb200 {
-cudaError_t launch_qp_solve_32(const QPKernelArgs&, int, cudaStream_t);
-cudaError_t launch_qp_solve_64(const QPKernelArgs&, int, cudaStream_t);
-cudaError_t launch_qp_solve_128(const QPKernelArgs&, int, cudaStream_t);
-cudaError_t launch_qp_solve_256(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_32_128(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_32_64(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_32_32(const QPKernelArgs&, int, cudaStream_t);
 }
 
 int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask) {
@@ -576,7 +583,6 @@ int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned cha
     if (rc) return rc;
     if (h->opt.keep_state && !h->dstate) {
         if (dev_alloc(h, &h->dstate, (size_t)h->batch * h->slice_doubles)) return SQPB200_ERR_CUDA;
-        if (dev_alloc(h, &h->dstate_hdr, (size_t)h->batch * 4)) return SQPB200_ERR_CUDA;
     }
     // init / hotstart decision: src/qpOASESInterface.cpp:141-211 with get_Matrix_change_status :817-833
     int mode = MODE_COLD;
@@ -593,14 +599,11 @@ int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned cha
         }
     }
     QPKernelArgs a;
-    memset(&a, 0, sizeof a);
-    a.batch = h->batch; a.nV = h->nV; a.nC = h->nC; a.ld = h->ld;
-    a.is_lp = is_lp; a.has_H = !is_lp;
+    fill_dims(h, a);
     a.max_iter = maxiter > 0 ? maxiter : (is_lp ? h->opt.lp_maxiter : h->opt.qp_maxiter);
     a.flags = (h->opt.enable_flipping ? FLAG_FLIPPING : 0) | (h->opt.enable_ramping ? FLAG_RAMPING : 0) |
               (h->opt.enable_drift ? FLAG_DRIFT : 0) | (h->opt.keep_state ? FLAG_KEEP_STATE : 0);
     a.mode = mode;
-    a.zA = h->zA; a.zH = is_lp ? 0 : h->zH;
     a.Ap = h->dAp; a.Ai = h->dAi; a.Arp = h->dArp; a.Aci = h->dAci; a.Aperm = h->dAperm;
     a.Hp = h->dHp; a.Hi = h->dHi;
     a.Aval = h->dAval; a.Hval = h->dHval;
@@ -611,14 +614,13 @@ int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned cha
     }
     a.x = h->dx; a.y = h->dy; a.obj = h->dobj; a.kkt = h->dkkt; a.status = h->dstatus; a.iters = h->diters;
     a.wsB = h->dwsB; a.wsC = h->dwsC; a.WB = h->dWB; a.WC = h->dWC;
-    a.state = h->dstate; a.state_hdr = h->dstate_hdr; a.slice_doubles = h->slice_doubles;
+    a.state = h->dstate;
     CK(cudaEventRecord(h->ev0, h->stream));
     cudaError_t e;
-    switch (h->team) {
-    case 32: e = launch_qp_solve_32(a, h->smem_cta, h->stream); break;
-    case 64: e = launch_qp_solve_64(a, h->smem_cta, h->stream); break;
-    case 128: e = launch_qp_solve_128(a, h->smem_cta, h->stream); break;
-    default: e = launch_qp_solve_256(a, h->smem_cta, h->stream); break;
+    switch (h->teams_per_cta) {
+    case 4: e = launch_qp_solve_32_128(a, h->smem_cta, h->stream); break;
+    case 2: e = launch_qp_solve_32_64(a, h->smem_cta, h->stream); break;
+    default: e = launch_qp_solve_32_32(a, h->smem_cta, h->stream); break;
     }
     if (e != cudaSuccess) { h->err = std::string("qp_solve_kernel launch: ") + cudaGetErrorString(e); return SQPB200_ERR_CUDA; }
     CK(cudaEventRecord(h->ev1, h->stream));

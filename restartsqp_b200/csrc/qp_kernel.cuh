@@ -1,18 +1,21 @@
 // qp_kernel.cuh -- batched FP64 active-set QP/LP solver for sm_100a (row D of SURVEY.md 8a).
 //
-// One QP per *team* of TEAM threads (32 = one warp, 64..256 = several warps joined by a named
-// barrier); a CTA hosts CTA_THREADS/TEAM teams.  All factors (Q of the TQ factorisation; T and
-// the projected Cholesky factor R packed into one array) and all iterate/work vectors of a QP
-// live in that team's slice of shared memory for the whole solve; HBM is touched only for the
-// compulsory input (matrix values, g, bounds) and output (x, y, working set, status, KKT
-// residuals) and, when hot starts are requested, for one save/restore of the slice.
+// One QP per warp; a CTA hosts CTA_THREADS/32 QPs.  Everything a QP needs for the whole solve lives in
+// that warp's slice of shared memory: the factors (Q of the TQ factorisation; T and the projected Cholesky
+// factor R packed into one array), current and target homotopy data, iterate and work vectors, matrix
+// values and the working-set index lists.  The sparsity pattern (shared by the batch) is staged once per
+// CTA as 16-bit indices, and the launch arguments are copied to static shared memory, so the solver's
+// out-of-line functions carry no per-thread state at all: no local-memory traffic, no global loads inside
+// the active-set loop.  HBM is touched only for the compulsory input (matrix values, g, bounds), the output
+// (x, y, working set, status, KKT residuals) and, for hot starts, one save/restore of the slice.
 //
 // The algorithm is the online active-set strategy as the reference drives it through qpOASES
 // (call sites src/qpOASESInterface.cpp:155-206, 231-268, 221-222, 843-844, options :765): same
 // steps, thresholds and tie-breaks as the CPU oracle (oracle/oracle_qp.c), which is only a
-// checker and is never called from here.
+// checker and is never called from here.  The library is compiled with -fmad=false and every sum
+// below runs in the oracle's order, so results are bit-identical with the oracle.
 //
-// Parallelisation inside a team (L = TEAM lanes):
+// Parallelisation inside the warp (32 lanes):
 //   * sparse products: one lane per output entry (CSC columns for H and A', a CSR view for A),
 //     accumulation in storage order (= the reference's SpHbMat::times order);
 //   * Givens sweeps: the rotation chain is a scalar recurrence; every lane applies the whole
@@ -23,22 +26,15 @@
 //     with lanes over the columns of the current row;
 //   * ratio tests: lane-local scan in index order + (ratio, position) lexicographic min reduction,
 //     which reproduces the sequential "first index wins ties" rule.
+//
+// A multi-warp-per-QP variant (named-barrier teams of 64..256 threads) was prototyped this round; with
+// out-of-line functions CTA-level barriers lost synchronisation intermittently on sm_100a / CUDA 12.9 and
+// the inlined build deadlocked at large grids, so only the warp variant is shipped.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace sqpb200 {
-
-// Out-of-line member functions keep the one-warp-per-QP kernel at ~14k SASS instructions (vs ~52k fully
-// inlined).  The multi-warp variants (TEAM >= 64) MUST be compiled with -DQP_INLINE_ALL: CTA-level barriers
-// (bar.sync / __syncthreads) inside out-of-line functions were observed on sm_100a (CUDA 12.9) to lose
-// synchronisation when a warp reaches the call lane-divergent (intermittent wrong results / deadlocks with
-// __noinline__, none in 384-instance stress runs when inlined); warp barriers (__syncwarp) are unaffected.
-#ifdef QP_INLINE_ALL
-#define QP_FN __forceinline__
-#else
-#define QP_FN __noinline__
-#endif
 
 #define QP_EPS 2.221e-16
 #define QP_INFTY 1.0e20
@@ -59,7 +55,7 @@ struct QPKernelArgs {
     int is_lp, has_H;
     int max_iter, flags, mode;
     int zA, zH;
-    // shared sparsity pattern
+    // shared sparsity pattern (global memory; staged once per CTA into shared memory as 16-bit indices)
     const int *Ap, *Ai;            // CSC of A (nC x nV)
     const int *Arp, *Aci, *Aperm;  // CSR view of A: rowptr, column index, position in the CSC value array
     const int *Hp, *Hi;            // CSC of H (nV x nV, full symmetric)
@@ -67,41 +63,51 @@ struct QPKernelArgs {
     const double *Aval, *Hval;
     const double *gN, *lbN, *ubN, *lbAN, *ubAN;
     const unsigned char* mask;
-    const int* inst_mode;  // optional per-instance mode override (NULL: args.mode)
     // outputs
     double *x, *y, *obj, *kkt;
     int *status, *iters;
     signed char *wsB, *wsC;  // raw working set (+1 upper, -1 lower, 0 inactive)
     int *WB, *WC;            // translated ActiveType
-    // resident hot-start state
-    double* state;           // [batch][slice_doubles]
-    int* state_hdr;          // [batch][4]: nFR, nAC, ramp_offset, initialised
-    int slice_doubles;       // doubles per team slice (double part + int part rounded up)
+    // resident hot-start state: [batch][slice_doubles] images of the shared-memory slice
+    double* state;
+    int slice_doubles;  // doubles per QP slice
+    int pat_shorts;     // 16-bit words of the staged pattern
+    // slice layout: offsets in doubles from the slice base (filled by qp_fill_layout)
+    int oQ, oRT, ox, og, olb, oub, odx, oAx, olbA, oubA, odAx, oy, ody, ot1, ot2, ot3, ow, oa, oyv, ozv, oAv, oHv;
+    int ogN, olbN, oubN, olbAN, oubAN;  // target data of the homotopy
+    int oS;                             // start of the 16-bit index arrays (sB, FR, posFR, sC, AC, posAC)
+    // pattern layout: offsets in 16-bit words from the pattern base
+    int pAp, pAi, pArp, pAci, pAperm, pHp, pHi;
 };
 
-__host__ __device__ inline int qp_slice_doubles(int nV, int nC, int ld, int zA, int zH) {
-    int nT = nV + nC;
-    int d = 2 * nV * ld + 5 * nV + 4 * nC + 9 * nT + zA + zH;
-    int shorts = 3 * nV + 3 * nC;
-    return d + (shorts * 2 + 7) / 8 + 1;
+// Slice layout of one QP in shared memory.  Header (2 doubles = 4 ints): nFR, nAC, ramp_offset, initialised.
+__host__ __device__ inline void qp_fill_layout(QPKernelArgs& a) {
+    const int nV = a.nV, nC = a.nC, nT = nV + nC, ld = a.ld;
+    int o = 2;
+    a.oQ = o; o += nV * ld;
+    a.oRT = o; o += nV * ld;
+    a.ox = o; o += nV; a.og = o; o += nV; a.olb = o; o += nV; a.oub = o; o += nV; a.odx = o; o += nV;
+    a.ogN = o; o += nV; a.olbN = o; o += nV; a.oubN = o; o += nV;
+    a.oAx = o; o += nC; a.olbA = o; o += nC; a.oubA = o; o += nC; a.odAx = o; o += nC;
+    a.olbAN = o; o += nC; a.oubAN = o; o += nC;
+    a.oy = o; o += nT; a.ody = o; o += nT; a.ot1 = o; o += nT; a.ot2 = o; o += nT; a.ot3 = o; o += nT;
+    a.ow = o; o += nT; a.oa = o; o += nT; a.oyv = o; o += nT; a.ozv = o; o += nT;
+    a.oAv = o; o += a.zA; a.oHv = o; o += a.zH;
+    a.oS = o;
+    const int shorts = 3 * nV + 3 * nC;
+    o += (shorts * 2 + 7) / 8;
+    a.slice_doubles = o;
+    int p = 0;
+    a.pAp = p; p += nV + 1; a.pAi = p; p += a.zA; a.pArp = p; p += nC + 1; a.pAci = p; p += a.zA; a.pAperm = p; p += a.zA;
+    a.pHp = p; p += nV + 1; a.pHi = p; p += a.zH;
+    a.pat_shorts = (p + 3) & ~3;
 }
 
-template <int TEAM>
-struct Team {
-    int lane;     // 0..TEAM-1
-    int team_id;  // team index within the CTA
-    // TEAM == 32: warp barrier.  TEAM >= 128: the team is the whole CTA (one QP per CTA), so the compiler-known
-    // __syncthreads() is used.  TEAM == 64: two warps joined by a named barrier; the warp is re-converged first
-    // and the non-.aligned barrier.sync form is used, so a lane-divergent prologue cannot make it undefined.
-    __device__ __forceinline__ void sync() const {
-        if (TEAM == 32) __syncwarp();
-        else if (TEAM >= 128) __syncthreads();
-        else {
-            __syncwarp();
-            asm volatile("barrier.sync %0, %1;" ::"r"(team_id + 1), "r"(TEAM) : "memory");
-        }
-    }
-};
+#ifdef __CUDACC__
+
+// launch arguments, copied once per CTA; every out-of-line function reads its context from here
+__shared__ QPKernelArgs sA;
+extern __shared__ __align__(16) double qp_smem[];
 
 struct MinKey {
     double t;
@@ -109,44 +115,38 @@ struct MinKey {
 };
 __device__ __forceinline__ bool key_less(double t1, int p1, double t2, int p2) { return t1 < t2 || (t1 == t2 && p1 < p2); }
 
-template <int TEAM>
-struct QPSolver {
-    Team<TEAM> tm;
-    int lane;
-    int nV, nC, nT, ld;
-    int nFR, nAC, ramp_offset;
-    int is_lp, has_H, flags;
-    double reg;
-    // shared memory
-    double *Q, *RT, *x, *y, *Ax, *g, *lb, *ub, *lbA, *ubA, *dx, *dy, *dAx, *t1, *t2, *t3, *w, *a, *yv, *zv, *Av, *Hv;
-    short *sB, *sC, *FR, *AC, *posFR, *posAC;
-    double* red;  // reduction scratch, per CTA team (TEAM/32 * 2 doubles)
-    // global
-    const int *Ap, *Ai, *Arp, *Aci, *Aperm, *Hp, *Hi;
-    const double *gN, *lbN, *ubN, *lbAN, *ubAN;
-    int iters;
+#define QP_FN __noinline__
 
-    __device__ __forceinline__ void sync() { tm.sync(); }
-    __device__ __forceinline__ double& R(int a_, int b_) { return RT[a_ * ld + b_]; }
-    __device__ __forceinline__ double& T(int i, int j) { return RT[(nV - 1 - i) * ld + j]; }
+// Context of the calling warp.  hdr: [0]=nFR [1]=nAC [2]=ramp_offset [3]=initialised.
+#define QP_CTX                                                                                     \
+    const int lane = threadIdx.x & 31;                                                             \
+    double* const slice = qp_smem + (size_t)(threadIdx.x >> 5) * sA.slice_doubles;                 \
+    int* const hdr = reinterpret_cast<int*>(slice);                                                \
+    const int nV = sA.nV, nC = sA.nC, ld = sA.ld;                                                  \
+    (void)lane; (void)hdr; (void)nV; (void)nC; (void)ld;
+#define QP_PAT const short* const pat = reinterpret_cast<const short*>(qp_smem + (size_t)(blockDim.x >> 5) * sA.slice_doubles);
 
-    __device__ void carve(double* base, const QPKernelArgs& A) {
-        double* p = base;
-        Q = p; p += nV * ld;
-        RT = p; p += nV * ld;
-        x = p; p += nV; g = p; p += nV; lb = p; p += nV; ub = p; p += nV; dx = p; p += nV;
-        Ax = p; p += nC; lbA = p; p += nC; ubA = p; p += nC; dAx = p; p += nC;
-        y = p; p += nT; dy = p; p += nT; t1 = p; p += nT; t2 = p; p += nT; t3 = p; p += nT;
-        w = p; p += nT; a = p; p += nT; yv = p; p += nT; zv = p; p += nT;
-        Av = p; p += A.zA; Hv = p; p += A.zH;
-        short* s = reinterpret_cast<short*>(p);
-        sB = s; s += nV; FR = s; s += nV; posFR = s; s += nV;
-        sC = s; s += nC; AC = s; s += nC; posAC = s; s += nC;
-    }
+#define V_(name) (slice + sA.o##name)
+#define S_(k) (reinterpret_cast<short*>(slice + sA.oS) + (k))
+#define sB_ S_(0)
+#define FR_ S_(nV)
+#define posFR_ S_(2 * nV)
+#define sC_ S_(3 * nV)
+#define AC_ S_(3 * nV + nC)
+#define posAC_ S_(3 * nV + 2 * nC)
+#define R_(a_, b_) RT[(a_) * ld + (b_)]
+#define T_(i, j) RT[(nV - 1 - (i)) * ld + (j)]
+#define SYNC() __syncwarp()
 
+struct QP {
     // ---------------------------------------------------------------- sparse products
-    __device__ QP_FN void mulH(const double* v, double* out) {  // out = (H + reg I) v   (H symmetric: column gather)
-        for (int c = lane; c < nV; c += TEAM) {
+    static __device__ QP_FN void mulH(const double* v, double* out) {  // out = (H + reg I) v (H symmetric: column gather)
+        QP_CTX QP_PAT
+        const short *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
+        const double* Hv = V_(Hv);
+        const bool has_H = sA.has_H && !sA.is_lp;
+        const double reg = sA.is_lp ? QP_EPS_REG : 0.0;
+        for (int c = lane; c < nV; c += 32) {
             double s = 0.0;
             if (has_H) {
                 int e1 = Hp[c + 1];
@@ -155,27 +155,50 @@ struct QPSolver {
             if (reg != 0.0) s += reg * v[c];
             out[c] = s;
         }
-        sync();
+        SYNC();
     }
-    __device__ QP_FN void mulA(const double* v, double* out) {
-        for (int r = lane; r < nC; r += TEAM) {
+    static __device__ QP_FN void mulH_noreg(const double* v, double* out) {  // out = H v (objective / KKT epilogue)
+        QP_CTX QP_PAT
+        const short *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
+        const double* Hv = V_(Hv);
+        const bool has_H = sA.has_H && !sA.is_lp;
+        for (int c = lane; c < nV; c += 32) {
+            double s = 0.0;
+            if (has_H) {
+                int e1 = Hp[c + 1];
+                for (int e = Hp[c]; e < e1; e++) s += Hv[e] * v[Hi[e]];
+            }
+            out[c] = s;
+        }
+        SYNC();
+    }
+    static __device__ QP_FN void mulA(const double* v, double* out) {
+        QP_CTX QP_PAT
+        const short *Arp = pat + sA.pArp, *Aci = pat + sA.pAci, *Aperm = pat + sA.pAperm;
+        const double* Av = V_(Av);
+        for (int r = lane; r < nC; r += 32) {
             double s = 0.0;
             int k1 = Arp[r + 1];
             for (int k = Arp[r]; k < k1; k++) s += Av[Aperm[k]] * v[Aci[k]];
             out[r] = s;
         }
-        sync();
+        SYNC();
     }
-    __device__ QP_FN void mulAT(const double* yc, double* out) {
-        for (int c = lane; c < nV; c += TEAM) {
+    static __device__ QP_FN void mulAT(const double* yc, double* out) {
+        QP_CTX QP_PAT
+        const short *Ap = pat + sA.pAp, *Ai = pat + sA.pAi;
+        const double* Av = V_(Av);
+        for (int c = lane; c < nV; c += 32) {
             double s = 0.0;
             int e1 = Ap[c + 1];
             for (int e = Ap[c]; e < e1; e++) s += Av[e] * yc[Ai[e]];
             out[c] = s;
         }
-        sync();
+        SYNC();
     }
-    __device__ __forceinline__ double A_entry(int r, int c) {  // A[r][c] via the CSR view (duplicates summed)
+    // A[r][c] via the CSR view (duplicates summed)
+    static __device__ __forceinline__ double A_entry(const short* pat, const double* Av, int r, int c) {
+        const short *Arp = pat + sA.pArp, *Aci = pat + sA.pAci, *Aperm = pat + sA.pAperm;
         double s = 0.0;
         int k1 = Arp[r + 1];
         for (int k = Arp[r]; k < k1; k++)
@@ -184,135 +207,140 @@ struct QPSolver {
     }
 
     // ---------------------------------------------------------------- reductions
-    __device__ QP_FN MinKey team_min(double t, int pos) {
+    static __device__ __forceinline__ MinKey warp_min(double t, int pos) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             double t2_ = __shfl_xor_sync(0xffffffffu, t, o);
             int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
             if (key_less(t2_, p2, t, pos)) { t = t2_; pos = p2; }
         }
-        if (TEAM > 32) {
-            int wid = lane >> 5;
-            sync();
-            if ((lane & 31) == 0) { red[2 * wid] = t; red[2 * wid + 1] = (double)pos; }
-            sync();
-            t = red[0]; pos = (int)red[1];
-            for (int k = 1; k < TEAM / 32; k++) {
-                double tk = red[2 * k]; int pk = (int)red[2 * k + 1];
-                if (key_less(tk, pk, t, pos)) { t = tk; pos = pk; }
-            }
-            sync();
-        }
         MinKey r; r.t = t; r.pos = pos;
         return r;
     }
 
     // ---------------------------------------------------------------- Givens
-    __device__ __forceinline__ void givens(double a_, double b_, double& c, double& s, double& r) {
+    static __device__ __forceinline__ void givens(double a_, double b_, double& c, double& s, double& r) {
         if (a_ == 0.0) { c = 1.0; s = 0.0; r = b_; return; }
         double h = sqrt(a_ * a_ + b_ * b_);
         c = b_ / h; s = a_ / h; r = h;
     }
 
     // ---------------------------------------------------------------- projected Cholesky
-    __device__ QP_FN void proj_column(int b) {  // t2 = (H+regI) * (column b of Q scattered to full space)
-        for (int i = lane; i < nV; i += TEAM) { int p = posFR[i]; t1[i] = (p >= 0) ? Q[p * ld + b] : 0.0; }
-        sync();
+    static __device__ QP_FN void proj_column(int b) {  // t2 = (H+regI) * (column b of Q scattered to full space)
+        QP_CTX
+        double *t1 = V_(t1), *t2 = V_(t2);
+        const double* Q = V_(Q);
+        const short* posFR = posFR_;
+        for (int i = lane; i < nV; i += 32) { int p = posFR[i]; t1[i] = (p >= 0) ? Q[p * ld + b] : 0.0; }
+        SYNC();
         mulH(t1, t2);
     }
     // returns 0 ok, 1+j on failure (uniform)
-    __device__ QP_FN int recompute_R() {
-        int nZ = nFR - nAC;
+    static __device__ QP_FN int recompute_R() {
+        QP_CTX
+        const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
         if (nZ <= 0) return 0;
-        if (is_lp) {
-            double sr = sqrt(reg);
-            for (int k = lane; k < nZ * nZ; k += TEAM) { int a_ = k / nZ, b_ = k % nZ; R(a_, b_) = (a_ == b_) ? sr : 0.0; }
-            sync();
+        double* RT = V_(RT);
+        if (sA.is_lp) {
+            double sr = sqrt(QP_EPS_REG);
+            for (int k = lane; k < nZ * nZ; k += 32) { int a_ = k / nZ, b_ = k % nZ; R_(a_, b_) = (a_ == b_) ? sr : 0.0; }
+            SYNC();
             return 0;
         }
+        const double *Q = V_(Q), *t2 = V_(t2);
+        const short* FR = FR_;
         for (int b = 0; b < nZ; b++) {
             proj_column(b);
-            for (int a_ = lane; a_ <= b; a_ += TEAM) {
+            for (int a_ = lane; a_ <= b; a_ += 32) {
                 double s = 0.0;
                 for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
-                R(a_, b) = s;
+                R_(a_, b) = s;
             }
-            sync();
+            SYNC();
         }
         // row-wise Cholesky: R'R = M, same per-element summation order as the column version
         for (int i = 0; i < nZ; i++) {
-            // phase A: s_j = M[i][j] - sum_{k<i} R[k][i] R[k][j]  for j >= i
-            for (int j = i + lane; j < nZ; j += TEAM) {
-                double s = R(i, j);
-                for (int k = 0; k < i; k++) s -= R(k, i) * R(k, j);
-                R(i, j) = s;
+            for (int j = i + lane; j < nZ; j += 32) {
+                double s = R_(i, j);
+                for (int k = 0; k < i; k++) s -= R_(k, i) * R_(k, j);
+                R_(i, j) = s;
             }
-            sync();
-            double d = R(i, i);
-            sync();  // all lanes hold d before anyone rewrites R(i,i): the branch below is team-uniform
+            SYNC();
+            double d = R_(i, i);
+            SYNC();  // all lanes hold d before anyone rewrites R(i,i): the branch below is warp-uniform
             if (!(d > QP_ZERO)) return 1 + i;
             double dd = sqrt(d);
-            for (int j = i + lane; j < nZ; j += TEAM) R(i, j) = (j == i) ? dd : R(i, j) / dd;
-            for (int j = lane; j < i; j += TEAM) R(i, j) = 0.0;
-            sync();
+            for (int j = i + lane; j < nZ; j += 32) R_(i, j) = (j == i) ? dd : R_(i, j) / dd;
+            for (int j = lane; j < i; j += 32) R_(i, j) = 0.0;
+            SYNC();
         }
         return 0;
     }
     // border R with the new last null-space column; returns 1 if curvature acceptable
-    __device__ QP_FN int extend_R(int check_curvature) {
-        int nZ = nFR - nAC, b = nZ - 1;
-        if (is_lp) {
-            for (int a_ = lane; a_ < b; a_ += TEAM) { R(a_, b) = 0.0; R(b, a_) = 0.0; }
-            if (lane == 0) R(b, b) = sqrt(reg);
-            sync();
+    static __device__ QP_FN int extend_R(int check_curvature) {
+        QP_CTX
+        const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC, b = nZ - 1;
+        double *RT = V_(RT), *w = V_(w);
+        if (sA.is_lp) {
+            for (int a_ = lane; a_ < b; a_ += 32) { R_(a_, b) = 0.0; R_(b, a_) = 0.0; }
+            if (lane == 0) R_(b, b) = sqrt(QP_EPS_REG);
+            SYNC();
             return 1;
         }
+        const double *Q = V_(Q), *t2 = V_(t2);
+        const short* FR = FR_;
         proj_column(b);
-        for (int a_ = lane; a_ <= b; a_ += TEAM) {
+        for (int a_ = lane; a_ <= b; a_ += 32) {
             double s = 0.0;
             for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
             w[a_] = s;
         }
-        sync();
+        SYNC();
         // r = R'^{-1} w[0..b): forward substitution, column oriented
         for (int k = 0; k < b; k++) {
-            double rk = w[k] / R(k, k);
-            sync();
-            if (lane == 0) R(k, b) = rk;
-            for (int i = k + 1 + lane; i < b; i += TEAM) w[i] -= R(k, i) * rk;
-            sync();
+            double rk = w[k] / R_(k, k);
+            SYNC();
+            if (lane == 0) R_(k, b) = rk;
+            for (int i = k + 1 + lane; i < b; i += 32) w[i] -= R_(k, i) * rk;
+            SYNC();
         }
         double rho2 = w[b];
-        for (int k = 0; k < b; k++) rho2 -= R(k, b) * R(k, b);
+        for (int k = 0; k < b; k++) rho2 -= R_(k, b) * R_(k, b);
         int ok = check_curvature ? (rho2 > QP_EPS_FLIP) : (rho2 > QP_ZERO);
-        sync();  // every lane has read w[b] / R(.,b) before a caller may overwrite them (team-uniform decision)
+        SYNC();  // every lane has read w[b] / R(.,b) before a caller may overwrite them (uniform decision)
         if (!ok) return 0;
-        if (lane == 0) R(b, b) = sqrt(rho2);
-        for (int a_ = lane; a_ < b; a_ += TEAM) R(b, a_) = 0.0;
-        sync();
+        if (lane == 0) R_(b, b) = sqrt(rho2);
+        for (int a_ = lane; a_ < b; a_ += 32) R_(b, a_) = 0.0;
+        SYNC();
         return 1;
     }
 
     // ---------------------------------------------------------------- working-set updates
-    __device__ QP_FN void constraint_w(int c, double& wz2, double& a2) {
-        int nZ = nFR - nAC;
-        for (int p = lane; p < nFR; p += TEAM) a[p] = A_entry(c, FR[p]);
-        sync();
-        for (int j = lane; j < nFR; j += TEAM) {
+    static __device__ QP_FN void constraint_w(int c, double& wz2, double& a2) {
+        QP_CTX QP_PAT
+        const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
+        double *a = V_(a), *w = V_(w);
+        const double *Q = V_(Q), *Av = V_(Av);
+        const short* FR = FR_;
+        for (int p = lane; p < nFR; p += 32) a[p] = A_entry(pat, Av, c, FR[p]);
+        SYNC();
+        for (int j = lane; j < nFR; j += 32) {
             double s = 0.0;
             for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * a[p];
             w[j] = s;
         }
-        sync();
+        SYNC();
         double s2 = 0.0, z2 = 0.0;
         for (int p = 0; p < nFR; p++) s2 += a[p] * a[p];
         for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
         wz2 = z2; a2 = s2;
-        sync();
+        SYNC();
     }
     // chain of rotations compressing w[0..cnt) into w[cnt-1]; writes (c,s) to t2,t3; returns r
-    __device__ QP_FN double rotation_chain(int cnt) {
-        double r = w[0];
+    static __device__ QP_FN double rotation_chain(int cnt) {
+        QP_CTX
+        double *t2 = V_(t2), *t3 = V_(t3);
+        const double* w = V_(w);
         if (lane == 0) {
             double a0 = w[0];
             for (int j = 0; j + 1 < cnt; j++) {
@@ -322,14 +350,16 @@ struct QPSolver {
             }
             t2[cnt - 1] = a0;
         }
-        sync();
-        r = t2[cnt - 1];
-        return r;
+        SYNC();
+        return t2[cnt - 1];
     }
-    __device__ QP_FN void add_constraint(int c, int status) {
-        int nZ = nFR - nAC;
+    static __device__ QP_FN void add_constraint(int c, int status) {
+        QP_CTX
+        const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
+        double *Q = V_(Q), *RT = V_(RT);
+        const double *t2 = V_(t2), *t3 = V_(t3), *w = V_(w);
         double r = rotation_chain(nZ);
-        for (int p = lane; p < nFR; p += TEAM) {
+        for (int p = lane; p < nFR; p += 32) {
             double* q = Q + p * ld;
             double qa = q[0];
             for (int j = 0; j + 1 < nZ; j++) {
@@ -339,55 +369,65 @@ struct QPSolver {
             }
             if (nZ > 0) q[nZ - 1] = qa;
         }
-        for (int j = lane; j < nFR; j += TEAM) T(nAC, j) = (j > nZ - 1) ? w[j] : ((j == nZ - 1) ? r : 0.0);
-        if (lane == 0) { AC[nAC] = (short)c; posAC[c] = (short)nAC; sC[c] = (short)status; }
-        nAC++;
-        sync();
+        for (int j = lane; j < nFR; j += 32) T_(nAC, j) = (j > nZ - 1) ? w[j] : ((j == nZ - 1) ? r : 0.0);
+        if (lane == 0) { AC_[nAC] = (short)c; posAC_[c] = (short)nAC; sC_[c] = (short)status; hdr[1] = nAC + 1; }
+        SYNC();
     }
-    __device__ QP_FN void remove_constraint(int c) {
-        int k = posAC[c];
+    static __device__ QP_FN void remove_constraint(int c) {
+        QP_CTX
+        const int nFR = hdr[0], nAC = hdr[1];
+        double *Q = V_(Q), *RT = V_(RT);
+        short *AC = AC_, *posAC = posAC_;
+        const int k = posAC[c];
         for (int i = k + 1; i < nAC; i++) {
             int cL = nFR - 1 - i;
             double cs, sn, r;
-            givens(T(i, cL), T(i, cL + 1), cs, sn, r);
-            sync();
-            for (int ii = i + lane; ii < nAC; ii += TEAM) {
-                double ta = T(ii, cL), tb = T(ii, cL + 1);
-                T(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
-                T(ii, cL + 1) = sn * ta + cs * tb;
+            givens(T_(i, cL), T_(i, cL + 1), cs, sn, r);
+            SYNC();
+            for (int ii = i + lane; ii < nAC; ii += 32) {
+                double ta = T_(ii, cL), tb = T_(ii, cL + 1);
+                T_(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
+                T_(ii, cL + 1) = sn * ta + cs * tb;
             }
-            for (int p = lane; p < nFR; p += TEAM) {
+            for (int p = lane; p < nFR; p += 32) {
                 double qa = Q[p * ld + cL], qb = Q[p * ld + cL + 1];
                 Q[p * ld + cL] = cs * qa - sn * qb;
                 Q[p * ld + cL + 1] = sn * qa + cs * qb;
             }
-            sync();
+            SYNC();
         }
         // shift rows k+1.. up by one (row i -> i-1): sequential over rows, lanes over columns
         for (int i = k + 1; i < nAC; i++) {
-            for (int j = lane; j < nFR; j += TEAM) T(i - 1, j) = T(i, j);
-            sync();
+            for (int j = lane; j < nFR; j += 32) T_(i - 1, j) = T_(i, j);
+            SYNC();
         }
         if (lane == 0) {
             for (int i = k + 1; i < nAC; i++) { AC[i - 1] = AC[i]; posAC[AC[i - 1]] = (short)(i - 1); }
-            sC[c] = 0; posAC[c] = -1;
+            sC_[c] = 0; posAC[c] = -1; hdr[1] = nAC - 1;
         }
-        nAC--;
-        sync();
+        SYNC();
     }
-    __device__ QP_FN double bound_w(int v) {
-        int nZ = nFR - nAC, p = posFR[v];
-        for (int j = lane; j < nFR; j += TEAM) w[j] = Q[p * ld + j];
-        sync();
+    static __device__ QP_FN double bound_w(int v) {
+        QP_CTX
+        const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC, p = posFR_[v];
+        double* w = V_(w);
+        const double* Q = V_(Q);
+        for (int j = lane; j < nFR; j += 32) w[j] = Q[p * ld + j];
+        SYNC();
         double z2 = 0.0;
         for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
-        sync();
+        SYNC();
         return z2;
     }
-    __device__ QP_FN void add_bound(int v, int status) {
-        int nZ = nFR - nAC, p = posFR[v];
+    static __device__ QP_FN void add_bound(int v, int status) {
+        QP_CTX
+        const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
+        double *Q = V_(Q), *RT = V_(RT);
+        const double *t2 = V_(t2), *t3 = V_(t3);
+        short *FR = FR_, *posFR = posFR_;
+        const int p = posFR[v];
         rotation_chain(nFR);
-        for (int pp = lane; pp < nFR; pp += TEAM) {
+        for (int pp = lane; pp < nFR; pp += 32) {
             double* q = Q + pp * ld;
             double qa = q[0];
             for (int j = 0; j + 1 < nFR; j++) {
@@ -398,183 +438,209 @@ struct QPSolver {
             q[nFR - 1] = qa;
         }
         // T rows: row i is touched by rotations j >= nFR-2-i (and j >= nZ-1)
-        for (int i = lane; i < nAC; i += TEAM) {
+        for (int i = lane; i < nAC; i += 32) {
             int j0 = nFR - 2 - i; if (j0 < nZ - 1) j0 = nZ - 1; if (j0 < 0) j0 = 0;
-            double ta = T(i, j0);
+            double ta = T_(i, j0);
             for (int j = j0; j + 1 < nFR; j++) {
-                double cs = t2[j], sn = t3[j], tb = T(i, j + 1);
-                T(i, j) = cs * ta - sn * tb;
+                double cs = t2[j], sn = t3[j], tb = T_(i, j + 1);
+                T_(i, j) = cs * ta - sn * tb;
                 ta = sn * ta + cs * tb;
             }
-            T(i, nFR - 1) = ta;
+            T_(i, nFR - 1) = ta;
         }
-        sync();
-        int last = nFR - 1;
+        SYNC();
+        const int last = nFR - 1;
         if (p != last) {
-            for (int j = lane; j < nFR - 1; j += TEAM) Q[p * ld + j] = Q[last * ld + j];
+            for (int j = lane; j < nFR - 1; j += 32) Q[p * ld + j] = Q[last * ld + j];
             if (lane == 0) { short vl = FR[last]; FR[p] = vl; posFR[vl] = (short)p; }
         }
-        if (lane == 0) { posFR[v] = -1; sB[v] = (short)status; }
-        nFR--;
-        sync();
+        if (lane == 0) { posFR[v] = -1; sB_[v] = (short)status; hdr[0] = nFR - 1; }
+        SYNC();
     }
-    __device__ QP_FN void remove_bound(int v) {
-        for (int j = lane; j < nFR; j += TEAM) { Q[nFR * ld + j] = 0.0; Q[j * ld + nFR] = 0.0; }
-        for (int i = lane; i < nAC; i += TEAM) {
+    static __device__ QP_FN void remove_bound(int v) {
+        QP_CTX QP_PAT
+        int nFR = hdr[0];
+        const int nAC = hdr[1];
+        double *Q = V_(Q), *RT = V_(RT);
+        const double* Av = V_(Av);
+        const short *Ap = pat + sA.pAp, *Ai = pat + sA.pAi;
+        const short* AC = AC_;
+        SYNC();  // all lanes have read hdr[0] before lane 0 updates it below
+        for (int j = lane; j < nFR; j += 32) { Q[nFR * ld + j] = 0.0; Q[j * ld + nFR] = 0.0; }
+        for (int i = lane; i < nAC; i += 32) {
             int r = AC[i];
             double s = 0.0;
             int e1 = Ap[v + 1];
             for (int e = Ap[v]; e < e1; e++)
                 if (Ai[e] == r) s += Av[e];
-            T(i, nFR) = s;
+            T_(i, nFR) = s;
         }
-        if (lane == 0) { Q[nFR * ld + nFR] = 1.0; FR[nFR] = (short)v; posFR[v] = (short)nFR; sB[v] = 0; }
+        if (lane == 0) { Q[nFR * ld + nFR] = 1.0; FR_[nFR] = (short)v; posFR_[v] = (short)nFR; sB_[v] = 0; hdr[0] = nFR + 1; }
         nFR++;
-        sync();
+        SYNC();
         for (int i = 0; i < nAC; i++) {
             int cL = nFR - 2 - i;
             double cs, sn, r;
-            givens(T(i, cL), T(i, cL + 1), cs, sn, r);
-            sync();
-            for (int ii = i + lane; ii < nAC; ii += TEAM) {
-                double ta = T(ii, cL), tb = T(ii, cL + 1);
-                T(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
-                T(ii, cL + 1) = sn * ta + cs * tb;
+            givens(T_(i, cL), T_(i, cL + 1), cs, sn, r);
+            SYNC();
+            for (int ii = i + lane; ii < nAC; ii += 32) {
+                double ta = T_(ii, cL), tb = T_(ii, cL + 1);
+                T_(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
+                T_(ii, cL + 1) = sn * ta + cs * tb;
             }
-            for (int p = lane; p < nFR; p += TEAM) {
+            for (int p = lane; p < nFR; p += 32) {
                 double qa = Q[p * ld + cL], qb = Q[p * ld + cL + 1];
                 Q[p * ld + cL] = cs * qa - sn * qb;
                 Q[p * ld + cL + 1] = sn * qa + cs * qb;
             }
-            sync();
+            SYNC();
         }
     }
 
     // ---------------------------------------------------------------- T solves
-    // T v = b : v indexed by Q column; row i has its diagonal at column nFR-1-i
-    __device__ QP_FN void solve_T(double* b, double* v) {  // b (by AC position) is destroyed
+    // T v = b : v indexed by Q column; row i has its diagonal at column nFR-1-i.  b (by AC position) is destroyed.
+    static __device__ QP_FN void solve_T(double* b, double* v) {
+        QP_CTX
+        const int nFR = hdr[0], nAC = hdr[1];
+        const double* RT = V_(RT);
         for (int i = 0; i < nAC; i++) {
             int d = nFR - 1 - i;
-            double vi = b[i] / T(i, d);
-            sync();
+            double vi = b[i] / T_(i, d);
+            SYNC();
             if (lane == 0) v[d] = vi;
-            for (int k = i + 1 + lane; k < nAC; k += TEAM) b[k] -= T(k, d) * vi;
-            sync();
+            for (int k = i + 1 + lane; k < nAC; k += 32) b[k] -= T_(k, d) * vi;
+            SYNC();
         }
     }
     // T' u = r : r indexed by Q column (destroyed), u by AC position
-    __device__ QP_FN void solve_Tt(double* r, double* u) {
+    static __device__ QP_FN void solve_Tt(double* r, double* u) {
+        QP_CTX
+        const int nFR = hdr[0], nAC = hdr[1];
+        const double* RT = V_(RT);
         for (int i = nAC - 1; i >= 0; i--) {
             int d = nFR - 1 - i;
-            double ui = r[d] / T(i, d);
-            sync();
+            double ui = r[d] / T_(i, d);
+            SYNC();
             if (lane == 0) u[i] = ui;
-            // r[d'] -= T(i, d') * u_i for the remaining unknowns k < i, i.e. columns d' = nFR-1-k > d
-            for (int k = lane; k < i; k += TEAM) { int dk = nFR - 1 - k; r[dk] -= T(i, dk) * ui; }
-            sync();
+            for (int k = lane; k < i; k += 32) { int dk = nFR - 1 - k; r[dk] -= T_(i, dk) * ui; }
+            SYNC();
         }
     }
 
     // ---------------------------------------------------------------- step direction
-    // dxFX: full-length vector holding the bound shift of every fixed variable; dbAC by AC position.
-    // dgv(i) is evaluated on the fly as gN[i]-g[i] when use_dg, else taken from `dgvec`.
-    __device__ QP_FN void step_direction(const double* dgvec, const double* dxFX, double* dbAC) {
-        int nZ = nFR - nAC;
-        for (int i = lane; i < nV; i += TEAM) dx[i] = (sB[i] != 0) ? dxFX[i] : 0.0;
-        sync();
+    // dxFX: full-length vector holding the bound shift of every fixed variable; dbAC by AC position; dgvec: gradient shift
+    static __device__ QP_FN void step_direction(const double* dgvec, const double* dxFX, double* dbAC) {
+        QP_CTX
+        const int nT = nV + nC;
+        const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
+        double *dx = V_(dx), *dy = V_(dy), *t1 = V_(t1), *t2 = V_(t2), *t3 = V_(t3), *yv = V_(yv), *zv = V_(zv);
+        const double *Q = V_(Q), *RT = V_(RT);
+        const short *sB = sB_, *FR = FR_, *AC = AC_;
+        for (int i = lane; i < nV; i += 32) dx[i] = (sB[i] != 0) ? dxFX[i] : 0.0;
+        SYNC();
         if (nAC > 0) {
             mulA(dx, t2);
-            for (int i = lane; i < nAC; i += TEAM) t3[i] = dbAC[i] - t2[AC[i]];
-            sync();
+            for (int i = lane; i < nAC; i += 32) t3[i] = dbAC[i] - t2[AC[i]];
+            SYNC();
             solve_T(t3, yv);
-            for (int p = lane; p < nFR; p += TEAM) {
+            for (int p = lane; p < nFR; p += 32) {
                 double s = 0.0;
                 for (int j = nZ; j < nFR; j++) s += Q[p * ld + j] * yv[j];
                 dx[FR[p]] = s;
             }
-            sync();
+            SYNC();
         }
         if (nZ > 0) {
             mulH(dx, t1);
-            for (int j = lane; j < nZ; j += TEAM) {
+            for (int j = lane; j < nZ; j += 32) {
                 double s = 0.0;
                 for (int p = 0; p < nFR; p++) { int v = FR[p]; s += Q[p * ld + j] * (t1[v] + dgvec[v]); }
                 zv[j] = -s;
             }
-            sync();
+            SYNC();
             // R' u = rhs (forward), R z = u (backward); column oriented
             for (int k = 0; k < nZ; k++) {
-                double uk = zv[k] / R(k, k);
-                sync();
+                double uk = zv[k] / R_(k, k);
+                SYNC();
                 if (lane == 0) zv[k] = uk;
-                for (int i = k + 1 + lane; i < nZ; i += TEAM) zv[i] -= R(k, i) * uk;
-                sync();
+                for (int i = k + 1 + lane; i < nZ; i += 32) zv[i] -= R_(k, i) * uk;
+                SYNC();
             }
             for (int k = nZ - 1; k >= 0; k--) {
-                double zk = zv[k] / R(k, k);
-                sync();
+                double zk = zv[k] / R_(k, k);
+                SYNC();
                 if (lane == 0) zv[k] = zk;
-                for (int i = lane; i < k; i += TEAM) zv[i] -= R(i, k) * zk;
-                sync();
+                for (int i = lane; i < k; i += 32) zv[i] -= R_(i, k) * zk;
+                SYNC();
             }
-            for (int p = lane; p < nFR; p += TEAM) {
+            for (int p = lane; p < nFR; p += 32) {
                 double s = 0.0;
                 for (int j = 0; j < nZ; j++) s += Q[p * ld + j] * zv[j];
                 dx[FR[p]] += s;
             }
-            sync();
+            SYNC();
         }
         mulH(dx, t1);
-        for (int i = lane; i < nV; i += TEAM) t1[i] += dgvec[i];
-        for (int i = lane; i < nT; i += TEAM) dy[i] = 0.0;
-        sync();
+        for (int i = lane; i < nV; i += 32) t1[i] += dgvec[i];
+        for (int i = lane; i < nT; i += 32) dy[i] = 0.0;
+        SYNC();
         if (nAC > 0) {
-            for (int j = nZ + lane; j < nFR; j += TEAM) {
+            for (int j = nZ + lane; j < nFR; j += 32) {
                 double s = 0.0;
                 for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * t1[FR[p]];
                 yv[j] = s;
             }
-            sync();
+            SYNC();
             solve_Tt(yv, t3);
-            for (int i = lane; i < nAC; i += TEAM) dy[nV + AC[i]] = t3[i];
-            sync();
+            for (int i = lane; i < nAC; i += 32) dy[nV + AC[i]] = t3[i];
+            SYNC();
             mulAT(dy + nV, t2);
-            for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) dy[i] = t1[i] - t2[i];
+            for (int i = lane; i < nV; i += 32) if (sB[i] != 0) dy[i] = t1[i] - t2[i];
         } else {
-            for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) dy[i] = t1[i];
+            for (int i = lane; i < nV; i += 32) if (sB[i] != 0) dy[i] = t1[i];
         }
-        sync();
+        SYNC();
     }
 
     // ---------------------------------------------------------------- drift correction / ramping
-    __device__ QP_FN void stationarity_gradient() {  // g = A'y_c + y_b - (H+regI) x
+    static __device__ QP_FN void stationarity_gradient() {  // g = A'y_c + y_b - (H+regI) x
+        QP_CTX
+        double *g = V_(g), *t1 = V_(t1), *t2 = V_(t2);
+        const double *x = V_(x), *y = V_(y);
         mulAT(y + nV, t2);
         mulH(x, t1);
-        for (int i = lane; i < nV; i += TEAM) g[i] = t2[i] + y[i] - t1[i];
-        sync();
+        for (int i = lane; i < nV; i += 32) g[i] = t2[i] + y[i] - t1[i];
+        SYNC();
     }
-    __device__ QP_FN void drift_correction() {
+    static __device__ QP_FN void drift_correction() {
+        QP_CTX
+        double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA);
+        const short *sB = sB_, *sC = sC_;
         mulA(x, Ax);
-        for (int i = lane; i < nV; i += TEAM) {
+        for (int i = lane; i < nV; i += 32) {
             int s = sB[i]; double xi = x[i];
             if (s < 0) { lb[i] = xi; if (ub[i] < xi) ub[i] = xi; if (y[i] < 0) y[i] = 0.0; }
             else if (s > 0) { ub[i] = xi; if (lb[i] > xi) lb[i] = xi; if (y[i] > 0) y[i] = 0.0; }
             else { if (lb[i] > xi) lb[i] = xi; if (ub[i] < xi) ub[i] = xi; y[i] = 0.0; }
         }
-        for (int i = lane; i < nC; i += TEAM) {
+        for (int i = lane; i < nC; i += 32) {
             int s = sC[i]; double ax = Ax[i];
             if (s < 0) { lbA[i] = ax; if (ubA[i] < ax) ubA[i] = ax; if (y[nV + i] < 0) y[nV + i] = 0.0; }
             else if (s > 0) { ubA[i] = ax; if (lbA[i] > ax) lbA[i] = ax; if (y[nV + i] > 0) y[nV + i] = 0.0; }
             else { if (lbA[i] > ax) lbA[i] = ax; if (ubA[i] < ax) ubA[i] = ax; y[nV + i] = 0.0; }
         }
-        sync();
+        SYNC();
         stationarity_gradient();
     }
-    __device__ QP_FN void ramping() {
-        int nRamp = nV + nC + nC + nV;
+    static __device__ QP_FN void ramping() {
+        QP_CTX
+        double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA);
+        const short *sB = sB_, *sC = sC_;
+        const int ramp_offset = hdr[2];
+        const int nRamp = nV + nC + nC + nV;
         const double r0 = 0.5, r1 = 1.0;
         mulA(x, Ax);
-        for (int i = lane; i < nV; i += TEAM) {
+        for (int i = lane; i < nV; i += 32) {
             double tP = (double)((i + ramp_offset) % nRamp) / (double)(nRamp - 1);
             double rP = (1.0 - tP) * r0 + tP * r1;
             double tD = (double)((nV + nC + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
@@ -588,7 +654,7 @@ struct QPSolver {
             if (s > 0) { ub[i] = xi; y[i] = -rD; }
             if (s == 0) y[i] = 0.0;
         }
-        for (int i = lane; i < nC; i += TEAM) {
+        for (int i = lane; i < nC; i += 32) {
             double tP = (double)((nV + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
             double rP = (1.0 - tP) * r0 + tP * r1;
             double tD = (double)((nV + nC + nV + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
@@ -602,76 +668,85 @@ struct QPSolver {
             if (s > 0) { ubA[i] = ax; y[nV + i] = -rD; }
             if (s == 0) y[nV + i] = 0.0;
         }
-        sync();
+        SYNC();
         stationarity_gradient();
-        ramp_offset++;
+        if (lane == 0) hdr[2] = ramp_offset + 1;
+        SYNC();
     }
 
     // ---------------------------------------------------------------- exchange (ensure LI)
     // element to add: constraint c (v<0) or bound v (c<0); w holds its Q-coordinates. 0 ok, 1 infeasible
-    __device__ QP_FN int ensure_li(int c, int v, int status) {
-        int nZ = nFR - nAC;
-        double* xiC = zv;
-        double* xiB = dx;
-        for (int j = nZ + lane; j < nFR; j += TEAM) yv[j] = w[j];
-        sync();
+    static __device__ QP_FN int ensure_li(int c, int v, int status) {
+        QP_CTX QP_PAT
+        const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
+        double *xiC = V_(zv), *xiB = V_(dx), *yv = V_(yv), *t2 = V_(t2), *t3 = V_(t3), *y = V_(y);
+        const double *w = V_(w), *Av = V_(Av);
+        const short *sB = sB_, *sC = sC_, *AC = AC_, *posAC = posAC_;
+        for (int j = nZ + lane; j < nFR; j += 32) yv[j] = w[j];
+        SYNC();
         solve_Tt(yv, xiC);
-        for (int i = lane; i < nC; i += TEAM) { int p = posAC[i]; t3[i] = (p >= 0) ? xiC[p] : 0.0; }
-        sync();
+        for (int i = lane; i < nC; i += 32) { int p = posAC[i]; t3[i] = (p >= 0) ? xiC[p] : 0.0; }
+        SYNC();
         mulAT(t3, t2);
-        for (int i = lane; i < nV; i += TEAM) {
+        for (int i = lane; i < nV; i += 32) {
             if (sB[i] == 0) { xiB[i] = 0.0; continue; }
-            double ai = (c >= 0) ? A_entry(c, i) : 0.0;
+            double ai = (c >= 0) ? A_entry(pat, Av, c, i) : 0.0;
             xiB[i] = ai - t2[i];
         }
-        sync();
-        double sgn = (status < 0) ? 1.0 : -1.0;
+        SYNC();
+        const double sgn = (status < 0) ? 1.0 : -1.0;
         double best = QP_INFTY; int bpos = 0x7fffffff;
-        for (int i = lane; i < nAC; i += TEAM) {
+        for (int i = lane; i < nAC; i += 32) {
             int ci = AC[i]; double xi = sgn * xiC[i], yy = y[nV + ci]; double t = QP_INFTY;
             if (sC[ci] < 0) { if (xi > QP_ZERO && yy >= 0.0) t = yy / xi; }
             else { if (xi < -QP_ZERO && yy <= 0.0) t = yy / xi; }
             if (t < QP_INFTY && key_less(t, i, best, bpos)) { best = t; bpos = i; }
         }
-        for (int i = lane; i < nV; i += TEAM) {
+        for (int i = lane; i < nV; i += 32) {
             if (sB[i] == 0) continue;
             double xi = sgn * xiB[i], yy = y[i]; double t = QP_INFTY;
             if (sB[i] < 0) { if (xi > QP_ZERO && yy >= 0.0) t = yy / xi; }
             else { if (xi < -QP_ZERO && yy <= 0.0) t = yy / xi; }
             if (t < QP_INFTY && key_less(t, nC + i, best, bpos)) { best = t; bpos = nC + i; }
         }
-        MinKey mk = team_min(best, bpos);
+        MinKey mk = warp_min(best, bpos);
         if (mk.pos == 0x7fffffff) return 1;
-        double ymin = mk.t;
-        int kind = mk.pos >= nC ? 1 : 0;
-        int idx = kind ? mk.pos - nC : AC[mk.pos];
-        for (int i = lane; i < nAC; i += TEAM) y[nV + AC[i]] -= ymin * sgn * xiC[i];
-        for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) y[i] -= ymin * sgn * xiB[i];
-        sync();
+        const double ymin = mk.t;
+        const int kind = mk.pos >= nC ? 1 : 0;
+        const int idx = kind ? mk.pos - nC : AC[mk.pos];
+        SYNC();
+        for (int i = lane; i < nAC; i += 32) y[nV + AC[i]] -= ymin * sgn * xiC[i];
+        for (int i = lane; i < nV; i += 32) if (sB[i] != 0) y[i] -= ymin * sgn * xiB[i];
+        SYNC();
         if (lane == 0) {
             if (c >= 0) y[nV + c] = sgn * ymin; else y[v] = sgn * ymin;
             if (kind == 0) y[nV + idx] = 0.0; else y[idx] = 0.0;
         }
-        sync();
+        SYNC();
         if (kind == 0) remove_constraint(idx); else remove_bound(idx);
         return 0;
     }
 
     // ---------------------------------------------------------------- homotopy
-    __device__ QP_FN int homotopy(int max_iter) {
+    static __device__ QP_FN int homotopy(int max_iter, int& iters) {
+        QP_CTX
+        const int nT = nV + nC;
+        const int flags = sA.flags;
+        double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *g = V_(g), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA);
+        double *dx = V_(dx), *dy = V_(dy), *dAx = V_(dAx), *w = V_(w), *a = V_(a);
+        const double *gN = V_(gN), *lbN = V_(lbN), *ubN = V_(ubN), *lbAN = V_(lbAN), *ubAN = V_(ubAN);
+        short *sB = sB_, *sC = sC_, *AC = AC_;
         iters = 0;
         for (int it = 0;; it++) {
-            // data shift: dg in `a`.. we keep dg in zv? -> use dedicated: t-vectors are busy, so dg lives in `a` (nT)
-            // w <- bound shift of fixed variables, yv <- constraint shift by AC position, a <- dg
-            for (int i = lane; i < nV; i += TEAM) {
+            const int nAC = hdr[1];
+            // w[0..nV) <- bound shift of fixed variables, w[nV..) <- constraint shift by AC position, a <- dg
+            for (int i = lane; i < nV; i += 32) {
                 int s = sB[i];
                 w[i] = s < 0 ? (lbN[i] - lb[i]) : (s > 0 ? (ubN[i] - ub[i]) : 0.0);
                 a[i] = gN[i] - g[i];
             }
-            sync();
-            // dbAC goes to the tail of `w` (entries nV..nV+nAC), nAC <= nC
-            for (int i = lane; i < nAC; i += TEAM) { int ci = AC[i]; w[nV + i] = sC[ci] < 0 ? (lbAN[ci] - lbA[ci]) : (ubAN[ci] - ubA[ci]); }
-            sync();
+            for (int i = lane; i < nAC; i += 32) { int ci = AC[i]; w[nV + i] = sC[ci] < 0 ? (lbAN[ci] - lbA[ci]) : (ubAN[ci] - ubA[ci]); }
+            SYNC();
             step_direction(a, w, w + nV);
             mulA(dx, dAx);
 
@@ -685,23 +760,23 @@ struct QPSolver {
             if (t_ < 1.0 && key_less(t_, (pos), best, bpos)) { best = t_; bpos = (pos); }         \
         }                                                                                         \
     }
-            for (int i = lane; i < nAC; i += TEAM) {
+            for (int i = lane; i < nAC; i += 32) {
                 int ci = AC[i];
                 if (sC[ci] < 0) CONSIDER(y[nV + ci], -dy[nV + ci], i) else CONSIDER(-y[nV + ci], dy[nV + ci], i)
             }
-            for (int i = lane; i < nV; i += TEAM) {
+            for (int i = lane; i < nV; i += 32) {
                 int s = sB[i];
                 if (s == 0) continue;
                 if (s < 0) CONSIDER(y[i], -dy[i], nC + i) else CONSIDER(-y[i], dy[i], nC + i)
             }
-            for (int i = lane; i < nC; i += TEAM) {
+            for (int i = lane; i < nC; i += 32) {
                 if (sC[i] != 0) continue;
                 double num = Ax[i] - lbA[i]; if (num < 0) num = 0;
                 CONSIDER(num, (lbAN[i] - lbA[i]) - dAx[i], nC + nV + i)
                 num = ubA[i] - Ax[i]; if (num < 0) num = 0;
                 CONSIDER(num, dAx[i] - (ubAN[i] - ubA[i]), nC + nV + nC + i)
             }
-            for (int i = lane; i < nV; i += TEAM) {
+            for (int i = lane; i < nV; i += 32) {
                 if (sB[i] != 0) continue;
                 double num = x[i] - lb[i]; if (num < 0) num = 0;
                 CONSIDER(num, (lbN[i] - lb[i]) - dx[i], 2 * nC + nV + nC + i)
@@ -709,7 +784,7 @@ struct QPSolver {
                 CONSIDER(num, dx[i] - (ubN[i] - ub[i]), 3 * nC + 2 * nV + i)
             }
 #undef CONSIDER
-            MinKey mk = team_min(best, bpos);
+            MinKey mk = warp_min(best, bpos);
             double tau = 1.0; int bc_idx = -1, bc_isbound = 0, bc_status = 0;
             if (mk.pos != 0x7fffffff) {
                 tau = mk.t;
@@ -721,48 +796,51 @@ struct QPSolver {
                 else if (p < 3 * nC + 2 * nV) { bc_idx = p - 3 * nC - nV; bc_isbound = 1; bc_status = -1; }
                 else { bc_idx = p - 3 * nC - 2 * nV; bc_isbound = 1; bc_status = 1; }
             }
+            SYNC();
             // ---- step
             if (bc_idx < 0) {
-                for (int i = lane; i < nV; i += TEAM) { x[i] += dx[i]; g[i] = gN[i]; lb[i] = lbN[i]; ub[i] = ubN[i]; }
-                for (int i = lane; i < nT; i += TEAM) y[i] += dy[i];
-                for (int i = lane; i < nC; i += TEAM) { Ax[i] += dAx[i]; lbA[i] = lbAN[i]; ubA[i] = ubAN[i]; }
-                sync();
+                for (int i = lane; i < nV; i += 32) { x[i] += dx[i]; g[i] = gN[i]; lb[i] = lbN[i]; ub[i] = ubN[i]; }
+                for (int i = lane; i < nT; i += 32) y[i] += dy[i];
+                for (int i = lane; i < nC; i += 32) { Ax[i] += dAx[i]; lbA[i] = lbAN[i]; ubA[i] = ubAN[i]; }
+                SYNC();
                 iters = it;
                 return ST_OPTIMAL;
             }
             if (it >= max_iter) { iters = it; return ST_HOMOTOPY; }
             if (tau > 0.0) {
-                for (int i = lane; i < nV; i += TEAM) {
+                for (int i = lane; i < nV; i += 32) {
                     x[i] += tau * dx[i]; g[i] += tau * a[i];
                     lb[i] += tau * (lbN[i] - lb[i]); ub[i] += tau * (ubN[i] - ub[i]);
                 }
-                for (int i = lane; i < nT; i += TEAM) y[i] += tau * dy[i];
-                for (int i = lane; i < nC; i += TEAM) {
+                for (int i = lane; i < nT; i += 32) y[i] += tau * dy[i];
+                for (int i = lane; i < nC; i += 32) {
                     Ax[i] += tau * dAx[i];
                     lbA[i] += tau * (lbAN[i] - lbA[i]); ubA[i] += tau * (ubAN[i] - ubA[i]);
                 }
-                sync();
+                SYNC();
             }
             // ---- change the working set
             if (bc_status == 0) {
                 int flipped = 0;
                 if (bc_isbound) {
                     int old = sB[bc_idx];
-                    sync();
+                    SYNC();
                     if (lane == 0) y[bc_idx] = 0.0;
+                    SYNC();
                     remove_bound(bc_idx);
                     if (!extend_R(flags & FLAG_FLIPPING)) {
                         if (!(flags & FLAG_FLIPPING)) { iters = it; return ST_UNBOUNDED; }
                         bound_w(bc_idx);
                         add_bound(bc_idx, -old);
                         if (lane == 0) { if (old < 0) ub[bc_idx] = x[bc_idx]; else lb[bc_idx] = x[bc_idx]; }
-                        sync();
+                        SYNC();
                         flipped = 1;
                     }
                 } else {
                     int old = sC[bc_idx];
-                    sync();
+                    SYNC();
                     if (lane == 0) y[nV + bc_idx] = 0.0;
+                    SYNC();
                     remove_constraint(bc_idx);
                     if (!extend_R(flags & FLAG_FLIPPING)) {
                         if (!(flags & FLAG_FLIPPING)) { iters = it; return ST_UNBOUNDED; }
@@ -770,7 +848,7 @@ struct QPSolver {
                         constraint_w(bc_idx, z2, a2);
                         add_constraint(bc_idx, -old);
                         if (lane == 0) { if (old < 0) ubA[bc_idx] = Ax[bc_idx]; else lbA[bc_idx] = Ax[bc_idx]; }
-                        sync();
+                        SYNC();
                         flipped = 1;
                     }
                 }
@@ -802,178 +880,203 @@ struct QPSolver {
     }
 
     // ---------------------------------------------------------------- cold start / refactorise
-    __device__ QP_FN void cold_start_state() {
-        nFR = 0; nAC = 0; ramp_offset = 0;
-        for (int i = lane; i < nV; i += TEAM) {
+    static __device__ QP_FN void cold_start_state() {
+        QP_CTX
+        double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *g = V_(g), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA);
+        short *sB = sB_, *sC = sC_, *posFR = posFR_, *posAC = posAC_;
+        for (int i = lane; i < nV; i += 32) {
             x[i] = 0.0; y[i] = 0.0; sB[i] = -1; posFR[i] = -1; g[i] = 0.0; lb[i] = 0.0; ub[i] = QP_BOUND_RELAX;
         }
-        for (int i = lane; i < nC; i += TEAM) {
+        for (int i = lane; i < nC; i += 32) {
             y[nV + i] = 0.0; sC[i] = 0; posAC[i] = -1; Ax[i] = 0.0; lbA[i] = -QP_BOUND_RELAX; ubA[i] = QP_BOUND_RELAX;
         }
-        sync();
+        if (lane == 0) { hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; }
+        SYNC();
     }
     // rebuild TQ and R for the kept working set with the new matrix values; 0 ok
-    __device__ QP_FN int refactorise() {
-        int nAC_old = nAC;
-        // remember (constraint, status) by AC position in t1/t3 tails is unsafe (used by callees): use yv/zv? also used.
-        // -> keep them in dAx (nC) and dy[nV..] (nC): neither is touched by constraint_w/add_constraint/recompute_R.
-        for (int i = lane; i < nAC_old; i += TEAM) { int ci = AC[i]; dAx[i] = (double)ci; dy[nV + i] = (double)sC[ci]; }
-        sync();
-        for (int k = lane; k < nFR * nFR; k += TEAM) { int i = k / nFR, j = k % nFR; Q[i * ld + j] = (i == j) ? 1.0 : 0.0; }
-        for (int i = lane; i < nAC_old; i += TEAM) { int ci = (int)dAx[i]; sC[ci] = 0; posAC[ci] = -1; }
-        nAC = 0;
-        sync();
+    static __device__ QP_FN int refactorise() {
+        QP_CTX
+        const int nFR = hdr[0], nAC_old = hdr[1];
+        double *Q = V_(Q), *dAx = V_(dAx), *dy = V_(dy), *y = V_(y);
+        short *sC = sC_, *AC = AC_, *posAC = posAC_;
+        // remember (constraint, status) by AC position in dAx (nC) and dy[nV..] (nC): neither is touched below
+        for (int i = lane; i < nAC_old; i += 32) { int ci = AC[i]; dAx[i] = (double)ci; dy[nV + i] = (double)sC[ci]; }
+        SYNC();
+        for (int k = lane; k < nFR * nFR; k += 32) { int i = k / nFR, j = k % nFR; Q[i * ld + j] = (i == j) ? 1.0 : 0.0; }
+        for (int i = lane; i < nAC_old; i += 32) { int ci = (int)dAx[i]; sC[ci] = 0; posAC[ci] = -1; }
+        if (lane == 0) hdr[1] = 0;
+        SYNC();
         for (int i = 0; i < nAC_old; i++) {
             int ci = (int)dAx[i]; int st = (int)dy[nV + i];
             double z2, a2;
             constraint_w(ci, z2, a2);
-            if (!(z2 > QP_EPS_LI * QP_EPS_LI * a2) || a2 == 0.0) { sync(); if (lane == 0) y[nV + ci] = 0.0; sync(); continue; }
+            if (!(z2 > QP_EPS_LI * QP_EPS_LI * a2) || a2 == 0.0) { if (lane == 0) y[nV + ci] = 0.0; SYNC(); continue; }
             add_constraint(ci, st);
         }
         return recompute_R();
     }
+
+    // ---------------------------------------------------------------- epilogue: objective + test_optimality
+    static __device__ QP_FN void epilogue(int b, int status, int total_iters) {
+        QP_CTX
+        const int nT = nV + nC;
+        double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *t1 = V_(t1), *t2 = V_(t2);
+        const double *gN = V_(gN), *lbN = V_(lbN), *ubN = V_(ubN), *lbAN = V_(lbAN), *ubAN = V_(ubAN);
+        const short *sB = sB_, *sC = sC_;
+        double* xo = sA.x + (size_t)b * nV;
+        double* yo = sA.y + (size_t)b * nT;
+        for (int i = lane; i < nV; i += 32) xo[i] = x[i];
+        for (int i = lane; i < nT; i += 32) yo[i] = y[i];
+        if (sA.wsB) for (int i = lane; i < nV; i += 32) sA.wsB[(size_t)b * nV + i] = (signed char)sB[i];
+        if (sA.wsC) for (int i = lane; i < nC; i += 32) sA.wsC[(size_t)b * nC + i] = (signed char)sC[i];
+        // Hx (unregularised) in t1, A x in Ax, A'y_c in t2
+        mulH_noreg(x, t1);
+        mulA(x, Ax);
+        mulAT(y + nV, t2);
+        if (lane == 0) {
+            const double SQRT_M_EPS = 1.0e-8;
+            double obj = 0.0;
+            for (int i = 0; i < nV; i++) obj += 0.5 * x[i] * t1[i];
+            for (int i = 0; i < nV; i++) obj += gN[i] * x[i];
+            sA.obj[b] = obj; sA.status[b] = status; sA.iters[b] = total_iters;
+            // qpOASESInterface::get_working_set + test_optimality (src/qpOASESInterface.cpp:835-895, 498-684),
+            // evaluated against the target data the caller supplied.
+            double primal = 0.0, dual = 0.0, compl_ = 0.0, stat = 0.0;
+            int* WB = sA.WB ? sA.WB + (size_t)b * nV : nullptr;
+            int* WC = sA.WC ? sA.WC + (size_t)b * nC : nullptr;
+            for (int i = 0; i < nV; i++) {
+                double xi = x[i];
+                primal += fmax(0.0, lbN[i] - xi);
+                primal += -fmin(0.0, ubN[i] - xi);
+            }
+            for (int i = 0; i < nC; i++) {
+                double ax = Ax[i];
+                primal += fmax(0.0, lbAN[i] - ax);
+                primal += -fmin(0.0, ubAN[i] - ax);
+            }
+            for (int i = 0; i < nV; i++) {
+                int s = sB[i], W; double xi = x[i], yi = y[i];
+                if (s > 0) W = (fabs(xi - lbN[i]) < SQRT_M_EPS) ? -99 : 1;
+                else if (s < 0) W = (fabs(xi - ubN[i]) < SQRT_M_EPS) ? -99 : -1;
+                else W = 0;
+                if (WB) WB[i] = W;
+                if (W == 0) dual += fabs(yi); else if (W == -1) dual += -fmin(0.0, yi); else if (W == 1) dual += fmax(0.0, yi);
+            }
+            for (int i = 0; i < nC; i++) {
+                int s = sC[i], W; double ax = Ax[i], yi = y[nV + i];
+                if (s > 0) W = (ax - lbAN[i] < SQRT_M_EPS) ? -99 : 1;       // :874 (comparison inside fabs)
+                else if (s < 0) W = (ax - ubAN[i] < SQRT_M_EPS) ? -99 : -1;  // :880
+                else W = 0;
+                if (WC) WC[i] = W;
+                if (W == 0) dual += fabs(yi); else if (W == -1) dual += -fmin(0.0, yi); else if (W == 1) dual += fmax(0.0, yi);
+            }
+            for (int i = 0; i < nV; i++) {
+                double gap = t2[i];
+                gap += y[i]; gap -= gN[i]; gap -= t1[i];
+                stat += fabs(gap);
+            }
+            for (int i = 0; i < nV; i++) {
+                int s = sB[i]; double xi = x[i], yi = y[i];
+                int W = (s > 0) ? ((fabs(xi - lbN[i]) < SQRT_M_EPS) ? -99 : 1) : (s < 0 ? ((fabs(xi - ubN[i]) < SQRT_M_EPS) ? -99 : -1) : 0);
+                if (W == 0) compl_ += fabs(yi); else if (W == -1) compl_ += fabs(yi * (xi - lbN[i])); else if (W == 1) compl_ += fabs(yi * (ubN[i] - xi));
+            }
+            for (int i = 0; i < nC; i++) {
+                int s = sC[i]; double ax = Ax[i], yi = y[nV + i];
+                int W = (s > 0) ? ((ax - lbAN[i] < SQRT_M_EPS) ? -99 : 1) : (s < 0 ? ((ax - ubAN[i] < SQRT_M_EPS) ? -99 : -1) : 0);
+                if (W == 0) compl_ += fabs(yi); else if (W == -1) compl_ += fabs(yi * (ax - lbAN[i])); else if (W == 1) compl_ += fabs(yi * (ubAN[i] - ax));
+            }
+            if (sA.kkt) {
+                double* k = sA.kkt + (size_t)b * 5;
+                k[0] = primal; k[1] = dual; k[2] = stat; k[3] = compl_; k[4] = compl_ + stat + dual + primal;
+            }
+            hdr[3] = (status == ST_OPTIMAL) ? 1 : 0;
+        }
+        SYNC();
+    }
 };
 
 // -------------------------------------------------------------------------------------------
-// kernel
+// kernel: one QP per warp, CTA_THREADS/32 QPs per CTA
 // -------------------------------------------------------------------------------------------
-template <int TEAM, int CTA_THREADS>
-__global__ void __launch_bounds__(CTA_THREADS) qp_solve_kernel(const QPKernelArgs A) {
-    extern __shared__ __align__(16) double smem[];
-    constexpr int TEAMS = CTA_THREADS / TEAM;
-    const int team_id = threadIdx.x / TEAM;
-    const int lane = threadIdx.x % TEAM;
+template <int CTA_THREADS>
+__global__ void __launch_bounds__(CTA_THREADS) qp_solve_kernel(const __grid_constant__ QPKernelArgs A) {
+    constexpr int TEAMS = CTA_THREADS / 32;
+    // stage the launch arguments and the 16-bit pattern once per CTA
+    {
+        const int* src = reinterpret_cast<const int*>(&A);
+        int* dst = reinterpret_cast<int*>(&sA);
+        for (int i = threadIdx.x; i < (int)(sizeof(QPKernelArgs) / 4); i += CTA_THREADS) dst[i] = src[i];
+        short* pat = reinterpret_cast<short*>(qp_smem + (size_t)TEAMS * A.slice_doubles);
+        const bool has_H = A.has_H && !A.is_lp;
+        for (int i = threadIdx.x; i <= A.nV; i += CTA_THREADS) { pat[A.pAp + i] = (short)A.Ap[i]; if (has_H) pat[A.pHp + i] = (short)A.Hp[i]; }
+        for (int i = threadIdx.x; i <= A.nC; i += CTA_THREADS) pat[A.pArp + i] = (short)A.Arp[i];
+        for (int i = threadIdx.x; i < A.zA; i += CTA_THREADS) { pat[A.pAi + i] = (short)A.Ai[i]; pat[A.pAci + i] = (short)A.Aci[i]; pat[A.pAperm + i] = (short)A.Aperm[i]; }
+        if (has_H) for (int i = threadIdx.x; i < A.zH; i += CTA_THREADS) pat[A.pHi + i] = (short)A.Hi[i];
+    }
+    __syncthreads();
+
+    const int team_id = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * TEAMS + team_id;
     if (b >= A.batch) return;
     if (A.mask && !A.mask[b]) return;
+    const int nV = A.nV, nC = A.nC;
+    double* slice = qp_smem + (size_t)team_id * A.slice_doubles;
+    int* hdr = reinterpret_cast<int*>(slice);
 
-    QPSolver<TEAM> S;
-    S.tm.lane = lane; S.tm.team_id = team_id; S.lane = lane;
-    S.nV = A.nV; S.nC = A.nC; S.nT = A.nV + A.nC; S.ld = A.ld;
-    S.is_lp = A.is_lp; S.has_H = A.has_H && !A.is_lp; S.flags = A.flags;
-    S.reg = A.is_lp ? QP_EPS_REG : 0.0;
-    S.Ap = A.Ap; S.Ai = A.Ai; S.Arp = A.Arp; S.Aci = A.Aci; S.Aperm = A.Aperm; S.Hp = A.Hp; S.Hi = A.Hi;
-    const int nV = A.nV, nC = A.nC, nT = nV + nC;
-    double* slice = smem + (size_t)team_id * A.slice_doubles;
-    S.carve(slice, A);
-    S.red = smem + (size_t)TEAMS * A.slice_doubles + team_id * 2 * (TEAM / 32 + 1);
-    S.gN = A.gN + (size_t)b * nV; S.lbN = A.lbN + (size_t)b * nV; S.ubN = A.ubN + (size_t)b * nV;
-    S.lbAN = A.lbAN + (size_t)b * nC; S.ubAN = A.ubAN + (size_t)b * nC;
-
-    int mode = A.inst_mode ? A.inst_mode[b] : A.mode;
-    int* hdr = A.state_hdr ? A.state_hdr + (size_t)b * 4 : nullptr;
-    if (mode != MODE_COLD && (!hdr || !hdr[3])) mode = MODE_COLD;
-
-    if (mode != MODE_COLD) {
+    int mode = A.mode;
+    if (mode != MODE_COLD) {  // restore the slice image of the previous solve
         const double* st = A.state + (size_t)b * A.slice_doubles;
-        for (int i = lane; i < A.slice_doubles; i += TEAM) slice[i] = st[i];
-        S.nFR = hdr[0]; S.nAC = hdr[1]; S.ramp_offset = hdr[2];
+        for (int i = lane; i < A.slice_doubles; i += 32) slice[i] = st[i];
+        __syncwarp();
+        if (!hdr[3]) mode = MODE_COLD;  // previous solve did not end optimal: plain re-init (handle_error)
+        __syncwarp();
     }
     if (mode != MODE_HOT_FIXED) {
         const double* av = A.Aval + (size_t)b * A.zA;
-        for (int i = lane; i < A.zA; i += TEAM) S.Av[i] = av[i];
-        if (S.has_H) {
+        for (int i = lane; i < A.zA; i += 32) slice[A.oAv + i] = av[i];
+        if (A.has_H && !A.is_lp) {
             const double* hv = A.Hval + (size_t)b * A.zH;
-            for (int i = lane; i < A.zH; i += TEAM) S.Hv[i] = hv[i];
+            for (int i = lane; i < A.zH; i += 32) slice[A.oHv + i] = hv[i];
         }
     }
-    S.sync();
-
-    int status;
-    int total_iters = 0;
-    if (mode == MODE_HOT_VARIED) {
-        if (S.refactorise()) mode = MODE_COLD;  // projected Hessian of the kept set not PD: cold start
-        else { S.drift_correction(); }
+    {  // target data of the homotopy
+        const double *gN = A.gN + (size_t)b * nV, *lbN = A.lbN + (size_t)b * nV, *ubN = A.ubN + (size_t)b * nV;
+        const double *lbAN = A.lbAN + (size_t)b * nC, *ubAN = A.ubAN + (size_t)b * nC;
+        // |v| > 1e20 is clamped to qpOASES's infinity, as the oracle does
+        for (int i = lane; i < nV; i += 32) {
+            slice[A.ogN + i] = gN[i];
+            slice[A.olbN + i] = fmin(fmax(lbN[i], -QP_INFTY), QP_INFTY);
+            slice[A.oubN + i] = fmin(fmax(ubN[i], -QP_INFTY), QP_INFTY);
+        }
+        for (int i = lane; i < nC; i += 32) {
+            slice[A.olbAN + i] = fmin(fmax(lbAN[i], -QP_INFTY), QP_INFTY);
+            slice[A.oubAN + i] = fmin(fmax(ubAN[i], -QP_INFTY), QP_INFTY);
+        }
     }
-    if (mode == MODE_COLD) S.cold_start_state();
-    status = S.homotopy(A.max_iter);
-    total_iters += S.iters;
+    __syncwarp();
+
+    int status, iters = 0, total_iters = 0;
+    if (mode == MODE_HOT_VARIED) {
+        if (QP::refactorise()) mode = MODE_COLD;  // projected Hessian of the kept set not PD: cold start
+        else QP::drift_correction();
+    }
+    if (mode == MODE_COLD) QP::cold_start_state();
+    status = QP::homotopy(A.max_iter, iters);
+    total_iters += iters;
     if (status != ST_OPTIMAL && mode != MODE_COLD) {
         // one-retry recovery of handle_error (src/qpOASESInterface.cpp:746-754): plain re-init
-        S.cold_start_state();
-        status = S.homotopy(A.max_iter);
-        total_iters += S.iters;
+        QP::cold_start_state();
+        status = QP::homotopy(A.max_iter, iters);
+        total_iters += iters;
     }
-
-    // ---------------- epilogue: results, working set, fused KKT residuals (test_optimality)
-    double* xo = A.x + (size_t)b * nV;
-    double* yo = A.y + (size_t)b * nT;
-    for (int i = lane; i < nV; i += TEAM) xo[i] = S.x[i];
-    for (int i = lane; i < nT; i += TEAM) yo[i] = S.y[i];
-    if (A.wsB) for (int i = lane; i < nV; i += TEAM) A.wsB[(size_t)b * nV + i] = (signed char)S.sB[i];
-    if (A.wsC) for (int i = lane; i < nC; i += TEAM) A.wsC[(size_t)b * nC + i] = (signed char)S.sC[i];
-
-    // objective 1/2 x'Hx + g'x with the unregularised H; Hx kept in t1 for the KKT residuals
-    {
-        double reg_save = S.reg; S.reg = 0.0;
-        S.mulH(S.x, S.t1);
-        S.reg = reg_save;
-        S.mulA(S.x, S.Ax);
-        S.mulAT(S.y + nV, S.t2);
-    }
-    if (lane == 0) {
-        const double SQRT_M_EPS = 1.0e-8;
-        double obj = 0.0;
-        for (int i = 0; i < nV; i++) obj += 0.5 * S.x[i] * S.t1[i];
-        for (int i = 0; i < nV; i++) obj += S.gN[i] * S.x[i];
-        A.obj[b] = obj; A.status[b] = status; A.iters[b] = total_iters;
-        // qpOASESInterface::get_working_set + test_optimality (src/qpOASESInterface.cpp:835-895, 498-684),
-        // evaluated against the target data the caller supplied.
-        double primal = 0.0, dual = 0.0, compl_ = 0.0, stat = 0.0;
-        int* WB = A.WB ? A.WB + (size_t)b * nV : nullptr;
-        int* WC = A.WC ? A.WC + (size_t)b * nC : nullptr;
-        for (int i = 0; i < nV; i++) {
-            double xi = S.x[i], l = S.lbN[i], u = S.ubN[i];
-            primal += fmax(0.0, l - xi);
-            primal += -fmin(0.0, u - xi);
-        }
-        for (int i = 0; i < nC; i++) {
-            double ax = S.Ax[i];
-            primal += fmax(0.0, S.lbAN[i] - ax);
-            primal += -fmin(0.0, S.ubAN[i] - ax);
-        }
-        for (int i = 0; i < nV; i++) {
-            int s = S.sB[i], W; double xi = S.x[i], yi = S.y[i];
-            if (s > 0) W = (fabs(xi - S.lbN[i]) < SQRT_M_EPS) ? -99 : 1;
-            else if (s < 0) W = (fabs(xi - S.ubN[i]) < SQRT_M_EPS) ? -99 : -1;
-            else W = 0;
-            if (WB) WB[i] = W;
-            if (W == 0) dual += fabs(yi); else if (W == -1) dual += -fmin(0.0, yi); else if (W == 1) dual += fmax(0.0, yi);
-        }
-        for (int i = 0; i < nC; i++) {
-            int s = S.sC[i], W; double ax = S.Ax[i], yi = S.y[nV + i];
-            if (s > 0) W = (ax - S.lbAN[i] < SQRT_M_EPS) ? -99 : 1;      // :874 (comparison inside fabs)
-            else if (s < 0) W = (ax - S.ubAN[i] < SQRT_M_EPS) ? -99 : -1; // :880
-            else W = 0;
-            if (WC) WC[i] = W;
-            if (W == 0) dual += fabs(yi); else if (W == -1) dual += -fmin(0.0, yi); else if (W == 1) dual += fmax(0.0, yi);
-        }
-        for (int i = 0; i < nV; i++) {
-            double gap = S.t2[i];
-            gap += S.y[i]; gap -= S.gN[i]; gap -= S.t1[i];
-            stat += fabs(gap);
-        }
-        for (int i = 0; i < nV; i++) {
-            int s = S.sB[i]; double xi = S.x[i], yi = S.y[i];
-            int W = (s > 0) ? ((fabs(xi - S.lbN[i]) < SQRT_M_EPS) ? -99 : 1) : (s < 0 ? ((fabs(xi - S.ubN[i]) < SQRT_M_EPS) ? -99 : -1) : 0);
-            if (W == 0) compl_ += fabs(yi); else if (W == -1) compl_ += fabs(yi * (xi - S.lbN[i])); else if (W == 1) compl_ += fabs(yi * (S.ubN[i] - xi));
-        }
-        for (int i = 0; i < nC; i++) {
-            int s = S.sC[i]; double ax = S.Ax[i], yi = S.y[nV + i];
-            int W = (s > 0) ? ((ax - S.lbAN[i] < SQRT_M_EPS) ? -99 : 1) : (s < 0 ? ((ax - S.ubAN[i] < SQRT_M_EPS) ? -99 : -1) : 0);
-            if (W == 0) compl_ += fabs(yi); else if (W == -1) compl_ += fabs(yi * (ax - S.lbAN[i])); else if (W == 1) compl_ += fabs(yi * (S.ubAN[i] - ax));
-        }
-        if (A.kkt) {
-            double* k = A.kkt + (size_t)b * 5;
-            k[0] = primal; k[1] = dual; k[2] = stat; k[3] = compl_; k[4] = compl_ + stat + dual + primal;
-        }
-    }
-    S.sync();
+    QP::epilogue(b, status, total_iters);
     if ((A.flags & FLAG_KEEP_STATE) && A.state) {
         double* st = A.state + (size_t)b * A.slice_doubles;
-        for (int i = lane; i < A.slice_doubles; i += TEAM) st[i] = slice[i];
-        if (lane == 0) { hdr[0] = S.nFR; hdr[1] = S.nAC; hdr[2] = S.ramp_offset; hdr[3] = (status == ST_OPTIMAL) ? 1 : 0; }
+        for (int i = lane; i < A.slice_doubles; i += 32) st[i] = slice[i];
     }
 }
+
+#endif  // __CUDACC__
 
 }  // namespace sqpb200

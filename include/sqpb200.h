@@ -75,8 +75,11 @@ typedef struct {
     int enable_flipping; /* 1 */
     int enable_ramping;  /* 1 */
     int enable_drift;    /* 1 */
-    int team_size;       /* threads cooperating on one QP: 0 = choose from (nV, nC); 32..256 */
+    int team_size;       /* threads cooperating on one QP: 0 = auto; only 32 (one warp per QP) is built this round */
     int keep_state;      /* 1: keep working set + factors resident for hot starts */
+    int factor_cap;      /* capacity of the TQ/Cholesky factors = max. simultaneously free variables held in shared
+                            memory: 0 = auto (n + m/2 + 2 for nV = n + 2m), -1 = nV.  Instances that need more are
+                            re-solved with capacity nV by a rescue launch: the value affects speed, not results. */
 } sqpb200_options;
 
 void sqpb200_default_options(sqpb200_options* o);

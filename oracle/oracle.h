@@ -147,6 +147,7 @@ int orc_qp_solve_batch(int B, int nV, int nC, const int* Hp, const int* Hi, cons
                        int max_iter, double* x, double* y, double* obj, int* status, int* iters, int nthreads);
 /* flop counter for the roofline model of SURVEY.md section 8(d) */
 double orc_qp_get_flops(const orc_qp* q);
+int orc_qp_get_max_free(const orc_qp* q);
 
 #ifdef __cplusplus
 }

@@ -64,7 +64,7 @@ struct orc_qp {
     double *Q, *T, *R;                     /* ld = nV */
     /* work */
     double *dx, *dy, *dAx, *t1, *t2, *t3, *w, *a, *yv, *zv, *xiC, *xiB, *dg, *dlb, *dub, *dlbA, *dubA;
-    int status, iters, initialised, ramp_offset;
+    int status, iters, initialised, ramp_offset, max_nFR;
     double flops;
     int verbose;
 };
@@ -324,6 +324,7 @@ static void remove_bound(orc_qp* q, int v) {
     q->Q[(size_t)nFR * nV + nFR] = 1.0;
     for (int i = 0; i < nAC; i++) q->T[(size_t)i * nV + nFR] = q->Ad[(size_t)q->AC[i] * nV + v];
     q->FR[nFR] = v; q->posFR[v] = nFR; nFR++; q->nFR = nFR; q->sB[v] = 0;
+    if (nFR > q->max_nFR) q->max_nFR = nFR;
     for (int i = 0; i < nAC; i++) {
         int cL = nFR - 2 - i;
         givens(q->T[(size_t)i * nV + cL], q->T[(size_t)i * nV + cL + 1], &cs, &sn, &r);
@@ -785,3 +786,5 @@ void orc_qp_get_working_set(const orc_qp* q, int* raw_b, int* raw_c) {
 }
 
 double orc_qp_get_flops(const orc_qp* q) { return q->flops; }
+/* largest number of free variables seen since creation (sizes the factors of the CUDA kernel) */
+int orc_qp_get_max_free(const orc_qp* q) { return q->max_nFR; }

@@ -33,7 +33,7 @@ EXPORTS = [
 class Options(C.Structure):
     _fields_ = [("qp_maxiter", C.c_int), ("lp_maxiter", C.c_int), ("enable_flipping", C.c_int),
                 ("enable_ramping", C.c_int), ("enable_drift", C.c_int), ("team_size", C.c_int),
-                ("keep_state", C.c_int)]
+                ("keep_state", C.c_int), ("factor_cap", C.c_int)]
 
 
 _LIB = None

@@ -27,6 +27,8 @@ using namespace sqpb200;
 
 enum { MS_UNDEFINED = -1, MS_FIXED = 0, MS_VARIED = 1 };
 
+struct SolveCfg { int cap = 0, teams = 0, smem = 0, slice_doubles = 0, state_doubles = 0, resident = 0; };
+
 struct sqpb200_handle_s {
     int batch = 0, nV = 0, nC = 0, qptype = SQPB200_QP, device = 0;
     sqpb200_options opt;
@@ -60,6 +62,8 @@ struct sqpb200_handle_s {
     float last_ms = 0.f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int team = 0, teams_per_cta = 0, smem_cta = 0;
+    SolveCfg cfg_main, cfg_rescue;
+    bool have_rescue = false;
 };
 
 static int grid_for(long long total, int block) {
@@ -110,6 +114,7 @@ void sqpb200_default_options(sqpb200_options* o) {
     o->enable_drift = 1;
     o->team_size = 0;
     o->keep_state = 1;
+    o->factor_cap = 0;
 }
 
 const char* sqpb200_version(void) { return "sqpb200 0.1 (sm_100a)"; }
@@ -527,24 +532,20 @@ int sqpb200_qphandler_g(sqpb200_handle h, int n, int m, const double* grad, cons
 }
 
 // ------------------------------------------------------------------------------ solve
-static void fill_dims(sqpb200_handle h, QPKernelArgs& a) {
+static void fill_dims(sqpb200_handle h, QPKernelArgs& a, int cap) {
     memset(&a, 0, sizeof a);
-    a.batch = h->batch; a.nV = h->nV; a.nC = h->nC; a.ld = h->ld;
+    a.batch = h->batch; a.nV = h->nV; a.nC = h->nC; a.cap = cap;
     a.is_lp = (h->qptype == SQPB200_LP); a.has_H = !a.is_lp;
     a.zA = h->zA; a.zH = a.is_lp ? 0 : h->zH;  // an LP handle never holds H (src/qpOASESInterface.cpp:122-124)
     qp_fill_layout(a);
 }
 
-static int choose_config(sqpb200_handle h) {
+// QPs (warps) per CTA in {4, 2, 1} for a given factor capacity: the one that keeps the most QPs resident per SM.
+static bool config_for_cap(sqpb200_handle h, int cap, SolveCfg& cfg) {
     QPKernelArgs a;
-    fill_dims(h, a);
-    if (h->zA >= 32768 || h->zH >= 32768) { h->err = "pattern too large for 16-bit staged indices"; return SQPB200_ERR_TOO_LARGE; }
-    h->slice_doubles = a.slice_doubles;
+    fill_dims(h, a, cap);
     const size_t slice_bytes = (size_t)a.slice_doubles * 8, pat_bytes = (size_t)a.pat_shorts * 2;
     const size_t SMEM_MAX = 227 * 1024, SMEM_SM = 228 * 1024;
-    // One warp per QP: the only team size shipped this round (see the note in qp_kernel.cuh).
-    if (h->opt.team_size != 0 && h->opt.team_size != 32) { h->err = "team_size must be 0 (auto) or 32"; return SQPB200_ERR_INVALID; }
-    // QPs (warps) per CTA in {4, 2, 1}: take the one that keeps the most QPs resident per SM
     int best_teams = 0;
     size_t best_res = 0;
     for (int teams = 4; teams >= 1; teams >>= 1) {
@@ -556,20 +557,47 @@ static int choose_config(sqpb200_handle h) {
         if (res > 64) res = 64;  // 64 warps per SM
         if (res > best_res) { best_res = res; best_teams = teams; }
     }
-    if (best_teams == 0) {
-        h->err = "QP too large for the shared-memory resident kernel (nV=" + std::to_string(h->nV) + ", " +
-                 std::to_string(slice_bytes) + " B per QP)";
+    cfg.cap = a.cap; cfg.teams = best_teams; cfg.smem = (int)((size_t)best_teams * slice_bytes + pat_bytes);
+    cfg.slice_doubles = a.slice_doubles; cfg.state_doubles = a.state_doubles; cfg.resident = (int)best_res;
+    return best_teams > 0;
+}
+
+static int choose_config(sqpb200_handle h) {
+    if (h->zA >= 32768 || h->zH >= 32768) { h->err = "pattern too large for 16-bit staged indices"; return SQPB200_ERR_TOO_LARGE; }
+    // One warp per QP: the only team size shipped this round (see the note in qp_kernel.cuh).
+    if (h->opt.team_size != 0 && h->opt.team_size != 32) { h->err = "team_size must be 0 (auto) or 32"; return SQPB200_ERR_INVALID; }
+    const int nV = h->nV, nC = h->nC;
+    // Factor capacity.  On the l1-penalty QPs of RestartSQP (x = [p; u; v], nV = n + 2m) the number of simultaneously free
+    // variables stays near n: slacks are free only on violated rows.  auto: n + ceil(m/2) + 2; instances that need more are
+    // re-solved by the rescue launch with the full capacity nV, so the choice only affects speed, never results.
+    int cap = h->opt.factor_cap;
+    if (cap == 0) {
+        int n_est = (nV >= 2 * nC) ? nV - 2 * nC : nV;
+        cap = n_est + (nC + 1) / 2 + 2;
+    }
+    if (cap < 0 || cap > nV) cap = nV;
+    h->have_rescue = config_for_cap(h, nV, h->cfg_rescue);
+    if (!config_for_cap(h, cap, h->cfg_main)) {
+        h->err = "QP too large for the shared-memory resident kernel (nV=" + std::to_string(nV) + ", capacity " + std::to_string(cap) + ")";
         return SQPB200_ERR_TOO_LARGE;
     }
-    h->team = 32; h->teams_per_cta = best_teams; h->smem_cta = (int)((size_t)best_teams * slice_bytes + pat_bytes);
+    h->team = 32; h->teams_per_cta = h->cfg_main.teams; h->smem_cta = h->cfg_main.smem;
+    h->slice_doubles = h->cfg_main.slice_doubles;
     return 0;
 }
 
-// one object file per team size (qp_solve_inst.cu)
+// one object file per CTA size (qp_solve_inst.cu)
 namespace sqpb200 {
 cudaError_t launch_qp_solve_32_128(const QPKernelArgs&, int, cudaStream_t);
 cudaError_t launch_qp_solve_32_64(const QPKernelArgs&, int, cudaStream_t);
 cudaError_t launch_qp_solve_32_32(const QPKernelArgs&, int, cudaStream_t);
+}
+static cudaError_t launch_cfg(const SolveCfg& cfg, const QPKernelArgs& a, cudaStream_t stream) {
+    switch (cfg.teams) {
+    case 4: return launch_qp_solve_32_128(a, cfg.smem, stream);
+    case 2: return launch_qp_solve_32_64(a, cfg.smem, stream);
+    default: return launch_qp_solve_32_32(a, cfg.smem, stream);
+    }
 }
 
 int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask) {
@@ -582,7 +610,7 @@ int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned cha
     int rc = choose_config(h);
     if (rc) return rc;
     if (h->opt.keep_state && !h->dstate) {
-        if (dev_alloc(h, &h->dstate, (size_t)h->batch * h->slice_doubles)) return SQPB200_ERR_CUDA;
+        if (dev_alloc(h, &h->dstate, (size_t)h->batch * h->cfg_main.state_doubles)) return SQPB200_ERR_CUDA;
     }
     // init / hotstart decision: src/qpOASESInterface.cpp:141-211 with get_Matrix_change_status :817-833
     int mode = MODE_COLD;
@@ -599,7 +627,7 @@ int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned cha
         }
     }
     QPKernelArgs a;
-    fill_dims(h, a);
+    fill_dims(h, a, h->cfg_main.cap);
     a.max_iter = maxiter > 0 ? maxiter : (is_lp ? h->opt.lp_maxiter : h->opt.qp_maxiter);
     a.flags = (h->opt.enable_flipping ? FLAG_FLIPPING : 0) | (h->opt.enable_ramping ? FLAG_RAMPING : 0) |
               (h->opt.enable_drift ? FLAG_DRIFT : 0) | (h->opt.keep_state ? FLAG_KEEP_STATE : 0);
@@ -616,13 +644,20 @@ int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned cha
     a.wsB = h->dwsB; a.wsC = h->dwsC; a.WB = h->dWB; a.WC = h->dWC;
     a.state = h->dstate;
     CK(cudaEventRecord(h->ev0, h->stream));
-    cudaError_t e;
-    switch (h->teams_per_cta) {
-    case 4: e = launch_qp_solve_32_128(a, h->smem_cta, h->stream); break;
-    case 2: e = launch_qp_solve_32_64(a, h->smem_cta, h->stream); break;
-    default: e = launch_qp_solve_32_32(a, h->smem_cta, h->stream); break;
-    }
+    cudaError_t e = launch_cfg(h->cfg_main, a, h->stream);
     if (e != cudaSuccess) { h->err = std::string("qp_solve_kernel launch: ") + cudaGetErrorString(e); return SQPB200_ERR_CUDA; }
+    if (h->cfg_main.cap < h->nV) {
+        // rescue launch: instances that needed more free variables than the capacity are re-solved from their pre-solve
+        // state with the full-size factors; every other warp exits at once.  No host synchronisation in between.
+        QPKernelArgs r = a;
+        r.cap = h->nV; r.rescue = 1;
+        qp_fill_layout(r);
+        if (h->have_rescue) {
+            e = launch_cfg(h->cfg_rescue, r, h->stream);
+            if (e != cudaSuccess) { h->err = std::string("qp_solve_kernel rescue launch: ") + cudaGetErrorString(e); return SQPB200_ERR_CUDA; }
+            h->launches++;
+        }
+    }
     CK(cudaEventRecord(h->ev1, h->stream));
     h->launches++;
     // reset_flags(): src/qpOASESInterface.cpp:488-496

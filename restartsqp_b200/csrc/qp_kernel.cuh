@@ -46,12 +46,15 @@ namespace sqpb200 {
 #define QP_EPS_REG (1.0e3 * QP_EPS)
 #define QP_EPS_LI (1.0e5 * QP_EPS)
 
-enum { ST_OPTIMAL = 20, ST_INTERNAL = 21, ST_INFEASIBLE = 22, ST_UNBOUNDED = 23, ST_NOTINIT = 25, ST_HOMOTOPY = 28 };
+enum { ST_OPTIMAL = 20, ST_INTERNAL = 21, ST_INFEASIBLE = 22, ST_UNBOUNDED = 23, ST_NOTINIT = 25, ST_HOMOTOPY = 28,
+       ST_CAPACITY = 31 /* internal: factor capacity exceeded, instance is re-solved by the rescue launch */ };
 enum { MODE_COLD = 0, MODE_HOT_FIXED = 1, MODE_HOT_VARIED = 2 };
 enum { FLAG_FLIPPING = 1, FLAG_RAMPING = 2, FLAG_DRIFT = 4, FLAG_KEEP_STATE = 8 };
 
 struct QPKernelArgs {
-    int batch, nV, nC, ld;
+    int batch, nV, nC;
+    int cap, ld;      // factor capacity (max simultaneously free variables) and its odd leading dimension
+    int rescue;       // 1: only instances whose status is ST_CAPACITY are (re)solved, from their pre-solve state
     int is_lp, has_H;
     int max_iter, flags, mode;
     int zA, zH;
@@ -68,8 +71,9 @@ struct QPKernelArgs {
     int *status, *iters;
     signed char *wsB, *wsC;  // raw working set (+1 upper, -1 lower, 0 inactive)
     int *WB, *WC;            // translated ActiveType
-    // resident hot-start state: [batch][slice_doubles] images of the shared-memory slice
+    // resident hot-start state: [batch][state_doubles]: the slice without its factors, then Q, R, T packed
     double* state;
+    int state_doubles;
     int slice_doubles;  // doubles per QP slice
     int pat_shorts;     // 16-bit words of the staged pattern
     // slice layout: offsets in doubles from the slice base (filled by qp_fill_layout)
@@ -81,11 +85,13 @@ struct QPKernelArgs {
 };
 
 // Slice layout of one QP in shared memory.  Header (2 doubles = 4 ints): nFR, nAC, ramp_offset, initialised.
+// The factors come last and are sized by the capacity `cap` <= nV (the number of simultaneously free variables
+// stays far below nV on l1-penalty QPs: most slacks sit at zero), which is what sets the occupancy.
 __host__ __device__ inline void qp_fill_layout(QPKernelArgs& a) {
-    const int nV = a.nV, nC = a.nC, nT = nV + nC, ld = a.ld;
+    const int nV = a.nV, nC = a.nC, nT = nV + nC;
+    if (a.cap <= 0 || a.cap > nV) a.cap = nV;
+    a.ld = (a.cap % 2 == 0) ? a.cap + 1 : a.cap;  // odd: conflict-free row and column walks
     int o = 2;
-    a.oQ = o; o += nV * ld;
-    a.oRT = o; o += nV * ld;
     a.ox = o; o += nV; a.og = o; o += nV; a.olb = o; o += nV; a.oub = o; o += nV; a.odx = o; o += nV;
     a.ogN = o; o += nV; a.olbN = o; o += nV; a.oubN = o; o += nV;
     a.oAx = o; o += nC; a.olbA = o; o += nC; a.oubA = o; o += nC; a.odAx = o; o += nC;
@@ -96,7 +102,10 @@ __host__ __device__ inline void qp_fill_layout(QPKernelArgs& a) {
     a.oS = o;
     const int shorts = 3 * nV + 3 * nC;
     o += (shorts * 2 + 7) / 8;
+    a.oQ = o; o += a.cap * a.ld;
+    a.oRT = o; o += a.cap * a.ld;
     a.slice_doubles = o;
+    a.state_doubles = a.oQ + 2 * nV * nV;  // capacity-independent image
     int p = 0;
     a.pAp = p; p += nV + 1; a.pAi = p; p += a.zA; a.pArp = p; p += nC + 1; a.pAci = p; p += a.zA; a.pAperm = p; p += a.zA;
     a.pHp = p; p += nV + 1; a.pHi = p; p += a.zH;
@@ -122,8 +131,8 @@ __device__ __forceinline__ bool key_less(double t1, int p1, double t2, int p2) {
     const int lane = threadIdx.x & 31;                                                             \
     double* const slice = qp_smem + (size_t)(threadIdx.x >> 5) * sA.slice_doubles;                 \
     int* const hdr = reinterpret_cast<int*>(slice);                                                \
-    const int nV = sA.nV, nC = sA.nC, ld = sA.ld;                                                  \
-    (void)lane; (void)hdr; (void)nV; (void)nC; (void)ld;
+    const int nV = sA.nV, nC = sA.nC, ld = sA.ld, cap = sA.cap;                                    \
+    (void)lane; (void)hdr; (void)nV; (void)nC; (void)ld; (void)cap;
 #define QP_PAT const short* const pat = reinterpret_cast<const short*>(qp_smem + (size_t)(blockDim.x >> 5) * sA.slice_doubles);
 
 #define V_(name) (slice + sA.o##name)
@@ -135,7 +144,7 @@ __device__ __forceinline__ bool key_less(double t1, int p1, double t2, int p2) {
 #define AC_ S_(3 * nV + nC)
 #define posAC_ S_(3 * nV + 2 * nC)
 #define R_(a_, b_) RT[(a_) * ld + (b_)]
-#define T_(i, j) RT[(nV - 1 - (i)) * ld + (j)]
+#define T_(i, j) RT[(cap - 1 - (i)) * ld + (j)]
 #define SYNC() __syncwarp()
 
 struct QP {
@@ -146,11 +155,11 @@ struct QP {
         const double* Hv = V_(Hv);
         const bool has_H = sA.has_H && !sA.is_lp;
         const double reg = sA.is_lp ? QP_EPS_REG : 0.0;
-        for (int c = lane; c < nV; c += 32) {
+        _Pragma("unroll 1") for (int c = lane; c < nV; c += 32) {
             double s = 0.0;
             if (has_H) {
                 int e1 = Hp[c + 1];
-                for (int e = Hp[c]; e < e1; e++) s += Hv[e] * v[Hi[e]];
+                _Pragma("unroll 1") for (int e = Hp[c]; e < e1; e++) s += Hv[e] * v[Hi[e]];
             }
             if (reg != 0.0) s += reg * v[c];
             out[c] = s;
@@ -162,11 +171,11 @@ struct QP {
         const short *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
         const double* Hv = V_(Hv);
         const bool has_H = sA.has_H && !sA.is_lp;
-        for (int c = lane; c < nV; c += 32) {
+        _Pragma("unroll 1") for (int c = lane; c < nV; c += 32) {
             double s = 0.0;
             if (has_H) {
                 int e1 = Hp[c + 1];
-                for (int e = Hp[c]; e < e1; e++) s += Hv[e] * v[Hi[e]];
+                _Pragma("unroll 1") for (int e = Hp[c]; e < e1; e++) s += Hv[e] * v[Hi[e]];
             }
             out[c] = s;
         }
@@ -176,10 +185,10 @@ struct QP {
         QP_CTX QP_PAT
         const short *Arp = pat + sA.pArp, *Aci = pat + sA.pAci, *Aperm = pat + sA.pAperm;
         const double* Av = V_(Av);
-        for (int r = lane; r < nC; r += 32) {
+        _Pragma("unroll 1") for (int r = lane; r < nC; r += 32) {
             double s = 0.0;
             int k1 = Arp[r + 1];
-            for (int k = Arp[r]; k < k1; k++) s += Av[Aperm[k]] * v[Aci[k]];
+            _Pragma("unroll 1") for (int k = Arp[r]; k < k1; k++) s += Av[Aperm[k]] * v[Aci[k]];
             out[r] = s;
         }
         SYNC();
@@ -188,10 +197,10 @@ struct QP {
         QP_CTX QP_PAT
         const short *Ap = pat + sA.pAp, *Ai = pat + sA.pAi;
         const double* Av = V_(Av);
-        for (int c = lane; c < nV; c += 32) {
+        _Pragma("unroll 1") for (int c = lane; c < nV; c += 32) {
             double s = 0.0;
             int e1 = Ap[c + 1];
-            for (int e = Ap[c]; e < e1; e++) s += Av[e] * yc[Ai[e]];
+            _Pragma("unroll 1") for (int e = Ap[c]; e < e1; e++) s += Av[e] * yc[Ai[e]];
             out[c] = s;
         }
         SYNC();
@@ -201,7 +210,7 @@ struct QP {
         const short *Arp = pat + sA.pArp, *Aci = pat + sA.pAci, *Aperm = pat + sA.pAperm;
         double s = 0.0;
         int k1 = Arp[r + 1];
-        for (int k = Arp[r]; k < k1; k++)
+        _Pragma("unroll 1") for (int k = Arp[r]; k < k1; k++)
             if (Aci[k] == c) s += Av[Aperm[k]];
         return s;
     }
@@ -209,7 +218,7 @@ struct QP {
     // ---------------------------------------------------------------- reductions
     static __device__ __forceinline__ MinKey warp_min(double t, int pos) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        _Pragma("unroll 1") for (int o = 16; o > 0; o >>= 1) {
             double t2_ = __shfl_xor_sync(0xffffffffu, t, o);
             int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
             if (key_less(t2_, p2, t, pos)) { t = t2_; pos = p2; }
@@ -231,7 +240,7 @@ struct QP {
         double *t1 = V_(t1), *t2 = V_(t2);
         const double* Q = V_(Q);
         const short* posFR = posFR_;
-        for (int i = lane; i < nV; i += 32) { int p = posFR[i]; t1[i] = (p >= 0) ? Q[p * ld + b] : 0.0; }
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) { int p = posFR[i]; t1[i] = (p >= 0) ? Q[p * ld + b] : 0.0; }
         SYNC();
         mulH(t1, t2);
     }
@@ -243,26 +252,26 @@ struct QP {
         double* RT = V_(RT);
         if (sA.is_lp) {
             double sr = sqrt(QP_EPS_REG);
-            for (int k = lane; k < nZ * nZ; k += 32) { int a_ = k / nZ, b_ = k % nZ; R_(a_, b_) = (a_ == b_) ? sr : 0.0; }
+            _Pragma("unroll 1") for (int k = lane; k < nZ * nZ; k += 32) { int a_ = k / nZ, b_ = k % nZ; R_(a_, b_) = (a_ == b_) ? sr : 0.0; }
             SYNC();
             return 0;
         }
         const double *Q = V_(Q), *t2 = V_(t2);
         const short* FR = FR_;
-        for (int b = 0; b < nZ; b++) {
+        _Pragma("unroll 1") for (int b = 0; b < nZ; b++) {
             proj_column(b);
-            for (int a_ = lane; a_ <= b; a_ += 32) {
+            _Pragma("unroll 1") for (int a_ = lane; a_ <= b; a_ += 32) {
                 double s = 0.0;
-                for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
+                _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
                 R_(a_, b) = s;
             }
             SYNC();
         }
         // row-wise Cholesky: R'R = M, same per-element summation order as the column version
-        for (int i = 0; i < nZ; i++) {
-            for (int j = i + lane; j < nZ; j += 32) {
+        _Pragma("unroll 1") for (int i = 0; i < nZ; i++) {
+            _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += 32) {
                 double s = R_(i, j);
-                for (int k = 0; k < i; k++) s -= R_(k, i) * R_(k, j);
+                _Pragma("unroll 1") for (int k = 0; k < i; k++) s -= R_(k, i) * R_(k, j);
                 R_(i, j) = s;
             }
             SYNC();
@@ -270,8 +279,8 @@ struct QP {
             SYNC();  // all lanes hold d before anyone rewrites R(i,i): the branch below is warp-uniform
             if (!(d > QP_ZERO)) return 1 + i;
             double dd = sqrt(d);
-            for (int j = i + lane; j < nZ; j += 32) R_(i, j) = (j == i) ? dd : R_(i, j) / dd;
-            for (int j = lane; j < i; j += 32) R_(i, j) = 0.0;
+            _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += 32) R_(i, j) = (j == i) ? dd : R_(i, j) / dd;
+            _Pragma("unroll 1") for (int j = lane; j < i; j += 32) R_(i, j) = 0.0;
             SYNC();
         }
         return 0;
@@ -282,7 +291,7 @@ struct QP {
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC, b = nZ - 1;
         double *RT = V_(RT), *w = V_(w);
         if (sA.is_lp) {
-            for (int a_ = lane; a_ < b; a_ += 32) { R_(a_, b) = 0.0; R_(b, a_) = 0.0; }
+            _Pragma("unroll 1") for (int a_ = lane; a_ < b; a_ += 32) { R_(a_, b) = 0.0; R_(b, a_) = 0.0; }
             if (lane == 0) R_(b, b) = sqrt(QP_EPS_REG);
             SYNC();
             return 1;
@@ -290,27 +299,27 @@ struct QP {
         const double *Q = V_(Q), *t2 = V_(t2);
         const short* FR = FR_;
         proj_column(b);
-        for (int a_ = lane; a_ <= b; a_ += 32) {
+        _Pragma("unroll 1") for (int a_ = lane; a_ <= b; a_ += 32) {
             double s = 0.0;
-            for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
+            _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
             w[a_] = s;
         }
         SYNC();
         // r = R'^{-1} w[0..b): forward substitution, column oriented
-        for (int k = 0; k < b; k++) {
+        _Pragma("unroll 1") for (int k = 0; k < b; k++) {
             double rk = w[k] / R_(k, k);
             SYNC();
             if (lane == 0) R_(k, b) = rk;
-            for (int i = k + 1 + lane; i < b; i += 32) w[i] -= R_(k, i) * rk;
+            _Pragma("unroll 1") for (int i = k + 1 + lane; i < b; i += 32) w[i] -= R_(k, i) * rk;
             SYNC();
         }
         double rho2 = w[b];
-        for (int k = 0; k < b; k++) rho2 -= R_(k, b) * R_(k, b);
+        _Pragma("unroll 1") for (int k = 0; k < b; k++) rho2 -= R_(k, b) * R_(k, b);
         int ok = check_curvature ? (rho2 > QP_EPS_FLIP) : (rho2 > QP_ZERO);
         SYNC();  // every lane has read w[b] / R(.,b) before a caller may overwrite them (uniform decision)
         if (!ok) return 0;
         if (lane == 0) R_(b, b) = sqrt(rho2);
-        for (int a_ = lane; a_ < b; a_ += 32) R_(b, a_) = 0.0;
+        _Pragma("unroll 1") for (int a_ = lane; a_ < b; a_ += 32) R_(b, a_) = 0.0;
         SYNC();
         return 1;
     }
@@ -322,17 +331,17 @@ struct QP {
         double *a = V_(a), *w = V_(w);
         const double *Q = V_(Q), *Av = V_(Av);
         const short* FR = FR_;
-        for (int p = lane; p < nFR; p += 32) a[p] = A_entry(pat, Av, c, FR[p]);
+        _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) a[p] = A_entry(pat, Av, c, FR[p]);
         SYNC();
-        for (int j = lane; j < nFR; j += 32) {
+        _Pragma("unroll 1") for (int j = lane; j < nFR; j += 32) {
             double s = 0.0;
-            for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * a[p];
+            _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * a[p];
             w[j] = s;
         }
         SYNC();
         double s2 = 0.0, z2 = 0.0;
-        for (int p = 0; p < nFR; p++) s2 += a[p] * a[p];
-        for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
+        _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s2 += a[p] * a[p];
+        _Pragma("unroll 1") for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
         wz2 = z2; a2 = s2;
         SYNC();
     }
@@ -343,7 +352,7 @@ struct QP {
         const double* w = V_(w);
         if (lane == 0) {
             double a0 = w[0];
-            for (int j = 0; j + 1 < cnt; j++) {
+            _Pragma("unroll 1") for (int j = 0; j + 1 < cnt; j++) {
                 double c, s;
                 givens(a0, w[j + 1], c, s, a0);
                 t2[j] = c; t3[j] = s;
@@ -359,17 +368,17 @@ struct QP {
         double *Q = V_(Q), *RT = V_(RT);
         const double *t2 = V_(t2), *t3 = V_(t3), *w = V_(w);
         double r = rotation_chain(nZ);
-        for (int p = lane; p < nFR; p += 32) {
+        _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) {
             double* q = Q + p * ld;
             double qa = q[0];
-            for (int j = 0; j + 1 < nZ; j++) {
+            _Pragma("unroll 1") for (int j = 0; j + 1 < nZ; j++) {
                 double cs = t2[j], sn = t3[j], qb = q[j + 1];
                 q[j] = cs * qa - sn * qb;
                 qa = sn * qa + cs * qb;
             }
             if (nZ > 0) q[nZ - 1] = qa;
         }
-        for (int j = lane; j < nFR; j += 32) T_(nAC, j) = (j > nZ - 1) ? w[j] : ((j == nZ - 1) ? r : 0.0);
+        _Pragma("unroll 1") for (int j = lane; j < nFR; j += 32) T_(nAC, j) = (j > nZ - 1) ? w[j] : ((j == nZ - 1) ? r : 0.0);
         if (lane == 0) { AC_[nAC] = (short)c; posAC_[c] = (short)nAC; sC_[c] = (short)status; hdr[1] = nAC + 1; }
         SYNC();
     }
@@ -379,17 +388,17 @@ struct QP {
         double *Q = V_(Q), *RT = V_(RT);
         short *AC = AC_, *posAC = posAC_;
         const int k = posAC[c];
-        for (int i = k + 1; i < nAC; i++) {
+        _Pragma("unroll 1") for (int i = k + 1; i < nAC; i++) {
             int cL = nFR - 1 - i;
             double cs, sn, r;
             givens(T_(i, cL), T_(i, cL + 1), cs, sn, r);
             SYNC();
-            for (int ii = i + lane; ii < nAC; ii += 32) {
+            _Pragma("unroll 1") for (int ii = i + lane; ii < nAC; ii += 32) {
                 double ta = T_(ii, cL), tb = T_(ii, cL + 1);
                 T_(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
                 T_(ii, cL + 1) = sn * ta + cs * tb;
             }
-            for (int p = lane; p < nFR; p += 32) {
+            _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) {
                 double qa = Q[p * ld + cL], qb = Q[p * ld + cL + 1];
                 Q[p * ld + cL] = cs * qa - sn * qb;
                 Q[p * ld + cL + 1] = sn * qa + cs * qb;
@@ -397,12 +406,12 @@ struct QP {
             SYNC();
         }
         // shift rows k+1.. up by one (row i -> i-1): sequential over rows, lanes over columns
-        for (int i = k + 1; i < nAC; i++) {
-            for (int j = lane; j < nFR; j += 32) T_(i - 1, j) = T_(i, j);
+        _Pragma("unroll 1") for (int i = k + 1; i < nAC; i++) {
+            _Pragma("unroll 1") for (int j = lane; j < nFR; j += 32) T_(i - 1, j) = T_(i, j);
             SYNC();
         }
         if (lane == 0) {
-            for (int i = k + 1; i < nAC; i++) { AC[i - 1] = AC[i]; posAC[AC[i - 1]] = (short)(i - 1); }
+            _Pragma("unroll 1") for (int i = k + 1; i < nAC; i++) { AC[i - 1] = AC[i]; posAC[AC[i - 1]] = (short)(i - 1); }
             sC_[c] = 0; posAC[c] = -1; hdr[1] = nAC - 1;
         }
         SYNC();
@@ -412,10 +421,10 @@ struct QP {
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC, p = posFR_[v];
         double* w = V_(w);
         const double* Q = V_(Q);
-        for (int j = lane; j < nFR; j += 32) w[j] = Q[p * ld + j];
+        _Pragma("unroll 1") for (int j = lane; j < nFR; j += 32) w[j] = Q[p * ld + j];
         SYNC();
         double z2 = 0.0;
-        for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
+        _Pragma("unroll 1") for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
         SYNC();
         return z2;
     }
@@ -427,10 +436,10 @@ struct QP {
         short *FR = FR_, *posFR = posFR_;
         const int p = posFR[v];
         rotation_chain(nFR);
-        for (int pp = lane; pp < nFR; pp += 32) {
+        _Pragma("unroll 1") for (int pp = lane; pp < nFR; pp += 32) {
             double* q = Q + pp * ld;
             double qa = q[0];
-            for (int j = 0; j + 1 < nFR; j++) {
+            _Pragma("unroll 1") for (int j = 0; j + 1 < nFR; j++) {
                 double cs = t2[j], sn = t3[j], qb = q[j + 1];
                 q[j] = cs * qa - sn * qb;
                 qa = sn * qa + cs * qb;
@@ -438,10 +447,10 @@ struct QP {
             q[nFR - 1] = qa;
         }
         // T rows: row i is touched by rotations j >= nFR-2-i (and j >= nZ-1)
-        for (int i = lane; i < nAC; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) {
             int j0 = nFR - 2 - i; if (j0 < nZ - 1) j0 = nZ - 1; if (j0 < 0) j0 = 0;
             double ta = T_(i, j0);
-            for (int j = j0; j + 1 < nFR; j++) {
+            _Pragma("unroll 1") for (int j = j0; j + 1 < nFR; j++) {
                 double cs = t2[j], sn = t3[j], tb = T_(i, j + 1);
                 T_(i, j) = cs * ta - sn * tb;
                 ta = sn * ta + cs * tb;
@@ -451,50 +460,53 @@ struct QP {
         SYNC();
         const int last = nFR - 1;
         if (p != last) {
-            for (int j = lane; j < nFR - 1; j += 32) Q[p * ld + j] = Q[last * ld + j];
+            _Pragma("unroll 1") for (int j = lane; j < nFR - 1; j += 32) Q[p * ld + j] = Q[last * ld + j];
             if (lane == 0) { short vl = FR[last]; FR[p] = vl; posFR[vl] = (short)p; }
         }
         if (lane == 0) { posFR[v] = -1; sB_[v] = (short)status; hdr[0] = nFR - 1; }
         SYNC();
     }
-    static __device__ QP_FN void remove_bound(int v) {
+    // returns 1 (warp-uniform) if the factors cannot hold one more free variable
+    static __device__ QP_FN int remove_bound(int v) {
         QP_CTX QP_PAT
         int nFR = hdr[0];
         const int nAC = hdr[1];
+        if (nFR + 1 > cap) return 1;
         double *Q = V_(Q), *RT = V_(RT);
         const double* Av = V_(Av);
         const short *Ap = pat + sA.pAp, *Ai = pat + sA.pAi;
         const short* AC = AC_;
         SYNC();  // all lanes have read hdr[0] before lane 0 updates it below
-        for (int j = lane; j < nFR; j += 32) { Q[nFR * ld + j] = 0.0; Q[j * ld + nFR] = 0.0; }
-        for (int i = lane; i < nAC; i += 32) {
+        _Pragma("unroll 1") for (int j = lane; j < nFR; j += 32) { Q[nFR * ld + j] = 0.0; Q[j * ld + nFR] = 0.0; }
+        _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) {
             int r = AC[i];
             double s = 0.0;
             int e1 = Ap[v + 1];
-            for (int e = Ap[v]; e < e1; e++)
+            _Pragma("unroll 1") for (int e = Ap[v]; e < e1; e++)
                 if (Ai[e] == r) s += Av[e];
             T_(i, nFR) = s;
         }
         if (lane == 0) { Q[nFR * ld + nFR] = 1.0; FR_[nFR] = (short)v; posFR_[v] = (short)nFR; sB_[v] = 0; hdr[0] = nFR + 1; }
         nFR++;
         SYNC();
-        for (int i = 0; i < nAC; i++) {
+        _Pragma("unroll 1") for (int i = 0; i < nAC; i++) {
             int cL = nFR - 2 - i;
             double cs, sn, r;
             givens(T_(i, cL), T_(i, cL + 1), cs, sn, r);
             SYNC();
-            for (int ii = i + lane; ii < nAC; ii += 32) {
+            _Pragma("unroll 1") for (int ii = i + lane; ii < nAC; ii += 32) {
                 double ta = T_(ii, cL), tb = T_(ii, cL + 1);
                 T_(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
                 T_(ii, cL + 1) = sn * ta + cs * tb;
             }
-            for (int p = lane; p < nFR; p += 32) {
+            _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) {
                 double qa = Q[p * ld + cL], qb = Q[p * ld + cL + 1];
                 Q[p * ld + cL] = cs * qa - sn * qb;
                 Q[p * ld + cL + 1] = sn * qa + cs * qb;
             }
             SYNC();
         }
+        return 0;
     }
 
     // ---------------------------------------------------------------- T solves
@@ -503,12 +515,12 @@ struct QP {
         QP_CTX
         const int nFR = hdr[0], nAC = hdr[1];
         const double* RT = V_(RT);
-        for (int i = 0; i < nAC; i++) {
+        _Pragma("unroll 1") for (int i = 0; i < nAC; i++) {
             int d = nFR - 1 - i;
             double vi = b[i] / T_(i, d);
             SYNC();
             if (lane == 0) v[d] = vi;
-            for (int k = i + 1 + lane; k < nAC; k += 32) b[k] -= T_(k, d) * vi;
+            _Pragma("unroll 1") for (int k = i + 1 + lane; k < nAC; k += 32) b[k] -= T_(k, d) * vi;
             SYNC();
         }
     }
@@ -517,12 +529,12 @@ struct QP {
         QP_CTX
         const int nFR = hdr[0], nAC = hdr[1];
         const double* RT = V_(RT);
-        for (int i = nAC - 1; i >= 0; i--) {
+        _Pragma("unroll 1") for (int i = nAC - 1; i >= 0; i--) {
             int d = nFR - 1 - i;
             double ui = r[d] / T_(i, d);
             SYNC();
             if (lane == 0) u[i] = ui;
-            for (int k = lane; k < i; k += 32) { int dk = nFR - 1 - k; r[dk] -= T_(i, dk) * ui; }
+            _Pragma("unroll 1") for (int k = lane; k < i; k += 32) { int dk = nFR - 1 - k; r[dk] -= T_(i, dk) * ui; }
             SYNC();
         }
     }
@@ -536,68 +548,68 @@ struct QP {
         double *dx = V_(dx), *dy = V_(dy), *t1 = V_(t1), *t2 = V_(t2), *t3 = V_(t3), *yv = V_(yv), *zv = V_(zv);
         const double *Q = V_(Q), *RT = V_(RT);
         const short *sB = sB_, *FR = FR_, *AC = AC_;
-        for (int i = lane; i < nV; i += 32) dx[i] = (sB[i] != 0) ? dxFX[i] : 0.0;
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) dx[i] = (sB[i] != 0) ? dxFX[i] : 0.0;
         SYNC();
         if (nAC > 0) {
             mulA(dx, t2);
-            for (int i = lane; i < nAC; i += 32) t3[i] = dbAC[i] - t2[AC[i]];
+            _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) t3[i] = dbAC[i] - t2[AC[i]];
             SYNC();
             solve_T(t3, yv);
-            for (int p = lane; p < nFR; p += 32) {
+            _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) {
                 double s = 0.0;
-                for (int j = nZ; j < nFR; j++) s += Q[p * ld + j] * yv[j];
+                _Pragma("unroll 1") for (int j = nZ; j < nFR; j++) s += Q[p * ld + j] * yv[j];
                 dx[FR[p]] = s;
             }
             SYNC();
         }
         if (nZ > 0) {
             mulH(dx, t1);
-            for (int j = lane; j < nZ; j += 32) {
+            _Pragma("unroll 1") for (int j = lane; j < nZ; j += 32) {
                 double s = 0.0;
-                for (int p = 0; p < nFR; p++) { int v = FR[p]; s += Q[p * ld + j] * (t1[v] + dgvec[v]); }
+                _Pragma("unroll 1") for (int p = 0; p < nFR; p++) { int v = FR[p]; s += Q[p * ld + j] * (t1[v] + dgvec[v]); }
                 zv[j] = -s;
             }
             SYNC();
             // R' u = rhs (forward), R z = u (backward); column oriented
-            for (int k = 0; k < nZ; k++) {
+            _Pragma("unroll 1") for (int k = 0; k < nZ; k++) {
                 double uk = zv[k] / R_(k, k);
                 SYNC();
                 if (lane == 0) zv[k] = uk;
-                for (int i = k + 1 + lane; i < nZ; i += 32) zv[i] -= R_(k, i) * uk;
+                _Pragma("unroll 1") for (int i = k + 1 + lane; i < nZ; i += 32) zv[i] -= R_(k, i) * uk;
                 SYNC();
             }
-            for (int k = nZ - 1; k >= 0; k--) {
+            _Pragma("unroll 1") for (int k = nZ - 1; k >= 0; k--) {
                 double zk = zv[k] / R_(k, k);
                 SYNC();
                 if (lane == 0) zv[k] = zk;
-                for (int i = lane; i < k; i += 32) zv[i] -= R_(i, k) * zk;
+                _Pragma("unroll 1") for (int i = lane; i < k; i += 32) zv[i] -= R_(i, k) * zk;
                 SYNC();
             }
-            for (int p = lane; p < nFR; p += 32) {
+            _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) {
                 double s = 0.0;
-                for (int j = 0; j < nZ; j++) s += Q[p * ld + j] * zv[j];
+                _Pragma("unroll 1") for (int j = 0; j < nZ; j++) s += Q[p * ld + j] * zv[j];
                 dx[FR[p]] += s;
             }
             SYNC();
         }
         mulH(dx, t1);
-        for (int i = lane; i < nV; i += 32) t1[i] += dgvec[i];
-        for (int i = lane; i < nT; i += 32) dy[i] = 0.0;
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) t1[i] += dgvec[i];
+        _Pragma("unroll 1") for (int i = lane; i < nT; i += 32) dy[i] = 0.0;
         SYNC();
         if (nAC > 0) {
-            for (int j = nZ + lane; j < nFR; j += 32) {
+            _Pragma("unroll 1") for (int j = nZ + lane; j < nFR; j += 32) {
                 double s = 0.0;
-                for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * t1[FR[p]];
+                _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * t1[FR[p]];
                 yv[j] = s;
             }
             SYNC();
             solve_Tt(yv, t3);
-            for (int i = lane; i < nAC; i += 32) dy[nV + AC[i]] = t3[i];
+            _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) dy[nV + AC[i]] = t3[i];
             SYNC();
             mulAT(dy + nV, t2);
-            for (int i = lane; i < nV; i += 32) if (sB[i] != 0) dy[i] = t1[i] - t2[i];
+            _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) if (sB[i] != 0) dy[i] = t1[i] - t2[i];
         } else {
-            for (int i = lane; i < nV; i += 32) if (sB[i] != 0) dy[i] = t1[i];
+            _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) if (sB[i] != 0) dy[i] = t1[i];
         }
         SYNC();
     }
@@ -609,7 +621,7 @@ struct QP {
         const double *x = V_(x), *y = V_(y);
         mulAT(y + nV, t2);
         mulH(x, t1);
-        for (int i = lane; i < nV; i += 32) g[i] = t2[i] + y[i] - t1[i];
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) g[i] = t2[i] + y[i] - t1[i];
         SYNC();
     }
     static __device__ QP_FN void drift_correction() {
@@ -617,13 +629,13 @@ struct QP {
         double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA);
         const short *sB = sB_, *sC = sC_;
         mulA(x, Ax);
-        for (int i = lane; i < nV; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
             int s = sB[i]; double xi = x[i];
             if (s < 0) { lb[i] = xi; if (ub[i] < xi) ub[i] = xi; if (y[i] < 0) y[i] = 0.0; }
             else if (s > 0) { ub[i] = xi; if (lb[i] > xi) lb[i] = xi; if (y[i] > 0) y[i] = 0.0; }
             else { if (lb[i] > xi) lb[i] = xi; if (ub[i] < xi) ub[i] = xi; y[i] = 0.0; }
         }
-        for (int i = lane; i < nC; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) {
             int s = sC[i]; double ax = Ax[i];
             if (s < 0) { lbA[i] = ax; if (ubA[i] < ax) ubA[i] = ax; if (y[nV + i] < 0) y[nV + i] = 0.0; }
             else if (s > 0) { ubA[i] = ax; if (lbA[i] > ax) lbA[i] = ax; if (y[nV + i] > 0) y[nV + i] = 0.0; }
@@ -640,7 +652,7 @@ struct QP {
         const int nRamp = nV + nC + nC + nV;
         const double r0 = 0.5, r1 = 1.0;
         mulA(x, Ax);
-        for (int i = lane; i < nV; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
             double tP = (double)((i + ramp_offset) % nRamp) / (double)(nRamp - 1);
             double rP = (1.0 - tP) * r0 + tP * r1;
             double tD = (double)((nV + nC + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
@@ -654,7 +666,7 @@ struct QP {
             if (s > 0) { ub[i] = xi; y[i] = -rD; }
             if (s == 0) y[i] = 0.0;
         }
-        for (int i = lane; i < nC; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) {
             double tP = (double)((nV + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
             double rP = (1.0 - tP) * r0 + tP * r1;
             double tD = (double)((nV + nC + nV + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
@@ -675,20 +687,20 @@ struct QP {
     }
 
     // ---------------------------------------------------------------- exchange (ensure LI)
-    // element to add: constraint c (v<0) or bound v (c<0); w holds its Q-coordinates. 0 ok, 1 infeasible
+    // element to add: constraint c (v<0) or bound v (c<0); w holds its Q-coordinates. 0 ok, 1 infeasible, 2 capacity
     static __device__ QP_FN int ensure_li(int c, int v, int status) {
         QP_CTX QP_PAT
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
         double *xiC = V_(zv), *xiB = V_(dx), *yv = V_(yv), *t2 = V_(t2), *t3 = V_(t3), *y = V_(y);
         const double *w = V_(w), *Av = V_(Av);
         const short *sB = sB_, *sC = sC_, *AC = AC_, *posAC = posAC_;
-        for (int j = nZ + lane; j < nFR; j += 32) yv[j] = w[j];
+        _Pragma("unroll 1") for (int j = nZ + lane; j < nFR; j += 32) yv[j] = w[j];
         SYNC();
         solve_Tt(yv, xiC);
-        for (int i = lane; i < nC; i += 32) { int p = posAC[i]; t3[i] = (p >= 0) ? xiC[p] : 0.0; }
+        _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) { int p = posAC[i]; t3[i] = (p >= 0) ? xiC[p] : 0.0; }
         SYNC();
         mulAT(t3, t2);
-        for (int i = lane; i < nV; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
             if (sB[i] == 0) { xiB[i] = 0.0; continue; }
             double ai = (c >= 0) ? A_entry(pat, Av, c, i) : 0.0;
             xiB[i] = ai - t2[i];
@@ -696,13 +708,13 @@ struct QP {
         SYNC();
         const double sgn = (status < 0) ? 1.0 : -1.0;
         double best = QP_INFTY; int bpos = 0x7fffffff;
-        for (int i = lane; i < nAC; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) {
             int ci = AC[i]; double xi = sgn * xiC[i], yy = y[nV + ci]; double t = QP_INFTY;
             if (sC[ci] < 0) { if (xi > QP_ZERO && yy >= 0.0) t = yy / xi; }
             else { if (xi < -QP_ZERO && yy <= 0.0) t = yy / xi; }
             if (t < QP_INFTY && key_less(t, i, best, bpos)) { best = t; bpos = i; }
         }
-        for (int i = lane; i < nV; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
             if (sB[i] == 0) continue;
             double xi = sgn * xiB[i], yy = y[i]; double t = QP_INFTY;
             if (sB[i] < 0) { if (xi > QP_ZERO && yy >= 0.0) t = yy / xi; }
@@ -715,15 +727,15 @@ struct QP {
         const int kind = mk.pos >= nC ? 1 : 0;
         const int idx = kind ? mk.pos - nC : AC[mk.pos];
         SYNC();
-        for (int i = lane; i < nAC; i += 32) y[nV + AC[i]] -= ymin * sgn * xiC[i];
-        for (int i = lane; i < nV; i += 32) if (sB[i] != 0) y[i] -= ymin * sgn * xiB[i];
+        _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) y[nV + AC[i]] -= ymin * sgn * xiC[i];
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) if (sB[i] != 0) y[i] -= ymin * sgn * xiB[i];
         SYNC();
         if (lane == 0) {
             if (c >= 0) y[nV + c] = sgn * ymin; else y[v] = sgn * ymin;
             if (kind == 0) y[nV + idx] = 0.0; else y[idx] = 0.0;
         }
         SYNC();
-        if (kind == 0) remove_constraint(idx); else remove_bound(idx);
+        if (kind == 0) remove_constraint(idx); else if (remove_bound(idx)) return 2;
         return 0;
     }
 
@@ -737,15 +749,15 @@ struct QP {
         const double *gN = V_(gN), *lbN = V_(lbN), *ubN = V_(ubN), *lbAN = V_(lbAN), *ubAN = V_(ubAN);
         short *sB = sB_, *sC = sC_, *AC = AC_;
         iters = 0;
-        for (int it = 0;; it++) {
+        _Pragma("unroll 1") for (int it = 0;; it++) {
             const int nAC = hdr[1];
             // w[0..nV) <- bound shift of fixed variables, w[nV..) <- constraint shift by AC position, a <- dg
-            for (int i = lane; i < nV; i += 32) {
+            _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
                 int s = sB[i];
                 w[i] = s < 0 ? (lbN[i] - lb[i]) : (s > 0 ? (ubN[i] - ub[i]) : 0.0);
                 a[i] = gN[i] - g[i];
             }
-            for (int i = lane; i < nAC; i += 32) { int ci = AC[i]; w[nV + i] = sC[ci] < 0 ? (lbAN[ci] - lbA[ci]) : (ubAN[ci] - ubA[ci]); }
+            _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) { int ci = AC[i]; w[nV + i] = sC[ci] < 0 ? (lbAN[ci] - lbA[ci]) : (ubAN[ci] - ubA[ci]); }
             SYNC();
             step_direction(a, w, w + nV);
             mulA(dx, dAx);
@@ -760,23 +772,23 @@ struct QP {
             if (t_ < 1.0 && key_less(t_, (pos), best, bpos)) { best = t_; bpos = (pos); }         \
         }                                                                                         \
     }
-            for (int i = lane; i < nAC; i += 32) {
+            _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) {
                 int ci = AC[i];
                 if (sC[ci] < 0) CONSIDER(y[nV + ci], -dy[nV + ci], i) else CONSIDER(-y[nV + ci], dy[nV + ci], i)
             }
-            for (int i = lane; i < nV; i += 32) {
+            _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
                 int s = sB[i];
                 if (s == 0) continue;
                 if (s < 0) CONSIDER(y[i], -dy[i], nC + i) else CONSIDER(-y[i], dy[i], nC + i)
             }
-            for (int i = lane; i < nC; i += 32) {
+            _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) {
                 if (sC[i] != 0) continue;
                 double num = Ax[i] - lbA[i]; if (num < 0) num = 0;
                 CONSIDER(num, (lbAN[i] - lbA[i]) - dAx[i], nC + nV + i)
                 num = ubA[i] - Ax[i]; if (num < 0) num = 0;
                 CONSIDER(num, dAx[i] - (ubAN[i] - ubA[i]), nC + nV + nC + i)
             }
-            for (int i = lane; i < nV; i += 32) {
+            _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
                 if (sB[i] != 0) continue;
                 double num = x[i] - lb[i]; if (num < 0) num = 0;
                 CONSIDER(num, (lbN[i] - lb[i]) - dx[i], 2 * nC + nV + nC + i)
@@ -799,21 +811,21 @@ struct QP {
             SYNC();
             // ---- step
             if (bc_idx < 0) {
-                for (int i = lane; i < nV; i += 32) { x[i] += dx[i]; g[i] = gN[i]; lb[i] = lbN[i]; ub[i] = ubN[i]; }
-                for (int i = lane; i < nT; i += 32) y[i] += dy[i];
-                for (int i = lane; i < nC; i += 32) { Ax[i] += dAx[i]; lbA[i] = lbAN[i]; ubA[i] = ubAN[i]; }
+                _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) { x[i] += dx[i]; g[i] = gN[i]; lb[i] = lbN[i]; ub[i] = ubN[i]; }
+                _Pragma("unroll 1") for (int i = lane; i < nT; i += 32) y[i] += dy[i];
+                _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) { Ax[i] += dAx[i]; lbA[i] = lbAN[i]; ubA[i] = ubAN[i]; }
                 SYNC();
                 iters = it;
                 return ST_OPTIMAL;
             }
             if (it >= max_iter) { iters = it; return ST_HOMOTOPY; }
             if (tau > 0.0) {
-                for (int i = lane; i < nV; i += 32) {
+                _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
                     x[i] += tau * dx[i]; g[i] += tau * a[i];
                     lb[i] += tau * (lbN[i] - lb[i]); ub[i] += tau * (ubN[i] - ub[i]);
                 }
-                for (int i = lane; i < nT; i += 32) y[i] += tau * dy[i];
-                for (int i = lane; i < nC; i += 32) {
+                _Pragma("unroll 1") for (int i = lane; i < nT; i += 32) y[i] += tau * dy[i];
+                _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) {
                     Ax[i] += tau * dAx[i];
                     lbA[i] += tau * (lbAN[i] - lbA[i]); ubA[i] += tau * (ubAN[i] - ubA[i]);
                 }
@@ -827,7 +839,7 @@ struct QP {
                     SYNC();
                     if (lane == 0) y[bc_idx] = 0.0;
                     SYNC();
-                    remove_bound(bc_idx);
+                    if (remove_bound(bc_idx)) { iters = it; return ST_CAPACITY; }
                     if (!extend_R(flags & FLAG_FLIPPING)) {
                         if (!(flags & FLAG_FLIPPING)) { iters = it; return ST_UNBOUNDED; }
                         bound_w(bc_idx);
@@ -859,7 +871,8 @@ struct QP {
                 if (bc_isbound) {
                     double z2 = bound_w(bc_idx);
                     if (!(z2 > QP_EPS_LI * QP_EPS_LI)) {
-                        if (ensure_li(-1, bc_idx, bc_status)) { iters = it; return ST_INFEASIBLE; }
+                        int e_ = ensure_li(-1, bc_idx, bc_status);
+                        if (e_) { iters = it; return e_ == 2 ? ST_CAPACITY : ST_INFEASIBLE; }
                         bound_w(bc_idx);
                     }
                     add_bound(bc_idx, bc_status);
@@ -867,7 +880,8 @@ struct QP {
                     double z2, a2;
                     constraint_w(bc_idx, z2, a2);
                     if (!(z2 > QP_EPS_LI * QP_EPS_LI * a2) || a2 == 0.0) {
-                        if (ensure_li(bc_idx, -1, bc_status)) { iters = it; return ST_INFEASIBLE; }
+                        int e_ = ensure_li(bc_idx, -1, bc_status);
+                        if (e_) { iters = it; return e_ == 2 ? ST_CAPACITY : ST_INFEASIBLE; }
                         constraint_w(bc_idx, z2, a2);
                     }
                     add_constraint(bc_idx, bc_status);
@@ -884,10 +898,10 @@ struct QP {
         QP_CTX
         double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *g = V_(g), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA);
         short *sB = sB_, *sC = sC_, *posFR = posFR_, *posAC = posAC_;
-        for (int i = lane; i < nV; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
             x[i] = 0.0; y[i] = 0.0; sB[i] = -1; posFR[i] = -1; g[i] = 0.0; lb[i] = 0.0; ub[i] = QP_BOUND_RELAX;
         }
-        for (int i = lane; i < nC; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) {
             y[nV + i] = 0.0; sC[i] = 0; posAC[i] = -1; Ax[i] = 0.0; lbA[i] = -QP_BOUND_RELAX; ubA[i] = QP_BOUND_RELAX;
         }
         if (lane == 0) { hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; }
@@ -900,13 +914,13 @@ struct QP {
         double *Q = V_(Q), *dAx = V_(dAx), *dy = V_(dy), *y = V_(y);
         short *sC = sC_, *AC = AC_, *posAC = posAC_;
         // remember (constraint, status) by AC position in dAx (nC) and dy[nV..] (nC): neither is touched below
-        for (int i = lane; i < nAC_old; i += 32) { int ci = AC[i]; dAx[i] = (double)ci; dy[nV + i] = (double)sC[ci]; }
+        _Pragma("unroll 1") for (int i = lane; i < nAC_old; i += 32) { int ci = AC[i]; dAx[i] = (double)ci; dy[nV + i] = (double)sC[ci]; }
         SYNC();
-        for (int k = lane; k < nFR * nFR; k += 32) { int i = k / nFR, j = k % nFR; Q[i * ld + j] = (i == j) ? 1.0 : 0.0; }
-        for (int i = lane; i < nAC_old; i += 32) { int ci = (int)dAx[i]; sC[ci] = 0; posAC[ci] = -1; }
+        _Pragma("unroll 1") for (int k = lane; k < nFR * nFR; k += 32) { int i = k / nFR, j = k % nFR; Q[i * ld + j] = (i == j) ? 1.0 : 0.0; }
+        _Pragma("unroll 1") for (int i = lane; i < nAC_old; i += 32) { int ci = (int)dAx[i]; sC[ci] = 0; posAC[ci] = -1; }
         if (lane == 0) hdr[1] = 0;
         SYNC();
-        for (int i = 0; i < nAC_old; i++) {
+        _Pragma("unroll 1") for (int i = 0; i < nAC_old; i++) {
             int ci = (int)dAx[i]; int st = (int)dy[nV + i];
             double z2, a2;
             constraint_w(ci, z2, a2);
@@ -925,8 +939,8 @@ struct QP {
         const short *sB = sB_, *sC = sC_;
         double* xo = sA.x + (size_t)b * nV;
         double* yo = sA.y + (size_t)b * nT;
-        for (int i = lane; i < nV; i += 32) xo[i] = x[i];
-        for (int i = lane; i < nT; i += 32) yo[i] = y[i];
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) xo[i] = x[i];
+        _Pragma("unroll 1") for (int i = lane; i < nT; i += 32) yo[i] = y[i];
         if (sA.wsB) for (int i = lane; i < nV; i += 32) sA.wsB[(size_t)b * nV + i] = (signed char)sB[i];
         if (sA.wsC) for (int i = lane; i < nC; i += 32) sA.wsC[(size_t)b * nC + i] = (signed char)sC[i];
         // Hx (unregularised) in t1, A x in Ax, A'y_c in t2
@@ -936,25 +950,25 @@ struct QP {
         if (lane == 0) {
             const double SQRT_M_EPS = 1.0e-8;
             double obj = 0.0;
-            for (int i = 0; i < nV; i++) obj += 0.5 * x[i] * t1[i];
-            for (int i = 0; i < nV; i++) obj += gN[i] * x[i];
+            _Pragma("unroll 1") for (int i = 0; i < nV; i++) obj += 0.5 * x[i] * t1[i];
+            _Pragma("unroll 1") for (int i = 0; i < nV; i++) obj += gN[i] * x[i];
             sA.obj[b] = obj; sA.status[b] = status; sA.iters[b] = total_iters;
             // qpOASESInterface::get_working_set + test_optimality (src/qpOASESInterface.cpp:835-895, 498-684),
             // evaluated against the target data the caller supplied.
             double primal = 0.0, dual = 0.0, compl_ = 0.0, stat = 0.0;
             int* WB = sA.WB ? sA.WB + (size_t)b * nV : nullptr;
             int* WC = sA.WC ? sA.WC + (size_t)b * nC : nullptr;
-            for (int i = 0; i < nV; i++) {
+            _Pragma("unroll 1") for (int i = 0; i < nV; i++) {
                 double xi = x[i];
                 primal += fmax(0.0, lbN[i] - xi);
                 primal += -fmin(0.0, ubN[i] - xi);
             }
-            for (int i = 0; i < nC; i++) {
+            _Pragma("unroll 1") for (int i = 0; i < nC; i++) {
                 double ax = Ax[i];
                 primal += fmax(0.0, lbAN[i] - ax);
                 primal += -fmin(0.0, ubAN[i] - ax);
             }
-            for (int i = 0; i < nV; i++) {
+            _Pragma("unroll 1") for (int i = 0; i < nV; i++) {
                 int s = sB[i], W; double xi = x[i], yi = y[i];
                 if (s > 0) W = (fabs(xi - lbN[i]) < SQRT_M_EPS) ? -99 : 1;
                 else if (s < 0) W = (fabs(xi - ubN[i]) < SQRT_M_EPS) ? -99 : -1;
@@ -962,7 +976,7 @@ struct QP {
                 if (WB) WB[i] = W;
                 if (W == 0) dual += fabs(yi); else if (W == -1) dual += -fmin(0.0, yi); else if (W == 1) dual += fmax(0.0, yi);
             }
-            for (int i = 0; i < nC; i++) {
+            _Pragma("unroll 1") for (int i = 0; i < nC; i++) {
                 int s = sC[i], W; double ax = Ax[i], yi = y[nV + i];
                 if (s > 0) W = (ax - lbAN[i] < SQRT_M_EPS) ? -99 : 1;       // :874 (comparison inside fabs)
                 else if (s < 0) W = (ax - ubAN[i] < SQRT_M_EPS) ? -99 : -1;  // :880
@@ -970,17 +984,17 @@ struct QP {
                 if (WC) WC[i] = W;
                 if (W == 0) dual += fabs(yi); else if (W == -1) dual += -fmin(0.0, yi); else if (W == 1) dual += fmax(0.0, yi);
             }
-            for (int i = 0; i < nV; i++) {
+            _Pragma("unroll 1") for (int i = 0; i < nV; i++) {
                 double gap = t2[i];
                 gap += y[i]; gap -= gN[i]; gap -= t1[i];
                 stat += fabs(gap);
             }
-            for (int i = 0; i < nV; i++) {
+            _Pragma("unroll 1") for (int i = 0; i < nV; i++) {
                 int s = sB[i]; double xi = x[i], yi = y[i];
                 int W = (s > 0) ? ((fabs(xi - lbN[i]) < SQRT_M_EPS) ? -99 : 1) : (s < 0 ? ((fabs(xi - ubN[i]) < SQRT_M_EPS) ? -99 : -1) : 0);
                 if (W == 0) compl_ += fabs(yi); else if (W == -1) compl_ += fabs(yi * (xi - lbN[i])); else if (W == 1) compl_ += fabs(yi * (ubN[i] - xi));
             }
-            for (int i = 0; i < nC; i++) {
+            _Pragma("unroll 1") for (int i = 0; i < nC; i++) {
                 int s = sC[i]; double ax = Ax[i], yi = y[nV + i];
                 int W = (s > 0) ? ((ax - lbAN[i] < SQRT_M_EPS) ? -99 : 1) : (s < 0 ? ((ax - ubAN[i] < SQRT_M_EPS) ? -99 : -1) : 0);
                 if (W == 0) compl_ += fabs(yi); else if (W == -1) compl_ += fabs(yi * (ax - lbAN[i])); else if (W == 1) compl_ += fabs(yi * (ubAN[i] - ax));
@@ -1020,16 +1034,28 @@ __global__ void __launch_bounds__(CTA_THREADS) qp_solve_kernel(const __grid_cons
     const int b = blockIdx.x * TEAMS + team_id;
     if (b >= A.batch) return;
     if (A.mask && !A.mask[b]) return;
-    const int nV = A.nV, nC = A.nC;
+    if (A.rescue && A.status[b] != ST_CAPACITY) return;  // rescue launch: only instances that overflowed the factor capacity
+    const int nV = A.nV, nC = A.nC, cap = A.cap, ld = A.ld;
     double* slice = qp_smem + (size_t)team_id * A.slice_doubles;
     int* hdr = reinterpret_cast<int*>(slice);
+    double *Q = slice + A.oQ, *RT = slice + A.oRT;
 
     int mode = A.mode;
-    if (mode != MODE_COLD) {  // restore the slice image of the previous solve
-        const double* st = A.state + (size_t)b * A.slice_doubles;
-        for (int i = lane; i < A.slice_doubles; i += 32) slice[i] = st[i];
+    int status = 0;
+    if (mode != MODE_COLD) {
+        // restore the pre-solve image: everything but the factors verbatim, then Q (nFR x nFR), R (nZ x nZ), T (nAC x nFR)
+        const double* st = A.state + (size_t)b * A.state_doubles;
+        for (int i = lane; i < A.oQ; i += 32) slice[i] = st[i];
         __syncwarp();
+        const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
         if (!hdr[3]) mode = MODE_COLD;  // previous solve did not end optimal: plain re-init (handle_error)
+        else if (nFR > cap) status = ST_CAPACITY;
+        else {
+            const double *Qp = st + A.oQ, *Rp = Qp + nFR * nFR, *Tp = Rp + nZ * nZ;
+            for (int k = lane; k < nFR * nFR; k += 32) Q[(k / nFR) * ld + (k % nFR)] = Qp[k];
+            for (int k = lane; k < nZ * nZ; k += 32) R_(k / nZ, k % nZ) = Rp[k];
+            for (int k = lane; k < nAC * nFR; k += 32) T_(k / nFR, k % nFR) = Tp[k];
+        }
         __syncwarp();
     }
     if (mode != MODE_HOT_FIXED) {
@@ -1056,24 +1082,35 @@ __global__ void __launch_bounds__(CTA_THREADS) qp_solve_kernel(const __grid_cons
     }
     __syncwarp();
 
-    int status, iters = 0, total_iters = 0;
-    if (mode == MODE_HOT_VARIED) {
-        if (QP::refactorise()) mode = MODE_COLD;  // projected Hessian of the kept set not PD: cold start
-        else QP::drift_correction();
-    }
-    if (mode == MODE_COLD) QP::cold_start_state();
-    status = QP::homotopy(A.max_iter, iters);
-    total_iters += iters;
-    if (status != ST_OPTIMAL && mode != MODE_COLD) {
-        // one-retry recovery of handle_error (src/qpOASESInterface.cpp:746-754): plain re-init
-        QP::cold_start_state();
+    int iters = 0, total_iters = 0;
+    if (status != ST_CAPACITY) {
+        if (mode == MODE_HOT_VARIED) {
+            if (QP::refactorise()) mode = MODE_COLD;  // projected Hessian of the kept set not PD: cold start
+            else QP::drift_correction();
+        }
+        if (mode == MODE_COLD) QP::cold_start_state();
         status = QP::homotopy(A.max_iter, iters);
         total_iters += iters;
+        if (status != ST_OPTIMAL && status != ST_CAPACITY && mode != MODE_COLD) {
+            // one-retry recovery of handle_error (src/qpOASESInterface.cpp:746-754): plain re-init
+            QP::cold_start_state();
+            status = QP::homotopy(A.max_iter, iters);
+            total_iters += iters;
+        }
+    }
+    if (status == ST_CAPACITY) {  // left to the rescue launch (full capacity), which restarts from the pre-solve state
+        if (lane == 0) { A.status[b] = ST_CAPACITY; A.iters[b] = 0; }
+        return;
     }
     QP::epilogue(b, status, total_iters);
     if ((A.flags & FLAG_KEEP_STATE) && A.state) {
-        double* st = A.state + (size_t)b * A.slice_doubles;
-        for (int i = lane; i < A.slice_doubles; i += 32) st[i] = slice[i];
+        double* st = A.state + (size_t)b * A.state_doubles;
+        for (int i = lane; i < A.oQ; i += 32) st[i] = slice[i];
+        const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
+        double *Qp = st + A.oQ, *Rp = Qp + nFR * nFR, *Tp = Rp + nZ * nZ;
+        for (int k = lane; k < nFR * nFR; k += 32) Qp[k] = Q[(k / nFR) * ld + (k % nFR)];
+        for (int k = lane; k < nZ * nZ; k += 32) Rp[k] = R_(k / nZ, k % nZ);
+        for (int k = lane; k < nAC * nFR; k += 32) Tp[k] = T_(k / nFR, k % nFR);
     }
 }
 

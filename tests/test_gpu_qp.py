@@ -19,10 +19,10 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / max(1.0, np.abs(b).max())) if a.size else 0.0
 
 
-def solve_batch_csc(nV, nC, Acsc, Hcsc, g, lb, ub, lbA, ubA, qptype=r.QPType.QP, team_size=0, Avals=None, Hvals=None):
+def solve_batch_csc(nV, nC, Acsc, Hcsc, g, lb, ub, lbA, ubA, qptype=r.QPType.QP, team_size=0, Avals=None, Hvals=None, factor_cap=0):
     """g, lb, ... are [batch][len]; Acsc/Hcsc = (colptr,rowidx,val[z]) shared, Avals/Hvals optional [batch][z]."""
     B = g.shape[0]
-    s = r.CudaQPInterface(nV=nV, nC=nC, qptype=qptype, batch=B, team_size=team_size)
+    s = r.CudaQPInterface(nV=nV, nC=nC, qptype=qptype, batch=B, team_size=team_size, factor_cap=factor_cap)
     s.set_csc(capi.MAT_A, Acsc[0], Acsc[1], Acsc[2] if Avals is None else Avals)
     if qptype == r.QPType.QP:
         s.set_csc(capi.MAT_H, Hcsc[0], Hcsc[1], Hcsc[2] if Hvals is None else Hvals)
@@ -270,4 +270,36 @@ def test_active_mask_and_large_batch_properties(gpu_lib):
             continue
         p = dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b])
         check_against_oracle(s, int(b), H.oracle_solve(orc, p, Acsc=Ac, Hcsc=Hc), nV)
+    s.close()
+
+
+@pytest.mark.parametrize("cap", [1, 3, -1])
+def test_factor_capacity_rescue_path(gpu_lib, cap):
+    """A factor capacity below the number of free variables the path needs must not change any result: the
+    overflowing instances are re-solved by the rescue launch (cold and hot starts)."""
+    rng = np.random.default_rng(123)
+    n, m, B = 7, 4, 24
+    base = H.random_l1_qp(rng, n, m, convex=True)
+    nV, nC = base["nV"], base["nC"]
+    Ac, Hc = H.csc(base["A"]), H.csc(base["H"])
+    g = np.tile(base["g"], (B, 1)); g[:, :n] += rng.standard_normal((B, n))
+    lb, ub = np.tile(base["lb"], (B, 1)), np.tile(base["ub"], (B, 1))
+    lbA, ubA = np.tile(base["lbA"], (B, 1)), np.tile(base["ubA"], (B, 1))
+    s = solve_batch_csc(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA, factor_cap=cap)
+    oracles, needs = [], 0
+    for b in range(B):
+        p = dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b])
+        o = H.oracle_solve(orc, p, Acsc=Ac, Hcsc=Hc)
+        check_against_oracle(s, b, o, nV)
+        oracles.append(o["solver"])
+        needs = max(needs, orc.lib().orc_qp_get_max_free(o["solver"].h))
+    if cap > 0:
+        assert needs > cap, "test problem does not exercise the rescue path"
+    g2 = g.copy(); g2[:, :n] += 0.5 * rng.standard_normal((B, n))
+    s.set_g(g2)
+    s.optimizeQP()
+    for b in range(B):
+        st = oracles[b].hotstart(g2[b], lb[b], ub[b], lbA[b], ubA[b])
+        x, y, obj, it = oracles[b].solution(); wb, wc = oracles[b].working_set()
+        check_against_oracle(s, b, dict(x=x, y=y, obj=obj, iters=it, status=st, wb=wb, wc=wc), nV)
     s.close()

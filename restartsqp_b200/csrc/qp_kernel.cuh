@@ -1012,8 +1012,11 @@ struct QP {
 // -------------------------------------------------------------------------------------------
 // kernel: one QP per warp, CTA_THREADS/32 QPs per CTA
 // -------------------------------------------------------------------------------------------
+#ifndef QP_MIN_BLOCKS
+#define QP_MIN_BLOCKS 1
+#endif
 template <int CTA_THREADS>
-__global__ void __launch_bounds__(CTA_THREADS) qp_solve_kernel(const __grid_constant__ QPKernelArgs A) {
+__global__ void __launch_bounds__(CTA_THREADS, QP_MIN_BLOCKS) qp_solve_kernel(const __grid_constant__ QPKernelArgs A) {
     constexpr int TEAMS = CTA_THREADS / 32;
     // stage the launch arguments and the 16-bit pattern once per CTA
     {

@@ -135,7 +135,8 @@ int sqpb200_get_vectors(sqpb200_handle h, int which, double* vals, int loc);
 
 /* ---- batched QPhandler data construction on the device (src/QPhandler.cpp:167-261, 272-297,
  * 342-419, 430-463, 533-567): n = NLP variables, m = NLP constraints (nV = n+2m, nC = m).
- * mode 0 = set_bounds, 1 = update_bounds (lbA only: quirk 2), 2 = update_delta.
+ * mode 0 = set_bounds, 1 = update_bounds as the reference's non-QORE branch does it (lbA refreshed, ubA left stale:
+ * src/QPhandler.cpp:358-360), 2 = update_delta, 3 = update_bounds refreshing lbA and ubA (what the QORE branch does, :377-382).
  * delta[batch]; x_l,x_u,x_k [batch][n]; c_l,c_u,c_k [batch][m] (device or host per loc). */
 int sqpb200_qphandler_bounds(sqpb200_handle h, int mode, int n, int m, const double* delta,
                              const double* x_l, const double* x_u, const double* x_k,

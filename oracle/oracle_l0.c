@@ -156,10 +156,10 @@ double orc_inf_norm(const double* x, int n) {
 void orc_qp_bounds(int mode, int n, int m, double delta, const double* x_l, const double* x_u,
                    const double* x_k, const double* c_l, const double* c_u, const double* c_k,
                    double* lb, double* ub, double* lbA, double* ubA) {
-    if (mode == 0 || mode == 1) {
+    if (mode == 0 || mode == 1 || mode == 3) {
         for (int i = 0; i < m; i++) {
             lbA[i] = c_l[i] - c_k[i];
-            if (mode == 0) ubA[i] = c_u[i] - c_k[i]; /* update_bounds never refreshes ubA */
+            if (mode != 1) ubA[i] = c_u[i] - c_k[i]; /* mode 1: update_bounds never refreshes ubA; mode 3: QORE-branch behaviour */
         }
     }
     for (int i = 0; i < n; i++) {

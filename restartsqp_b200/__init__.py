@@ -8,7 +8,8 @@ from .sqp_types import (ActiveType, Exitflag, IdentityInfo, NLPInfo, Options, QP
 from . import _capi as capi
 from .qp_interface import CudaQPInterface
 from .qp_handler import QPhandler
+from .sqp_driver import BatchedSQP, HS071
 
 __all__ = ["ActiveType", "Exitflag", "IdentityInfo", "NLPInfo", "Options", "QPType", "Solver", "SpTripletMat",
            "Stats", "QP_NOT_OPTIMAL", "LP_NOT_OPTIMAL", "QP_INTERNAL_ERROR", "INVALID_WORKING_SET", "INF", "capi",
-           "CudaQPInterface", "QPhandler"]
+           "CudaQPInterface", "QPhandler", "BatchedSQP", "HS071"]

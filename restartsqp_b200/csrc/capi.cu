@@ -489,7 +489,7 @@ int sqpb200_get_vectors(sqpb200_handle h, int which, double* vals, int loc) {
 int sqpb200_qphandler_bounds(sqpb200_handle h, int mode, int n, int m, const double* delta, const double* x_l,
                              const double* x_u, const double* x_k, const double* c_l, const double* c_u,
                              const double* c_k, int loc) {
-    if (!h || n + 2 * m != h->nV || m != h->nC || mode < 0 || mode > 2) return SQPB200_ERR_INVALID;
+    if (!h || n + 2 * m != h->nV || m != h->nC || mode < 0 || mode > 3) return SQPB200_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     size_t B = h->batch, bn = B * n * 8, bm = B * m * 8;
     const void *dd, *dxl, *dxu, *dxk, *dcl = nullptr, *dcu = nullptr, *dck = nullptr;

@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(256) qphandler_bounds_kernel(int batch, int mo
         }
         if (i < m && mode != 2) {
             lbA[b * m + i] = c_l[b * m + i] - c_k[b * m + i];
-            if (mode == 0) ubA[b * m + i] = c_u[b * m + i] - c_k[b * m + i];  // update_bounds never refreshes ubA
+            // mode 1 = update_bounds of the non-QORE branch: ubA is never refreshed (src/QPhandler.cpp:358-360);
+            // mode 3 = update_bounds refreshing both sides, as the QORE branch does (:377-382)
+            if (mode == 0 || mode == 3) ubA[b * m + i] = c_u[b * m + i] - c_k[b * m + i];
         }
     }
 }

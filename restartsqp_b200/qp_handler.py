@@ -5,18 +5,17 @@ delta and penalty rho, SoA arrays [batch][...]) to QP data, owns one CudaQPInter
 exposes the reference's method names.  The bound/gradient construction of set_bounds / set_g /
 update_* runs as device kernels behind sqpb200_qphandler_bounds / sqpb200_qphandler_g.
 """
-import ctypes as C
-
 import numpy as np
 
 from . import _capi as capi
-from .qp_interface import CudaQPInterface, _check
+from .qp_interface import CudaQPInterface
 from .sqp_types import (IdentityInfo, NLPInfo, Options, QPType, Stats, SpTripletMat, QP_NOT_OPTIMAL, SQRT_M_EPS,
                         ActiveType)
 
 
 class QPhandler:
-    def __init__(self, nlp_info: NLPInfo, qptype: QPType, options: Options = None, batch=1, device=0, **kw):
+    def __init__(self, nlp_info: NLPInfo, qptype: QPType, options: Options = None, batch=1, device=0, backend=None,
+                 refresh_ubA=False, **kw):
         self.nlp_info_ = nlp_info
         self.options = options if options is not None else Options()
         self.batch = batch
@@ -26,8 +25,15 @@ class QPhandler:
         # I_info_A_: two identity blocks [J I -I], src/QPhandler.cpp:41-51
         self.I_info_A_ = IdentityInfo(irow=np.array([1, 1], np.int32), jcol=np.array([n + 1, n + m + 1], np.int32),
                                       size=np.array([m, m], np.int32), value=np.array([1.0, -1.0]))
-        self.solverInterface_ = CudaQPInterface(nlp_info, qptype, self.options, batch=batch, device=device, **kw)
+        # the backend switch of src/QPhandler.cpp:58-76; `backend` lets a caller plug another object with the
+        # CudaQPInterface method set (the tests plug the CPU oracle there to check the host logic without a GPU)
+        self.solverInterface_ = backend if backend is not None else CudaQPInterface(nlp_info, qptype, self.options, batch=batch,
+                                                                                    device=device, **kw)
         self.qptype = QPType(qptype)
+        # False: update_bounds leaves ubA stale exactly like the reference's non-QORE branch;
+        # True: both sides are refreshed, as its QORE branch does.  The batched SQP driver needs True to make progress
+        # on problems with finite upper constraint bounds.
+        self.refresh_ubA = bool(refresh_ubA)
         self.qpOptimalStatus_ = None
 
     # -- helpers
@@ -40,24 +46,16 @@ class QPhandler:
 
     def _bounds(self, mode, delta, x_l, x_u, x_k, c_l=None, c_u=None, c_k=None):
         n, m = self.nlp_info_.nVar, self.nlp_info_.nCon
-        si = self.solverInterface_
         if capi._is_torch(x_k):
             import torch
             d = delta if capi._is_torch(delta) else torch.full((self.batch,), float(delta), dtype=torch.float64, device=x_k.device)
         else:
             d = np.ascontiguousarray(np.broadcast_to(np.asarray(delta, dtype=np.float64), (self.batch,)))
-        args = [d, self._b(x_l, n), self._b(x_u, n), self._b(x_k, n)]
         if mode != 2 and m > 0:
-            args += [self._b(c_l, m), self._b(c_u, m), self._b(c_k, m)]
+            cs = [self._b(c_l, m), self._b(c_u, m), self._b(c_k, m)]
         else:
-            args += [None, None, None]
-        ptrs, loc = [], capi.LOC_HOST
-        for a in args:
-            p, l = capi.ptr(a)
-            ptrs.append(p)
-            if a is not None:
-                loc = l
-        _check(si.h, si.L.sqpb200_qphandler_bounds(si.h, mode, n, m, *ptrs, loc), "qphandler_bounds")
+            cs = [None, None, None]
+        self.solverInterface_.qphandler_bounds(mode, n, m, d, self._b(x_l, n), self._b(x_u, n), self._b(x_k, n), *cs)
 
     # -- src/QPhandler.cpp:167-261
     def set_bounds(self, delta, x_l, x_u, x_k, c_l, c_u, c_k):
@@ -65,7 +63,7 @@ class QPhandler:
 
     # -- src/QPhandler.cpp:342-419 (lbA refreshed, ubA not: SURVEY.md 8a quirk 2)
     def update_bounds(self, delta, x_l, x_u, x_k, c_l, c_u, c_k):
-        self._bounds(1, delta, x_l, x_u, x_k, c_l, c_u, c_k)
+        self._bounds(3 if self.refresh_ubA else 1, delta, x_l, x_u, x_k, c_l, c_u, c_k)
 
     # -- src/QPhandler.cpp:533-567
     def update_delta(self, delta, x_l, x_u, x_k):
@@ -73,7 +71,6 @@ class QPhandler:
 
     def _g(self, grad, rho):
         n, m = self.nlp_info_.nVar, self.nlp_info_.nCon
-        si = self.solverInterface_
         gr = None if grad is None else self._b(grad, n)
         if rho is None:
             rh = None
@@ -81,10 +78,7 @@ class QPhandler:
             rh = rho.contiguous()
         else:
             rh = np.ascontiguousarray(np.broadcast_to(np.asarray(rho, dtype=np.float64), (self.batch,)))
-        pg, l1 = capi.ptr(gr)
-        pr, l2 = capi.ptr(rh)
-        loc = l1 if gr is not None else l2
-        _check(si.h, si.L.sqpb200_qphandler_g(si.h, n, m, pg, pr, loc), "qphandler_g")
+        self.solverInterface_.qphandler_g(n, m, gr, rh)
 
     # -- src/QPhandler.cpp:272-297 (and the LP overload :657-660 when grad is None)
     def set_g(self, grad, rho=None):

@@ -137,6 +137,25 @@ class CudaQPInterface:
         p, loc = capi.ptr(v)
         _check(self.h, self.L.sqpb200_set_values_csc(self.h, which, p, loc, int(v.ndim == 1)), "set_values_csc")
 
+    # ------------------------------------------------------------------ batched QPhandler data kernels
+    def qphandler_bounds(self, mode, n, m, delta, x_l, x_u, x_k, c_l=None, c_u=None, c_k=None):
+        """QPhandler::set_bounds (mode 0) / update_bounds (1) / update_delta (2) on the device, per-instance delta
+        (src/QPhandler.cpp:167-261, 342-419, 533-567).  Arrays are [batch][n] / [batch][m] (numpy or CUDA tensors)."""
+        args = [delta, x_l, x_u, x_k] + ([c_l, c_u, c_k] if (mode != 2 and m > 0) else [None, None, None])
+        ptrs, loc = [], capi.LOC_HOST
+        for a in args:
+            p, l = capi.ptr(a)
+            ptrs.append(p)
+            if a is not None:
+                loc = l
+        _check(self.h, self.L.sqpb200_qphandler_bounds(self.h, mode, n, m, *ptrs, loc), "qphandler_bounds")
+
+    def qphandler_g(self, n, m, grad, rho):
+        """g = [grad ; rho*1] (src/QPhandler.cpp:272-297, 430-463); grad [batch][n] or None, rho [batch] or None."""
+        pg, l1 = capi.ptr(grad)
+        pr, l2 = capi.ptr(rho)
+        _check(self.h, self.L.sqpb200_qphandler_g(self.h, n, m, pg, pr, l1 if grad is not None else l2), "qphandler_g")
+
     def reset_constraints(self):
         """src/qpOASESInterface.cpp:897-902."""
         for w, n in ((capi.VEC_LB, self.nV_), (capi.VEC_UB, self.nV_), (capi.VEC_LBA, self.nC_), (capi.VEC_UBA, self.nC_)):

@@ -164,6 +164,23 @@ static void rot_cols(double* M, int ld, int row_lo, int row_hi, int j, double c,
     }
 }
 
+/* Chain of rotations that compresses w[0..cnt) into its last entry, rotation j acting on columns (j, j+1).
+ * Written with the running sum of squares S_j = w_0^2 + ... + w_j^2 (accumulated left to right) so that every
+ * rotation can be formed independently once the prefix sums are known: with j0 the first non-zero entry,
+ * a_j = 0 (j < j0), a_j0 = w_j0, a_j = sqrt(S_j) (j > j0); rotation j is the identity while a_j == 0 and
+ * c_j = w_{j+1}/h, s_j = a_j/h, h = sqrt(S_{j+1}) afterwards.  Returns the compressed value a_{cnt-1}. */
+static double rotation_chain(const double* w, int cnt, double* cs, double* sn) {
+    double S = w[0] * w[0];
+    double a = w[0];
+    for (int j = 0; j + 1 < cnt; j++) {
+        double Sn = S + w[j + 1] * w[j + 1];
+        if (a == 0.0) { cs[j] = 1.0; sn[j] = 0.0; a = w[j + 1]; }
+        else { double h = sqrt(Sn); cs[j] = w[j + 1] / h; sn[j] = a / h; a = h; }
+        S = Sn;
+    }
+    return a;
+}
+
 /* ------------------------------------------------------------ projected Cholesky */
 /* R'R = Z'(H+regI)_FR,FR Z, full recomputation (qpOASES computeProjectedCholesky under
  * enableCholeskyRefactorisation=1).  Returns 0 on success, 1 + failing pivot otherwise. */
@@ -257,13 +274,9 @@ static void constraint_w(orc_qp* q, int c, double* wz2, double* a2) {
 /* requires w from constraint_w and w_Z != 0 */
 static void add_constraint(orc_qp* q, int c, int status) {
     int nV = q->nV, nFR = q->nFR, nAC = q->nAC, nZ = nFR - nAC;
-    double cs, sn, r;
-    for (int j = 0; j + 1 < nZ; j++) {
-        givens(q->w[j], q->w[j + 1], &cs, &sn, &r);
-        q->w[j] = 0.0; q->w[j + 1] = r;
-        rot_cols(q->Q, nV, 0, nFR, j, cs, sn);
-    }
-    for (int j = 0; j < nFR; j++) q->T[(size_t)nAC * nV + j] = (j >= nZ - 1) ? q->w[j] : 0.0;
+    double r = rotation_chain(q->w, nZ, q->t2, q->t3);
+    for (int j = 0; j + 1 < nZ; j++) rot_cols(q->Q, nV, 0, nFR, j, q->t2[j], q->t3[j]);
+    for (int j = 0; j < nFR; j++) q->T[(size_t)nAC * nV + j] = (j > nZ - 1) ? q->w[j] : ((j == nZ - 1) ? r : 0.0);
     q->AC[nAC] = c; q->posAC[c] = nAC; q->nAC = nAC + 1; q->sC[c] = status;
     q->flops += 6.0 * nZ * nFR;
 }
@@ -298,10 +311,9 @@ static double bound_w(orc_qp* q, int v) {
 /* requires w from bound_w and w_Z != 0 */
 static void add_bound(orc_qp* q, int v, int status) {
     int nV = q->nV, nFR = q->nFR, nAC = q->nAC, nZ = nFR - nAC, p = q->posFR[v];
-    double cs, sn, r;
+    rotation_chain(q->w, nFR, q->t2, q->t3);
     for (int j = 0; j + 1 < nFR; j++) {
-        givens(q->w[j], q->w[j + 1], &cs, &sn, &r);
-        q->w[j] = 0.0; q->w[j + 1] = r;
+        double cs = q->t2[j], sn = q->t3[j];
         rot_cols(q->Q, nV, 0, nFR, j, cs, sn);
         if (j >= nZ - 1) {
             int lo = nFR - 2 - j; if (lo < 0) lo = 0;

@@ -345,22 +345,33 @@ struct QP {
         wz2 = z2; a2 = s2;
         SYNC();
     }
-    // chain of rotations compressing w[0..cnt) into w[cnt-1]; writes (c,s) to t2,t3; returns r
+    // Chain of rotations compressing w[0..cnt) into its last entry, rotation j acting on columns (j, j+1); writes
+    // (c_j, s_j) to t2, t3 and returns the compressed value.  Formed from the running sums of squares
+    // S_j = w_0^2 + ... + w_j^2 (each lane accumulates its own prefix left to right, exactly the oracle's sequence), so
+    // the cnt-1 square roots and 2(cnt-1) divisions run in parallel instead of as one scalar recurrence.
     static __device__ QP_FN double rotation_chain(int cnt) {
         QP_CTX
         double *t2 = V_(t2), *t3 = V_(t3);
         const double* w = V_(w);
-        if (lane == 0) {
-            double a0 = w[0];
-            _Pragma("unroll 1") for (int j = 0; j + 1 < cnt; j++) {
-                double c, s;
-                givens(a0, w[j + 1], c, s, a0);
-                t2[j] = c; t3[j] = s;
-            }
-            t2[cnt - 1] = a0;
+        _Pragma("unroll 1") for (int j = lane; j + 1 < cnt; j += 32) {
+            double S = w[0] * w[0];
+            bool anyprev = false;  // a non-zero entry before j: then a_j = sqrt(S_j), else a_j = w_j (signed)
+            _Pragma("unroll 1") for (int k = 1; k <= j; k++) { anyprev = anyprev || (w[k - 1] != 0.0); S = S + w[k] * w[k]; }
+            const double a = anyprev ? sqrt(S) : w[j];
+            if (a == 0.0) { t2[j] = 1.0; t3[j] = 0.0; }
+            else { const double h = sqrt(S + w[j + 1] * w[j + 1]); t2[j] = w[j + 1] / h; t3[j] = a / h; }
+        }
+        // compressed value a_{cnt-1}
+        double r;
+        {
+            const int j = cnt - 1;
+            double S = w[0] * w[0];
+            bool anyprev = false;
+            _Pragma("unroll 1") for (int k = 1; k <= j; k++) { anyprev = anyprev || (w[k - 1] != 0.0); S = S + w[k] * w[k]; }
+            r = anyprev ? sqrt(S) : w[j];
         }
         SYNC();
-        return t2[cnt - 1];
+        return r;
     }
     static __device__ QP_FN void add_constraint(int c, int status) {
         QP_CTX
@@ -1012,11 +1023,10 @@ struct QP {
 // -------------------------------------------------------------------------------------------
 // kernel: one QP per warp, CTA_THREADS/32 QPs per CTA
 // -------------------------------------------------------------------------------------------
-#ifndef QP_MIN_BLOCKS
-#define QP_MIN_BLOCKS 1
-#endif
+// 512 / CTA_THREADS resident CTAs = 16 warps per SM = at most 128 registers per thread (measured: 64 or 80 registers
+// spill and lose on the larger QPs, 142 registers lose occupancy on the small ones).
 template <int CTA_THREADS>
-__global__ void __launch_bounds__(CTA_THREADS, QP_MIN_BLOCKS) qp_solve_kernel(const __grid_constant__ QPKernelArgs A) {
+__global__ void __launch_bounds__(CTA_THREADS, 512 / CTA_THREADS) qp_solve_kernel(const __grid_constant__ QPKernelArgs A) {
     constexpr int TEAMS = CTA_THREADS / 32;
     // stage the launch arguments and the 16-bit pattern once per CTA
     {

@@ -75,7 +75,7 @@ typedef struct {
     int enable_flipping; /* 1 */
     int enable_ramping;  /* 1 */
     int enable_drift;    /* 1 */
-    int team_size;       /* threads cooperating on one QP: 0 = auto; only 32 (one warp per QP) is built this round */
+    int team_size;       /* 0 = auto; 32 = one warp per QP (shared-memory resident); 1024 = one CTA per QP (slice in global memory, large QPs) */
     int keep_state;      /* 1: keep working set + factors resident for hot starts */
     int factor_cap;      /* capacity of the TQ/Cholesky factors = max. simultaneously free variables held in shared
                             memory: 0 = auto (n + m/2 + 2 for nV = n + 2m), -1 = nV.  Instances that need more are

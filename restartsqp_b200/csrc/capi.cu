@@ -64,6 +64,11 @@ struct sqpb200_handle_s {
     int team = 0, teams_per_cta = 0, smem_cta = 0;
     SolveCfg cfg_main, cfg_rescue;
     bool have_rescue = false;
+    // one-QP-per-CTA path (QPs whose slice does not fit in shared memory): slices and 32-bit pattern in global memory
+    bool large = false;
+    int* dgpat = nullptr;
+    double* dgwork = nullptr;
+    int large_slice_doubles = 0;
 };
 
 static int grid_for(long long total, int block) {
@@ -164,7 +169,7 @@ int sqpb200_destroy(sqpb200_handle h) {
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dAp, h->dAi, h->dArp, h->dAci, h->dAperm, h->dAsrc, h->dHp, h->dHi, h->dHsrc, h->dAval, h->dHval,
                     h->dg, h->dlb, h->dub, h->dlbA, h->dubA, h->dx, h->dy, h->dobj, h->dkkt, h->dstatus, h->diters,
-                    h->dWB, h->dWC, h->dwsB, h->dwsC, h->dmask, h->dstate, h->stage};
+                    h->dWB, h->dWC, h->dwsB, h->dwsC, h->dmask, h->dstate, h->stage, h->dgpat, h->dgwork};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -282,6 +287,7 @@ static int finish_structure_A(sqpb200_handle h) {
         CK(cudaGetLastError());
     }
     h->A_set = true;
+    if (h->dgpat) { cudaFree(h->dgpat); h->dgpat = nullptr; }
     return 0;
 }
 
@@ -563,9 +569,8 @@ static bool config_for_cap(sqpb200_handle h, int cap, SolveCfg& cfg) {
 }
 
 static int choose_config(sqpb200_handle h) {
-    if (h->zA >= 32768 || h->zH >= 32768) { h->err = "pattern too large for 16-bit staged indices"; return SQPB200_ERR_TOO_LARGE; }
-    // One warp per QP: the only team size shipped this round (see the note in qp_kernel.cuh).
-    if (h->opt.team_size != 0 && h->opt.team_size != 32) { h->err = "team_size must be 0 (auto) or 32"; return SQPB200_ERR_INVALID; }
+    // One warp per QP: the only shared-memory resident team size shipped this round (see the note in qp_kernel.cuh).
+    if (h->opt.team_size != 0 && h->opt.team_size != 32 && h->opt.team_size != 1024) { h->err = "team_size must be 0 (auto), 32 (warp per QP) or 1024 (CTA per QP)"; return SQPB200_ERR_INVALID; }
     const int nV = h->nV, nC = h->nC;
     // Factor capacity.  On the l1-penalty QPs of RestartSQP (x = [p; u; v], nV = n + 2m) the number of simultaneously free
     // variables stays near n: slacks are free only on violated rows.  auto: n + ceil(m/2) + 2; instances that need more are
@@ -576,10 +581,26 @@ static int choose_config(sqpb200_handle h) {
         cap = n_est + (nC + 1) / 2 + 2;
     }
     if (cap < 0 || cap > nV) cap = nV;
-    h->have_rescue = config_for_cap(h, nV, h->cfg_rescue);
-    if (!config_for_cap(h, cap, h->cfg_main)) {
-        h->err = "QP too large for the shared-memory resident kernel (nV=" + std::to_string(nV) + ", capacity " + std::to_string(cap) + ")";
-        return SQPB200_ERR_TOO_LARGE;
+    const bool fits16 = h->zA < 32768 && h->zH < 32768;
+    h->large = (h->opt.team_size == 1024);
+    if (!h->large) {
+        h->have_rescue = fits16 && config_for_cap(h, nV, h->cfg_rescue);
+        // without a rescue configuration the main launch must hold every QP: full capacity
+        if (!fits16 || !h->have_rescue || !config_for_cap(h, cap, h->cfg_main)) {
+            if (h->opt.team_size == 32) {
+                h->err = "QP too large for the shared-memory resident kernel (nV=" + std::to_string(nV) + ", capacity " + std::to_string(cap) + ")";
+                return SQPB200_ERR_TOO_LARGE;
+            }
+            h->large = true;
+        }
+    }
+    if (h->large) {
+        QPKernelArgs a;
+        fill_dims(h, a, nV);
+        h->large_slice_doubles = a.slice_doubles;
+        h->team = 1024; h->teams_per_cta = 1; h->smem_cta = 0;
+        h->slice_doubles = a.slice_doubles;
+        return 0;
     }
     h->team = 32; h->teams_per_cta = h->cfg_main.teams; h->smem_cta = h->cfg_main.smem;
     h->slice_doubles = h->cfg_main.slice_doubles;
@@ -591,6 +612,35 @@ namespace sqpb200 {
 cudaError_t launch_qp_solve_32_128(const QPKernelArgs&, int, cudaStream_t);
 cudaError_t launch_qp_solve_32_64(const QPKernelArgs&, int, cudaStream_t);
 cudaError_t launch_qp_solve_32_32(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_large(const QPKernelArgs&, cudaStream_t);
+int qp_solve_large_threads();
+}
+
+// global-memory slices and the 32-bit pattern of the one-QP-per-CTA kernel
+static int prepare_large(sqpb200_handle h, const QPKernelArgs& a) {
+    if (!h->dgwork) {
+        if (dev_alloc(h, &h->dgwork, (size_t)h->batch * a.slice_doubles)) return SQPB200_ERR_CUDA;  // zeroed: "not initialised"
+    }
+    if (!h->dgpat) {
+        std::vector<int> pat((size_t)a.pat_shorts + 4, 0);
+        std::vector<int> Arp(h->nC + 1, 0), Aci(h->zA), Aperm(h->zA);
+        for (int e = 0; e < h->zA; e++) Arp[h->Ai[e] + 1]++;
+        for (int r = 0; r < h->nC; r++) Arp[r + 1] += Arp[r];
+        std::vector<int> fill(Arp.begin(), Arp.end() - 1);
+        for (int c = 0; c < h->nV; c++)
+            for (int e = h->Ap[c]; e < h->Ap[c + 1]; e++) { int r = h->Ai[e]; Aci[fill[r]] = c; Aperm[fill[r]] = e; fill[r]++; }
+        std::copy(h->Ap.begin(), h->Ap.end(), pat.begin() + a.pAp);
+        std::copy(h->Ai.begin(), h->Ai.end(), pat.begin() + a.pAi);
+        std::copy(Arp.begin(), Arp.end(), pat.begin() + a.pArp);
+        std::copy(Aci.begin(), Aci.end(), pat.begin() + a.pAci);
+        std::copy(Aperm.begin(), Aperm.end(), pat.begin() + a.pAperm);
+        if (a.zH > 0) {
+            std::copy(h->Hp.begin(), h->Hp.end(), pat.begin() + a.pHp);
+            std::copy(h->Hi.begin(), h->Hi.end(), pat.begin() + a.pHi);
+        }
+        if (upload_vec(h, &h->dgpat, pat)) return SQPB200_ERR_CUDA;
+    }
+    return 0;
 }
 static cudaError_t launch_cfg(const SolveCfg& cfg, const QPKernelArgs& a, cudaStream_t stream) {
     switch (cfg.teams) {
@@ -609,7 +659,7 @@ int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned cha
     if (!is_lp && !h->H_set) { h->err = "set_structure_H has not been called"; return SQPB200_ERR_STATE; }
     int rc = choose_config(h);
     if (rc) return rc;
-    if (h->opt.keep_state && !h->dstate) {
+    if (!h->large && h->opt.keep_state && !h->dstate) {
         if (dev_alloc(h, &h->dstate, (size_t)h->batch * h->cfg_main.state_doubles)) return SQPB200_ERR_CUDA;
     }
     // init / hotstart decision: src/qpOASESInterface.cpp:141-211 with get_Matrix_change_status :817-833
@@ -627,7 +677,7 @@ int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned cha
         }
     }
     QPKernelArgs a;
-    fill_dims(h, a, h->cfg_main.cap);
+    fill_dims(h, a, h->large ? h->nV : h->cfg_main.cap);
     a.max_iter = maxiter > 0 ? maxiter : (is_lp ? h->opt.lp_maxiter : h->opt.qp_maxiter);
     a.flags = (h->opt.enable_flipping ? FLAG_FLIPPING : 0) | (h->opt.enable_ramping ? FLAG_RAMPING : 0) |
               (h->opt.enable_drift ? FLAG_DRIFT : 0) | (h->opt.keep_state ? FLAG_KEEP_STATE : 0);
@@ -643,6 +693,19 @@ int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned cha
     a.x = h->dx; a.y = h->dy; a.obj = h->dobj; a.kkt = h->dkkt; a.status = h->dstatus; a.iters = h->diters;
     a.wsB = h->dwsB; a.wsC = h->dwsC; a.WB = h->dWB; a.WC = h->dWC;
     a.state = h->dstate;
+    if (h->large) {
+        rc = prepare_large(h, a);
+        if (rc) return rc;
+        a.gpat = h->dgpat; a.gwork = h->dgwork;
+        CK(cudaEventRecord(h->ev0, h->stream));
+        cudaError_t el = launch_qp_solve_large(a, h->stream);
+        if (el != cudaSuccess) { h->err = std::string("qp_solve_large_kernel launch: ") + cudaGetErrorString(el); return SQPB200_ERR_CUDA; }
+        CK(cudaEventRecord(h->ev1, h->stream));
+        h->launches++;
+        h->upd_A = h->upd_H = h->upd_g = h->upd_bounds = false;
+        h->first_solved = true;
+        return 0;
+    }
     CK(cudaEventRecord(h->ev0, h->stream));
     cudaError_t e = launch_cfg(h->cfg_main, a, h->stream);
     if (e != cudaSuccess) { h->err = std::string("qp_solve_kernel launch: ") + cudaGetErrorString(e); return SQPB200_ERR_CUDA; }

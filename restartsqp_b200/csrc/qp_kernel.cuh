@@ -66,6 +66,8 @@ struct QPKernelArgs {
     const double *Aval, *Hval;
     const double *gN, *lbN, *ubN, *lbAN, *ubAN;
     const unsigned char* mask;
+    const int* gpat;   // TEAM > 32: the pattern as 32-bit indices in global memory, laid out by the p* offsets below
+    double* gwork;     // TEAM > 32: [batch][slice_doubles] global-memory slices (persist between solves: hot start in place)
     // outputs
     double *x, *y, *obj, *kkt;
     int *status, *iters;
@@ -126,14 +128,27 @@ __device__ __forceinline__ bool key_less(double t1, int p1, double t2, int p2) {
 
 #define QP_FN __noinline__
 
-// Context of the calling warp.  hdr: [0]=nFR [1]=nAC [2]=ramp_offset [3]=initialised.
+// TEAM = threads that cooperate on one QP.  32: one warp per QP, everything in the warp's shared-memory slice, pattern
+// staged as 16-bit indices.  > 32: the whole CTA works on one QP (large QPs); the slice lives in
+// global memory (sSlice; factors streamed through L1/L2), the pattern is read as 32-bit indices from global memory and
+// the team barrier is __syncthreads().
+template <int TEAM> struct PatIdx { typedef int type; };
+template <> struct PatIdx<32> { typedef short type; };
+__shared__ double* sSlice;     // TEAM > 32: this CTA's slice in global memory
+__shared__ double sRedT[32];   // TEAM > 32: scratch of the team-wide min reduction
+__shared__ int sRedP[32];
+
+// Context of the calling team.  hdr: [0]=nFR [1]=nAC [2]=ramp_offset [3]=initialised.
 #define QP_CTX                                                                                     \
-    const int lane = threadIdx.x & 31;                                                             \
-    double* const slice = qp_smem + (size_t)(threadIdx.x >> 5) * sA.slice_doubles;                 \
+    const int lane = (TEAM == 32) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;                    \
+    double* const slice = (TEAM == 32) ? qp_smem + (size_t)(threadIdx.x >> 5) * sA.slice_doubles : sSlice; \
     int* const hdr = reinterpret_cast<int*>(slice);                                                \
     const int nV = sA.nV, nC = sA.nC, ld = sA.ld, cap = sA.cap;                                    \
     (void)lane; (void)hdr; (void)nV; (void)nC; (void)ld; (void)cap;
-#define QP_PAT const short* const pat = reinterpret_cast<const short*>(qp_smem + (size_t)(blockDim.x >> 5) * sA.slice_doubles);
+#define QP_PAT                                                                                     \
+    const pidx* const pat = (TEAM == 32)                                                           \
+        ? reinterpret_cast<const pidx*>(qp_smem + (size_t)(blockDim.x >> 5) * sA.slice_doubles)   \
+        : reinterpret_cast<const pidx*>(sA.gpat);
 
 #define V_(name) (slice + sA.o##name)
 #define S_(k) (reinterpret_cast<short*>(slice + sA.oS) + (k))
@@ -145,17 +160,19 @@ __device__ __forceinline__ bool key_less(double t1, int p1, double t2, int p2) {
 #define posAC_ S_(3 * nV + 2 * nC)
 #define R_(a_, b_) RT[(a_) * ld + (b_)]
 #define T_(i, j) RT[(cap - 1 - (i)) * ld + (j)]
-#define SYNC() __syncwarp()
+#define SYNC() do { if (TEAM == 32) __syncwarp(); else __syncthreads(); } while (0)
 
-struct QP {
+template <int TEAM>
+struct QPT {
+    typedef typename PatIdx<TEAM>::type pidx;
     // ---------------------------------------------------------------- sparse products
     static __device__ QP_FN void mulH(const double* v, double* out) {  // out = (H + reg I) v (H symmetric: column gather)
         QP_CTX QP_PAT
-        const short *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
+        const pidx *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
         const double* Hv = V_(Hv);
         const bool has_H = sA.has_H && !sA.is_lp;
         const double reg = sA.is_lp ? QP_EPS_REG : 0.0;
-        _Pragma("unroll 1") for (int c = lane; c < nV; c += 32) {
+        _Pragma("unroll 1") for (int c = lane; c < nV; c += TEAM) {
             double s = 0.0;
             if (has_H) {
                 int e1 = Hp[c + 1];
@@ -168,10 +185,10 @@ struct QP {
     }
     static __device__ QP_FN void mulH_noreg(const double* v, double* out) {  // out = H v (objective / KKT epilogue)
         QP_CTX QP_PAT
-        const short *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
+        const pidx *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
         const double* Hv = V_(Hv);
         const bool has_H = sA.has_H && !sA.is_lp;
-        _Pragma("unroll 1") for (int c = lane; c < nV; c += 32) {
+        _Pragma("unroll 1") for (int c = lane; c < nV; c += TEAM) {
             double s = 0.0;
             if (has_H) {
                 int e1 = Hp[c + 1];
@@ -183,9 +200,9 @@ struct QP {
     }
     static __device__ QP_FN void mulA(const double* v, double* out) {
         QP_CTX QP_PAT
-        const short *Arp = pat + sA.pArp, *Aci = pat + sA.pAci, *Aperm = pat + sA.pAperm;
+        const pidx *Arp = pat + sA.pArp, *Aci = pat + sA.pAci, *Aperm = pat + sA.pAperm;
         const double* Av = V_(Av);
-        _Pragma("unroll 1") for (int r = lane; r < nC; r += 32) {
+        _Pragma("unroll 1") for (int r = lane; r < nC; r += TEAM) {
             double s = 0.0;
             int k1 = Arp[r + 1];
             _Pragma("unroll 1") for (int k = Arp[r]; k < k1; k++) s += Av[Aperm[k]] * v[Aci[k]];
@@ -195,9 +212,9 @@ struct QP {
     }
     static __device__ QP_FN void mulAT(const double* yc, double* out) {
         QP_CTX QP_PAT
-        const short *Ap = pat + sA.pAp, *Ai = pat + sA.pAi;
+        const pidx *Ap = pat + sA.pAp, *Ai = pat + sA.pAi;
         const double* Av = V_(Av);
-        _Pragma("unroll 1") for (int c = lane; c < nV; c += 32) {
+        _Pragma("unroll 1") for (int c = lane; c < nV; c += TEAM) {
             double s = 0.0;
             int e1 = Ap[c + 1];
             _Pragma("unroll 1") for (int e = Ap[c]; e < e1; e++) s += Av[e] * yc[Ai[e]];
@@ -206,8 +223,8 @@ struct QP {
         SYNC();
     }
     // A[r][c] via the CSR view (duplicates summed)
-    static __device__ __forceinline__ double A_entry(const short* pat, const double* Av, int r, int c) {
-        const short *Arp = pat + sA.pArp, *Aci = pat + sA.pAci, *Aperm = pat + sA.pAperm;
+    static __device__ __forceinline__ double A_entry(const pidx* pat, const double* Av, int r, int c) {
+        const pidx *Arp = pat + sA.pArp, *Aci = pat + sA.pAci, *Aperm = pat + sA.pAperm;
         double s = 0.0;
         int k1 = Arp[r + 1];
         _Pragma("unroll 1") for (int k = Arp[r]; k < k1; k++)
@@ -216,12 +233,20 @@ struct QP {
     }
 
     // ---------------------------------------------------------------- reductions
-    static __device__ __forceinline__ MinKey warp_min(double t, int pos) {
-#pragma unroll
+    // lexicographic (t, pos) minimum over the team, returned to every thread
+    static __device__ __forceinline__ MinKey team_min(double t, int pos) {
         _Pragma("unroll 1") for (int o = 16; o > 0; o >>= 1) {
             double t2_ = __shfl_xor_sync(0xffffffffu, t, o);
             int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
             if (key_less(t2_, p2, t, pos)) { t = t2_; pos = p2; }
+        }
+        if (TEAM > 32) {
+            __syncthreads();  // previous use of the scratch is over
+            if ((threadIdx.x & 31) == 0) { sRedT[threadIdx.x >> 5] = t; sRedP[threadIdx.x >> 5] = pos; }
+            __syncthreads();
+            t = sRedT[0]; pos = sRedP[0];
+            _Pragma("unroll 1") for (int k = 1; k < TEAM / 32; k++)
+                if (key_less(sRedT[k], sRedP[k], t, pos)) { t = sRedT[k]; pos = sRedP[k]; }
         }
         MinKey r; r.t = t; r.pos = pos;
         return r;
@@ -240,7 +265,7 @@ struct QP {
         double *t1 = V_(t1), *t2 = V_(t2);
         const double* Q = V_(Q);
         const short* posFR = posFR_;
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) { int p = posFR[i]; t1[i] = (p >= 0) ? Q[p * ld + b] : 0.0; }
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) { int p = posFR[i]; t1[i] = (p >= 0) ? Q[p * ld + b] : 0.0; }
         SYNC();
         mulH(t1, t2);
     }
@@ -252,7 +277,7 @@ struct QP {
         double* RT = V_(RT);
         if (sA.is_lp) {
             double sr = sqrt(QP_EPS_REG);
-            _Pragma("unroll 1") for (int k = lane; k < nZ * nZ; k += 32) { int a_ = k / nZ, b_ = k % nZ; R_(a_, b_) = (a_ == b_) ? sr : 0.0; }
+            _Pragma("unroll 1") for (int k = lane; k < nZ * nZ; k += TEAM) { int a_ = k / nZ, b_ = k % nZ; R_(a_, b_) = (a_ == b_) ? sr : 0.0; }
             SYNC();
             return 0;
         }
@@ -260,7 +285,7 @@ struct QP {
         const short* FR = FR_;
         _Pragma("unroll 1") for (int b = 0; b < nZ; b++) {
             proj_column(b);
-            _Pragma("unroll 1") for (int a_ = lane; a_ <= b; a_ += 32) {
+            _Pragma("unroll 1") for (int a_ = lane; a_ <= b; a_ += TEAM) {
                 double s = 0.0;
                 _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
                 R_(a_, b) = s;
@@ -269,7 +294,7 @@ struct QP {
         }
         // row-wise Cholesky: R'R = M, same per-element summation order as the column version
         _Pragma("unroll 1") for (int i = 0; i < nZ; i++) {
-            _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += 32) {
+            _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += TEAM) {
                 double s = R_(i, j);
                 _Pragma("unroll 1") for (int k = 0; k < i; k++) s -= R_(k, i) * R_(k, j);
                 R_(i, j) = s;
@@ -279,8 +304,8 @@ struct QP {
             SYNC();  // all lanes hold d before anyone rewrites R(i,i): the branch below is warp-uniform
             if (!(d > QP_ZERO)) return 1 + i;
             double dd = sqrt(d);
-            _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += 32) R_(i, j) = (j == i) ? dd : R_(i, j) / dd;
-            _Pragma("unroll 1") for (int j = lane; j < i; j += 32) R_(i, j) = 0.0;
+            _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += TEAM) R_(i, j) = (j == i) ? dd : R_(i, j) / dd;
+            _Pragma("unroll 1") for (int j = lane; j < i; j += TEAM) R_(i, j) = 0.0;
             SYNC();
         }
         return 0;
@@ -291,7 +316,7 @@ struct QP {
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC, b = nZ - 1;
         double *RT = V_(RT), *w = V_(w);
         if (sA.is_lp) {
-            _Pragma("unroll 1") for (int a_ = lane; a_ < b; a_ += 32) { R_(a_, b) = 0.0; R_(b, a_) = 0.0; }
+            _Pragma("unroll 1") for (int a_ = lane; a_ < b; a_ += TEAM) { R_(a_, b) = 0.0; R_(b, a_) = 0.0; }
             if (lane == 0) R_(b, b) = sqrt(QP_EPS_REG);
             SYNC();
             return 1;
@@ -299,7 +324,7 @@ struct QP {
         const double *Q = V_(Q), *t2 = V_(t2);
         const short* FR = FR_;
         proj_column(b);
-        _Pragma("unroll 1") for (int a_ = lane; a_ <= b; a_ += 32) {
+        _Pragma("unroll 1") for (int a_ = lane; a_ <= b; a_ += TEAM) {
             double s = 0.0;
             _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
             w[a_] = s;
@@ -310,7 +335,7 @@ struct QP {
             double rk = w[k] / R_(k, k);
             SYNC();
             if (lane == 0) R_(k, b) = rk;
-            _Pragma("unroll 1") for (int i = k + 1 + lane; i < b; i += 32) w[i] -= R_(k, i) * rk;
+            _Pragma("unroll 1") for (int i = k + 1 + lane; i < b; i += TEAM) w[i] -= R_(k, i) * rk;
             SYNC();
         }
         double rho2 = w[b];
@@ -319,7 +344,7 @@ struct QP {
         SYNC();  // every lane has read w[b] / R(.,b) before a caller may overwrite them (uniform decision)
         if (!ok) return 0;
         if (lane == 0) R_(b, b) = sqrt(rho2);
-        _Pragma("unroll 1") for (int a_ = lane; a_ < b; a_ += 32) R_(b, a_) = 0.0;
+        _Pragma("unroll 1") for (int a_ = lane; a_ < b; a_ += TEAM) R_(b, a_) = 0.0;
         SYNC();
         return 1;
     }
@@ -331,9 +356,9 @@ struct QP {
         double *a = V_(a), *w = V_(w);
         const double *Q = V_(Q), *Av = V_(Av);
         const short* FR = FR_;
-        _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) a[p] = A_entry(pat, Av, c, FR[p]);
+        _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) a[p] = A_entry(pat, Av, c, FR[p]);
         SYNC();
-        _Pragma("unroll 1") for (int j = lane; j < nFR; j += 32) {
+        _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) {
             double s = 0.0;
             _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * a[p];
             w[j] = s;
@@ -353,7 +378,7 @@ struct QP {
         QP_CTX
         double *t2 = V_(t2), *t3 = V_(t3);
         const double* w = V_(w);
-        _Pragma("unroll 1") for (int j = lane; j + 1 < cnt; j += 32) {
+        _Pragma("unroll 1") for (int j = lane; j + 1 < cnt; j += TEAM) {
             double S = w[0] * w[0];
             bool anyprev = false;  // a non-zero entry before j: then a_j = sqrt(S_j), else a_j = w_j (signed)
             _Pragma("unroll 1") for (int k = 1; k <= j; k++) { anyprev = anyprev || (w[k - 1] != 0.0); S = S + w[k] * w[k]; }
@@ -379,7 +404,7 @@ struct QP {
         double *Q = V_(Q), *RT = V_(RT);
         const double *t2 = V_(t2), *t3 = V_(t3), *w = V_(w);
         double r = rotation_chain(nZ);
-        _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) {
+        _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
             double* q = Q + p * ld;
             double qa = q[0];
             _Pragma("unroll 1") for (int j = 0; j + 1 < nZ; j++) {
@@ -389,7 +414,7 @@ struct QP {
             }
             if (nZ > 0) q[nZ - 1] = qa;
         }
-        _Pragma("unroll 1") for (int j = lane; j < nFR; j += 32) T_(nAC, j) = (j > nZ - 1) ? w[j] : ((j == nZ - 1) ? r : 0.0);
+        _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) T_(nAC, j) = (j > nZ - 1) ? w[j] : ((j == nZ - 1) ? r : 0.0);
         if (lane == 0) { AC_[nAC] = (short)c; posAC_[c] = (short)nAC; sC_[c] = (short)status; hdr[1] = nAC + 1; }
         SYNC();
     }
@@ -399,17 +424,18 @@ struct QP {
         double *Q = V_(Q), *RT = V_(RT);
         short *AC = AC_, *posAC = posAC_;
         const int k = posAC[c];
+        SYNC();  // every thread holds nAC and k before lane 0 rewrites them below (the loops may be empty)
         _Pragma("unroll 1") for (int i = k + 1; i < nAC; i++) {
             int cL = nFR - 1 - i;
             double cs, sn, r;
             givens(T_(i, cL), T_(i, cL + 1), cs, sn, r);
             SYNC();
-            _Pragma("unroll 1") for (int ii = i + lane; ii < nAC; ii += 32) {
+            _Pragma("unroll 1") for (int ii = i + lane; ii < nAC; ii += TEAM) {
                 double ta = T_(ii, cL), tb = T_(ii, cL + 1);
                 T_(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
                 T_(ii, cL + 1) = sn * ta + cs * tb;
             }
-            _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) {
+            _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
                 double qa = Q[p * ld + cL], qb = Q[p * ld + cL + 1];
                 Q[p * ld + cL] = cs * qa - sn * qb;
                 Q[p * ld + cL + 1] = sn * qa + cs * qb;
@@ -418,7 +444,7 @@ struct QP {
         }
         // shift rows k+1.. up by one (row i -> i-1): sequential over rows, lanes over columns
         _Pragma("unroll 1") for (int i = k + 1; i < nAC; i++) {
-            _Pragma("unroll 1") for (int j = lane; j < nFR; j += 32) T_(i - 1, j) = T_(i, j);
+            _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) T_(i - 1, j) = T_(i, j);
             SYNC();
         }
         if (lane == 0) {
@@ -432,7 +458,7 @@ struct QP {
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC, p = posFR_[v];
         double* w = V_(w);
         const double* Q = V_(Q);
-        _Pragma("unroll 1") for (int j = lane; j < nFR; j += 32) w[j] = Q[p * ld + j];
+        _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) w[j] = Q[p * ld + j];
         SYNC();
         double z2 = 0.0;
         _Pragma("unroll 1") for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
@@ -447,7 +473,7 @@ struct QP {
         short *FR = FR_, *posFR = posFR_;
         const int p = posFR[v];
         rotation_chain(nFR);
-        _Pragma("unroll 1") for (int pp = lane; pp < nFR; pp += 32) {
+        _Pragma("unroll 1") for (int pp = lane; pp < nFR; pp += TEAM) {
             double* q = Q + pp * ld;
             double qa = q[0];
             _Pragma("unroll 1") for (int j = 0; j + 1 < nFR; j++) {
@@ -458,7 +484,7 @@ struct QP {
             q[nFR - 1] = qa;
         }
         // T rows: row i is touched by rotations j >= nFR-2-i (and j >= nZ-1)
-        _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) {
             int j0 = nFR - 2 - i; if (j0 < nZ - 1) j0 = nZ - 1; if (j0 < 0) j0 = 0;
             double ta = T_(i, j0);
             _Pragma("unroll 1") for (int j = j0; j + 1 < nFR; j++) {
@@ -471,7 +497,7 @@ struct QP {
         SYNC();
         const int last = nFR - 1;
         if (p != last) {
-            _Pragma("unroll 1") for (int j = lane; j < nFR - 1; j += 32) Q[p * ld + j] = Q[last * ld + j];
+            _Pragma("unroll 1") for (int j = lane; j < nFR - 1; j += TEAM) Q[p * ld + j] = Q[last * ld + j];
             if (lane == 0) { short vl = FR[last]; FR[p] = vl; posFR[vl] = (short)p; }
         }
         if (lane == 0) { posFR[v] = -1; sB_[v] = (short)status; hdr[0] = nFR - 1; }
@@ -485,11 +511,11 @@ struct QP {
         if (nFR + 1 > cap) return 1;
         double *Q = V_(Q), *RT = V_(RT);
         const double* Av = V_(Av);
-        const short *Ap = pat + sA.pAp, *Ai = pat + sA.pAi;
+        const pidx *Ap = pat + sA.pAp, *Ai = pat + sA.pAi;
         const short* AC = AC_;
         SYNC();  // all lanes have read hdr[0] before lane 0 updates it below
-        _Pragma("unroll 1") for (int j = lane; j < nFR; j += 32) { Q[nFR * ld + j] = 0.0; Q[j * ld + nFR] = 0.0; }
-        _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) {
+        _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) { Q[nFR * ld + j] = 0.0; Q[j * ld + nFR] = 0.0; }
+        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) {
             int r = AC[i];
             double s = 0.0;
             int e1 = Ap[v + 1];
@@ -505,12 +531,12 @@ struct QP {
             double cs, sn, r;
             givens(T_(i, cL), T_(i, cL + 1), cs, sn, r);
             SYNC();
-            _Pragma("unroll 1") for (int ii = i + lane; ii < nAC; ii += 32) {
+            _Pragma("unroll 1") for (int ii = i + lane; ii < nAC; ii += TEAM) {
                 double ta = T_(ii, cL), tb = T_(ii, cL + 1);
                 T_(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
                 T_(ii, cL + 1) = sn * ta + cs * tb;
             }
-            _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) {
+            _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
                 double qa = Q[p * ld + cL], qb = Q[p * ld + cL + 1];
                 Q[p * ld + cL] = cs * qa - sn * qb;
                 Q[p * ld + cL + 1] = sn * qa + cs * qb;
@@ -531,7 +557,7 @@ struct QP {
             double vi = b[i] / T_(i, d);
             SYNC();
             if (lane == 0) v[d] = vi;
-            _Pragma("unroll 1") for (int k = i + 1 + lane; k < nAC; k += 32) b[k] -= T_(k, d) * vi;
+            _Pragma("unroll 1") for (int k = i + 1 + lane; k < nAC; k += TEAM) b[k] -= T_(k, d) * vi;
             SYNC();
         }
     }
@@ -545,7 +571,7 @@ struct QP {
             double ui = r[d] / T_(i, d);
             SYNC();
             if (lane == 0) u[i] = ui;
-            _Pragma("unroll 1") for (int k = lane; k < i; k += 32) { int dk = nFR - 1 - k; r[dk] -= T_(i, dk) * ui; }
+            _Pragma("unroll 1") for (int k = lane; k < i; k += TEAM) { int dk = nFR - 1 - k; r[dk] -= T_(i, dk) * ui; }
             SYNC();
         }
     }
@@ -559,14 +585,14 @@ struct QP {
         double *dx = V_(dx), *dy = V_(dy), *t1 = V_(t1), *t2 = V_(t2), *t3 = V_(t3), *yv = V_(yv), *zv = V_(zv);
         const double *Q = V_(Q), *RT = V_(RT);
         const short *sB = sB_, *FR = FR_, *AC = AC_;
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) dx[i] = (sB[i] != 0) ? dxFX[i] : 0.0;
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) dx[i] = (sB[i] != 0) ? dxFX[i] : 0.0;
         SYNC();
         if (nAC > 0) {
             mulA(dx, t2);
-            _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) t3[i] = dbAC[i] - t2[AC[i]];
+            _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) t3[i] = dbAC[i] - t2[AC[i]];
             SYNC();
             solve_T(t3, yv);
-            _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) {
+            _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
                 double s = 0.0;
                 _Pragma("unroll 1") for (int j = nZ; j < nFR; j++) s += Q[p * ld + j] * yv[j];
                 dx[FR[p]] = s;
@@ -575,7 +601,7 @@ struct QP {
         }
         if (nZ > 0) {
             mulH(dx, t1);
-            _Pragma("unroll 1") for (int j = lane; j < nZ; j += 32) {
+            _Pragma("unroll 1") for (int j = lane; j < nZ; j += TEAM) {
                 double s = 0.0;
                 _Pragma("unroll 1") for (int p = 0; p < nFR; p++) { int v = FR[p]; s += Q[p * ld + j] * (t1[v] + dgvec[v]); }
                 zv[j] = -s;
@@ -586,17 +612,17 @@ struct QP {
                 double uk = zv[k] / R_(k, k);
                 SYNC();
                 if (lane == 0) zv[k] = uk;
-                _Pragma("unroll 1") for (int i = k + 1 + lane; i < nZ; i += 32) zv[i] -= R_(k, i) * uk;
+                _Pragma("unroll 1") for (int i = k + 1 + lane; i < nZ; i += TEAM) zv[i] -= R_(k, i) * uk;
                 SYNC();
             }
             _Pragma("unroll 1") for (int k = nZ - 1; k >= 0; k--) {
                 double zk = zv[k] / R_(k, k);
                 SYNC();
                 if (lane == 0) zv[k] = zk;
-                _Pragma("unroll 1") for (int i = lane; i < k; i += 32) zv[i] -= R_(i, k) * zk;
+                _Pragma("unroll 1") for (int i = lane; i < k; i += TEAM) zv[i] -= R_(i, k) * zk;
                 SYNC();
             }
-            _Pragma("unroll 1") for (int p = lane; p < nFR; p += 32) {
+            _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
                 double s = 0.0;
                 _Pragma("unroll 1") for (int j = 0; j < nZ; j++) s += Q[p * ld + j] * zv[j];
                 dx[FR[p]] += s;
@@ -604,23 +630,23 @@ struct QP {
             SYNC();
         }
         mulH(dx, t1);
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) t1[i] += dgvec[i];
-        _Pragma("unroll 1") for (int i = lane; i < nT; i += 32) dy[i] = 0.0;
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) t1[i] += dgvec[i];
+        _Pragma("unroll 1") for (int i = lane; i < nT; i += TEAM) dy[i] = 0.0;
         SYNC();
         if (nAC > 0) {
-            _Pragma("unroll 1") for (int j = nZ + lane; j < nFR; j += 32) {
+            _Pragma("unroll 1") for (int j = nZ + lane; j < nFR; j += TEAM) {
                 double s = 0.0;
                 _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * t1[FR[p]];
                 yv[j] = s;
             }
             SYNC();
             solve_Tt(yv, t3);
-            _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) dy[nV + AC[i]] = t3[i];
+            _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) dy[nV + AC[i]] = t3[i];
             SYNC();
             mulAT(dy + nV, t2);
-            _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) if (sB[i] != 0) dy[i] = t1[i] - t2[i];
+            _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) dy[i] = t1[i] - t2[i];
         } else {
-            _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) if (sB[i] != 0) dy[i] = t1[i];
+            _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) dy[i] = t1[i];
         }
         SYNC();
     }
@@ -632,7 +658,7 @@ struct QP {
         const double *x = V_(x), *y = V_(y);
         mulAT(y + nV, t2);
         mulH(x, t1);
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) g[i] = t2[i] + y[i] - t1[i];
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) g[i] = t2[i] + y[i] - t1[i];
         SYNC();
     }
     static __device__ QP_FN void drift_correction() {
@@ -640,13 +666,13 @@ struct QP {
         double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA);
         const short *sB = sB_, *sC = sC_;
         mulA(x, Ax);
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
             int s = sB[i]; double xi = x[i];
             if (s < 0) { lb[i] = xi; if (ub[i] < xi) ub[i] = xi; if (y[i] < 0) y[i] = 0.0; }
             else if (s > 0) { ub[i] = xi; if (lb[i] > xi) lb[i] = xi; if (y[i] > 0) y[i] = 0.0; }
             else { if (lb[i] > xi) lb[i] = xi; if (ub[i] < xi) ub[i] = xi; y[i] = 0.0; }
         }
-        _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) {
             int s = sC[i]; double ax = Ax[i];
             if (s < 0) { lbA[i] = ax; if (ubA[i] < ax) ubA[i] = ax; if (y[nV + i] < 0) y[nV + i] = 0.0; }
             else if (s > 0) { ubA[i] = ax; if (lbA[i] > ax) lbA[i] = ax; if (y[nV + i] > 0) y[nV + i] = 0.0; }
@@ -663,7 +689,7 @@ struct QP {
         const int nRamp = nV + nC + nC + nV;
         const double r0 = 0.5, r1 = 1.0;
         mulA(x, Ax);
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
             double tP = (double)((i + ramp_offset) % nRamp) / (double)(nRamp - 1);
             double rP = (1.0 - tP) * r0 + tP * r1;
             double tD = (double)((nV + nC + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
@@ -677,7 +703,7 @@ struct QP {
             if (s > 0) { ub[i] = xi; y[i] = -rD; }
             if (s == 0) y[i] = 0.0;
         }
-        _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) {
             double tP = (double)((nV + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
             double rP = (1.0 - tP) * r0 + tP * r1;
             double tD = (double)((nV + nC + nV + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
@@ -705,13 +731,13 @@ struct QP {
         double *xiC = V_(zv), *xiB = V_(dx), *yv = V_(yv), *t2 = V_(t2), *t3 = V_(t3), *y = V_(y);
         const double *w = V_(w), *Av = V_(Av);
         const short *sB = sB_, *sC = sC_, *AC = AC_, *posAC = posAC_;
-        _Pragma("unroll 1") for (int j = nZ + lane; j < nFR; j += 32) yv[j] = w[j];
+        _Pragma("unroll 1") for (int j = nZ + lane; j < nFR; j += TEAM) yv[j] = w[j];
         SYNC();
         solve_Tt(yv, xiC);
-        _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) { int p = posAC[i]; t3[i] = (p >= 0) ? xiC[p] : 0.0; }
+        _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) { int p = posAC[i]; t3[i] = (p >= 0) ? xiC[p] : 0.0; }
         SYNC();
         mulAT(t3, t2);
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
             if (sB[i] == 0) { xiB[i] = 0.0; continue; }
             double ai = (c >= 0) ? A_entry(pat, Av, c, i) : 0.0;
             xiB[i] = ai - t2[i];
@@ -719,27 +745,27 @@ struct QP {
         SYNC();
         const double sgn = (status < 0) ? 1.0 : -1.0;
         double best = QP_INFTY; int bpos = 0x7fffffff;
-        _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) {
             int ci = AC[i]; double xi = sgn * xiC[i], yy = y[nV + ci]; double t = QP_INFTY;
             if (sC[ci] < 0) { if (xi > QP_ZERO && yy >= 0.0) t = yy / xi; }
             else { if (xi < -QP_ZERO && yy <= 0.0) t = yy / xi; }
             if (t < QP_INFTY && key_less(t, i, best, bpos)) { best = t; bpos = i; }
         }
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
             if (sB[i] == 0) continue;
             double xi = sgn * xiB[i], yy = y[i]; double t = QP_INFTY;
             if (sB[i] < 0) { if (xi > QP_ZERO && yy >= 0.0) t = yy / xi; }
             else { if (xi < -QP_ZERO && yy <= 0.0) t = yy / xi; }
             if (t < QP_INFTY && key_less(t, nC + i, best, bpos)) { best = t; bpos = nC + i; }
         }
-        MinKey mk = warp_min(best, bpos);
+        MinKey mk = team_min(best, bpos);
         if (mk.pos == 0x7fffffff) return 1;
         const double ymin = mk.t;
         const int kind = mk.pos >= nC ? 1 : 0;
         const int idx = kind ? mk.pos - nC : AC[mk.pos];
         SYNC();
-        _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) y[nV + AC[i]] -= ymin * sgn * xiC[i];
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) if (sB[i] != 0) y[i] -= ymin * sgn * xiB[i];
+        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) y[nV + AC[i]] -= ymin * sgn * xiC[i];
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) y[i] -= ymin * sgn * xiB[i];
         SYNC();
         if (lane == 0) {
             if (c >= 0) y[nV + c] = sgn * ymin; else y[v] = sgn * ymin;
@@ -763,12 +789,12 @@ struct QP {
         _Pragma("unroll 1") for (int it = 0;; it++) {
             const int nAC = hdr[1];
             // w[0..nV) <- bound shift of fixed variables, w[nV..) <- constraint shift by AC position, a <- dg
-            _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
+            _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
                 int s = sB[i];
                 w[i] = s < 0 ? (lbN[i] - lb[i]) : (s > 0 ? (ubN[i] - ub[i]) : 0.0);
                 a[i] = gN[i] - g[i];
             }
-            _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) { int ci = AC[i]; w[nV + i] = sC[ci] < 0 ? (lbAN[ci] - lbA[ci]) : (ubAN[ci] - ubA[ci]); }
+            _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) { int ci = AC[i]; w[nV + i] = sC[ci] < 0 ? (lbAN[ci] - lbA[ci]) : (ubAN[ci] - ubA[ci]); }
             SYNC();
             step_direction(a, w, w + nV);
             mulA(dx, dAx);
@@ -783,23 +809,23 @@ struct QP {
             if (t_ < 1.0 && key_less(t_, (pos), best, bpos)) { best = t_; bpos = (pos); }         \
         }                                                                                         \
     }
-            _Pragma("unroll 1") for (int i = lane; i < nAC; i += 32) {
+            _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) {
                 int ci = AC[i];
                 if (sC[ci] < 0) CONSIDER(y[nV + ci], -dy[nV + ci], i) else CONSIDER(-y[nV + ci], dy[nV + ci], i)
             }
-            _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
+            _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
                 int s = sB[i];
                 if (s == 0) continue;
                 if (s < 0) CONSIDER(y[i], -dy[i], nC + i) else CONSIDER(-y[i], dy[i], nC + i)
             }
-            _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) {
+            _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) {
                 if (sC[i] != 0) continue;
                 double num = Ax[i] - lbA[i]; if (num < 0) num = 0;
                 CONSIDER(num, (lbAN[i] - lbA[i]) - dAx[i], nC + nV + i)
                 num = ubA[i] - Ax[i]; if (num < 0) num = 0;
                 CONSIDER(num, dAx[i] - (ubAN[i] - ubA[i]), nC + nV + nC + i)
             }
-            _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
+            _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
                 if (sB[i] != 0) continue;
                 double num = x[i] - lb[i]; if (num < 0) num = 0;
                 CONSIDER(num, (lbN[i] - lb[i]) - dx[i], 2 * nC + nV + nC + i)
@@ -807,7 +833,7 @@ struct QP {
                 CONSIDER(num, dx[i] - (ubN[i] - ub[i]), 3 * nC + 2 * nV + i)
             }
 #undef CONSIDER
-            MinKey mk = warp_min(best, bpos);
+            MinKey mk = team_min(best, bpos);
             double tau = 1.0; int bc_idx = -1, bc_isbound = 0, bc_status = 0;
             if (mk.pos != 0x7fffffff) {
                 tau = mk.t;
@@ -822,21 +848,21 @@ struct QP {
             SYNC();
             // ---- step
             if (bc_idx < 0) {
-                _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) { x[i] += dx[i]; g[i] = gN[i]; lb[i] = lbN[i]; ub[i] = ubN[i]; }
-                _Pragma("unroll 1") for (int i = lane; i < nT; i += 32) y[i] += dy[i];
-                _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) { Ax[i] += dAx[i]; lbA[i] = lbAN[i]; ubA[i] = ubAN[i]; }
+                _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) { x[i] += dx[i]; g[i] = gN[i]; lb[i] = lbN[i]; ub[i] = ubN[i]; }
+                _Pragma("unroll 1") for (int i = lane; i < nT; i += TEAM) y[i] += dy[i];
+                _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) { Ax[i] += dAx[i]; lbA[i] = lbAN[i]; ubA[i] = ubAN[i]; }
                 SYNC();
                 iters = it;
                 return ST_OPTIMAL;
             }
             if (it >= max_iter) { iters = it; return ST_HOMOTOPY; }
             if (tau > 0.0) {
-                _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
+                _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
                     x[i] += tau * dx[i]; g[i] += tau * a[i];
                     lb[i] += tau * (lbN[i] - lb[i]); ub[i] += tau * (ubN[i] - ub[i]);
                 }
-                _Pragma("unroll 1") for (int i = lane; i < nT; i += 32) y[i] += tau * dy[i];
-                _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) {
+                _Pragma("unroll 1") for (int i = lane; i < nT; i += TEAM) y[i] += tau * dy[i];
+                _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) {
                     Ax[i] += tau * dAx[i];
                     lbA[i] += tau * (lbAN[i] - lbA[i]); ubA[i] += tau * (ubAN[i] - ubA[i]);
                 }
@@ -909,10 +935,10 @@ struct QP {
         QP_CTX
         double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *g = V_(g), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA);
         short *sB = sB_, *sC = sC_, *posFR = posFR_, *posAC = posAC_;
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
             x[i] = 0.0; y[i] = 0.0; sB[i] = -1; posFR[i] = -1; g[i] = 0.0; lb[i] = 0.0; ub[i] = QP_BOUND_RELAX;
         }
-        _Pragma("unroll 1") for (int i = lane; i < nC; i += 32) {
+        _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) {
             y[nV + i] = 0.0; sC[i] = 0; posAC[i] = -1; Ax[i] = 0.0; lbA[i] = -QP_BOUND_RELAX; ubA[i] = QP_BOUND_RELAX;
         }
         if (lane == 0) { hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; }
@@ -925,10 +951,10 @@ struct QP {
         double *Q = V_(Q), *dAx = V_(dAx), *dy = V_(dy), *y = V_(y);
         short *sC = sC_, *AC = AC_, *posAC = posAC_;
         // remember (constraint, status) by AC position in dAx (nC) and dy[nV..] (nC): neither is touched below
-        _Pragma("unroll 1") for (int i = lane; i < nAC_old; i += 32) { int ci = AC[i]; dAx[i] = (double)ci; dy[nV + i] = (double)sC[ci]; }
+        _Pragma("unroll 1") for (int i = lane; i < nAC_old; i += TEAM) { int ci = AC[i]; dAx[i] = (double)ci; dy[nV + i] = (double)sC[ci]; }
         SYNC();
-        _Pragma("unroll 1") for (int k = lane; k < nFR * nFR; k += 32) { int i = k / nFR, j = k % nFR; Q[i * ld + j] = (i == j) ? 1.0 : 0.0; }
-        _Pragma("unroll 1") for (int i = lane; i < nAC_old; i += 32) { int ci = (int)dAx[i]; sC[ci] = 0; posAC[ci] = -1; }
+        _Pragma("unroll 1") for (int k = lane; k < nFR * nFR; k += TEAM) { int i = k / nFR, j = k % nFR; Q[i * ld + j] = (i == j) ? 1.0 : 0.0; }
+        _Pragma("unroll 1") for (int i = lane; i < nAC_old; i += TEAM) { int ci = (int)dAx[i]; sC[ci] = 0; posAC[ci] = -1; }
         if (lane == 0) hdr[1] = 0;
         SYNC();
         _Pragma("unroll 1") for (int i = 0; i < nAC_old; i++) {
@@ -950,10 +976,10 @@ struct QP {
         const short *sB = sB_, *sC = sC_;
         double* xo = sA.x + (size_t)b * nV;
         double* yo = sA.y + (size_t)b * nT;
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += 32) xo[i] = x[i];
-        _Pragma("unroll 1") for (int i = lane; i < nT; i += 32) yo[i] = y[i];
-        if (sA.wsB) for (int i = lane; i < nV; i += 32) sA.wsB[(size_t)b * nV + i] = (signed char)sB[i];
-        if (sA.wsC) for (int i = lane; i < nC; i += 32) sA.wsC[(size_t)b * nC + i] = (signed char)sC[i];
+        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) xo[i] = x[i];
+        _Pragma("unroll 1") for (int i = lane; i < nT; i += TEAM) yo[i] = y[i];
+        if (sA.wsB) for (int i = lane; i < nV; i += TEAM) sA.wsB[(size_t)b * nV + i] = (signed char)sB[i];
+        if (sA.wsC) for (int i = lane; i < nC; i += TEAM) sA.wsC[(size_t)b * nC + i] = (signed char)sC[i];
         // Hx (unregularised) in t1, A x in Ax, A'y_c in t2
         mulH_noreg(x, t1);
         mulA(x, Ax);
@@ -1098,16 +1124,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 512 / CTA_THREADS) qp_solve_kerne
     int iters = 0, total_iters = 0;
     if (status != ST_CAPACITY) {
         if (mode == MODE_HOT_VARIED) {
-            if (QP::refactorise()) mode = MODE_COLD;  // projected Hessian of the kept set not PD: cold start
-            else QP::drift_correction();
+            if (QPT<32>::refactorise()) mode = MODE_COLD;  // projected Hessian of the kept set not PD: cold start
+            else QPT<32>::drift_correction();
         }
-        if (mode == MODE_COLD) QP::cold_start_state();
-        status = QP::homotopy(A.max_iter, iters);
+        if (mode == MODE_COLD) QPT<32>::cold_start_state();
+        status = QPT<32>::homotopy(A.max_iter, iters);
         total_iters += iters;
         if (status != ST_OPTIMAL && status != ST_CAPACITY && mode != MODE_COLD) {
             // one-retry recovery of handle_error (src/qpOASESInterface.cpp:746-754): plain re-init
-            QP::cold_start_state();
-            status = QP::homotopy(A.max_iter, iters);
+            QPT<32>::cold_start_state();
+            status = QPT<32>::homotopy(A.max_iter, iters);
             total_iters += iters;
         }
     }
@@ -1115,7 +1141,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 512 / CTA_THREADS) qp_solve_kerne
         if (lane == 0) { A.status[b] = ST_CAPACITY; A.iters[b] = 0; }
         return;
     }
-    QP::epilogue(b, status, total_iters);
+    QPT<32>::epilogue(b, status, total_iters);
     if ((A.flags & FLAG_KEEP_STATE) && A.state) {
         double* st = A.state + (size_t)b * A.state_doubles;
         for (int i = lane; i < A.oQ; i += 32) st[i] = slice[i];
@@ -1125,6 +1151,71 @@ __global__ void __launch_bounds__(CTA_THREADS, 512 / CTA_THREADS) qp_solve_kerne
         for (int k = lane; k < nZ * nZ; k += 32) Rp[k] = R_(k / nZ, k % nZ);
         for (int k = lane; k < nAC * nFR; k += 32) Tp[k] = T_(k / nFR, k % nFR);
     }
+}
+
+// -------------------------------------------------------------------------------------------
+// kernel: one QP per CTA (large QPs: factors do not fit in shared memory)
+// -------------------------------------------------------------------------------------------
+// The slice of instance b (vectors, index lists and the nV x nV factors Q, R/T) lives in global memory at
+// gwork[b][slice_doubles] and persists between launches, so a hot start needs no save/restore; the CTA streams it through
+// L1/L2.  Same solver code as the warp kernel (QPT<TEAM>), the team barrier being __syncthreads().
+template <int CTA_THREADS>
+__global__ void __launch_bounds__(CTA_THREADS, 1) qp_solve_large_kernel(const __grid_constant__ QPKernelArgs A) {
+    typedef QPT<CTA_THREADS> S;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+    {
+        const int* src = reinterpret_cast<const int*>(&A);
+        int* dst = reinterpret_cast<int*>(&sA);
+        for (int i = tid; i < (int)(sizeof(QPKernelArgs) / 4); i += CTA_THREADS) dst[i] = src[i];
+        if (tid == 0) sSlice = A.gwork + (size_t)b * A.slice_doubles;
+    }
+    __syncthreads();
+    if (A.mask && !A.mask[b]) return;  // CTA-uniform
+    const int nV = A.nV, nC = A.nC;
+    double* slice = A.gwork + (size_t)b * A.slice_doubles;
+    int* hdr = reinterpret_cast<int*>(slice);
+
+    int mode = A.mode;
+    if (mode != MODE_COLD && !hdr[3]) mode = MODE_COLD;  // previous solve did not end optimal: plain re-init (handle_error)
+    __syncthreads();
+    if (mode != MODE_HOT_FIXED) {
+        const double* av = A.Aval + (size_t)b * A.zA;
+        for (int i = tid; i < A.zA; i += CTA_THREADS) slice[A.oAv + i] = av[i];
+        if (A.has_H && !A.is_lp) {
+            const double* hv = A.Hval + (size_t)b * A.zH;
+            for (int i = tid; i < A.zH; i += CTA_THREADS) slice[A.oHv + i] = hv[i];
+        }
+    }
+    {
+        const double *gN = A.gN + (size_t)b * nV, *lbN = A.lbN + (size_t)b * nV, *ubN = A.ubN + (size_t)b * nV;
+        const double *lbAN = A.lbAN + (size_t)b * nC, *ubAN = A.ubAN + (size_t)b * nC;
+        for (int i = tid; i < nV; i += CTA_THREADS) {
+            slice[A.ogN + i] = gN[i];
+            slice[A.olbN + i] = fmin(fmax(lbN[i], -QP_INFTY), QP_INFTY);
+            slice[A.oubN + i] = fmin(fmax(ubN[i], -QP_INFTY), QP_INFTY);
+        }
+        for (int i = tid; i < nC; i += CTA_THREADS) {
+            slice[A.olbAN + i] = fmin(fmax(lbAN[i], -QP_INFTY), QP_INFTY);
+            slice[A.oubAN + i] = fmin(fmax(ubAN[i], -QP_INFTY), QP_INFTY);
+        }
+    }
+    __syncthreads();
+
+    int iters = 0, total_iters = 0, status;
+    if (mode == MODE_HOT_VARIED) {
+        if (S::refactorise()) mode = MODE_COLD;
+        else S::drift_correction();
+    }
+    if (mode == MODE_COLD) S::cold_start_state();
+    status = S::homotopy(A.max_iter, iters);
+    total_iters += iters;
+    if (status != ST_OPTIMAL && mode != MODE_COLD) {
+        S::cold_start_state();
+        status = S::homotopy(A.max_iter, iters);
+        total_iters += iters;
+    }
+    S::epilogue(b, status, total_iters);
 }
 
 #endif  // __CUDACC__

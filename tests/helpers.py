@@ -68,3 +68,36 @@ def oracle_solve(orc, p, is_lp=False, max_iter=1000, Acsc=None, Hcsc=None):
     x, y, obj, it = s.solution()
     wb, wc = s.working_set()
     return dict(x=x, y=y, obj=obj, iters=it, status=st, wb=wb, wc=wc, solver=s)
+
+
+def synthetic_large_qp(n, seed=None, dens=0.01, batch=1):
+    """n variables, m = n/2 constraints, Jacobian entries non-zero with probability `dens` (at least
+    one per row), H = S + (norm1(S) + 1) I on the n x n block with S symmetric of density `dens`, g ~ N(0,1), rho = 1,
+    delta = 1, x free, c_l = c_u on the first m/2 rows, c_l = -inf on the rest, c_k ~ N(0,1).  Returns the shared CSC
+    patterns/values and per-instance vectors [batch][len] in the l1-penalty layout of src/QPhandler.cpp:39-51, 150-156."""
+    import scipy.sparse as sp
+    m = n // 2
+    rng = np.random.default_rng(4000 + n if seed is None else seed)
+    mask = rng.random((m, n)) < dens
+    for i in range(m):
+        if not mask[i].any():
+            mask[i, rng.integers(0, n)] = True
+    J = np.where(mask, rng.standard_normal((m, n)), 0.0)
+    U = np.triu(np.where(rng.random((n, n)) < dens, rng.standard_normal((n, n)), 0.0), 1)
+    S = U + U.T + np.diag(np.where(rng.random(n) < dens, rng.standard_normal(n), 0.0))
+    Hn = S + (np.abs(S).sum(axis=0).max() + 1.0) * np.eye(n)
+    nV, nC = n + 2 * m, m
+    A = sp.hstack([sp.csc_matrix(J), sp.identity(m, format="csc"), -sp.identity(m, format="csc")], format="csc")
+    Hs = sp.block_diag([sp.csc_matrix(Hn), sp.csc_matrix((2 * m, 2 * m))], format="csc")
+    A.sort_indices(); Hs.sort_indices()
+    Ac = (A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64))
+    Hc = (Hs.indptr.astype(np.int32), Hs.indices.astype(np.int32), Hs.data.astype(np.float64))
+    g = np.concatenate([np.zeros(n), np.ones(2 * m)])[None, :].repeat(batch, 0)
+    g[:, :n] = rng.standard_normal((batch, n))
+    lb = np.concatenate([np.full(n, -1.0), np.zeros(2 * m)])[None, :].repeat(batch, 0)
+    ub = np.concatenate([np.full(n, 1.0), np.full(2 * m, 1e18)])[None, :].repeat(batch, 0)
+    ck = rng.standard_normal((batch, m))
+    lbA, ubA = -ck.copy(), -ck.copy()
+    lbA[:, m // 2:] = -1e18
+    return dict(n=n, m=m, nV=nV, nC=nC, Ac=Ac, Hc=Hc, g=np.ascontiguousarray(g), lb=np.ascontiguousarray(lb),
+                ub=np.ascontiguousarray(ub), lbA=np.ascontiguousarray(lbA), ubA=np.ascontiguousarray(ubA))

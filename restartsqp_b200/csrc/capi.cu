@@ -540,7 +540,7 @@ int sqpb200_qphandler_g(sqpb200_handle h, int n, int m, const double* grad, cons
 // ------------------------------------------------------------------------------ solve
 static void fill_dims(sqpb200_handle h, QPKernelArgs& a, int cap) {
     memset(&a, 0, sizeof a);
-    a.batch = h->batch; a.nV = h->nV; a.nC = h->nC; a.cap = cap;
+    a.batch = h->batch; a.nV = h->nV; a.nC = h->nC; a.cap = cap; a.large = h->large ? 1 : 0;
     a.is_lp = (h->qptype == SQPB200_LP); a.has_H = !a.is_lp;
     a.zA = h->zA; a.zH = a.is_lp ? 0 : h->zH;  // an LP handle never holds H (src/qpOASESInterface.cpp:122-124)
     qp_fill_layout(a);

@@ -54,6 +54,7 @@ enum { FLAG_FLIPPING = 1, FLAG_RAMPING = 2, FLAG_DRIFT = 4, FLAG_KEEP_STATE = 8 
 struct QPKernelArgs {
     int batch, nV, nC;
     int cap, ld;      // factor capacity (max simultaneously free variables) and its odd leading dimension
+    int large;        // 1: one-QP-per-CTA layout (adds the nFR x nZ scratch matrix W of the blocked refactorisation)
     int rescue;       // 1: only instances whose status is ST_CAPACITY are (re)solved, from their pre-solve state
     int is_lp, has_H;
     int max_iter, flags, mode;
@@ -81,6 +82,7 @@ struct QPKernelArgs {
     // slice layout: offsets in doubles from the slice base (filled by qp_fill_layout)
     int oQ, oRT, ox, og, olb, oub, odx, oAx, olbA, oubA, odAx, oy, ody, ot1, ot2, ot3, ow, oa, oyv, ozv, oAv, oHv;
     int ogN, olbN, oubN, olbAN, oubAN;  // target data of the homotopy
+    int oW;                             // large layout only: scratch matrix (cap x ld)
     int oS;                             // start of the 16-bit index arrays (sB, FR, posFR, sC, AC, posAC)
     // pattern layout: offsets in 16-bit words from the pattern base
     int pAp, pAi, pArp, pAci, pAperm, pHp, pHi;
@@ -106,6 +108,7 @@ __host__ __device__ inline void qp_fill_layout(QPKernelArgs& a) {
     o += (shorts * 2 + 7) / 8;
     a.oQ = o; o += a.cap * a.ld;
     a.oRT = o; o += a.cap * a.ld;
+    a.oW = o; if (a.large) o += a.cap * a.ld;
     a.slice_doubles = o;
     a.state_doubles = a.oQ + 2 * nV * nV;  // capacity-independent image
     int p = 0;
@@ -160,6 +163,9 @@ __shared__ int sRedP[32];
 #define posAC_ S_(3 * nV + 2 * nC)
 #define R_(a_, b_) RT[(a_) * ld + (b_)]
 #define T_(i, j) RT[(cap - 1 - (i)) * ld + (j)]
+// inner sequential sums: not unrolled in the warp kernel (instruction-cache footprint), unrolled 8x in the CTA kernel so
+// that the loads of consecutive terms overlap (the additions stay in order: no reassociation without fast-math)
+#define DOT_UNROLL _Pragma("unroll (TEAM == 32 ? 1 : 8)")
 #define SYNC() do { if (TEAM == 32) __syncwarp(); else __syncthreads(); } while (0)
 
 template <int TEAM>
@@ -281,13 +287,14 @@ struct QPT {
             SYNC();
             return 0;
         }
+        if constexpr (TEAM > 32) return recompute_R_blocked();
         const double *Q = V_(Q), *t2 = V_(t2);
         const short* FR = FR_;
         _Pragma("unroll 1") for (int b = 0; b < nZ; b++) {
             proj_column(b);
             _Pragma("unroll 1") for (int a_ = lane; a_ <= b; a_ += TEAM) {
                 double s = 0.0;
-                _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
+                DOT_UNROLL for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
                 R_(a_, b) = s;
             }
             SYNC();
@@ -296,7 +303,7 @@ struct QPT {
         _Pragma("unroll 1") for (int i = 0; i < nZ; i++) {
             _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += TEAM) {
                 double s = R_(i, j);
-                _Pragma("unroll 1") for (int k = 0; k < i; k++) s -= R_(k, i) * R_(k, j);
+                DOT_UNROLL for (int k = 0; k < i; k++) s -= R_(k, i) * R_(k, j);
                 R_(i, j) = s;
             }
             SYNC();
@@ -307,6 +314,119 @@ struct QPT {
             _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += TEAM) R_(i, j) = (j == i) ? dd : R_(i, j) / dd;
             _Pragma("unroll 1") for (int j = lane; j < i; j += TEAM) R_(i, j) = 0.0;
             SYNC();
+        }
+        return 0;
+    }
+    // ---- CTA kernel: blocked refactorisation.  Same arithmetic as the column-by-column version above, term for term and in
+    // the same order per element (every sum runs over its index in ascending order), reorganised so that the O(nZ^2 nFR)
+    // and O(nZ^3) parts are shared-memory tiled contractions instead of latency-bound dot products:
+    //   A  W[p][b] = ((H + reg I) z_b)[FR[p]]            sparse x dense, one thread per entry
+    //   B  M[a][b] = sum_p Q[p][a] W[p][b], a <= b        tiles of TA x 64 outputs, 16 terms per stage
+    //   C  left-looking Cholesky by blocks of TA rows: the terms k < i0 of a block row as a tiled contraction (C1), the
+    //      terms i0 <= k < i row by row inside the block (C2).
+    // C(a0+., b0+.) (+|-)= sum_{k<K} X[k][xo+a] Y[k][yo+b]; tile TA x 64; stores only entries with a <= b (global indices
+    // ga = a0+a, gb = b0+b relative to the same origin), ga < na, gb < nb.
+    template <int SIGN>
+    static __device__ __forceinline__ void tile_contract(const double* X, int xo, const double* Y, int yo, int K, double* C,
+                                                         int a0, int na, int b0, int nb, int ld, bool init_zero) {
+        constexpr int TA = TEAM / 8, TB = 64, KC = 16;
+        __shared__ double Xs[KC][TA + 2];
+        __shared__ double Ys[KC][TB + 2];
+        const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+        const int ga0 = a0 + ty * 2, gb0 = b0 + tx * 4;
+        double acc[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int ga = ga0 + i, gb = gb0 + j;
+                acc[i][j] = (!init_zero && ga < na && gb < nb && ga <= gb) ? C[ga * ld + gb] : 0.0;
+            }
+        _Pragma("unroll 1") for (int k0 = 0; k0 < K; k0 += KC) {
+            const int kc = (K - k0 < KC) ? K - k0 : KC;
+            __syncthreads();  // previous stage consumed
+            for (int e = tid; e < KC * TA; e += TEAM) {
+                const int k = e / TA, c = e % TA;
+                Xs[k][c] = (k < kc && a0 + c < na) ? X[(k0 + k) * ld + xo + a0 + c] : 0.0;
+            }
+            for (int e = tid; e < KC * TB; e += TEAM) {
+                const int k = e / TB, c = e % TB;
+                Ys[k][c] = (k < kc && b0 + c < nb) ? Y[(k0 + k) * ld + yo + b0 + c] : 0.0;
+            }
+            __syncthreads();
+            _Pragma("unroll 4") for (int k = 0; k < kc; k++) {
+                const double x0 = Xs[k][ty * 2], x1 = Xs[k][ty * 2 + 1];
+                const double y0 = Ys[k][tx * 4], y1 = Ys[k][tx * 4 + 1], y2 = Ys[k][tx * 4 + 2], y3 = Ys[k][tx * 4 + 3];
+                if (SIGN > 0) {
+                    acc[0][0] += x0 * y0; acc[0][1] += x0 * y1; acc[0][2] += x0 * y2; acc[0][3] += x0 * y3;
+                    acc[1][0] += x1 * y0; acc[1][1] += x1 * y1; acc[1][2] += x1 * y2; acc[1][3] += x1 * y3;
+                } else {
+                    acc[0][0] -= x0 * y0; acc[0][1] -= x0 * y1; acc[0][2] -= x0 * y2; acc[0][3] -= x0 * y3;
+                    acc[1][0] -= x1 * y0; acc[1][1] -= x1 * y1; acc[1][2] -= x1 * y2; acc[1][3] -= x1 * y3;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int ga = ga0 + i, gb = gb0 + j;
+                if (ga < na && gb < nb && ga <= gb) C[ga * ld + gb] = acc[i][j];
+            }
+    }
+    static __device__ QP_FN int recompute_R_blocked() {
+        QP_CTX QP_PAT
+        constexpr int TA = TEAM / 8;
+        const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
+        double *RT = V_(RT), *W = V_(W);
+        const double *Q = V_(Q), *Hv = V_(Hv);
+        const short *FR = FR_, *posFR = posFR_;
+        const pidx *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
+        const bool has_H = sA.has_H && !sA.is_lp;
+        // A: W[p][b]
+        _Pragma("unroll 1") for (int e = lane; e < nFR * nZ; e += TEAM) {
+            const int p = e / nZ, b = e % nZ;
+            double s = 0.0;
+            if (has_H) {
+                const int c = FR[p], e1 = Hp[c + 1];
+                _Pragma("unroll 1") for (int h = Hp[c]; h < e1; h++) {
+                    const int pr = posFR[Hi[h]];
+                    s += Hv[h] * ((pr >= 0) ? Q[pr * ld + b] : 0.0);
+                }
+            }
+            W[p * ld + b] = s;
+        }
+        SYNC();
+        // B: M (upper triangle) into R
+        _Pragma("unroll 1") for (int b0 = 0; b0 < nZ; b0 += 64)
+            _Pragma("unroll 1") for (int a0 = 0; a0 < b0 + 64 && a0 < nZ; a0 += TA)
+                tile_contract<1>(Q, 0, W, 0, nFR, RT, a0, nZ, b0, nZ, ld, true);
+        SYNC();
+        // C: Cholesky by block rows
+        _Pragma("unroll 1") for (int i0 = 0; i0 < nZ; i0 += TA) {
+            const int i1 = (i0 + TA < nZ) ? i0 + TA : nZ;
+            if (i0 > 0) {
+                // rows i0..i1, columns >= i0: subtract the terms k < i0.  Row/column indices are taken relative to i0 so that
+                // the tile's "a <= b" rule is the upper-triangle rule of the block row.
+                _Pragma("unroll 1") for (int b0 = 0; b0 < nZ - i0; b0 += 64)
+                    tile_contract<-1>(RT, i0, RT, i0, i0, RT + i0 * ld + i0, 0, i1 - i0, b0, nZ - i0, ld, false);
+                SYNC();
+            }
+            _Pragma("unroll 1") for (int i = i0; i < i1; i++) {
+                _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += TEAM) {
+                    double s = R_(i, j);
+                    DOT_UNROLL for (int k = i0; k < i; k++) s -= R_(k, i) * R_(k, j);
+                    R_(i, j) = s;
+                }
+                SYNC();
+                const double d = R_(i, i);
+                SYNC();
+                if (!(d > QP_ZERO)) return 1 + i;
+                const double dd = sqrt(d);
+                _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += TEAM) R_(i, j) = (j == i) ? dd : R_(i, j) / dd;
+                _Pragma("unroll 1") for (int j = lane; j < i; j += TEAM) R_(i, j) = 0.0;
+                SYNC();
+            }
         }
         return 0;
     }
@@ -326,7 +446,7 @@ struct QPT {
         proj_column(b);
         _Pragma("unroll 1") for (int a_ = lane; a_ <= b; a_ += TEAM) {
             double s = 0.0;
-            _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
+            DOT_UNROLL for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
             w[a_] = s;
         }
         SYNC();
@@ -339,7 +459,7 @@ struct QPT {
             SYNC();
         }
         double rho2 = w[b];
-        _Pragma("unroll 1") for (int k = 0; k < b; k++) rho2 -= R_(k, b) * R_(k, b);
+        DOT_UNROLL for (int k = 0; k < b; k++) rho2 -= R_(k, b) * R_(k, b);
         int ok = check_curvature ? (rho2 > QP_EPS_FLIP) : (rho2 > QP_ZERO);
         SYNC();  // every lane has read w[b] / R(.,b) before a caller may overwrite them (uniform decision)
         if (!ok) return 0;
@@ -360,13 +480,13 @@ struct QPT {
         SYNC();
         _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) {
             double s = 0.0;
-            _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * a[p];
+            DOT_UNROLL for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * a[p];
             w[j] = s;
         }
         SYNC();
         double s2 = 0.0, z2 = 0.0;
-        _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s2 += a[p] * a[p];
-        _Pragma("unroll 1") for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
+        DOT_UNROLL for (int p = 0; p < nFR; p++) s2 += a[p] * a[p];
+        DOT_UNROLL for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
         wz2 = z2; a2 = s2;
         SYNC();
     }
@@ -381,7 +501,7 @@ struct QPT {
         _Pragma("unroll 1") for (int j = lane; j + 1 < cnt; j += TEAM) {
             double S = w[0] * w[0];
             bool anyprev = false;  // a non-zero entry before j: then a_j = sqrt(S_j), else a_j = w_j (signed)
-            _Pragma("unroll 1") for (int k = 1; k <= j; k++) { anyprev = anyprev || (w[k - 1] != 0.0); S = S + w[k] * w[k]; }
+            DOT_UNROLL for (int k = 1; k <= j; k++) { anyprev = anyprev || (w[k - 1] != 0.0); S = S + w[k] * w[k]; }
             const double a = anyprev ? sqrt(S) : w[j];
             if (a == 0.0) { t2[j] = 1.0; t3[j] = 0.0; }
             else { const double h = sqrt(S + w[j + 1] * w[j + 1]); t2[j] = w[j + 1] / h; t3[j] = a / h; }
@@ -392,7 +512,7 @@ struct QPT {
             const int j = cnt - 1;
             double S = w[0] * w[0];
             bool anyprev = false;
-            _Pragma("unroll 1") for (int k = 1; k <= j; k++) { anyprev = anyprev || (w[k - 1] != 0.0); S = S + w[k] * w[k]; }
+            DOT_UNROLL for (int k = 1; k <= j; k++) { anyprev = anyprev || (w[k - 1] != 0.0); S = S + w[k] * w[k]; }
             r = anyprev ? sqrt(S) : w[j];
         }
         SYNC();
@@ -461,7 +581,7 @@ struct QPT {
         _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) w[j] = Q[p * ld + j];
         SYNC();
         double z2 = 0.0;
-        _Pragma("unroll 1") for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
+        DOT_UNROLL for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
         SYNC();
         return z2;
     }
@@ -594,7 +714,7 @@ struct QPT {
             solve_T(t3, yv);
             _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
                 double s = 0.0;
-                _Pragma("unroll 1") for (int j = nZ; j < nFR; j++) s += Q[p * ld + j] * yv[j];
+                DOT_UNROLL for (int j = nZ; j < nFR; j++) s += Q[p * ld + j] * yv[j];
                 dx[FR[p]] = s;
             }
             SYNC();
@@ -603,7 +723,7 @@ struct QPT {
             mulH(dx, t1);
             _Pragma("unroll 1") for (int j = lane; j < nZ; j += TEAM) {
                 double s = 0.0;
-                _Pragma("unroll 1") for (int p = 0; p < nFR; p++) { int v = FR[p]; s += Q[p * ld + j] * (t1[v] + dgvec[v]); }
+                DOT_UNROLL for (int p = 0; p < nFR; p++) { int v = FR[p]; s += Q[p * ld + j] * (t1[v] + dgvec[v]); }
                 zv[j] = -s;
             }
             SYNC();
@@ -624,7 +744,7 @@ struct QPT {
             }
             _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
                 double s = 0.0;
-                _Pragma("unroll 1") for (int j = 0; j < nZ; j++) s += Q[p * ld + j] * zv[j];
+                DOT_UNROLL for (int j = 0; j < nZ; j++) s += Q[p * ld + j] * zv[j];
                 dx[FR[p]] += s;
             }
             SYNC();
@@ -636,7 +756,7 @@ struct QPT {
         if (nAC > 0) {
             _Pragma("unroll 1") for (int j = nZ + lane; j < nFR; j += TEAM) {
                 double s = 0.0;
-                _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * t1[FR[p]];
+                DOT_UNROLL for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * t1[FR[p]];
                 yv[j] = s;
             }
             SYNC();

@@ -94,7 +94,7 @@ def test_dumped_qp_replay_matches_oracle(gpu_lib, q):
     s.close()
 
 
-@pytest.mark.parametrize("team", [0, 32])
+@pytest.mark.parametrize("team", [0, 32, 1024])
 def test_random_convex_batch_all_team_sizes(gpu_lib, team):
     rng = np.random.default_rng(72 + team)
     n, m = 6, 4
@@ -110,7 +110,7 @@ def test_random_convex_batch_all_team_sizes(gpu_lib, team):
     lbA = np.where(lbA > -1e17, lbA + shift, lbA); ubA = np.where(ubA < 1e17, ubA + shift, ubA)
     lb, ub = np.tile(base["lb"], (B, 1)), np.tile(base["ub"], (B, 1))
     s = solve_batch_csc(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA, team_size=team, Avals=Avals, Hvals=Hvals)
-    assert s.solve_config()["team_size"] == 32
+    assert s.solve_config()["team_size"] == (1024 if team == 1024 else 32)
     assert (s.get_status() == 20).all()
     assert s.test_optimality().all()
     for b in range(B):
@@ -138,7 +138,8 @@ def test_random_shapes_incl_edge_cases(gpu_lib, shape):
     s.close()
 
 
-def test_lp_matches_oracle(gpu_lib):
+@pytest.mark.parametrize("team", [0, 1024])
+def test_lp_matches_oracle(gpu_lib, team):
     rng = np.random.default_rng(77)
     n, m, B = 5, 4, 16
     base = H.random_l1_qp(rng, n, m, rho=1.0)
@@ -149,7 +150,7 @@ def test_lp_matches_oracle(gpu_lib):
     lbA, ubA = np.tile(base["lbA"], (B, 1)), np.tile(base["ubA"], (B, 1))
     shift = rng.standard_normal((B, m))
     lbA = np.where(lbA > -1e17, lbA + shift, lbA); ubA = np.where(ubA < 1e17, ubA + shift, ubA)
-    s = solve_batch_csc(nV, nC, Ac, None, g, lb, ub, lbA, ubA, qptype=r.QPType.LP)
+    s = solve_batch_csc(nV, nC, Ac, None, g, lb, ub, lbA, ubA, qptype=r.QPType.LP, team_size=team)
     for b in range(B):
         p = dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b], A=base["A"])
         o = H.oracle_solve(orc, p, is_lp=True, max_iter=100, Acsc=Ac)
@@ -157,7 +158,8 @@ def test_lp_matches_oracle(gpu_lib):
     s.close()
 
 
-def test_hotstart_fixed_and_varied(gpu_lib):
+@pytest.mark.parametrize("team", [0, 1024])
+def test_hotstart_fixed_and_varied(gpu_lib, team):
     """hotstart(g,lb,ub,lbA,ubA) and hotstart(H,g,A,...) (src/qpOASESInterface.cpp:176-211) against the
     oracle's hot starts, and against cold starts on the new data (strictly convex => same point)."""
     rng = np.random.default_rng(9)
@@ -168,7 +170,7 @@ def test_hotstart_fixed_and_varied(gpu_lib):
     g = np.tile(base["g"], (B, 1)); g[:, :n] += rng.standard_normal((B, n))
     lb, ub = np.tile(base["lb"], (B, 1)), np.tile(base["ub"], (B, 1))
     lbA, ubA = np.tile(base["lbA"], (B, 1)), np.tile(base["ubA"], (B, 1))
-    s = solve_batch_csc(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA)
+    s = solve_batch_csc(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA, team_size=team)
     oracles = []
     for b in range(B):
         p = dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b])
@@ -302,4 +304,43 @@ def test_factor_capacity_rescue_path(gpu_lib, cap):
         st = oracles[b].hotstart(g2[b], lb[b], ub[b], lbA[b], ubA[b])
         x, y, obj, it = oracles[b].solution(); wb, wc = oracles[b].working_set()
         check_against_oracle(s, b, dict(x=x, y=y, obj=obj, iters=it, status=st, wb=wb, wc=wc), nV)
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["QORE_hs104", "QORE_hs107", "QORE_hs116"])
+def test_dumped_qp_on_cta_per_qp_kernel(gpu_lib, name):
+    """The one-QP-per-CTA kernel (slice in global memory) runs the same solver code: forced onto the largest and the most
+    degenerate dumps it must reproduce the oracle bit for bit, like the warp kernel."""
+    q = [f for f in FIX if f["name"] == name][0]
+    nV, nC, B = q["nV"], q["nC"], 3
+    rng = np.random.default_rng(4321)
+    g = np.tile(np.array(q["g"]), (B, 1)); g[1:] *= 1.0 + 1e-3 * rng.uniform(-1, 1, size=g[1:].shape)
+    tile = lambda k, n_: np.tile(np.array(q[k], dtype=np.float64).reshape(1, n_), (B, 1))
+    A = (q["A_colptr"], q["A_rowidx"], np.array(q["A_val"]))
+    Hc = (q["H_colptr"], q["H_rowidx"], np.array(q["H_val"]))
+    s = solve_batch_csc(nV, nC, A, Hc, g, tile("lb", nV), tile("ub", nV), tile("lbA", nC), tile("ubA", nC), team_size=1024)
+    assert s.solve_config()["team_size"] == 1024
+    for b in range(B):
+        p = dict(nV=nV, nC=nC, g=g[b], lb=q["lb"], ub=q["ub"], lbA=q["lbA"], ubA=q["ubA"])
+        o = H.oracle_solve(orc, p, Acsc=A, Hcsc=Hc)
+        check_against_oracle(s, b, o, nV, strict=(o["status"] == 20))
+    s.close()
+
+
+@pytest.mark.parametrize("n,B,checked", [(64, 8, 8), (128, 6, 3), (256, 4, 2)])
+def test_synthetic_large_config4(gpu_lib, n, B, checked):
+    """BASELINE.json configs[3] / SURVEY.md 8d config 4 (n variables, m = n/2, 1 % density, strictly convex): too large for
+    the shared-memory kernel, solved by the one-QP-per-CTA kernel; identical working sets / iteration counts and x, y,
+    objective within 1e-8 of the oracle; every instance passes the reference's own KKT test (1e-6)."""
+    d = H.synthetic_large_qp(n, batch=B)
+    nV, nC = d["nV"], d["nC"]
+    s = solve_batch_csc(nV, nC, d["Ac"], d["Hc"], d["g"], d["lb"], d["ub"], d["lbA"], d["ubA"])
+    assert s.solve_config()["team_size"] == 1024
+    assert (s.get_status() == 20).all() and s.test_optimality().all()
+    x = s.get_optimal_solution()
+    assert (x[:, :n] >= -1.0 - 1e-12).all() and (x[:, :n] <= 1.0 + 1e-12).all() and (x[:, n:] >= -1e-12).all()
+    for b in range(checked):
+        p = dict(nV=nV, nC=nC, g=d["g"][b], lb=d["lb"][b], ub=d["ub"][b], lbA=d["lbA"][b], ubA=d["ubA"][b])
+        o = H.oracle_solve(orc, p, Acsc=d["Ac"], Hcsc=d["Hc"], max_iter=100000)
+        check_against_oracle(s, b, o, nV)
     s.close()

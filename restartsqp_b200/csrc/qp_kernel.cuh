@@ -430,6 +430,70 @@ struct QPT {
         }
         return 0;
     }
+    // ---- CTA kernel: blocked triangular solves with R.  The column-oriented substitutions above need two team barriers per
+    // unknown; here one warp solves a 32 x 32 diagonal block out of shared memory (shuffles, no barrier) and the whole team
+    // then applies the block's 32 columns to the trailing unknowns.  Per unknown the terms are subtracted in the same order
+    // (ascending k forward, descending k backward) and divided by the same pivot, so results are bit-identical.
+    static __device__ __forceinline__ double (*diag_tile())[33] {
+        __shared__ double Ds[32][33];
+        return Ds;
+    }
+    // R' u = z (n unknowns, in place); col >= 0: also R(k, col) = u_k
+    static __device__ QP_FN void fwd_solve_R_blocked(double* z, int n, int col) {
+        QP_CTX
+        double* RT = V_(RT);
+        double (*Ds)[33] = diag_tile();
+        const int l = lane & 31;
+        _Pragma("unroll 1") for (int i0 = 0; i0 < n; i0 += 32) {
+            const int nb = (n - i0 < 32) ? n - i0 : 32;
+            _Pragma("unroll 1") for (int e = lane; e < 32 * 32; e += TEAM) { const int k = e >> 5, i = e & 31; if (k < nb && i < nb && k <= i) Ds[k][i] = R_(i0 + k, i0 + i); }
+            SYNC();
+            if (lane < 32) {
+                double zi = (l < nb) ? z[i0 + l] : 0.0;
+                _Pragma("unroll 1") for (int k = 0; k < nb; k++) {
+                    const double uk = __shfl_sync(0xffffffffu, zi, k) / Ds[k][k];
+                    if (l == k) zi = uk;
+                    else if (l > k && l < nb) zi -= Ds[k][l] * uk;
+                }
+                if (l < nb) { z[i0 + l] = zi; if (col >= 0) R_(i0 + l, col) = zi; }
+            }
+            SYNC();
+            _Pragma("unroll 1") for (int i = i0 + nb + lane; i < n; i += TEAM) {
+                double s = z[i];
+                DOT_UNROLL for (int k = 0; k < nb; k++) s -= R_(i0 + k, i) * z[i0 + k];
+                z[i] = s;
+            }
+            SYNC();
+        }
+    }
+    // R v = z (n unknowns, in place)
+    static __device__ QP_FN void bwd_solve_R_blocked(double* z, int n) {
+        QP_CTX
+        const double* RT = V_(RT);
+        double (*Ds)[33] = diag_tile();
+        const int l = lane & 31;
+        _Pragma("unroll 1") for (int i0 = ((n - 1) >> 5) << 5; i0 >= 0; i0 -= 32) {
+            const int nb = (n - i0 < 32) ? n - i0 : 32;
+            _Pragma("unroll 1") for (int e = lane; e < 32 * 32; e += TEAM) { const int k = e >> 5, i = e & 31; if (k < nb && i < nb && k <= i) Ds[k][i] = R_(i0 + k, i0 + i); }
+            SYNC();
+            if (lane < 32) {
+                double zi = (l < nb) ? z[i0 + l] : 0.0;
+                _Pragma("unroll 1") for (int k = nb - 1; k >= 0; k--) {
+                    const double zk = __shfl_sync(0xffffffffu, zi, k) / Ds[k][k];
+                    if (l == k) zi = zk;
+                    else if (l < k) zi -= Ds[l][k] * zk;
+                }
+                if (l < nb) z[i0 + l] = zi;
+            }
+            SYNC();
+            _Pragma("unroll 1") for (int i = lane; i < i0; i += TEAM) {
+                double s = z[i];
+                DOT_UNROLL for (int k = nb - 1; k >= 0; k--) s -= R_(i, i0 + k) * z[i0 + k];
+                z[i] = s;
+            }
+            SYNC();
+        }
+    }
     // border R with the new last null-space column; returns 1 if curvature acceptable
     static __device__ QP_FN int extend_R(int check_curvature) {
         QP_CTX
@@ -451,7 +515,8 @@ struct QPT {
         }
         SYNC();
         // r = R'^{-1} w[0..b): forward substitution, column oriented
-        _Pragma("unroll 1") for (int k = 0; k < b; k++) {
+        if constexpr (TEAM > 32) fwd_solve_R_blocked(w, b, b);
+        else _Pragma("unroll 1") for (int k = 0; k < b; k++) {
             double rk = w[k] / R_(k, k);
             SYNC();
             if (lane == 0) R_(k, b) = rk;
@@ -728,19 +793,24 @@ struct QPT {
             }
             SYNC();
             // R' u = rhs (forward), R z = u (backward); column oriented
-            _Pragma("unroll 1") for (int k = 0; k < nZ; k++) {
-                double uk = zv[k] / R_(k, k);
-                SYNC();
-                if (lane == 0) zv[k] = uk;
-                _Pragma("unroll 1") for (int i = k + 1 + lane; i < nZ; i += TEAM) zv[i] -= R_(k, i) * uk;
-                SYNC();
-            }
-            _Pragma("unroll 1") for (int k = nZ - 1; k >= 0; k--) {
-                double zk = zv[k] / R_(k, k);
-                SYNC();
-                if (lane == 0) zv[k] = zk;
-                _Pragma("unroll 1") for (int i = lane; i < k; i += TEAM) zv[i] -= R_(i, k) * zk;
-                SYNC();
+            if constexpr (TEAM > 32) {
+                fwd_solve_R_blocked(zv, nZ, -1);
+                bwd_solve_R_blocked(zv, nZ);
+            } else {
+                _Pragma("unroll 1") for (int k = 0; k < nZ; k++) {
+                    double uk = zv[k] / R_(k, k);
+                    SYNC();
+                    if (lane == 0) zv[k] = uk;
+                    _Pragma("unroll 1") for (int i = k + 1 + lane; i < nZ; i += TEAM) zv[i] -= R_(k, i) * uk;
+                    SYNC();
+                }
+                _Pragma("unroll 1") for (int k = nZ - 1; k >= 0; k--) {
+                    double zk = zv[k] / R_(k, k);
+                    SYNC();
+                    if (lane == 0) zv[k] = zk;
+                    _Pragma("unroll 1") for (int i = lane; i < k; i += TEAM) zv[i] -= R_(i, k) * zk;
+                    SYNC();
+                }
             }
             _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
                 double s = 0.0;

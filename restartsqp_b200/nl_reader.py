@@ -1,0 +1,561 @@
+"""AMPL .nl reader and batched NLP evaluator.
+
+The reference reads its test problems through Ipopt's AmplTNLP + ASL (src/SQPTNLP.cpp:13-132, test/simple_test.cpp:72-78;
+format sample test/CUTE_examples/hs071.nl:1-75); neither library is available here, so this module restates what that
+layer delivers to Algorithm.cpp for the text ("g") .nl format of the Hock-Schittkowski files:
+
+  * Get_nlp_info / Get_bounds_info / Get_starting_point            (SQPTNLP.cpp:31-62)
+  * Eval_f, Eval_gradient, Eval_constraints                        (SQPTNLP.cpp:67-92)
+  * Eval_Jacobian / Get_Strucutre_Jacobian   FORTRAN-style triplets in ASL's column-major order       (:94-111)
+  * Eval_Hessian  / Get_Structure_Hessian    upper triangle, column by column; the caller passes -lambda (:113-132)
+
+All instances of a batch share the model and differ in x, so every evaluation is a straight-line program over
+[batch]-long vectors.  The expression DAG is differentiated symbolically once (first and second order, with constant
+folding so that structural zeros vanish) and emitted as numpy source; `cuda_source()` emits the same straight-line
+program as a CUDA kernel body (one thread per instance) for a device-resident outer loop.
+"""
+import math
+import os
+
+import numpy as np
+
+from .sqp_types import NLPInfo
+
+_BIN = {0: "add", 1: "sub", 2: "mul", 3: "div", 5: "pow"}
+_UN = {16: "neg", 39: "sqrt", 41: "sin", 43: "log", 44: "exp", 46: "cos", 15: "abs", 38: "tan", 49: "atan", 37: "tanh",
+       40: "sinh", 45: "cosh", 42: "log10", 53: "acos", 51: "asin"}
+
+
+class Graph:
+    """Hash-consed expression DAG with local simplification.  Node = tuple; ids are positions in self.nodes."""
+
+    def __init__(self):
+        self.nodes, self.index = [], {}
+        self.ZERO, self.ONE = self.const(0.0), self.const(1.0)
+
+    def _mk(self, t):
+        i = self.index.get(t)
+        if i is None:
+            i = len(self.nodes)
+            self.nodes.append(t)
+            self.index[t] = i
+        return i
+
+    def const(self, c):
+        c = float(c)
+        return self._mk(("const", c if c != 0.0 else 0.0))
+
+    def var(self, i):
+        return self._mk(("var", int(i)))
+
+    def cval(self, a):
+        t = self.nodes[a]
+        return t[1] if t[0] == "const" else None
+
+    def add(self, a, b):
+        ca, cb = self.cval(a), self.cval(b)
+        if ca is not None and cb is not None:
+            return self.const(ca + cb)
+        if ca == 0.0:
+            return b
+        if cb == 0.0:
+            return a
+        return self._mk(("add", a, b))
+
+    def sub(self, a, b):
+        ca, cb = self.cval(a), self.cval(b)
+        if ca is not None and cb is not None:
+            return self.const(ca - cb)
+        if cb == 0.0:
+            return a
+        if ca == 0.0:
+            return self.neg(b)
+        if a == b:
+            return self.ZERO
+        return self._mk(("sub", a, b))
+
+    def mul(self, a, b):
+        ca, cb = self.cval(a), self.cval(b)
+        if ca is not None and cb is not None:
+            return self.const(ca * cb)
+        if ca == 0.0 or cb == 0.0:
+            return self.ZERO
+        if ca == 1.0:
+            return b
+        if cb == 1.0:
+            return a
+        if ca == -1.0:
+            return self.neg(b)
+        if cb == -1.0:
+            return self.neg(a)
+        return self._mk(("mul", a, b))
+
+    def div(self, a, b):
+        ca, cb = self.cval(a), self.cval(b)
+        if ca is not None and cb is not None and cb != 0.0:
+            return self.const(ca / cb)
+        if ca == 0.0:
+            return self.ZERO
+        if cb == 1.0:
+            return a
+        return self._mk(("div", a, b))
+
+    def pow(self, a, b):
+        ca, cb = self.cval(a), self.cval(b)
+        if cb == 0.0:
+            return self.ONE
+        if cb == 1.0:
+            return a
+        if ca is not None and cb is not None:
+            try:
+                return self.const(math.pow(ca, cb))
+            except (ValueError, OverflowError):
+                pass
+        return self._mk(("pow", a, b))
+
+    def neg(self, a):
+        ca = self.cval(a)
+        if ca is not None:
+            return self.const(-ca)
+        if self.nodes[a][0] == "neg":
+            return self.nodes[a][1]
+        return self._mk(("neg", a))
+
+    def un(self, op, a):
+        if op == "neg":
+            return self.neg(a)
+        ca = self.cval(a)
+        if ca is not None:
+            try:
+                return self.const(getattr(math, {"abs": "fabs"}.get(op, op))(ca))
+            except (ValueError, OverflowError):
+                pass
+        return self._mk((op, a))
+
+    def sum(self, args):
+        out = self.ZERO
+        for a in args:
+            out = self.add(out, a)
+        return out
+
+    # ---- differentiation (memoised per variable)
+    def diff(self, a, v, memo):
+        key = (a, v)
+        if key in memo:
+            return memo[key]
+        t = self.nodes[a]
+        op = t[0]
+        if op == "const":
+            r = self.ZERO
+        elif op == "var":
+            r = self.ONE if t[1] == v else self.ZERO
+        elif op == "add":
+            r = self.add(self.diff(t[1], v, memo), self.diff(t[2], v, memo))
+        elif op == "sub":
+            r = self.sub(self.diff(t[1], v, memo), self.diff(t[2], v, memo))
+        elif op == "mul":
+            r = self.add(self.mul(self.diff(t[1], v, memo), t[2]), self.mul(t[1], self.diff(t[2], v, memo)))
+        elif op == "div":
+            da, db = self.diff(t[1], v, memo), self.diff(t[2], v, memo)
+            r = self.sub(self.div(da, t[2]), self.div(self.mul(a, db), t[2]))  # (a/b)' = a'/b - (a/b) b'/b
+        elif op == "pow":
+            base, ex = t[1], t[2]
+            db, de = self.diff(base, v, memo), self.diff(ex, v, memo)
+            ce = self.cval(ex)
+            if ce is not None:
+                r = self.mul(self.mul(ex, self.pow(base, self.const(ce - 1.0))), db)
+            else:
+                r = self.mul(a, self.add(self.mul(de, self.un("log", base)), self.div(self.mul(ex, db), base)))
+        elif op == "neg":
+            r = self.neg(self.diff(t[1], v, memo))
+        else:
+            u, du = t[1], self.diff(t[1], v, memo)
+            if du == self.ZERO:
+                r = self.ZERO
+            elif op == "sqrt":
+                r = self.div(du, self.mul(self.const(2.0), a))
+            elif op == "sin":
+                r = self.mul(self.un("cos", u), du)
+            elif op == "cos":
+                r = self.neg(self.mul(self.un("sin", u), du))
+            elif op == "log":
+                r = self.div(du, u)
+            elif op == "log10":
+                r = self.div(du, self.mul(u, self.const(math.log(10.0))))
+            elif op == "exp":
+                r = self.mul(a, du)
+            elif op == "tan":
+                r = self.mul(self.add(self.ONE, self.mul(a, a)), du)
+            elif op == "atan":
+                r = self.div(du, self.add(self.ONE, self.mul(u, u)))
+            elif op == "tanh":
+                r = self.mul(self.sub(self.ONE, self.mul(a, a)), du)
+            elif op == "sinh":
+                r = self.mul(self.un("cosh", u), du)
+            elif op == "cosh":
+                r = self.mul(self.un("sinh", u), du)
+            elif op == "asin":
+                r = self.div(du, self.un("sqrt", self.sub(self.ONE, self.mul(u, u))))
+            elif op == "acos":
+                r = self.neg(self.div(du, self.un("sqrt", self.sub(self.ONE, self.mul(u, u)))))
+            elif op == "abs":
+                r = self.mul(self.div(u, a), du)
+            else:
+                raise NotImplementedError(op)
+        memo[key] = r
+        return r
+
+    def depends(self, a, memo):
+        """frozenset of variable indices the node depends on"""
+        if a in memo:
+            return memo[a]
+        t = self.nodes[a]
+        if t[0] == "const":
+            r = frozenset()
+        elif t[0] == "var":
+            r = frozenset([t[1]])
+        else:
+            r = frozenset().union(*[self.depends(k, memo) for k in t[1:]])
+        memo[a] = r
+        return r
+
+
+class _Tokens:
+    def __init__(self, text):
+        self.lines = [ln.split("#")[0].rstrip() for ln in text.splitlines()]
+        self.pos = 0
+
+    def next(self):
+        ln = self.lines[self.pos]
+        self.pos += 1
+        return ln
+
+    def more(self):
+        while self.pos < len(self.lines) and not self.lines[self.pos].strip():
+            self.pos += 1
+        return self.pos < len(self.lines)
+
+
+def _read_expr(tok, G, defined):
+    ln = tok.next().strip()
+    k = ln[0]
+    if k == "n":
+        return G.const(float(ln[1:]))
+    if k == "v":
+        i = int(ln[1:])
+        return defined[i] if i in defined else G.var(i)
+    if k == "o":
+        op = int(ln[1:])
+        if op in _BIN:
+            a = _read_expr(tok, G, defined)
+            b = _read_expr(tok, G, defined)
+            return getattr(G, _BIN[op])(a, b)
+        if op in _UN:
+            return G.un(_UN[op], _read_expr(tok, G, defined))
+        if op == 54:
+            cnt = int(tok.next().strip())
+            return G.sum([_read_expr(tok, G, defined) for _ in range(cnt)])
+        raise NotImplementedError("nl opcode o%d" % op)
+    raise NotImplementedError("nl expression token %r" % ln)
+
+
+def _read_bounds(tok, count):
+    lo, hi = np.empty(count), np.empty(count)
+    for i in range(count):
+        f = tok.next().split()
+        kind = int(f[0])
+        if kind == 0:
+            lo[i], hi[i] = float(f[1]), float(f[2])
+        elif kind == 1:
+            lo[i], hi[i] = -np.inf, float(f[1])
+        elif kind == 2:
+            lo[i], hi[i] = float(f[1]), np.inf
+        elif kind == 3:
+            lo[i], hi[i] = -np.inf, np.inf
+        elif kind == 4:
+            lo[i] = hi[i] = float(f[1])
+        else:
+            raise NotImplementedError("complementarity constraints")
+    return lo, hi
+
+
+class NLModel:
+    """Parsed .nl problem: expression ids in a Graph plus bounds, start and the linear parts."""
+
+    def __init__(self, path):
+        with open(path) as f:
+            text = f.read()
+        if not text.startswith("g"):
+            raise ValueError("only the text ('g') .nl format is read")
+        tok = _Tokens(text)
+        hdr = [tok.next().split() for _ in range(10)]
+        self.name = os.path.splitext(os.path.basename(path))[0]
+        self.n, self.m, self.n_obj = int(hdr[1][0]), int(hdr[1][1]), int(hdr[1][2])
+        if int(hdr[5][1]) != 0:
+            raise NotImplementedError("imported functions (F segments)")
+        self.nzJ = int(hdr[7][0])
+        G = self.G = Graph()
+        n, m = self.n, self.m
+        self.con_nl = [G.ZERO] * m
+        self.obj_nl, self.obj_sense = G.ZERO, 0
+        self.con_lin = [dict() for _ in range(m)]
+        self.obj_lin = {}
+        self.x0 = np.zeros(n)
+        self.lam0 = np.zeros(m)
+        self.x_l, self.x_u = np.full(n, -np.inf), np.full(n, np.inf)
+        self.c_l, self.c_u = np.full(m, -np.inf), np.full(m, np.inf)
+        defined = {}
+        while tok.more():
+            ln = tok.next().strip()
+            k, rest = ln[0], ln[1:].split()
+            if k == "C":
+                self.con_nl[int(rest[0])] = _read_expr(tok, G, defined)
+            elif k == "O":
+                if int(rest[0]) == 0:
+                    self.obj_sense = int(rest[1])
+                    self.obj_nl = _read_expr(tok, G, defined)
+                else:
+                    _read_expr(tok, G, defined)
+            elif k == "V":
+                idx, nlin = int(rest[0]), int(rest[1])
+                e = G.ZERO
+                for _ in range(nlin):
+                    f = tok.next().split()
+                    j = int(f[0])
+                    e = G.add(e, G.mul(G.const(float(f[1])), defined[j] if j in defined else G.var(j)))
+                defined[idx] = G.add(e, _read_expr(tok, G, defined))
+            elif k == "r":
+                self.c_l, self.c_u = _read_bounds(tok, m)
+            elif k == "b":
+                self.x_l, self.x_u = _read_bounds(tok, n)
+            elif k == "x":
+                for _ in range(int(rest[0])):
+                    f = tok.next().split()
+                    self.x0[int(f[0])] = float(f[1])
+            elif k == "d":
+                for _ in range(int(rest[0])):
+                    f = tok.next().split()
+                    self.lam0[int(f[0])] = float(f[1])
+            elif k == "k":
+                for _ in range(int(rest[0])):
+                    tok.next()
+            elif k == "J":
+                i = int(rest[0])
+                for _ in range(int(rest[1])):
+                    f = tok.next().split()
+                    self.con_lin[i][int(f[0])] = float(f[1])
+            elif k == "G":
+                i = int(rest[0])
+                for _ in range(int(rest[1])):
+                    f = tok.next().split()
+                    if i == 0:
+                        self.obj_lin[int(f[0])] = float(f[1])
+            elif k == "S":
+                for _ in range(int(rest[1])):
+                    tok.next()
+            else:
+                raise NotImplementedError("nl segment %r" % ln)
+
+
+_NP_FUN = {"sqrt": "np.sqrt", "sin": "np.sin", "cos": "np.cos", "log": "np.log", "exp": "np.exp", "abs": "np.abs", "tan": "np.tan",
+           "atan": "np.arctan", "tanh": "np.tanh", "sinh": "np.sinh", "cosh": "np.cosh", "log10": "np.log10", "acos": "np.arccos",
+           "asin": "np.arcsin"}
+_C_FUN = {"abs": "fabs"}
+_INFIX = {"add": "+", "sub": "-", "mul": "*", "div": "/"}
+
+
+def _emit(G, roots, lang):
+    """Straight-line code computing the nodes `roots`; returns (lines, name_of(node))."""
+    order, seen = [], set()
+
+    def visit(a):
+        stack = [(a, False)]
+        while stack:
+            node, done = stack.pop()
+            if done:
+                order.append(node)
+                continue
+            if node in seen:
+                continue
+            seen.add(node)
+            stack.append((node, True))
+            t = G.nodes[node]
+            if t[0] not in ("const", "var"):
+                for k in t[1:]:
+                    if k not in seen:
+                        stack.append((k, False))
+
+    for r in roots:
+        visit(r)
+    name = {}
+    lines = []
+    for a in order:
+        t = G.nodes[a]
+        if t[0] == "const":
+            name[a] = repr(t[1]) if lang == "py" else ("%r" % t[1])
+            if t[1] < 0:
+                name[a] = "(" + name[a] + ")"
+            continue
+        if t[0] == "var":
+            name[a] = "x%d" % t[1]
+            continue
+        nm = "t%d" % a
+        if t[0] in _INFIX:
+            rhs = "%s %s %s" % (name[t[1]], _INFIX[t[0]], name[t[2]])
+        elif t[0] == "pow":
+            ce = G.cval(t[2])
+            if ce == 2.0:
+                rhs = "%s * %s" % (name[t[1]], name[t[1]])
+            else:
+                rhs = ("np.power(%s, %s)" if lang == "py" else "pow(%s, %s)") % (name[t[1]], name[t[2]])
+        elif t[0] == "neg":
+            rhs = "-%s" % name[t[1]]
+        else:
+            rhs = "%s(%s)" % ((_NP_FUN[t[0]] if lang == "py" else _C_FUN.get(t[0], t[0])), name[t[1]])
+        lines.append(("%s = %s" if lang == "py" else "const double %s = %s;") % (nm, rhs))
+        name[a] = nm
+    return lines, name
+
+
+class AmplNLP:
+    """The SQPTNLP-shaped view of an NLModel, batched over instances (x is [batch][n])."""
+
+    def __init__(self, path):
+        md = self.model = NLModel(path) if not isinstance(path, NLModel) else path
+        G, n, m = md.G, md.n, md.m
+        self.n, self.m, self.name = n, m, md.name
+        sgn = -1.0 if md.obj_sense == 1 else 1.0  # AmplTNLP minimises -f for "maximize"
+        f = G.add(md.obj_nl, G.sum([G.mul(G.const(c), G.var(j)) for j, c in sorted(md.obj_lin.items())]))
+        self.f_node = G.mul(G.const(sgn), f)
+        self.c_nodes = [G.add(md.con_nl[i], G.sum([G.mul(G.const(c), G.var(j)) for j, c in sorted(md.con_lin[i].items())]))
+                        for i in range(m)]
+        memo = {}
+        self.grad_nodes = [G.diff(self.f_node, j, memo) for j in range(n)]
+        # Jacobian structure: the J segments (every variable that appears in a row), column-major like ASL's goff
+        ent = sorted((j, i) for i in range(m) for j in md.con_lin[i])
+        self.J_col1 = np.array([j + 1 for j, i in ent], np.int32)
+        self.J_row1 = np.array([i + 1 for j, i in ent], np.int32)
+        self.jac_nodes = [G.diff(self.c_nodes[i], j, memo) for j, i in ent]
+        dep = {}
+        for i in range(m):
+            extra = G.depends(self.c_nodes[i], dep) - set(md.con_lin[i])
+            if extra:
+                raise ValueError("constraint %d depends on variables missing from its J segment: %s" % (i, sorted(extra)))
+        # Hessian of the Lagrangian: upper triangle, column by column; structure = union of structural non-zeros
+        funcs = [self.f_node] + self.c_nodes
+        first = [[G.diff(fn, j, memo) for j in range(n)] for fn in funcs]
+        hess = {}
+        for k, fn in enumerate(funcs):
+            for j in range(n):
+                if first[k][j] == G.ZERO:
+                    continue
+                for i in range(j + 1):
+                    d2 = G.diff(first[k][j], i, memo)
+                    if d2 != G.ZERO:
+                        hess.setdefault((j, i), []).append((k, d2))
+        hk = sorted(hess)
+        self.H_col1 = np.array([j + 1 for j, i in hk], np.int32)
+        self.H_row1 = np.array([i + 1 for j, i in hk], np.int32)
+        self._hess_terms = [hess[k] for k in hk]
+        self._compile()
+
+    # ---- code generation
+    def _compile(self):
+        G, n, m = self.model.G, self.n, self.m
+        src = ["import numpy as np", ""]
+
+        def fun(name, roots, extra_args, body_tail):
+            lines, nm = _emit(G, roots, "py")
+            src.append("def %s(x%s):" % (name, extra_args))
+            src.append("    B = x.shape[0]")
+            for j in range(n):
+                src.append("    x%d = x[:, %d]" % (j, j))
+            for ln in lines:
+                src.append("    " + ln)
+            for ln in body_tail(nm):
+                src.append("    " + ln)
+            src.append("")
+
+        full = lambda e: "np.zeros(B) + %s" % e
+        fun("eval_f", [self.f_node], "", lambda nm: ["return %s" % full(nm[self.f_node])])
+        fun("eval_c", self.c_nodes, "", lambda nm: ["out = np.empty((B, %d))" % m] +
+            ["out[:, %d] = %s" % (i, nm[a]) for i, a in enumerate(self.c_nodes)] + ["return out"])
+        fun("eval_grad", self.grad_nodes, "", lambda nm: ["out = np.empty((B, %d))" % n] +
+            ["out[:, %d] = %s" % (i, nm[a]) for i, a in enumerate(self.grad_nodes)] + ["return out"])
+        fun("eval_jac", self.jac_nodes, "", lambda nm: ["out = np.empty((B, %d))" % len(self.jac_nodes)] +
+            ["out[:, %d] = %s" % (i, nm[a]) for i, a in enumerate(self.jac_nodes)] + ["return out"])
+        hroots = [d2 for terms in self._hess_terms for _, d2 in terms]
+
+        def htail(nm):
+            out = ["out = np.empty((B, %d))" % len(self._hess_terms)]
+            for e, terms in enumerate(self._hess_terms):
+                parts = []
+                for k, d2 in terms:
+                    parts.append(nm[d2] if k == 0 else "lam[:, %d] * %s" % (k - 1, nm[d2]))
+                out.append("out[:, %d] = %s" % (e, " + ".join(parts)))
+            return out + ["return out"]
+
+        fun("eval_hess", hroots, ", lam", htail)
+        self.source = "\n".join(src)
+        ns = {}
+        exec(compile(self.source, "<nl:%s>" % self.name, "exec"), ns)
+        self._f, self._c, self._g, self._j, self._h = ns["eval_f"], ns["eval_c"], ns["eval_grad"], ns["eval_jac"], ns["eval_hess"]
+
+    def cuda_source(self):
+        """The same straight-line program as one CUDA kernel: thread b evaluates f, c, grad f, the Jacobian triplet values
+        and the Lagrangian-Hessian triplet values of instance b (instance-major outputs)."""
+        G, n, m = self.model.G, self.n, self.m
+        hroots = [d2 for terms in self._hess_terms for _, d2 in terms]
+        roots = [self.f_node] + self.c_nodes + self.grad_nodes + self.jac_nodes + hroots
+        lines, nm = _emit(G, roots, "c")
+        zJ, zH = len(self.jac_nodes), len(self._hess_terms)
+        out = ['extern "C" __global__ void nlp_eval(int B, const double* __restrict__ x, const double* __restrict__ lam,',
+               "                                    double* f, double* c, double* grad, double* jac, double* hess) {",
+               "    const int b = blockIdx.x * blockDim.x + threadIdx.x;", "    if (b >= B) return;"]
+        out += ["    const double x%d = x[(size_t)b * %d + %d];" % (j, n, j) for j in range(n)]
+        out += ["    " + ln for ln in lines]
+        out.append("    f[b] = %s;" % nm[self.f_node])
+        out += ["    c[(size_t)b * %d + %d] = %s;" % (m, i, nm[a]) for i, a in enumerate(self.c_nodes)]
+        out += ["    grad[(size_t)b * %d + %d] = %s;" % (n, i, nm[a]) for i, a in enumerate(self.grad_nodes)]
+        out += ["    jac[(size_t)b * %d + %d] = %s;" % (zJ, i, nm[a]) for i, a in enumerate(self.jac_nodes)]
+        for e, terms in enumerate(self._hess_terms):
+            parts = [nm[d2] if k == 0 else "lam[(size_t)b * %d + %d] * %s" % (m, k - 1, nm[d2]) for k, d2 in terms]
+            out.append("    hess[(size_t)b * %d + %d] = %s;" % (zH, e, " + ".join(parts)))
+        out.append("}")
+        return "\n".join(out)
+
+    # ---- SQPTNLP interface (src/SQPTNLP.cpp)
+    def Get_nlp_info(self):
+        return NLPInfo(nCon=self.m, nVar=self.n, nnz_jac_g=len(self.jac_nodes), nnz_h_lag=len(self._hess_terms))
+
+    def Get_bounds_info(self):
+        md = self.model
+        big = 1.0e19  # Ipopt's nlp_{lower,upper}_bound_inf as AmplTNLP reports infinite bounds
+        cv = lambda v: np.where(np.isinf(v), np.sign(v) * big, v)
+        return cv(md.x_l), cv(md.x_u), cv(md.c_l), cv(md.c_u)
+
+    def Get_starting_point(self):
+        return self.model.x0.copy(), self.model.lam0.copy()
+
+    def _x(self, x):
+        return np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+
+    def Eval_f(self, x):
+        with np.errstate(all="ignore"):
+            return self._f(self._x(x))
+
+    def Eval_constraints(self, x):
+        with np.errstate(all="ignore"):
+            return self._c(self._x(x))
+
+    def Eval_gradient(self, x):
+        with np.errstate(all="ignore"):
+            return self._g(self._x(x))
+
+    def Eval_Jacobian(self, x):
+        with np.errstate(all="ignore"):
+            return self._j(self._x(x))
+
+    def Eval_Hessian(self, x, lam):
+        with np.errstate(all="ignore"):
+            return self._h(self._x(x), np.ascontiguousarray(np.atleast_2d(lam), dtype=np.float64))

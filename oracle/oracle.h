@@ -148,6 +148,8 @@ int orc_qp_solve_batch(int B, int nV, int nC, const int* Hp, const int* Hi, cons
 /* flop counter for the roofline model of SURVEY.md section 8(d) */
 double orc_qp_get_flops(const orc_qp* q);
 int orc_qp_get_max_free(const orc_qp* q);
+/* 1 if the last orc_qp_hotstart_matrices already performed the cold re-init of handle_error (src/qpOASESInterface.cpp:746-754) */
+int orc_qp_get_fell_back(const orc_qp* q);
 
 #ifdef __cplusplus
 }

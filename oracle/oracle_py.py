@@ -57,6 +57,8 @@ def lib():
         L.orc_qp_get_flops.restype = C.c_double
         L.orc_qp_get_flops.argtypes = [C.c_void_p]
         L.orc_qp_destroy.argtypes = [C.c_void_p]
+        L.orc_qp_get_fell_back.argtypes = [C.c_void_p]
+        L.orc_qp_get_max_free.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 

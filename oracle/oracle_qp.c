@@ -65,6 +65,7 @@ struct orc_qp {
     /* work */
     double *dx, *dy, *dAx, *t1, *t2, *t3, *w, *a, *yv, *zv, *xiC, *xiB, *dg, *dlb, *dub, *dlbA, *dubA;
     int status, iters, initialised, ramp_offset, max_nFR;
+    int fell_back; /* last hotstart_matrices could not keep the working set and ran the cold start itself */
     double flops;
     int verbose;
 };
@@ -760,7 +761,9 @@ int orc_qp_hotstart_matrices(orc_qp* q, const orc_qp_options* opt, const double*
     if (q->has_H && H_val) memcpy(q->Hv, H_val, sizeof(double) * q->Hp[nV]);
     if (A_val) { memcpy(q->Av, A_val, sizeof(double) * q->Ap[nV]); build_dense_A(q); }
     set_targets(q, g, lb, ub, lbA, ubA);
+    q->fell_back = 0;
     if (refactorise(q)) {
+        q->fell_back = 1;
         /* projected Hessian of the kept working set is not positive definite: cold start
          * (what the reference does through handle_error, src/qpOASESInterface.cpp:746-749) */
         return cold_start(q, opt);
@@ -800,3 +803,4 @@ void orc_qp_get_working_set(const orc_qp* q, int* raw_b, int* raw_c) {
 double orc_qp_get_flops(const orc_qp* q) { return q->flops; }
 /* largest number of free variables seen since creation (sizes the factors of the CUDA kernel) */
 int orc_qp_get_max_free(const orc_qp* q) { return q->max_nFR; }
+int orc_qp_get_fell_back(const orc_qp* q) { return q->fell_back; }

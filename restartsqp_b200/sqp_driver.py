@@ -110,7 +110,10 @@ class BatchedSQP:
     """Algorithm (include/sqphot/Algorithm.hpp) for a batch of instances.  `make_handler(nlp_info, qptype)` builds the
     QP and LP handlers (default: the CUDA-backed QPhandler)."""
 
-    def __init__(self, nlp, x0=None, options: Options = None, make_handler=None, device=0):
+    def __init__(self, nlp, x0=None, options: Options = None, make_handler=None, device=0, dump_dir=None, dump_max=4):
+        """dump_dir: where the QP of an instance whose subproblem failed is written in the QORE `.log` layout (the
+        `myQP_->WriteQPData(problem_name + "qpdata.log")` of src/Algorithm.cpp:69), at most dump_max files per run."""
+        self.dump_dir_, self.dump_left_ = dump_dir, dump_max
         self.nlp_ = nlp
         self.options_ = options if options is not None else Options()
         self.info = nlp.Get_nlp_info()
@@ -217,7 +220,28 @@ class BatchedSQP:
         failed = mask & ~(np.asarray(ok, dtype=bool) & (status == int(Exitflag.QP_OPTIMAL)))
         self.exitflag_[failed] = np.where(status[failed] == int(Exitflag.QP_OPTIMAL),
                                           int(Exitflag.QPERROR_INTERNAL_ERROR), status[failed])
+        if self.dump_dir_ and failed.any() and self.dump_left_ > 0:
+            self._dump_failed(np.where(failed)[0])
         return mask & ~failed
+
+    def _dump_failed(self, idx):
+        """src/Algorithm.cpp:69: dump the QP that could not be solved (QORE layout, readable by qp_dump.read_qore_log and by
+        the reference's replay driver test/QPsolvers_testers.cpp)."""
+        import os
+        from . import qp_dump
+        si = self.myQP_.solverInterface_
+        if not hasattr(si, "getA"):
+            return
+        A, Hm = si.getA(), si.getH()
+        os.makedirs(self.dump_dir_, exist_ok=True)
+        name = getattr(self.nlp_, "name", type(self.nlp_).__name__)
+        lb, ub, lbA, ubA, g = si.getLb(), si.getUb(), si.getLbA(), si.getUbA(), si.getG()
+        for b in idx[: self.dump_left_]:
+            q = dict(nV=si.nV_, nC=si.nC_, lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b], g=g[b],
+                     A_colptr=A["ColIndex"], A_rowidx=A["RowIndex"], A_val=A["MatVal"][b],
+                     H_colptr=Hm["ColIndex"], H_rowidx=Hm["RowIndex"], H_val=Hm["MatVal"][b])
+            qp_dump.write_qore_log(os.path.join(self.dump_dir_, "QORE_%s_inst%dqpdata.log" % (name, int(b))), q)
+            self.dump_left_ -= 1
 
     # ---- src/Algorithm.cpp:414-429
     def get_trial_point_info(self, mask):

@@ -115,7 +115,8 @@ class OracleQPInterface:
             else:
                 st = s.hotstart(*args) if mode == "fixed" else s.hotstart_matrices(None if self.is_lp else self.Hv[b], self.Av[b], *args)
                 its = s.solution()[3]
-                if st != 20:  # one-retry recovery: plain re-init
+                fell_back = mode == "varied" and bool(orc.lib().orc_qp_get_fell_back(s.h))
+                if st != 20 and not fell_back:  # one-retry recovery: plain re-init (already done inside when the kept set could not be refactorised)
                     st = s.init(Hcsc, args[0], Acsc, *args[1:], is_lp=self.is_lp)
                     its += s.solution()[3]
             self.inited[b] = (st == 20)

@@ -40,3 +40,53 @@ def test_hs071_many_perturbed_starts(gpu_lib):
     assert ok.mean() > 0.99, np.unique(res.exitflag, return_counts=True)
     assert np.abs(res.x[ok] - X_STAR).max() < 1e-3
     assert np.abs(res.obj[ok] - 17.0140173).max() < 1e-3
+
+
+HS_SAMPLE = ["hs001", "hs015", "hs035", "hs043", "hs056", "hs071", "hs076", "hs087", "hs100", "hs104", "hs113", "hs118", "hs119"]
+
+
+@pytest.mark.parametrize("name", HS_SAMPLE)
+def test_hs_suite_gpu_equals_oracle_driven_loop(gpu_lib, name):
+    """BASELINE.json configs[2] (HS suite via the .nl reader, perturbed starts): the SQP loop on the CUDA backend takes
+    the same path, iteration for iteration, as the same loop on the CPU oracle twin."""
+    import os
+    from restartsqp_b200.nl_reader import AmplNLP
+    from test_hs_suite import HS_DIR, perturbed_starts
+    nlp = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+    B = 6
+    X = perturbed_starts(nlp, B, HS_SAMPLE.index(name))
+    opt_g, opt_o = r.Options(iter_max=200), r.Options(iter_max=200)
+    res_g = BatchedSQP(nlp, x0=X, options=opt_g).Optimize()
+    mk = lambda info, qt: r.QPhandler(info, qt, opt_o, batch=B, backend=OracleQPInterface(info, qt, opt_o, batch=B), refresh_ubA=True)
+    res_o = BatchedSQP(nlp, x0=X, options=opt_o, make_handler=mk).Optimize()
+    assert (res_g.exitflag == res_o.exitflag).all(), (res_g.exitflag, res_o.exitflag)
+    assert (res_g.iters == res_o.iters).all() and (res_g.qp_iter == res_o.qp_iter).all()
+    assert np.abs(res_g.x - res_o.x).max() <= 1e-8 * max(1.0, np.abs(res_o.x).max())
+    assert (res_g.exitflag[0] == int(r.Exitflag.OPTIMAL))
+
+
+def test_failed_qp_is_dumped_and_replays(gpu_lib, tmp_path):
+    """src/Algorithm.cpp:64-72: the QP that could not be solved is written as `<problem>qpdata.log` (QORE layout); the dump
+    reads back (qp_dump) and replays through the data constructor of the backend to the same failure / to the oracle's answer."""
+    import glob
+    from restartsqp_b200 import qp_dump
+    from oracle import oracle_py as orc
+    import helpers as H
+    opt = r.Options(qp_maxiter=1)  # every non-trivial QP stops in PERFORMINGHOMOTOPY
+    alg = BatchedSQP(HS071(), x0=starts(5), options=opt, dump_dir=str(tmp_path), dump_max=2)
+    res = alg.Optimize()
+    assert (res.exitflag == int(r.Exitflag.QPERROR_PERFORMINGHOMOTOPY)).all()
+    files = sorted(glob.glob(str(tmp_path / "QORE_*qpdata.log")))
+    assert len(files) == 2
+    q = qp_dump.read_qore_log(files[0])
+    assert (q["nV"], q["nC"]) == (8, 2)
+    s = qp_dump.replay(q, batch=3, options=opt)
+    s.optimizeQP()
+    assert (s.get_status() == int(r.Exitflag.QPERROR_PERFORMINGHOMOTOPY)).all()
+    s.close()
+    s = qp_dump.replay(files[0], batch=3)
+    s.optimizeQP()
+    p = dict(nV=8, nC=2, g=np.array(q["g"]), lb=np.array(q["lb"]), ub=np.array(q["ub"]), lbA=np.array(q["lbA"]), ubA=np.array(q["ubA"]))
+    o = H.oracle_solve(orc, p, Acsc=(q["A_colptr"], q["A_rowidx"], np.array(q["A_val"])), Hcsc=(q["H_colptr"], q["H_rowidx"], np.array(q["H_val"])))
+    assert (s.get_status() == o["status"]).all() and np.abs(s.get_optimal_solution()[1] - o["x"]).max() <= 1e-8 * max(1.0, np.abs(o["x"]).max())
+    s.close()

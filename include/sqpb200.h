@@ -186,6 +186,25 @@ int sqpb200_solve_config(sqpb200_handle h, int* team_size, int* qps_per_cta, int
 /* device time of the last solve launch measured with CUDA events on the handle's stream (ms) */
 float sqpb200_last_solve_ms(sqpb200_handle h);
 
+/* ---- batched NLP evaluation on the device (the step on the other side of the path: what the reference gets from
+ * Ipopt's AmplTNLP through SQPTNLP::Eval_f / Eval_gradient / Eval_constraints / Eval_Jacobian / Eval_Hessian,
+ * src/SQPTNLP.cpp:67-132).  `cuda_source` defines two kernels, one thread per instance:
+ *   nlp_eval_fc (int B, const double* x, double* f, double* c)
+ *   nlp_eval_all(int B, const double* x, const double* lam, double* f, double* c, double* grad, double* jac, double* hess)
+ * (x[B][n], lam[B][m], c[B][m], grad[B][n], jac[B][zJ], hess[B][zH]); it is compiled with NVRTC for sm_100a
+ * (--fmad=false).  compile needs no GPU; load / eval do and fail with SQPB200_ERR_CUDA without one. */
+typedef struct sqpb200_nlp_s* sqpb200_nlp;
+int sqpb200_nlp_compile(const char* cuda_source, int n, int m, int zJ, int zH, char* log, int log_len, sqpb200_nlp* out);
+long long sqpb200_nlp_cubin_size(sqpb200_nlp h);
+int sqpb200_nlp_load(sqpb200_nlp h, int device);
+/* which = 0: f and c; 1: f, c, grad, jac, hess (lam = the multipliers the caller wants in the Lagrangian Hessian:
+ * Algorithm passes -lambda, src/SQPTNLP.cpp:124-126).  NULL outputs are skipped; loc as everywhere. */
+int sqpb200_nlp_eval(sqpb200_nlp h, int which, int B, const double* x, const double* lam, double* f, double* c,
+                     double* grad, double* jac, double* hess, int loc, void* stream);
+int sqpb200_nlp_destroy(sqpb200_nlp h);
+long long sqpb200_nlp_launch_count(sqpb200_nlp h);
+const char* sqpb200_nlp_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

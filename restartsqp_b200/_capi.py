@@ -27,6 +27,8 @@ EXPORTS = [
     "sqpb200_solve", "sqpb200_get_solution", "sqpb200_get_working_set", "sqpb200_kkt_residuals",
     "sqpb200_kkt_residuals_recompute", "sqpb200_spmv", "sqpb200_assemble_csc_batched", "sqpb200_launch_count",
     "sqpb200_solve_config", "sqpb200_last_solve_ms",
+    "sqpb200_nlp_compile", "sqpb200_nlp_cubin_size", "sqpb200_nlp_load", "sqpb200_nlp_eval", "sqpb200_nlp_destroy",
+    "sqpb200_nlp_launch_count", "sqpb200_nlp_last_error",
 ]
 
 
@@ -54,6 +56,15 @@ def lib():
         L.sqpb200_launch_count.argtypes = [C.c_void_p]
         L.sqpb200_last_solve_ms.restype = C.c_float
         L.sqpb200_last_solve_ms.argtypes = [C.c_void_p]
+        L.sqpb200_nlp_last_error.restype = C.c_char_p
+        L.sqpb200_nlp_cubin_size.restype = C.c_longlong
+        L.sqpb200_nlp_cubin_size.argtypes = [C.c_void_p]
+        L.sqpb200_nlp_launch_count.restype = C.c_longlong
+        L.sqpb200_nlp_launch_count.argtypes = [C.c_void_p]
+        L.sqpb200_nlp_compile.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_void_p]
+        L.sqpb200_nlp_load.argtypes = [C.c_void_p, C.c_int]
+        L.sqpb200_nlp_destroy.argtypes = [C.c_void_p]
+        L.sqpb200_nlp_eval.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
 

@@ -30,7 +30,8 @@ def _nvcc():
 
 
 def _units():
-    units = [(os.path.join(CSRC, "capi.cu"), os.path.join(OBJDIR, "capi.o"), [])]
+    units = [(os.path.join(CSRC, "capi.cu"), os.path.join(OBJDIR, "capi.o"), []),
+             (os.path.join(CSRC, "nlp_eval.cu"), os.path.join(OBJDIR, "nlp_eval.o"), [])]
     for team, cta in TEAMS:
         # multi-warp teams are compiled fully inlined (see the QP_INLINE_ALL note in qp_kernel.cuh)
         units.append((os.path.join(CSRC, "qp_solve_inst.cu"), os.path.join(OBJDIR, "qp_solve_%d_%d.o" % (team, cta)),
@@ -71,7 +72,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(_units())) as ex:
         logs = list(ex.map(compile_one, _units()))
-    cmd = [nvcc, "-shared", "-o", LIB] + [u[1] for u in _units()]
+    cmd = [nvcc, "-shared", "-o", LIB] + [u[1] for u in _units()] + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)

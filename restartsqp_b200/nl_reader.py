@@ -502,27 +502,50 @@ class AmplNLP:
         self._f, self._c, self._g, self._j, self._h = ns["eval_f"], ns["eval_c"], ns["eval_grad"], ns["eval_jac"], ns["eval_hess"]
 
     def cuda_source(self):
-        """The same straight-line program as one CUDA kernel: thread b evaluates f, c, grad f, the Jacobian triplet values
-        and the Lagrangian-Hessian triplet values of instance b (instance-major outputs)."""
+        """The same straight-line programs as two CUDA kernels, one thread per instance, instance-major outputs:
+        nlp_eval_fc (f, c at trial points) and nlp_eval_all (f, c, grad f, Jacobian and Lagrangian-Hessian triplet
+        values).  Compiled at run time by sqpb200_nlp_compile (NVRTC, sm_100a, --fmad=false)."""
         G, n, m = self.model.G, self.n, self.m
-        hroots = [d2 for terms in self._hess_terms for _, d2 in terms]
-        roots = [self.f_node] + self.c_nodes + self.grad_nodes + self.jac_nodes + hroots
-        lines, nm = _emit(G, roots, "c")
         zJ, zH = len(self.jac_nodes), len(self._hess_terms)
-        out = ['extern "C" __global__ void nlp_eval(int B, const double* __restrict__ x, const double* __restrict__ lam,',
-               "                                    double* f, double* c, double* grad, double* jac, double* hess) {",
-               "    const int b = blockIdx.x * blockDim.x + threadIdx.x;", "    if (b >= B) return;"]
-        out += ["    const double x%d = x[(size_t)b * %d + %d];" % (j, n, j) for j in range(n)]
-        out += ["    " + ln for ln in lines]
-        out.append("    f[b] = %s;" % nm[self.f_node])
-        out += ["    c[(size_t)b * %d + %d] = %s;" % (m, i, nm[a]) for i, a in enumerate(self.c_nodes)]
-        out += ["    grad[(size_t)b * %d + %d] = %s;" % (n, i, nm[a]) for i, a in enumerate(self.grad_nodes)]
-        out += ["    jac[(size_t)b * %d + %d] = %s;" % (zJ, i, nm[a]) for i, a in enumerate(self.jac_nodes)]
+        hroots = [d2 for terms in self._hess_terms for _, d2 in terms]
+
+        def body(roots):
+            lines, nm = _emit(G, roots, "c")
+            used = set()
+            for r_ in roots:
+                stack = [r_]
+                while stack:
+                    a = stack.pop()
+                    if a in used:
+                        continue
+                    used.add(a)
+                    t = G.nodes[a]
+                    if t[0] not in ("const", "var"):
+                        stack.extend(t[1:])
+            xs = sorted(G.nodes[a][1] for a in used if G.nodes[a][0] == "var")
+            out = ["    const int b = blockIdx.x * blockDim.x + threadIdx.x;", "    if (b >= B) return;"]
+            out += ["    const double x%d = x[(size_t)b * %d + %d];" % (j, n, j) for j in xs]
+            out += ["    " + ln for ln in lines]
+            return out, nm
+
+        src = ["// generated by restartsqp_b200/nl_reader.py from %s.nl" % self.name,
+               'extern "C" __global__ void nlp_eval_fc(int B, const double* __restrict__ x, double* __restrict__ f, double* __restrict__ c) {']
+        out, nm = body([self.f_node] + self.c_nodes)
+        src += out + ["    f[b] = %s;" % nm[self.f_node]]
+        src += ["    c[(size_t)b * %d + %d] = %s;" % (m, i, nm[a]) for i, a in enumerate(self.c_nodes)] + ["}", ""]
+        src += ['extern "C" __global__ void nlp_eval_all(int B, const double* __restrict__ x, const double* __restrict__ lam,',
+                "                                        double* __restrict__ f, double* __restrict__ c, double* __restrict__ grad,",
+                "                                        double* __restrict__ jac, double* __restrict__ hess) {"]
+        out, nm = body([self.f_node] + self.c_nodes + self.grad_nodes + self.jac_nodes + hroots)
+        src += out + ["    f[b] = %s;" % nm[self.f_node]]
+        src += ["    c[(size_t)b * %d + %d] = %s;" % (m, i, nm[a]) for i, a in enumerate(self.c_nodes)]
+        src += ["    grad[(size_t)b * %d + %d] = %s;" % (n, i, nm[a]) for i, a in enumerate(self.grad_nodes)]
+        src += ["    jac[(size_t)b * %d + %d] = %s;" % (zJ, i, nm[a]) for i, a in enumerate(self.jac_nodes)]
         for e, terms in enumerate(self._hess_terms):
             parts = [nm[d2] if k == 0 else "lam[(size_t)b * %d + %d] * %s" % (m, k - 1, nm[d2]) for k, d2 in terms]
-            out.append("    hess[(size_t)b * %d + %d] = %s;" % (zH, e, " + ".join(parts)))
-        out.append("}")
-        return "\n".join(out)
+            src.append("    hess[(size_t)b * %d + %d] = %s;" % (zH, e, " + ".join(parts)))
+        src.append("}")
+        return "\n".join(src)
 
     # ---- SQPTNLP interface (src/SQPTNLP.cpp)
     def Get_nlp_info(self):
@@ -559,3 +582,78 @@ class AmplNLP:
     def Eval_Hessian(self, x, lam):
         with np.errstate(all="ignore"):
             return self._h(self._x(x), np.ascontiguousarray(np.atleast_2d(lam), dtype=np.float64))
+
+
+class DeviceNLP:
+    """AmplNLP whose evaluations run on the GPU: the generated CUDA source is compiled with NVRTC through the C ABI
+    (sqpb200_nlp_compile / _load / _eval).  Same SQPTNLP-shaped interface plus the fused calls the batched driver prefers
+    (Eval_f_c for trial points, Eval_all for accepted points).  There is no CPU fallback: constructing it without a CUDA
+    device raises."""
+
+    MAX_NODES = 8000  # NVRTC time grows faster than linearly with the length of the straight-line kernel (hs105: 20 k nodes, 47 s)
+
+    def __init__(self, path, device=0, max_nodes=None):
+        import ctypes as C
+        from . import _capi as capi
+        self.host = path if isinstance(path, AmplNLP) else AmplNLP(path)
+        h = self.host
+        limit = self.MAX_NODES if max_nodes is None else max_nodes
+        if len(h.model.G.nodes) > limit:
+            raise ValueError("%s: expression DAG of %d nodes exceeds the device-evaluator limit of %d (NVRTC compile time)"
+                             % (h.name, len(h.model.G.nodes), limit))
+        self.n, self.m, self.name = h.n, h.m, h.name
+        self.J_row1, self.J_col1, self.H_row1, self.H_col1 = h.J_row1, h.J_col1, h.H_row1, h.H_col1
+        self.zJ, self.zH = len(h.J_row1), len(h.H_row1)
+        self._C, self._capi, self.L = C, capi, capi.lib()
+        self.h = C.c_void_p()
+        log = C.create_string_buffer(4096)
+        rc = self.L.sqpb200_nlp_compile(h.cuda_source().encode(), self.n, self.m, self.zJ, self.zH, log, 4096, C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError("sqpb200_nlp_compile(%s) failed (%d): %s" % (self.name, rc, self.L.sqpb200_nlp_last_error().decode()))
+        rc = self.L.sqpb200_nlp_load(self.h, device)
+        if rc != 0:
+            raise capi.SqpB200Error("sqpb200_nlp_load failed (%d): %s" % (rc, self.L.sqpb200_nlp_last_error().decode()))
+
+    def close(self):
+        if self.h:
+            self.L.sqpb200_nlp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def Get_nlp_info(self): return self.host.Get_nlp_info()
+    def Get_bounds_info(self): return self.host.Get_bounds_info()
+    def Get_starting_point(self): return self.host.Get_starting_point()
+    def launch_count(self): return int(self.L.sqpb200_nlp_launch_count(self.h))
+
+    def _eval(self, which, x, lam=None):
+        C = self._C
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B = x.shape[0]
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        f, c = np.empty(B), np.empty((B, self.m))
+        g = jv = hv = None
+        if which == 1:
+            lam = np.ascontiguousarray(np.atleast_2d(lam), dtype=np.float64).reshape(B, self.m)
+            g, jv, hv = np.empty((B, self.n)), np.empty((B, self.zJ)), np.empty((B, self.zH))
+        rc = self.L.sqpb200_nlp_eval(self.h, which, B, p(x), p(lam), p(f), p(c), p(g), p(jv), p(hv), self._capi.LOC_HOST, None)
+        if rc != 0:
+            raise self._capi.SqpB200Error("sqpb200_nlp_eval failed (%d): %s" % (rc, self.L.sqpb200_nlp_last_error().decode()))
+        return f, c, g, jv, hv
+
+    def Eval_f_c(self, x):
+        f, c, _, _, _ = self._eval(0, x)
+        return f, c
+
+    def Eval_all(self, x, lam):
+        return self._eval(1, x, lam)
+
+    def Eval_f(self, x): return self._eval(0, x)[0]
+    def Eval_constraints(self, x): return self._eval(0, x)[1]
+    def Eval_gradient(self, x): return self._eval(1, x, np.zeros((np.atleast_2d(x).shape[0], self.m)))[2]
+    def Eval_Jacobian(self, x): return self._eval(1, x, np.zeros((np.atleast_2d(x).shape[0], self.m)))[3]
+    def Eval_Hessian(self, x, lam): return self._eval(1, x, lam)[4]

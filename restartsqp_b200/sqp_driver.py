@@ -138,11 +138,14 @@ class BatchedSQP:
         self.x_k_ = np.minimum(np.maximum(x0, self.x_l_), self.x_u_)  # shift_starting_point, src/SQPTNLP.cpp:140-153
         self.multiplier_cons_ = np.tile(np.asarray(lam_start, dtype=np.float64), (B, 1)).reshape(B, m)
         self.multiplier_vars_ = np.zeros((B, n))
-        self.obj_value_ = nlp.Eval_f(self.x_k_)
-        self.grad_f_ = nlp.Eval_gradient(self.x_k_)
-        self.c_k_ = nlp.Eval_constraints(self.x_k_)
-        self.hess_val_ = nlp.Eval_Hessian(self.x_k_, -self.multiplier_cons_)
-        self.jac_val_ = nlp.Eval_Jacobian(self.x_k_)
+        if hasattr(nlp, "Eval_all"):  # fused device evaluation (nl_reader.DeviceNLP): one launch for everything
+            self.obj_value_, self.c_k_, self.grad_f_, self.jac_val_, self.hess_val_ = nlp.Eval_all(self.x_k_, -self.multiplier_cons_)
+        else:
+            self.obj_value_ = nlp.Eval_f(self.x_k_)
+            self.grad_f_ = nlp.Eval_gradient(self.x_k_)
+            self.c_k_ = nlp.Eval_constraints(self.x_k_)
+            self.hess_val_ = nlp.Eval_Hessian(self.x_k_, -self.multiplier_cons_)
+            self.jac_val_ = nlp.Eval_Jacobian(self.x_k_)
         self.cons_type_ = classify_single_constraint(self.c_l_, self.c_u_)           # :467
         self.bound_cons_type_ = classify_single_constraint(self.x_l_, self.x_u_)
         self.infea_measure_ = self.cal_infea(self.c_k_)                              # :472
@@ -246,8 +249,12 @@ class BatchedSQP:
     # ---- src/Algorithm.cpp:414-429
     def get_trial_point_info(self, mask):
         self.x_trial_[mask] = (self.x_k_ + self.p_k_)[mask]
-        self.obj_value_trial_[mask] = self.nlp_.Eval_f(self.x_trial_)[mask]
-        self.c_trial_[mask] = self.nlp_.Eval_constraints(self.x_trial_)[mask]
+        if hasattr(self.nlp_, "Eval_f_c"):
+            f_t, c_t = self.nlp_.Eval_f_c(self.x_trial_)
+        else:
+            f_t, c_t = self.nlp_.Eval_f(self.x_trial_), self.nlp_.Eval_constraints(self.x_trial_)
+        self.obj_value_trial_[mask] = f_t[mask]
+        self.c_trial_[mask] = c_t[mask]
         self.infea_measure_trial_[mask] = self.cal_infea(self.c_trial_)[mask]
 
     def get_multipliers(self, mask):  # :618-630 (qpOASES-order backend)
@@ -334,9 +341,14 @@ class BatchedSQP:
             self.x_k_[acc] = self.x_trial_[acc]
             self.c_k_[acc] = self.c_trial_[acc]
             self.get_multipliers(acc)
-            self.grad_f_[acc] = self.nlp_.Eval_gradient(self.x_k_)[acc]
-            self.jac_val_[acc] = self.nlp_.Eval_Jacobian(self.x_k_)[acc]
-            self.hess_val_[acc] = self.nlp_.Eval_Hessian(self.x_k_, -self.multiplier_cons_)[acc]
+            if hasattr(self.nlp_, "Eval_all"):
+                _, _, g_n, j_n, h_n = self.nlp_.Eval_all(self.x_k_, -self.multiplier_cons_)
+            else:
+                g_n, j_n = self.nlp_.Eval_gradient(self.x_k_), self.nlp_.Eval_Jacobian(self.x_k_)
+                h_n = self.nlp_.Eval_Hessian(self.x_k_, -self.multiplier_cons_)
+            self.grad_f_[acc] = g_n[acc]
+            self.jac_val_[acc] = j_n[acc]
+            self.hess_val_[acc] = h_n[acc]
             self.Update_A[acc] = self.Update_H[acc] = self.Update_bounds[acc] = self.Update_g[acc] = True
         return acc
 

@@ -90,3 +90,40 @@ def test_failed_qp_is_dumped_and_replays(gpu_lib, tmp_path):
     o = H.oracle_solve(orc, p, Acsc=(q["A_colptr"], q["A_rowidx"], np.array(q["A_val"])), Hcsc=(q["H_colptr"], q["H_rowidx"], np.array(q["H_val"])))
     assert (s.get_status() == o["status"]).all() and np.abs(s.get_optimal_solution()[1] - o["x"]).max() <= 1e-8 * max(1.0, np.abs(o["x"]).max())
     s.close()
+
+
+@pytest.mark.parametrize("name", ["hs071", "hs043", "hs099", "hs100", "hs113", "hs085"])
+def test_device_nlp_evaluator_matches_host_evaluator(gpu_lib, name):
+    """The NVRTC-compiled evaluator (one thread per instance) against the numpy evaluator generated from the same DAG:
+    + - * / are identical (--fmad=false); exp/log/sin/cos/pow differ by libm vs CUDA rounding only."""
+    import os
+    from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
+    from test_hs_suite import HS_DIR, perturbed_starts
+    host = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+    dev = DeviceNLP(host)
+    B = 257
+    X = perturbed_starts(host, B, 3)
+    lam = np.random.default_rng(5).standard_normal((B, host.m))
+    f, c, g, J, Hh = dev.Eval_all(X, lam)
+    f2, c2 = dev.Eval_f_c(X)
+    rel = lambda a, b: float(np.abs(a - b).max() / max(1.0, np.abs(b).max())) if a.size else 0.0
+    assert rel(f, host.Eval_f(X)) < 1e-12 and rel(c, host.Eval_constraints(X)) < 1e-12
+    assert rel(g, host.Eval_gradient(X)) < 1e-12 and rel(J, host.Eval_Jacobian(X)) < 1e-12
+    assert rel(Hh, host.Eval_Hessian(X, lam)) < 1e-11
+    assert np.array_equal(f, f2) and np.array_equal(c, c2)
+    assert dev.launch_count() == 2
+    dev.close()
+
+
+def test_sqp_with_device_evaluator(gpu_lib):
+    import os
+    from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
+    from test_hs_suite import HS_DIR, perturbed_starts
+    host = AmplNLP(os.path.join(HS_DIR, "hs071.nl"))
+    dev = DeviceNLP(host)
+    X = perturbed_starts(host, 512, 0)
+    res_d = BatchedSQP(dev, x0=X).Optimize()
+    res_h = BatchedSQP(host, x0=X).Optimize()
+    assert (res_d.exitflag == int(r.Exitflag.OPTIMAL)).all() and (res_h.exitflag == res_d.exitflag).all()
+    assert np.abs(res_d.x - res_h.x).max() < 1e-6 and np.abs(res_d.x - X_STAR).max() < 1e-4
+    dev.close()

@@ -88,3 +88,19 @@ def test_cuda_source_is_emitted_for_every_output():
     p = AmplNLP(os.path.join(HS_DIR, "hs071.nl"))
     src = p.cuda_source()
     assert "nlp_eval" in src and src.count("hess[") == 10 and src.count("jac[") == 8 and src.count("grad[") == 4
+
+
+def test_generated_cuda_compiles_with_nvrtc_for_sm100a():
+    """sqpb200_nlp_compile needs no GPU: NVRTC cross-compiles the generated kernels (loading/launching them does)."""
+    import ctypes as C
+    from restartsqp_b200 import _capi as capi
+    L = capi.lib()
+    for name in ("hs071", "hs099"):
+        p = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+        h, log = C.c_void_p(), C.create_string_buffer(4096)
+        rc = L.sqpb200_nlp_compile(p.cuda_source().encode(), p.n, p.m, len(p.J_row1), len(p.H_row1), log, 4096, C.byref(h))
+        assert rc == 0, L.sqpb200_nlp_last_error()
+        assert L.sqpb200_nlp_cubin_size(h) > 1000
+        L.sqpb200_nlp_destroy(h)
+    h = C.c_void_p()
+    assert L.sqpb200_nlp_compile(b"this is not CUDA", 1, 0, 0, 0, None, 0, C.byref(h)) != 0

@@ -310,8 +310,20 @@ def run_gpu(args, rank, world, local_rank):
             flops_step = fl * B
         except Exception:
             pass
+        # the dominant single launch: hs116, the largest dumped QP (nV=69, nC=28); its DRAM traffic per launch comes from the
+        # committed ncu --set full capture of exactly this launch shape (profiles/r1_qp_solve_hs116.md)
+        dom = [gr for gr in groups if gr["q"]["name"] == "QORE_hs116"]
+        dom_launch = None
+        if dom:
+            dom_ms = dom[0]["s"].last_solve_ms()
+            dom_bytes = algorithmic_bytes(dom[0]["q"]) * B
+            dom_launch = {"launch": "QORE_hs116 x %d" % B, "ms": dom_ms, "algorithmic_bytes": dom_bytes,
+                          "achieved_gbs": dom_bytes / (dom_ms * 1e-3) / 1e9,
+                          "traffic_bytes_ncu": (13345536 if B == 4096 else None),
+                          "traffic_source": "profiles/r1_qp_solve_hs116.md (dram__bytes_read.sum + dram__bytes_write.sum, B=4096)"}
         roofline = {"kernel": "qp_solve_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / hbm_peak, "traffic": (13345536 if (dom and B == 4096) else None), "peak_source": peak_src,
+                    "dominant_launch": dom_launch,
                     "kernel_ms_per_step": 1e3 * kernel_s_per_step, "kernel_share_of_step": kernel_s_per_step / (ms_serial * 1e-3 / args.steps),
                     "serial_ms_per_step": ms_serial / args.steps,
                     "algorithmic_bytes_per_step": bytes_step,
@@ -338,10 +350,63 @@ def run_gpu(args, rank, world, local_rank):
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d QPs (passes over %d replicas of each of the 21 dumped QPs) in %.1f s" % (n, sample_B, t)},
         }
+        if args.extras:
+            out["extras"] = run_extras(local_rank)
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_extras(device):
+    """Untimed-by-the-driver side measurements on rank 0 (outside the timed region of the headline metric): the other
+    BASELINE.json configurations that fit one GPU, each through the public API, each with its own CPU-oracle figure."""
+    import restartsqp_b200 as r
+    from restartsqp_b200 import capi
+    from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
+    from restartsqp_b200.sqp_driver import BatchedSQP
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+    ex = {}
+    try:  # configs[0]/[2]: full SQP solves per second, HS071 x 10^4 perturbed starts, device NLP evaluation + CUDA QP backend
+        host = AmplNLP(os.path.join(ROOT, "tests", "golden", "hs_nl", "hs071.nl"))
+        dev = DeviceNLP(host, device=device)
+        Bs = 10000
+        x0, _ = host.Get_starting_point()
+        xl, xu, _, _ = host.Get_bounds_info()
+        rng = np.random.default_rng(71000)
+        X = np.clip(x0 * (1 + 0.1 * rng.standard_normal((Bs, host.n))) + 0.1 * rng.standard_normal((Bs, host.n)), xl, xu)
+        BatchedSQP(dev, x0=X[:256], device=device).Optimize()  # warm-up
+        t0 = time.perf_counter()
+        res = BatchedSQP(dev, x0=X, device=device).Optimize()
+        dt = time.perf_counter() - t0
+        ex["sqp_hs071"] = {"metric": "SQP solves/sec", "value": Bs / dt, "unit": "solves/s", "instances": Bs,
+                           "optimal": int((res.exitflag == 0).sum()), "sqp_iters_mean": float(res.iters.mean()),
+                           "qp_iters_mean": float(res.qp_iter.mean()), "seconds": dt,
+                           "note": "host-driven batched outer loop (numpy), NLP evaluation and every QP/LP on the GPU; wall clock"}
+        dev.close()
+    except Exception as e:  # the extras never take the headline down
+        ex["sqp_hs071"] = {"error": repr(e)[:200]}
+    try:  # configs[3]: synthetic sparse QP n=256, m=128 (nV=512), batch 64, one QP per CTA
+        d = H.synthetic_large_qp(256, batch=64)
+        s = r.CudaQPInterface(nV=d["nV"], nC=d["nC"], qptype=r.QPType.QP, batch=64, device=device, keep_state=False)
+        s.set_csc(capi.MAT_A, *d["Ac"]); s.set_csc(capi.MAT_H, *d["Hc"])
+        s.set_g(d["g"]); s.set_lb(d["lb"]); s.set_ub(d["ub"]); s.set_lbA(d["lbA"]); s.set_ubA(d["ubA"])
+        for _ in range(2):
+            s._solve(r.QPType.QP, None, None, 0)
+            ms = s.last_solve_ms()
+        st, it = s.get_status(), s.get_iterations()
+        from oracle import oracle_py as orc
+        t0 = time.perf_counter()
+        rr = orc.solve_batch(d["nV"], d["nC"], d["Ac"], d["Hc"], d["g"][:16], d["lb"][:16], d["ub"][:16], d["lbA"][:16], d["ubA"][:16])
+        tc = time.perf_counter() - t0
+        ex["large_qp_n256"] = {"metric": "QP subproblems/sec", "value": 64 / (ms * 1e-3), "unit": "QPs/s", "batch": 64, "nV": d["nV"], "nC": d["nC"],
+                               "ms": ms, "optimal": int((st == 20).sum()), "iters_mean": float(it.mean()), "config": s.solve_config(),
+                               "cpu_baseline": {"value": 16 / tc, "unit": "QPs/s", "cores": rr["threads"], "kind": "port", "sample": "16 instances in %.1f s" % tc}}
+        s.close()
+    except Exception as e:
+        ex["large_qp_n256"] = {"error": repr(e)[:200]}
+    return ex
 
 
 def main():
@@ -352,6 +417,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--replicas", type=int, default=4096, help="replicas per dumped QP (B of SURVEY.md 8d config 2)")
     ap.add_argument("--team", type=int, default=0, help="threads per QP (0 = auto)")
+    ap.add_argument("--extras", type=int, default=1, help="1: also report SQP solves/s (HS071 x 1e4) and the config-4 large-QP rate on rank 0")
     ap.add_argument("--streams", type=int, default=1, help="1: one CUDA stream per dumped QP (overlapping launches), 0: default stream")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -376,10 +376,14 @@ def run_extras(device):
         xl, xu, _, _ = host.Get_bounds_info()
         rng = np.random.default_rng(71000)
         X = np.clip(x0 * (1 + 0.1 * rng.standard_normal((Bs, host.n))) + 0.1 * rng.standard_normal((Bs, host.n)), xl, xu)
-        BatchedSQP(dev, x0=X[:256], device=device).Optimize()  # warm-up
-        t0 = time.perf_counter()
-        res = BatchedSQP(dev, x0=X, device=device).Optimize()
+        warm = BatchedSQP(dev, x0=X[:256], device=device)
+        warm.Optimize()
+        t0 = time.perf_counter()  # initialization + Optimize, like the reference's own timing (src/Algorithm.cpp:57)
+        alg = BatchedSQP(dev, x0=X, device=device)
+        res = alg.Optimize()
         dt = time.perf_counter() - t0
+        for a_ in (warm, alg):  # handle teardown (cudaFree) is outside the timed region
+            a_.myQP_.solverInterface_.close(); a_.myLP_.solverInterface_.close()
         ex["sqp_hs071"] = {"metric": "SQP solves/sec", "value": Bs / dt, "unit": "solves/s", "instances": Bs,
                            "optimal": int((res.exitflag == 0).sum()), "sqp_iters_mean": float(res.iters.mean()),
                            "qp_iters_mean": float(res.qp_iter.mean()), "seconds": dt,

@@ -258,6 +258,16 @@ def run_gpu(args, rank, world, local_rank):
         launches = sum(gr["s"].launch_count() for gr in groups) - launches0
         return float(t.item()), launches, kms
 
+    # Launch order: longest solve first.  The step is bounded by its longest kernel (hs107: a few replicas need 400
+    # working-set changes), so that kernel must start first and the short ones fill the SMs its tail leaves idle.  The order
+    # comes from one untimed calibration pass on the default stream.
+    step_resident()
+    torch.cuda.synchronize()
+    cal = [gr["s"].last_solve_ms() for gr in groups]
+    order = sorted(range(len(groups)), key=lambda i: -cal[i])
+    groups[:] = [groups[i] for i in order]
+    if streams:
+        streams = streams[: len(groups)]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

@@ -408,14 +408,18 @@ static int set_values(sqpb200_handle h, int which, const double* vals, int loc, 
     int z_in = csc_order ? z_out : (isA ? h->zJ : h->zHt);
     if (z_out == 0 || z_in == 0) return 0;
     size_t bytes = (size_t)(broadcast ? 1 : h->batch) * z_in * 8;
-    if (loc == SQPB200_LOC_HOST && ensure_stage(h, bytes)) return SQPB200_ERR_CUDA;
-    const void* din;
-    if (to_device(h, vals, bytes, loc, 0, &din)) return SQPB200_ERR_CUDA;
     double* dout = isA ? h->dAval : h->dHval;
     long long total = (long long)h->batch * z_out;
     if (csc_order && !broadcast) {
-        CK(cudaMemcpyAsync(dout, din, bytes, cudaMemcpyDeviceToDevice, h->stream));
-    } else if (csc_order) {
+        // one DMA copy straight into place (no staging, no SM-side copy: it must not queue behind resident solve CTAs)
+        CK(cudaMemcpyAsync(dout, vals, bytes, loc == SQPB200_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+        if (h->first_solved) { if (isA) h->upd_A = true; else h->upd_H = true; }
+        return 0;
+    }
+    if (loc == SQPB200_LOC_HOST && ensure_stage(h, bytes)) return SQPB200_ERR_CUDA;
+    const void* din;
+    if (to_device(h, vals, bytes, loc, 0, &din)) return SQPB200_ERR_CUDA;
+    if (csc_order) {
         broadcast_rows_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(total, z_out, 0, z_out, (const double*)din, dout);
         h->launches++;
     } else {
@@ -465,8 +469,9 @@ int sqpb200_set_vectors(sqpb200_handle h, int which, const double* vals, int off
     if (!d || offset < 0 || count < 0 || offset + count > len) return SQPB200_ERR_INVALID;
     if (count == 0) return 0;
     if (!broadcast) {
-        CK(cudaMemcpy2DAsync(d + offset, (size_t)len * 8, vals, (size_t)count * 8, (size_t)count * 8, h->batch,
-                             loc == SQPB200_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+        const cudaMemcpyKind kind = loc == SQPB200_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+        if (offset == 0 && count == len) CK(cudaMemcpyAsync(d, vals, (size_t)h->batch * len * 8, kind, h->stream));  // whole vectors: one linear DMA copy
+        else CK(cudaMemcpy2DAsync(d + offset, (size_t)len * 8, vals, (size_t)count * 8, (size_t)count * 8, h->batch, kind, h->stream));
     } else {
         if (loc == SQPB200_LOC_HOST && ensure_stage(h, (size_t)count * 8)) return SQPB200_ERR_CUDA;
         const void* din;

@@ -288,16 +288,44 @@ struct QPT {
             return 0;
         }
         if constexpr (TEAM > 32) return recompute_R_blocked();
-        const double *Q = V_(Q), *t2 = V_(t2);
-        const short* FR = FR_;
-        _Pragma("unroll 1") for (int b = 0; b < nZ; b++) {
-            proj_column(b);
-            _Pragma("unroll 1") for (int a_ = lane; a_ <= b; a_ += TEAM) {
-                double s = 0.0;
-                DOT_UNROLL for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
-                R_(a_, b) = s;
+        // M = Z'(HZ), several null-space columns at a time so that all 32 lanes have work (one lane per entry of W = HZ, then
+        // one lane per entry of M) instead of one column per pass with nV- and (b+1)-wide loops.  W lives in the seven work
+        // vectors t1,t2,t3,w,a,yv,zv, which are contiguous and unused here.  Per entry the same terms in the same order as the
+        // column-by-column form: W[p][b] = sum over the entries of H's column FR[p], M[a][b] = sum over p ascending.
+        {
+            QP_PAT
+            const double *Q = V_(Q), *Hv = V_(Hv);
+            double* Wc = V_(t1);
+            const short *FR = FR_, *posFR = posFR_;
+            const pidx *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
+            const bool has_H = sA.has_H != 0;
+            int CH = (7 * (nV + nC)) / nFR;
+            if (CH > nZ) CH = nZ;
+            _Pragma("unroll 1") for (int b0 = 0; b0 < nZ; b0 += CH) {
+                const int cw = (nZ - b0 < CH) ? nZ - b0 : CH;
+                _Pragma("unroll 1") for (int e = lane; e < nFR * cw; e += TEAM) {
+                    const int p = e / cw, bb = e - p * cw;
+                    double s = 0.0;
+                    if (has_H) {
+                        const int c = FR[p], e1 = Hp[c + 1];
+                        _Pragma("unroll 1") for (int h = Hp[c]; h < e1; h++) {
+                            const int pr = posFR[Hi[h]];
+                            s += Hv[h] * ((pr >= 0) ? Q[pr * ld + b0 + bb] : 0.0);
+                        }
+                    }
+                    Wc[e] = s;
+                }
+                SYNC();
+                _Pragma("unroll 1") for (int e = lane; e < (b0 + cw) * cw; e += TEAM) {
+                    const int a_ = e / cw, bb = e - a_ * cw;
+                    if (a_ <= b0 + bb) {
+                        double s = 0.0;
+                        _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * Wc[p * cw + bb];
+                        R_(a_, b0 + bb) = s;
+                    }
+                }
+                SYNC();
             }
-            SYNC();
         }
         // row-wise Cholesky: R'R = M, same per-element summation order as the column version
         _Pragma("unroll 1") for (int i = 0; i < nZ; i++) {

@@ -388,15 +388,20 @@ def run_extras(device):
         X = np.clip(x0 * (1 + 0.1 * rng.standard_normal((Bs, host.n))) + 0.1 * rng.standard_normal((Bs, host.n)), xl, xu)
         warm = BatchedSQP(dev, x0=X[:256], device=device)
         warm.Optimize()
-        t0 = time.perf_counter()  # initialization + Optimize, like the reference's own timing (src/Algorithm.cpp:57)
-        alg = BatchedSQP(dev, x0=X, device=device)
-        res = alg.Optimize()
-        dt = time.perf_counter() - t0
-        for a_ in (warm, alg):  # handle teardown (cudaFree) is outside the timed region
-            a_.myQP_.solverInterface_.close(); a_.myLP_.solverInterface_.close()
+        runs = []
+        for _ in range(3):  # initialization + Optimize, like the reference's own timing (src/Algorithm.cpp:57)
+            t0 = time.perf_counter()
+            alg = BatchedSQP(dev, x0=X, device=device)
+            t1 = time.perf_counter()
+            res = alg.Optimize()
+            runs.append((time.perf_counter() - t0, t1 - t0))
+            alg.myQP_.solverInterface_.close(); alg.myLP_.solverInterface_.close()  # teardown (cudaFree) is outside the timed region
+        warm.myQP_.solverInterface_.close(); warm.myLP_.solverInterface_.close()
+        dt = float(np.median([r_[0] for r_ in runs]))
+        t0, t1 = 0.0, float(np.median([r_[1] for r_ in runs]))
         ex["sqp_hs071"] = {"metric": "SQP solves/sec", "value": Bs / dt, "unit": "solves/s", "instances": Bs,
                            "optimal": int((res.exitflag == 0).sum()), "sqp_iters_mean": float(res.iters.mean()),
-                           "qp_iters_mean": float(res.qp_iter.mean()), "seconds": dt,
+                           "qp_iters_mean": float(res.qp_iter.mean()), "seconds": dt, "seconds_initialization": t1 - t0, "seconds_all_runs": [r_[0] for r_ in runs],
                            "note": "host-driven batched outer loop (numpy), NLP evaluation and every QP/LP on the GPU; wall clock"}
         dev.close()
     except Exception as e:  # the extras never take the headline down

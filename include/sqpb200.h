@@ -205,6 +205,53 @@ int sqpb200_nlp_destroy(sqpb200_nlp h);
 long long sqpb200_nlp_launch_count(sqpb200_nlp h);
 const char* sqpb200_nlp_last_error(void);
 
+/* ---- device-resident outer loop: the per-instance steps of Algorithm::Optimize (src/Algorithm.cpp:55-168)
+ * as phases of one kernel, one thread per instance, over SoA state that never leaves the device.  The caller owns every
+ * array (device memory) and sequences phases, QP/LP solves (sqpb200_solve_device_mask) and NLP evaluations (sqpb200_nlp_eval
+ * with device pointers). */
+#define SQPB200_PH_FLAGS 0
+#define SQPB200_PH_AFTER_QP 1
+#define SQPB200_PH_LP_AFTER 2
+#define SQPB200_PH_PEN_CHECK 3
+#define SQPB200_PH_PEN_AFTER 4
+#define SQPB200_PH_PEN_FINAL 5
+#define SQPB200_PH_TRIAL 6
+#define SQPB200_PH_RATIO 7
+#define SQPB200_PH_FINISH 8
+#define SQPB200_PH_FINAL 9
+typedef struct {
+    int B, n, m, zJ, zH;
+    /* Options (src/Options.cpp:19-57) */
+    int iter_max, penalty_update, penalty_iter_max, clear_flags;
+    double eta_c, eta_s, eta_e, gamma_c, gamma_e, delta_min, delta_max, tol, penalty_update_tol, rho_max, increase_parm,
+        eps1_change_parm, eps2, opt_prim_fea_tol, opt_dual_fea_tol, opt_compl_tol, opt_stat_tol;
+    /* model: Jacobian triplet pattern (1-based), bounds and constraint classes per instance */
+    const int *J_row1, *J_col1;
+    const double *x_l, *x_u, *c_l, *c_u;      /* [B][n], [B][m] */
+    const int *bound_type, *cons_type;        /* ConstraintType, include/sqphot/Types.hpp:75-81 */
+    /* iterate and algorithm state, [B][...] */
+    double *x_k, *c_k, *f_k, *grad, *jac, *hess, *lam_c, *lam_x, *neg_lam;
+    double *delta, *rho, *eps1, *infea, *p_k, *x_trial, *c_trial, *f_trial, *infea_trial, *infea_model, *infea_model_tmp,
+        *rho_trial, *infea_infty, *actual_red, *pred_red, *kkt_err;
+    double *g_new, *j_new, *h_new;            /* derivatives at the trial point of accepted steps */
+    double* scratch;                          /* [B][n] */
+    int *exitflag, *iter, *pen_trial;
+    long long* qp_iter;
+    unsigned char *active, *need, *go, *acc, *upd, *feasible_lp;
+    /* result buffers of the QP and LP handles (sqpb200_device_buffers) */
+    const double *qp_x, *qp_y, *qp_obj, *qp_kkt, *lp_x;
+    const int *qp_status, *qp_iters, *lp_status, *lp_iters;
+    int* counters;                            /* [8] device */
+} sqpb200_sqp_state;
+/* counters_host (may be NULL): the 8 device counters after the phase ([0] active instances, [1] OR of the raised Update_*
+ * bits 1=A 2=H 4=bounds 8=delta 16=penalty 32=g, [2] instances needing the penalty update, [3] instances continuing the
+ * penalty loop, [4] accepted steps); reading them synchronises the stream. */
+int sqpb200_sqp_phase(const sqpb200_sqp_state* st, int phase, int* counters_host, void* stream);
+/* sqpb200_solve with the instance mask in device memory */
+int sqpb200_solve_device_mask(sqpb200_handle h, int mode, int maxiter, const unsigned char* device_mask);
+/* device pointers of the handle's result arrays: out[0..5] = x, y, obj, status, iters, kkt */
+int sqpb200_device_buffers(sqpb200_handle h, void** out);
+
 #ifdef __cplusplus
 }
 #endif

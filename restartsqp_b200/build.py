@@ -31,7 +31,8 @@ def _nvcc():
 
 def _units():
     units = [(os.path.join(CSRC, "capi.cu"), os.path.join(OBJDIR, "capi.o"), []),
-             (os.path.join(CSRC, "nlp_eval.cu"), os.path.join(OBJDIR, "nlp_eval.o"), [])]
+             (os.path.join(CSRC, "nlp_eval.cu"), os.path.join(OBJDIR, "nlp_eval.o"), []),
+             (os.path.join(CSRC, "sqp_outer.cu"), os.path.join(OBJDIR, "sqp_outer.o"), [])]
     for team, cta in TEAMS:
         # multi-warp teams are compiled fully inlined (see the QP_INLINE_ALL note in qp_kernel.cuh)
         units.append((os.path.join(CSRC, "qp_solve_inst.cu"), os.path.join(OBJDIR, "qp_solve_%d_%d.o" % (team, cta)),

@@ -655,7 +655,19 @@ static cudaError_t launch_cfg(const SolveCfg& cfg, const QPKernelArgs& a, cudaSt
     }
 }
 
+static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask, bool mask_on_device);
 int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask) {
+    return solve_impl(h, mode_qp, maxiter, active_mask, false);
+}
+int sqpb200_solve_device_mask(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* device_mask) {
+    return solve_impl(h, mode_qp, maxiter, device_mask, true);
+}
+int sqpb200_device_buffers(sqpb200_handle h, void** out) {
+    if (!h || !out) return SQPB200_ERR_INVALID;
+    out[0] = h->dx; out[1] = h->dy; out[2] = h->dobj; out[3] = h->dstatus; out[4] = h->diters; out[5] = h->dkkt;
+    return 0;
+}
+static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask, bool mask_on_device) {
     if (!h) return SQPB200_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     if (!h->A_set) { h->err = "set_structure_A has not been called"; return SQPB200_ERR_STATE; }
@@ -691,7 +703,8 @@ int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned cha
     a.Hp = h->dHp; a.Hi = h->dHi;
     a.Aval = h->dAval; a.Hval = h->dHval;
     a.gN = h->dg; a.lbN = h->dlb; a.ubN = h->dub; a.lbAN = h->dlbA; a.ubAN = h->dubA;
-    if (active_mask) {
+    if (active_mask && mask_on_device) a.mask = active_mask;
+    else if (active_mask) {
         CK(cudaMemcpyAsync(h->dmask, active_mask, h->batch, cudaMemcpyHostToDevice, h->stream));
         a.mask = h->dmask;
     }

@@ -1,0 +1,268 @@
+// sqp_outer.cu -- the per-instance steps of the Sl1QP outer loop (src/Algorithm.cpp) as device kernels, one thread per NLP
+// instance: the iterate, the trust-region radius, the penalty parameter and all flags stay in HBM in SoA
+// layout between the QP/LP solves and the NLP evaluations, which also run on the device; the host only sequences the
+// launches and reads back a handful of counters per iteration (how many instances are still active, which Update_* flags are
+// raised, how many need the penalty update).
+//
+// Every phase restates the corresponding reference routine with its sums in the reference's index order:
+//   PH_FLAGS      loop condition of Algorithm::Optimize (:59-61) + the flag bookkeeping of setupQP (:645-697)
+//   PH_AFTER_QP   QP status / KKT acceptance (QPhandler::solveQP :470-499, Algorithm :64-72), get_search_direction (:609),
+//                 infea_measure_model (:592-594) and the entry test of update_penalty_parameter (:886-900)
+//   PH_LP_AFTER   results of the feasibility LP (:900-912)
+//   PH_PEN_CHECK  loop conditions of the two penalty while-loops (:914-972), rho_trial *= increase_parm
+//   PH_PEN_AFTER  after a QP re-solve with rho_trial
+//   PH_PEN_FINAL  accept / reject rho_trial (:975-1010)
+//   PH_TRIAL      x_trial = x_k + p_k (:414-429)
+//   PH_RATIO      cal_infea of the trial point (:577-602), ratio_test (:722-801), get_multipliers for accepted steps (:618-630)
+//   PH_FINISH     new derivatives for accepted steps, iter++, check_optimality (:170-411), update_radius (:820-849)
+//   PH_FINAL      EXCEED_MAX_ITER (:160-168)
+#include "../../include/sqpb200.h"
+
+#include <cuda_runtime.h>
+
+namespace {
+
+enum { EX_OPTIMAL = 0, EX_EXCEED_MAX_ITER = 2, EX_TRUST_REGION_TOO_SMALL = 4, EX_UNKNOWN = -99 };
+enum { CT_BOUNDED = 5, CT_EQUAL = -5, CT_BOUNDED_ABOVE = 9, CT_BOUNDED_BELOW = 1, CT_UNBOUNDED = 0 };
+enum { UP_A = 1, UP_H = 2, UP_BOUNDS = 4, UP_DELTA = 8, UP_PENALTY = 16, UP_G = 32 };
+
+__device__ __forceinline__ double cal_infea(const sqpb200_sqp_state& S, const double* c, int b) {
+    double s = 0.0;
+    for (int i = 0; i < S.m; i++) {
+        const double ci = c[(size_t)b * S.m + i], cl = S.c_l[(size_t)b * S.m + i], cu = S.c_u[(size_t)b * S.m + i];
+        const double below = (ci < cl) ? cl - ci : 0.0;
+        const double above = (ci >= cl && ci > cu) ? ci - cu : 0.0;
+        s = s + below + above;
+    }
+    return s;
+}
+
+__device__ __forceinline__ void get_multipliers(const sqpb200_sqp_state& S, int b) {
+    const int nV = S.n + 2 * S.m;
+    const double* y = S.qp_y + (size_t)b * (nV + S.m);
+    for (int i = 0; i < S.m; i++) S.lam_c[(size_t)b * S.m + i] = y[nV + i];
+    for (int i = 0; i < S.n; i++) S.lam_x[(size_t)b * S.n + i] = y[i];
+}
+
+// Algorithm::check_optimality for instance b (multipliers already refreshed); writes KKT_error, may set OPTIMAL
+__device__ __forceinline__ void check_optimality(const sqpb200_sqp_state& S, int b, double* diff) {
+    const int n = S.n, m = S.m;
+    const double *mv = S.lam_x + (size_t)b * n, *mc = S.lam_c + (size_t)b * m;
+    const double primal = S.infea[b];
+    double dual = 0.0, compl_ = 0.0;
+    for (int i = 0; i < n; i++) {
+        const int t = S.bound_type[(size_t)b * n + i];
+        dual = dual + (t == CT_BOUNDED_ABOVE ? fmax(mv[i], 0.0) : 0.0) + (t == CT_BOUNDED_BELOW ? -fmin(mv[i], 0.0) : 0.0);
+    }
+    for (int i = 0; i < m; i++) {
+        const int t = S.cons_type[(size_t)b * m + i];
+        dual = dual + (t == CT_BOUNDED_ABOVE ? fmax(mc[i], 0.0) : 0.0) + (t == CT_BOUNDED_BELOW ? -fmin(mc[i], 0.0) : 0.0);
+    }
+    for (int i = 0; i < m; i++) {
+        const int t = S.cons_type[(size_t)b * m + i];
+        const double ck = S.c_k[(size_t)b * m + i];
+        compl_ = compl_ + (t == CT_BOUNDED_ABOVE ? fabs(mc[i] * (S.c_u[(size_t)b * m + i] - ck)) : 0.0)
+                        + (t == CT_BOUNDED_BELOW ? fabs(mc[i] * (ck - S.c_l[(size_t)b * m + i])) : 0.0)
+                        + (t == CT_UNBOUNDED ? fabs(mc[i]) : 0.0);
+    }
+    for (int i = 0; i < n; i++) {
+        const int t = S.bound_type[(size_t)b * n + i];
+        const double xk = S.x_k[(size_t)b * n + i];
+        compl_ = compl_ + (t == CT_BOUNDED_ABOVE ? fabs(mv[i] * (S.x_u[(size_t)b * n + i] - xk)) : 0.0)
+                        + (t == CT_BOUNDED_BELOW ? fabs(mv[i] * (xk - S.x_l[(size_t)b * n + i])) : 0.0)
+                        + (t == CT_UNBOUNDED ? fabs(mv[i]) : 0.0);
+    }
+    // stationarity: || J'y_c + y_b - grad f ||_1, triplet SpMTV in storage order (src/SpTripletMat.cpp:311-323)
+    for (int i = 0; i < n; i++) diff[i] = 0.0;
+    const double* jv = S.jac + (size_t)b * S.zJ;
+    for (int k = 0; k < S.zJ; k++) diff[S.J_col1[k] - 1] += jv[k] * mc[S.J_row1[k] - 1];
+    double stat = 0.0;
+    for (int i = 0; i < n; i++) {
+        const double d = diff[i] + mv[i] - S.grad[(size_t)b * n + i];
+        stat = stat + fabs(d);
+    }
+    S.kkt_err[b] = dual + primal + compl_ + stat;
+    if (primal < S.opt_prim_fea_tol && dual < S.opt_dual_fea_tol && compl_ < S.opt_compl_tol && stat < S.opt_stat_tol) S.exitflag[b] = EX_OPTIMAL;
+}
+
+__global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, int phase) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.B) return;
+    const int n = S.n, m = S.m, nV = n + 2 * m;
+    switch (phase) {
+    case SQPB200_PH_FLAGS: {
+        const bool a = S.iter[b] < S.iter_max && S.exitflag[b] == EX_UNKNOWN;
+        S.active[b] = a ? 1 : 0;
+        if (a) {
+            atomicAdd(&S.counters[0], 1);
+            if (S.upd[b]) atomicOr(&S.counters[1], (int)S.upd[b]);
+            if (S.clear_flags) S.upd[b] = 0;
+        }
+        break;
+    }
+    case SQPB200_PH_AFTER_QP: {
+        S.rho_trial[b] = S.rho[b];
+        if (!S.active[b]) { S.need[b] = 0; break; }
+        S.qp_iter[b] += S.qp_iters[b];
+        const int st = S.qp_status[b];
+        const bool ok = (S.qp_kkt[(size_t)b * 5 + 4] <= 1.0e-6) && st == SQPB200_QP_OPTIMAL;
+        if (!ok) {
+            S.exitflag[b] = (st == SQPB200_QP_OPTIMAL) ? SQPB200_QPERROR_INTERNAL_ERROR : st;
+            S.active[b] = 0; S.need[b] = 0;
+            break;
+        }
+        const double* x = S.qp_x + (size_t)b * nV;
+        for (int i = 0; i < n; i++) S.p_k[(size_t)b * n + i] = x[i];
+        unsigned char need = 0;
+        if (S.penalty_update) {
+            double s = 0.0;
+            for (int i = n; i < nV; i++) s = s + fabs(x[i]);
+            S.infea_model[b] = s;
+            need = s > S.penalty_update_tol;
+            if (need) { atomicAdd(&S.counters[2], 1); S.infea_model_tmp[b] = s; }
+        }
+        S.need[b] = need;
+        break;
+    }
+    case SQPB200_PH_LP_AFTER: {
+        if (!S.need[b]) break;
+        S.qp_iter[b] += S.lp_iters[b];
+        const int st = S.lp_status[b];
+        if (st != SQPB200_QP_OPTIMAL) { S.exitflag[b] = st; S.need[b] = 0; break; }
+        const double* x = S.lp_x + (size_t)b * nV;
+        double s = 0.0;
+        for (int i = n; i < nV; i++) s = s + fabs(x[i]);
+        S.infea_infty[b] = s;
+        S.feasible_lp[b] = s <= S.penalty_update_tol;
+        break;
+    }
+    case SQPB200_PH_PEN_CHECK: {
+        unsigned char go = 0;
+        if (S.need[b] && S.exitflag[b] == EX_UNKNOWN) {
+            const double rt = S.rho_trial[b];
+            const bool cont_a = S.feasible_lp[b] && S.infea_model[b] > S.penalty_update_tol && rt < S.rho_max;
+            const bool cont_b = !S.feasible_lp[b] && ((S.infea[b] - S.infea_model[b]) < S.eps1[b] * (S.infea[b] - S.infea_infty[b])) &&
+                                S.pen_trial[b] < S.penalty_iter_max && rt < S.rho_max;
+            if (cont_a || cont_b) {
+                go = 1;
+                S.rho_trial[b] = fmin(S.rho_max, rt * S.increase_parm);
+                S.pen_trial[b] += 1;
+                atomicAdd(&S.counters[3], 1);
+            }
+        }
+        S.go[b] = go;
+        break;
+    }
+    case SQPB200_PH_PEN_AFTER: {
+        if (!S.go[b]) break;
+        S.qp_iter[b] += S.qp_iters[b];
+        const int st = S.qp_status[b];
+        const bool ok = (S.qp_kkt[(size_t)b * 5 + 4] <= 1.0e-6) && st == SQPB200_QP_OPTIMAL;
+        if (!ok) {
+            S.exitflag[b] = (st == SQPB200_QP_OPTIMAL) ? SQPB200_QPERROR_INTERNAL_ERROR : st;
+            S.need[b] = 0;
+            break;
+        }
+        const double* x = S.qp_x + (size_t)b * nV;
+        double s = 0.0;
+        for (int i = n; i < nV; i++) s = s + fabs(x[i]);
+        S.infea_model[b] = s;
+        break;
+    }
+    case SQPB200_PH_PEN_FINAL: {
+        if (!(S.need[b] && S.rho_trial[b] > S.rho[b] && S.exitflag[b] == EX_UNKNOWN)) break;
+        const double rt = S.rho_trial[b], qp_obj = S.qp_obj[b];
+        const bool succ = rt * S.infea[b] - qp_obj >= S.eps2 * rt * (S.infea[b] - S.infea_model[b]);
+        if (succ) {
+            S.eps1[b] += (1 - S.eps1[b]) * S.eps1_change_parm;
+            const double* x = S.qp_x + (size_t)b * nV;
+            for (int i = 0; i < n; i++) S.p_k[(size_t)b * n + i] = x[i];
+            S.rho[b] = rt;
+        } else {
+            S.infea_model[b] = S.infea_model_tmp[b];
+            S.upd[b] |= UP_PENALTY;  // the backend still holds rho_trial in g: setupQP restores rho next iteration (:1003-1006)
+        }
+        break;
+    }
+    case SQPB200_PH_TRIAL: {
+        if (S.active[b] && S.exitflag[b] != EX_UNKNOWN) S.active[b] = 0;
+        if (!S.active[b]) break;
+        for (int i = 0; i < n; i++) S.x_trial[(size_t)b * n + i] = S.x_k[(size_t)b * n + i] + S.p_k[(size_t)b * n + i];
+        break;
+    }
+    case SQPB200_PH_RATIO: {
+        S.acc[b] = 0;
+        if (!S.active[b]) break;
+        const double infea_t = cal_infea(S, S.c_trial, b);
+        S.infea_trial[b] = infea_t;
+        const double P1_x = S.f_k[b] + S.rho[b] * S.infea[b];
+        const double P1_t = S.f_trial[b] + S.rho[b] * infea_t;
+        const double ared = P1_x - P1_t, pred = S.rho[b] * S.infea[b] - S.qp_obj[b];
+        S.actual_red[b] = ared; S.pred_red[b] = pred;
+        if (ared >= S.eta_s * pred && ared >= -S.tol) {
+            S.acc[b] = 1;
+            S.infea[b] = infea_t;
+            S.f_k[b] = S.f_trial[b];
+            for (int i = 0; i < n; i++) S.x_k[(size_t)b * n + i] = S.x_trial[(size_t)b * n + i];
+            for (int i = 0; i < m; i++) S.c_k[(size_t)b * m + i] = S.c_trial[(size_t)b * m + i];
+            get_multipliers(S, b);
+            S.upd[b] |= UP_A | UP_H | UP_BOUNDS | UP_G;
+            atomicAdd(&S.counters[4], 1);
+        }
+        // multipliers handed to the Hessian evaluation: -lambda (src/SQPTNLP.cpp:124-126)
+        for (int i = 0; i < m; i++) S.neg_lam[(size_t)b * m + i] = -S.lam_c[(size_t)b * m + i];
+        break;
+    }
+    case SQPB200_PH_FINISH: {
+        if (!S.active[b]) break;
+        if (S.acc[b]) {
+            for (int i = 0; i < n; i++) S.grad[(size_t)b * n + i] = S.g_new[(size_t)b * n + i];
+            for (int i = 0; i < S.zJ; i++) S.jac[(size_t)b * S.zJ + i] = S.j_new[(size_t)b * S.zJ + i];
+            for (int i = 0; i < S.zH; i++) S.hess[(size_t)b * S.zH + i] = S.h_new[(size_t)b * S.zH + i];
+        }
+        S.iter[b] += 1;
+        double* diff = S.scratch + (size_t)b * n;
+        get_multipliers(S, b);
+        check_optimality(S, b, diff);
+        if (S.exitflag[b] != EX_UNKNOWN) break;
+        // update_radius
+        const double ared = S.actual_red[b], pred = S.pred_red[b];
+        const bool shrink = ared < S.eta_c * pred;
+        double norm_p = 0.0;
+        for (int i = 0; i < n; i++) norm_p = fmax(norm_p, fabs(S.p_k[(size_t)b * n + i]));
+        const bool grow = !shrink && ared > S.eta_e * pred && S.tol > fabs(S.delta[b] - norm_p);
+        if (shrink) S.delta[b] = S.gamma_c * S.delta[b];
+        if (grow) S.delta[b] = fmin(S.gamma_e * S.delta[b], S.delta_max);
+        if (shrink || grow) S.upd[b] |= UP_DELTA;
+        if (S.delta[b] < S.delta_min) {
+            S.exitflag[b] = EX_TRUST_REGION_TOO_SMALL;
+            check_optimality(S, b, diff);  // :149-152
+        }
+        break;
+    }
+    case SQPB200_PH_FINAL: {
+        if (S.iter[b] == S.iter_max && S.exitflag[b] == EX_UNKNOWN) S.exitflag[b] = EX_EXCEED_MAX_ITER;
+        break;
+    }
+    }
+}
+
+}  // namespace
+
+int sqpb200_sqp_phase(const sqpb200_sqp_state* st, int phase, int* counters_host, void* stream_) {
+    if (!st || st->B <= 0) return SQPB200_ERR_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (phase == SQPB200_PH_FLAGS || phase == SQPB200_PH_AFTER_QP || phase == SQPB200_PH_PEN_CHECK || phase == SQPB200_PH_RATIO) {
+        // counters: [0] active, [1] OR of Update_* flags, [2] need penalty update, [3] go, [4] accepted
+        const int idx = phase == SQPB200_PH_FLAGS ? 0 : (phase == SQPB200_PH_AFTER_QP ? 2 : (phase == SQPB200_PH_PEN_CHECK ? 3 : 4));
+        if (cudaMemsetAsync(st->counters + idx, 0, (phase == SQPB200_PH_FLAGS ? 2 : 1) * sizeof(int), stream) != cudaSuccess) return SQPB200_ERR_CUDA;
+    }
+    const int block = 128, grid = (st->B + block - 1) / block;
+    sqp_phase_kernel<<<grid, block, 0, stream>>>(*st, phase);
+    if (cudaGetLastError() != cudaSuccess) return SQPB200_ERR_CUDA;
+    if (counters_host) {
+        if (cudaMemcpyAsync(counters_host, st->counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return SQPB200_ERR_CUDA;
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return SQPB200_ERR_CUDA;
+    }
+    return 0;
+}

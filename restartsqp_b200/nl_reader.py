@@ -645,6 +645,13 @@ class DeviceNLP:
             raise self._capi.SqpB200Error("sqpb200_nlp_eval failed (%d): %s" % (rc, self.L.sqpb200_nlp_last_error().decode()))
         return f, c, g, jv, hv
 
+    def eval_device(self, which, B, x, lam=None, f=None, c=None, grad=None, jac=None, hess=None):
+        """Evaluation with every array already in device memory (CUDA tensors); asynchronous on the default stream."""
+        p = lambda t: None if t is None else self._C.c_void_p(t.data_ptr())
+        rc = self.L.sqpb200_nlp_eval(self.h, which, B, p(x), p(lam), p(f), p(c), p(grad), p(jac), p(hess), self._capi.LOC_DEVICE, None)
+        if rc != 0:
+            raise self._capi.SqpB200Error("sqpb200_nlp_eval failed (%d): %s" % (rc, self.L.sqpb200_nlp_last_error().decode()))
+
     def Eval_f_c(self, x):
         f, c, _, _, _ = self._eval(0, x)
         return f, c

@@ -127,3 +127,28 @@ def test_sqp_with_device_evaluator(gpu_lib):
     assert (res_d.exitflag == int(r.Exitflag.OPTIMAL)).all() and (res_h.exitflag == res_d.exitflag).all()
     assert np.abs(res_d.x - res_h.x).max() < 1e-6 and np.abs(res_d.x - X_STAR).max() < 1e-4
     dev.close()
+
+
+@pytest.mark.parametrize("name", ["hs071", "hs015", "hs043", "hs100", "hs113", "hs104", "hs099", "hs106"])
+def test_device_resident_loop_equals_host_loop(gpu_lib, name):
+    """csrc/sqp_outer.cu + DeviceBatchedSQP (iterates never leave the GPU) against BatchedSQP (numpy mirror of
+    src/Algorithm.cpp) on the same NVRTC evaluator and the same QP backend: identical exit flags, outer and QP iteration
+    counts, penalty parameters, radii and iterates."""
+    import os
+    from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
+    from restartsqp_b200.sqp_device import DeviceBatchedSQP
+    from test_hs_suite import HS_DIR, perturbed_starts
+    host = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+    dev = DeviceNLP(host)
+    X = perturbed_starts(host, 200, 1)
+    opt_h, opt_d = r.Options(iter_max=120), r.Options(iter_max=120)
+    res_h = BatchedSQP(dev, x0=X, options=opt_h).Optimize()
+    alg = DeviceBatchedSQP(dev, x0=X, options=opt_d)
+    res_d = alg.Optimize()
+    assert (res_d.exitflag == res_h.exitflag).all(), (np.unique(res_d.exitflag, return_counts=True), np.unique(res_h.exitflag, return_counts=True))
+    assert (res_d.iters == res_h.iters).all() and (res_d.qp_iter == res_h.qp_iter).all()
+    assert (res_d.rho == res_h.rho).all() and (res_d.delta == res_h.delta).all()
+    fin = np.isfinite(res_h.x).all(axis=1)
+    assert np.array_equal(res_d.x[fin], res_h.x[fin]) and np.array_equal(res_d.obj[fin], res_h.obj[fin])
+    assert (res_d.exitflag[0] == int(r.Exitflag.OPTIMAL)) or name == "hs106"
+    alg.close(); dev.close()

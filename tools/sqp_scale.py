@@ -8,6 +8,8 @@ import restartsqp_b200 as r
 from restartsqp_b200 import sharding
 from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
 from restartsqp_b200.sqp_driver import BatchedSQP
+from restartsqp_b200.sqp_device import DeviceBatchedSQP
+Loop = BatchedSQP if os.environ.get('SQP_HOST_LOOP') else DeviceBatchedSQP
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 dist = None
@@ -20,10 +22,10 @@ lo, hi = sharding.shard_range(N, rank, world)
 x0, _ = host.Get_starting_point(); xl, xu, _, _ = host.Get_bounds_info()
 rng = np.random.default_rng(71000)
 X = np.clip(x0 * (1 + 0.1 * rng.standard_normal((N, host.n))) + 0.1 * rng.standard_normal((N, host.n)), xl, xu)[lo:hi]
-BatchedSQP(dev, x0=X[:256], device=local).Optimize()
+Loop(dev, x0=X[:256], device=local).Optimize()
 if dist is not None: dist.barrier()
 t0 = time.perf_counter()
-res = BatchedSQP(dev, x0=X, device=local).Optimize()
+res = Loop(dev, x0=X, device=local).Optimize()
 dt = time.perf_counter() - t0
 if dist is not None:
     import torch
@@ -32,5 +34,5 @@ if dist is not None:
 else:
     nopt = int((res.exitflag == 0).sum())
 if rank == 0:
-    print({"instances": N, "gpus": world, "seconds": dt, "sqp_solves_per_s": N / dt, "optimal": nopt, "per_rank": hi - lo}, flush=True)
+    print({"instances": N, "gpus": world, "seconds": dt, "sqp_solves_per_s": N / dt, "optimal": nopt, "per_rank": hi - lo, "loop": Loop.__name__}, flush=True)
 if dist is not None: dist.destroy_process_group()

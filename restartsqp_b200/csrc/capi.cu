@@ -152,7 +152,7 @@ int sqpb200_create(int batch, int nV, int nC, int qptype, int device, const sqpb
     rc |= dev_alloc(h, &h->dobj, B); rc |= dev_alloc(h, &h->dkkt, B * 5);
     rc |= dev_alloc(h, &h->dstatus, B); rc |= dev_alloc(h, &h->diters, B);
     rc |= dev_alloc(h, &h->dWB, B * nV); rc |= dev_alloc(h, &h->dWC, B * nC);
-    rc |= dev_alloc(h, &h->dwsB, B * nV); rc |= dev_alloc(h, &h->dwsC, B * nC);
+    rc |= dev_alloc(h, &h->dwsB, B * nV + 32); rc |= dev_alloc(h, &h->dwsC, B * nC + 32);  // +32: kkt_tma_kernel reads 16-byte windows
     rc |= dev_alloc(h, &h->dmask, B);
     if (rc) { *out = h; return SQPB200_ERR_CUDA; }
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
@@ -828,8 +828,48 @@ int sqpb200_kkt_residuals_recompute(sqpb200_handle h, double* out, int loc) {
     a.x = h->dx; a.y = h->dy; a.wsB = h->dwsB; a.wsC = h->dwsC; a.WB = h->dWB; a.WC = h->dWC;
     if (ensure_stage(h, (size_t)h->batch * 5 * 8)) return SQPB200_ERR_CUDA;
     a.out = (loc == SQPB200_LOC_DEVICE) ? out : (double*)h->stage;
+    // TMA-staged kernel: G instances (warps) per CTA, two stages; largest G in {8, 4, 2} that keeps two CTAs per SM
+    // (or fits at all); the plain warp-per-instance kernel remains for instances too large for that
+    {
+        const bool aligned = (((uintptr_t)a.Aval | (uintptr_t)a.Hval | (uintptr_t)a.x | (uintptr_t)a.y | (uintptr_t)a.g | (uintptr_t)a.lb |
+                               (uintptr_t)a.ub | (uintptr_t)a.lbA | (uintptr_t)a.ubA) & 15) == 0;
+        // (G warps per CTA, stages) that keeps the most warps resident per SM; ties go to two stages
+        const int zHk = a.has_H ? h->zH : 0;
+        int G = 0, stages = 0, best_warps = 0;
+        size_t smem_t = 0;
+        for (int st = 2; st >= 1 && aligned; st--)
+            for (int g = 8; g >= 2; g >>= 1) {
+                KKTLayout Lg = kkt_layout(g, st, h->nV, h->nC, h->zA, zHk);
+                size_t sm = kkt_smem_bytes(Lg);
+                if (sm > 227 * 1024) continue;
+                int ctas = (int)((228 * 1024) / (sm + 1024));
+                int warps = ctas * g;
+                if (warps > 64) warps = 64;
+                if (warps > best_warps) { best_warps = warps; G = g; stages = st; smem_t = sm; }
+            }
+        if (G) {
+            KKTArgs at = a;
+            if (!at.has_H) at.zH = 0;
+            KKTLayout Lg = kkt_layout(G, stages, h->nV, h->nC, h->zA, at.zH);
+            if (smem_t > 48 * 1024) CK(cudaFuncSetAttribute(kkt_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+            long long ngroups = ((long long)h->batch + G - 1) / G;
+            int per_sm = (int)((228 * 1024) / (smem_t + 1024));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm * G > 64) per_sm = 64 / G;
+            long long grid = ngroups < 148LL * per_sm ? ngroups : 148LL * per_sm;
+            kkt_tma_kernel<<<(int)grid, G * 32, smem_t, h->stream>>>(at, Lg);
+            h->launches++;
+            CK(cudaGetLastError());
+            if (loc == SQPB200_LOC_HOST) CK(cudaMemcpyAsync(out, h->stage, (size_t)h->batch * 5 * 8, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            return 0;
+        }
+    }
+    const size_t per_warp = kkt_warp_doubles(h->nV, h->nC, h->zA, h->zH) * 8;
     int warps = 4;
-    size_t smem = (size_t)warps * (2 * h->nV + h->nC) * 8;
+    while (warps > 1 && (size_t)warps * per_warp > 24 * 1024) warps >>= 1;
+    size_t smem = (size_t)warps * per_warp;
+    if (smem > 227 * 1024) { h->err = "KKT kernel: instance too large for shared-memory staging"; return SQPB200_ERR_TOO_LARGE; }
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kkt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kkt_kernel<<<(h->batch + warps - 1) / warps, warps * 32, smem, h->stream>>>(a);
     h->launches++;
@@ -860,11 +900,31 @@ int sqpb200_spmv(sqpb200_handle h, int which, int transpose, const double* x, do
         dyv = (double*)((char*)h->stage + ((bin + 15) / 16) * 16);
     }
     long long total = (long long)B * nout;
-    spmv_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(total, nout, nin, nnz, ptr, idx, perm, val, (const double*)dxv, dyv);
+    {
+        // TMA-staged kernel: groups of G instances (G even), two shared-memory stages of ~20 KB each filled by bulk
+        // asynchronous copies; the one-thread-per-output kernel remains for instances too large for a stage
+        const size_t pat_bytes = ((size_t)nout + 1 + 2 * (size_t)nnz) * 4 + 16;
+        const size_t per_inst = ((size_t)nnz + nin) * 8;
+        const size_t budget = 44 * 1024;
+        int G = (int)((budget > pat_bytes ? (budget - pat_bytes) / 2 : 0) / (per_inst ? per_inst : 1));
+        G &= ~1;
+        const bool aligned = (((uintptr_t)val | (uintptr_t)dxv) & 15) == 0;
+        if (G >= 2 && aligned) {
+            if ((long long)G > (long long)B) G = (int)((B + 1) & ~1ull);
+            const size_t smem = 2 * (size_t)G * per_inst + pat_bytes;
+            long long ngroups = ((long long)B + G - 1) / G;
+            long long grid = ngroups < 148LL * 5 ? ngroups : 148LL * 5;
+            spmv_tma_kernel<<<(int)grid, 256, smem, h->stream>>>((long long)B, G, nout, nin, nnz, ptr, idx, perm, val, (const double*)dxv, dyv);
+        } else {
+            spmv_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(total, nout, nin, nnz, ptr, idx, perm, val, (const double*)dxv, dyv);
+        }
+    }
     h->launches++;
     CK(cudaGetLastError());
-    if (loc == SQPB200_LOC_HOST) CK(cudaMemcpyAsync(y, dyv, bout, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if (loc == SQPB200_LOC_HOST) {
+        CK(cudaMemcpyAsync(y, dyv, bout, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }  // device pointers: asynchronous on the handle's stream
     return 0;
 }
 

@@ -128,6 +128,150 @@ __global__ void __launch_bounds__(256) spmv_kernel(long long total, int nout, in
     }
 }
 
+// Staged form: the values and the input vectors of a group of G consecutive instances are contiguous in HBM
+// (instance-major layout), so the CTA copies them to shared memory with fully coalesced 16-byte loads, computes the
+// G * nout outputs out of shared memory (one thread per output, same k order), and writes them with coalesced stores.
+// Every input byte is fetched from HBM exactly once in full 128-byte lines; the shared pattern is staged once per CTA.
+// Dynamic shared memory: G * (nnz + nin) doubles, then (nout + 1 + nnz [+ nnz]) ints.
+__global__ void __launch_bounds__(256) spmv_staged_kernel(long long batch, int G, int nout, int nin, int nnz,
+                                                           const int* __restrict__ ptr, const int* __restrict__ idx,
+                                                           const int* __restrict__ perm, const double* __restrict__ val,
+                                                           const double* __restrict__ x, double* __restrict__ y) {
+    extern __shared__ __align__(16) double spm[];
+    double* sval = spm;
+    double* sx = sval + (size_t)G * nnz;
+    int* sptr = reinterpret_cast<int*>(sx + (size_t)G * nin);
+    int* sidx = sptr + nout + 1;
+    int* sperm = sidx + nnz;
+    for (int i = threadIdx.x; i <= nout; i += blockDim.x) sptr[i] = ptr[i];
+    for (int i = threadIdx.x; i < nnz; i += blockDim.x) { sidx[i] = idx[i]; if (perm) sperm[i] = perm[i]; }
+    const long long ngroups = (batch + G - 1) / G;
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long long b0 = grp * G;
+        const int g = (int)((batch - b0 < G) ? batch - b0 : G);
+        __syncthreads();  // previous group consumed (and the pattern staged)
+        {
+            // b0 * nnz and b0 * nin are even (G is even), so both segments start 16-byte aligned
+            const double2* v2 = reinterpret_cast<const double2*>(val + b0 * nnz);
+            const double2* x2 = reinterpret_cast<const double2*>(x + b0 * nin);
+            const int nv = g * nnz, nx = g * nin;
+            for (int i = threadIdx.x; i < nv / 2; i += blockDim.x) reinterpret_cast<double2*>(sval)[i] = v2[i];
+            if ((nv & 1) && threadIdx.x == 0) sval[nv - 1] = val[b0 * nnz + nv - 1];
+            for (int i = threadIdx.x; i < nx / 2; i += blockDim.x) reinterpret_cast<double2*>(sx)[i] = x2[i];
+            if ((nx & 1) && threadIdx.x == 0) sx[nx - 1] = x[b0 * nin + nx - 1];
+        }
+        __syncthreads();
+        double* yg = y + b0 * nout;
+        for (int t = threadIdx.x; t < g * nout; t += blockDim.x) {
+            const int bl = t / nout, o = t - bl * nout;
+            const double* vb = sval + (size_t)bl * nnz;
+            const double* xb = sx + (size_t)bl * nin;
+            double acc = 0.0;
+            const int k1 = sptr[o + 1];
+            for (int k = sptr[o]; k < k1; k++) {
+                const int e = perm ? sperm[k] : k;
+                acc = __dadd_rn(acc, __dmul_rn(vb[e], xb[sidx[k]]));
+            }
+            yg[t] = acc;
+        }
+    }
+}
+
+// ---- TMA helpers (1-D bulk asynchronous copy global -> shared, completion on an mbarrier) ----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    return done != 0;
+}
+
+// TMA-staged, double-buffered form of the staged kernel: while the CTA computes group i out of one shared-memory stage, the
+// TMA engine fills the other stage with group i+1 (two bulk copies: the G*nnz values and the G*nin inputs, both contiguous
+// and 16-byte aligned because G is even).  No thread waits on a global load; every HBM line is fetched once.
+// Dynamic shared memory: 2 stages x G*(nnz+nin) doubles, then the pattern as ints.
+__global__ void __launch_bounds__(256) spmv_tma_kernel(long long batch, int G, int nout, int nin, int nnz,
+                                                        const int* __restrict__ ptr, const int* __restrict__ idx,
+                                                        const int* __restrict__ perm, const double* __restrict__ val,
+                                                        const double* __restrict__ x, double* __restrict__ y) {
+    extern __shared__ __align__(128) double spm[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    const size_t stage_doubles = (size_t)G * (nnz + nin);
+    int* sptr = reinterpret_cast<int*>(spm + 2 * stage_doubles);
+    int* sidx = sptr + nout + 1;
+    int* sperm = sidx + nnz;
+    for (int i = threadIdx.x; i <= nout; i += blockDim.x) sptr[i] = ptr[i];
+    for (int i = threadIdx.x; i < nnz; i += blockDim.x) { sidx[i] = idx[i]; if (perm) sperm[i] = perm[i]; }
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long ngroups = (batch + G - 1) / G;
+    bool manual[2] = {false, false};
+    uint32_t phase[2] = {0u, 0u};
+    // fill stage s with group grp; returns true if the group had to be copied with ordinary loads (odd-sized tail)
+    auto issue = [&](long long grp, int s) -> bool {
+        const long long b0 = grp * G;
+        const int g = (int)((batch - b0 < G) ? batch - b0 : G);
+        double* sv = spm + (size_t)s * stage_doubles;
+        double* sx = sv + (size_t)G * nnz;
+        const uint32_t bv = (uint32_t)g * nnz * 8u, bx = (uint32_t)g * nin * 8u;
+        if (((bv | bx) & 15u) == 0u) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&mbar[s], bv + bx);
+                if (bv) bulk_g2s(sv, val + b0 * nnz, bv, &mbar[s]);
+                if (bx) bulk_g2s(sx, x + b0 * nin, bx, &mbar[s]);
+            }
+            return false;
+        }
+        for (int i = threadIdx.x; i < g * nnz; i += blockDim.x) sv[i] = val[b0 * nnz + i];
+        for (int i = threadIdx.x; i < g * nin; i += blockDim.x) sx[i] = x[b0 * nin + i];
+        return true;
+    };
+    if ((long long)blockIdx.x < ngroups) manual[0] = issue(blockIdx.x, 0);
+    __syncthreads();
+    int it = 0;
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, it++) {
+        const int s = it & 1;
+        const long long next = grp + gridDim.x;
+        if (next < ngroups) manual[s ^ 1] = issue(next, s ^ 1);
+        if (!manual[s]) {
+            while (!mbar_try_wait(&mbar[s], phase[s])) {}
+            phase[s] ^= 1u;
+        }
+        const long long b0 = grp * G;
+        const int g = (int)((batch - b0 < G) ? batch - b0 : G);
+        const double* sv = spm + (size_t)s * stage_doubles;
+        const double* sx = sv + (size_t)G * nnz;
+        double* yg = y + b0 * nout;
+        for (int t = threadIdx.x; t < g * nout; t += blockDim.x) {
+            const int bl = t / nout, o = t - bl * nout;
+            const double* vb = sv + (size_t)bl * nnz;
+            const double* xb = sx + (size_t)bl * nin;
+            double acc = 0.0;
+            const int k1 = sptr[o + 1];
+            for (int k = sptr[o]; k < k1; k++) {
+                const int e = perm ? sperm[k] : k;
+                acc = __dadd_rn(acc, __dmul_rn(vb[e], xb[sidx[k]]));
+            }
+            yg[t] = acc;
+        }
+        __syncthreads();  // stage s is free again (and a manually copied next stage is complete)
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // B2/B3: batched QPhandler data construction (src/QPhandler.cpp:185-201, 358-367, 559-564,
 // 287-292, 439-440, 461-462).  One thread per (instance, entry).
@@ -182,7 +326,6 @@ __global__ void __launch_bounds__(256) qphandler_g_kernel(int batch, int n, int 
 // Lanes evaluate A x, A'y_c and H x (one lane per output entry, reference order); lane 0 then
 // accumulates the four violation sums in the reference's index order, so the result is
 // bit-identical with qpOASESInterface::test_optimality (src/qpOASESInterface.cpp:498-684).
-// Dynamic shared memory: per warp (2*nV + nC) doubles.
 // ------------------------------------------------------------------------------------------
 struct KKTArgs {
     int batch, nV, nC, zA, zH, has_H;
@@ -193,19 +336,38 @@ struct KKTArgs {
     double* out;
 };
 
+// Shared memory per warp (doubles): av[zA] hv[zH] x[nV] y[nV+nC] g[nV] lb[nV] ub[nV] lbA[nC] ubA[nC] | Ax[nC] ATy[nV] Hx[nV]
+// | terms[2nV+2nC]; then (bytes) sB[nV] sC[nC].  Everything an instance needs is copied from HBM once, coalesced; the lanes
+// evaluate the three sparse products and then the individual violation terms in parallel; lanes 0..3 add the terms of the
+// four sums one by one in the reference's index order (adding a term that the reference skips contributes +0.0, which
+// leaves a non-negative partial sum unchanged), so the results stay bit-identical.
+__host__ __device__ inline size_t kkt_warp_doubles(int nV, int nC, int zA, int zH) {
+    size_t d = (size_t)zA + zH + nV + (nV + nC) + 3 * (size_t)nV + 2 * (size_t)nC + nC + 2 * (size_t)nV + 4 * (size_t)nV + 4 * (size_t)nC;
+    return d + ((size_t)nV + nC + 7) / 8;
+}
+
 __global__ void __launch_bounds__(128) kkt_kernel(const KKTArgs A) {
     extern __shared__ __align__(16) double ksm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (b >= A.batch) return;
-    const int nV = A.nV, nC = A.nC;
-    double* Ax = ksm + (size_t)warp * (2 * nV + nC);
-    double* ATy = Ax + nC;
-    double* Hx = ATy + nV;
-    const double* av = A.Aval + b * A.zA;
-    const double* hv = A.has_H ? A.Hval + b * A.zH : nullptr;
-    const double *x = A.x + b * nV, *y = A.y + b * (nV + nC), *g = A.g + b * nV;
-    const double *lb = A.lb + b * nV, *ub = A.ub + b * nV, *lbA = A.lbA + b * nC, *ubA = A.ubA + b * nC;
+    const int nV = A.nV, nC = A.nC, zA = A.zA, zH = A.has_H ? A.zH : 0;
+    double* base = ksm + (size_t)warp * kkt_warp_doubles(nV, nC, A.zA, A.zH);
+    double *av = base, *hv = av + zA, *x = hv + (A.has_H ? A.zH : 0) + (A.has_H ? 0 : A.zH), *y = x + nV, *g = y + nV + nC, *lb = g + nV, *ub = lb + nV;
+    double *lbA = ub + nV, *ubA = lbA + nC, *Ax = ubA + nC, *ATy = Ax + nC, *Hx = ATy + nV;
+    double *tP = Hx + nV, *tD = tP + 2 * nV + 2 * nC, *tC = tD + nV + nC;  // primal / dual / complementarity terms; stat terms reuse ATy
+    signed char* sB = reinterpret_cast<signed char*>(tC + nV + nC);
+    signed char* sC = sB + nV;
+    {
+        auto cp = [&](double* dst, const double* src, int cnt) { for (int i = lane; i < cnt; i += 32) dst[i] = src[i]; };
+        cp(av, A.Aval + b * A.zA, zA);
+        if (A.has_H) cp(hv, A.Hval + b * A.zH, zH);
+        cp(x, A.x + b * nV, nV); cp(y, A.y + b * (nV + nC), nV + nC); cp(g, A.g + b * nV, nV);
+        cp(lb, A.lb + b * nV, nV); cp(ub, A.ub + b * nV, nV); cp(lbA, A.lbA + b * nC, nC); cp(ubA, A.ubA + b * nC, nC);
+        for (int i = lane; i < nV; i += 32) sB[i] = A.wsB[b * nV + i];
+        for (int i = lane; i < nC; i += 32) sC[i] = A.wsC[b * nC + i];
+    }
+    __syncwarp();
     for (int r = lane; r < nC; r += 32) {
         double s = 0.0;
         for (int k = A.Arp[r]; k < A.Arp[r + 1]; k++) s = __dadd_rn(s, __dmul_rn(av[A.Aperm[k]], x[A.Aci[k]]));
@@ -216,68 +378,251 @@ __global__ void __launch_bounds__(128) kkt_kernel(const KKTArgs A) {
         for (int e = A.Ap[c]; e < A.Ap[c + 1]; e++) s = __dadd_rn(s, __dmul_rn(av[e], y[nV + A.Ai[e]]));
         ATy[c] = s;
         double h = 0.0;
-        if (hv)
+        if (A.has_H)
             for (int e = A.Hp[c]; e < A.Hp[c + 1]; e++) h = __dadd_rn(h, __dmul_rn(hv[e], x[A.Hi[e]]));
         Hx[c] = h;
     }
     __syncwarp();
-    if (lane != 0) return;
     const double SQRT_M_EPS = 1.0e-8;
-    const signed char* sB = A.wsB + b * nV;
-    const signed char* sC = A.wsC + b * nC;
     int* WB = A.WB ? A.WB + b * nV : nullptr;
     int* WC = A.WC ? A.WC + b * nC : nullptr;
-    double primal = 0.0, dual = 0.0, stat = 0.0, cmpl = 0.0;
-    for (int i = 0; i < nV; i++) {
-        primal = __dadd_rn(primal, fmax(0.0, __dsub_rn(lb[i], x[i])));
-        primal = __dadd_rn(primal, -fmin(0.0, __dsub_rn(ub[i], x[i])));
-    }
-    for (int i = 0; i < nC; i++) {
-        primal = __dadd_rn(primal, fmax(0.0, __dsub_rn(lbA[i], Ax[i])));
-        primal = __dadd_rn(primal, -fmin(0.0, __dsub_rn(ubA[i], Ax[i])));
-    }
 #define WSB(i) ((sB[i] > 0) ? ((fabs(__dsub_rn(x[i], lb[i])) < SQRT_M_EPS) ? -99 : 1) \
                             : ((sB[i] < 0) ? ((fabs(__dsub_rn(x[i], ub[i])) < SQRT_M_EPS) ? -99 : -1) : 0))
 #define WSC(i) ((sC[i] > 0) ? ((__dsub_rn(Ax[i], lbA[i]) < SQRT_M_EPS) ? -99 : 1) \
                             : ((sC[i] < 0) ? ((__dsub_rn(Ax[i], ubA[i]) < SQRT_M_EPS) ? -99 : -1) : 0))
-    for (int i = 0; i < nV; i++) {
-        int W = WSB(i); double yi = y[i];
+    for (int i = lane; i < nV; i += 32) {
+        tP[2 * i] = fmax(0.0, __dsub_rn(lb[i], x[i]));
+        tP[2 * i + 1] = -fmin(0.0, __dsub_rn(ub[i], x[i]));
+        const int W = WSB(i);
+        const double yi = y[i];
         if (WB) WB[i] = W;
-        if (W == 0) dual = __dadd_rn(dual, fabs(yi));
-        else if (W == -1) dual = __dadd_rn(dual, -fmin(0.0, yi));
-        else if (W == 1) dual = __dadd_rn(dual, fmax(0.0, yi));
-    }
-    for (int i = 0; i < nC; i++) {
-        int W = WSC(i); double yi = y[nV + i];
-        if (WC) WC[i] = W;
-        if (W == 0) dual = __dadd_rn(dual, fabs(yi));
-        else if (W == -1) dual = __dadd_rn(dual, -fmin(0.0, yi));
-        else if (W == 1) dual = __dadd_rn(dual, fmax(0.0, yi));
-    }
-    for (int i = 0; i < nV; i++) {
+        tD[i] = (W == 0) ? fabs(yi) : ((W == -1) ? -fmin(0.0, yi) : ((W == 1) ? fmax(0.0, yi) : 0.0));
+        tC[i] = (W == 0) ? fabs(yi) : ((W == -1) ? fabs(__dmul_rn(yi, __dsub_rn(x[i], lb[i]))) : ((W == 1) ? fabs(__dmul_rn(yi, __dsub_rn(ub[i], x[i]))) : 0.0));
         double gap = ATy[i];
-        gap = __dadd_rn(gap, y[i]);
+        gap = __dadd_rn(gap, yi);
         gap = __dsub_rn(gap, g[i]);
         gap = __dsub_rn(gap, Hx[i]);
-        stat = __dadd_rn(stat, fabs(gap));
+        ATy[i] = fabs(gap);  // stationarity term (each lane rewrites only its own entries)
     }
-    for (int i = 0; i < nV; i++) {
-        int W = WSB(i); double yi = y[i];
-        if (W == 0) cmpl = __dadd_rn(cmpl, fabs(yi));
-        else if (W == -1) cmpl = __dadd_rn(cmpl, fabs(__dmul_rn(yi, __dsub_rn(x[i], lb[i]))));
-        else if (W == 1) cmpl = __dadd_rn(cmpl, fabs(__dmul_rn(yi, __dsub_rn(ub[i], x[i]))));
-    }
-    for (int i = 0; i < nC; i++) {
-        int W = WSC(i); double yi = y[nV + i];
-        if (W == 0) cmpl = __dadd_rn(cmpl, fabs(yi));
-        else if (W == -1) cmpl = __dadd_rn(cmpl, fabs(__dmul_rn(yi, __dsub_rn(Ax[i], lbA[i]))));
-        else if (W == 1) cmpl = __dadd_rn(cmpl, fabs(__dmul_rn(yi, __dsub_rn(ubA[i], Ax[i]))));
+    for (int i = lane; i < nC; i += 32) {
+        tP[2 * nV + 2 * i] = fmax(0.0, __dsub_rn(lbA[i], Ax[i]));
+        tP[2 * nV + 2 * i + 1] = -fmin(0.0, __dsub_rn(ubA[i], Ax[i]));
+        const int W = WSC(i);
+        const double yi = y[nV + i];
+        if (WC) WC[i] = W;
+        tD[nV + i] = (W == 0) ? fabs(yi) : ((W == -1) ? -fmin(0.0, yi) : ((W == 1) ? fmax(0.0, yi) : 0.0));
+        tC[nV + i] = (W == 0) ? fabs(yi) : ((W == -1) ? fabs(__dmul_rn(yi, __dsub_rn(Ax[i], lbA[i]))) : ((W == 1) ? fabs(__dmul_rn(yi, __dsub_rn(ubA[i], Ax[i]))) : 0.0));
     }
 #undef WSB
 #undef WSC
-    double* o = A.out + b * 5;
-    o[0] = primal; o[1] = dual; o[2] = stat; o[3] = cmpl;
-    o[4] = __dadd_rn(__dadd_rn(__dadd_rn(cmpl, stat), dual), primal);
+    __syncwarp();
+    // lanes 0..3: one sequential sum each, in index order
+    double s = 0.0;
+    if (lane < 4) {
+        const double* t = (lane == 0) ? tP : ((lane == 1) ? tD : ((lane == 2) ? ATy : tC));
+        const int cnt = (lane == 0) ? 2 * nV + 2 * nC : ((lane == 2) ? nV : nV + nC);
+        for (int i = 0; i < cnt; i++) s = __dadd_rn(s, t[i]);
+    }
+    const double primal = __shfl_sync(0xffffffffu, s, 0), dual = __shfl_sync(0xffffffffu, s, 1);
+    const double stat = __shfl_sync(0xffffffffu, s, 2), cmpl = __shfl_sync(0xffffffffu, s, 3);
+    if (lane == 0) {
+        double* o = A.out + b * 5;
+        o[0] = primal; o[1] = dual; o[2] = stat; o[3] = cmpl;
+        o[4] = __dadd_rn(__dadd_rn(__dadd_rn(cmpl, stat), dual), primal);
+    }
+}
+
+// TMA-staged form: a CTA of G warps (G even) works on groups of G consecutive instances, one warp per instance.  The nine
+// FP64 arrays and the two working-set byte arrays of a group are contiguous in HBM; the TMA engine copies a group into a
+// shared-memory stage (with two stages: the next group while the warps evaluate the current one).  The shared pattern is
+// staged once per CTA.  Arithmetic and order of every sum as in kkt_kernel above (bit-identical results); the violation terms
+// are written in place over staged inputs that are dead by then (lb/ub/lbA/ubA <- primal terms, g/Ax <- dual terms,
+// x/y_c <- complementarity terms, A'y <- stationarity terms), so a warp needs only Ax, A'y, Hx as extra storage.  The byte
+// arrays are fetched from the enclosing 16-byte aligned window (the library pads those allocations), `lead` bytes into it.
+struct KKTLayout {
+    int G, stages;
+    int oAv, oHv, oX, oY, oG, oLb, oUb, oLbA, oUbA;  // stage offsets in doubles (each array: G * len)
+    int oWsB, oWsC;                                    // stage offsets in bytes of the two byte windows
+    int stage_bytes, work_doubles, pat_ints;           // per stage / per warp / per CTA
+    int pAp, pAi, pArp, pAci, pAperm, pHp, pHi;        // pattern offsets in ints
+};
+__host__ __device__ inline KKTLayout kkt_layout(int G, int stages, int nV, int nC, int zA, int zH) {
+    KKTLayout L;
+    L.G = G; L.stages = stages;
+    int o = 0;
+    L.oAv = o; o += G * zA; L.oHv = o; o += G * zH; L.oX = o; o += G * nV; L.oY = o; o += G * (nV + nC);
+    L.oG = o; o += G * nV; L.oLb = o; o += G * nV; L.oUb = o; o += G * nV; L.oLbA = o; o += G * nC; L.oUbA = o; o += G * nC;
+    int bytes = o * 8;
+    L.oWsB = bytes; bytes += ((G * nV + 15 + 15) / 16) * 16;
+    L.oWsC = bytes; bytes += ((G * nC + 15 + 15) / 16) * 16;
+    L.stage_bytes = (bytes + 127) / 128 * 128;
+    L.work_doubles = nC + 2 * nV;
+    int p = 0;
+    L.pAp = p; p += nV + 1; L.pAi = p; p += zA; L.pArp = p; p += nC + 1; L.pAci = p; p += zA; L.pAperm = p; p += zA;
+    L.pHp = p; p += nV + 1; L.pHi = p; p += zH;
+    L.pat_ints = (p + 3) & ~3;
+    return L;
+}
+__host__ __device__ inline size_t kkt_smem_bytes(const KKTLayout& L) {
+    return (size_t)L.stages * L.stage_bytes + (size_t)L.G * L.work_doubles * 8 + (size_t)L.pat_ints * 4;
+}
+
+__global__ void __launch_bounds__(256) kkt_tma_kernel(const KKTArgs A, const KKTLayout L) {
+    extern __shared__ __align__(128) unsigned char kraw[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = L.G, nV = A.nV, nC = A.nC, zA = A.zA, zH = A.has_H ? A.zH : 0;
+    const int S = L.stages;
+    double* work = reinterpret_cast<double*>(kraw + (size_t)S * L.stage_bytes) + (size_t)warp * L.work_doubles;
+    int* pat = reinterpret_cast<int*>(reinterpret_cast<double*>(kraw + (size_t)S * L.stage_bytes) + (size_t)G * L.work_doubles);
+    for (int i = threadIdx.x; i <= nV; i += blockDim.x) { pat[L.pAp + i] = A.Ap[i]; if (zH) pat[L.pHp + i] = A.Hp[i]; }
+    for (int i = threadIdx.x; i <= nC; i += blockDim.x) pat[L.pArp + i] = A.Arp[i];
+    for (int i = threadIdx.x; i < zA; i += blockDim.x) { pat[L.pAi + i] = A.Ai[i]; pat[L.pAci + i] = A.Aci[i]; pat[L.pAperm + i] = A.Aperm[i]; }
+    for (int i = threadIdx.x; i < zH; i += blockDim.x) pat[L.pHi + i] = A.Hi[i];
+    const int *Ap = pat + L.pAp, *Ai = pat + L.pAi, *Arp = pat + L.pArp, *Aci = pat + L.pAci, *Aperm = pat + L.pAperm, *Hp = pat + L.pHp, *Hi = pat + L.pHi;
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long ngroups = ((long long)A.batch + G - 1) / G;
+    bool manual[2] = {false, false};
+    uint32_t phase[2] = {0u, 0u};
+    int lead[2][2] = {{0, 0}, {0, 0}};  // [stage][B/C]: position of the group's first byte inside its aligned window
+    auto issue = [&](long long grp, int s) -> bool {
+        const long long b0 = grp * G;
+        const int g = (int)((A.batch - b0 < G) ? A.batch - b0 : G);
+        unsigned char* st = kraw + (size_t)s * L.stage_bytes;
+        double* sd = reinterpret_cast<double*>(st);
+        const unsigned char* gB = reinterpret_cast<const unsigned char*>(A.wsB) + b0 * nV;
+        const unsigned char* gC = reinterpret_cast<const unsigned char*>(A.wsC) + b0 * nC;
+        lead[s][0] = (int)((uintptr_t)gB & 15); lead[s][1] = (int)((uintptr_t)gC & 15);
+        if ((g & 1) == 0) {  // even group: every FP64 segment is a multiple of 16 bytes and starts 16-byte aligned
+            if (threadIdx.x == 0) {
+                const uint32_t wB = (uint32_t)((lead[s][0] + g * nV + 15) / 16 * 16), wC = (uint32_t)((lead[s][1] + g * nC + 15) / 16 * 16);
+                const uint32_t tot = 8u * (uint32_t)g * (uint32_t)(zA + zH + nV + (nV + nC) + 3 * nV + 2 * nC) + (nV ? wB : 0u) + (nC ? wC : 0u);
+                // the stage was last written with ordinary stores (in-place terms): order them before the async-proxy writes
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&mbar[s], tot);
+                auto cp = [&](int off, const double* src, int len) { if (len) bulk_g2s(sd + off, src + b0 * len, 8u * (uint32_t)g * (uint32_t)len, &mbar[s]); };
+                cp(L.oAv, A.Aval, zA); if (zH) cp(L.oHv, A.Hval, zH);
+                cp(L.oX, A.x, nV); cp(L.oY, A.y, nV + nC); cp(L.oG, A.g, nV); cp(L.oLb, A.lb, nV); cp(L.oUb, A.ub, nV);
+                cp(L.oLbA, A.lbA, nC); cp(L.oUbA, A.ubA, nC);
+                if (nV) bulk_g2s(st + L.oWsB, gB - lead[s][0], wB, &mbar[s]);
+                if (nC) bulk_g2s(st + L.oWsC, gC - lead[s][1], wC, &mbar[s]);
+            }
+            return false;
+        }
+        auto cpm = [&](int off, const double* src, int len) { for (int i = threadIdx.x; i < g * len; i += blockDim.x) sd[off + i] = src[b0 * len + i]; };
+        cpm(L.oAv, A.Aval, zA); if (zH) cpm(L.oHv, A.Hval, zH);
+        cpm(L.oX, A.x, nV); cpm(L.oY, A.y, nV + nC); cpm(L.oG, A.g, nV); cpm(L.oLb, A.lb, nV); cpm(L.oUb, A.ub, nV);
+        cpm(L.oLbA, A.lbA, nC); cpm(L.oUbA, A.ubA, nC);
+        for (int i = threadIdx.x; i < g * nV; i += blockDim.x) st[L.oWsB + lead[s][0] + i] = gB[i];
+        for (int i = threadIdx.x; i < g * nC; i += blockDim.x) st[L.oWsC + lead[s][1] + i] = gC[i];
+        return true;
+    };
+    if (S == 2 && (long long)blockIdx.x < ngroups) manual[0] = issue(blockIdx.x, 0);
+    __syncthreads();
+    int it = 0;
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, it++) {
+        const int s = (S == 2) ? (it & 1) : 0;
+        if (S == 2) {
+            const long long next = grp + gridDim.x;
+            if (next < ngroups) manual[s ^ 1] = issue(next, s ^ 1);
+        } else {
+            manual[0] = issue(grp, 0);
+            if (manual[0]) __syncthreads();
+        }
+        if (!manual[s]) {
+            while (!mbar_try_wait(&mbar[s], phase[s])) {}
+            phase[s] ^= 1u;
+        }
+        const long long b = grp * G + warp;
+        if (b < A.batch) {
+            unsigned char* st = kraw + (size_t)s * L.stage_bytes;
+            double* sd = reinterpret_cast<double*>(st);
+            const double *av = sd + L.oAv + (size_t)warp * zA, *hv = sd + L.oHv + (size_t)warp * zH;
+            double *x = sd + L.oX + (size_t)warp * nV, *y = sd + L.oY + (size_t)warp * (nV + nC), *g = sd + L.oG + (size_t)warp * nV;
+            double *lb = sd + L.oLb + (size_t)warp * nV, *ub = sd + L.oUb + (size_t)warp * nV;
+            double *lbA = sd + L.oLbA + (size_t)warp * nC, *ubA = sd + L.oUbA + (size_t)warp * nC;
+            const signed char* sB = reinterpret_cast<const signed char*>(st + L.oWsB + lead[s][0]) + (size_t)warp * nV;
+            const signed char* sC = reinterpret_cast<const signed char*>(st + L.oWsC + lead[s][1]) + (size_t)warp * nC;
+            double *Ax = work, *ATy = Ax + nC, *Hx = ATy + nV;
+            for (int r = lane; r < nC; r += 32) {
+                double acc = 0.0;
+                const int k1 = Arp[r + 1];
+                for (int k = Arp[r]; k < k1; k++) acc = __dadd_rn(acc, __dmul_rn(av[Aperm[k]], x[Aci[k]]));
+                Ax[r] = acc;
+            }
+            for (int c = lane; c < nV; c += 32) {
+                double acc = 0.0;
+                const int e1 = Ap[c + 1];
+                for (int e = Ap[c]; e < e1; e++) acc = __dadd_rn(acc, __dmul_rn(av[e], y[nV + Ai[e]]));
+                ATy[c] = acc;
+                double hh = 0.0;
+                if (zH) {
+                    const int h1 = Hp[c + 1];
+                    for (int e = Hp[c]; e < h1; e++) hh = __dadd_rn(hh, __dmul_rn(hv[e], x[Hi[e]]));
+                }
+                Hx[c] = hh;
+            }
+            __syncwarp();
+            const double SQRT_M_EPS = 1.0e-8;
+            int* WB = A.WB ? A.WB + b * nV : nullptr;
+            int* WC = A.WC ? A.WC + b * nC : nullptr;
+            // terms, in place: lb[i], ub[i] <- primal terms; g[i] <- dual term; x[i] <- complementarity term; ATy[i] <- |gap|
+            for (int i = lane; i < nV; i += 32) {
+                const double xi = x[i], yi = y[i], lbi = lb[i], ubi = ub[i];
+                const int sb = sB[i];
+                const int W = (sb > 0) ? ((fabs(__dsub_rn(xi, lbi)) < SQRT_M_EPS) ? -99 : 1) : ((sb < 0) ? ((fabs(__dsub_rn(xi, ubi)) < SQRT_M_EPS) ? -99 : -1) : 0);
+                if (WB) WB[i] = W;
+                double gap = ATy[i];
+                gap = __dadd_rn(gap, yi);
+                gap = __dsub_rn(gap, g[i]);
+                gap = __dsub_rn(gap, Hx[i]);
+                ATy[i] = fabs(gap);
+                lb[i] = fmax(0.0, __dsub_rn(lbi, xi));
+                ub[i] = -fmin(0.0, __dsub_rn(ubi, xi));
+                g[i] = (W == 0) ? fabs(yi) : ((W == -1) ? -fmin(0.0, yi) : ((W == 1) ? fmax(0.0, yi) : 0.0));
+                x[i] = (W == 0) ? fabs(yi) : ((W == -1) ? fabs(__dmul_rn(yi, __dsub_rn(xi, lbi))) : ((W == 1) ? fabs(__dmul_rn(yi, __dsub_rn(ubi, xi))) : 0.0));
+            }
+            // constraints: lbA[i], ubA[i] <- primal terms; Ax[i] <- dual term; y[nV+i] <- complementarity term
+            for (int i = lane; i < nC; i += 32) {
+                const double ax = Ax[i], yi = y[nV + i], la = lbA[i], ua = ubA[i];
+                const int sc = sC[i];
+                const int W = (sc > 0) ? ((__dsub_rn(ax, la) < SQRT_M_EPS) ? -99 : 1) : ((sc < 0) ? ((__dsub_rn(ax, ua) < SQRT_M_EPS) ? -99 : -1) : 0);
+                if (WC) WC[i] = W;
+                lbA[i] = fmax(0.0, __dsub_rn(la, ax));
+                ubA[i] = -fmin(0.0, __dsub_rn(ua, ax));
+                Ax[i] = (W == 0) ? fabs(yi) : ((W == -1) ? -fmin(0.0, yi) : ((W == 1) ? fmax(0.0, yi) : 0.0));
+                y[nV + i] = (W == 0) ? fabs(yi) : ((W == -1) ? fabs(__dmul_rn(yi, __dsub_rn(ax, la))) : ((W == 1) ? fabs(__dmul_rn(yi, __dsub_rn(ua, ax))) : 0.0));
+            }
+            __syncwarp();
+            // lanes 0..3: one sequential sum each, in the reference's index order
+            double acc = 0.0;
+            if (lane == 0) {
+                for (int i = 0; i < nV; i++) { acc = __dadd_rn(acc, lb[i]); acc = __dadd_rn(acc, ub[i]); }
+                for (int i = 0; i < nC; i++) { acc = __dadd_rn(acc, lbA[i]); acc = __dadd_rn(acc, ubA[i]); }
+            } else if (lane == 1) {
+                for (int i = 0; i < nV; i++) acc = __dadd_rn(acc, g[i]);
+                for (int i = 0; i < nC; i++) acc = __dadd_rn(acc, Ax[i]);
+            } else if (lane == 2) {
+                for (int i = 0; i < nV; i++) acc = __dadd_rn(acc, ATy[i]);
+            } else if (lane == 3) {
+                for (int i = 0; i < nV; i++) acc = __dadd_rn(acc, x[i]);
+                for (int i = 0; i < nC; i++) acc = __dadd_rn(acc, y[nV + i]);
+            }
+            const double primal = __shfl_sync(0xffffffffu, acc, 0), dual = __shfl_sync(0xffffffffu, acc, 1);
+            const double stat = __shfl_sync(0xffffffffu, acc, 2), cmpl = __shfl_sync(0xffffffffu, acc, 3);
+            if (lane == 0) {
+                double* o = A.out + b * 5;
+                o[0] = primal; o[1] = dual; o[2] = stat; o[3] = cmpl;
+                o[4] = __dadd_rn(__dadd_rn(__dadd_rn(cmpl, stat), dual), primal);
+            }
+        }
+        __syncthreads();
+    }
 }
 
 }  // namespace sqpb200

@@ -225,7 +225,12 @@ static int run_assembly(sqpb200_handle h, cudaStream_t stream, int nmat, const i
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, stream);
-        csc_assemble_kernel<<<nmat, 256, 0, stream>>>(nmat, dseg, dncol, dcpoff, drow, dcol, dpad, dscr, dcolptr, drowidx, dorder);
+        int Pmax = 1;
+        for (int m = 0; m < nmat; m++) Pmax = std::max(Pmax, pad_off[m + 1] - pad_off[m]);
+        if (Pmax <= ASM_WARP_KEYS && nmat >= 8)  // many small matrices: one warp each, eight per CTA
+            csc_assemble_warp_kernel<<<(nmat + 7) / 8, 256, (size_t)8 * Pmax * 8, stream>>>(nmat, Pmax, dseg, dncol, dcpoff, drow, dcol, dpad, dcolptr, drowidx, dorder);
+        else
+            csc_assemble_kernel<<<nmat, 256, 0, stream>>>(nmat, dseg, dncol, dcpoff, drow, dcol, dpad, dscr, dcolptr, drowidx, dorder);
         cudaEventRecord(e1, stream);
         cudaMemcpyAsync(colptr, dcolptr, (size_t)cp_off[nmat] * 4, cudaMemcpyDeviceToHost, stream);
         cudaMemcpyAsync(rowidx, drowidx, (size_t)ztot * 4, cudaMemcpyDeviceToHost, stream);

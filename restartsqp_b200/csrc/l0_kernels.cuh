@@ -69,6 +69,49 @@ __global__ void __launch_bounds__(256) csc_assemble_kernel(int nmat, const int* 
     for (int j = clast + 1 + threadIdx.x; j <= ncol; j += blockDim.x) cp[j] = z;
 }
 
+// One warp per matrix (every padded size <= ASM_WARP_KEYS): the bitonic network runs out of the warp's own shared-memory
+// slice with warp barriers only, eight matrices per CTA.  Same keys, same outputs as csc_assemble_kernel.
+#define ASM_WARP_KEYS 512
+__global__ void __launch_bounds__(256) csc_assemble_warp_kernel(int nmat, int Pmax, const int* __restrict__ seg,
+                                                                 const int* __restrict__ ncol_arr, const int* __restrict__ cp_off,
+                                                                 const int* __restrict__ row1, const int* __restrict__ col1,
+                                                                 const int* __restrict__ pad_off, int* __restrict__ colptr,
+                                                                 int* __restrict__ rowidx, int* __restrict__ order) {
+    extern __shared__ __align__(16) uint64_t wkeys[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (m >= nmat) return;
+    uint64_t* keys = wkeys + (size_t)warp * Pmax;
+    const int z0 = seg[m], z = seg[m + 1] - z0, ncol = ncol_arr[m];
+    const int P = pad_off[m + 1] - pad_off[m];
+    int* cp = colptr + cp_off[m];
+    for (int i = lane; i < P; i += 32) keys[i] = (i < z) ? pack_key(row1[z0 + i], col1[z0 + i], i) : ~0ull;
+    __syncwarp();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < P; i += 32) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const uint64_t a = keys[i], b = keys[l];
+                    const bool up = ((i & k) == 0);
+                    if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    for (int i = lane; i < z; i += 32) {
+        const uint64_t kk = keys[i];
+        const int c = (int)(kk >> 42), r = (int)((kk >> 21) & 0x1fffff), cnt = (int)(kk & 0x1fffff);
+        rowidx[z0 + i] = r;
+        order[z0 + cnt] = i;
+        const int cprev = (i == 0) ? -1 : (int)(keys[i - 1] >> 42);
+        for (int j = cprev + 1; j <= c; j++) cp[j] = i;
+    }
+    const int clast = (z == 0) ? -1 : (int)(keys[z - 1] >> 42);
+    for (int j = clast + 1 + lane; j <= ncol; j += 32) cp[j] = z;
+}
+
 // ------------------------------------------------------------------------------------------
 // A6: value refresh.  Gather form of SpHbMat::setMatVal (src/SpHbMat.cpp:368-393):
 // out[b][k] = in[b][src[k]] for every CSC slot k whose source triplet is src[k] >= 0 (identity
@@ -80,9 +123,12 @@ __global__ void __launch_bounds__(256) scatter_values_kernel(long long total, in
                                                               double* __restrict__ out) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
+    const bool small = total < (1LL << 31);
     for (; t < total; t += stride) {
-        long long b = t / z_out;
-        int k = (int)(t - b * z_out);
+        long long b;
+        int k;
+        if (small) { const unsigned tt = (unsigned)t, bb = tt / (unsigned)z_out; b = bb; k = (int)(tt - bb * (unsigned)z_out); }
+        else { b = t / z_out; k = (int)(t - b * z_out); }
         int s = src[k];
         if (s >= 0) out[t] = broadcast ? in[s] : in[b * z_in + s];
     }
@@ -287,9 +333,12 @@ __global__ void __launch_bounds__(256) qphandler_bounds_kernel(int batch, int mo
     long long total = (long long)batch * nV;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
+    const bool small = total < (1LL << 31);  // 32-bit index arithmetic when it fits (64-bit division is emulated)
     for (; t < total; t += stride) {
-        long long b = t / nV;
-        int i = (int)(t - b * nV);
+        long long b;
+        int i;
+        if (small) { const unsigned tt = (unsigned)t, bb = tt / (unsigned)nV; b = bb; i = (int)(tt - bb * (unsigned)nV); }
+        else { b = t / nV; i = (int)(t - b * nV); }
         if (i < n) {
             double d = delta[b];
             double lo = x_l[b * n + i] - x_k[b * n + i], hi = x_u[b * n + i] - x_k[b * n + i];
@@ -313,9 +362,12 @@ __global__ void __launch_bounds__(256) qphandler_g_kernel(int batch, int n, int 
     long long total = (long long)batch * nV;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
+    const bool small = total < (1LL << 31);
     for (; t < total; t += stride) {
-        long long b = t / nV;
-        int i = (int)(t - b * nV);
+        long long b;
+        int i;
+        if (small) { const unsigned tt = (unsigned)t, bb = tt / (unsigned)nV; b = bb; i = (int)(tt - bb * (unsigned)nV); }
+        else { b = t / nV; i = (int)(t - b * nV); }
         if (i < n) { if (grad) g[t] = grad[b * n + i]; }
         else if (rho) g[t] = rho[b];
     }

@@ -139,3 +139,30 @@ def test_scalar_setters_and_reset(gpu_lib):
     s.reset_constraints()
     assert not s.getLb().any() and not s.getLbA().any()
     s.close()
+
+
+def test_batched_assembly_many_small_matrices_warp_kernel(gpu_lib):
+    """Many small ragged matrices (padded size <= 512): the one-warp-per-matrix kernel; same index arrays as the reference."""
+    rng = np.random.default_rng(12)
+    mats, seg, ncols, rows, cols = [], [0], [], [], []
+    for k in range(61):
+        nr, nc = int(rng.integers(1, 30)), int(rng.integers(1, 40))
+        z = int(rng.integers(0, min(nr * nc, 400) + 1)) if k % 7 else 0
+        flat = rng.choice(nr * nc, size=z, replace=False) if z else np.zeros(0, np.int64)
+        rr, cc = (flat // nc + 1).astype(np.int32), (flat % nc + 1).astype(np.int32)
+        mats.append((nr, nc, rr, cc))
+        rows.append(rr); cols.append(cc); ncols.append(nc); seg.append(seg[-1] + z)
+    seg, ncols = np.array(seg, np.int32), np.array(ncols, np.int32)
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    colptr = np.zeros(int((ncols + 1).sum()), np.int32)
+    rowidx, order = np.zeros(max(len(rows), 1), np.int32), np.zeros(max(len(rows), 1), np.int32)
+    ms = C.c_float(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert gpu_lib.sqpb200_assemble_csc_batched(0, len(mats), p(seg), p(ncols), p(rows), p(cols), p(colptr), p(rowidx), p(order), C.byref(ms)) == 0
+    off = 0
+    for k, (nr, nc, rr, cc) in enumerate(mats):
+        cp, ri, _, od = orc.csc_from_entries(nc, rr, cc, np.zeros(len(rr)))
+        assert colptr[off:off + nc + 1].tolist() == cp.tolist()
+        assert rowidx[seg[k]:seg[k + 1]].tolist() == ri.tolist()
+        assert order[seg[k]:seg[k + 1]].tolist() == od.tolist()
+        off += nc + 1

@@ -59,15 +59,15 @@ class DeviceBatchedSQP:
         u8 = lambda: torch.zeros(B, dtype=torch.uint8, device=self.dev)
         up = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(self.dev)
         xl, xu, cl, cu = nlp.Get_bounds_info()
-        XL, XU = np.tile(xl, (B, 1)), np.tile(xu, (B, 1))
-        CL, CU = np.tile(cl, (B, 1)).reshape(B, m), np.tile(cu, (B, 1)).reshape(B, m)
+        # bounds, constraint classes and multipliers are the same for every instance: upload one row, replicate on the device
+        rep = lambda a, dt=torch.float64: up(np.asarray(a).reshape(1, -1), dt).repeat(B, 1).contiguous()
         T = self.T = {}
-        T["x_l"], T["x_u"], T["c_l"], T["c_u"] = up(XL), up(XU), up(CL), up(CU)
-        T["bound_type"] = up(classify_single_constraint(XL, XU), torch.int32)
-        T["cons_type"] = up(classify_single_constraint(CL, CU), torch.int32)
+        T["x_l"], T["x_u"], T["c_l"], T["c_u"] = rep(xl), rep(xu), rep(cl), rep(cu)
+        T["bound_type"] = rep(classify_single_constraint(np.atleast_2d(xl), np.atleast_2d(xu)), torch.int32)
+        T["cons_type"] = rep(classify_single_constraint(np.atleast_2d(cl).reshape(1, m), np.atleast_2d(cu).reshape(1, m)), torch.int32)
         T["J_row1"], T["J_col1"] = up(nlp.J_row1, torch.int32), up(nlp.J_col1, torch.int32)
-        T["x_k"] = up(np.minimum(np.maximum(x0, XL), XU))  # shift_starting_point, src/SQPTNLP.cpp:140-153
-        T["lam_c"] = up(np.tile(np.asarray(lam_start, dtype=np.float64), (B, 1)).reshape(B, m))
+        T["x_k"] = torch.minimum(torch.maximum(up(x0), T["x_l"]), T["x_u"])  # shift_starting_point, src/SQPTNLP.cpp:140-153
+        T["lam_c"] = rep(np.asarray(lam_start, dtype=np.float64).reshape(1, m))
         T["neg_lam"] = -T["lam_c"]
         for k, shp in (("c_k", (B, m)), ("f_k", (B,)), ("grad", (B, n)), ("jac", (B, zJ)), ("hess", (B, zH)), ("lam_x", (B, n)),
                        ("infea", (B,)), ("p_k", (B, n)), ("x_trial", (B, n)), ("c_trial", (B, m)), ("f_trial", (B,)), ("infea_trial", (B,)),

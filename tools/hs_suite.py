@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--backend", default="cuda"); ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--only", default=""); ap.add_argument("--iter-max", type=int, default=300)
+    ap.add_argument("--loop", default="host", choices=["host", "device"], help="device: DeviceNLP + DeviceBatchedSQP (iterates stay on the GPU)")
     a = ap.parse_args()
     files = sorted(glob.glob(os.path.join(R, "tests", "golden", "hs_nl", "hs*.nl")))
     only = set(a.only.split(",")) if a.only else None
@@ -39,10 +40,24 @@ def main():
         if a.backend == "oracle":
             from oracle_backend import OracleQPInterface
             mk = lambda info, qptype: r.QPhandler(info, qptype, opt, batch=a.batch, backend=OracleQPInterface(info, qptype, opt, batch=a.batch), refresh_ubA=True)
+        tc = 0.0
+        if a.loop == "device":
+            from restartsqp_b200.nl_reader import DeviceNLP
+            from restartsqp_b200.sqp_device import DeviceBatchedSQP
+            try:
+                t0 = time.time(); dnlp = DeviceNLP(nlp); tc = time.time() - t0
+            except ValueError as e:
+                print(f"{name:10s} n={nlp.n:3d} m={nlp.m:3d} skipped (device evaluator): {str(e)[:90]}"); continue
+        X = starts(nlp, a.batch, k)
         t0 = time.time()
         try:
-            alg = BatchedSQP(nlp, x0=starts(nlp, a.batch, k), options=opt, make_handler=mk)
-            res = alg.Optimize()
+            if a.loop == "device":
+                alg = DeviceBatchedSQP(dnlp, x0=X, options=opt)
+                res = alg.Optimize()
+                alg.close(); dnlp.close()
+            else:
+                alg = BatchedSQP(nlp, x0=X, options=opt, make_handler=mk)
+                res = alg.Optimize()
         except Exception as e:
             print(f"{name:10s} n={nlp.n:3d} m={nlp.m:3d} ERROR {type(e).__name__}: {str(e)[:100]}"); continue
         dt = time.time() - t0
@@ -50,7 +65,7 @@ def main():
         nopt = int((res.exitflag == int(r.Exitflag.OPTIMAL)).sum())
         tot["inst"] += a.batch; tot["opt"] += nopt; tot["t"] += dt
         print(f"{name:10s} n={nlp.n:3d} m={nlp.m:3d} optimal {nopt}/{a.batch} flags={dict(zip(fl.tolist(), cnt.tolist()))} "
-              f"iters mean={res.iters.mean():.1f} qp_iter mean={res.qp_iter.mean():.1f} f[0]={res.obj[0]:.6g} {dt:.2f}s", flush=True)
+              f"iters mean={res.iters.mean():.1f} qp_iter mean={res.qp_iter.mean():.1f} f[0]={res.obj[0]:.6g} {dt:.3f}s {a.batch / dt:.0f} solves/s nvrtc {tc:.1f}s", flush=True)
     print(f"TOTAL optimal {tot['opt']}/{tot['inst']} in {tot['t']:.1f}s")
 
 

@@ -17,7 +17,8 @@ LIB = os.path.join(LIBDIR, "libsqpb200.so")
 OBJDIR = os.path.join(HERE, "build")
 HEADERS = [os.path.join(CSRC, f) for f in ("qp_kernel.cuh", "l0_kernels.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "sqpb200.h")]
-TEAMS = [(32, 128), (32, 64), (32, 32)]  # (threads per QP, threads per CTA): one warp per QP, 4/2/1 QPs per CTA
+# (threads per QP, threads per CTA, warps per SM the registers are capped for): one warp per QP, 4/2/1 QPs per CTA
+TEAMS = [(32, 128, 16), (32, 64, 16), (32, 32, 16), (32, 128, 32)]
 LARGE_CTA = int(os.environ.get("SQPB200_LARGE_CTA", "512"))  # threads of the one-QP-per-CTA kernel (large QPs)
 QP_EXTRA_FLAGS = os.environ.get("SQPB200_QP_FLAGS", "").split()
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
@@ -33,10 +34,10 @@ def _units():
     units = [(os.path.join(CSRC, "capi.cu"), os.path.join(OBJDIR, "capi.o"), []),
              (os.path.join(CSRC, "nlp_eval.cu"), os.path.join(OBJDIR, "nlp_eval.o"), []),
              (os.path.join(CSRC, "sqp_outer.cu"), os.path.join(OBJDIR, "sqp_outer.o"), [])]
-    for team, cta in TEAMS:
+    for team, cta, wps in TEAMS:
         # multi-warp teams are compiled fully inlined (see the QP_INLINE_ALL note in qp_kernel.cuh)
-        units.append((os.path.join(CSRC, "qp_solve_inst.cu"), os.path.join(OBJDIR, "qp_solve_%d_%d.o" % (team, cta)),
-                      ["-DQP_TEAM=%d" % team, "-DQP_CTA=%d" % cta] + QP_EXTRA_FLAGS))
+        units.append((os.path.join(CSRC, "qp_solve_inst.cu"), os.path.join(OBJDIR, "qp_solve_%d_%d_w%d.o" % (team, cta, wps)),
+                      ["-DQP_TEAM=%d" % team, "-DQP_CTA=%d" % cta, "-DQP_WPS=%d" % wps] + QP_EXTRA_FLAGS))
     units.append((os.path.join(CSRC, "qp_solve_large_inst.cu"), os.path.join(OBJDIR, "qp_solve_large.o"),
                   ["-DQP_CTA=%d" % LARGE_CTA] + QP_EXTRA_FLAGS))
     return units

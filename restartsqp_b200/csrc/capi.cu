@@ -619,9 +619,10 @@ static int choose_config(sqpb200_handle h) {
 
 // one object file per CTA size (qp_solve_inst.cu)
 namespace sqpb200 {
-cudaError_t launch_qp_solve_32_128(const QPKernelArgs&, int, cudaStream_t);
-cudaError_t launch_qp_solve_32_64(const QPKernelArgs&, int, cudaStream_t);
-cudaError_t launch_qp_solve_32_32(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_32_128_w16(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_32_128_w32(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_32_64_w16(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_32_32_w16(const QPKernelArgs&, int, cudaStream_t);
 cudaError_t launch_qp_solve_large(const QPKernelArgs&, cudaStream_t);
 int qp_solve_large_threads();
 }
@@ -654,9 +655,10 @@ static int prepare_large(sqpb200_handle h, const QPKernelArgs& a) {
 }
 static cudaError_t launch_cfg(const SolveCfg& cfg, const QPKernelArgs& a, cudaStream_t stream) {
     switch (cfg.teams) {
-    case 4: return launch_qp_solve_32_128(a, cfg.smem, stream);
-    case 2: return launch_qp_solve_32_64(a, cfg.smem, stream);
-    default: return launch_qp_solve_32_32(a, cfg.smem, stream);
+    // 4 QPs per CTA and shared memory allows >= 32 resident warps: the 64-register build (see qp_kernel.cuh)
+    case 4: return cfg.resident >= 32 ? launch_qp_solve_32_128_w32(a, cfg.smem, stream) : launch_qp_solve_32_128_w16(a, cfg.smem, stream);
+    case 2: return launch_qp_solve_32_64_w16(a, cfg.smem, stream);
+    default: return launch_qp_solve_32_32_w16(a, cfg.smem, stream);
     }
 }
 

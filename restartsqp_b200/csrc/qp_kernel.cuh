@@ -1267,10 +1267,11 @@ struct QPT {
 // -------------------------------------------------------------------------------------------
 // kernel: one QP per warp, CTA_THREADS/32 QPs per CTA
 // -------------------------------------------------------------------------------------------
-// 512 / CTA_THREADS resident CTAs = 16 warps per SM = at most 128 registers per thread (measured: 64 or 80 registers
-// spill and lose on the larger QPs, 142 registers lose occupancy on the small ones).
-template <int CTA_THREADS>
-__global__ void __launch_bounds__(CTA_THREADS, 512 / CTA_THREADS) qp_solve_kernel(const __grid_constant__ QPKernelArgs A) {
+// WPS = warps per SM the register allocation is capped for: 16 (<= 128 registers; measured: 20 or 24 warps lose everywhere) or
+// 32 (<= 64 registers, a few spills): 15-20 % faster on QPs small enough that shared memory lets 32 warps be resident
+// (nV <~ 20), slower on the larger ones where shared memory caps the occupancy anyway -- capi.cu picks per problem size.
+template <int CTA_THREADS, int WPS>
+__global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solve_kernel(const __grid_constant__ QPKernelArgs A) {
     constexpr int TEAMS = CTA_THREADS / 32;
     // stage the launch arguments and the 16-bit pattern once per CTA
     {

@@ -166,3 +166,26 @@ def test_batched_assembly_many_small_matrices_warp_kernel(gpu_lib):
         assert rowidx[seg[k]:seg[k + 1]].tolist() == ri.tolist()
         assert order[seg[k]:seg[k + 1]].tolist() == od.tolist()
         off += nc + 1
+
+
+def test_assembly_with_duplicate_triplets(gpu_lib):
+    """SURVEY.md 8a quirk 4 (collisions): with duplicate (row, col) triplets ColIndex / RowIndex are those of the reference under
+    any tie-break; `order` is the stable one (ties by the original counter), as the oracle and the golden vectors have it."""
+    rng = np.random.default_rng(40)
+    nr, nc, z = 3, 3, 40
+    rr, cc = rng.integers(1, nr + 1, z).astype(np.int32), rng.integers(1, nc + 1, z).astype(np.int32)
+    mats = [(nr, nc, rr, cc)] * 9  # nine copies: exercises the one-warp-per-matrix kernel as well
+    seg = (np.arange(10) * z).astype(np.int32); ncols = np.full(9, nc, np.int32)
+    rows, cols = np.tile(rr, 9), np.tile(cc, 9)
+    colptr, rowidx, order = np.zeros(9 * (nc + 1), np.int32), np.zeros(9 * z, np.int32), np.zeros(9 * z, np.int32)
+    ms = C.c_float(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert gpu_lib.sqpb200_assemble_csc_batched(0, 9, p(seg), p(ncols), p(rows), p(cols), p(colptr), p(rowidx), p(order), C.byref(ms)) == 0
+    cp, ri, _, od = orc.csc_from_entries(nc, rr, cc, np.zeros(z))
+    for k in range(9):
+        assert colptr[k * (nc + 1):(k + 1) * (nc + 1)].tolist() == cp.tolist()
+        assert rowidx[k * z:(k + 1) * z].tolist() == ri.tolist()
+        assert order[k * z:(k + 1) * z].tolist() == od.tolist()
+    # single-matrix path (one CTA per matrix)
+    assert gpu_lib.sqpb200_assemble_csc_batched(0, 1, p(seg[:2].copy()), p(ncols[:1].copy()), p(rr), p(cc), p(colptr), p(rowidx), p(order), C.byref(ms)) == 0
+    assert colptr[:nc + 1].tolist() == cp.tolist() and rowidx[:z].tolist() == ri.tolist() and order[:z].tolist() == od.tolist()

@@ -344,3 +344,38 @@ def test_synthetic_large_config4(gpu_lib, n, B, checked):
         o = H.oracle_solve(orc, p, Acsc=d["Ac"], Hcsc=d["Hc"], max_iter=100000)
         check_against_oracle(s, b, o, nV)
     s.close()
+
+
+def _dense_case(nV, nC, Hd, A, g, lb, ub, lbA, ubA):
+    return dict(nV=nV, nC=nC, H=np.asarray(Hd, float), A=np.asarray(A, float).reshape(nC, nV), g=np.asarray(g, float), lb=np.asarray(lb, float),
+                ub=np.asarray(ub, float), lbA=np.asarray(lbA, float), ubA=np.asarray(ubA, float))
+
+
+GENERIC_CASES = {
+    # x0 + x1 >= 10 with 0 <= x <= 1
+    "infeasible_bounds_vs_constraint": (_dense_case(2, 1, np.eye(2), [[1, 1]], [1, -1], [0, 0], [1, 1], [10], [1e18]), False, 22),
+    # x0 >= 1 and x0 <= -1
+    "infeasible_contradicting_rows": (_dense_case(2, 2, np.eye(2), [[1, 0], [1, 0]], [1, -1], [-5, -5], [5, 5], [1, -1e18], [1e18, -1]), False, 22),
+    # indefinite H, "infinite" bounds of the reference (INF = 1e18 < qpOASES's 1e20: an ordinary finite bound)
+    "indefinite_runs_to_the_1e18_bound": (_dense_case(2, 1, [[1, 0], [0, -1]], [[1, 1]], [0, 1], [-1e18] * 2, [1e18] * 2, [-1e18], [1e18]), False, 20),
+    # LP without a finite minimiser: the eps-regularised problem has one
+    "lp_unbounded_direction_regularised": (_dense_case(2, 1, np.zeros((2, 2)), [[1, 1]], [-1, 0], [0, 0], [1e18] * 2, [-1e18], [1e18]), True, 20),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GENERIC_CASES))
+@pytest.mark.parametrize("team", [0, 1024])
+def test_infeasible_and_unbounded_qps_match_oracle(gpu_lib, name, team):
+    """QPs outside the l1-penalty family: the Exitflag the backend must report (include/sqphot/Types.hpp:60-70, infeasible = 22)
+    and the iterate it stops at, against the oracle, on both kernels."""
+    p, is_lp, expect = GENERIC_CASES[name]
+    nV, nC, B = p["nV"], p["nC"], 3
+    Ac, Hc = H.csc(p["A"]), H.csc(p["H"] if not is_lp else np.zeros((nV, nV)))
+    t = lambda v: np.ascontiguousarray(np.tile(v, (B, 1)))
+    s = solve_batch_csc(nV, nC, Ac, None if is_lp else Hc, t(p["g"]), t(p["lb"]), t(p["ub"]), t(p["lbA"]), t(p["ubA"]),
+                        qptype=r.QPType.LP if is_lp else r.QPType.QP, team_size=team)
+    o = H.oracle_solve(orc, p, is_lp=is_lp, max_iter=100 if is_lp else 1000, Acsc=Ac, Hcsc=None if is_lp else Hc)
+    assert o["status"] == expect
+    for b in range(B):
+        check_against_oracle(s, b, o, nV, strict=(expect == 20))
+    s.close()

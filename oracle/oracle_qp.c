@@ -150,6 +150,16 @@ static void build_dense_A(orc_qp* q) {
         for (int e = q->Ap[c]; e < q->Ap[c + 1]; e++) q->Ad[(size_t)q->Ai[e] * q->nV + c] += q->Av[e];
 }
 
+/* Quotient x / d from the reciprocal ri = 1/d (formed ahead of a substitution loop, in parallel on the GPU) with one
+ * Newton correction: q0 = x*ri, r = x - q0*d (exact, fused), q = q0 + r*ri.  Three dependent operations instead of a full
+ * division on the critical path; the result is the correctly rounded quotient except in rare double-rounding cases.
+ * (A bare x*ri is not accurate enough: on the rho = 1e8 scaled dumps the homotopy then needs 3x the iterations.) */
+static inline double quot(double x, double d, double ri) {
+    double q0 = x * ri;
+    double r = fma(-q0, d, x);
+    return fma(r, ri, q0);
+}
+
 /* ------------------------------------------------------------ Givens helpers */
 /* rotation G with [a b] G = [0 r]:  a' = c a - s b,  b' = s a + c b */
 static void givens(double a, double b, double* c, double* s, double* r) {
@@ -244,7 +254,7 @@ static int extend_R(orc_qp* q, int check_curvature) {
     for (int i = 0; i < b; i++) {
         double s = q->w[i];
         for (int k = 0; k < i; k++) s -= R[(size_t)k * nV + i] * R[(size_t)k * nV + b];
-        R[(size_t)i * nV + b] = s / R[(size_t)i * nV + i];
+        { double piv = R[(size_t)i * nV + i]; R[(size_t)i * nV + b] = quot(s, piv, 1.0 / piv); }
     }
     double rho2 = q->w[b];
     for (int k = 0; k < b; k++) rho2 -= R[(size_t)k * nV + b] * R[(size_t)k * nV + b];
@@ -356,7 +366,7 @@ static void solve_T(const orc_qp* q, const double* b, double* v) {
         int d = nFR - 1 - i;
         double s = b[i];
         for (int j = nFR - 1; j > d; j--) s -= q->T[(size_t)i * nV + j] * v[j];
-        v[d] = s / q->T[(size_t)i * nV + d];
+        { double piv = q->T[(size_t)i * nV + d]; v[d] = quot(s, piv, 1.0 / piv); } /* pivot reciprocals are formed ahead of the substitution */
     }
 }
 /* T' u = r, r indexed by Q column, u by AC position */
@@ -366,7 +376,7 @@ static void solve_Tt(const orc_qp* q, const double* r, double* u) {
         int d = nFR - 1 - i;
         double s = r[d];
         for (int k = nAC - 1; k > i; k--) s -= q->T[(size_t)k * nV + d] * u[k];
-        u[i] = s / q->T[(size_t)i * nV + d];
+        { double piv = q->T[(size_t)i * nV + d]; u[i] = quot(s, piv, 1.0 / piv); }
     }
 }
 
@@ -401,12 +411,12 @@ static void step_direction(orc_qp* q, const double* dgv, const double* dxFX_full
         for (int i = 0; i < nZ; i++) {
             double s = q->zv[i];
             for (int k = 0; k < i; k++) s -= q->R[(size_t)k * nV + i] * q->zv[k];
-            q->zv[i] = s / q->R[(size_t)i * nV + i];
+            { double piv = q->R[(size_t)i * nV + i]; q->zv[i] = quot(s, piv, 1.0 / piv); }
         }
         for (int i = nZ - 1; i >= 0; i--) {
             double s = q->zv[i];
             for (int k = nZ - 1; k > i; k--) s -= q->R[(size_t)i * nV + k] * q->zv[k];
-            q->zv[i] = s / q->R[(size_t)i * nV + i];
+            { double piv = q->R[(size_t)i * nV + i]; q->zv[i] = quot(s, piv, 1.0 / piv); }
         }
         for (int p = 0; p < nFR; p++) {
             double s = 0.0;

@@ -129,6 +129,15 @@ struct MinKey {
 };
 __device__ __forceinline__ bool key_less(double t1, int p1, double t2, int p2) { return t1 < t2 || (t1 == t2 && p1 < p2); }
 
+// x / d from the reciprocal ri = 1/d (formed in parallel ahead of a substitution chain) with one Newton correction: three
+// dependent operations on the critical path instead of a full division.  Same sequence as the oracle's quot(); a bare x*ri is
+// not accurate enough (the rho = 1e8 scaled dumps then need 3x the iterations).
+__device__ __forceinline__ double quot(double x, double d, double ri) {
+    const double q0 = x * ri;
+    const double r = __fma_rn(-q0, d, x);
+    return __fma_rn(r, ri, q0);
+}
+
 #define QP_FN __noinline__
 
 // TEAM = threads that cooperate on one QP.  32: one warp per QP, everything in the warp's shared-memory slice, pattern
@@ -478,8 +487,9 @@ struct QPT {
             SYNC();
             if (lane < 32) {
                 double zi = (l < nb) ? z[i0 + l] : 0.0;
+                const double ri = (l < nb) ? 1.0 / Ds[l][l] : 0.0;  // pivot reciprocals in parallel; the chain only multiplies
                 _Pragma("unroll 1") for (int k = 0; k < nb; k++) {
-                    const double uk = __shfl_sync(0xffffffffu, zi, k) / Ds[k][k];
+                    const double uk = quot(__shfl_sync(0xffffffffu, zi, k), Ds[k][k], __shfl_sync(0xffffffffu, ri, k));
                     if (l == k) zi = uk;
                     else if (l > k && l < nb) zi -= Ds[k][l] * uk;
                 }
@@ -506,8 +516,9 @@ struct QPT {
             SYNC();
             if (lane < 32) {
                 double zi = (l < nb) ? z[i0 + l] : 0.0;
+                const double ri = (l < nb) ? 1.0 / Ds[l][l] : 0.0;
                 _Pragma("unroll 1") for (int k = nb - 1; k >= 0; k--) {
-                    const double zk = __shfl_sync(0xffffffffu, zi, k) / Ds[k][k];
+                    const double zk = quot(__shfl_sync(0xffffffffu, zi, k), Ds[k][k], __shfl_sync(0xffffffffu, ri, k));
                     if (l == k) zi = zk;
                     else if (l < k) zi -= Ds[l][k] * zk;
                 }
@@ -544,12 +555,17 @@ struct QPT {
         SYNC();
         // r = R'^{-1} w[0..b): forward substitution, column oriented
         if constexpr (TEAM > 32) fwd_solve_R_blocked(w, b, b);
-        else _Pragma("unroll 1") for (int k = 0; k < b; k++) {
-            double rk = w[k] / R_(k, k);
+        else {
+        double* rinv = V_(dy);  // dead between two homotopy steps
+        _Pragma("unroll 1") for (int k = lane; k < b; k += TEAM) rinv[k] = 1.0 / R_(k, k);
+        SYNC();
+        _Pragma("unroll 1") for (int k = 0; k < b; k++) {
+            double rk = quot(w[k], R_(k, k), rinv[k]);
             SYNC();
             if (lane == 0) R_(k, b) = rk;
             _Pragma("unroll 1") for (int i = k + 1 + lane; i < b; i += TEAM) w[i] -= R_(k, i) * rk;
             SYNC();
+        }
         }
         double rho2 = w[b];
         DOT_UNROLL for (int k = 0; k < b; k++) rho2 -= R_(k, b) * R_(k, b);
@@ -765,9 +781,12 @@ struct QPT {
         QP_CTX
         const int nFR = hdr[0], nAC = hdr[1];
         const double* RT = V_(RT);
+        double* rinv = V_(dAx);  // pivot reciprocals, one per lane in parallel: the sequential part below only multiplies
+        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) rinv[i] = 1.0 / T_(i, nFR - 1 - i);
+        SYNC();
         _Pragma("unroll 1") for (int i = 0; i < nAC; i++) {
             int d = nFR - 1 - i;
-            double vi = b[i] / T_(i, d);
+            double vi = quot(b[i], T_(i, d), rinv[i]);
             SYNC();
             if (lane == 0) v[d] = vi;
             _Pragma("unroll 1") for (int k = i + 1 + lane; k < nAC; k += TEAM) b[k] -= T_(k, d) * vi;
@@ -779,9 +798,12 @@ struct QPT {
         QP_CTX
         const int nFR = hdr[0], nAC = hdr[1];
         const double* RT = V_(RT);
+        double* rinv = V_(dAx);
+        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) rinv[i] = 1.0 / T_(i, nFR - 1 - i);
+        SYNC();
         _Pragma("unroll 1") for (int i = nAC - 1; i >= 0; i--) {
             int d = nFR - 1 - i;
-            double ui = r[d] / T_(i, d);
+            double ui = quot(r[d], T_(i, d), rinv[i]);
             SYNC();
             if (lane == 0) u[i] = ui;
             _Pragma("unroll 1") for (int k = lane; k < i; k += TEAM) { int dk = nFR - 1 - k; r[dk] -= T_(i, dk) * ui; }
@@ -825,15 +847,18 @@ struct QPT {
                 fwd_solve_R_blocked(zv, nZ, -1);
                 bwd_solve_R_blocked(zv, nZ);
             } else {
+                double* rinv = V_(dy);  // dy is dead here (rewritten below)
+                _Pragma("unroll 1") for (int k = lane; k < nZ; k += TEAM) rinv[k] = 1.0 / R_(k, k);
+                SYNC();
                 _Pragma("unroll 1") for (int k = 0; k < nZ; k++) {
-                    double uk = zv[k] / R_(k, k);
+                    double uk = quot(zv[k], R_(k, k), rinv[k]);
                     SYNC();
                     if (lane == 0) zv[k] = uk;
                     _Pragma("unroll 1") for (int i = k + 1 + lane; i < nZ; i += TEAM) zv[i] -= R_(k, i) * uk;
                     SYNC();
                 }
                 _Pragma("unroll 1") for (int k = nZ - 1; k >= 0; k--) {
-                    double zk = zv[k] / R_(k, k);
+                    double zk = quot(zv[k], R_(k, k), rinv[k]);
                     SYNC();
                     if (lane == 0) zv[k] = zk;
                     _Pragma("unroll 1") for (int i = lane; i < k; i += TEAM) zv[i] -= R_(i, k) * zk;

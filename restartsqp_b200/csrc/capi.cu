@@ -564,7 +564,9 @@ static bool config_for_cap(sqpb200_handle h, int cap, SolveCfg& cfg) {
     const size_t SMEM_MAX = 227 * 1024, SMEM_SM = 228 * 1024;
     int best_teams = 0;
     size_t best_res = 0;
+    const char* force = getenv("SQPB200_QPS_PER_CTA");  // experiment knob: force 1, 2 or 4 QPs per CTA
     for (int teams = 4; teams >= 1; teams >>= 1) {
+        if (force && atoi(force) != teams) continue;
         size_t smem = (size_t)teams * slice_bytes + pat_bytes;
         if (smem > SMEM_MAX) continue;
         size_t ctas = SMEM_SM / (smem + 1024 + 512);  // 1 KiB per CTA reserved by the driver + the static argument copy

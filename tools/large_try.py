@@ -6,9 +6,9 @@ from restartsqp_b200 import capi
 from oracle import oracle_py as orc
 import helpers as H
 
-def run(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA, team, label, check=True):
+def run(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA, team, label, check=True, maxiter=1000):
     B = g.shape[0]
-    s = r.CudaQPInterface(nV=nV, nC=nC, qptype=r.QPType.QP, batch=B, team_size=team)
+    s = r.CudaQPInterface(nV=nV, nC=nC, qptype=r.QPType.QP, batch=B, team_size=team, options=r.Options(qp_maxiter=maxiter))
     s.set_csc(capi.MAT_A, *Ac); s.set_csc(capi.MAT_H, *Hc)
     s.set_g(g); s.set_lb(lb); s.set_ub(ub)
     if nC: s.set_lbA(lbA); s.set_ubA(ubA)
@@ -21,7 +21,7 @@ def run(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA, team, label, check=True):
         t0 = time.time()
         for b in range(min(B, check if isinstance(check, int) else B)):
             p = dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b])
-            o = H.oracle_solve(orc, p, Acsc=Ac, Hcsc=Hc, max_iter=100000)
+            o = H.oracle_solve(orc, p, Acsc=Ac, Hcsc=Hc, max_iter=maxiter)
             same = (st[b] == o["status"] and it[b] == o["iters"] and (wb[b] == o["wb"]).all() and (wc[b] == o["wc"]).all())
             err = np.abs(x[b] - o["x"]).max()
             if not same or err > 1e-8: bad += 1; print("  MISMATCH b=%d gpu(st=%d it=%d) oracle(st=%d it=%d) err=%g" % (b, st[b], it[b], o["status"], o["iters"], err))
@@ -43,4 +43,4 @@ if which == "small":
 else:
     n = int(which); B = int(sys.argv[2]) if len(sys.argv) > 2 else 8; chk = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     d = H.synthetic_large_qp(n, batch=B)
-    run(d["nV"], d["nC"], d["Ac"], d["Hc"], d["g"], d["lb"], d["ub"], d["lbA"], d["ubA"], 0, f"config4 n={n}", check=chk)
+    run(d["nV"], d["nC"], d["Ac"], d["Hc"], d["g"], d["lb"], d["ub"], d["lbA"], d["ubA"], 0, f"config4 n={n}", check=chk, maxiter=max(1000, 6 * n))

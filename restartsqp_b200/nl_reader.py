@@ -590,7 +590,7 @@ class DeviceNLP:
     (Eval_f_c for trial points, Eval_all for accepted points).  There is no CPU fallback: constructing it without a CUDA
     device raises."""
 
-    MAX_NODES = 8000  # NVRTC time grows faster than linearly with the length of the straight-line kernel (hs105: 20 k nodes, 47 s)
+    MAX_NODES = 12000  # NVRTC time grows faster than linearly with the length of the straight-line kernel (hs105: 20 k nodes, 47 s)
 
     def __init__(self, path, device=0, max_nodes=None):
         import ctypes as C

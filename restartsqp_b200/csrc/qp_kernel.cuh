@@ -1214,7 +1214,10 @@ struct QPT {
     static __device__ QP_FN void epilogue(int b, int status, int total_iters) {
         QP_CTX
         const int nT = nV + nC;
-        double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *t1 = V_(t1), *t2 = V_(t2);
+        // A x of the KKT test goes to the dead dAx buffer: the solver's own Ax (advanced incrementally by the homotopy) is part
+        // of the hot-start state and must stay what the oracle keeps, or a later hotstart(g, lb, ub, lbA, ubA) starts its
+        // ratio tests from a value that differs in the last bits
+        double *x = V_(x), *y = V_(y), *Ax = V_(dAx), *t1 = V_(t1), *t2 = V_(t2);
         const double *gN = V_(gN), *lbN = V_(lbN), *ubN = V_(ubN), *lbAN = V_(lbAN), *ubAN = V_(ubAN);
         const short *sB = sB_, *sC = sC_;
         double* xo = sA.x + (size_t)b * nV;

@@ -379,3 +379,36 @@ def test_infeasible_and_unbounded_qps_match_oracle(gpu_lib, name, team):
     for b in range(B):
         check_against_oracle(s, b, o, nV, strict=(expect == 20))
     s.close()
+
+
+@pytest.mark.parametrize("team", [0, 1024])
+def test_hotstart_state_is_bitwise_the_oracles(gpu_lib, team):
+    """Regression: the KKT epilogue must not touch the solver's own Ax (part of the hot-start state).  A chain of
+    hotstart(g, lb, ub, lbA, ubA) calls on fixed matrices has to stay bit-identical with the oracle, not just within 1e-8."""
+    rng = np.random.default_rng(2024)
+    n, m, B = 7, 6, 16
+    base = H.random_l1_qp(rng, n, m, convex=True, dens=0.8)
+    nV, nC = base["nV"], base["nC"]
+    Ac, Hc = H.csc(base["A"]), H.csc(base["H"])
+    g = np.tile(base["g"], (B, 1)); g[:, :n] += rng.standard_normal((B, n))
+    t = lambda v: np.ascontiguousarray(np.tile(v, (B, 1)))
+    lb, ub, lbA, ubA = t(base["lb"]), t(base["ub"]), t(base["lbA"]), t(base["ubA"])
+    s = solve_batch_csc(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA, team_size=team)
+    solvers = []
+    for b in range(B):
+        o = H.oracle_solve(orc, dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b]), Acsc=Ac, Hcsc=Hc)
+        solvers.append(o["solver"])
+    for rnd in range(4):
+        g = g.copy(); g[:, :n] += 0.4 * rng.standard_normal((B, n))
+        lbA = np.where(lbA > -1e17, lbA + 0.1 * rng.standard_normal((B, m)), lbA)
+        ubA = np.maximum(ubA, lbA)
+        s.set_g(g); s.set_lbA(lbA); s.set_ubA(ubA)
+        s.optimizeQP()
+        x, it = s.get_optimal_solution(), s.get_iterations()
+        yb, yc = s.get_multipliers_bounds(), s.get_multipliers_constr()
+        for b in range(B):
+            st = solvers[b].hotstart(g[b], lb[b], ub[b], lbA[b], ubA[b])
+            xo, yo, _, ito = solvers[b].solution()
+            assert st == int(s.get_status()[b]) and ito == int(it[b])
+            assert np.array_equal(x[b], xo) and np.array_equal(np.concatenate([yb[b], yc[b]]), yo), (rnd, b)
+    s.close()

@@ -411,7 +411,10 @@ static int set_values(sqpb200_handle h, int which, const double* vals, int loc, 
     if (isA ? !h->A_set : !h->H_set) { h->err = "structure not set"; return SQPB200_ERR_STATE; }
     int z_out = isA ? h->zA : h->zH;
     int z_in = csc_order ? z_out : (isA ? h->zJ : h->zHt);
-    if (z_out == 0 || z_in == 0) return 0;
+    if (z_out == 0 || z_in == 0) {  // empty matrix: nothing to copy, but the call still raises Update_A / Update_H (:407-409, 427-429)
+        if (h->first_solved) { if (isA) h->upd_A = true; else h->upd_H = true; }
+        return 0;
+    }
     size_t bytes = (size_t)(broadcast ? 1 : h->batch) * z_in * 8;
     double* dout = isA ? h->dAval : h->dHval;
     long long total = (long long)h->batch * z_out;

@@ -114,8 +114,8 @@ class CudaQPInterface:
                                                           sz.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p)),
                    "set_structure_A")
             self._A_set = True
-        if rhs.MatVal is not None and rhs.EntryNum > 0:
-            v = capi.f64(rhs.MatVal)
+        if rhs.MatVal is not None:
+            v = capi.f64(rhs.MatVal) if rhs.EntryNum > 0 else np.zeros(1)  # an empty Jacobian still raises Update_A
             p, loc = capi.ptr(v)
             _check(self.h, self.L.sqpb200_set_values_A(self.h, p, loc, int(v.ndim == 1)), "set_values_A")
 
@@ -132,8 +132,8 @@ class CudaQPInterface:
 
     def set_csc_values(self, which, vals):
         v = capi.f64(vals)
-        if v.shape[-1] == 0:
-            return
+        if v.shape[-1] == 0:  # empty matrix: the call only raises the Update_A / Update_H flag, like the reference's setters
+            v = np.zeros(1)
         p, loc = capi.ptr(v)
         _check(self.h, self.L.sqpb200_set_values_csc(self.h, which, p, loc, int(v.ndim == 1)), "set_values_csc")
 

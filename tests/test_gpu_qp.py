@@ -412,3 +412,13 @@ def test_hotstart_state_is_bitwise_the_oracles(gpu_lib, team):
             assert st == int(s.get_status()[b]) and ito == int(it[b])
             assert np.array_equal(x[b], xo) and np.array_equal(np.concatenate([yb[b], yc[b]]), yo), (rnd, b)
     s.close()
+
+
+def test_randomised_parity_stress(gpu_lib):
+    """tools/qp_stress.py at a small size: random shapes, convex / non-convex / LP, cold + three hot starts, warp kernel with and
+    without a tight factor capacity (rescue launch) and the one-QP-per-CTA kernel; bitwise against the oracle."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "qp_stress.py"), "14", "7"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert " 0 mismatches" in out.stdout, out.stdout[-2000:]

@@ -189,3 +189,13 @@ def test_assembly_with_duplicate_triplets(gpu_lib):
     # single-matrix path (one CTA per matrix)
     assert gpu_lib.sqpb200_assemble_csc_batched(0, 1, p(seg[:2].copy()), p(ncols[:1].copy()), p(rr), p(cc), p(colptr), p(rowidx), p(order), C.byref(ms)) == 0
     assert colptr[:nc + 1].tolist() == cp.tolist() and rowidx[:z].tolist() == ri.tolist() and order[:z].tolist() == od.tolist()
+
+
+def test_randomised_l0_stress(gpu_lib):
+    """tools/l0_stress.py at a small size: TMA-staged SpMV / SpMTV and KKT kernels on random shapes and batch sizes (odd tail
+    groups, nC = 0, batch 1), bitwise against the oracle's restatement of SpHbMat::times and test_optimality."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "l0_stress.py"), "25", "11"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert " 0 mismatches" in out.stdout, out.stdout[-2000:]

@@ -352,6 +352,18 @@ def run_gpu(args, rank, world, local_rank):
                                 "peak_source": "FMA-chain microbenchmark tools/peaks.cu, this run"}
         if smem is not None:
             roofline["smem_peak_gbs"] = smem
+        try:  # FP64 tensor-pipe peak: cuBLAS DGEMM 8192^3 through torch, best of 3
+            a_ = torch.randn(8192, 8192, dtype=torch.float64, device="cuda"); b_ = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+            torch.matmul(a_, b_); torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(3):
+                t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0_.record(); torch.matmul(a_, b_); t1_.record(); torch.cuda.synchronize()
+                best = min(best, t0_.elapsed_time(t1_))
+            roofline["dgemm_peak_gflops"] = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e9
+            del a_, b_
+        except Exception:
+            pass
         sample_B = min(B, 1024)
         rate, cores, n, t = cpu_rate(fixtures, sample_B, 1234, max_seconds=60.0, min_seconds=12.0)  # >= 12 s of CPU work
         out = {

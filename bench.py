@@ -420,7 +420,7 @@ def run_extras(device):
         t0, t1 = 0.0, float(np.median([r_[1] for r_ in runs]))
         ex["sqp_hs071"] = {"metric": "SQP solves/sec", "value": Bs / dt, "unit": "solves/s", "instances": Bs,
                            "optimal": int((res.exitflag == 0).sum()), "sqp_iters_mean": float(res.iters.mean()),
-                           "qp_iters_mean": float(res.qp_iter.mean()), "seconds": dt, "seconds_initialization": t1 - t0, "seconds_all_runs": [r_[0] for r_ in runs],
+                           "qp_iters_mean": float(res.qp_iter.mean()), "seconds": dt, "seconds_initialization": t1 - t0, "seconds_all_runs": [r_[0] for r_ in runs], "value_best_of_3": Bs / min(r_[0] for r_ in runs),
                            "note": "device-resident outer loop (csrc/sqp_outer.cu), NVRTC NLP evaluation and every QP/LP on the GPU; starts uploaded from the host, results read back; wall clock"}
         dev.close()
     except Exception as e:  # the extras never take the headline down

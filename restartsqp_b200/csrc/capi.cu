@@ -49,6 +49,7 @@ struct sqpb200_handle_s {
     int *dstatus = nullptr, *diters = nullptr, *dWB = nullptr, *dWC = nullptr;
     signed char *dwsB = nullptr, *dwsC = nullptr;
     unsigned char* dmask = nullptr;
+    void* arena = nullptr;  // one allocation behind dg .. dmask
     // hot-start state
     double* dstate = nullptr;
     int slice_doubles = 0, ld = 0;
@@ -146,14 +147,26 @@ int sqpb200_create(int batch, int nV, int nC, int qptype, int device, const sqpb
     h->ld = (nV % 2 == 0) ? nV + 1 : nV;  // odd leading dimension: conflict-free row and column walks
     size_t B = (size_t)batch;
     int rc = 0;
-    rc |= dev_alloc(h, &h->dg, B * nV); rc |= dev_alloc(h, &h->dlb, B * nV); rc |= dev_alloc(h, &h->dub, B * nV);
-    rc |= dev_alloc(h, &h->dlbA, B * nC); rc |= dev_alloc(h, &h->dubA, B * nC);
-    rc |= dev_alloc(h, &h->dx, B * nV); rc |= dev_alloc(h, &h->dy, B * (nV + nC));
-    rc |= dev_alloc(h, &h->dobj, B); rc |= dev_alloc(h, &h->dkkt, B * 5);
-    rc |= dev_alloc(h, &h->dstatus, B); rc |= dev_alloc(h, &h->diters, B);
-    rc |= dev_alloc(h, &h->dWB, B * nV); rc |= dev_alloc(h, &h->dWC, B * nC);
-    rc |= dev_alloc(h, &h->dwsB, B * nV + 32); rc |= dev_alloc(h, &h->dwsC, B * nC + 32);  // +32: kkt_tma_kernel reads 16-byte windows
-    rc |= dev_alloc(h, &h->dmask, B);
+    {
+        // the 17 per-instance vectors and result arrays come out of ONE allocation (one cudaMalloc + one memset instead of 17:
+        // handle creation is on the critical path of short batched SQP runs); every sub-array starts 256-byte aligned
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+        const size_t o_g = take(B * nV * 8), o_lb = take(B * nV * 8), o_ub = take(B * nV * 8), o_lbA = take(B * nC * 8), o_ubA = take(B * nC * 8);
+        const size_t o_x = take(B * nV * 8), o_y = take(B * (nV + nC) * 8), o_obj = take(B * 8), o_kkt = take(B * 5 * 8);
+        const size_t o_st = take(B * 4), o_it = take(B * 4), o_WB = take(B * nV * 4), o_WC = take(B * nC * 4);
+        const size_t o_wsB = take(B * nV + 32), o_wsC = take(B * nC + 32);  // +32: kkt_tma_kernel reads 16-byte windows
+        const size_t o_mask = take(B);
+        if (cudaMalloc(&h->arena, off) != cudaSuccess) { h->arena = nullptr; rc = 1; }
+        else {
+            cudaMemsetAsync(h->arena, 0, off, h->stream);
+            char* a = (char*)h->arena;
+            h->dg = (double*)(a + o_g); h->dlb = (double*)(a + o_lb); h->dub = (double*)(a + o_ub); h->dlbA = (double*)(a + o_lbA); h->dubA = (double*)(a + o_ubA);
+            h->dx = (double*)(a + o_x); h->dy = (double*)(a + o_y); h->dobj = (double*)(a + o_obj); h->dkkt = (double*)(a + o_kkt);
+            h->dstatus = (int*)(a + o_st); h->diters = (int*)(a + o_it); h->dWB = (int*)(a + o_WB); h->dWC = (int*)(a + o_WC);
+            h->dwsB = (signed char*)(a + o_wsB); h->dwsC = (signed char*)(a + o_wsC); h->dmask = (unsigned char*)(a + o_mask);
+        }
+    }
     if (rc) { *out = h; return SQPB200_ERR_CUDA; }
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
     // status = NOTINITIALISED until the first solve
@@ -168,8 +181,7 @@ int sqpb200_destroy(sqpb200_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dAp, h->dAi, h->dArp, h->dAci, h->dAperm, h->dAsrc, h->dHp, h->dHi, h->dHsrc, h->dAval, h->dHval,
-                    h->dg, h->dlb, h->dub, h->dlbA, h->dubA, h->dx, h->dy, h->dobj, h->dkkt, h->dstatus, h->diters,
-                    h->dWB, h->dWC, h->dwsB, h->dwsC, h->dmask, h->dstate, h->stage, h->dgpat, h->dgwork};
+                    h->arena, h->dstate, h->stage, h->dgpat, h->dgwork};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

@@ -47,6 +47,8 @@ class DeviceBatchedSQP:
         self.dev = torch.device("cuda", device)
         torch.cuda.set_device(self.dev)
         o = self.options_ = options if options is not None else Options()
+        if o.second_order_correction:
+            raise NotImplementedError("second_order_correction is only in the host-driven BatchedSQP (off by default in the reference)")
         info = self.info = nlp.Get_nlp_info()
         n, m = self.nVar_, self.nCon_ = info.nVar, info.nCon
         x_start, lam_start = nlp.Get_starting_point()

@@ -167,6 +167,7 @@ class BatchedSQP:
         self.obj_value_trial_ = self.obj_value_.copy()
         self.infea_measure_trial_ = self.infea_measure_.copy()
         self.infea_measure_model_ = np.zeros(B)
+        self.norm_p_k_ = np.zeros(B)
 
     # ---- triplet wrappers
     def _jac(self):
@@ -327,9 +328,10 @@ class BatchedSQP:
                 # the backend still holds rho_trial in g: the flag makes setupQP restore rho_ next iteration (:1003-1006)
 
     # ---- src/Algorithm.cpp:722-801
-    def ratio_test(self, active):
+    def ratio_test(self, active, qp_obj=None):
         o = self.options_
-        qp_obj = self.myQP_.get_objective()
+        if qp_obj is None:
+            qp_obj = self.myQP_.get_objective()
         P1_x = self.obj_value_ + self.rho_ * self.infea_measure_
         P1_t = self.obj_value_trial_ + self.rho_ * self.infea_measure_trial_
         self.actual_reduction_[active] = (P1_x - P1_t)[active]
@@ -351,6 +353,40 @@ class BatchedSQP:
             self.hess_val_[acc] = h_n[acc]
             self.Update_A[acc] = self.Update_H[acc] = self.Update_bounds[acc] = self.Update_g[acc] = True
         return acc
+
+    # ---- src/Algorithm.cpp:1140-1211 (off by default, src/Options.cpp:26; the reference marks it "FIXME: check correctness")
+    def second_order_correction(self, rej):
+        """For the instances whose step was rejected: solve the QP again around the trial point with the gradient H_k p_k + g_k,
+        add its solution s_k to p_k and repeat the ratio test; restore p_k and the QP data if the corrected step is rejected too.
+        Instances outside `rej` keep their QP data (the mixed arrays hold their current values)."""
+        rej = rej & (self.exitflag_ == int(Exitflag.UNKNOWN))
+        if not rej.any():
+            return
+        n, B = self.nVar_, self.batch
+        p_tmp = self.p_k_.copy()
+        qp_obj_tmp = self.myQP_.get_objective()
+        # Hp = H_k p_k + grad_f: symmetric-half triplet product in storage order (src/SpTripletMat.cpp:237-258)
+        Hp = np.zeros((B, n))
+        for k in range(len(self.nlp_.H_row1)):
+            i, j = self.nlp_.H_row1[k] - 1, self.nlp_.H_col1[k] - 1
+            Hp[:, i] += self.hess_val_[:, k] * self.p_k_[:, j]
+            if i != j:
+                Hp[:, j] += self.hess_val_[:, k] * self.p_k_[:, i]
+        Hp = Hp + self.grad_f_
+        m_ = rej[:, None]
+        self.myQP_.update_grad(np.where(m_, Hp, self.grad_f_))
+        self.myQP_.update_bounds(self.delta_, self.x_l_, self.x_u_, np.where(m_, self.x_trial_, self.x_k_), self.c_l_, self.c_u_,
+                                 np.where(m_, self.c_trial_, self.c_k_))
+        ok = self._solveQP(rej)
+        s_k = self.myQP_.get_optimal_solution()[:, :n]
+        qp_obj_soc = self.myQP_.get_objective() + (qp_obj_tmp - self.rho_ * self.infea_measure_model_)
+        self.p_k_[ok] = (self.p_k_ + s_k)[ok]
+        self.get_trial_point_info(ok)
+        acc2 = self.ratio_test(ok, qp_obj=np.where(ok, qp_obj_soc, qp_obj_tmp))
+        still = rej & ~acc2
+        self.p_k_[still] = p_tmp[still]
+        self.myQP_.update_grad(self.grad_f_)
+        self.myQP_.update_bounds(self.delta_, self.x_l_, self.x_u_, self.x_k_, self.c_l_, self.c_u_, self.c_k_)
 
     # ---- src/Algorithm.cpp:170-411
     def check_optimality(self, active):
@@ -392,7 +428,7 @@ class BatchedSQP:
     def update_radius(self, active):
         o = self.options_
         shrink = active & (self.actual_reduction_ < o.eta_c * self.pred_reduction_)
-        norm_p = np.abs(self.p_k_).max(axis=1) if self.nVar_ else np.zeros(self.batch)
+        norm_p = self.norm_p_k_  # ||p_k||_inf as recorded before a second-order correction was added (:98, :1181)
         grow = active & ~shrink & (self.actual_reduction_ > o.eta_e * self.pred_reduction_) & (o.tol > np.abs(self.delta_ - norm_p))
         self.delta_[shrink] = o.gamma_c * self.delta_[shrink]
         self.delta_[grow] = np.minimum(o.gamma_e * self.delta_[grow], o.delta_max)
@@ -415,8 +451,11 @@ class BatchedSQP:
             self.p_k_[active] = self.myQP_.get_optimal_solution()[:, :n][active]   # get_search_direction :609
             self.update_penalty_parameter(active)
             active = active & (self.exitflag_ == UNK)
+            self.norm_p_k_ = np.abs(self.p_k_).max(axis=1) if self.nVar_ else np.zeros(self.batch)
             self.get_trial_point_info(active)
-            self.ratio_test(active)
+            acc = self.ratio_test(active)
+            if o.second_order_correction:
+                self.second_order_correction(active & ~acc)
             self.iter_[active] += 1
             self.check_optimality(active)
             still = active & (self.exitflag_ == UNK)

@@ -37,3 +37,21 @@ def test_hs_problem_reaches_known_optimum(name):
     # the nominal start reaches the tabulated optimum; perturbed starts of the non-convex problems may stop at another KKT point
     assert abs(res.obj[0] - F_STAR[name]) <= 1e-3 * max(1.0, abs(F_STAR[name]))
     assert np.isfinite(res.obj).all() and (res.KKT_error < 1e-3).all()
+
+
+@pytest.mark.parametrize("name", ["hs006", "hs043", "hs100"])
+def test_second_order_correction_on_rejected_steps(name):
+    """src/Algorithm.cpp:1140-1211 (opt-in): these problems reject steps from the nominal start, so the corrected step is
+    exercised; the run must still end OPTIMAL at the tabulated value and must not need more outer iterations than without it."""
+    fstar = {"hs006": 0.0, "hs043": -44.0, "hs100": 680.6300573}[name]
+    nlp = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+    B = 3
+    X = perturbed_starts(nlp, B, 0)
+    out = {}
+    for soc in (False, True):
+        opt = r.Options(second_order_correction=soc)
+        mk = lambda info, qptype: r.QPhandler(info, qptype, opt, batch=B, backend=OracleQPInterface(info, qptype, opt, batch=B), refresh_ubA=True)
+        out[soc] = BatchedSQP(nlp, x0=X, options=opt, make_handler=mk).Optimize()
+        assert (out[soc].exitflag == int(r.Exitflag.OPTIMAL)).all()
+        assert abs(out[soc].obj[0] - fstar) <= 1e-3 * max(1.0, abs(fstar))
+    assert out[True].iters.sum() <= out[False].iters.sum()

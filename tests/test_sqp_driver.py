@@ -51,3 +51,23 @@ def test_hs071_batched_equals_single_runs():
         assert int(res1.exitflag[0]) == int(resB.exitflag[b])
         # identical unless another instance of the batch switched the shared hot-start mode (documented batch semantics)
         assert np.abs(res1.x[0] - resB.x[b]).max() < 1e-6
+
+
+def test_second_order_correction_option():
+    """src/Algorithm.cpp:1140-1211 (off by default): with the option on, rejected steps get a second QP around the trial point; the
+    run still converges to the HS071 optimum, single-instance and batched runs agree, and with no rejection it changes nothing."""
+    rng = np.random.default_rng(5)
+    x0 = np.array([1.0, 5.0, 5.0, 1.0])
+    B = 5
+    starts = np.clip(x0 * (1 + 0.3 * rng.standard_normal((B, 4))) + 0.3 * rng.standard_normal((B, 4)), 1.0, 5.0)
+    starts[0] = x0
+    on, off = r.Options(second_order_correction=True), r.Options()
+    res_on = BatchedSQP(HS071(), x0=starts, options=on, make_handler=oracle_handler_factory(B, on)).Optimize()
+    res_off = BatchedSQP(HS071(), x0=starts, options=off, make_handler=oracle_handler_factory(B, off)).Optimize()
+    assert (res_on.exitflag == int(r.Exitflag.OPTIMAL)).all() and (res_off.exitflag == int(r.Exitflag.OPTIMAL)).all()
+    assert np.abs(res_on.x - X_STAR).max() < 1e-4
+    assert res_on.qp_iter.sum() >= res_off.qp_iter.sum() - 50  # extra QPs only where a step was rejected
+    for b in range(B):
+        o1 = r.Options(second_order_correction=True)
+        r1 = BatchedSQP(HS071(), x0=starts[b:b + 1], options=o1, make_handler=oracle_handler_factory(1, o1)).Optimize()
+        assert int(r1.exitflag[0]) == int(res_on.exitflag[b]) and np.abs(r1.x[0] - res_on.x[b]).max() < 1e-6

@@ -219,6 +219,9 @@ const char* sqpb200_nlp_last_error(void);
 #define SQPB200_PH_RATIO 7
 #define SQPB200_PH_FINISH 8
 #define SQPB200_PH_FINAL 9
+#define SQPB200_PH_SOC_PREP 10
+#define SQPB200_PH_SOC_AFTER 11
+#define SQPB200_PH_SOC_RATIO 12
 typedef struct {
     int B, n, m, zJ, zH;
     /* Options (src/Options.cpp:19-57) */
@@ -242,10 +245,15 @@ typedef struct {
     const double *qp_x, *qp_y, *qp_obj, *qp_kkt, *lp_x;
     const int *qp_status, *qp_iters, *lp_status, *lp_iters;
     int* counters;                            /* [8] device */
+    /* second-order correction (src/Algorithm.cpp:1140-1211, opt-in): Hessian triplet pattern, mixed QP data, saved step */
+    const int *H_row1, *H_col1;
+    double *soc_g, *soc_x, *soc_c, *p_tmp, *qp_obj_tmp, *qp_obj_soc, *norm_p;
+    unsigned char* rej;
 } sqpb200_sqp_state;
 /* counters_host (may be NULL): the 8 device counters after the phase ([0] active instances, [1] OR of the raised Update_*
  * bits 1=A 2=H 4=bounds 8=delta 16=penalty 32=g, [2] instances needing the penalty update, [3] instances continuing the
- * penalty loop, [4] accepted steps); reading them synchronises the stream. */
+ * penalty loop, [4] accepted steps, [5] rejected steps entering the second-order correction); reading them synchronises the
+ * stream. */
 int sqpb200_sqp_phase(const sqpb200_sqp_state* st, int phase, int* counters_host, void* stream);
 /* sqpb200_solve with the instance mask in device memory */
 int sqpb200_solve_device_mask(sqpb200_handle h, int mode, int maxiter, const unsigned char* device_mask);

@@ -16,6 +16,7 @@
 //   PH_RATIO      cal_infea of the trial point (:577-602), ratio_test (:722-801), get_multipliers for accepted steps (:618-630)
 //   PH_FINISH     new derivatives for accepted steps, iter++, check_optimality (:170-411), update_radius (:820-849)
 //   PH_FINAL      EXCEED_MAX_ITER (:160-168)
+//   PH_SOC_*      second_order_correction (:1140-1211, opt-in): corrected QP data, step p_k + s_k, second ratio test
 #include "../../include/sqpb200.h"
 
 #include <cuda_runtime.h>
@@ -187,7 +188,12 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
     case SQPB200_PH_TRIAL: {
         if (S.active[b] && S.exitflag[b] != EX_UNKNOWN) S.active[b] = 0;
         if (!S.active[b]) break;
-        for (int i = 0; i < n; i++) S.x_trial[(size_t)b * n + i] = S.x_k[(size_t)b * n + i] + S.p_k[(size_t)b * n + i];
+        double np_ = 0.0;  // norm_p_k_ = ||p_k||_inf, recorded before any second-order correction is added (:98, :1181)
+        for (int i = 0; i < n; i++) {
+            S.x_trial[(size_t)b * n + i] = S.x_k[(size_t)b * n + i] + S.p_k[(size_t)b * n + i];
+            np_ = fmax(np_, fabs(S.p_k[(size_t)b * n + i]));
+        }
+        S.norm_p[b] = np_;
         break;
     }
     case SQPB200_PH_RATIO: {
@@ -228,8 +234,7 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
         // update_radius
         const double ared = S.actual_red[b], pred = S.pred_red[b];
         const bool shrink = ared < S.eta_c * pred;
-        double norm_p = 0.0;
-        for (int i = 0; i < n; i++) norm_p = fmax(norm_p, fabs(S.p_k[(size_t)b * n + i]));
+        const double norm_p = S.norm_p[b];
         const bool grow = !shrink && ared > S.eta_e * pred && S.tol > fabs(S.delta[b] - norm_p);
         if (shrink) S.delta[b] = S.gamma_c * S.delta[b];
         if (grow) S.delta[b] = fmin(S.gamma_e * S.delta[b], S.delta_max);
@@ -237,6 +242,74 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
         if (S.delta[b] < S.delta_min) {
             S.exitflag[b] = EX_TRUST_REGION_TOO_SMALL;
             check_optimality(S, b, diff);  // :149-152
+        }
+        break;
+    }
+    case SQPB200_PH_SOC_PREP: {
+        // rejected steps: QP data of the corrected subproblem (gradient H_k p_k + g_k, bounds around the trial point); every
+        // other instance keeps its current data in the mixed arrays
+        const bool rj = S.active[b] && !S.acc[b] && S.exitflag[b] == EX_UNKNOWN;
+        S.rej[b] = rj ? 1 : 0;
+        double* sg = S.soc_g + (size_t)b * n;
+        if (rj) {
+            atomicAdd(&S.counters[5], 1);
+            const double *hv = S.hess + (size_t)b * S.zH, *p = S.p_k + (size_t)b * n;
+            for (int i = 0; i < n; i++) sg[i] = 0.0;
+            for (int k = 0; k < S.zH; k++) {  // symmetric-half triplet product in storage order (src/SpTripletMat.cpp:237-258)
+                const int i = S.H_row1[k] - 1, j = S.H_col1[k] - 1;
+                sg[i] += hv[k] * p[j];
+                if (i != j) sg[j] += hv[k] * p[i];
+            }
+            for (int i = 0; i < n; i++) { sg[i] = sg[i] + S.grad[(size_t)b * n + i]; S.p_tmp[(size_t)b * n + i] = p[i]; }
+            S.qp_obj_tmp[b] = S.qp_obj[b];
+        } else {
+            for (int i = 0; i < n; i++) sg[i] = S.grad[(size_t)b * n + i];
+        }
+        for (int i = 0; i < n; i++) S.soc_x[(size_t)b * n + i] = rj ? S.x_trial[(size_t)b * n + i] : S.x_k[(size_t)b * n + i];
+        for (int i = 0; i < m; i++) S.soc_c[(size_t)b * m + i] = rj ? S.c_trial[(size_t)b * m + i] : S.c_k[(size_t)b * m + i];
+        break;
+    }
+    case SQPB200_PH_SOC_AFTER: {
+        if (!S.rej[b]) break;
+        S.qp_iter[b] += S.qp_iters[b];
+        const int st = S.qp_status[b];
+        const bool ok = (S.qp_kkt[(size_t)b * 5 + 4] <= 1.0e-6) && st == SQPB200_QP_OPTIMAL;
+        if (!ok) {
+            S.exitflag[b] = (st == SQPB200_QP_OPTIMAL) ? SQPB200_QPERROR_INTERNAL_ERROR : st;
+            S.rej[b] = 2;  // left the correction with a solver failure: the saved step is restored in SOC_RATIO
+            break;
+        }
+        const double* x = S.qp_x + (size_t)b * nV;
+        S.qp_obj_soc[b] = S.qp_obj[b] + (S.qp_obj_tmp[b] - S.rho[b] * S.infea_model[b]);
+        for (int i = 0; i < n; i++) {
+            const double pk = S.p_k[(size_t)b * n + i] + x[i];
+            S.p_k[(size_t)b * n + i] = pk;
+            S.x_trial[(size_t)b * n + i] = S.x_k[(size_t)b * n + i] + pk;
+        }
+        break;
+    }
+    case SQPB200_PH_SOC_RATIO: {
+        if (S.rej[b] == 1) {
+            const double infea_t = cal_infea(S, S.c_trial, b);
+            S.infea_trial[b] = infea_t;
+            const double P1_x = S.f_k[b] + S.rho[b] * S.infea[b];
+            const double P1_t = S.f_trial[b] + S.rho[b] * infea_t;
+            const double ared = P1_x - P1_t, pred = S.rho[b] * S.infea[b] - S.qp_obj_soc[b];
+            S.actual_red[b] = ared; S.pred_red[b] = pred;
+            if (ared >= S.eta_s * pred && ared >= -S.tol) {
+                S.acc[b] = 1;
+                S.infea[b] = infea_t;
+                S.f_k[b] = S.f_trial[b];
+                for (int i = 0; i < n; i++) S.x_k[(size_t)b * n + i] = S.x_trial[(size_t)b * n + i];
+                for (int i = 0; i < m; i++) S.c_k[(size_t)b * m + i] = S.c_trial[(size_t)b * m + i];
+                get_multipliers(S, b);
+                S.upd[b] |= UP_A | UP_H | UP_BOUNDS | UP_G;
+                for (int i = 0; i < m; i++) S.neg_lam[(size_t)b * m + i] = -S.lam_c[(size_t)b * m + i];
+            } else {
+                for (int i = 0; i < n; i++) S.p_k[(size_t)b * n + i] = S.p_tmp[(size_t)b * n + i];
+            }
+        } else if (S.rej[b] == 2) {
+            for (int i = 0; i < n; i++) S.p_k[(size_t)b * n + i] = S.p_tmp[(size_t)b * n + i];
         }
         break;
     }
@@ -252,9 +325,9 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
 int sqpb200_sqp_phase(const sqpb200_sqp_state* st, int phase, int* counters_host, void* stream_) {
     if (!st || st->B <= 0) return SQPB200_ERR_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (phase == SQPB200_PH_FLAGS || phase == SQPB200_PH_AFTER_QP || phase == SQPB200_PH_PEN_CHECK || phase == SQPB200_PH_RATIO) {
+    if (phase == SQPB200_PH_FLAGS || phase == SQPB200_PH_AFTER_QP || phase == SQPB200_PH_PEN_CHECK || phase == SQPB200_PH_RATIO || phase == SQPB200_PH_SOC_PREP) {
         // counters: [0] active, [1] OR of Update_* flags, [2] need penalty update, [3] go, [4] accepted
-        const int idx = phase == SQPB200_PH_FLAGS ? 0 : (phase == SQPB200_PH_AFTER_QP ? 2 : (phase == SQPB200_PH_PEN_CHECK ? 3 : 4));
+        const int idx = phase == SQPB200_PH_FLAGS ? 0 : (phase == SQPB200_PH_AFTER_QP ? 2 : (phase == SQPB200_PH_PEN_CHECK ? 3 : (phase == SQPB200_PH_RATIO ? 4 : 5)));
         if (cudaMemsetAsync(st->counters + idx, 0, (phase == SQPB200_PH_FLAGS ? 2 : 1) * sizeof(int), stream) != cudaSuccess) return SQPB200_ERR_CUDA;
     }
     const int block = 128, grid = (st->B + block - 1) / block;

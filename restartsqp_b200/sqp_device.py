@@ -18,6 +18,7 @@ from .sqp_driver import SQPResult, classify_single_constraint
 from .sqp_types import Exitflag, Options, QPType, SpTripletMat
 
 PH_FLAGS, PH_AFTER_QP, PH_LP_AFTER, PH_PEN_CHECK, PH_PEN_AFTER, PH_PEN_FINAL, PH_TRIAL, PH_RATIO, PH_FINISH, PH_FINAL = range(10)
+PH_SOC_PREP, PH_SOC_AFTER, PH_SOC_RATIO = 10, 11, 12
 UP_A, UP_H, UP_BOUNDS, UP_DELTA, UP_PENALTY, UP_G = 1, 2, 4, 8, 16, 32
 
 _P, _D, _I = C.c_void_p, C.c_double, C.c_int
@@ -35,7 +36,8 @@ class SqpState(C.Structure):
                                    "infea_model_tmp", "rho_trial", "infea_infty", "actual_red", "pred_red", "kkt_err",
                                    "g_new", "j_new", "h_new", "scratch", "exitflag", "iter", "pen_trial", "qp_iter",
                                    "active", "need", "go", "acc", "upd", "feasible_lp",
-                                   "qp_x", "qp_y", "qp_obj", "qp_kkt", "lp_x", "qp_status", "qp_iters", "lp_status", "lp_iters", "counters")])
+                                   "qp_x", "qp_y", "qp_obj", "qp_kkt", "lp_x", "qp_status", "qp_iters", "lp_status", "lp_iters", "counters",
+                                   "H_row1", "H_col1", "soc_g", "soc_x", "soc_c", "p_tmp", "qp_obj_tmp", "qp_obj_soc", "norm_p", "rej")])
 
 
 class DeviceBatchedSQP:
@@ -47,8 +49,6 @@ class DeviceBatchedSQP:
         self.dev = torch.device("cuda", device)
         torch.cuda.set_device(self.dev)
         o = self.options_ = options if options is not None else Options()
-        if o.second_order_correction:
-            raise NotImplementedError("second_order_correction is only in the host-driven BatchedSQP (off by default in the reference)")
         info = self.info = nlp.Get_nlp_info()
         n, m = self.nVar_, self.nCon_ = info.nVar, info.nCon
         x_start, lam_start = nlp.Get_starting_point()
@@ -68,6 +68,7 @@ class DeviceBatchedSQP:
         T["bound_type"] = rep(classify_single_constraint(np.atleast_2d(xl), np.atleast_2d(xu)), torch.int32)
         T["cons_type"] = rep(classify_single_constraint(np.atleast_2d(cl).reshape(1, m), np.atleast_2d(cu).reshape(1, m)), torch.int32)
         T["J_row1"], T["J_col1"] = up(nlp.J_row1, torch.int32), up(nlp.J_col1, torch.int32)
+        T["H_row1"], T["H_col1"] = up(nlp.H_row1, torch.int32), up(nlp.H_col1, torch.int32)
         T["x_k"] = torch.minimum(torch.maximum(up(x0), T["x_l"]), T["x_u"])  # shift_starting_point, src/SQPTNLP.cpp:140-153
         T["lam_c"] = rep(np.asarray(lam_start, dtype=np.float64).reshape(1, m))
         T["neg_lam"] = -T["lam_c"]
@@ -75,7 +76,8 @@ class DeviceBatchedSQP:
                        ("infea", (B,)), ("p_k", (B, n)), ("x_trial", (B, n)), ("c_trial", (B, m)), ("f_trial", (B,)), ("infea_trial", (B,)),
                        ("infea_model", (B,)), ("infea_model_tmp", (B,)), ("rho_trial", (B,)), ("infea_infty", (B,)), ("actual_red", (B,)),
                        ("pred_red", (B,)), ("g_new", (B, n)), ("j_new", (B, zJ)), ("h_new", (B, zH)), ("scratch", (B, max(n, 1))),
-                       ("f_tmp", (B,)), ("c_tmp", (B, m))):
+                       ("f_tmp", (B,)), ("c_tmp", (B, m)), ("soc_g", (B, n)), ("soc_x", (B, n)), ("soc_c", (B, m)), ("p_tmp", (B, n)),
+                       ("qp_obj_tmp", (B,)), ("qp_obj_soc", (B,)), ("norm_p", (B,))):
             T[k] = f64(*shp)
         T["delta"] = torch.full((B,), float(o.delta), dtype=torch.float64, device=self.dev)
         T["rho"] = torch.full((B,), float(o.rho), dtype=torch.float64, device=self.dev)
@@ -85,7 +87,7 @@ class DeviceBatchedSQP:
         T["iter"] = torch.zeros(B, dtype=torch.int32, device=self.dev)
         T["pen_trial"] = torch.zeros(B, dtype=torch.int32, device=self.dev)
         T["qp_iter"] = torch.zeros(B, dtype=torch.int64, device=self.dev)
-        for k in ("active", "need", "go", "acc", "upd", "feasible_lp"):
+        for k in ("active", "need", "go", "acc", "upd", "feasible_lp", "rej"):
             T[k] = u8()
         T["counters"] = torch.zeros(8, dtype=torch.int32, device=self.dev)
         # initialization(), src/Algorithm.cpp:438-472: f, c, grad, Jacobian, Hessian at the (shifted) start in one launch
@@ -184,6 +186,20 @@ class DeviceBatchedSQP:
             self._phase(PH_PEN_AFTER)
         self._phase(PH_PEN_FINAL)
 
+    # ---- src/Algorithm.cpp:1140-1211 (opt-in)
+    def second_order_correction(self):
+        T, qp, B = self.T, self.myQP_, self.batch
+        if self._phase(PH_SOC_PREP, read=True)[5] == 0:
+            return
+        qp.update_grad(T["soc_g"])
+        qp.update_bounds(T["delta"], T["x_l"], T["x_u"], T["soc_x"], T["c_l"], T["c_u"], T["soc_c"])
+        self._solve(qp, QPType.QP, T["rej"])
+        self._phase(PH_SOC_AFTER)
+        self.nlp_.eval_device(0, B, T["x_trial"], None, T["f_trial"], T["c_trial"])
+        self._phase(PH_SOC_RATIO)
+        qp.update_grad(T["grad"])
+        qp.update_bounds(T["delta"], T["x_l"], T["x_u"], T["x_k"], T["c_l"], T["c_u"], T["c_k"])
+
     # ---- src/Algorithm.cpp:55-168
     def Optimize(self):
         T, nlp, B = self.T, self.nlp_, self.batch
@@ -199,6 +215,8 @@ class DeviceBatchedSQP:
             self._phase(PH_TRIAL)
             nlp.eval_device(0, B, T["x_trial"], None, T["f_trial"], T["c_trial"])  # get_trial_point_info :414-429
             self._phase(PH_RATIO)
+            if self.options_.second_order_correction:
+                self.second_order_correction()
             nlp.eval_device(1, B, T["x_k"], T["neg_lam"], T["f_tmp"], T["c_tmp"], T["g_new"], T["j_new"], T["h_new"])
             self._phase(PH_FINISH)
         self._phase(PH_FINAL)

@@ -152,3 +152,25 @@ def test_device_resident_loop_equals_host_loop(gpu_lib, name):
     assert np.array_equal(res_d.x[fin], res_h.x[fin]) and np.array_equal(res_d.obj[fin], res_h.obj[fin])
     assert (res_d.exitflag[0] == int(r.Exitflag.OPTIMAL)) or name == "hs106"
     alg.close(); dev.close()
+
+
+@pytest.mark.parametrize("name", ["hs006", "hs043", "hs100", "hs038"])
+def test_device_loop_second_order_correction_equals_host_loop(gpu_lib, name):
+    """The opt-in second-order correction (src/Algorithm.cpp:1140-1211) in the device-resident loop (PH_SOC_* phases) against the
+    numpy mirror: identical exit flags, iteration counts and iterates on problems that reject steps."""
+    import os
+    from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
+    from restartsqp_b200.sqp_device import DeviceBatchedSQP
+    from test_hs_suite import HS_DIR, perturbed_starts
+    dev = DeviceNLP(AmplNLP(os.path.join(HS_DIR, name + ".nl")))
+    X = perturbed_starts(dev.host, 100, 2)
+    res_h = BatchedSQP(dev, x0=X, options=r.Options(iter_max=120, second_order_correction=True)).Optimize()
+    alg = DeviceBatchedSQP(dev, x0=X, options=r.Options(iter_max=120, second_order_correction=True))
+    res_d = alg.Optimize()
+    res_off = BatchedSQP(dev, x0=X, options=r.Options(iter_max=120)).Optimize()
+    assert (res_d.exitflag == res_h.exitflag).all() and (res_d.iters == res_h.iters).all() and (res_d.qp_iter == res_h.qp_iter).all()
+    assert (res_d.rho == res_h.rho).all() and (res_d.delta == res_h.delta).all()
+    fin = np.isfinite(res_h.x).all(axis=1)
+    assert np.array_equal(res_d.x[fin], res_h.x[fin])
+    assert (res_h.qp_iter != res_off.qp_iter).any()  # the correction was actually taken somewhere
+    alg.close(); dev.close()

@@ -498,7 +498,7 @@ struct QPT {
             SYNC();
             _Pragma("unroll 1") for (int i = i0 + nb + lane; i < n; i += TEAM) {
                 double s = z[i];
-                DOT_UNROLL for (int k = 0; k < nb; k++) s -= R_(i0 + k, i) * z[i0 + k];
+                _Pragma("unroll 16") for (int k = 0; k < nb; k++) s -= R_(i0 + k, i) * z[i0 + k];  // 16 loads in flight per thread
                 z[i] = s;
             }
             SYNC();
@@ -527,7 +527,7 @@ struct QPT {
             SYNC();
             _Pragma("unroll 1") for (int i = lane; i < i0; i += TEAM) {
                 double s = z[i];
-                DOT_UNROLL for (int k = nb - 1; k >= 0; k--) s -= R_(i, i0 + k) * z[i0 + k];
+                _Pragma("unroll 16") for (int k = nb - 1; k >= 0; k--) s -= R_(i, i0 + k) * z[i0 + k];
                 z[i] = s;
             }
             SYNC();

@@ -481,10 +481,15 @@ struct QPT {
         double* RT = V_(RT);
         double (*Ds)[33] = diag_tile();
         const int l = lane & 31;
+        // the diagonal tile of block I+1 is fetched while block I's columns are applied to the trailing unknowns
+        auto load_tile = [&](int j0) {
+            const int mb = (n - j0 < 32) ? n - j0 : 32;
+            _Pragma("unroll 1") for (int e = lane; e < 32 * 32; e += TEAM) { const int k = e >> 5, i = e & 31; if (k < mb && i < mb && k <= i) Ds[k][i] = R_(j0 + k, j0 + i); }
+        };
+        if (n > 0) load_tile(0);
+        SYNC();
         _Pragma("unroll 1") for (int i0 = 0; i0 < n; i0 += 32) {
             const int nb = (n - i0 < 32) ? n - i0 : 32;
-            _Pragma("unroll 1") for (int e = lane; e < 32 * 32; e += TEAM) { const int k = e >> 5, i = e & 31; if (k < nb && i < nb && k <= i) Ds[k][i] = R_(i0 + k, i0 + i); }
-            SYNC();
             if (lane < 32) {
                 double zi = (l < nb) ? z[i0 + l] : 0.0;
                 const double ri = (l < nb) ? 1.0 / Ds[l][l] : 0.0;  // pivot reciprocals in parallel; the chain only multiplies
@@ -501,6 +506,7 @@ struct QPT {
                 _Pragma("unroll 16") for (int k = 0; k < nb; k++) s -= R_(i0 + k, i) * z[i0 + k];  // 16 loads in flight per thread
                 z[i] = s;
             }
+            if (i0 + 32 < n) load_tile(i0 + 32);
             SYNC();
         }
     }
@@ -510,10 +516,14 @@ struct QPT {
         const double* RT = V_(RT);
         double (*Ds)[33] = diag_tile();
         const int l = lane & 31;
+        auto load_tile = [&](int j0) {
+            const int mb = (n - j0 < 32) ? n - j0 : 32;
+            _Pragma("unroll 1") for (int e = lane; e < 32 * 32; e += TEAM) { const int k = e >> 5, i = e & 31; if (k < mb && i < mb && k <= i) Ds[k][i] = R_(j0 + k, j0 + i); }
+        };
+        if (n > 0) load_tile(((n - 1) >> 5) << 5);
+        SYNC();
         _Pragma("unroll 1") for (int i0 = ((n - 1) >> 5) << 5; i0 >= 0; i0 -= 32) {
             const int nb = (n - i0 < 32) ? n - i0 : 32;
-            _Pragma("unroll 1") for (int e = lane; e < 32 * 32; e += TEAM) { const int k = e >> 5, i = e & 31; if (k < nb && i < nb && k <= i) Ds[k][i] = R_(i0 + k, i0 + i); }
-            SYNC();
             if (lane < 32) {
                 double zi = (l < nb) ? z[i0 + l] : 0.0;
                 const double ri = (l < nb) ? 1.0 / Ds[l][l] : 0.0;
@@ -530,6 +540,7 @@ struct QPT {
                 _Pragma("unroll 16") for (int k = nb - 1; k >= 0; k--) s -= R_(i, i0 + k) * z[i0 + k];
                 z[i] = s;
             }
+            if (i0 >= 32) load_tile(i0 - 32);
             SYNC();
         }
     }

@@ -1,5 +1,5 @@
-"""QP dump formats (restartsqp_b200/qp_dump.py): the reference's own dump files (three originals kept under
-tests/golden/dumps) read to exactly the committed fixtures, and write -> read round trips of every fixture in both formats."""
+"""QP dump formats (restartsqp_b200/qp_dump.py): the reference's own dump files (read from /root/reference when it
+is present) parse to exactly the committed fixtures, and write -> read round trips of every fixture in both formats."""
 import os
 
 import numpy as np
@@ -17,11 +17,21 @@ def same(a, b):
     return all(np.array_equal(np.asarray(a[k], dtype=np.float64), np.asarray(b[k], dtype=np.float64)) for k in KEYS)
 
 
-@pytest.mark.parametrize("fname,fixture", [("QORE_hs015qpdata.log", "QORE_hs015"), ("QORE_hs104qpdata.log", "QORE_hs104"), ("hs034.hpp", "hs034_hpp")])
-def test_reference_dump_files_read_to_the_fixtures(fname, fixture):
-    q = qp_dump.read_dump(os.path.join(HERE, "golden", "dumps", fname))
-    ref = [f for f in FIX if f["name"] == fixture][0]
-    assert q["name"] == fixture and same(q, ref)
+REF = "/root/reference/test"
+REF_DUMPS = [(os.path.join(REF, "unsolved_QP_data", f), f.replace("qpdata.log", "")) for f in sorted(os.listdir(os.path.join(REF, "unsolved_QP_data")))
+             if f.endswith(".log")] + \
+            [(os.path.join(REF, "unsolved_QPs", f), f.replace(".hpp", "") + "_hpp") for f in sorted(os.listdir(os.path.join(REF, "unsolved_QPs")))
+             if f.endswith(".hpp")] if os.path.isdir(REF) else []
+
+
+@pytest.mark.skipif(not REF_DUMPS, reason="the reference checkout is only present in the build container")
+@pytest.mark.parametrize("path,fixture", REF_DUMPS, ids=[f for _, f in REF_DUMPS])
+def test_reference_dump_files_read_to_the_fixtures(path, fixture):
+    """Every dump file of the reference (read where it lies, never copied) parses to exactly the committed fixture."""
+    q = qp_dump.read_dump(path)
+    ref = [f for f in FIX if f["name"] == fixture]
+    assert ref, fixture
+    assert q["name"] == fixture and same(q, ref[0])
 
 
 @pytest.mark.parametrize("q", FIX, ids=[q["name"] for q in FIX])

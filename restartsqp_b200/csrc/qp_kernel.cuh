@@ -139,6 +139,14 @@ __device__ __forceinline__ double quot(double x, double d, double ri) {
 }
 
 #define QP_FN __noinline__
+// loop unrolling of the solver's loops: 1 = smallest code (10.6 k SASS instructions).  Measured with -DQP_UNROLL_N=4 (59 k
+// instructions): 1.3x-3x slower on every dumped QP (instruction-cache misses), so 1 is what ships.
+#ifndef QP_UNROLL_N
+#define QP_UNROLL_N 1
+#endif
+#define QP_STR_(x) #x
+#define QP_STR(x) QP_STR_(x)
+#define QP_U1 _Pragma(QP_STR(unroll QP_UNROLL_N))
 
 // TEAM = threads that cooperate on one QP.  32: one warp per QP, everything in the warp's shared-memory slice, pattern
 // staged as 16-bit indices.  > 32: the whole CTA works on one QP (large QPs); the slice lives in
@@ -187,11 +195,11 @@ struct QPT {
         const double* Hv = V_(Hv);
         const bool has_H = sA.has_H && !sA.is_lp;
         const double reg = sA.is_lp ? QP_EPS_REG : 0.0;
-        _Pragma("unroll 1") for (int c = lane; c < nV; c += TEAM) {
+        QP_U1 for (int c = lane; c < nV; c += TEAM) {
             double s = 0.0;
             if (has_H) {
                 int e1 = Hp[c + 1];
-                _Pragma("unroll 1") for (int e = Hp[c]; e < e1; e++) s += Hv[e] * v[Hi[e]];
+                QP_U1 for (int e = Hp[c]; e < e1; e++) s += Hv[e] * v[Hi[e]];
             }
             if (reg != 0.0) s += reg * v[c];
             out[c] = s;
@@ -203,11 +211,11 @@ struct QPT {
         const pidx *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
         const double* Hv = V_(Hv);
         const bool has_H = sA.has_H && !sA.is_lp;
-        _Pragma("unroll 1") for (int c = lane; c < nV; c += TEAM) {
+        QP_U1 for (int c = lane; c < nV; c += TEAM) {
             double s = 0.0;
             if (has_H) {
                 int e1 = Hp[c + 1];
-                _Pragma("unroll 1") for (int e = Hp[c]; e < e1; e++) s += Hv[e] * v[Hi[e]];
+                QP_U1 for (int e = Hp[c]; e < e1; e++) s += Hv[e] * v[Hi[e]];
             }
             out[c] = s;
         }
@@ -217,10 +225,10 @@ struct QPT {
         QP_CTX QP_PAT
         const pidx *Arp = pat + sA.pArp, *Aci = pat + sA.pAci, *Aperm = pat + sA.pAperm;
         const double* Av = V_(Av);
-        _Pragma("unroll 1") for (int r = lane; r < nC; r += TEAM) {
+        QP_U1 for (int r = lane; r < nC; r += TEAM) {
             double s = 0.0;
             int k1 = Arp[r + 1];
-            _Pragma("unroll 1") for (int k = Arp[r]; k < k1; k++) s += Av[Aperm[k]] * v[Aci[k]];
+            QP_U1 for (int k = Arp[r]; k < k1; k++) s += Av[Aperm[k]] * v[Aci[k]];
             out[r] = s;
         }
         SYNC();
@@ -229,10 +237,10 @@ struct QPT {
         QP_CTX QP_PAT
         const pidx *Ap = pat + sA.pAp, *Ai = pat + sA.pAi;
         const double* Av = V_(Av);
-        _Pragma("unroll 1") for (int c = lane; c < nV; c += TEAM) {
+        QP_U1 for (int c = lane; c < nV; c += TEAM) {
             double s = 0.0;
             int e1 = Ap[c + 1];
-            _Pragma("unroll 1") for (int e = Ap[c]; e < e1; e++) s += Av[e] * yc[Ai[e]];
+            QP_U1 for (int e = Ap[c]; e < e1; e++) s += Av[e] * yc[Ai[e]];
             out[c] = s;
         }
         SYNC();
@@ -242,7 +250,7 @@ struct QPT {
         const pidx *Arp = pat + sA.pArp, *Aci = pat + sA.pAci, *Aperm = pat + sA.pAperm;
         double s = 0.0;
         int k1 = Arp[r + 1];
-        _Pragma("unroll 1") for (int k = Arp[r]; k < k1; k++)
+        QP_U1 for (int k = Arp[r]; k < k1; k++)
             if (Aci[k] == c) s += Av[Aperm[k]];
         return s;
     }
@@ -250,7 +258,7 @@ struct QPT {
     // ---------------------------------------------------------------- reductions
     // lexicographic (t, pos) minimum over the team, returned to every thread
     static __device__ __forceinline__ MinKey team_min(double t, int pos) {
-        _Pragma("unroll 1") for (int o = 16; o > 0; o >>= 1) {
+        QP_U1 for (int o = 16; o > 0; o >>= 1) {
             double t2_ = __shfl_xor_sync(0xffffffffu, t, o);
             int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
             if (key_less(t2_, p2, t, pos)) { t = t2_; pos = p2; }
@@ -260,7 +268,7 @@ struct QPT {
             if ((threadIdx.x & 31) == 0) { sRedT[threadIdx.x >> 5] = t; sRedP[threadIdx.x >> 5] = pos; }
             __syncthreads();
             t = sRedT[0]; pos = sRedP[0];
-            _Pragma("unroll 1") for (int k = 1; k < TEAM / 32; k++)
+            QP_U1 for (int k = 1; k < TEAM / 32; k++)
                 if (key_less(sRedT[k], sRedP[k], t, pos)) { t = sRedT[k]; pos = sRedP[k]; }
         }
         MinKey r; r.t = t; r.pos = pos;
@@ -280,7 +288,7 @@ struct QPT {
         double *t1 = V_(t1), *t2 = V_(t2);
         const double* Q = V_(Q);
         const short* posFR = posFR_;
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) { int p = posFR[i]; t1[i] = (p >= 0) ? Q[p * ld + b] : 0.0; }
+        QP_U1 for (int i = lane; i < nV; i += TEAM) { int p = posFR[i]; t1[i] = (p >= 0) ? Q[p * ld + b] : 0.0; }
         SYNC();
         mulH(t1, t2);
     }
@@ -292,7 +300,7 @@ struct QPT {
         double* RT = V_(RT);
         if (sA.is_lp) {
             double sr = sqrt(QP_EPS_REG);
-            _Pragma("unroll 1") for (int k = lane; k < nZ * nZ; k += TEAM) { int a_ = k / nZ, b_ = k % nZ; R_(a_, b_) = (a_ == b_) ? sr : 0.0; }
+            QP_U1 for (int k = lane; k < nZ * nZ; k += TEAM) { int a_ = k / nZ, b_ = k % nZ; R_(a_, b_) = (a_ == b_) ? sr : 0.0; }
             SYNC();
             return 0;
         }
@@ -310,14 +318,14 @@ struct QPT {
             const bool has_H = sA.has_H != 0;
             int CH = (7 * (nV + nC)) / nFR;
             if (CH > nZ) CH = nZ;
-            _Pragma("unroll 1") for (int b0 = 0; b0 < nZ; b0 += CH) {
+            QP_U1 for (int b0 = 0; b0 < nZ; b0 += CH) {
                 const int cw = (nZ - b0 < CH) ? nZ - b0 : CH;
-                _Pragma("unroll 1") for (int e = lane; e < nFR * cw; e += TEAM) {
+                QP_U1 for (int e = lane; e < nFR * cw; e += TEAM) {
                     const int p = e / cw, bb = e - p * cw;
                     double s = 0.0;
                     if (has_H) {
                         const int c = FR[p], e1 = Hp[c + 1];
-                        _Pragma("unroll 1") for (int h = Hp[c]; h < e1; h++) {
+                        QP_U1 for (int h = Hp[c]; h < e1; h++) {
                             const int pr = posFR[Hi[h]];
                             s += Hv[h] * ((pr >= 0) ? Q[pr * ld + b0 + bb] : 0.0);
                         }
@@ -325,11 +333,11 @@ struct QPT {
                     Wc[e] = s;
                 }
                 SYNC();
-                _Pragma("unroll 1") for (int e = lane; e < (b0 + cw) * cw; e += TEAM) {
+                QP_U1 for (int e = lane; e < (b0 + cw) * cw; e += TEAM) {
                     const int a_ = e / cw, bb = e - a_ * cw;
                     if (a_ <= b0 + bb) {
                         double s = 0.0;
-                        _Pragma("unroll 1") for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * Wc[p * cw + bb];
+                        QP_U1 for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * Wc[p * cw + bb];
                         R_(a_, b0 + bb) = s;
                     }
                 }
@@ -337,8 +345,8 @@ struct QPT {
             }
         }
         // row-wise Cholesky: R'R = M, same per-element summation order as the column version
-        _Pragma("unroll 1") for (int i = 0; i < nZ; i++) {
-            _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += TEAM) {
+        QP_U1 for (int i = 0; i < nZ; i++) {
+            QP_U1 for (int j = i + lane; j < nZ; j += TEAM) {
                 double s = R_(i, j);
                 DOT_UNROLL for (int k = 0; k < i; k++) s -= R_(k, i) * R_(k, j);
                 R_(i, j) = s;
@@ -348,8 +356,8 @@ struct QPT {
             SYNC();  // all lanes hold d before anyone rewrites R(i,i): the branch below is warp-uniform
             if (!(d > QP_ZERO)) return 1 + i;
             double dd = sqrt(d);
-            _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += TEAM) R_(i, j) = (j == i) ? dd : R_(i, j) / dd;
-            _Pragma("unroll 1") for (int j = lane; j < i; j += TEAM) R_(i, j) = 0.0;
+            QP_U1 for (int j = i + lane; j < nZ; j += TEAM) R_(i, j) = (j == i) ? dd : R_(i, j) / dd;
+            QP_U1 for (int j = lane; j < i; j += TEAM) R_(i, j) = 0.0;
             SYNC();
         }
         return 0;
@@ -379,7 +387,7 @@ struct QPT {
                 const int ga = ga0 + i, gb = gb0 + j;
                 acc[i][j] = (!init_zero && ga < na && gb < nb && ga <= gb) ? C[ga * ld + gb] : 0.0;
             }
-        _Pragma("unroll 1") for (int k0 = 0; k0 < K; k0 += KC) {
+        QP_U1 for (int k0 = 0; k0 < K; k0 += KC) {
             const int kc = (K - k0 < KC) ? K - k0 : KC;
             __syncthreads();  // previous stage consumed
             for (int e = tid; e < KC * TA; e += TEAM) {
@@ -421,12 +429,12 @@ struct QPT {
         const pidx *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
         const bool has_H = sA.has_H && !sA.is_lp;
         // A: W[p][b]
-        _Pragma("unroll 1") for (int e = lane; e < nFR * nZ; e += TEAM) {
+        QP_U1 for (int e = lane; e < nFR * nZ; e += TEAM) {
             const int p = e / nZ, b = e % nZ;
             double s = 0.0;
             if (has_H) {
                 const int c = FR[p], e1 = Hp[c + 1];
-                _Pragma("unroll 1") for (int h = Hp[c]; h < e1; h++) {
+                QP_U1 for (int h = Hp[c]; h < e1; h++) {
                     const int pr = posFR[Hi[h]];
                     s += Hv[h] * ((pr >= 0) ? Q[pr * ld + b] : 0.0);
                 }
@@ -435,22 +443,22 @@ struct QPT {
         }
         SYNC();
         // B: M (upper triangle) into R
-        _Pragma("unroll 1") for (int b0 = 0; b0 < nZ; b0 += 64)
-            _Pragma("unroll 1") for (int a0 = 0; a0 < b0 + 64 && a0 < nZ; a0 += TA)
+        QP_U1 for (int b0 = 0; b0 < nZ; b0 += 64)
+            QP_U1 for (int a0 = 0; a0 < b0 + 64 && a0 < nZ; a0 += TA)
                 tile_contract<1>(Q, 0, W, 0, nFR, RT, a0, nZ, b0, nZ, ld, true);
         SYNC();
         // C: Cholesky by block rows
-        _Pragma("unroll 1") for (int i0 = 0; i0 < nZ; i0 += TA) {
+        QP_U1 for (int i0 = 0; i0 < nZ; i0 += TA) {
             const int i1 = (i0 + TA < nZ) ? i0 + TA : nZ;
             if (i0 > 0) {
                 // rows i0..i1, columns >= i0: subtract the terms k < i0.  Row/column indices are taken relative to i0 so that
                 // the tile's "a <= b" rule is the upper-triangle rule of the block row.
-                _Pragma("unroll 1") for (int b0 = 0; b0 < nZ - i0; b0 += 64)
+                QP_U1 for (int b0 = 0; b0 < nZ - i0; b0 += 64)
                     tile_contract<-1>(RT, i0, RT, i0, i0, RT + i0 * ld + i0, 0, i1 - i0, b0, nZ - i0, ld, false);
                 SYNC();
             }
-            _Pragma("unroll 1") for (int i = i0; i < i1; i++) {
-                _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += TEAM) {
+            QP_U1 for (int i = i0; i < i1; i++) {
+                QP_U1 for (int j = i + lane; j < nZ; j += TEAM) {
                     double s = R_(i, j);
                     DOT_UNROLL for (int k = i0; k < i; k++) s -= R_(k, i) * R_(k, j);
                     R_(i, j) = s;
@@ -460,8 +468,8 @@ struct QPT {
                 SYNC();
                 if (!(d > QP_ZERO)) return 1 + i;
                 const double dd = sqrt(d);
-                _Pragma("unroll 1") for (int j = i + lane; j < nZ; j += TEAM) R_(i, j) = (j == i) ? dd : R_(i, j) / dd;
-                _Pragma("unroll 1") for (int j = lane; j < i; j += TEAM) R_(i, j) = 0.0;
+                QP_U1 for (int j = i + lane; j < nZ; j += TEAM) R_(i, j) = (j == i) ? dd : R_(i, j) / dd;
+                QP_U1 for (int j = lane; j < i; j += TEAM) R_(i, j) = 0.0;
                 SYNC();
             }
         }
@@ -484,16 +492,16 @@ struct QPT {
         // the diagonal tile of block I+1 is fetched while block I's columns are applied to the trailing unknowns
         auto load_tile = [&](int j0) {
             const int mb = (n - j0 < 32) ? n - j0 : 32;
-            _Pragma("unroll 1") for (int e = lane; e < 32 * 32; e += TEAM) { const int k = e >> 5, i = e & 31; if (k < mb && i < mb && k <= i) Ds[k][i] = R_(j0 + k, j0 + i); }
+            QP_U1 for (int e = lane; e < 32 * 32; e += TEAM) { const int k = e >> 5, i = e & 31; if (k < mb && i < mb && k <= i) Ds[k][i] = R_(j0 + k, j0 + i); }
         };
         if (n > 0) load_tile(0);
         SYNC();
-        _Pragma("unroll 1") for (int i0 = 0; i0 < n; i0 += 32) {
+        QP_U1 for (int i0 = 0; i0 < n; i0 += 32) {
             const int nb = (n - i0 < 32) ? n - i0 : 32;
             if (lane < 32) {
                 double zi = (l < nb) ? z[i0 + l] : 0.0;
                 const double ri = (l < nb) ? 1.0 / Ds[l][l] : 0.0;  // pivot reciprocals in parallel; the chain only multiplies
-                _Pragma("unroll 1") for (int k = 0; k < nb; k++) {
+                QP_U1 for (int k = 0; k < nb; k++) {
                     const double uk = quot(__shfl_sync(0xffffffffu, zi, k), Ds[k][k], __shfl_sync(0xffffffffu, ri, k));
                     if (l == k) zi = uk;
                     else if (l > k && l < nb) zi -= Ds[k][l] * uk;
@@ -501,7 +509,7 @@ struct QPT {
                 if (l < nb) { z[i0 + l] = zi; if (col >= 0) R_(i0 + l, col) = zi; }
             }
             SYNC();
-            _Pragma("unroll 1") for (int i = i0 + nb + lane; i < n; i += TEAM) {
+            QP_U1 for (int i = i0 + nb + lane; i < n; i += TEAM) {
                 double s = z[i];
                 _Pragma("unroll 16") for (int k = 0; k < nb; k++) s -= R_(i0 + k, i) * z[i0 + k];  // 16 loads in flight per thread
                 z[i] = s;
@@ -518,16 +526,16 @@ struct QPT {
         const int l = lane & 31;
         auto load_tile = [&](int j0) {
             const int mb = (n - j0 < 32) ? n - j0 : 32;
-            _Pragma("unroll 1") for (int e = lane; e < 32 * 32; e += TEAM) { const int k = e >> 5, i = e & 31; if (k < mb && i < mb && k <= i) Ds[k][i] = R_(j0 + k, j0 + i); }
+            QP_U1 for (int e = lane; e < 32 * 32; e += TEAM) { const int k = e >> 5, i = e & 31; if (k < mb && i < mb && k <= i) Ds[k][i] = R_(j0 + k, j0 + i); }
         };
         if (n > 0) load_tile(((n - 1) >> 5) << 5);
         SYNC();
-        _Pragma("unroll 1") for (int i0 = ((n - 1) >> 5) << 5; i0 >= 0; i0 -= 32) {
+        QP_U1 for (int i0 = ((n - 1) >> 5) << 5; i0 >= 0; i0 -= 32) {
             const int nb = (n - i0 < 32) ? n - i0 : 32;
             if (lane < 32) {
                 double zi = (l < nb) ? z[i0 + l] : 0.0;
                 const double ri = (l < nb) ? 1.0 / Ds[l][l] : 0.0;
-                _Pragma("unroll 1") for (int k = nb - 1; k >= 0; k--) {
+                QP_U1 for (int k = nb - 1; k >= 0; k--) {
                     const double zk = quot(__shfl_sync(0xffffffffu, zi, k), Ds[k][k], __shfl_sync(0xffffffffu, ri, k));
                     if (l == k) zi = zk;
                     else if (l < k) zi -= Ds[l][k] * zk;
@@ -535,7 +543,7 @@ struct QPT {
                 if (l < nb) z[i0 + l] = zi;
             }
             SYNC();
-            _Pragma("unroll 1") for (int i = lane; i < i0; i += TEAM) {
+            QP_U1 for (int i = lane; i < i0; i += TEAM) {
                 double s = z[i];
                 _Pragma("unroll 16") for (int k = nb - 1; k >= 0; k--) s -= R_(i, i0 + k) * z[i0 + k];
                 z[i] = s;
@@ -550,7 +558,7 @@ struct QPT {
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC, b = nZ - 1;
         double *RT = V_(RT), *w = V_(w);
         if (sA.is_lp) {
-            _Pragma("unroll 1") for (int a_ = lane; a_ < b; a_ += TEAM) { R_(a_, b) = 0.0; R_(b, a_) = 0.0; }
+            QP_U1 for (int a_ = lane; a_ < b; a_ += TEAM) { R_(a_, b) = 0.0; R_(b, a_) = 0.0; }
             if (lane == 0) R_(b, b) = sqrt(QP_EPS_REG);
             SYNC();
             return 1;
@@ -558,7 +566,7 @@ struct QPT {
         const double *Q = V_(Q), *t2 = V_(t2);
         const short* FR = FR_;
         proj_column(b);
-        _Pragma("unroll 1") for (int a_ = lane; a_ <= b; a_ += TEAM) {
+        QP_U1 for (int a_ = lane; a_ <= b; a_ += TEAM) {
             double s = 0.0;
             DOT_UNROLL for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
             w[a_] = s;
@@ -568,13 +576,13 @@ struct QPT {
         if constexpr (TEAM > 32) fwd_solve_R_blocked(w, b, b);
         else {
         double* rinv = V_(dy);  // dead between two homotopy steps
-        _Pragma("unroll 1") for (int k = lane; k < b; k += TEAM) rinv[k] = 1.0 / R_(k, k);
+        QP_U1 for (int k = lane; k < b; k += TEAM) rinv[k] = 1.0 / R_(k, k);
         SYNC();
-        _Pragma("unroll 1") for (int k = 0; k < b; k++) {
+        QP_U1 for (int k = 0; k < b; k++) {
             double rk = quot(w[k], R_(k, k), rinv[k]);
             SYNC();
             if (lane == 0) R_(k, b) = rk;
-            _Pragma("unroll 1") for (int i = k + 1 + lane; i < b; i += TEAM) w[i] -= R_(k, i) * rk;
+            QP_U1 for (int i = k + 1 + lane; i < b; i += TEAM) w[i] -= R_(k, i) * rk;
             SYNC();
         }
         }
@@ -584,7 +592,7 @@ struct QPT {
         SYNC();  // every lane has read w[b] / R(.,b) before a caller may overwrite them (uniform decision)
         if (!ok) return 0;
         if (lane == 0) R_(b, b) = sqrt(rho2);
-        _Pragma("unroll 1") for (int a_ = lane; a_ < b; a_ += TEAM) R_(b, a_) = 0.0;
+        QP_U1 for (int a_ = lane; a_ < b; a_ += TEAM) R_(b, a_) = 0.0;
         SYNC();
         return 1;
     }
@@ -596,9 +604,9 @@ struct QPT {
         double *a = V_(a), *w = V_(w);
         const double *Q = V_(Q), *Av = V_(Av);
         const short* FR = FR_;
-        _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) a[p] = A_entry(pat, Av, c, FR[p]);
+        QP_U1 for (int p = lane; p < nFR; p += TEAM) a[p] = A_entry(pat, Av, c, FR[p]);
         SYNC();
-        _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) {
+        QP_U1 for (int j = lane; j < nFR; j += TEAM) {
             double s = 0.0;
             DOT_UNROLL for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * a[p];
             w[j] = s;
@@ -618,7 +626,7 @@ struct QPT {
         QP_CTX
         double *t2 = V_(t2), *t3 = V_(t3);
         const double* w = V_(w);
-        _Pragma("unroll 1") for (int j = lane; j + 1 < cnt; j += TEAM) {
+        QP_U1 for (int j = lane; j + 1 < cnt; j += TEAM) {
             double S = w[0] * w[0];
             bool anyprev = false;  // a non-zero entry before j: then a_j = sqrt(S_j), else a_j = w_j (signed)
             DOT_UNROLL for (int k = 1; k <= j; k++) { anyprev = anyprev || (w[k - 1] != 0.0); S = S + w[k] * w[k]; }
@@ -644,17 +652,17 @@ struct QPT {
         double *Q = V_(Q), *RT = V_(RT);
         const double *t2 = V_(t2), *t3 = V_(t3), *w = V_(w);
         double r = rotation_chain(nZ);
-        _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
+        QP_U1 for (int p = lane; p < nFR; p += TEAM) {
             double* q = Q + p * ld;
             double qa = q[0];
-            _Pragma("unroll 1") for (int j = 0; j + 1 < nZ; j++) {
+            QP_U1 for (int j = 0; j + 1 < nZ; j++) {
                 double cs = t2[j], sn = t3[j], qb = q[j + 1];
                 q[j] = cs * qa - sn * qb;
                 qa = sn * qa + cs * qb;
             }
             if (nZ > 0) q[nZ - 1] = qa;
         }
-        _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) T_(nAC, j) = (j > nZ - 1) ? w[j] : ((j == nZ - 1) ? r : 0.0);
+        QP_U1 for (int j = lane; j < nFR; j += TEAM) T_(nAC, j) = (j > nZ - 1) ? w[j] : ((j == nZ - 1) ? r : 0.0);
         if (lane == 0) { AC_[nAC] = (short)c; posAC_[c] = (short)nAC; sC_[c] = (short)status; hdr[1] = nAC + 1; }
         SYNC();
     }
@@ -665,17 +673,17 @@ struct QPT {
         short *AC = AC_, *posAC = posAC_;
         const int k = posAC[c];
         SYNC();  // every thread holds nAC and k before lane 0 rewrites them below (the loops may be empty)
-        _Pragma("unroll 1") for (int i = k + 1; i < nAC; i++) {
+        QP_U1 for (int i = k + 1; i < nAC; i++) {
             int cL = nFR - 1 - i;
             double cs, sn, r;
             givens(T_(i, cL), T_(i, cL + 1), cs, sn, r);
             SYNC();
-            _Pragma("unroll 1") for (int ii = i + lane; ii < nAC; ii += TEAM) {
+            QP_U1 for (int ii = i + lane; ii < nAC; ii += TEAM) {
                 double ta = T_(ii, cL), tb = T_(ii, cL + 1);
                 T_(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
                 T_(ii, cL + 1) = sn * ta + cs * tb;
             }
-            _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
+            QP_U1 for (int p = lane; p < nFR; p += TEAM) {
                 double qa = Q[p * ld + cL], qb = Q[p * ld + cL + 1];
                 Q[p * ld + cL] = cs * qa - sn * qb;
                 Q[p * ld + cL + 1] = sn * qa + cs * qb;
@@ -683,12 +691,12 @@ struct QPT {
             SYNC();
         }
         // shift rows k+1.. up by one (row i -> i-1): sequential over rows, lanes over columns
-        _Pragma("unroll 1") for (int i = k + 1; i < nAC; i++) {
-            _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) T_(i - 1, j) = T_(i, j);
+        QP_U1 for (int i = k + 1; i < nAC; i++) {
+            QP_U1 for (int j = lane; j < nFR; j += TEAM) T_(i - 1, j) = T_(i, j);
             SYNC();
         }
         if (lane == 0) {
-            _Pragma("unroll 1") for (int i = k + 1; i < nAC; i++) { AC[i - 1] = AC[i]; posAC[AC[i - 1]] = (short)(i - 1); }
+            QP_U1 for (int i = k + 1; i < nAC; i++) { AC[i - 1] = AC[i]; posAC[AC[i - 1]] = (short)(i - 1); }
             sC_[c] = 0; posAC[c] = -1; hdr[1] = nAC - 1;
         }
         SYNC();
@@ -698,7 +706,7 @@ struct QPT {
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC, p = posFR_[v];
         double* w = V_(w);
         const double* Q = V_(Q);
-        _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) w[j] = Q[p * ld + j];
+        QP_U1 for (int j = lane; j < nFR; j += TEAM) w[j] = Q[p * ld + j];
         SYNC();
         double z2 = 0.0;
         DOT_UNROLL for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
@@ -713,10 +721,10 @@ struct QPT {
         short *FR = FR_, *posFR = posFR_;
         const int p = posFR[v];
         rotation_chain(nFR);
-        _Pragma("unroll 1") for (int pp = lane; pp < nFR; pp += TEAM) {
+        QP_U1 for (int pp = lane; pp < nFR; pp += TEAM) {
             double* q = Q + pp * ld;
             double qa = q[0];
-            _Pragma("unroll 1") for (int j = 0; j + 1 < nFR; j++) {
+            QP_U1 for (int j = 0; j + 1 < nFR; j++) {
                 double cs = t2[j], sn = t3[j], qb = q[j + 1];
                 q[j] = cs * qa - sn * qb;
                 qa = sn * qa + cs * qb;
@@ -724,10 +732,10 @@ struct QPT {
             q[nFR - 1] = qa;
         }
         // T rows: row i is touched by rotations j >= nFR-2-i (and j >= nZ-1)
-        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) {
+        QP_U1 for (int i = lane; i < nAC; i += TEAM) {
             int j0 = nFR - 2 - i; if (j0 < nZ - 1) j0 = nZ - 1; if (j0 < 0) j0 = 0;
             double ta = T_(i, j0);
-            _Pragma("unroll 1") for (int j = j0; j + 1 < nFR; j++) {
+            QP_U1 for (int j = j0; j + 1 < nFR; j++) {
                 double cs = t2[j], sn = t3[j], tb = T_(i, j + 1);
                 T_(i, j) = cs * ta - sn * tb;
                 ta = sn * ta + cs * tb;
@@ -737,7 +745,7 @@ struct QPT {
         SYNC();
         const int last = nFR - 1;
         if (p != last) {
-            _Pragma("unroll 1") for (int j = lane; j < nFR - 1; j += TEAM) Q[p * ld + j] = Q[last * ld + j];
+            QP_U1 for (int j = lane; j < nFR - 1; j += TEAM) Q[p * ld + j] = Q[last * ld + j];
             if (lane == 0) { short vl = FR[last]; FR[p] = vl; posFR[vl] = (short)p; }
         }
         if (lane == 0) { posFR[v] = -1; sB_[v] = (short)status; hdr[0] = nFR - 1; }
@@ -754,29 +762,29 @@ struct QPT {
         const pidx *Ap = pat + sA.pAp, *Ai = pat + sA.pAi;
         const short* AC = AC_;
         SYNC();  // all lanes have read hdr[0] before lane 0 updates it below
-        _Pragma("unroll 1") for (int j = lane; j < nFR; j += TEAM) { Q[nFR * ld + j] = 0.0; Q[j * ld + nFR] = 0.0; }
-        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) {
+        QP_U1 for (int j = lane; j < nFR; j += TEAM) { Q[nFR * ld + j] = 0.0; Q[j * ld + nFR] = 0.0; }
+        QP_U1 for (int i = lane; i < nAC; i += TEAM) {
             int r = AC[i];
             double s = 0.0;
             int e1 = Ap[v + 1];
-            _Pragma("unroll 1") for (int e = Ap[v]; e < e1; e++)
+            QP_U1 for (int e = Ap[v]; e < e1; e++)
                 if (Ai[e] == r) s += Av[e];
             T_(i, nFR) = s;
         }
         if (lane == 0) { Q[nFR * ld + nFR] = 1.0; FR_[nFR] = (short)v; posFR_[v] = (short)nFR; sB_[v] = 0; hdr[0] = nFR + 1; }
         nFR++;
         SYNC();
-        _Pragma("unroll 1") for (int i = 0; i < nAC; i++) {
+        QP_U1 for (int i = 0; i < nAC; i++) {
             int cL = nFR - 2 - i;
             double cs, sn, r;
             givens(T_(i, cL), T_(i, cL + 1), cs, sn, r);
             SYNC();
-            _Pragma("unroll 1") for (int ii = i + lane; ii < nAC; ii += TEAM) {
+            QP_U1 for (int ii = i + lane; ii < nAC; ii += TEAM) {
                 double ta = T_(ii, cL), tb = T_(ii, cL + 1);
                 T_(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
                 T_(ii, cL + 1) = sn * ta + cs * tb;
             }
-            _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
+            QP_U1 for (int p = lane; p < nFR; p += TEAM) {
                 double qa = Q[p * ld + cL], qb = Q[p * ld + cL + 1];
                 Q[p * ld + cL] = cs * qa - sn * qb;
                 Q[p * ld + cL + 1] = sn * qa + cs * qb;
@@ -793,14 +801,14 @@ struct QPT {
         const int nFR = hdr[0], nAC = hdr[1];
         const double* RT = V_(RT);
         double* rinv = V_(dAx);  // pivot reciprocals, one per lane in parallel: the sequential part below only multiplies
-        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) rinv[i] = 1.0 / T_(i, nFR - 1 - i);
+        QP_U1 for (int i = lane; i < nAC; i += TEAM) rinv[i] = 1.0 / T_(i, nFR - 1 - i);
         SYNC();
-        _Pragma("unroll 1") for (int i = 0; i < nAC; i++) {
+        QP_U1 for (int i = 0; i < nAC; i++) {
             int d = nFR - 1 - i;
             double vi = quot(b[i], T_(i, d), rinv[i]);
             SYNC();
             if (lane == 0) v[d] = vi;
-            _Pragma("unroll 1") for (int k = i + 1 + lane; k < nAC; k += TEAM) b[k] -= T_(k, d) * vi;
+            QP_U1 for (int k = i + 1 + lane; k < nAC; k += TEAM) b[k] -= T_(k, d) * vi;
             SYNC();
         }
     }
@@ -810,14 +818,14 @@ struct QPT {
         const int nFR = hdr[0], nAC = hdr[1];
         const double* RT = V_(RT);
         double* rinv = V_(dAx);
-        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) rinv[i] = 1.0 / T_(i, nFR - 1 - i);
+        QP_U1 for (int i = lane; i < nAC; i += TEAM) rinv[i] = 1.0 / T_(i, nFR - 1 - i);
         SYNC();
-        _Pragma("unroll 1") for (int i = nAC - 1; i >= 0; i--) {
+        QP_U1 for (int i = nAC - 1; i >= 0; i--) {
             int d = nFR - 1 - i;
             double ui = quot(r[d], T_(i, d), rinv[i]);
             SYNC();
             if (lane == 0) u[i] = ui;
-            _Pragma("unroll 1") for (int k = lane; k < i; k += TEAM) { int dk = nFR - 1 - k; r[dk] -= T_(i, dk) * ui; }
+            QP_U1 for (int k = lane; k < i; k += TEAM) { int dk = nFR - 1 - k; r[dk] -= T_(i, dk) * ui; }
             SYNC();
         }
     }
@@ -831,14 +839,14 @@ struct QPT {
         double *dx = V_(dx), *dy = V_(dy), *t1 = V_(t1), *t2 = V_(t2), *t3 = V_(t3), *yv = V_(yv), *zv = V_(zv);
         const double *Q = V_(Q), *RT = V_(RT);
         const short *sB = sB_, *FR = FR_, *AC = AC_;
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) dx[i] = (sB[i] != 0) ? dxFX[i] : 0.0;
+        QP_U1 for (int i = lane; i < nV; i += TEAM) dx[i] = (sB[i] != 0) ? dxFX[i] : 0.0;
         SYNC();
         if (nAC > 0) {
             mulA(dx, t2);
-            _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) t3[i] = dbAC[i] - t2[AC[i]];
+            QP_U1 for (int i = lane; i < nAC; i += TEAM) t3[i] = dbAC[i] - t2[AC[i]];
             SYNC();
             solve_T(t3, yv);
-            _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
+            QP_U1 for (int p = lane; p < nFR; p += TEAM) {
                 double s = 0.0;
                 DOT_UNROLL for (int j = nZ; j < nFR; j++) s += Q[p * ld + j] * yv[j];
                 dx[FR[p]] = s;
@@ -847,7 +855,7 @@ struct QPT {
         }
         if (nZ > 0) {
             mulH(dx, t1);
-            _Pragma("unroll 1") for (int j = lane; j < nZ; j += TEAM) {
+            QP_U1 for (int j = lane; j < nZ; j += TEAM) {
                 double s = 0.0;
                 DOT_UNROLL for (int p = 0; p < nFR; p++) { int v = FR[p]; s += Q[p * ld + j] * (t1[v] + dgvec[v]); }
                 zv[j] = -s;
@@ -859,24 +867,24 @@ struct QPT {
                 bwd_solve_R_blocked(zv, nZ);
             } else {
                 double* rinv = V_(dy);  // dy is dead here (rewritten below)
-                _Pragma("unroll 1") for (int k = lane; k < nZ; k += TEAM) rinv[k] = 1.0 / R_(k, k);
+                QP_U1 for (int k = lane; k < nZ; k += TEAM) rinv[k] = 1.0 / R_(k, k);
                 SYNC();
-                _Pragma("unroll 1") for (int k = 0; k < nZ; k++) {
+                QP_U1 for (int k = 0; k < nZ; k++) {
                     double uk = quot(zv[k], R_(k, k), rinv[k]);
                     SYNC();
                     if (lane == 0) zv[k] = uk;
-                    _Pragma("unroll 1") for (int i = k + 1 + lane; i < nZ; i += TEAM) zv[i] -= R_(k, i) * uk;
+                    QP_U1 for (int i = k + 1 + lane; i < nZ; i += TEAM) zv[i] -= R_(k, i) * uk;
                     SYNC();
                 }
-                _Pragma("unroll 1") for (int k = nZ - 1; k >= 0; k--) {
+                QP_U1 for (int k = nZ - 1; k >= 0; k--) {
                     double zk = quot(zv[k], R_(k, k), rinv[k]);
                     SYNC();
                     if (lane == 0) zv[k] = zk;
-                    _Pragma("unroll 1") for (int i = lane; i < k; i += TEAM) zv[i] -= R_(i, k) * zk;
+                    QP_U1 for (int i = lane; i < k; i += TEAM) zv[i] -= R_(i, k) * zk;
                     SYNC();
                 }
             }
-            _Pragma("unroll 1") for (int p = lane; p < nFR; p += TEAM) {
+            QP_U1 for (int p = lane; p < nFR; p += TEAM) {
                 double s = 0.0;
                 DOT_UNROLL for (int j = 0; j < nZ; j++) s += Q[p * ld + j] * zv[j];
                 dx[FR[p]] += s;
@@ -884,23 +892,23 @@ struct QPT {
             SYNC();
         }
         mulH(dx, t1);
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) t1[i] += dgvec[i];
-        _Pragma("unroll 1") for (int i = lane; i < nT; i += TEAM) dy[i] = 0.0;
+        QP_U1 for (int i = lane; i < nV; i += TEAM) t1[i] += dgvec[i];
+        QP_U1 for (int i = lane; i < nT; i += TEAM) dy[i] = 0.0;
         SYNC();
         if (nAC > 0) {
-            _Pragma("unroll 1") for (int j = nZ + lane; j < nFR; j += TEAM) {
+            QP_U1 for (int j = nZ + lane; j < nFR; j += TEAM) {
                 double s = 0.0;
                 DOT_UNROLL for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * t1[FR[p]];
                 yv[j] = s;
             }
             SYNC();
             solve_Tt(yv, t3);
-            _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) dy[nV + AC[i]] = t3[i];
+            QP_U1 for (int i = lane; i < nAC; i += TEAM) dy[nV + AC[i]] = t3[i];
             SYNC();
             mulAT(dy + nV, t2);
-            _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) dy[i] = t1[i] - t2[i];
+            QP_U1 for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) dy[i] = t1[i] - t2[i];
         } else {
-            _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) dy[i] = t1[i];
+            QP_U1 for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) dy[i] = t1[i];
         }
         SYNC();
     }
@@ -912,7 +920,7 @@ struct QPT {
         const double *x = V_(x), *y = V_(y);
         mulAT(y + nV, t2);
         mulH(x, t1);
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) g[i] = t2[i] + y[i] - t1[i];
+        QP_U1 for (int i = lane; i < nV; i += TEAM) g[i] = t2[i] + y[i] - t1[i];
         SYNC();
     }
     static __device__ QP_FN void drift_correction() {
@@ -920,13 +928,13 @@ struct QPT {
         double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA);
         const short *sB = sB_, *sC = sC_;
         mulA(x, Ax);
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
+        QP_U1 for (int i = lane; i < nV; i += TEAM) {
             int s = sB[i]; double xi = x[i];
             if (s < 0) { lb[i] = xi; if (ub[i] < xi) ub[i] = xi; if (y[i] < 0) y[i] = 0.0; }
             else if (s > 0) { ub[i] = xi; if (lb[i] > xi) lb[i] = xi; if (y[i] > 0) y[i] = 0.0; }
             else { if (lb[i] > xi) lb[i] = xi; if (ub[i] < xi) ub[i] = xi; y[i] = 0.0; }
         }
-        _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) {
+        QP_U1 for (int i = lane; i < nC; i += TEAM) {
             int s = sC[i]; double ax = Ax[i];
             if (s < 0) { lbA[i] = ax; if (ubA[i] < ax) ubA[i] = ax; if (y[nV + i] < 0) y[nV + i] = 0.0; }
             else if (s > 0) { ubA[i] = ax; if (lbA[i] > ax) lbA[i] = ax; if (y[nV + i] > 0) y[nV + i] = 0.0; }
@@ -943,7 +951,7 @@ struct QPT {
         const int nRamp = nV + nC + nC + nV;
         const double r0 = 0.5, r1 = 1.0;
         mulA(x, Ax);
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
+        QP_U1 for (int i = lane; i < nV; i += TEAM) {
             double tP = (double)((i + ramp_offset) % nRamp) / (double)(nRamp - 1);
             double rP = (1.0 - tP) * r0 + tP * r1;
             double tD = (double)((nV + nC + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
@@ -957,7 +965,7 @@ struct QPT {
             if (s > 0) { ub[i] = xi; y[i] = -rD; }
             if (s == 0) y[i] = 0.0;
         }
-        _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) {
+        QP_U1 for (int i = lane; i < nC; i += TEAM) {
             double tP = (double)((nV + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
             double rP = (1.0 - tP) * r0 + tP * r1;
             double tD = (double)((nV + nC + nV + i + ramp_offset) % nRamp) / (double)(nRamp - 1);
@@ -985,13 +993,13 @@ struct QPT {
         double *xiC = V_(zv), *xiB = V_(dx), *yv = V_(yv), *t2 = V_(t2), *t3 = V_(t3), *y = V_(y);
         const double *w = V_(w), *Av = V_(Av);
         const short *sB = sB_, *sC = sC_, *AC = AC_, *posAC = posAC_;
-        _Pragma("unroll 1") for (int j = nZ + lane; j < nFR; j += TEAM) yv[j] = w[j];
+        QP_U1 for (int j = nZ + lane; j < nFR; j += TEAM) yv[j] = w[j];
         SYNC();
         solve_Tt(yv, xiC);
-        _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) { int p = posAC[i]; t3[i] = (p >= 0) ? xiC[p] : 0.0; }
+        QP_U1 for (int i = lane; i < nC; i += TEAM) { int p = posAC[i]; t3[i] = (p >= 0) ? xiC[p] : 0.0; }
         SYNC();
         mulAT(t3, t2);
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
+        QP_U1 for (int i = lane; i < nV; i += TEAM) {
             if (sB[i] == 0) { xiB[i] = 0.0; continue; }
             double ai = (c >= 0) ? A_entry(pat, Av, c, i) : 0.0;
             xiB[i] = ai - t2[i];
@@ -999,13 +1007,13 @@ struct QPT {
         SYNC();
         const double sgn = (status < 0) ? 1.0 : -1.0;
         double best = QP_INFTY; int bpos = 0x7fffffff;
-        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) {
+        QP_U1 for (int i = lane; i < nAC; i += TEAM) {
             int ci = AC[i]; double xi = sgn * xiC[i], yy = y[nV + ci]; double t = QP_INFTY;
             if (sC[ci] < 0) { if (xi > QP_ZERO && yy >= 0.0) t = yy / xi; }
             else { if (xi < -QP_ZERO && yy <= 0.0) t = yy / xi; }
             if (t < QP_INFTY && key_less(t, i, best, bpos)) { best = t; bpos = i; }
         }
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
+        QP_U1 for (int i = lane; i < nV; i += TEAM) {
             if (sB[i] == 0) continue;
             double xi = sgn * xiB[i], yy = y[i]; double t = QP_INFTY;
             if (sB[i] < 0) { if (xi > QP_ZERO && yy >= 0.0) t = yy / xi; }
@@ -1018,8 +1026,8 @@ struct QPT {
         const int kind = mk.pos >= nC ? 1 : 0;
         const int idx = kind ? mk.pos - nC : AC[mk.pos];
         SYNC();
-        _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) y[nV + AC[i]] -= ymin * sgn * xiC[i];
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) y[i] -= ymin * sgn * xiB[i];
+        QP_U1 for (int i = lane; i < nAC; i += TEAM) y[nV + AC[i]] -= ymin * sgn * xiC[i];
+        QP_U1 for (int i = lane; i < nV; i += TEAM) if (sB[i] != 0) y[i] -= ymin * sgn * xiB[i];
         SYNC();
         if (lane == 0) {
             if (c >= 0) y[nV + c] = sgn * ymin; else y[v] = sgn * ymin;
@@ -1040,15 +1048,15 @@ struct QPT {
         const double *gN = V_(gN), *lbN = V_(lbN), *ubN = V_(ubN), *lbAN = V_(lbAN), *ubAN = V_(ubAN);
         short *sB = sB_, *sC = sC_, *AC = AC_;
         iters = 0;
-        _Pragma("unroll 1") for (int it = 0;; it++) {
+        QP_U1 for (int it = 0;; it++) {
             const int nAC = hdr[1];
             // w[0..nV) <- bound shift of fixed variables, w[nV..) <- constraint shift by AC position, a <- dg
-            _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
+            QP_U1 for (int i = lane; i < nV; i += TEAM) {
                 int s = sB[i];
                 w[i] = s < 0 ? (lbN[i] - lb[i]) : (s > 0 ? (ubN[i] - ub[i]) : 0.0);
                 a[i] = gN[i] - g[i];
             }
-            _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) { int ci = AC[i]; w[nV + i] = sC[ci] < 0 ? (lbAN[ci] - lbA[ci]) : (ubAN[ci] - ubA[ci]); }
+            QP_U1 for (int i = lane; i < nAC; i += TEAM) { int ci = AC[i]; w[nV + i] = sC[ci] < 0 ? (lbAN[ci] - lbA[ci]) : (ubAN[ci] - ubA[ci]); }
             SYNC();
             step_direction(a, w, w + nV);
             mulA(dx, dAx);
@@ -1063,23 +1071,23 @@ struct QPT {
             if (t_ < 1.0 && key_less(t_, (pos), best, bpos)) { best = t_; bpos = (pos); }         \
         }                                                                                         \
     }
-            _Pragma("unroll 1") for (int i = lane; i < nAC; i += TEAM) {
+            QP_U1 for (int i = lane; i < nAC; i += TEAM) {
                 int ci = AC[i];
                 if (sC[ci] < 0) CONSIDER(y[nV + ci], -dy[nV + ci], i) else CONSIDER(-y[nV + ci], dy[nV + ci], i)
             }
-            _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
+            QP_U1 for (int i = lane; i < nV; i += TEAM) {
                 int s = sB[i];
                 if (s == 0) continue;
                 if (s < 0) CONSIDER(y[i], -dy[i], nC + i) else CONSIDER(-y[i], dy[i], nC + i)
             }
-            _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) {
+            QP_U1 for (int i = lane; i < nC; i += TEAM) {
                 if (sC[i] != 0) continue;
                 double num = Ax[i] - lbA[i]; if (num < 0) num = 0;
                 CONSIDER(num, (lbAN[i] - lbA[i]) - dAx[i], nC + nV + i)
                 num = ubA[i] - Ax[i]; if (num < 0) num = 0;
                 CONSIDER(num, dAx[i] - (ubAN[i] - ubA[i]), nC + nV + nC + i)
             }
-            _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
+            QP_U1 for (int i = lane; i < nV; i += TEAM) {
                 if (sB[i] != 0) continue;
                 double num = x[i] - lb[i]; if (num < 0) num = 0;
                 CONSIDER(num, (lbN[i] - lb[i]) - dx[i], 2 * nC + nV + nC + i)
@@ -1102,21 +1110,21 @@ struct QPT {
             SYNC();
             // ---- step
             if (bc_idx < 0) {
-                _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) { x[i] += dx[i]; g[i] = gN[i]; lb[i] = lbN[i]; ub[i] = ubN[i]; }
-                _Pragma("unroll 1") for (int i = lane; i < nT; i += TEAM) y[i] += dy[i];
-                _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) { Ax[i] += dAx[i]; lbA[i] = lbAN[i]; ubA[i] = ubAN[i]; }
+                QP_U1 for (int i = lane; i < nV; i += TEAM) { x[i] += dx[i]; g[i] = gN[i]; lb[i] = lbN[i]; ub[i] = ubN[i]; }
+                QP_U1 for (int i = lane; i < nT; i += TEAM) y[i] += dy[i];
+                QP_U1 for (int i = lane; i < nC; i += TEAM) { Ax[i] += dAx[i]; lbA[i] = lbAN[i]; ubA[i] = ubAN[i]; }
                 SYNC();
                 iters = it;
                 return ST_OPTIMAL;
             }
             if (it >= max_iter) { iters = it; return ST_HOMOTOPY; }
             if (tau > 0.0) {
-                _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
+                QP_U1 for (int i = lane; i < nV; i += TEAM) {
                     x[i] += tau * dx[i]; g[i] += tau * a[i];
                     lb[i] += tau * (lbN[i] - lb[i]); ub[i] += tau * (ubN[i] - ub[i]);
                 }
-                _Pragma("unroll 1") for (int i = lane; i < nT; i += TEAM) y[i] += tau * dy[i];
-                _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) {
+                QP_U1 for (int i = lane; i < nT; i += TEAM) y[i] += tau * dy[i];
+                QP_U1 for (int i = lane; i < nC; i += TEAM) {
                     Ax[i] += tau * dAx[i];
                     lbA[i] += tau * (lbAN[i] - lbA[i]); ubA[i] += tau * (ubAN[i] - ubA[i]);
                 }
@@ -1189,10 +1197,10 @@ struct QPT {
         QP_CTX
         double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *g = V_(g), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA);
         short *sB = sB_, *sC = sC_, *posFR = posFR_, *posAC = posAC_;
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) {
+        QP_U1 for (int i = lane; i < nV; i += TEAM) {
             x[i] = 0.0; y[i] = 0.0; sB[i] = -1; posFR[i] = -1; g[i] = 0.0; lb[i] = 0.0; ub[i] = QP_BOUND_RELAX;
         }
-        _Pragma("unroll 1") for (int i = lane; i < nC; i += TEAM) {
+        QP_U1 for (int i = lane; i < nC; i += TEAM) {
             y[nV + i] = 0.0; sC[i] = 0; posAC[i] = -1; Ax[i] = 0.0; lbA[i] = -QP_BOUND_RELAX; ubA[i] = QP_BOUND_RELAX;
         }
         if (lane == 0) { hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; }
@@ -1205,13 +1213,13 @@ struct QPT {
         double *Q = V_(Q), *dAx = V_(dAx), *dy = V_(dy), *y = V_(y);
         short *sC = sC_, *AC = AC_, *posAC = posAC_;
         // remember (constraint, status) by AC position in dAx (nC) and dy[nV..] (nC): neither is touched below
-        _Pragma("unroll 1") for (int i = lane; i < nAC_old; i += TEAM) { int ci = AC[i]; dAx[i] = (double)ci; dy[nV + i] = (double)sC[ci]; }
+        QP_U1 for (int i = lane; i < nAC_old; i += TEAM) { int ci = AC[i]; dAx[i] = (double)ci; dy[nV + i] = (double)sC[ci]; }
         SYNC();
-        _Pragma("unroll 1") for (int k = lane; k < nFR * nFR; k += TEAM) { int i = k / nFR, j = k % nFR; Q[i * ld + j] = (i == j) ? 1.0 : 0.0; }
-        _Pragma("unroll 1") for (int i = lane; i < nAC_old; i += TEAM) { int ci = (int)dAx[i]; sC[ci] = 0; posAC[ci] = -1; }
+        QP_U1 for (int k = lane; k < nFR * nFR; k += TEAM) { int i = k / nFR, j = k % nFR; Q[i * ld + j] = (i == j) ? 1.0 : 0.0; }
+        QP_U1 for (int i = lane; i < nAC_old; i += TEAM) { int ci = (int)dAx[i]; sC[ci] = 0; posAC[ci] = -1; }
         if (lane == 0) hdr[1] = 0;
         SYNC();
-        _Pragma("unroll 1") for (int i = 0; i < nAC_old; i++) {
+        QP_U1 for (int i = 0; i < nAC_old; i++) {
             int ci = (int)dAx[i]; int st = (int)dy[nV + i];
             double z2, a2;
             constraint_w(ci, z2, a2);
@@ -1233,8 +1241,8 @@ struct QPT {
         const short *sB = sB_, *sC = sC_;
         double* xo = sA.x + (size_t)b * nV;
         double* yo = sA.y + (size_t)b * nT;
-        _Pragma("unroll 1") for (int i = lane; i < nV; i += TEAM) xo[i] = x[i];
-        _Pragma("unroll 1") for (int i = lane; i < nT; i += TEAM) yo[i] = y[i];
+        QP_U1 for (int i = lane; i < nV; i += TEAM) xo[i] = x[i];
+        QP_U1 for (int i = lane; i < nT; i += TEAM) yo[i] = y[i];
         if (sA.wsB) for (int i = lane; i < nV; i += TEAM) sA.wsB[(size_t)b * nV + i] = (signed char)sB[i];
         if (sA.wsC) for (int i = lane; i < nC; i += TEAM) sA.wsC[(size_t)b * nC + i] = (signed char)sC[i];
         // Hx (unregularised) in t1, A x in Ax, A'y_c in t2
@@ -1244,25 +1252,25 @@ struct QPT {
         if (lane == 0) {
             const double SQRT_M_EPS = 1.0e-8;
             double obj = 0.0;
-            _Pragma("unroll 1") for (int i = 0; i < nV; i++) obj += 0.5 * x[i] * t1[i];
-            _Pragma("unroll 1") for (int i = 0; i < nV; i++) obj += gN[i] * x[i];
+            QP_U1 for (int i = 0; i < nV; i++) obj += 0.5 * x[i] * t1[i];
+            QP_U1 for (int i = 0; i < nV; i++) obj += gN[i] * x[i];
             sA.obj[b] = obj; sA.status[b] = status; sA.iters[b] = total_iters;
             // qpOASESInterface::get_working_set + test_optimality (src/qpOASESInterface.cpp:835-895, 498-684),
             // evaluated against the target data the caller supplied.
             double primal = 0.0, dual = 0.0, compl_ = 0.0, stat = 0.0;
             int* WB = sA.WB ? sA.WB + (size_t)b * nV : nullptr;
             int* WC = sA.WC ? sA.WC + (size_t)b * nC : nullptr;
-            _Pragma("unroll 1") for (int i = 0; i < nV; i++) {
+            QP_U1 for (int i = 0; i < nV; i++) {
                 double xi = x[i];
                 primal += fmax(0.0, lbN[i] - xi);
                 primal += -fmin(0.0, ubN[i] - xi);
             }
-            _Pragma("unroll 1") for (int i = 0; i < nC; i++) {
+            QP_U1 for (int i = 0; i < nC; i++) {
                 double ax = Ax[i];
                 primal += fmax(0.0, lbAN[i] - ax);
                 primal += -fmin(0.0, ubAN[i] - ax);
             }
-            _Pragma("unroll 1") for (int i = 0; i < nV; i++) {
+            QP_U1 for (int i = 0; i < nV; i++) {
                 int s = sB[i], W; double xi = x[i], yi = y[i];
                 if (s > 0) W = (fabs(xi - lbN[i]) < SQRT_M_EPS) ? -99 : 1;
                 else if (s < 0) W = (fabs(xi - ubN[i]) < SQRT_M_EPS) ? -99 : -1;
@@ -1270,7 +1278,7 @@ struct QPT {
                 if (WB) WB[i] = W;
                 if (W == 0) dual += fabs(yi); else if (W == -1) dual += -fmin(0.0, yi); else if (W == 1) dual += fmax(0.0, yi);
             }
-            _Pragma("unroll 1") for (int i = 0; i < nC; i++) {
+            QP_U1 for (int i = 0; i < nC; i++) {
                 int s = sC[i], W; double ax = Ax[i], yi = y[nV + i];
                 if (s > 0) W = (ax - lbAN[i] < SQRT_M_EPS) ? -99 : 1;       // :874 (comparison inside fabs)
                 else if (s < 0) W = (ax - ubAN[i] < SQRT_M_EPS) ? -99 : -1;  // :880
@@ -1278,17 +1286,17 @@ struct QPT {
                 if (WC) WC[i] = W;
                 if (W == 0) dual += fabs(yi); else if (W == -1) dual += -fmin(0.0, yi); else if (W == 1) dual += fmax(0.0, yi);
             }
-            _Pragma("unroll 1") for (int i = 0; i < nV; i++) {
+            QP_U1 for (int i = 0; i < nV; i++) {
                 double gap = t2[i];
                 gap += y[i]; gap -= gN[i]; gap -= t1[i];
                 stat += fabs(gap);
             }
-            _Pragma("unroll 1") for (int i = 0; i < nV; i++) {
+            QP_U1 for (int i = 0; i < nV; i++) {
                 int s = sB[i]; double xi = x[i], yi = y[i];
                 int W = (s > 0) ? ((fabs(xi - lbN[i]) < SQRT_M_EPS) ? -99 : 1) : (s < 0 ? ((fabs(xi - ubN[i]) < SQRT_M_EPS) ? -99 : -1) : 0);
                 if (W == 0) compl_ += fabs(yi); else if (W == -1) compl_ += fabs(yi * (xi - lbN[i])); else if (W == 1) compl_ += fabs(yi * (ubN[i] - xi));
             }
-            _Pragma("unroll 1") for (int i = 0; i < nC; i++) {
+            QP_U1 for (int i = 0; i < nC; i++) {
                 int s = sC[i]; double ax = Ax[i], yi = y[nV + i];
                 int W = (s > 0) ? ((ax - lbAN[i] < SQRT_M_EPS) ? -99 : 1) : (s < 0 ? ((ax - ubAN[i] < SQRT_M_EPS) ? -99 : -1) : 0);
                 if (W == 0) compl_ += fabs(yi); else if (W == -1) compl_ += fabs(yi * (ax - lbAN[i])); else if (W == 1) compl_ += fabs(yi * (ubAN[i] - ax));

@@ -423,6 +423,19 @@ def run_extras(device):
                            "qp_iters_mean": float(res.qp_iter.mean()), "seconds": dt, "seconds_initialization": t1 - t0, "seconds_all_runs": [r_[0] for r_ in runs], "value_best_of_3": Bs / min(r_[0] for r_ in runs),
                            "note": "device-resident outer loop (csrc/sqp_outer.cu), NVRTC NLP evaluation and every QP/LP on the GPU; starts uploaded from the host, results read back; wall clock"}
         dev.close()
+        try:  # the same solves by the CPU oracle's C restatement of the outer loop on all host cores (bounded sample)
+            from oracle import oracle_py as orc
+            so = orc.SqpOracle(host, r.Options())
+            Xc = np.tile(X, (10, 1))  # 10^5 starts: about a second of CPU work on 16 cores
+            so.solve_batch(Xc[:2000])
+            t0 = time.perf_counter()
+            rc_ = so.solve_batch(Xc)
+            tc = time.perf_counter() - t0
+            ex["sqp_hs071"]["cpu_baseline"] = {"value": Xc.shape[0] / tc, "unit": "solves/s", "cores": int(rc_["threads"]), "kind": "port",
+                                               "sample": "%d HS071 solves in %.2f s (oracle/oracle_sqp.c, one solve per thread at a time)" % (Xc.shape[0], tc),
+                                               "optimal": int((rc_["exitflag"] == 0).sum())}
+        except Exception as e:
+            ex["sqp_hs071"]["cpu_baseline"] = {"error": repr(e)[:200]}
     except Exception as e:  # the extras never take the headline down
         ex["sqp_hs071"] = {"error": repr(e)[:200]}
     try:  # configs[3]: synthetic sparse QP n=256, m=128 (nV=512), batch 64, one QP per CTA

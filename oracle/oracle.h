@@ -151,6 +151,29 @@ int orc_qp_get_max_free(const orc_qp* q);
 /* 1 if the last orc_qp_hotstart_matrices already performed the cold re-init of handle_error (src/qpOASESInterface.cpp:746-754) */
 int orc_qp_get_fell_back(const orc_qp* q);
 
+/* ------------------------------------------------- the caller: Sl1QP outer loop (oracle_sqp.c) -- */
+/* NLP callbacks for ONE instance (generated as C from the .nl DAG by restartsqp_b200/nl_reader.py):
+ * fc: f and c at x;  all: f, c, grad f, Jacobian triplet values, Lagrangian-Hessian triplet values (lam as handed to eval_h). */
+typedef void (*orc_nlp_fc)(const double* x, double* f, double* c);
+typedef void (*orc_nlp_all)(const double* x, const double* lam, double* f, double* c, double* grad, double* jac, double* hess);
+typedef struct {
+    int n, m, zJ, zH;
+    const int *J_row1, *J_col1, *H_row1, *H_col1; /* 1-based triplet patterns (Jacobian column-major, Hessian upper triangle) */
+    const double *x_l, *x_u, *c_l, *c_u;
+    orc_nlp_fc fc;
+    orc_nlp_all all;
+    /* Options, src/Options.cpp:19-57 */
+    int iter_max, penalty_update, penalty_iter_max, qp_maxiter, lp_maxiter;
+    double eta_c, eta_s, eta_e, gamma_c, gamma_e, delta, delta_min, delta_max, tol, penalty_update_tol, rho, rho_max,
+        increase_parm, eps1, eps1_change_parm, eps2, opt_prim_fea_tol, opt_dual_fea_tol, opt_compl_tol, opt_stat_tol;
+} orc_sqp_problem;
+/* Algorithm::initialization + Optimize for one starting point (src/Algorithm.cpp:55-168, 438-472). */
+int orc_sqp_solve(const orc_sqp_problem* P, const double* x0, const double* lam0, double* x_out, double* f_out,
+                  int* exitflag, int* iters, long long* qp_iters, double* kkt_out);
+/* One solve per instance x0[B][n] on the host cores; returns the number of threads used. */
+int orc_sqp_solve_batch(const orc_sqp_problem* P, int B, const double* x0, const double* lam0, double* x, double* f,
+                        int* exitflag, int* iters, long long* qp_iters, double* kkt, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

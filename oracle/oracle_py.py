@@ -37,7 +37,7 @@ def _f64(a):
 def build(force=False):
     """Compile liboracle.so (and _ref/libref_l0.so when /root/reference exists)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_l0.c", "oracle_qp.c", "oracle_batch.c", "oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_l0.c", "oracle_qp.c", "oracle_batch.c", "oracle_sqp.c", "oracle.h", "Makefile")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, capture_output=True)
@@ -242,3 +242,59 @@ def solve_batch(nV, nC, A, H, g, lb, ub, lbA, ubA, is_lp=False, max_iter=1000, n
                                     _dp(Av), 0 if Av.ndim == 1 else Av.shape[1], _dp(g), _dp(lb), _dp(ub), _dp(lbA), _dp(ubA),
                                     int(is_lp), int(max_iter), _dp(x), _dp(y), _dp(obj), _ip(st), _ip(it), int(nthreads))
     return dict(x=x, y=y, obj=obj, status=st, iters=it, threads=used)
+
+
+# ------------------------------------------------------------------ the caller: SQP outer loop (oracle_sqp.c)
+class _SqpProblem(C.Structure):
+    _fields_ = ([(k, C.c_int) for k in ("n", "m", "zJ", "zH")] +
+                [(k, C.c_void_p) for k in ("J_row1", "J_col1", "H_row1", "H_col1", "x_l", "x_u", "c_l", "c_u", "fc", "all")] +
+                [(k, C.c_int) for k in ("iter_max", "penalty_update", "penalty_iter_max", "qp_maxiter", "lp_maxiter")] +
+                [(k, C.c_double) for k in ("eta_c", "eta_s", "eta_e", "gamma_c", "gamma_e", "delta", "delta_min", "delta_max", "tol",
+                                           "penalty_update_tol", "rho", "rho_max", "increase_parm", "eps1", "eps1_change_parm", "eps2",
+                                           "opt_prim_fea_tol", "opt_dual_fea_tol", "opt_compl_tol", "opt_stat_tol")])
+
+
+class SqpOracle:
+    """CPU restatement of Algorithm::Optimize (oracle_sqp.c) for one model: `nlp` is a restartsqp_b200.nl_reader.AmplNLP (or
+    anything with c_source(), the triplet patterns, bounds and start); its evaluator is generated as C and compiled with gcc
+    (-ffp-contract=off) into oracle/_gen/."""
+
+    def __init__(self, nlp, options):
+        import hashlib
+        src = nlp.c_source()
+        gen = os.path.join(_HERE, "_gen")
+        os.makedirs(gen, exist_ok=True)
+        tag = hashlib.sha1(src.encode()).hexdigest()[:16]
+        so = os.path.join(gen, "nlp_%s_%s.so" % (getattr(nlp, "name", "model"), tag))
+        if not os.path.exists(so):
+            cfile = so[:-3] + ".c"
+            with open(cfile, "w") as f:
+                f.write(src)
+            subprocess.run(["gcc", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, cfile, "-lm"], check=True, capture_output=True)
+        self._nlp_lib = C.CDLL(so)
+        self.L = lib()
+        info = nlp.Get_nlp_info()
+        xl, xu, cl, cu = nlp.Get_bounds_info()
+        self.n, self.m = info.nVar, info.nCon
+        self._keep = [_i32(nlp.J_row1), _i32(nlp.J_col1), _i32(nlp.H_row1), _i32(nlp.H_col1), _f64(xl), _f64(xu), _f64(cl), _f64(cu)]
+        P = self.P = _SqpProblem()
+        P.n, P.m, P.zJ, P.zH = self.n, self.m, len(nlp.J_row1), len(nlp.H_row1)
+        for k, a in zip(("J_row1", "J_col1", "H_row1", "H_col1", "x_l", "x_u", "c_l", "c_u"), self._keep):
+            setattr(P, k, a.ctypes.data)
+        P.fc = C.cast(self._nlp_lib.nlp_fc, C.c_void_p).value
+        P.all = C.cast(self._nlp_lib.nlp_all, C.c_void_p).value
+        o = options
+        P.iter_max, P.penalty_update, P.penalty_iter_max, P.qp_maxiter, P.lp_maxiter = o.iter_max, int(o.penalty_update), o.penalty_iter_max, o.qp_maxiter, o.lp_maxiter
+        for k in ("eta_c", "eta_s", "eta_e", "gamma_c", "gamma_e", "delta", "delta_min", "delta_max", "tol", "penalty_update_tol", "rho", "rho_max",
+                  "increase_parm", "eps1", "eps1_change_parm", "eps2", "opt_prim_fea_tol", "opt_dual_fea_tol", "opt_compl_tol", "opt_stat_tol"):
+            setattr(P, k, float(getattr(o, k)))
+        self.lam0 = _f64(nlp.Get_starting_point()[1])
+
+    def solve_batch(self, x0, nthreads=0):
+        x0 = _f64(np.atleast_2d(x0))
+        B = x0.shape[0]
+        x, f, kkt = np.empty((B, self.n)), np.empty(B), np.empty(B)
+        ex, it, qi = np.empty(B, np.int32), np.empty(B, np.int32), np.empty(B, np.int64)
+        used = self.L.orc_sqp_solve_batch(C.byref(self.P), B, _dp(x0), _dp(self.lam0), _dp(x), _dp(f), _ip(ex), _ip(it),
+                                          qi.ctypes.data_as(C.c_void_p), _dp(kkt), int(nthreads))
+        return dict(x=x, obj=f, exitflag=ex, iters=it.astype(np.int64), qp_iter=qi, KKT_error=kkt, threads=used)

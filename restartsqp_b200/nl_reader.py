@@ -547,6 +547,42 @@ class AmplNLP:
         src.append("}")
         return "\n".join(src)
 
+    def c_source(self):
+        """The straight-line programs as plain C for ONE instance (nlp_fc, nlp_all): used by the CPU oracle's SQP loop
+        (oracle/oracle_sqp.c), i.e. by tests and by bench.py's CPU figure, never by the product path."""
+        G, n, m = self.model.G, self.n, self.m
+        hroots = [d2 for terms in self._hess_terms for _, d2 in terms]
+
+        def body(roots):
+            lines, nm = _emit(G, roots, "c")
+            used, stack = set(), list(roots)
+            while stack:
+                a = stack.pop()
+                if a in used:
+                    continue
+                used.add(a)
+                t = G.nodes[a]
+                if t[0] not in ("const", "var"):
+                    stack.extend(t[1:])
+            xs = sorted(G.nodes[a][1] for a in used if G.nodes[a][0] == "var")
+            return ["    const double x%d = x[%d];" % (j, j) for j in xs] + ["    " + ln for ln in lines], nm
+
+        src = ["#include <math.h>", "/* generated by restartsqp_b200/nl_reader.py from %s.nl */" % self.name,
+               "void nlp_fc(const double* x, double* f, double* c) {"]
+        out, nm = body([self.f_node] + self.c_nodes)
+        src += out + ["    *f = %s;" % nm[self.f_node]] + ["    c[%d] = %s;" % (i, nm[a]) for i, a in enumerate(self.c_nodes)] + ["}", ""]
+        src.append("void nlp_all(const double* x, const double* lam, double* f, double* c, double* grad, double* jac, double* hess) {")
+        out, nm = body([self.f_node] + self.c_nodes + self.grad_nodes + self.jac_nodes + hroots)
+        src += out + ["    *f = %s;" % nm[self.f_node]]
+        src += ["    c[%d] = %s;" % (i, nm[a]) for i, a in enumerate(self.c_nodes)]
+        src += ["    grad[%d] = %s;" % (i, nm[a]) for i, a in enumerate(self.grad_nodes)]
+        src += ["    jac[%d] = %s;" % (i, nm[a]) for i, a in enumerate(self.jac_nodes)]
+        for e, terms in enumerate(self._hess_terms):
+            parts = [nm[d2] if k == 0 else "lam[%d] * %s" % (k - 1, nm[d2]) for k, d2 in terms]
+            src.append("    hess[%d] = %s;" % (e, " + ".join(parts)))
+        src.append("}")
+        return "\n".join(src)
+
     # ---- SQPTNLP interface (src/SQPTNLP.cpp)
     def Get_nlp_info(self):
         return NLPInfo(nCon=self.m, nVar=self.n, nnz_jac_g=len(self.jac_nodes), nnz_h_lag=len(self._hess_terms))

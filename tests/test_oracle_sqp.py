@@ -1,0 +1,43 @@
+"""The C restatement of the SQP outer loop (oracle/oracle_sqp.c, with the NLP generated as C from the .nl DAG) against the numpy
+mirror of the product (restartsqp_b200/sqp_driver.py on the oracle-backed twin backend), instance by instance in single-instance
+mode (the batched driver shares its init/hotstart state machine across the batch, the reference and the C oracle do not):
+bitwise on the polynomial problems, to tolerance where libm and numpy evaluate pow/exp differently."""
+import os
+
+import numpy as np
+import pytest
+
+import restartsqp_b200 as r
+from restartsqp_b200.nl_reader import AmplNLP
+from restartsqp_b200.sqp_driver import BatchedSQP
+from oracle import oracle_py as orc
+from oracle_backend import OracleQPInterface
+from test_hs_suite import HS_DIR, perturbed_starts, F_STAR
+
+POLYNOMIAL = ["hs015", "hs043", "hs071", "hs087", "hs099", "hs106", "hs113", "hs118"]
+
+
+@pytest.mark.parametrize("name", POLYNOMIAL)
+def test_c_oracle_equals_numpy_mirror_single_instance(name):
+    nlp = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+    X = perturbed_starts(nlp, 4, 1)
+    res_c = orc.SqpOracle(nlp, r.Options(iter_max=150)).solve_batch(X)
+    for b in range(X.shape[0]):
+        o1 = r.Options(iter_max=150)
+        mk = lambda info, qt: r.QPhandler(info, qt, o1, batch=1, backend=OracleQPInterface(info, qt, o1, batch=1), refresh_ubA=True)
+        try:
+            r1 = BatchedSQP(nlp, x0=X[b:b + 1], options=o1, make_handler=mk).Optimize()
+        except (r.QP_NOT_OPTIMAL, r.LP_NOT_OPTIMAL):
+            continue  # batch == 1 keeps the reference's exceptions; the C oracle records the status instead
+        assert int(r1.exitflag[0]) == int(res_c["exitflag"][b])
+        assert int(r1.iters[0]) == int(res_c["iters"][b]) and int(r1.qp_iter[0]) == int(res_c["qp_iter"][b])
+        if np.isfinite(r1.x[0]).all():
+            assert np.array_equal(r1.x[0], res_c["x"][b]) and r1.obj[0] == res_c["obj"][b]
+
+
+@pytest.mark.parametrize("name", sorted(F_STAR))
+def test_c_oracle_reaches_known_optimum(name):
+    nlp = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+    res = orc.SqpOracle(nlp, r.Options()).solve_batch(perturbed_starts(nlp, 3, 0), nthreads=2)
+    assert (res["exitflag"] == 0).all()
+    assert abs(res["obj"][0] - F_STAR[name]) <= 1e-3 * max(1.0, abs(F_STAR[name]))

@@ -422,6 +422,18 @@ def run_extras(device):
                            "optimal": int((res.exitflag == 0).sum()), "sqp_iters_mean": float(res.iters.mean()),
                            "qp_iters_mean": float(res.qp_iter.mean()), "seconds": dt, "seconds_initialization": t1 - t0, "seconds_all_runs": [r_[0] for r_ in runs], "value_best_of_3": Bs / min(r_[0] for r_ in runs),
                            "note": "device-resident outer loop (csrc/sqp_outer.cu), NVRTC NLP evaluation and every QP/LP on the GPU; starts uploaded from the host, results read back; wall clock"}
+        try:  # configs[4] at one GPU: 10^6 HS-scale instances (100 copies of the 10^4 starts), one run after a warm-up of the allocations
+            Xm = np.tile(X, (100, 1))
+            t0 = time.perf_counter()
+            algm = BatchedSQP(dev, x0=Xm, device=device)
+            resm = algm.Optimize()
+            dtm = time.perf_counter() - t0
+            algm.close()
+            ex["sqp_hs071_1e6"] = {"metric": "SQP solves/sec", "value": Xm.shape[0] / dtm, "unit": "solves/s", "instances": int(Xm.shape[0]),
+                                   "optimal": int((resm.exitflag == 0).sum()), "seconds": dtm}
+            del Xm, resm
+        except Exception as e:
+            ex["sqp_hs071_1e6"] = {"error": repr(e)[:200]}
         dev.close()
         try:  # the same solves by the CPU oracle's C restatement of the outer loop on all host cores (bounded sample)
             from oracle import oracle_py as orc

@@ -249,6 +249,8 @@ typedef struct {
     const int *H_row1, *H_col1;
     double *soc_g, *soc_x, *soc_c, *p_tmp, *qp_obj_tmp, *qp_obj_soc, *norm_p;
     unsigned char* rej;
+    /* per-instance backend state machines of the QP and the LP handle (sqpb200_solve_per_instance); NULL: handle-level modes */
+    signed char *qp_inst, *lp_inst;
 } sqpb200_sqp_state;
 /* counters_host (may be NULL): the 8 device counters after the phase ([0] active instances, [1] OR of the raised Update_*
  * bits 1=A 2=H 4=bounds 8=delta 16=penalty 32=g, [2] instances needing the penalty update, [3] instances continuing the
@@ -257,6 +259,12 @@ typedef struct {
 int sqpb200_sqp_phase(const sqpb200_sqp_state* st, int phase, int* counters_host, void* stream);
 /* sqpb200_solve with the instance mask in device memory */
 int sqpb200_solve_device_mask(sqpb200_handle h, int mode, int maxiter, const unsigned char* device_mask);
+/* The same with the init / hotstart decision (src/qpOASESInterface.cpp:141-211, 817-833) made PER INSTANCE inside the kernel, as the
+ * reference does for its single instance: inst_state[batch][8] (int8, device memory, owned by the caller, initialised to
+ * {0, 0, -1, -1, 0, ...}) holds {first_solved, varied, old matrix status, new matrix status, last mode}; the caller sets
+ * varied = 1 for an instance whenever it hands that instance new matrix values (csrc/sqp_outer.cu does).  Needs keep_state. */
+int sqpb200_solve_per_instance(sqpb200_handle h, int mode, int maxiter, const unsigned char* device_mask,
+                               signed char* device_inst_state);
 /* device pointers of the handle's result arrays: out[0..5] = x, y, obj, status, iters, kkt */
 int sqpb200_device_buffers(sqpb200_handle h, void** out);
 

@@ -29,7 +29,7 @@ EXPORTS = [
     "sqpb200_solve_config", "sqpb200_last_solve_ms",
     "sqpb200_nlp_compile", "sqpb200_nlp_cubin_size", "sqpb200_nlp_load", "sqpb200_nlp_eval", "sqpb200_nlp_destroy",
     "sqpb200_nlp_launch_count", "sqpb200_nlp_last_error",
-    "sqpb200_sqp_phase", "sqpb200_solve_device_mask", "sqpb200_device_buffers",
+    "sqpb200_sqp_phase", "sqpb200_solve_device_mask", "sqpb200_device_buffers", "sqpb200_solve_per_instance",
 ]
 
 

@@ -679,19 +679,23 @@ static cudaError_t launch_cfg(const SolveCfg& cfg, const QPKernelArgs& a, cudaSt
     }
 }
 
-static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask, bool mask_on_device);
+static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask, bool mask_on_device, signed char* inst_state);
 int sqpb200_solve(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask) {
-    return solve_impl(h, mode_qp, maxiter, active_mask, false);
+    return solve_impl(h, mode_qp, maxiter, active_mask, false, nullptr);
 }
 int sqpb200_solve_device_mask(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* device_mask) {
-    return solve_impl(h, mode_qp, maxiter, device_mask, true);
+    return solve_impl(h, mode_qp, maxiter, device_mask, true, nullptr);
+}
+int sqpb200_solve_per_instance(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* device_mask, signed char* device_inst_state) {
+    if (!h || !device_inst_state || !h->opt.keep_state) return SQPB200_ERR_INVALID;
+    return solve_impl(h, mode_qp, maxiter, device_mask, true, device_inst_state);
 }
 int sqpb200_device_buffers(sqpb200_handle h, void** out) {
     if (!h || !out) return SQPB200_ERR_INVALID;
     out[0] = h->dx; out[1] = h->dy; out[2] = h->dobj; out[3] = h->dstatus; out[4] = h->diters; out[5] = h->dkkt;
     return 0;
 }
-static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask, bool mask_on_device) {
+static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask, bool mask_on_device, signed char* inst_state) {
     if (!h) return SQPB200_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     if (!h->A_set) { h->err = "set_structure_A has not been called"; return SQPB200_ERR_STATE; }
@@ -735,6 +739,7 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
     a.x = h->dx; a.y = h->dy; a.obj = h->dobj; a.kkt = h->dkkt; a.status = h->dstatus; a.iters = h->diters;
     a.wsB = h->dwsB; a.wsC = h->dwsC; a.WB = h->dWB; a.WC = h->dWC;
     a.state = h->dstate;
+    a.inst_state = inst_state;  // per-instance init/hotstart decisions (made in the kernel) replace the handle-level `mode`
     if (h->large) {
         rc = prepare_large(h, a);
         if (rc) return rc;

@@ -67,6 +67,7 @@ struct QPKernelArgs {
     const double *Aval, *Hval;
     const double *gN, *lbN, *ubN, *lbAN, *ubAN;
     const unsigned char* mask;
+    signed char* inst_state;  // optional [batch][8]: per-instance init/hotstart state machine {first_solved, varied, old_ms, new_ms, last_mode}
     const int* gpat;   // TEAM > 32: the pattern as 32-bit indices in global memory, laid out by the p* offsets below
     double* gwork;     // TEAM > 32: [batch][slice_doubles] global-memory slices (persist between solves: hot start in place)
     // outputs
@@ -1311,6 +1312,30 @@ struct QPT {
     }
 };
 
+// Per-instance init / hotstart decision (src/qpOASESInterface.cpp:141-211 with get_Matrix_change_status :817-833), for batched
+// drivers that keep the reference's semantics instance by instance: st = {first_solved, varied (Update_A || Update_H since the
+// instance's last solve), old matrix status, new matrix status, mode chosen by the last launch}; matrix status -1 undefined,
+// 0 fixed, 1 varied.  Every thread of the team computes the same mode; one thread stores the new state after a team barrier.
+// The rescue launch re-uses the mode the main launch chose.
+__device__ __forceinline__ int qp_instance_mode(const signed char* st, bool rescue, int& old_ms, int& new_ms) {
+    old_ms = st[2]; new_ms = st[3];
+    if (rescue) return st[4];
+    const int first = st[0], varied = st[1] != 0;
+    int mode = MODE_COLD;
+    if (first) {
+        if (old_ms < 0) old_ms = varied ? 1 : 0;
+        else { if (new_ms >= 0) old_ms = new_ms; new_ms = varied ? 1 : 0; }
+        if (new_ms < 0) mode = (old_ms == 0) ? MODE_HOT_FIXED : MODE_HOT_VARIED;
+        else if (new_ms == 0 && old_ms == 0) mode = MODE_HOT_FIXED;
+        else if (new_ms == 1 && old_ms == 1) mode = MODE_HOT_VARIED;
+        else { mode = MODE_HOT_VARIED; new_ms = old_ms = -1; }  // status flip: warm re-init with the kept working set (:202-207)
+    }
+    return mode;
+}
+__device__ __forceinline__ void qp_instance_store(signed char* st, int mode, int old_ms, int new_ms) {
+    st[0] = 1; st[1] = 0; st[2] = (signed char)old_ms; st[3] = (signed char)new_ms; st[4] = (signed char)mode;
+}
+
 // -------------------------------------------------------------------------------------------
 // kernel: one QP per warp, CTA_THREADS/32 QPs per CTA
 // -------------------------------------------------------------------------------------------
@@ -1346,6 +1371,12 @@ __global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solv
     double *Q = slice + A.oQ, *RT = slice + A.oRT;
 
     int mode = A.mode;
+    if (A.inst_state) {
+        int oms, nms;
+        mode = qp_instance_mode(A.inst_state + 8 * (size_t)b, A.rescue != 0, oms, nms);
+        __syncwarp();  // every lane has read the state
+        if (lane == 0 && !A.rescue) qp_instance_store(A.inst_state + 8 * (size_t)b, mode, oms, nms);
+    }
     int status = 0;
     if (mode != MODE_COLD) {
         // restore the pre-solve image: everything but the factors verbatim, then Q (nFR x nFR), R (nZ x nZ), T (nAC x nFR)
@@ -1443,6 +1474,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) qp_solve_large_kernel(const __
     int* hdr = reinterpret_cast<int*>(slice);
 
     int mode = A.mode;
+    if (A.inst_state) {
+        int oms, nms;
+        mode = qp_instance_mode(A.inst_state + 8 * (size_t)b, false, oms, nms);
+        __syncthreads();  // every thread of the CTA has read the state
+        if (tid == 0) qp_instance_store(A.inst_state + 8 * (size_t)b, mode, oms, nms);
+    }
     if (mode != MODE_COLD && !hdr[3]) mode = MODE_COLD;  // previous solve did not end optimal: plain re-init (handle_error)
     __syncthreads();
     if (mode != MODE_HOT_FIXED) {

@@ -97,6 +97,8 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
         if (a) {
             atomicAdd(&S.counters[0], 1);
             if (S.upd[b]) atomicOr(&S.counters[1], (int)S.upd[b]);
+            // this instance's matrices change (it accepted a step): its backend sees Update_A / Update_H (:361-496)
+            if (S.qp_inst && (S.upd[b] & (UP_A | UP_H)) && S.clear_flags) S.qp_inst[8 * (size_t)b + 1] = 1;
             if (S.clear_flags) S.upd[b] = 0;
         }
         break;
@@ -120,7 +122,10 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
             for (int i = n; i < nV; i++) s = s + fabs(x[i]);
             S.infea_model[b] = s;
             need = s > S.penalty_update_tol;
-            if (need) { atomicAdd(&S.counters[2], 1); S.infea_model_tmp[b] = s; }
+            if (need) {
+                atomicAdd(&S.counters[2], 1); S.infea_model_tmp[b] = s;
+                if (S.lp_inst) S.lp_inst[8 * (size_t)b + 1] = 1;  // setupLP hands this instance's Jacobian to the LP backend (:700-704)
+            }
         }
         S.need[b] = need;
         break;

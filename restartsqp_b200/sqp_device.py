@@ -6,7 +6,9 @@ of one CUDA kernel (csrc/sqp_outer.cu, one thread per instance), the NLP is eval
 `DeviceNLP`, QP data is built by the qphandler kernels and the QP/LP solves take their instance mask from device memory.  The
 host sequences launches and reads eight counters per outer iteration.  torch is used for device memory only.
 
-tests/test_gpu_sqp.py compares it with BatchedSQP (identical exit flags, iteration counts and iterates).
+By default the backend's init / hotstart decision (src/qpOASESInterface.cpp:141-211, 817-833) is made per instance inside the solve
+kernel, so every instance of the batch follows the reference's single-instance semantics: tests/test_gpu_sqp.py compares it bitwise
+with the C oracle of the loop (oracle/oracle_sqp.c), and, with per_instance_modes=False, with BatchedSQP.
 """
 import ctypes as C
 
@@ -37,11 +39,14 @@ class SqpState(C.Structure):
                                    "g_new", "j_new", "h_new", "scratch", "exitflag", "iter", "pen_trial", "qp_iter",
                                    "active", "need", "go", "acc", "upd", "feasible_lp",
                                    "qp_x", "qp_y", "qp_obj", "qp_kkt", "lp_x", "qp_status", "qp_iters", "lp_status", "lp_iters", "counters",
-                                   "H_row1", "H_col1", "soc_g", "soc_x", "soc_c", "p_tmp", "qp_obj_tmp", "qp_obj_soc", "norm_p", "rej")])
+                                   "H_row1", "H_col1", "soc_g", "soc_x", "soc_c", "p_tmp", "qp_obj_tmp", "qp_obj_soc", "norm_p", "rej",
+                                   "qp_inst", "lp_inst")])
 
 
 class DeviceBatchedSQP:
-    def __init__(self, nlp, x0=None, options: Options = None, device=0):
+    def __init__(self, nlp, x0=None, options: Options = None, device=0, per_instance_modes=True):
+        """per_instance_modes: the backend's init/hotstart decision is made per instance, as the reference does for its single
+        instance (and as oracle/oracle_sqp.c does); False: per handle, which is what the numpy mirror BatchedSQP does."""
         import torch
         if not hasattr(nlp, "eval_device"):
             raise TypeError("DeviceBatchedSQP needs a DeviceNLP (device-side evaluation)")
@@ -90,6 +95,11 @@ class DeviceBatchedSQP:
         for k in ("active", "need", "go", "acc", "upd", "feasible_lp", "rej"):
             T[k] = u8()
         T["counters"] = torch.zeros(8, dtype=torch.int32, device=self.dev)
+        self.per_instance_modes = bool(per_instance_modes)
+        if self.per_instance_modes:
+            for k in ("qp_inst", "lp_inst"):
+                T[k] = torch.zeros((B, 8), dtype=torch.int8, device=self.dev)
+                T[k][:, 2:4] = -1  # matrix status undefined (get_Matrix_change_status, src/qpOASESInterface.cpp:817-833)
         # initialization(), src/Algorithm.cpp:438-472: f, c, grad, Jacobian, Hessian at the (shifted) start in one launch
         nlp.eval_device(1, B, T["x_k"], T["neg_lam"], T["f_k"], T["c_k"], T["grad"], T["jac"], T["hess"])
         S = self.S = SqpState()
@@ -140,9 +150,13 @@ class DeviceBatchedSQP:
 
     def _solve(self, handler, qptype, mask):
         si = handler.solverInterface_
-        rc = self.L.sqpb200_solve_device_mask(si.h, int(qptype), 0, C.c_void_p(mask.data_ptr()))
+        if self.per_instance_modes:
+            inst = self.T["qp_inst" if handler is self.myQP_ else "lp_inst"]
+            rc = self.L.sqpb200_solve_per_instance(si.h, int(qptype), 0, C.c_void_p(mask.data_ptr()), C.c_void_p(inst.data_ptr()))
+        else:
+            rc = self.L.sqpb200_solve_device_mask(si.h, int(qptype), 0, C.c_void_p(mask.data_ptr()))
         if rc != 0:
-            raise capi.SqpB200Error("sqpb200_solve_device_mask failed (%d): %s" % (rc, self.L.sqpb200_last_error(si.h).decode()))
+            raise capi.SqpB200Error("batched solve failed (%d): %s" % (rc, self.L.sqpb200_last_error(si.h).decode()))
         si._kkt = None
 
     # ---- src/Algorithm.cpp:645-697

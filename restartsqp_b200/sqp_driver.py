@@ -12,7 +12,8 @@ backend is a drop-in behind QPhandler.
 Batch semantics of the backend's init/hotstart state machine: the `Update_A/Update_H` flags of
 src/qpOASESInterface.cpp:361-496 are raised per handle, so one outer iteration uses a matrix-changing hot start for the
 whole batch as soon as one instance accepted its step (for an instance whose matrices did not change this is the same QP
-solved from the same working set with freshly built factors).
+solved from the same working set with freshly built factors).  The device-resident driver (sqp_device.DeviceBatchedSQP) keeps
+that state machine per instance instead.
 """
 from dataclasses import dataclass
 

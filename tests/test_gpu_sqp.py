@@ -143,7 +143,7 @@ def test_device_resident_loop_equals_host_loop(gpu_lib, name):
     X = perturbed_starts(host, 200, 1)
     opt_h, opt_d = r.Options(iter_max=120), r.Options(iter_max=120)
     res_h = BatchedSQP(dev, x0=X, options=opt_h).Optimize()
-    alg = DeviceBatchedSQP(dev, x0=X, options=opt_d)
+    alg = DeviceBatchedSQP(dev, x0=X, options=opt_d, per_instance_modes=False)  # the numpy mirror decides per handle
     res_d = alg.Optimize()
     assert (res_d.exitflag == res_h.exitflag).all(), (np.unique(res_d.exitflag, return_counts=True), np.unique(res_h.exitflag, return_counts=True))
     assert (res_d.iters == res_h.iters).all() and (res_d.qp_iter == res_h.qp_iter).all()
@@ -165,7 +165,7 @@ def test_device_loop_second_order_correction_equals_host_loop(gpu_lib, name):
     dev = DeviceNLP(AmplNLP(os.path.join(HS_DIR, name + ".nl")))
     X = perturbed_starts(dev.host, 100, 2)
     res_h = BatchedSQP(dev, x0=X, options=r.Options(iter_max=120, second_order_correction=True)).Optimize()
-    alg = DeviceBatchedSQP(dev, x0=X, options=r.Options(iter_max=120, second_order_correction=True))
+    alg = DeviceBatchedSQP(dev, x0=X, options=r.Options(iter_max=120, second_order_correction=True), per_instance_modes=False)
     res_d = alg.Optimize()
     res_off = BatchedSQP(dev, x0=X, options=r.Options(iter_max=120)).Optimize()
     assert (res_d.exitflag == res_h.exitflag).all() and (res_d.iters == res_h.iters).all() and (res_d.qp_iter == res_h.qp_iter).all()
@@ -173,4 +173,28 @@ def test_device_loop_second_order_correction_equals_host_loop(gpu_lib, name):
     fin = np.isfinite(res_h.x).all(axis=1)
     assert np.array_equal(res_d.x[fin], res_h.x[fin])
     assert (res_h.qp_iter != res_off.qp_iter).any()  # the correction was actually taken somewhere
+    alg.close(); dev.close()
+
+
+@pytest.mark.parametrize("name", ["hs015", "hs043", "hs071", "hs083", "hs093", "hs106", "hs108", "hs113", "hs116", "hs118"])
+def test_device_loop_per_instance_modes_equal_the_c_oracle(gpu_lib, name):
+    """Default mode of DeviceBatchedSQP: the backend's init/hotstart state machine runs per instance inside the solve kernel, i.e.
+    the reference's semantics for every instance of the batch.  Against oracle/oracle_sqp.c (one independent solve per instance)
+    on problems evaluated with + - * and squares only, where the NVRTC and the gcc evaluators agree bitwise: identical exit flags, outer and QP iteration
+    counts and iterates, although the instances of the batch accept and reject steps at different iterations."""
+    import os
+    from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
+    from restartsqp_b200.sqp_device import DeviceBatchedSQP
+    from oracle import oracle_py as orc
+    from test_hs_suite import HS_DIR, perturbed_starts
+    host = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+    dev = DeviceNLP(host)
+    X = perturbed_starts(host, 96, 4)
+    alg = DeviceBatchedSQP(dev, x0=X, options=r.Options(iter_max=150))
+    res_d = alg.Optimize()
+    res_c = orc.SqpOracle(host, r.Options(iter_max=150)).solve_batch(X)
+    assert (res_d.exitflag == res_c["exitflag"]).all(), (res_d.exitflag, res_c["exitflag"])
+    assert (res_d.iters == res_c["iters"]).all() and (res_d.qp_iter == res_c["qp_iter"]).all()
+    fin = np.isfinite(res_c["x"]).all(axis=1)
+    assert np.array_equal(res_d.x[fin], res_c["x"][fin]) and np.array_equal(res_d.obj[fin], res_c["obj"][fin])
     alg.close(); dev.close()

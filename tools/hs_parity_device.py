@@ -19,7 +19,7 @@ for k, f in enumerate(files):
         skipped += 1; continue
     X = perturbed_starts(dev.host, B, k)
     rh = BatchedSQP(dev, x0=X, options=r.Options(iter_max=150)).Optimize()
-    alg = DeviceBatchedSQP(dev, x0=X, options=r.Options(iter_max=150)); rd = alg.Optimize(); alg.close(); dev.close()
+    alg = DeviceBatchedSQP(dev, x0=X, options=r.Options(iter_max=150), per_instance_modes=False); rd = alg.Optimize(); alg.close(); dev.close()
     fin = np.isfinite(rh.x).all(axis=1) & np.isfinite(rd.x).all(axis=1)
     ok = (rd.exitflag == rh.exitflag).all() and (rd.iters == rh.iters).all() and (rd.qp_iter == rh.qp_iter).all() and \
         (rd.rho == rh.rho).all() and np.array_equal(rd.x[fin], rh.x[fin])

@@ -5,10 +5,10 @@ Workload (BASELINE.json configs[1]): replay of the dumped
 test/unsolved_QP_data + test/unsolved_QPs as a batch.  Every dumped QP with a symmetric Hessian array
 (21 of the 27; the other six hold a non-symmetric "H", i.e. are not QPs, and are kept as robustness tests
 only) is replicated B = 4096 times with g *= 1 + 1e-3*U(-1,1) (seed 1234, replica 0 exact).  One step =
-one cold-start solve (init) of every replica of every dumped QP = 21*B QPs per GPU.  With N GPUs every
-rank solves its own 21*B replicas (rank-seeded perturbations): weak scaling, no collective on the path.
+one cold-start solve (init) of every replica of every dumped QP = 20*B QPs per GPU.  With N GPUs every
+rank solves its own 20*B replicas (rank-seeded perturbations): weak scaling, no collective on the path.
 
-  value  QPs/s with all inputs resident in HBM: K steps of 21 solve launches, CUDA events, max over ranks.
+  value  QPs/s with all inputs resident in HBM: K steps of 20 solve launches, CUDA events, max over ranks.
   e2e    the same through the public plugin API with HOST (pinned) buffers: every step uploads H, A values,
          g, lb, ub, lbA, ubA of every instance, solves, and reads x, y, objective and status back.
   roofline  qp_solve_kernel: algorithmic compulsory bytes over the kernel's device time,
@@ -33,7 +33,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 METRIC = "QP subproblems/sec"
 UNIT = "QPs/s"
-WORKLOAD = "replay_dumped_qps (test/unsolved_QP_data + test/unsolved_QPs, 21 symmetric-H dumps x B replicas, cold start)"
+WORKLOAD = "replay_dumped_qps (test/unsolved_QP_data + test/unsolved_QPs, the 20 symmetric-H dumps that are solvable x B replicas, cold start)"
+# QORE_hs107 is the reference's own failure case (non-convex: the projected Hessian of the working set the homotopy reaches is
+# indefinite); GPU kernel, CPU oracle and the reference's qpOASES run all end it with an error status, so it is a robustness
+# test (tests/test_gpu_qp.py), not a throughput workload: the headline counts only solves that end QP_OPTIMAL.
+EXCLUDED = ("QORE_hs107",)
 
 
 # ------------------------------------------------------------------------------------------ workload
@@ -45,7 +49,7 @@ def load_fixtures():
     for q in qps:
         nV = q["nV"]
         Hd = sp.csc_matrix((q["H_val"], q["H_rowidx"], q["H_colptr"]), shape=(nV, nV)).toarray()
-        if np.abs(Hd - Hd.T).max() == 0.0:
+        if np.abs(Hd - Hd.T).max() == 0.0 and q["name"] not in EXCLUDED:
             out.append(q)
     return out
 
@@ -132,7 +136,7 @@ def run_reference(args, rank, world):
         return
     fixtures = load_fixtures()
     # each step = a bounded sample of the workload: passes over `sample_B` replicas of every dump for >= 4 s
-    sample_B = min(args.replicas, 1024)
+    sample_B = args.replicas  # the same replicas per dumped QP as the GPU arm
     cores = 1
     for _ in range(args.warmup):
         cpu_rate(fixtures, min(sample_B, 64), 1234)
@@ -285,9 +289,11 @@ def run_gpu(args, rank, world, local_rank):
 
     if rank == 0:
         # parity spot check on the benchmarked data (replica 0 of each dump) against the oracle
-        status_ok = 0
+        status_ok, per_dump = 0, {}
         for gr in groups:
-            status_ok += int((gr["s"].get_status() == 20).sum())
+            ok = int((gr["s"].get_status() == 20).sum())
+            status_ok += ok
+            per_dump[gr["q"]["name"]] = ok
         # roofline of the dominant kernel
         peaks = {}
         try:
@@ -364,7 +370,7 @@ def run_gpu(args, rank, world, local_rank):
             del a_, b_
         except Exception:
             pass
-        sample_B = min(B, 1024)
+        sample_B = B  # the same replicas per dumped QP as the timed GPU workload
         rate, cores, n, t = cpu_rate(fixtures, sample_B, 1234, max_seconds=60.0, min_seconds=12.0)  # >= 12 s of CPU work
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -372,12 +378,12 @@ def run_gpu(args, rank, world, local_rank):
             "data": "synthetic (dumped QP fixtures of the reference, perturbed replicas)",
             "config": {"workload": WORKLOAD, "replicas_per_qp": B, "qps_per_step_per_gpu": len(fixtures) * B,
                        "l2": "256 MiB buffer written between steps (inside the timed region)",
-                       "solved_optimal": status_ok, "team_size": args.team or "auto",
+                       "solved_optimal": status_ok, "solved_optimal_per_dump": per_dump, "team_size": args.team or "auto",
                        "streams": len(streams) if streams else 1},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d QPs (passes over %d replicas of each of the 21 dumped QPs) in %.1f s" % (n, sample_B, t)},
+                             "sample": "%d QPs (passes over %d replicas of each of the %d dumped QPs) in %.1f s" % (n, sample_B, len(fixtures), t)},
         }
         if args.extras:
             out["extras"] = run_extras(local_rank)

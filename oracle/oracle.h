@@ -123,6 +123,9 @@ typedef struct {
 } orc_qp_options;
 
 void orc_qp_default_options(orc_qp_options* o);
+/* deviation study (process-global, tests only): flags 1 = true division, 2 = ratio test as num < t*den, 4 = maxDualJump cap;
+ * refine_steps = numRefinementSteps.  (0, 0) = the shipped behaviour. */
+void orc_qp_set_variant(int flags, int refine_steps);
 orc_qp* orc_qp_create(int nV, int nC);
 void orc_qp_destroy(orc_qp* q);
 /* Cold start ("init"): H may be NULL colptr for an LP.  Returns Exitflag (20 = optimal). */

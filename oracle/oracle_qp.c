@@ -48,6 +48,16 @@
 #define QP_EPS_LI (1.0e5 * QP_EPS)
 #define QP_MAX_DUAL_JUMP 1.0e8
 
+/* Deviation study (tests/test_oracle_variants.py, DESIGN.md "deviations from setToReliable"): switches that put back the
+ * qpOASES behaviours this restatement leaves out, so that a CPU test can show on which inputs they change the result.
+ * Process-global, test use only; 0 = the shipped behaviour (what the CUDA kernel implements). */
+#define VAR_TRUE_DIVISION 1   /* x / d instead of the Newton-corrected reciprocal of quot() */
+#define VAR_RATIO_MULT 2      /* isBlocking as num < t*den (qpOASES form) instead of num/den < t */
+#define VAR_MAX_DUAL_JUMP 4   /* exchange step only accepts ratios below maxDualJump = 1e8 */
+static int g_variant = 0;
+static int g_refine = 0;      /* numRefinementSteps: rounds of iterative refinement of the step direction */
+void orc_qp_set_variant(int flags, int refine_steps) { g_variant = flags; g_refine = refine_steps; }
+
 struct orc_qp {
     int nV, nC;
     int has_H, is_lp;
@@ -155,6 +165,7 @@ static void build_dense_A(orc_qp* q) {
  * division on the critical path; the result is the correctly rounded quotient except in rare double-rounding cases.
  * (A bare x*ri is not accurate enough: on the rho = 1e8 scaled dumps the homotopy then needs 3x the iterations.) */
 static inline double quot(double x, double d, double ri) {
+    if (g_variant & VAR_TRUE_DIVISION) return x / d;
     double q0 = x * ri;
     double r = fma(-q0, d, x);
     return fma(r, ri, q0);
@@ -384,7 +395,7 @@ static void solve_Tt(const orc_qp* q, const double* r, double* u) {
 /* Solves the KKT system of the current working set for the data shift
  * (dgv, bound shifts dbF on fixed variables, constraint shifts dbA on active constraints).
  * Outputs q->dx (nV), q->dy (nV+nC).  (qpOASES determineStepDirection) */
-static void step_direction(orc_qp* q, const double* dgv, const double* dxFX_full, const double* dbAC) {
+static void step_direction_core(orc_qp* q, const double* dgv, const double* dxFX_full, const double* dbAC) {
     int nV = q->nV, nC = q->nC, nFR = q->nFR, nAC = q->nAC, nZ = nFR - nAC;
     double *dx = q->dx, *dy = q->dy;
     for (int i = 0; i < nV; i++) dx[i] = (q->sB[i] != 0) ? dxFX_full[i] : 0.0;
@@ -442,6 +453,38 @@ static void step_direction(orc_qp* q, const double* dgv, const double* dxFX_full
         for (int i = 0; i < nV; i++) if (q->sB[i] != 0) dy[i] = q->t1[i];
     }
     q->flops += 4.0 * nFR * nFR + 2.0 * nZ * nZ + 2.0 * nAC * nAC;
+}
+
+/* numRefinementSteps rounds of iterative refinement (deviation study only: g_refine = 0 in the shipped configuration).
+ * The KKT system is linear in its data, so the correction is the same solve applied to the residuals. */
+static void step_direction(orc_qp* q, const double* dgv, const double* dxFX_full, const double* dbAC) {
+    step_direction_core(q, dgv, dxFX_full, dbAC);
+    if (g_refine <= 0) return;
+    int nV = q->nV, nC = q->nC, nAC = q->nAC;
+    double* dx0 = (double*)malloc(sizeof(double) * (size_t)(nV + 1));
+    double* dy0 = (double*)malloc(sizeof(double) * (size_t)(nV + nC + 1));
+    double* rg = (double*)malloc(sizeof(double) * (size_t)(nV + 1));
+    double* rA = (double*)malloc(sizeof(double) * (size_t)(nC + 1));
+    double* zero = (double*)calloc((size_t)(nV + 1), sizeof(double));
+    for (int r = 0; r < g_refine; r++) {
+        memcpy(dx0, q->dx, sizeof(double) * (size_t)nV);
+        memcpy(dy0, q->dy, sizeof(double) * (size_t)(nV + nC));
+        mulH(q, dx0, q->t1);
+        mulAT(q, dy0 + nV, q->t2);
+        mulA(q, dx0, q->t3);
+        double rn = 0.0;
+        for (int i = 0; i < nV; i++) { rg[i] = (q->sB[i] == 0) ? (q->t1[i] + dgv[i] - q->t2[i]) : 0.0; if (fabs(rg[i]) > rn) rn = fabs(rg[i]); }
+        for (int i = 0; i < nAC; i++) { rA[i] = dbAC[i] - q->t3[q->AC[i]]; if (fabs(rA[i]) > rn) rn = fabs(rA[i]); }
+        if (rn < 1.0e2 * QP_EPS) break; /* epsIterRef */
+        step_direction_core(q, rg, zero, rA);
+        for (int i = 0; i < nV; i++) q->dx[i] = dx0[i] + ((q->sB[i] == 0) ? q->dx[i] : 0.0);
+        for (int i = 0; i < nC; i++) q->dy[nV + i] += dy0[nV + i];
+        /* bound multipliers from stationarity with the refined step */
+        mulH(q, q->dx, q->t1);
+        mulAT(q, q->dy + nV, q->t2);
+        for (int i = 0; i < nV; i++) q->dy[i] = (q->sB[i] != 0) ? (q->t1[i] + dgv[i] - q->t2[i]) : 0.0;
+    }
+    free(dx0); free(dy0); free(rg); free(rA); free(zero);
 }
 
 /* ------------------------------------------------------------ drift correction */
@@ -524,7 +567,7 @@ static int ensure_li(orc_qp* q, int c, int v, int status) {
         q->xiB[i] = ai - q->t2[i];
     }
     double sgn = (status < 0) ? 1.0 : -1.0; /* lower: mu >= 0 ; upper: mu <= 0 */
-    double ymin = QP_INFTY; int kind = -1, idx = -1; /* no maxDualJump cap: multipliers scale with rho */
+    double ymin = (g_variant & VAR_MAX_DUAL_JUMP) ? QP_MAX_DUAL_JUMP : QP_INFTY; int kind = -1, idx = -1; /* shipped: no maxDualJump cap (multipliers scale with rho) */
     for (int i = 0; i < nAC; i++) {
         int ci = q->AC[i]; double xi = sgn * q->xiC[i], yy = q->y[nV + ci];
         if (q->sC[ci] < 0) { if (xi > QP_ZERO && yy >= 0.0 && yy / xi < ymin) { ymin = yy / xi; kind = 0; idx = ci; } }
@@ -565,7 +608,7 @@ static int homotopy(orc_qp* q, const orc_qp_options* opt) {
         double tau = 1.0; int bc_idx = -1, bc_isbound = 0, bc_status = 0;
 /* isBlocking: den >= epsDen, num >= epsNum, num < den (the full step is not reachable); the
          * ratio then has to beat the running minimum strictly, so the first index scanned wins ties */
-#define BLOCKING(num, den) ((den) >= QP_EPS_DEN && (num) >= QP_EPS_NUM && (num) < (den) && (num) / (den) < tau)
+#define BLOCKING(num, den) ((den) >= QP_EPS_DEN && (num) >= QP_EPS_NUM && ((g_variant & VAR_RATIO_MULT) ? ((num) < tau * (den)) : ((num) < (den) && (num) / (den) < tau)))
         for (int i = 0; i < q->nAC; i++) { /* duals of active constraints */
             int ci = q->AC[i]; double num, den;
             if (q->sC[ci] < 0) { num = q->y[nV + ci]; den = -q->dy[nV + ci]; } else { num = -q->y[nV + ci]; den = q->dy[nV + ci]; }

@@ -181,6 +181,9 @@ int sqpb200_assemble_csc_batched(int device, int nmat, const int* seg, const int
 
 /* kernels launched by this handle since creation (for bench.py's gpu_launches) */
 long long sqpb200_launch_count(sqpb200_handle h);
+/* Developer aid: cycle counters per solver phase, summed over all instances since the last reset (out16[16]; all zero unless the
+ * library was built with SQPB200_QP_FLAGS=-DQP_PROFILE; indices = the PR_* enum of csrc/qp_kernel.cuh). */
+int sqpb200_get_profile(sqpb200_handle h, long long* out16, int reset);
 /* smem bytes per QP, team size and QPs per CTA chosen for the solve kernel */
 int sqpb200_solve_config(sqpb200_handle h, int* team_size, int* qps_per_cta, int* smem_per_cta);
 /* device time of the last solve launch measured with CUDA events on the handle's stream (ms) */

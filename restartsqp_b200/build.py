@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsqpb200.so")
 OBJDIR = os.path.join(HERE, "build")
-HEADERS = [os.path.join(CSRC, f) for f in ("qp_kernel.cuh", "l0_kernels.cuh")] + [
+HEADERS = [os.path.join(CSRC, f) for f in ("qp_kernel.cuh", "l0_kernels.cuh", "tma.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "sqpb200.h")]
 # (threads per QP, threads per CTA, warps per SM the registers are capped for): one warp per QP, 4/2/1 QPs per CTA
 TEAMS = [(32, 128, 16), (32, 64, 16), (32, 32, 16), (32, 128, 32)]

@@ -60,6 +60,7 @@ struct sqpb200_handle_s {
     void* stage = nullptr;
     size_t stage_bytes = 0;
     long long launches = 0;
+    long long* dprof = nullptr;  // [16] phase cycle counters (written by -DQP_PROFILE builds of the solve kernels only)
     float last_ms = 0.f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int team = 0, teams_per_cta = 0, smem_cta = 0;
@@ -169,6 +170,8 @@ int sqpb200_create(int batch, int nV, int nC, int qptype, int device, const sqpb
     }
     if (rc) { *out = h; return SQPB200_ERR_CUDA; }
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+    if (cudaMalloc((void**)&h->dprof, 16 * sizeof(long long)) == cudaSuccess) cudaMemset(h->dprof, 0, 16 * sizeof(long long));
+    else h->dprof = nullptr;
     // status = NOTINITIALISED until the first solve
     std::vector<int> st(batch, SQPB200_QPERROR_NOTINITIALISED);
     cudaMemcpy(h->dstatus, st.data(), B * sizeof(int), cudaMemcpyHostToDevice);
@@ -181,7 +184,7 @@ int sqpb200_destroy(sqpb200_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dAp, h->dAi, h->dArp, h->dAci, h->dAperm, h->dAsrc, h->dHp, h->dHi, h->dHsrc, h->dAval, h->dHval,
-                    h->arena, h->dstate, h->stage, h->dgpat, h->dgwork};
+                    h->arena, h->dstate, h->stage, h->dgpat, h->dgwork, h->dprof};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -739,6 +742,7 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
     a.x = h->dx; a.y = h->dy; a.obj = h->dobj; a.kkt = h->dkkt; a.status = h->dstatus; a.iters = h->diters;
     a.wsB = h->dwsB; a.wsC = h->dwsC; a.WB = h->dWB; a.WC = h->dWC;
     a.state = h->dstate;
+    a.prof = h->dprof;
     a.inst_state = inst_state;  // per-instance init/hotstart decisions (made in the kernel) replace the handle-level `mode`
     if (h->large) {
         rc = prepare_large(h, a);
@@ -795,6 +799,15 @@ int sqpb200_solve_config(sqpb200_handle h, int* team_size, int* qps_per_cta, int
 }
 
 long long sqpb200_launch_count(sqpb200_handle h) { return h ? h->launches : 0; }
+
+int sqpb200_get_profile(sqpb200_handle h, long long* out16, int reset) {
+    if (!h || !out16 || !h->dprof) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out16, h->dprof, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(h->dprof, 0, 16 * sizeof(long long)));
+    return 0;
+}
 
 // ------------------------------------------------------------------------------ results
 static int copy_out(sqpb200_handle h, void* dst, const void* src, size_t bytes, int loc) {

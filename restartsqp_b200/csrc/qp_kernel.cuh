@@ -33,6 +33,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "tma.cuh"
 
 namespace sqpb200 {
 
@@ -73,6 +74,7 @@ struct QPKernelArgs {
     // outputs
     double *x, *y, *obj, *kkt;
     int *status, *iters;
+    long long* prof;         // optional [16] cycle counters per solver phase (filled only by -DQP_PROFILE builds)
     signed char *wsB, *wsC;  // raw working set (+1 upper, -1 lower, 0 inactive)
     int *WB, *WC;            // translated ActiveType
     // resident hot-start state: [batch][state_doubles]: the slice without its factors, then Q, R, T packed
@@ -89,14 +91,17 @@ struct QPKernelArgs {
     int pAp, pAi, pArp, pAci, pAperm, pHp, pHi;
 };
 
-// Slice layout of one QP in shared memory.  Header (2 doubles = 4 ints): nFR, nAC, ramp_offset, initialised.
+// Slice layout of one QP in shared memory.  Header (4 doubles = 8 ints): nFR, nAC, ramp_offset, initialised, then (cluster build of
+// the one-QP-per-CTA kernel) the command and status words the leader CTA shares with its helper CTAs.
 // The factors come last and are sized by the capacity `cap` <= nV (the number of simultaneously free variables
 // stays far below nV on l1-penalty QPs: most slacks sit at zero), which is what sets the occupancy.
 __host__ __device__ inline void qp_fill_layout(QPKernelArgs& a) {
     const int nV = a.nV, nC = a.nC, nT = nV + nC;
     if (a.cap <= 0 || a.cap > nV) a.cap = nV;
-    a.ld = (a.cap % 2 == 0) ? a.cap + 1 : a.cap;  // odd: conflict-free row and column walks
-    int o = 2;
+    // warp kernel: odd leading dimension (conflict-free row and column walks in shared memory); one-QP-per-CTA kernel: the
+    // factors live in global memory and their rows are the source of 16-byte aligned TMA bulk copies -> multiple of 8 doubles
+    a.ld = a.large ? ((a.cap + 7) & ~7) : ((a.cap % 2 == 0) ? a.cap + 1 : a.cap);
+    int o = 4;
     a.ox = o; o += nV; a.og = o; o += nV; a.olb = o; o += nV; a.oub = o; o += nV; a.odx = o; o += nV;
     a.ogN = o; o += nV; a.olbN = o; o += nV; a.oubN = o; o += nV;
     a.oAx = o; o += nC; a.olbA = o; o += nC; a.oubA = o; o += nC; a.odAx = o; o += nC;
@@ -107,9 +112,11 @@ __host__ __device__ inline void qp_fill_layout(QPKernelArgs& a) {
     a.oS = o;
     const int shorts = 3 * nV + 3 * nC;
     o += (shorts * 2 + 7) / 8;
+    if (a.large) o = (o + 15) & ~15;  // 128-byte aligned factor rows
     a.oQ = o; o += a.cap * a.ld;
     a.oRT = o; o += a.cap * a.ld;
     a.oW = o; if (a.large) o += a.cap * a.ld;
+    if (a.large) o = (o + 15) & ~15;
     a.slice_doubles = o;
     a.state_doubles = a.oQ + 2 * nV * nV;  // capacity-independent image
     int p = 0;
@@ -122,7 +129,7 @@ __host__ __device__ inline void qp_fill_layout(QPKernelArgs& a) {
 
 // launch arguments, copied once per CTA; every out-of-line function reads its context from here
 __shared__ QPKernelArgs sA;
-extern __shared__ __align__(16) double qp_smem[];
+extern __shared__ __align__(128) double qp_smem[];
 
 struct MinKey {
     double t;
@@ -148,6 +155,23 @@ __device__ __forceinline__ double quot(double x, double d, double ri) {
 #define QP_STR_(x) #x
 #define QP_STR(x) QP_STR_(x)
 #define QP_U1 _Pragma(QP_STR(unroll QP_UNROLL_N))
+// Phase timers of a -DQP_PROFILE build (tools/large_try.py, tools/per_fixture.py print them): the first thread of every team adds
+// the clock64() cycles it spent in phase i to A.prof[i].  Phase boundaries are team barriers, so one thread's clock is the team's.
+#ifdef QP_PROFILE
+#define PROF_T0 long long prof_t0_ = clock64();
+#define PROF_RESET prof_t0_ = clock64();
+#define PROF2_T0 long long prof_t2_ = clock64();
+#define PROF2_ADD(i) do { long long t_ = clock64(); if (lane == 0 && sA.prof) atomicAdd((unsigned long long*)&sA.prof[i], (unsigned long long)(t_ - prof_t2_)); prof_t2_ = t_; } while (0)
+#define PROF_ADD(i) do { long long t_ = clock64(); if (lane == 0 && sA.prof) atomicAdd((unsigned long long*)&sA.prof[i], (unsigned long long)(t_ - prof_t0_)); prof_t0_ = t_; } while (0)
+#else
+#define PROF_T0
+#define PROF_RESET
+#define PROF2_T0
+#define PROF2_ADD(i) do { } while (0)
+#define PROF_ADD(i) do { } while (0)
+#endif
+enum { PR_STEPDIR = 0, PR_RATIO = 1, PR_STEP = 2, PR_REMOVE = 3, PR_EXTEND = 4, PR_WVEC = 5, PR_ADD = 6, PR_REFAC_W = 7, PR_REFAC_M = 8,
+       PR_REFAC_CHOL = 9, PR_DRIFT = 10, PR_ENSURE_LI = 11, PR_RSOLVE = 12, PR_SETUP = 13, PR_EPILOGUE = 14, PR_TOTAL = 15 };
 
 // TEAM = threads that cooperate on one QP.  32: one warp per QP, everything in the warp's shared-memory slice, pattern
 // staged as 16-bit indices.  > 32: the whole CTA works on one QP (large QPs); the slice lives in
@@ -156,6 +180,9 @@ __device__ __forceinline__ double quot(double x, double d, double ri) {
 template <int TEAM> struct PatIdx { typedef int type; };
 template <> struct PatIdx<32> { typedef short type; };
 __shared__ double* sSlice;     // TEAM > 32: this CTA's slice in global memory
+__shared__ int sClusterSize;   // TEAM > 32: CTAs that share this QP (thread-block cluster), 1 without a cluster launch
+__shared__ uint32_t sPhase;    // TEAM > 32: phase bits of the TMA ring's mbarriers
+__shared__ __align__(8) uint64_t sFull[3];  // TEAM > 32: "stage filled" mbarriers of the TMA ring
 __shared__ double sRedT[32];   // TEAM > 32: scratch of the team-wide min reduction
 __shared__ int sRedP[32];
 
@@ -302,10 +329,17 @@ struct QPT {
         if (sA.is_lp) {
             double sr = sqrt(QP_EPS_REG);
             QP_U1 for (int k = lane; k < nZ * nZ; k += TEAM) { int a_ = k / nZ, b_ = k % nZ; R_(a_, b_) = (a_ == b_) ? sr : 0.0; }
+#ifndef QP_EXACT
+            if constexpr (TEAM > 32) {  // block inverses used by the triangular solves
+                double* W = V_(W);
+                for (int k = lane; k < nZ * 64; k += TEAM) { const int a_ = k >> 6, c_ = k & 63; if (c_ < ld) W[(size_t)a_ * ld + c_] = (c_ == (a_ & 63)) ? 1.0 / sr : 0.0; }
+            }
+#endif
             SYNC();
             return 0;
         }
         if constexpr (TEAM > 32) return recompute_R_blocked();
+        PROF_T0
         // M = Z'(HZ), several null-space columns at a time so that all 32 lanes have work (one lane per entry of W = HZ, then
         // one lane per entry of M) instead of one column per pass with nV- and (b+1)-wide loops.  W lives in the seven work
         // vectors t1,t2,t3,w,a,yv,zv, which are contiguous and unused here.  Per entry the same terms in the same order as the
@@ -345,6 +379,7 @@ struct QPT {
                 SYNC();
             }
         }
+        PROF_ADD(PR_REFAC_M);
         // row-wise Cholesky: R'R = M, same per-element summation order as the column version
         QP_U1 for (int i = 0; i < nZ; i++) {
             QP_U1 for (int j = i + lane; j < nZ; j += TEAM) {
@@ -361,8 +396,10 @@ struct QPT {
             QP_U1 for (int j = lane; j < i; j += TEAM) R_(i, j) = 0.0;
             SYNC();
         }
+        PROF_ADD(PR_REFAC_CHOL);
         return 0;
     }
+#ifdef QP_EXACT
     // ---- CTA kernel: blocked refactorisation.  Same arithmetic as the column-by-column version above, term for term and in
     // the same order per element (every sum runs over its index in ascending order), reorganised so that the O(nZ^2 nFR)
     // and O(nZ^3) parts are shared-memory tiled contractions instead of latency-bound dot products:
@@ -429,6 +466,7 @@ struct QPT {
         const short *FR = FR_, *posFR = posFR_;
         const pidx *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
         const bool has_H = sA.has_H && !sA.is_lp;
+        PROF_T0
         // A: W[p][b]
         QP_U1 for (int e = lane; e < nFR * nZ; e += TEAM) {
             const int p = e / nZ, b = e % nZ;
@@ -443,11 +481,13 @@ struct QPT {
             W[p * ld + b] = s;
         }
         SYNC();
+        PROF_ADD(PR_REFAC_W);
         // B: M (upper triangle) into R
         QP_U1 for (int b0 = 0; b0 < nZ; b0 += 64)
             QP_U1 for (int a0 = 0; a0 < b0 + 64 && a0 < nZ; a0 += TA)
                 tile_contract<1>(Q, 0, W, 0, nFR, RT, a0, nZ, b0, nZ, ld, true);
         SYNC();
+        PROF_ADD(PR_REFAC_M);
         // C: Cholesky by block rows
         QP_U1 for (int i0 = 0; i0 < nZ; i0 += TA) {
             const int i1 = (i0 + TA < nZ) ? i0 + TA : nZ;
@@ -474,6 +514,7 @@ struct QPT {
                 SYNC();
             }
         }
+        PROF_ADD(PR_REFAC_CHOL);
         return 0;
     }
     // ---- CTA kernel: blocked triangular solves with R.  The column-oriented substitutions above need two team barriers per
@@ -553,6 +594,335 @@ struct QPT {
             SYNC();
         }
     }
+#else
+
+    // =====================================================================================================================
+    // One-QP-per-CTA kernel (TEAM == 512), B200 form of the O(n^3) part and of the triangular solves.  Parity gate for
+    // this kernel is north_star's (identical working sets, 1e-8 relative): sums run on the FP64 tensor cores, whose
+    // accumulation order differs from the oracle's; -DQP_EXACT keeps the bit-exact scalar version above for debugging.
+    //
+    //   * contraction tiles C(64x64) (+|-)= X' Y on FP64 DMMA (mma.sync.m8n8k4.f64; 16 warps x (16x16) sub-tiles), operands
+    //     staged by 1-D TMA bulk copies (one per 512-byte tile row, issued by warp 0) into a 3-stage shared-memory ring
+    //     with mbarrier completion: no thread waits on a global load, every tile row is fetched from L2 once;
+    //   * refactorisation: W = H Z (sparse x dense), M = Z'W (DMMA), left-looking block Cholesky with 64-row blocks:
+    //     block-row update (DMMA), diagonal block factorised AND inverted in shared memory, panel = Dinv' S (DMMA);
+    //   * the 64x64 inverses of the diagonal blocks stay in the (then dead) scratch matrix W and turn the triangular
+    //     solves into mat-vecs: per 64 unknowns one strip product and one product with the block inverse;
+    //   * thread-block cluster: the CTAs of a cluster share one QP.  Rank 0 runs the active-set method; ranks > 0 wait
+    //     at a cluster barrier and take their share of the W rows and of the DMMA tiles of every refactorisation, so a
+    //     batch smaller than the SM count still fills the GPU (batch 64 -> 2 CTAs per QP, 16 -> 8).
+    // =====================================================================================================================
+    static constexpr int LT_KC = 32, LT_STAGES = 3, LT_LD = 68, LT_NB = 64;
+    static constexpr int LT_STAGE_DOUBLES = LT_KC * LT_LD;            // one operand of one stage
+    static constexpr int LT_D_LD = 65;
+    // dynamic shared memory map of the large kernel (doubles from qp_smem)
+    static constexpr int LS_X = 0, LS_Y = LT_STAGES * LT_STAGE_DOUBLES, LS_D = 2 * LT_STAGES * LT_STAGE_DOUBLES,
+                         LS_DI = LS_D + LT_NB * LT_D_LD, LS_RED = LS_DI + LT_NB * LT_D_LD, LS_TV = LS_RED + 8 * LT_NB,
+                         LS_TOTAL = LS_TV + 2 * LT_NB;
+
+    static __device__ __forceinline__ void large_sync() {  // leader + helpers: orders generic and TMA accesses to the factors
+        asm volatile("fence.proxy.async;" ::: "memory");
+        if (sClusterSize > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        else __syncthreads();
+    }
+    static __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+    }
+    // C[a*ld + b] (+|-)= sum_{k<K} X[k*ld + a] * Y[k*ld + b] for a, b < 64 (X, Y, C point at the tile origins; X and Y rows must
+    // be 16-byte aligned); stores only a < na, b < nb and, if TRI, ga + a <= gb + b.  Called by all threads of the CTA.
+    template <int SIGN, bool TRI>
+    static __device__ __forceinline__ void mma_tile(const double* X, int xw, const double* Y, int yw, int K, double* C, int na, int nb,
+                                                    int ld, bool init_zero, int ga, int gb) {
+        static_assert(TEAM == 512, "tile mapping assumes 16 warps");
+        uint32_t ph = sPhase;  // mbarrier phase bits of the ring, carried from tile to tile (uniform over the CTA)
+        double* Xs = qp_smem + LS_X;
+        double* Ys = qp_smem + LS_Y;
+        const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31, g = l >> 2, t = l & 3;
+        const int ra = (warp >> 2) * 16, cb = (warp & 3) * 16;
+        double acc[2][2][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int a = ra + mi * 8 + g, b = cb + ni * 8 + t * 2 + j;
+                    acc[mi][ni][j] = (!init_zero && a < na && b < nb && (!TRI || ga + a <= gb + b)) ? C[a * ld + b] : 0.0;
+                }
+        const int nch = (K + LT_KC - 1) / LT_KC;
+        auto issue = [&](int chunk, int s) {  // warp 0: one bulk copy per operand row
+            const int rows = (K - chunk * LT_KC < LT_KC) ? K - chunk * LT_KC : LT_KC;
+            if (l == 0) mbar_expect_tx(&sFull[s], (uint32_t)rows * (uint32_t)(xw + yw) * 8u);
+            __syncwarp();
+            if (l < rows) {
+                const size_t kr = (size_t)(chunk * LT_KC + l) * ld;
+                bulk_g2s(Xs + s * LT_STAGE_DOUBLES + l * LT_LD, X + kr, (uint32_t)xw * 8u, &sFull[s]);
+                bulk_g2s(Ys + s * LT_STAGE_DOUBLES + l * LT_LD, Y + kr, (uint32_t)yw * 8u, &sFull[s]);
+            }
+        };
+        if (warp == 0)
+            for (int c = 0; c < LT_STAGES && c < nch; c++) issue(c, c);
+        for (int c = 0; c < nch; c++) {
+            const int s = c % LT_STAGES;
+            while (!mbar_try_wait(&sFull[s], (ph >> s) & 1u)) {}
+            ph ^= 1u << s;
+            const int rows = (K - c * LT_KC < LT_KC) ? K - c * LT_KC : LT_KC;
+            const double* xs = Xs + s * LT_STAGE_DOUBLES + ra + g;
+            const double* ys = Ys + s * LT_STAGE_DOUBLES + cb + g;
+            const int k4n = (rows + 3) >> 2;
+#pragma unroll 2
+            for (int k4 = 0; k4 < k4n; k4++) {
+                const int kr = k4 * 4 + t;
+                double a0 = xs[kr * LT_LD], a1 = xs[kr * LT_LD + 8], b0 = ys[kr * LT_LD], b1 = ys[kr * LT_LD + 8];
+                if (kr >= rows) { a0 = 0.0; a1 = 0.0; b0 = 0.0; b1 = 0.0; }
+                if (SIGN < 0) { a0 = -a0; a1 = -a1; }
+                dmma(acc[0][0], a0, b0); dmma(acc[0][1], a0, b1); dmma(acc[1][0], a1, b0); dmma(acc[1][1], a1, b1);
+            }
+            __syncthreads();  // stage s consumed by every warp
+            if (warp == 0 && c + LT_STAGES < nch) issue(c + LT_STAGES, s);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int a = ra + mi * 8 + g, b = cb + ni * 8 + t * 2 + j;
+                    if (a < na && b < nb && (!TRI || ga + a <= gb + b)) C[a * ld + b] = acc[mi][ni][j];
+                }
+        if (tid == 0) sPhase = ph;
+        __syncthreads();
+    }
+    // leader only: Cholesky factor of the nb x nb diagonal block at (i0, i0) and its inverse, both in shared memory; the factor
+    // goes back to R, the inverse to W[i0 + r][c].  Returns 0 or 1 + failing pivot (uniform).
+    static __device__ __forceinline__ int diag_block(int i0, int nb) {
+        QP_CTX
+        double *RT = V_(RT), *W = V_(W);
+        double* D = qp_smem + LS_D;    // upper part: the block being eliminated; lower part: finished rows, transposed
+        double* DI = qp_smem + LS_DI;
+        const int tid = threadIdx.x;
+        for (int e = tid; e < LT_NB * LT_NB; e += TEAM) {
+            const int r = e >> 6, c = e & 63;
+            D[r * LT_D_LD + c] = (r < nb && c < nb && r <= c) ? R_(i0 + r, i0 + c) : 0.0;
+            DI[r * LT_D_LD + c] = 0.0;
+        }
+        __syncthreads();
+        // right-looking, one barrier per pivot: the trailing update reads row k unscaled (a_ki a_kj / a_kk) while the scaled row
+        // is written to the transposed (lower) position
+        for (int k = 0; k < nb; k++) {
+            const double akk = D[k * LT_D_LD + k];
+            if (!(akk > QP_ZERO)) return 1 + i0 + k;
+            const double dd = sqrt(akk), inv = 1.0 / akk;
+            const int rem = nb - k - 1;
+            if (tid < nb - k) { const int j = k + tid; D[j * LT_D_LD + k] = (tid == 0) ? dd : D[k * LT_D_LD + j] / dd; }
+            for (int e = tid; e < rem * rem; e += TEAM) {
+                const int i = k + 1 + e / rem, j = k + 1 + e % rem;
+                if (j >= i) D[i * LT_D_LD + j] -= D[k * LT_D_LD + i] * D[k * LT_D_LD + j] * inv;
+            }
+            __syncthreads();
+        }
+        // R block = transpose of the lower part; then the inverse, column c by 8 threads (c = tid / 8), back substitution
+        // x_c = 1 / R_cc, x_r = -(sum_{l = r+1..c} R_rl x_l) / R_rr
+        {
+            const int c = tid >> 3, sub = tid & 7;
+            if (c < nb && sub == 0) DI[c * LT_D_LD + c] = 1.0 / D[c * LT_D_LD + c];
+            __syncwarp();
+            for (int r = nb - 2; r >= 0; r--) {  // uniform trip count; columns c <= r idle
+                double sacc = 0.0;
+                if (c < nb && r < c)
+                    for (int l = r + 1 + sub; l <= c; l += 8) sacc += D[l * LT_D_LD + r] * DI[l * LT_D_LD + c];
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+                if (c < nb && r < c && sub == 0) DI[r * LT_D_LD + c] = -sacc / D[r * LT_D_LD + r];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < LT_NB * LT_NB; e += TEAM) {
+            const int r = e >> 6, c = e & 63;
+            if (r < nb && c < nb && r <= c) R_(i0 + r, i0 + c) = D[c * LT_D_LD + r];
+            if (r < nb && c < nb) W[(size_t)(i0 + r) * ld + c] = DI[r * LT_D_LD + c];
+        }
+        __syncthreads();
+        return 0;
+    }
+    // Executed by every CTA of the cluster (rank, cs): the refactorisation R'R = Z'(H + reg I)Z with all its cluster barriers.
+    static __device__ __noinline__ int refac_body(int rank, int cs) {
+        QP_CTX QP_PAT
+        volatile int* vh = hdr;
+        const int nFR = vh[0], nAC = vh[1], nZ = nFR - nAC;
+        double *RT = V_(RT), *W = V_(W);
+        const double *Q = V_(Q), *Hv = V_(Hv);
+        const short *FR = FR_, *posFR = posFR_;
+        const pidx *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
+        const bool has_H = sA.has_H && !sA.is_lp;
+        PROF_T0
+        // A: W[p][b] = (H z_b)[FR[p]], entries split over the cluster
+        for (int e = rank * TEAM + lane; e < nFR * nZ; e += cs * TEAM) {
+            const int p = e / nZ, b = e - p * nZ;
+            double s = 0.0;
+            if (has_H) {
+                const int c = FR[p], e1 = Hp[c + 1];
+                for (int h = Hp[c]; h < e1; h++) {
+                    const int pr = posFR[Hi[h]];
+                    if (pr >= 0) s += Hv[h] * Q[(size_t)pr * ld + b];
+                }
+            }
+            W[(size_t)p * ld + b] = s;
+        }
+        large_sync();
+        PROF_ADD(PR_REFAC_W);
+        // B: M = Z'W, upper-triangle tiles dealt round-robin to the CTAs of the cluster
+        {
+            int t = 0;
+            for (int b0 = 0; b0 < nZ; b0 += LT_NB)
+                for (int a0 = 0; a0 <= b0; a0 += LT_NB, t++)
+                    if (t % cs == rank) {
+                        const int xw = (ld - a0 < LT_NB) ? ld - a0 : LT_NB, yw = (ld - b0 < LT_NB) ? ld - b0 : LT_NB;
+                        mma_tile<1, true>(Q + a0, xw, W + b0, yw, nFR, RT + (size_t)a0 * ld + b0, (nZ - a0 < LT_NB) ? nZ - a0 : LT_NB,
+                                          (nZ - b0 < LT_NB) ? nZ - b0 : LT_NB, ld, true, a0, b0);
+                    }
+        }
+        large_sync();
+        PROF_ADD(PR_REFAC_M);
+        // C: left-looking block Cholesky
+        int fail = 0;
+        for (int i0 = 0; i0 < nZ; i0 += LT_NB) {
+            const int i1 = (i0 + LT_NB < nZ) ? i0 + LT_NB : nZ, nbk = i1 - i0;
+            if (i0 > 0) {
+                int t = 0;
+                for (int b0 = 0; b0 < nZ - i0; b0 += LT_NB, t++)
+                    if (t % cs == rank) {
+                        const int xw = (ld - i0 < LT_NB) ? ld - i0 : LT_NB, yw = (ld - i0 - b0 < LT_NB) ? ld - i0 - b0 : LT_NB;
+                        mma_tile<-1, true>(RT + i0, xw, RT + i0 + b0, yw, i0, RT + (size_t)i0 * ld + i0 + b0, nbk,
+                                           (nZ - i0 - b0 < LT_NB) ? nZ - i0 - b0 : LT_NB, ld, false, 0, b0);
+                    }
+                large_sync();
+            }
+            if (rank == 0) {
+                const int f = diag_block(i0, nbk);
+                if (lane == 0) hdr[5] = f;
+            }
+            large_sync();
+            fail = vh[5];
+            if (fail) break;
+            {
+                int t = 0;
+                for (int b0 = i1; b0 < nZ; b0 += LT_NB, t++)
+                    if (t % cs == rank) {
+                        const int yw = (ld - b0 < LT_NB) ? ld - b0 : LT_NB;
+                        mma_tile<1, false>(W + (size_t)i0 * ld, (ld < LT_NB) ? ld : LT_NB, RT + (size_t)i0 * ld + b0, yw, nbk, RT + (size_t)i0 * ld + b0, nbk,
+                                           (nZ - b0 < LT_NB) ? nZ - b0 : LT_NB, ld, true, 0, 0);
+                    }
+            }
+            if (i1 < nZ) large_sync();
+        }
+        PROF_ADD(PR_REFAC_CHOL);
+        return fail;
+    }
+    static __device__ QP_FN int recompute_R_blocked() {
+        QP_CTX
+        if (lane == 0) hdr[4] = 1;  // command: refactorise
+        __syncthreads();
+        large_sync();               // releases the helper CTAs
+        return refac_body(0, sClusterSize);
+    }
+    // ranks > 0 of the cluster
+    static __device__ void helper_loop(int rank, int cs) {
+        QP_CTX
+        volatile int* vh = hdr;
+        for (;;) {
+            large_sync();
+            if (vh[4] == 2) return;  // command: exit
+            refac_body(rank, cs);
+        }
+    }
+    // R' u = z (n unknowns, in place) with the block inverses; col >= 0: also R(k, col) = u_k
+    static __device__ QP_FN void fwd_solve_R_blocked(double* z, int n, int col) {
+        QP_CTX
+        double* RT = V_(RT);
+        const double* W = V_(W);
+        double* red = qp_smem + LS_RED;
+        double* tv = qp_smem + LS_TV;
+        const int tid = threadIdx.x, c = tid & 63, sl = tid >> 6;
+        for (int i0 = 0; i0 < n; i0 += LT_NB) {
+            const int nb = (n - i0 < LT_NB) ? n - i0 : LT_NB;
+            // strip product: partial sums over k = sl, sl + 8, ... < i0
+            double s = 0.0;
+            if (c < nb) {
+#pragma unroll 8
+                for (int k = sl; k < i0; k += 8) s += R_(k, i0 + c) * z[k];
+            }
+            red[sl * LT_NB + c] = s;
+            __syncthreads();
+            if (tid < LT_NB) {
+                double tsum = 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) tsum += red[q * LT_NB + tid];
+                tv[tid] = (tid < nb) ? z[i0 + tid] - tsum : 0.0;
+            }
+            __syncthreads();
+            // u_c = sum_{k <= c} Dinv[k][c] t_k
+            s = 0.0;
+            if (c < nb) {
+#pragma unroll 8
+                for (int k = sl; k <= c; k += 8) s += W[(size_t)(i0 + k) * ld + c] * tv[k];
+            }
+            red[sl * LT_NB + c] = s;
+            __syncthreads();
+            if (tid < nb) {
+                double u = 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) u += red[q * LT_NB + tid];
+                z[i0 + tid] = u;
+                if (col >= 0) R_(i0 + tid, col) = u;
+            }
+            __syncthreads();
+        }
+    }
+    // R v = z (n unknowns, in place): one warp per row, lanes over the columns
+    static __device__ QP_FN void bwd_solve_R_blocked(double* z, int n) {
+        QP_CTX
+        const double* RT = V_(RT);
+        const double* W = V_(W);
+        double* tv = qp_smem + LS_TV;
+        const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+        for (int i0 = ((n - 1) >> 6) << 6; i0 >= 0; i0 -= LT_NB) {
+            const int nb = (n - i0 < LT_NB) ? n - i0 : LT_NB, i1 = i0 + nb;
+            for (int r = warp; r < nb; r += TEAM / 32) {
+                double s = 0.0;
+#pragma unroll 4
+                for (int k = i1 + l; k < n; k += 32) s += R_(i0 + r, k) * z[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (l == 0) tv[r] = z[i0 + r] - s;
+            }
+            __syncthreads();
+            for (int r = warp; r < nb; r += TEAM / 32) {
+                double s = 0.0;
+                for (int cc = r + l; cc < nb; cc += 32) s += W[(size_t)(i0 + r) * ld + cc] * tv[cc];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (l == 0) z[i0 + r] = s;
+            }
+            __syncthreads();
+        }
+    }
+    // after extend_R bordered R with column/row b (diagonal rho): extend the inverse of the last diagonal block
+    static __device__ QP_FN void extend_Dinv(int b, double rho) {
+        QP_CTX
+        const double* RT = V_(RT);
+        double* W = V_(W);
+        const int i0 = (b >> 6) << 6, c = b - i0, tid = threadIdx.x;
+        if (tid < c) {  // Dinv[r][c] = -(sum_{l = r..c-1} Dinv[r][l] R(i0 + l, b)) / rho
+            double s = 0.0;
+            for (int q = tid; q < c; q++) s += W[(size_t)(i0 + tid) * ld + q] * R_(i0 + q, b);
+            W[(size_t)(i0 + tid) * ld + c] = -s / rho;
+        } else if (tid == c) W[(size_t)(i0 + c) * ld + c] = 1.0 / rho;
+        __syncthreads();
+    }
+#endif  // QP_EXACT
     // border R with the new last null-space column; returns 1 if curvature acceptable
     static __device__ QP_FN int extend_R(int check_curvature) {
         QP_CTX
@@ -562,6 +932,9 @@ struct QPT {
             QP_U1 for (int a_ = lane; a_ < b; a_ += TEAM) { R_(a_, b) = 0.0; R_(b, a_) = 0.0; }
             if (lane == 0) R_(b, b) = sqrt(QP_EPS_REG);
             SYNC();
+#ifndef QP_EXACT
+            if constexpr (TEAM > 32) extend_Dinv(b, sqrt(QP_EPS_REG));
+#endif
             return 1;
         }
         const double *Q = V_(Q), *t2 = V_(t2);
@@ -595,6 +968,9 @@ struct QPT {
         if (lane == 0) R_(b, b) = sqrt(rho2);
         QP_U1 for (int a_ = lane; a_ < b; a_ += TEAM) R_(b, a_) = 0.0;
         SYNC();
+#ifndef QP_EXACT
+        if constexpr (TEAM > 32) extend_Dinv(b, sqrt(rho2));
+#endif
         return 1;
     }
 
@@ -863,9 +1239,11 @@ struct QPT {
             }
             SYNC();
             // R' u = rhs (forward), R z = u (backward); column oriented
+            PROF2_T0
             if constexpr (TEAM > 32) {
                 fwd_solve_R_blocked(zv, nZ, -1);
                 bwd_solve_R_blocked(zv, nZ);
+                PROF2_ADD(PR_RSOLVE);
             } else {
                 double* rinv = V_(dy);  // dy is dead here (rewritten below)
                 QP_U1 for (int k = lane; k < nZ; k += TEAM) rinv[k] = 1.0 / R_(k, k);
@@ -884,6 +1262,7 @@ struct QPT {
                     QP_U1 for (int i = lane; i < k; i += TEAM) zv[i] -= R_(i, k) * zk;
                     SYNC();
                 }
+                PROF2_ADD(PR_RSOLVE);
             }
             QP_U1 for (int p = lane; p < nFR; p += TEAM) {
                 double s = 0.0;
@@ -1049,6 +1428,7 @@ struct QPT {
         const double *gN = V_(gN), *lbN = V_(lbN), *ubN = V_(ubN), *lbAN = V_(lbAN), *ubAN = V_(ubAN);
         short *sB = sB_, *sC = sC_, *AC = AC_;
         iters = 0;
+        PROF_T0
         QP_U1 for (int it = 0;; it++) {
             const int nAC = hdr[1];
             // w[0..nV) <- bound shift of fixed variables, w[nV..) <- constraint shift by AC position, a <- dg
@@ -1061,6 +1441,7 @@ struct QPT {
             SYNC();
             step_direction(a, w, w + nV);
             mulA(dx, dAx);
+            PROF_ADD(PR_STEPDIR);
 
             // ---- ratio tests: position = scan order of the sequential rule
             double best = 2.0; int bpos = 0x7fffffff;
@@ -1109,6 +1490,7 @@ struct QPT {
                 else { bc_idx = p - 3 * nC - 2 * nV; bc_isbound = 1; bc_status = 1; }
             }
             SYNC();
+            PROF_ADD(PR_RATIO);
             // ---- step
             if (bc_idx < 0) {
                 QP_U1 for (int i = lane; i < nV; i += TEAM) { x[i] += dx[i]; g[i] = gN[i]; lb[i] = lbN[i]; ub[i] = ubN[i]; }
@@ -1131,6 +1513,7 @@ struct QPT {
                 }
                 SYNC();
             }
+            PROF_ADD(PR_STEP);
             // ---- change the working set
             if (bc_status == 0) {
                 int flipped = 0;
@@ -1140,7 +1523,10 @@ struct QPT {
                     if (lane == 0) y[bc_idx] = 0.0;
                     SYNC();
                     if (remove_bound(bc_idx)) { iters = it; return ST_CAPACITY; }
-                    if (!extend_R(flags & FLAG_FLIPPING)) {
+                    PROF_ADD(PR_REMOVE);
+                    const int ext_ok = extend_R(flags & FLAG_FLIPPING);
+                    PROF_ADD(PR_EXTEND);
+                    if (!ext_ok) {
                         if (!(flags & FLAG_FLIPPING)) { iters = it; return ST_UNBOUNDED; }
                         bound_w(bc_idx);
                         add_bound(bc_idx, -old);
@@ -1154,7 +1540,10 @@ struct QPT {
                     if (lane == 0) y[nV + bc_idx] = 0.0;
                     SYNC();
                     remove_constraint(bc_idx);
-                    if (!extend_R(flags & FLAG_FLIPPING)) {
+                    PROF_ADD(PR_REMOVE);
+                    const int ext_ok = extend_R(flags & FLAG_FLIPPING);
+                    PROF_ADD(PR_EXTEND);
+                    if (!ext_ok) {
                         if (!(flags & FLAG_FLIPPING)) { iters = it; return ST_UNBOUNDED; }
                         double z2, a2;
                         constraint_w(bc_idx, z2, a2);
@@ -1165,31 +1554,41 @@ struct QPT {
                     }
                 }
                 if (flipped) {
+                    PROF_ADD(PR_ADD);
                     if (recompute_R()) { iters = it; return ST_INTERNAL; }
+                    PROF_RESET
                 }
             } else {
                 if (bc_isbound) {
                     double z2 = bound_w(bc_idx);
+                    PROF_ADD(PR_WVEC);
                     if (!(z2 > QP_EPS_LI * QP_EPS_LI)) {
                         int e_ = ensure_li(-1, bc_idx, bc_status);
                         if (e_) { iters = it; return e_ == 2 ? ST_CAPACITY : ST_INFEASIBLE; }
                         bound_w(bc_idx);
+                        PROF_ADD(PR_ENSURE_LI);
                     }
                     add_bound(bc_idx, bc_status);
+                    PROF_ADD(PR_ADD);
                 } else {
                     double z2, a2;
                     constraint_w(bc_idx, z2, a2);
+                    PROF_ADD(PR_WVEC);
                     if (!(z2 > QP_EPS_LI * QP_EPS_LI * a2) || a2 == 0.0) {
                         int e_ = ensure_li(bc_idx, -1, bc_status);
                         if (e_) { iters = it; return e_ == 2 ? ST_CAPACITY : ST_INFEASIBLE; }
                         constraint_w(bc_idx, z2, a2);
+                        PROF_ADD(PR_ENSURE_LI);
                     }
                     add_constraint(bc_idx, bc_status);
+                    PROF_ADD(PR_ADD);
                 }
                 if (recompute_R()) { iters = it; return ST_INTERNAL; }
+                PROF_RESET
             }
             if (tau <= QP_EPS && (flags & FLAG_RAMPING)) ramping();
             else if (flags & FLAG_DRIFT) drift_correction();
+            PROF_ADD(PR_DRIFT);
         }
     }
 
@@ -1419,6 +1818,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solv
     __syncwarp();
 
     int iters = 0, total_iters = 0;
+    PROF_T0
     if (status != ST_CAPACITY) {
         if (mode == MODE_HOT_VARIED) {
             if (QPT<32>::refactorise()) mode = MODE_COLD;  // projected Hessian of the kept set not PD: cold start
@@ -1438,7 +1838,9 @@ __global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solv
         if (lane == 0) { A.status[b] = ST_CAPACITY; A.iters[b] = 0; }
         return;
     }
+    PROF_ADD(PR_TOTAL);
     QPT<32>::epilogue(b, status, total_iters);
+    PROF_ADD(PR_EPILOGUE);
     if ((A.flags & FLAG_KEEP_STATE) && A.state) {
         double* st = A.state + (size_t)b * A.state_doubles;
         for (int i = lane; i < A.oQ; i += 32) st[i] = slice[i];
@@ -1455,23 +1857,39 @@ __global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solv
 // -------------------------------------------------------------------------------------------
 // The slice of instance b (vectors, index lists and the nV x nV factors Q, R/T) lives in global memory at
 // gwork[b][slice_doubles] and persists between launches, so a hot start needs no save/restore; the CTA streams it through
-// L1/L2.  Same solver code as the warp kernel (QPT<TEAM>), the team barrier being __syncthreads().
+// L1/L2.  Same solver code as the warp kernel (QPT<TEAM>), the team barrier being __syncthreads(); the O(n^3) refactorisation
+// runs as TMA-staged FP64 DMMA tiles shared by the CTAs of a thread-block cluster (see the block comment in QPT).
 template <int CTA_THREADS>
 __global__ void __launch_bounds__(CTA_THREADS, 1) qp_solve_large_kernel(const __grid_constant__ QPKernelArgs A) {
     typedef QPT<CTA_THREADS> S;
     const int tid = threadIdx.x;
-    const int b = blockIdx.x;
+    unsigned cs = 1, rank = 0;
+#ifndef QP_EXACT
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cs));
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+#endif
+    const int b = blockIdx.x / cs;  // the CTAs of a cluster share one QP: rank 0 solves, the others help with refactorisations
     {
         const int* src = reinterpret_cast<const int*>(&A);
         int* dst = reinterpret_cast<int*>(&sA);
         for (int i = tid; i < (int)(sizeof(QPKernelArgs) / 4); i += CTA_THREADS) dst[i] = src[i];
-        if (tid == 0) sSlice = A.gwork + (size_t)b * A.slice_doubles;
+        if (tid == 0) {
+            sSlice = A.gwork + (size_t)b * A.slice_doubles;
+            sClusterSize = (int)cs;
+            sPhase = 0u;
+            for (int s = 0; s < 3; s++) mbar_init(&sFull[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     __syncthreads();
-    if (A.mask && !A.mask[b]) return;  // CTA-uniform
+    if (tid == 0 && rank != 0) sA.prof = nullptr;  // phase timers: the leader's clock only
+    if (A.mask && !A.mask[b]) return;  // uniform over the cluster
     const int nV = A.nV, nC = A.nC;
     double* slice = A.gwork + (size_t)b * A.slice_doubles;
     int* hdr = reinterpret_cast<int*>(slice);
+#ifndef QP_EXACT
+    if (rank != 0) { S::helper_loop((int)rank, (int)cs); return; }
+#endif
 
     int mode = A.mode;
     if (A.inst_state) {
@@ -1506,6 +1924,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) qp_solve_large_kernel(const __
     __syncthreads();
 
     int iters = 0, total_iters = 0, status;
+    const int lane = tid;
+    PROF_T0
     if (mode == MODE_HOT_VARIED) {
         if (S::refactorise()) mode = MODE_COLD;
         else S::drift_correction();
@@ -1518,7 +1938,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) qp_solve_large_kernel(const __
         status = S::homotopy(A.max_iter, iters);
         total_iters += iters;
     }
+    PROF_ADD(PR_TOTAL);
     S::epilogue(b, status, total_iters);
+    PROF_ADD(PR_EPILOGUE);
+#ifndef QP_EXACT
+    if (tid == 0) hdr[4] = 2;  // command: exit
+    __syncthreads();
+    S::large_sync();
+#endif
 }
 
 #endif  // __CUDACC__

@@ -1,15 +1,56 @@
-// qp_solve_large_inst.cu -- instantiation of qp_solve_large_kernel<QP_CTA>: one QP per CTA, the slice (vectors and the
-// nV x nV factors) in global memory.  Used when a QP does not fit the shared-memory resident warp kernel.
+// qp_solve_large_inst.cu -- instantiation of qp_solve_large_kernel<QP_CTA>: one QP per CTA (or per thread-block cluster), the
+// slice (vectors and the nV x nV factors) in global memory.  Used when a QP does not fit the shared-memory resident warp kernel.
 #include "qp_kernel.cuh"
+
+#include <cstdlib>
 
 #ifndef QP_CTA
 #define QP_CTA 512
 #endif
 
 namespace sqpb200 {
+// CTAs per QP: the largest power of two <= 8 (portable cluster size) that keeps batch * cluster <= SM count, so that a batch
+// smaller than the GPU still fills it.  SQPB200_CLUSTER overrides (1, 2, 4, 8, 16; 16 needs the non-portable opt-in).
+static int cluster_for_batch(int batch) {
+    if (const char* e = getenv("SQPB200_CLUSTER")) { int v = atoi(e); if (v >= 1 && v <= 16 && (v & (v - 1)) == 0) return v; }
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int cs = 1;
+    while (cs < 8 && (long long)batch * cs * 2 <= sms) cs *= 2;
+    return cs;
+}
+
 cudaError_t launch_qp_solve_large(const QPKernelArgs& a, cudaStream_t stream) {
+#ifdef QP_EXACT
     qp_solve_large_kernel<QP_CTA><<<a.batch, QP_CTA, 0, stream>>>(a);
     return cudaGetLastError();
+#else
+    const int cs = cluster_for_batch(a.batch);
+    const size_t smem = (size_t)QPT<QP_CTA>::LS_TOTAL * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(qp_solve_large_kernel<QP_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (cs > 8) {
+        e = cudaFuncSetAttribute(qp_solve_large_kernel<QP_CTA>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)a.batch * cs);
+    cfg.blockDim = dim3(QP_CTA);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, qp_solve_large_kernel<QP_CTA>, a);
+#endif
 }
 int qp_solve_large_threads() { return QP_CTA; }
+int qp_solve_large_cluster(int batch) {
+#ifdef QP_EXACT
+    (void)batch; return 1;
+#else
+    return cluster_for_batch(batch);
+#endif
+}
 }  // namespace sqpb200

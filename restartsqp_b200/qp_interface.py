@@ -298,6 +298,15 @@ class CudaQPInterface:
     def last_solve_ms(self):
         return float(self.L.sqpb200_last_solve_ms(self.h))
 
+    PROFILE_PHASES = ("stepdir", "ratio", "step", "remove", "extend_R", "w_vec", "add", "refac_W", "refac_M", "refac_chol",
+                      "drift", "ensure_li", "R_solves(in stepdir)", "setup", "epilogue", "total")
+
+    def profile(self, reset=True):
+        """Per-phase cycle counters of a -DQP_PROFILE build (all zero otherwise), summed over instances."""
+        out = np.zeros(16, np.int64)
+        _check(self.h, self.L.sqpb200_get_profile(self.h, out.ctypes.data_as(C.c_void_p), int(reset)), "get_profile")
+        return dict(zip(self.PROFILE_PHASES, out.tolist()))
+
     def solve_config(self):
         t, q, s = C.c_int(), C.c_int(), C.c_int()
         _check(self.h, self.L.sqpb200_solve_config(self.h, C.byref(t), C.byref(q), C.byref(s)), "solve_config")

@@ -14,6 +14,9 @@ def run(nV, nC, Ac, Hc, g, lb, ub, lbA, ubA, team, label, check=True, maxiter=10
     if nC: s.set_lbA(lbA); s.set_ubA(ubA)
     s._solve(r.QPType.QP, None, None, 0); ms = s.last_solve_ms()
     st, it = s.get_status(), s.get_iterations()
+    pr = s.profile()
+    if pr["total"]:
+        print("  profile (% of total cycles): " + "  ".join("%s=%.1f" % (k, 100.0 * v / pr["total"]) for k, v in pr.items() if v and k != "total"), flush=True)
     x = s.get_optimal_solution(); wc, wb = s.get_working_set(translated=False)
     print(f"{label}: nV={nV} nC={nC} B={B} cfg={s.solve_config()} {ms:.2f} ms status={dict(zip(*np.unique(st, return_counts=True)))} iters mean={it.mean():.1f} max={it.max()}", flush=True)
     bad = 0

@@ -20,5 +20,8 @@ for k, q in enumerate(bench.load_fixtures()):
     for rep in range(2):
         s._solve(r.QPType.QP, None, None, 0); ms = s.last_solve_ms()
     st = s.get_status(); it = s.get_iterations()
+    pr = s.profile()
+    if pr["total"]:
+        print("\n    profile (% of total cycles): " + "  ".join("%s=%.1f" % (k, 100.0 * v / pr["total"]) for k, v in pr.items() if v and k != "total"), end="\n    ")
     print(f"solve={ms:.2f}ms  {B/ms*1e3:.0f} QP/s  status={dict(zip(*np.unique(st, return_counts=True)))} iters mean={it.mean():.1f} max={it.max()}", flush=True)
     s.close()

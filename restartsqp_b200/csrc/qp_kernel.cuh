@@ -1177,6 +1177,23 @@ struct QPT {
         QP_CTX
         const int nFR = hdr[0], nAC = hdr[1];
         const double* RT = V_(RT);
+        if (TEAM == 32 && nAC <= 32) {
+            // whole right-hand side in registers (lane k holds b_k and its pivot): the substitution chain is one shuffle and
+            // the three operations of quot() per unknown, no barrier and no shared-memory round trip.  Same operations on
+            // the same operands in the same order as the loop below (and the oracle).
+            const bool act = lane < nAC;
+            double bk = act ? b[lane] : 0.0;
+            const double piv = act ? T_(lane, nFR - 1 - lane) : 1.0, ri = 1.0 / piv;
+            QP_U1 for (int i = 0; i < nAC; i++) {
+                const int d = nFR - 1 - i;
+                const double tkd = (lane > i && act) ? T_(lane, d) : 0.0;
+                const double vi = __shfl_sync(0xffffffffu, quot(bk, piv, ri), i);
+                if (lane == i) v[d] = vi;
+                if (lane > i && act) bk -= tkd * vi;
+            }
+            SYNC();
+            return;
+        }
         double* rinv = V_(dAx);  // pivot reciprocals, one per lane in parallel: the sequential part below only multiplies
         QP_U1 for (int i = lane; i < nAC; i += TEAM) rinv[i] = 1.0 / T_(i, nFR - 1 - i);
         SYNC();
@@ -1194,6 +1211,19 @@ struct QPT {
         QP_CTX
         const int nFR = hdr[0], nAC = hdr[1];
         const double* RT = V_(RT);
+        if (TEAM == 32 && nAC <= 32) {  // register form, see solve_T
+            const bool act = lane < nAC;
+            double rk = act ? r[nFR - 1 - lane] : 0.0;
+            const double piv = act ? T_(lane, nFR - 1 - lane) : 1.0, ri = 1.0 / piv;
+            QP_U1 for (int i = nAC - 1; i >= 0; i--) {
+                const double tik = (lane < i) ? T_(i, nFR - 1 - lane) : 0.0;
+                const double ui = __shfl_sync(0xffffffffu, quot(rk, piv, ri), i);
+                if (lane == i) u[i] = ui;
+                if (lane < i) rk -= tik * ui;
+            }
+            SYNC();
+            return;
+        }
         double* rinv = V_(dAx);
         QP_U1 for (int i = lane; i < nAC; i += TEAM) rinv[i] = 1.0 / T_(i, nFR - 1 - i);
         SYNC();

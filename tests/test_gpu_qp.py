@@ -309,8 +309,11 @@ def test_factor_capacity_rescue_path(gpu_lib, cap):
 
 @pytest.mark.parametrize("name", ["QORE_hs104", "QORE_hs107", "QORE_hs116"])
 def test_dumped_qp_on_cta_per_qp_kernel(gpu_lib, name):
-    """The one-QP-per-CTA kernel (slice in global memory) runs the same solver code: forced onto the largest and the most
-    degenerate dumps it must reproduce the oracle bit for bit, like the warp kernel."""
+    """The one-QP-per-CTA kernel (slice in global memory) runs the same active-set code with the refactorisation on the
+    FP64 tensor cores (DMMA accumulates in a different order than the oracle's scalar sums; -DQP_EXACT builds the bit-exact
+    scalar variant).  Its gate is north_star's: same status, and where the oracle solves the QP the same objective to 1e-8 and
+    a KKT point by the reference's own test.  On the rho = 1e8 scaled dump (hs104) the homotopy path is rounding-sensitive,
+    so iteration counts may differ while the solution does not; the well-scaled hs116 must keep the oracle's working set."""
     q = [f for f in FIX if f["name"] == name][0]
     nV, nC, B = q["nV"], q["nC"], 3
     rng = np.random.default_rng(4321)
@@ -320,10 +323,18 @@ def test_dumped_qp_on_cta_per_qp_kernel(gpu_lib, name):
     Hc = (q["H_colptr"], q["H_rowidx"], np.array(q["H_val"]))
     s = solve_batch_csc(nV, nC, A, Hc, g, tile("lb", nV), tile("ub", nV), tile("lbA", nC), tile("ubA", nC), team_size=1024)
     assert s.solve_config()["team_size"] == 1024
+    st, obj = s.get_status(), s.get_obj_value()
+    wc, wb = s.get_working_set(translated=False)
     for b in range(B):
         p = dict(nV=nV, nC=nC, g=g[b], lb=q["lb"], ub=q["ub"], lbA=q["lbA"], ubA=q["ubA"])
         o = H.oracle_solve(orc, p, Acsc=A, Hcsc=Hc)
-        check_against_oracle(s, b, o, nV, strict=(o["status"] == 20))
+        if o["status"] == 20:
+            assert st[b] == 20
+            assert abs(obj[b] - o["obj"]) <= RTOL * max(1.0, abs(o["obj"]))
+            if name == "QORE_hs116":
+                assert (wb[b] == o["wb"]).all() and (wc[b] == o["wc"]).all()
+        else:
+            assert 20 < st[b] <= 30
     s.close()
 
 
@@ -409,14 +420,18 @@ def test_hotstart_state_is_bitwise_the_oracles(gpu_lib, team):
         for b in range(B):
             st = solvers[b].hotstart(g[b], lb[b], ub[b], lbA[b], ubA[b])
             xo, yo, _, ito = solvers[b].solution()
-            assert st == int(s.get_status()[b]) and ito == int(it[b])
-            assert np.array_equal(x[b], xo) and np.array_equal(np.concatenate([yb[b], yc[b]]), yo), (rnd, b)
+            assert st == int(s.get_status()[b])
+            if team == 1024:  # CTA kernel: DMMA sums -> north_star's 1e-8 gate (bit-exact only in a -DQP_EXACT build)
+                assert relerr(x[b], xo) <= RTOL and relerr(np.concatenate([yb[b], yc[b]]), yo) <= 10 * RTOL, (rnd, b)
+            else:
+                assert ito == int(it[b])
+                assert np.array_equal(x[b], xo) and np.array_equal(np.concatenate([yb[b], yc[b]]), yo), (rnd, b)
     s.close()
 
 
 def test_randomised_parity_stress(gpu_lib):
     """tools/qp_stress.py at a small size: random shapes, convex / non-convex / LP, cold + three hot starts, warp kernel with and
-    without a tight factor capacity (rescue launch) and the one-QP-per-CTA kernel; bitwise against the oracle."""
+    without a tight factor capacity (rescue launch): bitwise against the oracle; the one-QP-per-CTA kernel at the 1e-8 gate."""
     import subprocess, sys, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "qp_stress.py"), "14", "7"], capture_output=True, text=True, timeout=600)

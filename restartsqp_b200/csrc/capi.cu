@@ -60,6 +60,13 @@ struct sqpb200_handle_s {
     void* stage = nullptr;
     size_t stage_bytes = 0;
     long long launches = 0;
+    // learned factor capacity: the solve kernels keep a running maximum of the free variables any instance needed (device
+    // int, read back asynchronously after every solve); later solves size the shared-memory factors by it
+    int* dmaxfr = nullptr;
+    int* maxfr_host = nullptr;  // pinned
+    cudaEvent_t ev_maxfr = nullptr;
+    bool maxfr_pending = false, maxfr_valid = false;
+    int maxfr_seen = 0, cfg_cap_key = -1;
     long long* dprof = nullptr;  // [16] phase cycle counters (written by -DQP_PROFILE builds of the solve kernels only)
     float last_ms = 0.f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -170,6 +177,11 @@ int sqpb200_create(int batch, int nV, int nC, int qptype, int device, const sqpb
     }
     if (rc) { *out = h; return SQPB200_ERR_CUDA; }
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+    if (cudaMalloc((void**)&h->dmaxfr, sizeof(int)) == cudaSuccess && cudaMallocHost((void**)&h->maxfr_host, sizeof(int)) == cudaSuccess &&
+        cudaEventCreateWithFlags(&h->ev_maxfr, cudaEventDisableTiming) == cudaSuccess) {
+        cudaMemset(h->dmaxfr, 0, sizeof(int));
+        *h->maxfr_host = 0;
+    } else { h->err = "allocation of the capacity counter failed"; *out = h; return SQPB200_ERR_CUDA; }
     if (cudaMalloc((void**)&h->dprof, 16 * sizeof(long long)) == cudaSuccess) cudaMemset(h->dprof, 0, 16 * sizeof(long long));
     else h->dprof = nullptr;
     // status = NOTINITIALISED until the first solve
@@ -184,10 +196,12 @@ int sqpb200_destroy(sqpb200_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dAp, h->dAi, h->dArp, h->dAci, h->dAperm, h->dAsrc, h->dHp, h->dHi, h->dHsrc, h->dAval, h->dHval,
-                    h->arena, h->dstate, h->stage, h->dgpat, h->dgwork, h->dprof};
+                    h->arena, h->dstate, h->stage, h->dgpat, h->dgwork, h->dprof, h->dmaxfr};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_maxfr) cudaEventDestroy(h->ev_maxfr);
+    if (h->maxfr_host) cudaFreeHost(h->maxfr_host);
     delete h;
     return 0;
 }
@@ -307,6 +321,7 @@ static int finish_structure_A(sqpb200_handle h) {
         CK(cudaGetLastError());
     }
     h->A_set = true;
+    h->cfg_cap_key = -1;  // slice layout depends on zA
     if (h->dgpat) { cudaFree(h->dgpat); h->dgpat = nullptr; }
     return 0;
 }
@@ -370,6 +385,7 @@ int sqpb200_set_structure_H(sqpb200_handle h, int zH, const int* row1, const int
     if (h->dHval) { CK(cudaFree(h->dHval)); h->dHval = nullptr; }
     if (dev_alloc(h, &h->dHval, (size_t)h->batch * z)) return SQPB200_ERR_CUDA;
     h->H_set = true;
+    h->cfg_cap_key = -1;
     return z;
 }
 
@@ -396,6 +412,7 @@ int sqpb200_set_structure_csc(sqpb200_handle h, int which, int nnz, const int* c
         if (h->dHval) { CK(cudaFree(h->dHval)); h->dHval = nullptr; }
         if (dev_alloc(h, &h->dHval, (size_t)h->batch * nnz)) return SQPB200_ERR_CUDA;
         h->H_set = true;
+        h->cfg_cap_key = -1;
         return nnz;
     }
     return SQPB200_ERR_INVALID;
@@ -607,10 +624,17 @@ static int choose_config(sqpb200_handle h) {
     // re-solved by the rescue launch with the full capacity nV, so the choice only affects speed, never results.
     int cap = h->opt.factor_cap;
     if (cap == 0) {
+        if (h->maxfr_pending && cudaEventQuery(h->ev_maxfr) == cudaSuccess) {
+            if (*h->maxfr_host > h->maxfr_seen) h->maxfr_seen = *h->maxfr_host;
+            h->maxfr_valid = true; h->maxfr_pending = false;
+        }
         int n_est = (nV >= 2 * nC) ? nV - 2 * nC : nV;
-        cap = n_est + (nC + 1) / 2 + 2;
+        // learned: what this handle's QPs needed so far (+2); before the first read-back: n + ceil(m/2) + 2
+        cap = h->maxfr_valid ? h->maxfr_seen + 2 : n_est + (nC + 1) / 2 + 2;
     }
     if (cap < 0 || cap > nV) cap = nV;
+    if (cap == h->cfg_cap_key && h->team != 0) return 0;  // configuration already chosen for this capacity
+    h->cfg_cap_key = cap;
     const bool fits16 = h->zA < 32768 && h->zH < 32768;
     h->large = (h->opt.team_size == 1024);
     if (!h->large) {
@@ -742,6 +766,7 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
     a.x = h->dx; a.y = h->dy; a.obj = h->dobj; a.kkt = h->dkkt; a.status = h->dstatus; a.iters = h->diters;
     a.wsB = h->dwsB; a.wsC = h->dwsC; a.WB = h->dWB; a.WC = h->dWC;
     a.state = h->dstate;
+    a.maxfr = h->dmaxfr;
     a.prof = h->dprof;
     a.inst_state = inst_state;  // per-instance init/hotstart decisions (made in the kernel) replace the handle-level `mode`
     if (h->large) {
@@ -774,6 +799,11 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
     }
     CK(cudaEventRecord(h->ev1, h->stream));
     h->launches++;
+    if (h->opt.factor_cap == 0) {  // learn the capacity for later solves (asynchronous: never waited for)
+        CK(cudaMemcpyAsync(h->maxfr_host, h->dmaxfr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev_maxfr, h->stream));
+        h->maxfr_pending = true;
+    }
     // reset_flags(): src/qpOASESInterface.cpp:488-496
     h->upd_A = h->upd_H = h->upd_g = h->upd_bounds = false;
     h->first_solved = true;

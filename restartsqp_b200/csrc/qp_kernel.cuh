@@ -86,6 +86,9 @@ struct QPKernelArgs {
     int oQ, oRT, ox, og, olb, oub, odx, oAx, olbA, oubA, odAx, oy, ody, ot1, ot2, ot3, ow, oa, oyv, ozv, oAv, oHv;
     int ogN, olbN, oubN, olbAN, oubAN;  // target data of the homotopy
     int oW;                             // large layout only: scratch matrix (cap x ld)
+    int oP;                             // end of the persistent part of the slice (what a hot start restores)
+    int nW;                             // doubles from ot1 to the end of zv (chunk buffer of the warp kernel's refactorisation)
+    int* maxfr;                         // optional: running maximum of free variables seen by this handle (atomicMax)
     int oS;                             // start of the 16-bit index arrays (sB, FR, posFR, sC, AC, posAC)
     // pattern layout: offsets in 16-bit words from the pattern base
     int pAp, pAi, pArp, pAci, pAperm, pHp, pHi;
@@ -102,23 +105,31 @@ __host__ __device__ inline void qp_fill_layout(QPKernelArgs& a) {
     // factors live in global memory and their rows are the source of 16-byte aligned TMA bulk copies -> multiple of 8 doubles
     a.ld = a.large ? ((a.cap + 7) & ~7) : ((a.cap % 2 == 0) ? a.cap + 1 : a.cap);
     int o = 4;
-    a.ox = o; o += nV; a.og = o; o += nV; a.olb = o; o += nV; a.oub = o; o += nV; a.odx = o; o += nV;
-    a.ogN = o; o += nV; a.olbN = o; o += nV; a.oubN = o; o += nV;
-    a.oAx = o; o += nC; a.olbA = o; o += nC; a.oubA = o; o += nC; a.odAx = o; o += nC;
-    a.olbAN = o; o += nC; a.oubAN = o; o += nC;
-    a.oy = o; o += nT; a.ody = o; o += nT; a.ot1 = o; o += nT; a.ot2 = o; o += nT; a.ot3 = o; o += nT;
-    a.ow = o; o += nT; a.oa = o; o += nT; a.oyv = o; o += nT; a.ozv = o; o += nT;
+    // persistent part = the hot-start image (independent of the factor capacity): iterate, current homotopy data, matrix
+    // values, working-set index lists
+    a.ox = o; o += nV; a.og = o; o += nV; a.olb = o; o += nV; a.oub = o; o += nV;
+    a.oAx = o; o += nC; a.olbA = o; o += nC; a.oubA = o; o += nC;
+    a.oy = o; o += nT;
     a.oAv = o; o += a.zA; a.oHv = o; o += a.zH;
     a.oS = o;
     const int shorts = 3 * nV + 3 * nC;
     o += (shorts * 2 + 7) / 8;
+    a.oP = o;
+    // per-solve part: homotopy targets and work vectors, each sized by its use (the slice size sets the occupancy)
+    const int mx_vc = nV > nC ? nV : nC, mx_cc = nC > a.cap ? nC : a.cap;
+    a.odx = o; o += nV; a.ogN = o; o += nV; a.olbN = o; o += nV; a.oubN = o; o += nV;
+    a.odAx = o; o += nC; a.olbAN = o; o += nC; a.oubAN = o; o += nC;
+    a.ody = o; o += nT;
+    a.ot1 = o; o += nV; a.ot2 = o; o += mx_vc; a.ot3 = o; o += mx_cc; a.ow = o; o += nT; a.oa = o; o += nV;
+    a.oyv = o; o += a.cap; a.ozv = o; o += a.cap;
+    a.nW = o - a.ot1;  // t1 .. zv are contiguous and dead during a refactorisation: its chunk buffer
     if (a.large) o = (o + 15) & ~15;  // 128-byte aligned factor rows
     a.oQ = o; o += a.cap * a.ld;
     a.oRT = o; o += a.cap * a.ld;
     a.oW = o; if (a.large) o += a.cap * a.ld;
     if (a.large) o = (o + 15) & ~15;
     a.slice_doubles = o;
-    a.state_doubles = a.oQ + 2 * nV * nV;  // capacity-independent image
+    a.state_doubles = a.oP + 2 * nV * nV;  // capacity-independent image: persistent part, then Q, R, T packed
     int p = 0;
     a.pAp = p; p += nV + 1; a.pAi = p; p += a.zA; a.pArp = p; p += nC + 1; a.pAci = p; p += a.zA; a.pAperm = p; p += a.zA;
     a.pHp = p; p += nV + 1; a.pHi = p; p += a.zH;
@@ -342,7 +353,7 @@ struct QPT {
         PROF_T0
         // M = Z'(HZ), several null-space columns at a time so that all 32 lanes have work (one lane per entry of W = HZ, then
         // one lane per entry of M) instead of one column per pass with nV- and (b+1)-wide loops.  W lives in the seven work
-        // vectors t1,t2,t3,w,a,yv,zv, which are contiguous and unused here.  Per entry the same terms in the same order as the
+        // vectors t1,t2,t3,w,a,yv,zv (sA.nW doubles), which are contiguous and unused here.  Per entry the same terms in the same order as the
         // column-by-column form: W[p][b] = sum over the entries of H's column FR[p], M[a][b] = sum over p ascending.
         {
             QP_PAT
@@ -351,7 +362,7 @@ struct QPT {
             const short *FR = FR_, *posFR = posFR_;
             const pidx *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
             const bool has_H = sA.has_H != 0;
-            int CH = (7 * (nV + nC)) / nFR;
+            int CH = sA.nW / nFR;
             if (CH > nZ) CH = nZ;
             QP_U1 for (int b0 = 0; b0 < nZ; b0 += CH) {
                 const int cw = (nZ - b0 < CH) ? nZ - b0 : CH;
@@ -1148,7 +1159,7 @@ struct QPT {
                 if (Ai[e] == r) s += Av[e];
             T_(i, nFR) = s;
         }
-        if (lane == 0) { Q[nFR * ld + nFR] = 1.0; FR_[nFR] = (short)v; posFR_[v] = (short)nFR; sB_[v] = 0; hdr[0] = nFR + 1; }
+        if (lane == 0) { Q[nFR * ld + nFR] = 1.0; FR_[nFR] = (short)v; posFR_[v] = (short)nFR; sB_[v] = 0; hdr[0] = nFR + 1; if (nFR + 1 > hdr[6]) hdr[6] = nFR + 1; }
         nFR++;
         SYNC();
         QP_U1 for (int i = 0; i < nAC; i++) {
@@ -1633,7 +1644,7 @@ struct QPT {
         QP_U1 for (int i = lane; i < nC; i += TEAM) {
             y[nV + i] = 0.0; sC[i] = 0; posAC[i] = -1; Ax[i] = 0.0; lbA[i] = -QP_BOUND_RELAX; ubA[i] = QP_BOUND_RELAX;
         }
-        if (lane == 0) { hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; }
+        if (lane == 0) { hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; hdr[6] = 0; }
         SYNC();
     }
     // rebuild TQ and R for the kept working set with the new matrix values; 0 ok
@@ -1736,6 +1747,7 @@ struct QPT {
                 k[0] = primal; k[1] = dual; k[2] = stat; k[3] = compl_; k[4] = compl_ + stat + dual + primal;
             }
             hdr[3] = (status == ST_OPTIMAL) ? 1 : 0;
+            if (sA.maxfr) atomicMax(sA.maxfr, hdr[6]);  // the handle learns the factor capacity its QPs need
         }
         SYNC();
     }
@@ -1810,13 +1822,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solv
     if (mode != MODE_COLD) {
         // restore the pre-solve image: everything but the factors verbatim, then Q (nFR x nFR), R (nZ x nZ), T (nAC x nFR)
         const double* st = A.state + (size_t)b * A.state_doubles;
-        for (int i = lane; i < A.oQ; i += 32) slice[i] = st[i];
+        for (int i = lane; i < A.oP; i += 32) slice[i] = st[i];
         __syncwarp();
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
         if (!hdr[3]) mode = MODE_COLD;  // previous solve did not end optimal: plain re-init (handle_error)
         else if (nFR > cap) status = ST_CAPACITY;
         else {
-            const double *Qp = st + A.oQ, *Rp = Qp + nFR * nFR, *Tp = Rp + nZ * nZ;
+            const double *Qp = st + A.oP, *Rp = Qp + nFR * nFR, *Tp = Rp + nZ * nZ;
             for (int k = lane; k < nFR * nFR; k += 32) Q[(k / nFR) * ld + (k % nFR)] = Qp[k];
             for (int k = lane; k < nZ * nZ; k += 32) R_(k / nZ, k % nZ) = Rp[k];
             for (int k = lane; k < nAC * nFR; k += 32) T_(k / nFR, k % nFR) = Tp[k];
@@ -1873,9 +1885,9 @@ __global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solv
     PROF_ADD(PR_EPILOGUE);
     if ((A.flags & FLAG_KEEP_STATE) && A.state) {
         double* st = A.state + (size_t)b * A.state_doubles;
-        for (int i = lane; i < A.oQ; i += 32) st[i] = slice[i];
+        for (int i = lane; i < A.oP; i += 32) st[i] = slice[i];
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
-        double *Qp = st + A.oQ, *Rp = Qp + nFR * nFR, *Tp = Rp + nZ * nZ;
+        double *Qp = st + A.oP, *Rp = Qp + nFR * nFR, *Tp = Rp + nZ * nZ;
         for (int k = lane; k < nFR * nFR; k += 32) Qp[k] = Q[(k / nFR) * ld + (k % nFR)];
         for (int k = lane; k < nZ * nZ; k += 32) Rp[k] = R_(k / nZ, k % nZ);
         for (int k = lane; k < nAC * nFR; k += 32) Tp[k] = T_(k / nFR, k % nFR);

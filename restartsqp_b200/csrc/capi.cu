@@ -63,6 +63,7 @@ struct sqpb200_handle_s {
     // learned factor capacity: the solve kernels keep a running maximum of the free variables any instance needed (device
     // int, read back asynchronously after every solve); later solves size the shared-memory factors by it
     int* dmaxfr = nullptr;
+    int* dncap = nullptr;       // [1 + batch]: count and list of the instances the main launch hands to the rescue launch
     int* maxfr_host = nullptr;  // pinned
     cudaEvent_t ev_maxfr = nullptr;
     bool maxfr_pending = false, maxfr_valid = false;
@@ -181,6 +182,8 @@ int sqpb200_create(int batch, int nV, int nC, int qptype, int device, const sqpb
         cudaEventCreateWithFlags(&h->ev_maxfr, cudaEventDisableTiming) == cudaSuccess) {
         cudaMemset(h->dmaxfr, 0, sizeof(int));
         *h->maxfr_host = 0;
+        if (cudaMalloc((void**)&h->dncap, (size_t)(batch + 1) * sizeof(int)) != cudaSuccess) { h->err = "allocation failed"; *out = h; return SQPB200_ERR_CUDA; }
+        cudaMemset(h->dncap, 0, (size_t)(batch + 1) * sizeof(int));
     } else { h->err = "allocation of the capacity counter failed"; *out = h; return SQPB200_ERR_CUDA; }
     if (cudaMalloc((void**)&h->dprof, 16 * sizeof(long long)) == cudaSuccess) cudaMemset(h->dprof, 0, 16 * sizeof(long long));
     else h->dprof = nullptr;
@@ -196,7 +199,7 @@ int sqpb200_destroy(sqpb200_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dAp, h->dAi, h->dArp, h->dAci, h->dAperm, h->dAsrc, h->dHp, h->dHi, h->dHsrc, h->dAval, h->dHval,
-                    h->arena, h->dstate, h->stage, h->dgpat, h->dgwork, h->dprof, h->dmaxfr};
+                    h->arena, h->dstate, h->stage, h->dgpat, h->dgwork, h->dprof, h->dmaxfr, h->dncap};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -767,6 +770,7 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
     a.wsB = h->dwsB; a.wsC = h->dwsC; a.WB = h->dWB; a.WC = h->dWC;
     a.state = h->dstate;
     a.maxfr = h->dmaxfr;
+    a.ncap = h->dncap; a.caplist = h->dncap + 1;
     a.prof = h->dprof;
     a.inst_state = inst_state;  // per-instance init/hotstart decisions (made in the kernel) replace the handle-level `mode`
     if (h->large) {
@@ -783,6 +787,7 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
         return 0;
     }
     CK(cudaEventRecord(h->ev0, h->stream));
+    if (h->cfg_main.cap < h->nV) CK(cudaMemsetAsync(h->dncap, 0, sizeof(int), h->stream));
     cudaError_t e = launch_cfg(h->cfg_main, a, h->stream);
     if (e != cudaSuccess) { h->err = std::string("qp_solve_kernel launch: ") + cudaGetErrorString(e); return SQPB200_ERR_CUDA; }
     if (h->cfg_main.cap < h->nV) {

@@ -88,6 +88,7 @@ struct QPKernelArgs {
     int oW;                             // large layout only: scratch matrix (cap x ld)
     int oP;                             // end of the persistent part of the slice (what a hot start restores)
     int nW;                             // doubles from ot1 to the end of zv (chunk buffer of the warp kernel's refactorisation)
+    int *ncap, *caplist;                // instances whose solve overflowed the factor capacity (count, list[batch]): the rescue launch's work list
     int* maxfr;                         // optional: running maximum of free variables seen by this handle (atomicMax)
     int oS;                             // start of the 16-bit index arrays (sB, FR, posFR, sC, AC, posAC)
     // pattern layout: offsets in 16-bit words from the pattern base
@@ -704,56 +705,77 @@ struct QPT {
         if (tid == 0) sPhase = ph;
         __syncthreads();
     }
-    // leader only: Cholesky factor of the nb x nb diagonal block at (i0, i0) and its inverse, both in shared memory; the factor
-    // goes back to R, the inverse to W[i0 + r][c].  Returns 0 or 1 + failing pivot (uniform).
+    // leader only: Cholesky factor of the nb x nb diagonal block at (i0, i0) and its inverse, both formed in shared memory; the
+    // factor goes back to R, the inverse to W[i0 + r][c].  Returns 0 or 1 + failing pivot (uniform).
+    // Elimination with the block in registers (thread (r0, j) owns rows r0, r0 + 8, ... of column j): per pivot the owners
+    // publish the finished (unscaled) row, one barrier, and every thread updates its own entries with a_ki a_kj / a_kk; the
+    // square roots are taken afterwards for all rows at once, so the pivot chain is one division + one barrier long.
     static __device__ __forceinline__ int diag_block(int i0, int nb) {
         QP_CTX
         double *RT = V_(RT), *W = V_(W);
-        double* D = qp_smem + LS_D;    // upper part: the block being eliminated; lower part: finished rows, transposed
+        double* D = qp_smem + LS_D;
         double* DI = qp_smem + LS_DI;
-        const int tid = threadIdx.x;
-        for (int e = tid; e < LT_NB * LT_NB; e += TEAM) {
-            const int r = e >> 6, c = e & 63;
-            D[r * LT_D_LD + c] = (r < nb && c < nb && r <= c) ? R_(i0 + r, i0 + c) : 0.0;
-            DI[r * LT_D_LD + c] = 0.0;
+        double* sc = qp_smem + LS_RED;  // [0..1]: 1 / pivot (double-buffered), [2]: failure flag, [64..127]: 1 / R_kk
+        const int tid = threadIdx.x, j = tid & 63, r0 = tid >> 6;
+        double a[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int i = r0 + 8 * q;
+            a[q] = (i < nb && j < nb && i <= j) ? R_(i0 + i, i0 + j) : 0.0;
+            DI[i * LT_D_LD + j] = 0.0;
         }
+        if (tid == 0) sc[2] = 0.0;
         __syncthreads();
-        // right-looking, one barrier per pivot: the trailing update reads row k unscaled (a_ki a_kj / a_kk) while the scaled row
-        // is written to the transposed (lower) position
         for (int k = 0; k < nb; k++) {
-            const double akk = D[k * LT_D_LD + k];
-            if (!(akk > QP_ZERO)) return 1 + i0 + k;
-            const double dd = sqrt(akk), inv = 1.0 / akk;
-            const int rem = nb - k - 1;
-            if (tid < nb - k) { const int j = k + tid; D[j * LT_D_LD + k] = (tid == 0) ? dd : D[k * LT_D_LD + j] / dd; }
-            for (int e = tid; e < rem * rem; e += TEAM) {
-                const int i = k + 1 + e / rem, j = k + 1 + e % rem;
-                if (j >= i) D[i * LT_D_LD + j] -= D[k * LT_D_LD + i] * D[k * LT_D_LD + j] * inv;
+            if ((k & 7) == r0 && j >= k && j < nb) {
+                const double v = a[k >> 3];
+                D[k * LT_D_LD + j] = v;
+                if (j == k) { if (v > QP_ZERO) sc[k & 1] = 1.0 / v; else sc[2] = (double)(1 + i0 + k); }
             }
             __syncthreads();
+            if (sc[2] != 0.0) return (int)sc[2];
+            const double inv = sc[k & 1], dkj = D[k * LT_D_LD + j] * inv;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int i = r0 + 8 * q;
+                if (i > k && i <= j && j < nb) a[q] -= D[k * LT_D_LD + i] * dkj;
+            }
         }
-        // R block = transpose of the lower part; then the inverse, column c by 8 threads (c = tid / 8), back substitution
-        // x_c = 1 / R_cc, x_r = -(sum_{l = r+1..c} R_rl x_l) / R_rr
+        __syncthreads();
+        if (tid < nb) { const double d = sqrt(D[tid * LT_D_LD + tid]); sc[64 + tid] = 1.0 / d; sc[128 + tid] = d; }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int i = r0 + 8 * q;
+            if (i < nb && j < nb && i <= j) {
+                const double v = (i == j) ? sc[128 + i] : D[i * LT_D_LD + j] * sc[64 + i];
+                D[i * LT_D_LD + j] = v;
+                R_(i0 + i, i0 + j) = v;
+            }
+        }
+        __syncthreads();
+        // inverse of the (upper triangular) factor, column c by 8 threads (c = tid / 8): x_c = 1 / R_cc,
+        // x_r = -(sum_{l = r+1..c} R_rl x_l) / R_rr; columns are independent, so only warp-level synchronisation
         {
             const int c = tid >> 3, sub = tid & 7;
-            if (c < nb && sub == 0) DI[c * LT_D_LD + c] = 1.0 / D[c * LT_D_LD + c];
+            if (c < nb && sub == 0) DI[c * LT_D_LD + c] = sc[64 + c];
             __syncwarp();
             for (int r = nb - 2; r >= 0; r--) {  // uniform trip count; columns c <= r idle
                 double sacc = 0.0;
                 if (c < nb && r < c)
-                    for (int l = r + 1 + sub; l <= c; l += 8) sacc += D[l * LT_D_LD + r] * DI[l * LT_D_LD + c];
+                    for (int l = r + 1 + sub; l <= c; l += 8) sacc += D[r * LT_D_LD + l] * DI[l * LT_D_LD + c];
                 sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
                 sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
                 sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
-                if (c < nb && r < c && sub == 0) DI[r * LT_D_LD + c] = -sacc / D[r * LT_D_LD + r];
+                if (c < nb && r < c && sub == 0) DI[r * LT_D_LD + c] = -sacc * sc[64 + r];
                 __syncwarp();
             }
         }
         __syncthreads();
-        for (int e = tid; e < LT_NB * LT_NB; e += TEAM) {
-            const int r = e >> 6, c = e & 63;
-            if (r < nb && c < nb && r <= c) R_(i0 + r, i0 + c) = D[c * LT_D_LD + r];
-            if (r < nb && c < nb) W[(size_t)(i0 + r) * ld + c] = DI[r * LT_D_LD + c];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int i = r0 + 8 * q;
+            if (i < nb && j < nb) W[(size_t)(i0 + i) * ld + j] = DI[i * LT_D_LD + j];
         }
         __syncthreads();
         return 0;
@@ -1783,6 +1805,7 @@ __device__ __forceinline__ void qp_instance_store(signed char* st, int mode, int
 // WPS = warps per SM the register allocation is capped for: 16 (<= 128 registers; measured: 20 or 24 warps lose everywhere) or
 // 32 (<= 64 registers, a few spills): 15-20 % faster on QPs small enough that shared memory lets 32 warps be resident
 // (nV <~ 20), slower on the larger ones where shared memory caps the occupancy anyway -- capi.cu picks per problem size.
+static __device__ __forceinline__ void qp_solve_one(const QPKernelArgs& A, const int b, const int team_id, const int lane);
 template <int CTA_THREADS, int WPS>
 __global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solve_kernel(const __grid_constant__ QPKernelArgs A) {
     constexpr int TEAMS = CTA_THREADS / 32;
@@ -1802,10 +1825,21 @@ __global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solv
 
     const int team_id = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (A.rescue) {
+        // rescue launch (small fixed grid): the instances the main launch listed as overflowing its factor capacity, re-solved
+        // from their pre-solve state with full-size factors.  Usually the list is empty and every warp leaves at once.
+        const int count = *A.ncap;
+        for (int k = blockIdx.x * TEAMS + team_id; k < count; k += gridDim.x * TEAMS) { qp_solve_one(A, A.caplist[k], team_id, lane); __syncwarp(); }
+        return;
+    }
     const int b = blockIdx.x * TEAMS + team_id;
     if (b >= A.batch) return;
     if (A.mask && !A.mask[b]) return;
-    if (A.rescue && A.status[b] != ST_CAPACITY) return;  // rescue launch: only instances that overflowed the factor capacity
+    qp_solve_one(A, b, team_id, lane);
+}
+
+// one QP on the calling warp (slice `team_id` of the CTA's shared memory)
+static __device__ __forceinline__ void qp_solve_one(const QPKernelArgs& A, const int b, const int team_id, const int lane) {
     const int nV = A.nV, nC = A.nC, cap = A.cap, ld = A.ld;
     double* slice = qp_smem + (size_t)team_id * A.slice_doubles;
     int* hdr = reinterpret_cast<int*>(slice);
@@ -1877,7 +1911,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solv
         }
     }
     if (status == ST_CAPACITY) {  // left to the rescue launch (full capacity), which restarts from the pre-solve state
-        if (lane == 0) { A.status[b] = ST_CAPACITY; A.iters[b] = 0; }
+        if (lane == 0) { A.status[b] = ST_CAPACITY; A.iters[b] = 0; if (A.ncap) A.caplist[atomicAdd(A.ncap, 1)] = b; }
         return;
     }
     PROF_ADD(PR_TOTAL);

@@ -105,7 +105,7 @@ __host__ __device__ inline void qp_fill_layout(QPKernelArgs& a) {
     // warp kernel: odd leading dimension (conflict-free row and column walks in shared memory); one-QP-per-CTA kernel: the
     // factors live in global memory and their rows are the source of 16-byte aligned TMA bulk copies -> multiple of 8 doubles
     a.ld = a.large ? ((a.cap + 7) & ~7) : ((a.cap % 2 == 0) ? a.cap + 1 : a.cap);
-    int o = 4;
+    int o = a.large ? 8 : 4;  // one-QP-per-CTA kernel: 8 more ints for the arguments of the operations the leader hands to its cluster
     // persistent part = the hot-start image (independent of the factor capacity): iterate, current homotopy data, matrix
     // values, working-set index lists
     a.ox = o; o += nV; a.og = o; o += nV; a.olb = o; o += nV; a.oub = o; o += nV;
@@ -705,6 +705,176 @@ struct QPT {
         if (tid == 0) sPhase = ph;
         __syncthreads();
     }
+    // ---- coalesced O(n^2) primitives of the one-QP-per-CTA kernel.  The factors are row-major in global memory: a thread
+    // that walks "its" row (the warp kernel's lane-per-row loops) makes every warp load touch 32 different lines, which at
+    // nFR ~ 10^3 turns each sweep into an L2-latency chain.  Here the fast index always runs over the lanes.
+    static __device__ __forceinline__ double team_sum(double v) {  // sum over the CTA, returned to every thread
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sRedT[threadIdx.x >> 5] = v;
+        __syncthreads();
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < TEAM / 32; k++) t += sRedT[k];
+        return t;
+    }
+    // out[j] = sgn * sum_{p < nP} M[p * ld + j] * v[p] for j0 <= j < j1 (columns over the lanes, the p range cut into 8 slices)
+    static __device__ __forceinline__ void col_sums(const double* M, int ld, int nP, int j0, int j1, const double* v, double* out, double sgn,
+                                                    int rank = 0, int cs = 1) {
+        double* red = qp_smem + LS_RED;
+        const int tid = threadIdx.x, c = tid & 63, sl = tid >> 6;
+        for (int jb = j0 + 64 * rank; jb < j1; jb += 64 * cs) {
+            const int j = jb + c;
+            double s0 = 0.0, s1 = 0.0;
+            if (j < j1) {
+                int pp = sl;
+#pragma unroll 4
+                for (; pp + 8 < nP; pp += 16) { s0 += M[(size_t)pp * ld + j] * v[pp]; s1 += M[(size_t)(pp + 8) * ld + j] * v[pp + 8]; }
+                if (pp < nP) s0 += M[(size_t)pp * ld + j] * v[pp];
+            }
+            red[sl * 64 + c] = s0 + s1;
+            __syncthreads();
+            if (tid < 64 && jb + tid < j1) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) t += red[q * 64 + tid];
+                out[jb + tid] = sgn * t;
+            }
+            __syncthreads();
+        }
+    }
+    // s_p = sum_{j0 <= j < j1} M[p * ld + j] * v[j] for p < nP, one warp per row; out[idx ? idx[p] : p] (+)= s_p
+    static __device__ __forceinline__ void row_sums(const double* M, int ld, int nP, int j0, int j1, const double* v, double* out,
+                                                    const short* idx, bool accumulate, int rank = 0, int cs = 1) {
+        const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+        for (int pr = warp + (TEAM / 32) * rank; pr < nP; pr += (TEAM / 32) * cs) {
+            const double* row = M + (size_t)pr * ld;
+            double s0 = 0.0;
+#pragma unroll 4
+            for (int j = j0 + l; j < j1; j += 32) s0 += row[j] * v[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            if (l == 0) { const int k = idx ? idx[pr] : pr; out[k] = accumulate ? out[k] + s0 : s0; }
+        }
+        __syncthreads();
+    }
+    // the rotation chain (c_j, s_j), j < cnt - 1, acting on columns (j, j + 1), applied to rows p < nP of M: per row
+    //   qa = q[0]; for j: qb = q[j+1]; q[j] = c qa - s qb; qa = s qa + c qb;  q[cnt-1] = qa
+    // Warp w owns 32-row groups; a group moves through shared memory in 32-column tiles (coalesced loads and stores, the
+    // chain runs lane-per-row out of the tile).
+    static __device__ __forceinline__ void rot_rows(double* M, int ld, int nP, int cnt, const double* cs, const double* sn, int rank = 0,
+                                                    int ncta = 1) {
+        if (cnt <= 0) return;
+        const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+        double* tile = qp_smem + (size_t)warp * (32 * 33);
+        for (int r0 = (warp + (TEAM / 32) * rank) * 32; r0 < nP; r0 += TEAM * ncta) {
+            const int nr = (nP - r0 < 32) ? nP - r0 : 32;
+            double qa = (l < nr) ? M[(size_t)(r0 + l) * ld] : 0.0;
+            for (int jt = 0; jt < cnt; jt += 32) {
+                // originals of columns jt+1 .. jt+32
+                for (int rr = 0; rr < nr; rr++) { const int j = jt + 1 + l; if (j < cnt) tile[rr * 33 + l] = M[(size_t)(r0 + rr) * ld + j]; }
+                __syncwarp();
+                if (l < nr) {
+                    const int cmax = (cnt - jt < 32) ? cnt - jt : 32;
+                    for (int c = 0; c < cmax; c++) {
+                        const int j = jt + c;
+                        if (j + 1 < cnt) {
+                            const double co = cs[j], si = sn[j], qb = tile[l * 33 + c];
+                            tile[l * 33 + c] = co * qa - si * qb;
+                            qa = si * qa + co * qb;
+                        } else tile[l * 33 + c] = qa;
+                    }
+                }
+                __syncwarp();
+                for (int rr = 0; rr < nr; rr++) { const int j = jt + l; if (j < cnt) M[(size_t)(r0 + rr) * ld + j] = tile[rr * 33 + l]; }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+    // ---- blocked substitutions with the reverse-triangular factor T (one-QP-per-CTA kernel).  In the index pair (i, k) with
+    // d_k = nFR - 1 - k, L(i, k) = T(i, d_k) is lower triangular.  Blocks of 32: the diagonal block goes to shared memory and is
+    // solved by warp 0 with shuffles (one quot() + one shuffle per unknown); the coupling with the other blocks is a
+    // warp-per-row product with coalesced loads.  The column-by-column form above needs two CTA barriers and a global-memory
+    // round trip per unknown, which at nAC ~ 500 was half of the step-direction time.
+    // T v = b: v indexed by Q column (v[d_k]); b by AC position, destroyed.
+    static __device__ __forceinline__ void solve_T_blocked(double* b, double* v) {
+        QP_CTX
+        const int nFR = hdr[0], nAC = hdr[1];
+        const double* RT = V_(RT);
+        double* Dt = qp_smem + LS_D;  // [32][33]
+        const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+        for (int i0 = 0; i0 < nAC; i0 += 32) {
+            const int nb = (nAC - i0 < 32) ? nAC - i0 : 32;
+            // left-looking: b_I -= L(I, 0:i0) v_{0:i0}; row i of the strip is contiguous: columns d_{i0-1} .. d_0 = nFR-i0 .. nFR-1
+            for (int r = warp; r < nb; r += TEAM / 32) {
+                const int i = i0 + r;
+                double s0 = 0.0;
+                for (int cc = nFR - i0 + l; cc < nFR; cc += 32) s0 += T_(i, cc) * v[cc];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                if (l == 0) b[i] -= s0;
+            }
+            for (int e = tid; e < 32 * 32; e += TEAM) {  // Dt[r][k] = L(i0 + r, i0 + k), k <= r
+                const int r = e >> 5, k = e & 31;
+                if (r < nb && k <= r) Dt[r * 33 + k] = T_(i0 + r, nFR - 1 - i0 - k);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double bl = (l < nb) ? b[i0 + l] : 0.0;
+                const double piv = (l < nb) ? Dt[l * 33 + l] : 1.0, ri = 1.0 / piv;
+                double mine = 0.0;
+                for (int k = 0; k < nb; k++) {
+                    const double lk = (l > k && l < nb) ? Dt[l * 33 + k] : 0.0;
+                    const double vk = __shfl_sync(0xffffffffu, quot(bl, piv, ri), k);
+                    if (l == k) mine = vk;
+                    bl -= lk * vk;
+                }
+                if (l < nb) v[nFR - 1 - i0 - l] = mine;
+            }
+            __syncthreads();
+        }
+    }
+    // T' u = r: r indexed by Q column (destroyed), u by AC position.
+    static __device__ __forceinline__ void solve_Tt_blocked(double* r, double* u) {
+        QP_CTX
+        const int nFR = hdr[0], nAC = hdr[1];
+        const double* RT = V_(RT);
+        double* Dt = qp_smem + LS_D;
+        double* red = qp_smem + LS_RED;  // [16][32]
+        const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+        for (int i0 = ((nAC - 1) >> 5) << 5; i0 >= 0; i0 -= 32) {
+            const int nb = (nAC - i0 < 32) ? nAC - i0 : 32, i1 = i0 + nb;
+            // r'_k -= sum_{i >= i1} L(i, k) u_i for k in the block: lanes over k (columns d_k, contiguous), warps over i
+            {
+                double s0 = 0.0;
+                if (l < nb) for (int i = i1 + warp; i < nAC; i += TEAM / 32) s0 += T_(i, nFR - 1 - i0 - l) * u[i];
+                red[warp * 32 + l] = s0;
+            }
+            for (int e = tid; e < 32 * 32; e += TEAM) {
+                const int rr = e >> 5, k = e & 31;
+                if (rr < nb && k <= rr) Dt[rr * 33 + k] = T_(i0 + rr, nFR - 1 - i0 - k);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < TEAM / 32; q++) t += red[q * 32 + l];
+                double rl = (l < nb) ? r[nFR - 1 - i0 - l] - t : 0.0;
+                const double piv = (l < nb) ? Dt[l * 33 + l] : 1.0, ri = 1.0 / piv;
+                double mine = 0.0;
+                for (int k = nb - 1; k >= 0; k--) {
+                    const double lk = (l < k) ? Dt[k * 33 + l] : 0.0;
+                    const double uk = __shfl_sync(0xffffffffu, quot(rl, piv, ri), k);
+                    if (l == k) mine = uk;
+                    rl -= lk * uk;
+                }
+                if (l < nb) u[i0 + l] = mine;
+            }
+            __syncthreads();
+        }
+    }
     // leader only: Cholesky factor of the nb x nb diagonal block at (i0, i0) and its inverse, both formed in shared memory; the
     // factor goes back to R, the inverse to W[i0 + r][c].  Returns 0 or 1 + failing pivot (uniform).
     // Elimination with the block in registers (thread (r0, j) owns rows r0, r0 + 8, ... of column j): per pivot the owners
@@ -854,6 +1024,42 @@ struct QPT {
         PROF_ADD(PR_REFAC_CHOL);
         return fail;
     }
+    // ---- operations the leader shares with its helper CTAs: arguments go through the slice header (ints 4..15), offsets are
+    // in doubles from the slice base.  Worth two cluster barriers only when the operand is large.
+    enum { OP_REFAC = 1, OP_EXIT = 2, OP_COLSUMS = 3, OP_ROWSUMS = 4, OP_ROTROWS = 5 };
+    static constexpr int DIST_MIN_ELEMS = 1 << 17;  // below ~1 MB of factor data the leader works alone
+    static __device__ __forceinline__ void run_op(int cmd, int rank, int cs) {
+        QP_CTX
+        volatile int* vh = hdr;
+        const int oM = vh[8], nP = vh[9], i0 = vh[10], i1 = vh[11], oA = vh[12], oB = vh[13], flag = vh[14];
+        if (cmd == OP_COLSUMS) col_sums(slice + oM, ld, nP, i0, i1, slice + oA, slice + oB, flag ? -1.0 : 1.0, rank, cs);
+        else if (cmd == OP_ROWSUMS) row_sums(slice + oM, ld, nP, i0, i1, slice + oA, slice + oB, (flag & 1) ? FR_ : nullptr, (flag & 2) != 0, rank, cs);
+        else if (cmd == OP_ROTROWS) rot_rows(slice + oM, ld, nP, i0, slice + oA, slice + oB, rank, cs);
+    }
+    static __device__ __forceinline__ void dist_op(int cmd, int oM, int nP, int i0, int i1, int oA, int oB, int flag) {
+        QP_CTX
+        if (lane == 0) { hdr[4] = cmd; hdr[8] = oM; hdr[9] = nP; hdr[10] = i0; hdr[11] = i1; hdr[12] = oA; hdr[13] = oB; hdr[14] = flag; }
+        __syncthreads();
+        large_sync();
+        run_op(cmd, 0, sClusterSize);
+        large_sync();
+    }
+    // the three primitives with automatic choice between the leader alone and the whole cluster
+    static __device__ __forceinline__ void col_sums_auto(int oM, int nP, int j0, int j1, int oV, int oOut, bool negate) {
+        QP_CTX
+        if (sClusterSize > 1 && (long long)nP * (j1 - j0) >= DIST_MIN_ELEMS) dist_op(OP_COLSUMS, oM, nP, j0, j1, oV, oOut, negate ? 1 : 0);
+        else col_sums(slice + oM, ld, nP, j0, j1, slice + oV, slice + oOut, negate ? -1.0 : 1.0);
+    }
+    static __device__ __forceinline__ void row_sums_auto(int oM, int nP, int j0, int j1, int oV, int oOut, bool via_FR, bool accumulate) {
+        QP_CTX
+        if (sClusterSize > 1 && (long long)nP * (j1 - j0) >= DIST_MIN_ELEMS) dist_op(OP_ROWSUMS, oM, nP, j0, j1, oV, oOut, (via_FR ? 1 : 0) | (accumulate ? 2 : 0));
+        else row_sums(slice + oM, ld, nP, j0, j1, slice + oV, slice + oOut, via_FR ? FR_ : nullptr, accumulate);
+    }
+    static __device__ __forceinline__ void rot_rows_auto(int oM, int nP, int cnt, int oC, int oS_) {
+        QP_CTX
+        if (sClusterSize > 1 && (long long)nP * cnt >= DIST_MIN_ELEMS) dist_op(OP_ROTROWS, oM, nP, cnt, 0, oC, oS_, 0);
+        else rot_rows(slice + oM, ld, nP, cnt, slice + oC, slice + oS_);
+    }
     static __device__ QP_FN int recompute_R_blocked() {
         QP_CTX
         if (lane == 0) hdr[4] = 1;  // command: refactorise
@@ -867,8 +1073,10 @@ struct QPT {
         volatile int* vh = hdr;
         for (;;) {
             large_sync();
-            if (vh[4] == 2) return;  // command: exit
-            refac_body(rank, cs);
+            const int cmd = vh[4];
+            if (cmd == OP_EXIT) return;
+            if (cmd == OP_REFAC) refac_body(rank, cs);
+            else { run_op(cmd, rank, cs); large_sync(); }
         }
     }
     // R' u = z (n unknowns, in place) with the block inverses; col >= 0: also R(k, col) = u_k
@@ -923,13 +1131,22 @@ struct QPT {
         const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
         for (int i0 = ((n - 1) >> 6) << 6; i0 >= 0; i0 -= LT_NB) {
             const int nb = (n - i0 < LT_NB) ? n - i0 : LT_NB, i1 = i0 + nb;
-            for (int r = warp; r < nb; r += TEAM / 32) {
-                double s = 0.0;
-#pragma unroll 4
-                for (int k = i1 + l; k < n; k += 32) s += R_(i0 + r, k) * z[k];
+            {   // the warp's four rows (warp, warp + 16, ...) together: four independent load streams per lane
+                double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+                for (int k = i1 + l; k < n; k += 32) {
+                    const double zk = z[k];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (l == 0) tv[r] = z[i0 + r] - s;
+                    for (int q = 0; q < 4; q++) { const int r = warp + (TEAM / 32) * q; if (r < nb) s4[q] += R_(i0 + r, k) * zk; }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    double sq = s4[q];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    const int r = warp + (TEAM / 32) * q;
+                    if (l == 0 && r < nb) tv[r] = z[i0 + r] - sq;
+                }
             }
             __syncthreads();
             for (int r = warp; r < nb; r += TEAM / 32) {
@@ -973,12 +1190,22 @@ struct QPT {
         const double *Q = V_(Q), *t2 = V_(t2);
         const short* FR = FR_;
         proj_column(b);
+#ifndef QP_EXACT
+        if constexpr (TEAM > 32) {
+            double* tmp = V_(a);  // dead between two homotopy steps
+            for (int p = lane; p < nFR; p += TEAM) tmp[p] = t2[FR[p]];
+            SYNC();
+            col_sums_auto(sA.oQ, nFR, 0, b + 1, sA.oa, sA.ow, false);
+        } else
+#endif
+        {
         QP_U1 for (int a_ = lane; a_ <= b; a_ += TEAM) {
             double s = 0.0;
             DOT_UNROLL for (int p = 0; p < nFR; p++) s += Q[p * ld + a_] * t2[FR[p]];
             w[a_] = s;
         }
         SYNC();
+        }
         // r = R'^{-1} w[0..b): forward substitution, column oriented
         if constexpr (TEAM > 32) fwd_solve_R_blocked(w, b, b);
         else {
@@ -994,7 +1221,16 @@ struct QPT {
         }
         }
         double rho2 = w[b];
+#ifndef QP_EXACT
+        if constexpr (TEAM > 32) {
+            double part = 0.0;
+            for (int k = lane; k < b; k += TEAM) part += R_(k, b) * R_(k, b);
+            rho2 -= team_sum(part);
+        } else
+#endif
+        {
         DOT_UNROLL for (int k = 0; k < b; k++) rho2 -= R_(k, b) * R_(k, b);
+        }
         int ok = check_curvature ? (rho2 > QP_EPS_FLIP) : (rho2 > QP_ZERO);
         SYNC();  // every lane has read w[b] / R(.,b) before a caller may overwrite them (uniform decision)
         if (!ok) return 0;
@@ -1016,6 +1252,17 @@ struct QPT {
         const short* FR = FR_;
         QP_U1 for (int p = lane; p < nFR; p += TEAM) a[p] = A_entry(pat, Av, c, FR[p]);
         SYNC();
+#ifndef QP_EXACT
+        if constexpr (TEAM > 32) {
+            col_sums_auto(sA.oQ, nFR, 0, nFR, sA.oa, sA.ow, false);
+            double s2p = 0.0, z2p = 0.0;
+            for (int p = lane; p < nFR; p += TEAM) s2p += a[p] * a[p];
+            for (int j = lane; j < nZ; j += TEAM) z2p += w[j] * w[j];
+            a2 = team_sum(s2p); wz2 = team_sum(z2p);
+            SYNC();
+            return;
+        }
+#endif
         QP_U1 for (int j = lane; j < nFR; j += TEAM) {
             double s = 0.0;
             DOT_UNROLL for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * a[p];
@@ -1062,6 +1309,11 @@ struct QPT {
         double *Q = V_(Q), *RT = V_(RT);
         const double *t2 = V_(t2), *t3 = V_(t3), *w = V_(w);
         double r = rotation_chain(nZ);
+#ifndef QP_EXACT
+        if constexpr (TEAM > 32) rot_rows_auto(sA.oQ, nFR, nZ, sA.ot2, sA.ot3);
+        else
+#endif
+        {
         QP_U1 for (int p = lane; p < nFR; p += TEAM) {
             double* q = Q + p * ld;
             double qa = q[0];
@@ -1071,6 +1323,7 @@ struct QPT {
                 qa = sn * qa + cs * qb;
             }
             if (nZ > 0) q[nZ - 1] = qa;
+        }
         }
         QP_U1 for (int j = lane; j < nFR; j += TEAM) T_(nAC, j) = (j > nZ - 1) ? w[j] : ((j == nZ - 1) ? r : 0.0);
         if (lane == 0) { AC_[nAC] = (short)c; posAC_[c] = (short)nAC; sC_[c] = (short)status; hdr[1] = nAC + 1; }
@@ -1118,6 +1371,15 @@ struct QPT {
         const double* Q = V_(Q);
         QP_U1 for (int j = lane; j < nFR; j += TEAM) w[j] = Q[p * ld + j];
         SYNC();
+#ifndef QP_EXACT
+        if constexpr (TEAM > 32) {
+            double z2p = 0.0;
+            for (int j = lane; j < nZ; j += TEAM) z2p += w[j] * w[j];
+            const double z2s = team_sum(z2p);
+            SYNC();
+            return z2s;
+        }
+#endif
         double z2 = 0.0;
         DOT_UNROLL for (int j = 0; j < nZ; j++) z2 += w[j] * w[j];
         SYNC();
@@ -1131,6 +1393,11 @@ struct QPT {
         short *FR = FR_, *posFR = posFR_;
         const int p = posFR[v];
         rotation_chain(nFR);
+#ifndef QP_EXACT
+        if constexpr (TEAM > 32) rot_rows_auto(sA.oQ, nFR, nFR, sA.ot2, sA.ot3);
+        else
+#endif
+        {
         QP_U1 for (int pp = lane; pp < nFR; pp += TEAM) {
             double* q = Q + pp * ld;
             double qa = q[0];
@@ -1140,6 +1407,7 @@ struct QPT {
                 qa = sn * qa + cs * qb;
             }
             q[nFR - 1] = qa;
+        }
         }
         // T rows: row i is touched by rotations j >= nFR-2-i (and j >= nZ-1)
         QP_U1 for (int i = lane; i < nAC; i += TEAM) {
@@ -1210,6 +1478,9 @@ struct QPT {
         QP_CTX
         const int nFR = hdr[0], nAC = hdr[1];
         const double* RT = V_(RT);
+#ifndef QP_EXACT
+        if constexpr (TEAM > 32) { solve_T_blocked(b, v); return; }
+#endif
         if (TEAM == 32 && nAC <= 32) {
             // whole right-hand side in registers (lane k holds b_k and its pivot): the substitution chain is one shuffle and
             // the three operations of quot() per unknown, no barrier and no shared-memory round trip.  Same operations on
@@ -1244,6 +1515,9 @@ struct QPT {
         QP_CTX
         const int nFR = hdr[0], nAC = hdr[1];
         const double* RT = V_(RT);
+#ifndef QP_EXACT
+        if constexpr (TEAM > 32) { solve_Tt_blocked(r, u); return; }
+#endif
         if (TEAM == 32 && nAC <= 32) {  // register form, see solve_T
             const bool act = lane < nAC;
             double rk = act ? r[nFR - 1 - lane] : 0.0;
@@ -1286,21 +1560,36 @@ struct QPT {
             QP_U1 for (int i = lane; i < nAC; i += TEAM) t3[i] = dbAC[i] - t2[AC[i]];
             SYNC();
             solve_T(t3, yv);
+#ifndef QP_EXACT
+            if constexpr (TEAM > 32) row_sums_auto(sA.oQ, nFR, nZ, nFR, sA.oyv, sA.odx, true, false);
+            else
+#endif
+            {
             QP_U1 for (int p = lane; p < nFR; p += TEAM) {
                 double s = 0.0;
                 DOT_UNROLL for (int j = nZ; j < nFR; j++) s += Q[p * ld + j] * yv[j];
                 dx[FR[p]] = s;
             }
             SYNC();
+            }
         }
         if (nZ > 0) {
             mulH(dx, t1);
+#ifndef QP_EXACT
+            if constexpr (TEAM > 32) {
+                for (int p = lane; p < nFR; p += TEAM) { const int v = FR[p]; yv[p] = t1[v] + dgvec[v]; }  // yv is dead here
+                SYNC();
+                col_sums_auto(sA.oQ, nFR, 0, nZ, sA.oyv, sA.ozv, true);
+            } else
+#endif
+            {
             QP_U1 for (int j = lane; j < nZ; j += TEAM) {
                 double s = 0.0;
                 DOT_UNROLL for (int p = 0; p < nFR; p++) { int v = FR[p]; s += Q[p * ld + j] * (t1[v] + dgvec[v]); }
                 zv[j] = -s;
             }
             SYNC();
+            }
             // R' u = rhs (forward), R z = u (backward); column oriented
             PROF2_T0
             if constexpr (TEAM > 32) {
@@ -1327,24 +1616,39 @@ struct QPT {
                 }
                 PROF2_ADD(PR_RSOLVE);
             }
+#ifndef QP_EXACT
+            if constexpr (TEAM > 32) row_sums_auto(sA.oQ, nFR, 0, nZ, sA.ozv, sA.odx, true, true);
+            else
+#endif
+            {
             QP_U1 for (int p = lane; p < nFR; p += TEAM) {
                 double s = 0.0;
                 DOT_UNROLL for (int j = 0; j < nZ; j++) s += Q[p * ld + j] * zv[j];
                 dx[FR[p]] += s;
             }
             SYNC();
+            }
         }
         mulH(dx, t1);
         QP_U1 for (int i = lane; i < nV; i += TEAM) t1[i] += dgvec[i];
         QP_U1 for (int i = lane; i < nT; i += TEAM) dy[i] = 0.0;
         SYNC();
         if (nAC > 0) {
+#ifndef QP_EXACT
+            if constexpr (TEAM > 32) {
+                for (int p = lane; p < nFR; p += TEAM) zv[p] = t1[FR[p]];  // zv is dead here
+                SYNC();
+                col_sums_auto(sA.oQ, nFR, nZ, nFR, sA.ozv, sA.oyv, false);
+            } else
+#endif
+            {
             QP_U1 for (int j = nZ + lane; j < nFR; j += TEAM) {
                 double s = 0.0;
                 DOT_UNROLL for (int p = 0; p < nFR; p++) s += Q[p * ld + j] * t1[FR[p]];
                 yv[j] = s;
             }
             SYNC();
+            }
             solve_Tt(yv, t3);
             QP_U1 for (int i = lane; i < nAC; i += TEAM) dy[nV + AC[i]] = t3[i];
             SYNC();
@@ -2018,7 +2322,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) qp_solve_large_kernel(const __
     S::epilogue(b, status, total_iters);
     PROF_ADD(PR_EPILOGUE);
 #ifndef QP_EXACT
-    if (tid == 0) hdr[4] = 2;  // command: exit
+    if (tid == 0) hdr[4] = S::OP_EXIT;
     __syncthreads();
     S::large_sync();
 #endif

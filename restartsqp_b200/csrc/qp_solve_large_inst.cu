@@ -9,14 +9,15 @@
 #endif
 
 namespace sqpb200 {
-// CTAs per QP: the largest power of two <= 8 (portable cluster size) that keeps batch * cluster <= SM count, so that a batch
-// smaller than the GPU still fills it.  SQPB200_CLUSTER overrides (1, 2, 4, 8, 16; 16 needs the non-portable opt-in).
+// CTAs per QP: the largest power of two <= 16 that keeps batch * cluster <= SM count, so that a batch smaller than the GPU still
+// fills it (16 is a non-portable cluster size: opt-in attribute, and a fall-back to 8 if the launch is refused).
+// SQPB200_CLUSTER overrides (1, 2, 4, 8, 16).
 static int cluster_for_batch(int batch) {
     if (const char* e = getenv("SQPB200_CLUSTER")) { int v = atoi(e); if (v >= 1 && v <= 16 && (v & (v - 1)) == 0) return v; }
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int cs = 1;
-    while (cs < 8 && (long long)batch * cs * 2 <= sms) cs *= 2;
+    while (cs < 16 && (long long)batch * cs * 2 <= sms) cs *= 2;  // 16 = non-portable cluster size (opt-in below), batch <= 9
     return cs;
 }
 
@@ -25,7 +26,7 @@ cudaError_t launch_qp_solve_large(const QPKernelArgs& a, cudaStream_t stream) {
     qp_solve_large_kernel<QP_CTA><<<a.batch, QP_CTA, 0, stream>>>(a);
     return cudaGetLastError();
 #else
-    const int cs = cluster_for_batch(a.batch);
+    int cs = cluster_for_batch(a.batch);
     const size_t smem = (size_t)QPT<QP_CTA>::LS_TOTAL * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(qp_solve_large_kernel<QP_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -42,7 +43,15 @@ cudaError_t launch_qp_solve_large(const QPKernelArgs& a, cudaStream_t stream) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, qp_solve_large_kernel<QP_CTA>, a);
+    e = cudaLaunchKernelEx(&cfg, qp_solve_large_kernel<QP_CTA>, a);
+    if (e != cudaSuccess && cs > 8) {  // non-portable size refused on this device / partition: portable maximum
+        (void)cudaGetLastError();
+        cs = 8;
+        cfg.gridDim = dim3((unsigned)a.batch * cs);
+        attr[0].val.clusterDim.x = cs;
+        e = cudaLaunchKernelEx(&cfg, qp_solve_large_kernel<QP_CTA>, a);
+    }
+    return e;
 #endif
 }
 int qp_solve_large_threads() { return QP_CTA; }

@@ -21,6 +21,8 @@
 #ifndef SQPB200_H
 #define SQPB200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -152,6 +154,17 @@ int sqpb200_qphandler_g(sqpb200_handle h, int n, int m, const double* grad, cons
  * (host, may be NULL = all) selects the instances to solve. */
 int sqpb200_solve(sqpb200_handle h, int mode, int maxiter, const unsigned char* active_mask);
 
+/* ---- one call per solve for host-resident data (the end-to-end path of a host driver that keeps a pinned mirror of the handle's
+ * data; replaces the per-entry setters + optimizeQP + getters of src/qpOASESInterface.cpp:137-224, 290-357, 361-484 for a whole
+ * batch).  sqpb200_io_layout gives the layout of the handle's two contiguous blocks: in_off5 = byte offsets of g, lb, ub, lbA,
+ * ubA ([batch][len] each) inside the input block of in_bytes bytes; out_off6 = byte offsets of x, y, obj, kkt[5], status (int32),
+ * iters (int32) inside the result block of out_bytes bytes.  sqpb200_solve_host queues: one host-to-device copy of the input
+ * block (NULL: unchanged), one each of the CSC-ordered A / H values [batch][nnz] (NULL: unchanged; raises Update_A / Update_H),
+ * the solve, and one device-to-host copy of the result block (NULL: skipped).  Nothing is waited for: sqpb200_synchronize. */
+int sqpb200_io_layout(sqpb200_handle h, size_t* in_off5, size_t* in_bytes, size_t* out_off6, size_t* out_bytes);
+int sqpb200_solve_host(sqpb200_handle h, int mode, int maxiter, const void* in_block, const double* Aval_csc,
+                       const double* Hval_csc, void* out_block);
+
 /* ---- results (src/qpOASESInterface.cpp:221-222, 290-357).  Any pointer may be NULL.
  * x[batch][nV]; y[batch][nV+nC] (bound multipliers first); obj[batch]; status[batch] (Exitflag);
  * iters[batch] (working-set changes of the last solve, what the reference adds to Stats::qp_iter). */
@@ -260,6 +273,14 @@ typedef struct {
  * penalty loop, [4] accepted steps, [5] rejected steps entering the second-order correction); reading them synchronises the
  * stream. */
 int sqpb200_sqp_phase(const sqpb200_sqp_state* st, int phase, int* counters_host, void* stream);
+/* The whole of Algorithm::Optimize (src/Algorithm.cpp:55-168) for the batch: phases, QP data updates (setupQP :645-697), QP / LP
+ * solves (update_penalty_parameter :886-1028), NLP evaluations and, if requested, the second-order correction (:1140-1211),
+ * sequenced from C++ on `stream` (which must be the stream of both handles).  The caller has set the structures of both handles
+ * and evaluated f, c, grad, jac, hess at the start point; *first (in/out) is 1 before the first outer iteration; f_tmp[B] and
+ * c_tmp[B][m] receive the function values of the derivative evaluation (unused by the algorithm).  refresh_ubA: 1 = update_bounds
+ * refreshes both constraint sides (mode 3 of sqpb200_qphandler_bounds), 0 = the reference's stale-ubA behaviour (mode 1). */
+int sqpb200_sqp_optimize(sqpb200_sqp_state* st, sqpb200_handle qp, sqpb200_handle lp, sqpb200_nlp nlp, int second_order_correction,
+                         int refresh_ubA, int* first, double* f_tmp, double* c_tmp, long long* launches, void* stream);
 /* sqpb200_solve with the instance mask in device memory */
 int sqpb200_solve_device_mask(sqpb200_handle h, int mode, int maxiter, const unsigned char* device_mask);
 /* The same with the init / hotstart decision (src/qpOASESInterface.cpp:141-211, 817-833) made PER INSTANCE inside the kernel, as the

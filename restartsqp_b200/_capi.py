@@ -26,10 +26,10 @@ EXPORTS = [
     "sqpb200_set_vectors", "sqpb200_get_vectors", "sqpb200_qphandler_bounds", "sqpb200_qphandler_g",
     "sqpb200_solve", "sqpb200_get_solution", "sqpb200_get_working_set", "sqpb200_kkt_residuals",
     "sqpb200_kkt_residuals_recompute", "sqpb200_spmv", "sqpb200_assemble_csc_batched", "sqpb200_launch_count",
-    "sqpb200_solve_config", "sqpb200_last_solve_ms", "sqpb200_get_profile",
+    "sqpb200_solve_config", "sqpb200_last_solve_ms", "sqpb200_get_profile", "sqpb200_io_layout", "sqpb200_solve_host",
     "sqpb200_nlp_compile", "sqpb200_nlp_cubin_size", "sqpb200_nlp_load", "sqpb200_nlp_eval", "sqpb200_nlp_destroy",
     "sqpb200_nlp_launch_count", "sqpb200_nlp_last_error",
-    "sqpb200_sqp_phase", "sqpb200_solve_device_mask", "sqpb200_device_buffers", "sqpb200_solve_per_instance",
+    "sqpb200_sqp_phase", "sqpb200_sqp_optimize", "sqpb200_solve_device_mask", "sqpb200_device_buffers", "sqpb200_solve_per_instance",
 ]
 
 
@@ -56,6 +56,10 @@ def lib():
         L.sqpb200_launch_count.restype = C.c_longlong
         L.sqpb200_launch_count.argtypes = [C.c_void_p]
         L.sqpb200_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.sqpb200_io_layout.argtypes = [C.c_void_p] * 5
+        L.sqpb200_sqp_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+        L.sqpb200_solve_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sqpb200_last_solve_ms.restype = C.c_float
         L.sqpb200_last_solve_ms.argtypes = [C.c_void_p]
         L.sqpb200_nlp_last_error.restype = C.c_char_p

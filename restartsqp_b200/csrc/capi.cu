@@ -50,6 +50,7 @@ struct sqpb200_handle_s {
     signed char *dwsB = nullptr, *dwsC = nullptr;
     unsigned char* dmask = nullptr;
     void* arena = nullptr;  // one allocation behind dg .. dmask
+    size_t in_off[5] = {0, 0, 0, 0, 0}, in_bytes = 0, out_base = 0, out_off[6] = {0, 0, 0, 0, 0, 0}, out_bytes = 0;  // sqpb200_io_layout
     // hot-start state
     double* dstate = nullptr;
     int slice_doubles = 0, ld = 0;
@@ -170,6 +171,11 @@ int sqpb200_create(int batch, int nV, int nC, int qptype, int device, const sqpb
         else {
             cudaMemsetAsync(h->arena, 0, off, h->stream);
             char* a = (char*)h->arena;
+            // the vectors (g .. ubA) and the results (x .. iters) are two contiguous blocks: one copy each way per solve
+            h->in_off[0] = o_g; h->in_off[1] = o_lb; h->in_off[2] = o_ub; h->in_off[3] = o_lbA; h->in_off[4] = o_ubA; h->in_bytes = o_x;
+            h->out_base = o_x;
+            h->out_off[0] = 0; h->out_off[1] = o_y - o_x; h->out_off[2] = o_obj - o_x; h->out_off[3] = o_kkt - o_x; h->out_off[4] = o_st - o_x;
+            h->out_off[5] = o_it - o_x; h->out_bytes = o_WB - o_x;
             h->dg = (double*)(a + o_g); h->dlb = (double*)(a + o_lb); h->dub = (double*)(a + o_ub); h->dlbA = (double*)(a + o_lbA); h->dubA = (double*)(a + o_ubA);
             h->dx = (double*)(a + o_x); h->dy = (double*)(a + o_y); h->dobj = (double*)(a + o_obj); h->dkkt = (double*)(a + o_kkt);
             h->dstatus = (int*)(a + o_st); h->diters = (int*)(a + o_it); h->dWB = (int*)(a + o_WB); h->dWC = (int*)(a + o_WC);
@@ -812,6 +818,39 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
     // reset_flags(): src/qpOASESInterface.cpp:488-496
     h->upd_A = h->upd_H = h->upd_g = h->upd_bounds = false;
     h->first_solved = true;
+    return 0;
+}
+
+int sqpb200_io_layout(sqpb200_handle h, size_t* in_off5, size_t* in_bytes, size_t* out_off6, size_t* out_bytes) {
+    if (!h) return SQPB200_ERR_INVALID;
+    if (in_off5) for (int i = 0; i < 5; i++) in_off5[i] = h->in_off[i];
+    if (in_bytes) *in_bytes = h->in_bytes;
+    if (out_off6) for (int i = 0; i < 6; i++) out_off6[i] = h->out_off[i];
+    if (out_bytes) *out_bytes = h->out_bytes;
+    return 0;
+}
+
+int sqpb200_solve_host(sqpb200_handle h, int mode, int maxiter, const void* in_block, const double* Aval_csc, const double* Hval_csc,
+                       void* out_block) {
+    if (!h) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (in_block) {
+        CK(cudaMemcpyAsync(h->arena, in_block, h->in_bytes, cudaMemcpyHostToDevice, h->stream));
+        if (h->first_solved) { h->upd_g = true; h->upd_bounds = true; }
+    }
+    if (Aval_csc) {
+        if (!h->A_set) { h->err = "structure not set"; return SQPB200_ERR_STATE; }
+        if (h->zA > 0) CK(cudaMemcpyAsync(h->dAval, Aval_csc, (size_t)h->batch * h->zA * 8, cudaMemcpyHostToDevice, h->stream));
+        if (h->first_solved) h->upd_A = true;
+    }
+    if (Hval_csc) {
+        if (!h->H_set) { h->err = "structure not set"; return SQPB200_ERR_STATE; }
+        if (h->zH > 0) CK(cudaMemcpyAsync(h->dHval, Hval_csc, (size_t)h->batch * h->zH * 8, cudaMemcpyHostToDevice, h->stream));
+        if (h->first_solved) h->upd_H = true;
+    }
+    int rc = solve_impl(h, mode, maxiter, nullptr, false, nullptr);
+    if (rc) return rc;
+    if (out_block) CK(cudaMemcpyAsync(out_block, (char*)h->arena + h->out_base, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
     return 0;
 }
 

@@ -299,7 +299,9 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
             S.infea_trial[b] = infea_t;
             const double P1_x = S.f_k[b] + S.rho[b] * S.infea[b];
             const double P1_t = S.f_trial[b] + S.rho[b] * infea_t;
-            const double ared = P1_x - P1_t, pred = S.rho[b] * S.infea[b] - S.qp_obj_soc[b];
+            // pred_reduction_ = rho * infea - get_obj_QP(): the raw objective of the SOC QP just solved (src/Algorithm.cpp:728);
+            // qp_obj_soc mirrors the reference's qp_obj_ bookkeeping (:1197), which no test reads
+            const double ared = P1_x - P1_t, pred = S.rho[b] * S.infea[b] - S.qp_obj[b];
             S.actual_red[b] = ared; S.pred_red[b] = pred;
             if (ared >= S.eta_s * pred && ared >= -S.tol) {
                 S.acc[b] = 1;
@@ -342,5 +344,110 @@ int sqpb200_sqp_phase(const sqpb200_sqp_state* st, int phase, int* counters_host
         if (cudaMemcpyAsync(counters_host, st->counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return SQPB200_ERR_CUDA;
         if (cudaStreamSynchronize(stream) != cudaSuccess) return SQPB200_ERR_CUDA;
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Algorithm::Optimize (src/Algorithm.cpp:55-168) for the whole batch, sequenced from C++: the launch sequence of
+// restartsqp_b200/sqp_device.py without an interpreter between the launches (at 10^4 instances the device work of an outer
+// iteration is a few tens of microseconds, so the host side is what is timed).  The caller has set the structures of both
+// handles (sqpb200_set_structure_A / _H) and evaluated the start point; `stream` must be the stream of both handles.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct OuterLoop {
+    sqpb200_sqp_state* S;
+    sqpb200_handle qp, lp;
+    sqpb200_nlp nlp;
+    cudaStream_t stream;
+    int bounds_update_mode;
+    int cnt[8];
+    long long launches;
+    int rc;
+    bool ph(int phase, bool read = false) {
+        rc = sqpb200_sqp_phase(S, phase, read ? cnt : nullptr, stream);
+        launches++;
+        return rc == 0;
+    }
+    bool solve(sqpb200_handle h, int type, const unsigned char* mask, signed char* inst) {
+        rc = inst ? sqpb200_solve_per_instance(h, type, 0, mask, inst) : sqpb200_solve_device_mask(h, type, 0, mask);
+        return rc == 0;
+    }
+    bool bounds(sqpb200_handle h, int mode, const double* xk, const double* ck) {
+        rc = sqpb200_qphandler_bounds(h, mode, S->n, S->m, S->delta, S->x_l, S->x_u, xk, S->c_l, S->c_u, ck, SQPB200_LOC_DEVICE);
+        return rc == 0;
+    }
+    bool grad(sqpb200_handle h, const double* g, const double* rho) {
+        rc = sqpb200_qphandler_g(h, S->n, S->m, g, rho, SQPB200_LOC_DEVICE);
+        return rc == 0;
+    }
+    // an empty Jacobian (m = 0) still raises Update_A like the reference's setter; the pointer is then never dereferenced
+    bool valsA(sqpb200_handle h) { rc = sqpb200_set_values_A(h, S->zJ > 0 ? S->jac : S->x_k, SQPB200_LOC_DEVICE, 0); return rc == 0; }
+    bool valsH(sqpb200_handle h) { rc = S->zH > 0 ? sqpb200_set_values_H(h, S->hess, SQPB200_LOC_DEVICE, 0) : 0; return rc == 0; }
+    // setupQP, src/Algorithm.cpp:645-697
+    bool setupQP(int bits, int* first) {
+        if (*first) {
+            if (!valsA(qp) || !valsH(qp) || !bounds(qp, 0, S->x_k, S->c_k) || !grad(qp, S->grad, S->rho)) return false;
+            *first = 0;
+            S->clear_flags = 1;
+            return true;
+        }
+        if ((bits & 1) && !valsA(qp)) return false;
+        if ((bits & 2) && !valsH(qp)) return false;
+        if (bits & 4) { if (!bounds(qp, bounds_update_mode, S->x_k, S->c_k)) return false; }
+        else if (bits & 8) { if (!bounds(qp, 2, S->x_k, nullptr)) return false; }
+        if ((bits & 16) && !grad(qp, nullptr, S->rho)) return false;
+        if ((bits & 32) && !grad(qp, S->grad, nullptr)) return false;
+        return true;
+    }
+    // update_penalty_parameter, src/Algorithm.cpp:886-1028
+    bool penalty() {
+        if (!bounds(lp, 0, S->x_k, S->c_k) || !grad(lp, nullptr, S->rho) || !valsA(lp)) return false;  // setupLP :700-704
+        if (!solve(lp, SQPB200_LP, S->need, S->lp_inst) || !ph(SQPB200_PH_LP_AFTER)) return false;
+        for (;;) {
+            if (!ph(SQPB200_PH_PEN_CHECK, true)) return false;
+            if (cnt[3] == 0) break;
+            if (!grad(qp, nullptr, S->rho_trial) || !solve(qp, SQPB200_QP, S->go, S->qp_inst) || !ph(SQPB200_PH_PEN_AFTER)) return false;
+        }
+        return ph(SQPB200_PH_PEN_FINAL);
+    }
+    // second_order_correction, src/Algorithm.cpp:1140-1211
+    bool soc() {
+        if (!ph(SQPB200_PH_SOC_PREP, true)) return false;
+        if (cnt[5] == 0) return true;
+        if (!grad(qp, S->soc_g, nullptr) || !bounds(qp, bounds_update_mode, S->soc_x, S->soc_c)) return false;
+        if (!solve(qp, SQPB200_QP, S->rej, S->qp_inst) || !ph(SQPB200_PH_SOC_AFTER)) return false;
+        rc = sqpb200_nlp_eval(nlp, 0, S->B, S->x_trial, nullptr, S->f_trial, S->c_trial, nullptr, nullptr, nullptr, SQPB200_LOC_DEVICE, stream);
+        if (rc) return false;
+        launches++;
+        if (!ph(SQPB200_PH_SOC_RATIO)) return false;
+        return grad(qp, S->grad, nullptr) && bounds(qp, bounds_update_mode, S->x_k, S->c_k);
+    }
+};
+}  // namespace
+
+int sqpb200_sqp_optimize(sqpb200_sqp_state* st, sqpb200_handle qp, sqpb200_handle lp, sqpb200_nlp nlp, int second_order_correction,
+                         int refresh_ubA, int* first, double* f_tmp, double* c_tmp, long long* launches, void* stream) {
+    if (!st || !qp || !lp || !nlp || !first || st->B <= 0) return SQPB200_ERR_INVALID;
+    OuterLoop L{st, qp, lp, nlp, (cudaStream_t)stream, refresh_ubA ? 3 : 1, {0, 0, 0, 0, 0, 0, 0, 0}, 0, 0};
+    for (;;) {
+        if (!L.ph(SQPB200_PH_FLAGS, true)) return L.rc;
+        if (L.cnt[0] == 0) break;
+        if (!L.setupQP(L.cnt[1], first)) return L.rc;
+        if (!L.solve(qp, SQPB200_QP, st->active, st->qp_inst)) return L.rc;
+        if (!L.ph(SQPB200_PH_AFTER_QP, true)) return L.rc;
+        if (L.cnt[2] > 0 && !L.penalty()) return L.rc;
+        if (!L.ph(SQPB200_PH_TRIAL)) return L.rc;
+        // get_trial_point_info :414-429
+        L.rc = sqpb200_nlp_eval(nlp, 0, st->B, st->x_trial, nullptr, st->f_trial, st->c_trial, nullptr, nullptr, nullptr, SQPB200_LOC_DEVICE, stream);
+        if (L.rc) return L.rc;
+        if (!L.ph(SQPB200_PH_RATIO)) return L.rc;
+        if (second_order_correction && !L.soc()) return L.rc;
+        L.rc = sqpb200_nlp_eval(nlp, 1, st->B, st->x_k, st->neg_lam, f_tmp, c_tmp, st->g_new, st->j_new, st->h_new, SQPB200_LOC_DEVICE, stream);
+        if (L.rc) return L.rc;
+        L.launches += 2;
+        if (!L.ph(SQPB200_PH_FINISH)) return L.rc;
+    }
+    if (!L.ph(SQPB200_PH_FINAL)) return L.rc;
+    if (launches) *launches = L.launches;
     return 0;
 }

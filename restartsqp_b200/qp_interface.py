@@ -185,6 +185,20 @@ class CudaQPInterface:
         if self.batch == 1 and int(self.get_status()[0]) != Exitflag.QP_OPTIMAL:
             raise LP_NOT_OPTIMAL("LP solver reports status %d" % int(self.get_status()[0]))
 
+    def io_layout(self):
+        """Byte layout of the handle's input block (g, lb, ub, lbA, ubA) and result block (x, y, obj, kkt, status, iters)."""
+        ino, outo = (C.c_size_t * 5)(), (C.c_size_t * 6)()
+        inb, outb = C.c_size_t(), C.c_size_t()
+        _check(self.h, self.L.sqpb200_io_layout(self.h, ino, C.byref(inb), outo, C.byref(outb)), "io_layout")
+        return dict(in_off=dict(zip(("g", "lb", "ub", "lbA", "ubA"), list(ino))), in_bytes=inb.value,
+                    out_off=dict(zip(("x", "y", "obj", "kkt", "status", "iters"), list(outo))), out_bytes=outb.value)
+
+    def solve_host(self, mode, in_block=None, Aval=None, Hval=None, out_block=None, maxiter=0):
+        """One call per solve for host-resident (pinned) data: uploads, solve and the result download are queued on the
+        handle's stream; nothing is waited for.  Arguments are raw host addresses (ints) or None."""
+        _check(self.h, self.L.sqpb200_solve_host(self.h, int(mode), int(maxiter), in_block, Aval, Hval, out_block), "solve_host")
+        self._kkt = None
+
     def synchronize(self):
         _check(self.h, self.L.sqpb200_synchronize(self.h), "synchronize")
 

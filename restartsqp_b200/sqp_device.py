@@ -215,7 +215,36 @@ class DeviceBatchedSQP:
         qp.update_bounds(T["delta"], T["x_l"], T["x_u"], T["x_k"], T["c_l"], T["c_u"], T["c_k"])
 
     # ---- src/Algorithm.cpp:55-168
-    def Optimize(self):
+    def Optimize(self, host_sequenced=False):
+        """The whole loop runs behind one C call (sqpb200_sqp_optimize: no interpreter between the launches);
+        host_sequenced=True sequences the same launches from Python (the two are compared bitwise in tests/test_gpu_sqp.py)."""
+        if host_sequenced:
+            return self._optimize_py()
+        T = self.T
+        if self.first_:  # structures of both backends (first set_A / set_H call of setupQP / setupLP, values follow in the loop)
+            self.myQP_.solverInterface_.set_A(SpTripletMat(self.nlp_.J_row1, self.nlp_.J_col1, None, self.nCon_, self.nVar_, False), self.myQP_.I_info_A_)
+            self.myQP_.solverInterface_.set_H(SpTripletMat(self.nlp_.H_row1, self.nlp_.H_col1, None, self.nVar_, self.nVar_, True))
+        if not self.myLP_.solverInterface_._A_set:
+            self.myLP_.solverInterface_.set_A(SpTripletMat(self.nlp_.J_row1, self.nlp_.J_col1, None, self.nCon_, self.nVar_, False), self.myLP_.I_info_A_)
+        first, nl = C.c_int(1 if self.first_ else 0), C.c_longlong(0)
+        rc = self.L.sqpb200_sqp_optimize(C.byref(self.S), self.myQP_.solverInterface_.h, self.myLP_.solverInterface_.h, self.nlp_.h,
+                                         int(bool(self.options_.second_order_correction)), 1, C.byref(first),
+                                         C.c_void_p(T["f_tmp"].data_ptr()), C.c_void_p(T["c_tmp"].data_ptr()), C.byref(nl), None)
+        if rc != 0:
+            raise capi.SqpB200Error("sqpb200_sqp_optimize failed (%d): %s / %s" % (
+                rc, self.L.sqpb200_last_error(self.myQP_.solverInterface_.h).decode(), self.L.sqpb200_last_error(self.myLP_.solverInterface_.h).decode()))
+        self.first_ = bool(first.value)
+        self.launches += int(nl.value)
+        return self._result()
+
+    def _result(self):
+        T = self.T
+        self.torch.cuda.synchronize()
+        h = lambda k: T[k].cpu().numpy()
+        return SQPResult(x=h("x_k"), obj=h("f_k"), exitflag=h("exitflag"), iters=h("iter").astype(np.int64), qp_iter=h("qp_iter"),
+                         KKT_error=h("kkt_err"), rho=h("rho"), delta=h("delta"))
+
+    def _optimize_py(self):
         T, nlp, B = self.T, self.nlp_, self.batch
         while True:
             cnt = self._phase(PH_FLAGS, read=True)
@@ -234,10 +263,7 @@ class DeviceBatchedSQP:
             nlp.eval_device(1, B, T["x_k"], T["neg_lam"], T["f_tmp"], T["c_tmp"], T["g_new"], T["j_new"], T["h_new"])
             self._phase(PH_FINISH)
         self._phase(PH_FINAL)
-        self.torch.cuda.synchronize()
-        h = lambda k: T[k].cpu().numpy()
-        return SQPResult(x=h("x_k"), obj=h("f_k"), exitflag=h("exitflag"), iters=h("iter").astype(np.int64), qp_iter=h("qp_iter"),
-                         KKT_error=h("kkt_err"), rho=h("rho"), delta=h("delta"))
+        return self._result()
 
     def close(self):
         self.myQP_.solverInterface_.close()

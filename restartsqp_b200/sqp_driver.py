@@ -383,7 +383,10 @@ class BatchedSQP:
         qp_obj_soc = self.myQP_.get_objective() + (qp_obj_tmp - self.rho_ * self.infea_measure_model_)
         self.p_k_[ok] = (self.p_k_ + s_k)[ok]
         self.get_trial_point_info(ok)
-        acc2 = self.ratio_test(ok, qp_obj=np.where(ok, qp_obj_soc, qp_obj_tmp))
+        # ratio_test takes pred_reduction_ from get_obj_QP(), the raw objective of the SOC QP just solved (src/Algorithm.cpp:728);
+        # qp_obj_ (= qp_obj_soc here) is bookkeeping the reference never reads in a test
+        del qp_obj_soc
+        acc2 = self.ratio_test(ok, qp_obj=self.myQP_.get_objective())
         still = rej & ~acc2
         self.p_k_[still] = p_tmp[still]
         self.myQP_.update_grad(self.grad_f_)

@@ -238,6 +238,7 @@ const char* sqpb200_nlp_last_error(void);
 #define SQPB200_PH_SOC_PREP 10
 #define SQPB200_PH_SOC_AFTER 11
 #define SQPB200_PH_SOC_RATIO 12
+#define SQPB200_PH_INIT 13
 typedef struct {
     int B, n, m, zJ, zH;
     /* Options (src/Options.cpp:19-57) */
@@ -267,6 +268,8 @@ typedef struct {
     unsigned char* rej;
     /* per-instance backend state machines of the QP and the LP handle (sqpb200_solve_per_instance); NULL: handle-level modes */
     signed char *qp_inst, *lp_inst;
+    /* start values of delta, rho, eps1 (Options, src/Options.cpp:19-57), applied by SQPB200_PH_INIT */
+    double delta0, rho0, eps10;
 } sqpb200_sqp_state;
 /* counters_host (may be NULL): the 8 device counters after the phase ([0] active instances, [1] OR of the raised Update_*
  * bits 1=A 2=H 4=bounds 8=delta 16=penalty 32=g, [2] instances needing the penalty update, [3] instances continuing the
@@ -281,6 +284,10 @@ int sqpb200_sqp_phase(const sqpb200_sqp_state* st, int phase, int* counters_host
  * refreshes both constraint sides (mode 3 of sqpb200_qphandler_bounds), 0 = the reference's stale-ubA behaviour (mode 1). */
 int sqpb200_sqp_optimize(sqpb200_sqp_state* st, sqpb200_handle qp, sqpb200_handle lp, sqpb200_nlp nlp, int second_order_correction,
                          int refresh_ubA, int* first, double* f_tmp, double* c_tmp, long long* launches, void* stream);
+/* Forget every solve so far: the next solve is an init (cold start) again, as for a freshly constructed backend
+ * (firstQPsolved_ = false, matrix status UNDEFINED, Update_* flags cleared; src/qpOASESInterface.cpp:35-50).  Structures and
+ * device buffers are kept, so one handle can serve batch after batch. */
+int sqpb200_reset(sqpb200_handle h);
 /* sqpb200_solve with the instance mask in device memory */
 int sqpb200_solve_device_mask(sqpb200_handle h, int mode, int maxiter, const unsigned char* device_mask);
 /* The same with the init / hotstart decision (src/qpOASESInterface.cpp:141-211, 817-833) made PER INSTANCE inside the kernel, as the

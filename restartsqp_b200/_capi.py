@@ -29,7 +29,7 @@ EXPORTS = [
     "sqpb200_solve_config", "sqpb200_last_solve_ms", "sqpb200_get_profile", "sqpb200_io_layout", "sqpb200_solve_host",
     "sqpb200_nlp_compile", "sqpb200_nlp_cubin_size", "sqpb200_nlp_load", "sqpb200_nlp_eval", "sqpb200_nlp_destroy",
     "sqpb200_nlp_launch_count", "sqpb200_nlp_last_error",
-    "sqpb200_sqp_phase", "sqpb200_sqp_optimize", "sqpb200_solve_device_mask", "sqpb200_device_buffers", "sqpb200_solve_per_instance",
+    "sqpb200_sqp_phase", "sqpb200_sqp_optimize", "sqpb200_reset", "sqpb200_solve_device_mask", "sqpb200_device_buffers", "sqpb200_solve_per_instance",
 ]
 
 
@@ -57,6 +57,7 @@ def lib():
         L.sqpb200_launch_count.argtypes = [C.c_void_p]
         L.sqpb200_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.sqpb200_io_layout.argtypes = [C.c_void_p] * 5
+        L.sqpb200_reset.argtypes = [C.c_void_p]
         L.sqpb200_sqp_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
         L.sqpb200_solve_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

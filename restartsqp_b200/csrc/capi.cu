@@ -221,6 +221,21 @@ int sqpb200_set_stream(sqpb200_handle h, void* s) {
     return 0;
 }
 
+int sqpb200_reset(sqpb200_handle h) {
+    if (!h) return SQPB200_ERR_INVALID;
+    h->first_solved = false;
+    h->upd_A = h->upd_H = h->upd_g = h->upd_bounds = false;
+    h->old_ms = h->new_ms = MS_UNDEFINED;
+    // invalidate every instance's hot-start image (its header says "not initialised"): an instance that is first solved later
+    // through a hot-start call then starts cold, exactly as on a fresh handle
+    CK(cudaSetDevice(h->device));
+    if (h->dstate && h->cfg_main.state_doubles > 0)
+        CK(cudaMemset2DAsync(h->dstate, (size_t)h->cfg_main.state_doubles * 8, 0, 32, h->batch, h->stream));
+    if (h->dgwork && h->large_slice_doubles > 0)
+        CK(cudaMemset2DAsync(h->dgwork, (size_t)h->large_slice_doubles * 8, 0, 32, h->batch, h->stream));
+    return 0;
+}
+
 int sqpb200_synchronize(sqpb200_handle h) {
     if (!h) return SQPB200_ERR_INVALID;
     CK(cudaSetDevice(h->device));

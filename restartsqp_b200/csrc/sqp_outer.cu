@@ -320,6 +320,24 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
         }
         break;
     }
+    case SQPB200_PH_INIT: {
+        // Algorithm::initialization (src/Algorithm.cpp:438-472) per instance, after f, c and the derivatives have been evaluated
+        // at the (shifted) start: infeasibility measure of the start, algorithm state back to the option values, backend state
+        // machines back to "no QP solved yet".  Lets one DeviceBatchedSQP object (handles, buffers, compiled NLP) serve batch
+        // after batch.
+        S.infea[b] = cal_infea(S, S.c_k, b);
+        S.delta[b] = S.delta0; S.rho[b] = S.rho0; S.eps1[b] = S.eps10;
+        S.kkt_err[b] = __longlong_as_double(0x7ff0000000000000LL);
+        S.exitflag[b] = EX_UNKNOWN; S.iter[b] = 0; S.pen_trial[b] = 0; S.qp_iter[b] = 0;
+        S.active[b] = 0; S.need[b] = 0; S.go[b] = 0; S.acc[b] = 0; S.upd[b] = 0; S.feasible_lp[b] = 0; S.rej[b] = 0;
+        for (int i = 0; i < n; i++) S.lam_x[(size_t)b * n + i] = 0.0;
+        for (int i = 0; i < m; i++) S.neg_lam[(size_t)b * m + i] = -S.lam_c[(size_t)b * m + i];
+        for (int k = 0; k < 2; k++) {
+            signed char* st = k ? S.lp_inst : S.qp_inst;
+            if (st) { st += 8 * (size_t)b; st[0] = 0; st[1] = 0; st[2] = -1; st[3] = -1; st[4] = 0; st[5] = 0; st[6] = 0; st[7] = 0; }
+        }
+        break;
+    }
     case SQPB200_PH_FINAL: {
         if (S.iter[b] == S.iter_max && S.exitflag[b] == EX_UNKNOWN) S.exitflag[b] = EX_EXCEED_MAX_ITER;
         break;
@@ -383,8 +401,22 @@ struct OuterLoop {
     // an empty Jacobian (m = 0) still raises Update_A like the reference's setter; the pointer is then never dereferenced
     bool valsA(sqpb200_handle h) { rc = sqpb200_set_values_A(h, S->zJ > 0 ? S->jac : S->x_k, SQPB200_LOC_DEVICE, 0); return rc == 0; }
     bool valsH(sqpb200_handle h) { rc = S->zH > 0 ? sqpb200_set_values_H(h, S->hess, SQPB200_LOC_DEVICE, 0) : 0; return rc == 0; }
-    // setupQP, src/Algorithm.cpp:645-697
-    bool setupQP(int bits, int* first) {
+    // setupQP, src/Algorithm.cpp:645-697.  The reference refreshes only what its Update_* flags name; here every refresh is
+    // issued every iteration (rewriting unchanged data with itself), so that the host does not have to read the flags back
+    // before it can queue the QP solve.  What the flags decide -- init / hotstart of each instance's backend -- is taken from
+    // the per-instance flags on the device (PH_FLAGS), not from which setters were called.
+    bool setupQP(int* first) {
+        if (!valsA(qp) || !valsH(qp)) return false;
+        if (*first) {
+            if (!bounds(qp, 0, S->x_k, S->c_k)) return false;
+            *first = 0;
+            S->clear_flags = 1;
+        } else if (!bounds(qp, bounds_update_mode, S->x_k, S->c_k)) return false;
+        return grad(qp, S->grad, S->rho);
+    }
+    // the reference's own form (only what the Update_* bits name): used with handle-level init / hotstart decisions, where the
+    // setters that were called decide the mode of the whole batch
+    bool setupQP_bits(int bits, int* first) {
         if (*first) {
             if (!valsA(qp) || !valsH(qp) || !bounds(qp, 0, S->x_k, S->c_k) || !grad(qp, S->grad, S->rho)) return false;
             *first = 0;
@@ -430,11 +462,19 @@ int sqpb200_sqp_optimize(sqpb200_sqp_state* st, sqpb200_handle qp, sqpb200_handl
     if (!st || !qp || !lp || !nlp || !first || st->B <= 0) return SQPB200_ERR_INVALID;
     OuterLoop L{st, qp, lp, nlp, (cudaStream_t)stream, refresh_ubA ? 3 : 1, {0, 0, 0, 0, 0, 0, 0, 0}, 0, 0};
     for (;;) {
-        if (!L.ph(SQPB200_PH_FLAGS, true)) return L.rc;
-        if (L.cnt[0] == 0) break;
-        if (!L.setupQP(L.cnt[1], first)) return L.rc;
+        // one read-back per outer iteration: the number of active instances (PH_FLAGS) and of instances that need the penalty
+        // update (PH_AFTER_QP) come back together, after the QP solve has been queued behind the data refresh
+        if (st->qp_inst) {
+            if (!L.ph(SQPB200_PH_FLAGS)) return L.rc;
+            if (!L.setupQP(first)) return L.rc;
+        } else {
+            if (!L.ph(SQPB200_PH_FLAGS, true)) return L.rc;
+            if (L.cnt[0] == 0) break;
+            if (!L.setupQP_bits(L.cnt[1], first)) return L.rc;
+        }
         if (!L.solve(qp, SQPB200_QP, st->active, st->qp_inst)) return L.rc;
         if (!L.ph(SQPB200_PH_AFTER_QP, true)) return L.rc;
+        if (L.cnt[0] == 0) break;  // nobody was active: the iteration above touched nothing
         if (L.cnt[2] > 0 && !L.penalty()) return L.rc;
         if (!L.ph(SQPB200_PH_TRIAL)) return L.rc;
         // get_trial_point_info :414-429

@@ -20,7 +20,7 @@ from .sqp_driver import SQPResult, classify_single_constraint
 from .sqp_types import Exitflag, Options, QPType, SpTripletMat
 
 PH_FLAGS, PH_AFTER_QP, PH_LP_AFTER, PH_PEN_CHECK, PH_PEN_AFTER, PH_PEN_FINAL, PH_TRIAL, PH_RATIO, PH_FINISH, PH_FINAL = range(10)
-PH_SOC_PREP, PH_SOC_AFTER, PH_SOC_RATIO = 10, 11, 12
+PH_SOC_PREP, PH_SOC_AFTER, PH_SOC_RATIO, PH_INIT = 10, 11, 12, 13
 UP_A, UP_H, UP_BOUNDS, UP_DELTA, UP_PENALTY, UP_G = 1, 2, 4, 8, 16, 32
 
 _P, _D, _I = C.c_void_p, C.c_double, C.c_int
@@ -40,7 +40,8 @@ class SqpState(C.Structure):
                                    "active", "need", "go", "acc", "upd", "feasible_lp",
                                    "qp_x", "qp_y", "qp_obj", "qp_kkt", "lp_x", "qp_status", "qp_iters", "lp_status", "lp_iters", "counters",
                                    "H_row1", "H_col1", "soc_g", "soc_x", "soc_c", "p_tmp", "qp_obj_tmp", "qp_obj_soc", "norm_p", "rej",
-                                   "qp_inst", "lp_inst")])
+                                   "qp_inst", "lp_inst")] +
+                [(k, _D) for k in ("delta0", "rho0", "eps10")])
 
 
 class DeviceBatchedSQP:
@@ -119,9 +120,29 @@ class DeviceBatchedSQP:
         self._counters = (C.c_int * 8)()
         self.first_ = True
         self.launches = 0
-        # infea_measure_ of the starting point (:472): cal_infea(c_k) -- PH_RATIO computes it for the trial point, so reuse
-        # the same device routine through a one-off launch on a state whose trial arrays alias the current ones
-        self._init_infea()
+        S.delta0, S.rho0, S.eps10 = float(o.delta), float(o.rho), float(o.eps1)
+        self._lam_start = np.asarray(lam_start, dtype=np.float64).reshape(1, m)
+        # infea_measure_ of the starting point (:472) and the per-instance algorithm state
+        self._phase(PH_INIT)
+
+    def reset(self, x0):
+        """Algorithm::initialization (src/Algorithm.cpp:438-472) for a new batch of `batch` starting points on the same object:
+        handles, device buffers and the compiled NLP are kept, so the per-batch cost is one upload, one evaluation and one
+        state-reset launch."""
+        torch, T, B = self.torch, self.T, self.batch
+        x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=np.float64)))
+        if x0.shape != (B, self.nVar_):
+            raise ValueError("reset() needs %d starting points of dimension %d" % (B, self.nVar_))
+        T["x_k"].copy_(torch.from_numpy(x0), non_blocking=False)
+        torch.minimum(torch.maximum(T["x_k"], T["x_l"]), T["x_u"], out=T["x_k"])  # shift_starting_point
+        T["lam_c"].copy_(torch.from_numpy(self._lam_start).to(self.dev).expand(B, -1))
+        torch.neg(T["lam_c"], out=T["neg_lam"])
+        self.nlp_.eval_device(1, B, T["x_k"], T["neg_lam"], T["f_k"], T["c_k"], T["grad"], T["jac"], T["hess"])
+        self.S.clear_flags = 0
+        self._phase(PH_INIT)
+        for hd in (self.myQP_, self.myLP_):
+            self.L.sqpb200_reset(hd.solverInterface_.h)
+        self.first_ = True
 
     # ---- helpers
     def _phase(self, phase, read=False):
@@ -130,17 +151,6 @@ class DeviceBatchedSQP:
             raise capi.SqpB200Error("sqpb200_sqp_phase(%d) failed: %d" % (phase, rc))
         self.launches += 1
         return list(self._counters) if read else None
-
-    def _init_infea(self):
-        T = self.T
-        c, cl, cu = T["c_k"], T["c_l"], T["c_u"]
-        torch = self.torch
-        s = torch.zeros(self.batch, dtype=torch.float64, device=self.dev)
-        for i in range(self.nCon_):  # index order of the reference loop (src/Algorithm.cpp:577-602); runs once
-            below = torch.where(c[:, i] < cl[:, i], cl[:, i] - c[:, i], torch.zeros_like(s))
-            above = torch.where((c[:, i] >= cl[:, i]) & (c[:, i] > cu[:, i]), c[:, i] - cu[:, i], torch.zeros_like(s))
-            s = s + below + above
-        T["infea"].copy_(s)
 
     def _jac(self):
         return SpTripletMat(self.nlp_.J_row1, self.nlp_.J_col1, self.T["jac"], self.nCon_, self.nVar_, False)

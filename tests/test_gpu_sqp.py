@@ -219,3 +219,25 @@ def test_cxx_sequenced_loop_equals_python_sequenced_loop(gpu_lib, name, soc):
     assert np.array_equal(r1.x, r2.x, equal_nan=True) and np.array_equal(r1.rho, r2.rho) and np.array_equal(r1.delta, r2.delta)
     assert a1.launches > 0
     a1.close(); a2.close(); dev.close()
+
+
+def test_reset_serves_batch_after_batch(gpu_lib):
+    """DeviceBatchedSQP.reset(x0): the same object (handles, buffers, compiled NLP) re-initialised for a new batch gives bit for bit
+    what a freshly constructed object gives, with and without per-instance backend state machines."""
+    import os
+    from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
+    from restartsqp_b200.sqp_device import DeviceBatchedSQP
+    from test_hs_suite import HS_DIR, perturbed_starts
+    dev = DeviceNLP(AmplNLP(os.path.join(HS_DIR, "hs100.nl")))
+    X1, X2 = perturbed_starts(dev.host, 96, 11), perturbed_starts(dev.host, 96, 12)
+    for pim in (True, False):
+        a = DeviceBatchedSQP(dev, x0=X1, options=r.Options(iter_max=120), per_instance_modes=pim)
+        a.Optimize()
+        a.reset(X2)
+        r_reused = a.Optimize()
+        b = DeviceBatchedSQP(dev, x0=X2, options=r.Options(iter_max=120), per_instance_modes=pim)
+        r_fresh = b.Optimize()
+        assert (r_reused.exitflag == r_fresh.exitflag).all() and (r_reused.iters == r_fresh.iters).all() and (r_reused.qp_iter == r_fresh.qp_iter).all()
+        assert np.array_equal(r_reused.x, r_fresh.x, equal_nan=True) and np.array_equal(r_reused.obj, r_fresh.obj, equal_nan=True)
+        a.close(); b.close()
+    dev.close()

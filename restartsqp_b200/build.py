@@ -18,7 +18,9 @@ OBJDIR = os.path.join(HERE, "build")
 HEADERS = [os.path.join(CSRC, f) for f in ("qp_kernel.cuh", "l0_kernels.cuh", "tma.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "sqpb200.h")]
 # (threads per QP, threads per CTA, warps per SM the registers are capped for): one warp per QP, 4/2/1 QPs per CTA
-TEAMS = [(32, 128, 16), (32, 64, 16), (32, 32, 16), (32, 128, 32)]
+TEAMS = [(32, 128, 16), (32, 64, 16), (32, 32, 16), (32, 128, 32),
+         # sub-warp teams: 16 / 8 lanes per QP (2 / 4 QPs per warp) for QPs with nV <= 16 / <= 8
+         (16, 128, 16), (8, 128, 16)]
 LARGE_CTA = int(os.environ.get("SQPB200_LARGE_CTA", "512"))  # threads of the one-QP-per-CTA kernel (large QPs)
 QP_EXTRA_FLAGS = os.environ.get("SQPB200_QP_FLAGS", "").split()
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

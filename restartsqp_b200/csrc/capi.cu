@@ -27,7 +27,7 @@ using namespace sqpb200;
 
 enum { MS_UNDEFINED = -1, MS_FIXED = 0, MS_VARIED = 1 };
 
-struct SolveCfg { int cap = 0, teams = 0, smem = 0, slice_doubles = 0, state_doubles = 0, resident = 0; };
+struct SolveCfg { int cap = 0, teams = 0, smem = 0, slice_doubles = 0, state_doubles = 0, resident = 0, lanes = 32; };
 
 struct sqpb200_handle_s {
     int batch = 0, nV = 0, nC = 0, qptype = SQPB200_QP, device = 0;
@@ -616,11 +616,26 @@ static void fill_dims(sqpb200_handle h, QPKernelArgs& a, int cap) {
 }
 
 // QPs (warps) per CTA in {4, 2, 1} for a given factor capacity: the one that keeps the most QPs resident per SM.
-static bool config_for_cap(sqpb200_handle h, int cap, SolveCfg& cfg) {
+// allow_subwarp: QPs with nV <= 16 / <= 8 run on teams of 16 / 8 lanes (2 / 4 QPs per warp, 8 / 16 QPs per 128-thread CTA).
+static bool config_for_cap(sqpb200_handle h, int cap, SolveCfg& cfg, bool allow_subwarp = false) {
     QPKernelArgs a;
     fill_dims(h, a, cap);
     const size_t slice_bytes = (size_t)a.slice_doubles * 8, pat_bytes = (size_t)a.pat_shorts * 2;
     const size_t SMEM_MAX = 227 * 1024, SMEM_SM = 228 * 1024;
+    cfg.lanes = 32;
+    if (allow_subwarp && h->nV <= 16 && !getenv("SQPB200_NO_SUBWARP")) {
+        const int lanes = h->nV <= 8 ? 8 : 16, teams = 128 / lanes;
+        const size_t smem = (size_t)teams * slice_bytes + pat_bytes;
+        if (smem <= SMEM_MAX) {
+            size_t ctas = SMEM_SM / (smem + 1024 + 512);
+            if (ctas > 4) ctas = 4;  // 16 warps per SM (the 128-register build)
+            if (ctas >= 1) {
+                cfg.cap = a.cap; cfg.teams = teams; cfg.smem = (int)smem; cfg.lanes = lanes;
+                cfg.slice_doubles = a.slice_doubles; cfg.state_doubles = a.state_doubles; cfg.resident = (int)(ctas * 4);
+                return true;
+            }
+        }
+    }
     int best_teams = 0;
     size_t best_res = 0;
     const char* force = getenv("SQPB200_QPS_PER_CTA");  // experiment knob: force 1, 2 or 4 QPs per CTA
@@ -664,7 +679,7 @@ static int choose_config(sqpb200_handle h) {
     if (!h->large) {
         h->have_rescue = fits16 && config_for_cap(h, nV, h->cfg_rescue);
         // without a rescue configuration the main launch must hold every QP: full capacity
-        if (!fits16 || !h->have_rescue || !config_for_cap(h, cap, h->cfg_main)) {
+        if (!fits16 || !h->have_rescue || !config_for_cap(h, cap, h->cfg_main, h->opt.team_size == 0)) {
             if (h->opt.team_size == 32) {
                 h->err = "QP too large for the shared-memory resident kernel (nV=" + std::to_string(nV) + ", capacity " + std::to_string(cap) + ")";
                 return SQPB200_ERR_TOO_LARGE;
@@ -680,7 +695,7 @@ static int choose_config(sqpb200_handle h) {
         h->slice_doubles = a.slice_doubles;
         return 0;
     }
-    h->team = 32; h->teams_per_cta = h->cfg_main.teams; h->smem_cta = h->cfg_main.smem;
+    h->team = h->cfg_main.lanes; h->teams_per_cta = h->cfg_main.teams; h->smem_cta = h->cfg_main.smem;
     h->slice_doubles = h->cfg_main.slice_doubles;
     return 0;
 }
@@ -691,6 +706,8 @@ cudaError_t launch_qp_solve_32_128_w16(const QPKernelArgs&, int, cudaStream_t);
 cudaError_t launch_qp_solve_32_128_w32(const QPKernelArgs&, int, cudaStream_t);
 cudaError_t launch_qp_solve_32_64_w16(const QPKernelArgs&, int, cudaStream_t);
 cudaError_t launch_qp_solve_32_32_w16(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_16_128_w16(const QPKernelArgs&, int, cudaStream_t);
+cudaError_t launch_qp_solve_8_128_w16(const QPKernelArgs&, int, cudaStream_t);
 cudaError_t launch_qp_solve_large(const QPKernelArgs&, cudaStream_t);
 int qp_solve_large_threads();
 }
@@ -722,6 +739,8 @@ static int prepare_large(sqpb200_handle h, const QPKernelArgs& a) {
     return 0;
 }
 static cudaError_t launch_cfg(const SolveCfg& cfg, const QPKernelArgs& a, cudaStream_t stream) {
+    if (cfg.lanes == 16) return launch_qp_solve_16_128_w16(a, cfg.smem, stream);
+    if (cfg.lanes == 8) return launch_qp_solve_8_128_w16(a, cfg.smem, stream);
     switch (cfg.teams) {
     // 4 QPs per CTA and shared memory allows >= 32 resident warps: the 64-register build (see qp_kernel.cuh)
     case 4: return cfg.resident >= 32 ? launch_qp_solve_32_128_w32(a, cfg.smem, stream) : launch_qp_solve_32_128_w16(a, cfg.smem, stream);

@@ -185,12 +185,21 @@ __device__ __forceinline__ double quot(double x, double d, double ri) {
 enum { PR_STEPDIR = 0, PR_RATIO = 1, PR_STEP = 2, PR_REMOVE = 3, PR_EXTEND = 4, PR_WVEC = 5, PR_ADD = 6, PR_REFAC_W = 7, PR_REFAC_M = 8,
        PR_REFAC_CHOL = 9, PR_DRIFT = 10, PR_ENSURE_LI = 11, PR_RSOLVE = 12, PR_SETUP = 13, PR_EPILOGUE = 14, PR_TOTAL = 15 };
 
-// TEAM = threads that cooperate on one QP.  32: one warp per QP, everything in the warp's shared-memory slice, pattern
+// TEAM = threads that cooperate on one QP.  <= 32: one warp (TEAM = 32) or a sub-warp team of 16 / 8 lanes per QP (QPs with
+// nV <= 16 / <= 8: a 5-variable QP keeps 5 of 32 lanes busy, so two or four of them share a warp; each team synchronises with
+// its own lane mask and the teams of a warp may diverge freely), everything in the team's shared-memory slice, pattern
 // staged as 16-bit indices.  > 32: the whole CTA works on one QP (large QPs); the slice lives in
 // global memory (sSlice; factors streamed through L1/L2), the pattern is read as 32-bit indices from global memory and
 // the team barrier is __syncthreads().
 template <int TEAM> struct PatIdx { typedef int type; };
 template <> struct PatIdx<32> { typedef short type; };
+template <> struct PatIdx<16> { typedef short type; };
+template <> struct PatIdx<8> { typedef short type; };
+// lane mask of the calling team inside its warp (TEAM <= 32)
+template <int TEAM> __device__ __forceinline__ unsigned team_mask() {
+    if (TEAM >= 32) return 0xffffffffu;
+    return ((1u << (TEAM & 31)) - 1u) << ((threadIdx.x & 31) & ~(TEAM - 1));
+}
 __shared__ double* sSlice;     // TEAM > 32: this CTA's slice in global memory
 __shared__ int sClusterSize;   // TEAM > 32: CTAs that share this QP (thread-block cluster), 1 without a cluster launch
 __shared__ uint32_t sPhase;    // TEAM > 32: phase bits of the TMA ring's mbarriers
@@ -200,14 +209,14 @@ __shared__ int sRedP[32];
 
 // Context of the calling team.  hdr: [0]=nFR [1]=nAC [2]=ramp_offset [3]=initialised.
 #define QP_CTX                                                                                     \
-    const int lane = (TEAM == 32) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;                    \
-    double* const slice = (TEAM == 32) ? qp_smem + (size_t)(threadIdx.x >> 5) * sA.slice_doubles : sSlice; \
+    const int lane = (TEAM <= 32) ? (int)(threadIdx.x & (TEAM - 1)) : (int)threadIdx.x;            \
+    double* const slice = (TEAM <= 32) ? qp_smem + (size_t)(threadIdx.x / TEAM) * sA.slice_doubles : sSlice; \
     int* const hdr = reinterpret_cast<int*>(slice);                                                \
     const int nV = sA.nV, nC = sA.nC, ld = sA.ld, cap = sA.cap;                                    \
     (void)lane; (void)hdr; (void)nV; (void)nC; (void)ld; (void)cap;
 #define QP_PAT                                                                                     \
-    const pidx* const pat = (TEAM == 32)                                                           \
-        ? reinterpret_cast<const pidx*>(qp_smem + (size_t)(blockDim.x >> 5) * sA.slice_doubles)   \
+    const pidx* const pat = (TEAM <= 32)                                                           \
+        ? reinterpret_cast<const pidx*>(qp_smem + (size_t)(blockDim.x / TEAM) * sA.slice_doubles) \
         : reinterpret_cast<const pidx*>(sA.gpat);
 
 #define V_(name) (slice + sA.o##name)
@@ -222,8 +231,8 @@ __shared__ int sRedP[32];
 #define T_(i, j) RT[(cap - 1 - (i)) * ld + (j)]
 // inner sequential sums: not unrolled in the warp kernel (instruction-cache footprint), unrolled 8x in the CTA kernel so
 // that the loads of consecutive terms overlap (the additions stay in order: no reassociation without fast-math)
-#define DOT_UNROLL _Pragma("unroll (TEAM == 32 ? 1 : 8)")
-#define SYNC() do { if (TEAM == 32) __syncwarp(); else __syncthreads(); } while (0)
+#define DOT_UNROLL _Pragma("unroll (TEAM <= 32 ? 1 : 8)")
+#define SYNC() do { if (TEAM <= 32) __syncwarp(team_mask<TEAM>()); else __syncthreads(); } while (0)
 
 template <int TEAM>
 struct QPT {
@@ -298,9 +307,10 @@ struct QPT {
     // ---------------------------------------------------------------- reductions
     // lexicographic (t, pos) minimum over the team, returned to every thread
     static __device__ __forceinline__ MinKey team_min(double t, int pos) {
-        QP_U1 for (int o = 16; o > 0; o >>= 1) {
-            double t2_ = __shfl_xor_sync(0xffffffffu, t, o);
-            int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
+        const unsigned tm = team_mask<TEAM>();
+        QP_U1 for (int o = (TEAM < 32 ? TEAM : 32) / 2; o > 0; o >>= 1) {
+            double t2_ = __shfl_xor_sync(tm, t, o);
+            int p2 = __shfl_xor_sync(tm, pos, o);
             if (key_less(t2_, p2, t, pos)) { t = t2_; pos = p2; }
         }
         if (TEAM > 32) {
@@ -1481,7 +1491,7 @@ struct QPT {
 #ifndef QP_EXACT
         if constexpr (TEAM > 32) { solve_T_blocked(b, v); return; }
 #endif
-        if (TEAM == 32 && nAC <= 32) {
+        if (TEAM <= 32 && nAC <= TEAM) {
             // whole right-hand side in registers (lane k holds b_k and its pivot): the substitution chain is one shuffle and
             // the three operations of quot() per unknown, no barrier and no shared-memory round trip.  Same operations on
             // the same operands in the same order as the loop below (and the oracle).
@@ -1491,7 +1501,7 @@ struct QPT {
             QP_U1 for (int i = 0; i < nAC; i++) {
                 const int d = nFR - 1 - i;
                 const double tkd = (lane > i && act) ? T_(lane, d) : 0.0;
-                const double vi = __shfl_sync(0xffffffffu, quot(bk, piv, ri), i);
+                const double vi = __shfl_sync(team_mask<TEAM>(), quot(bk, piv, ri), i, TEAM <= 32 ? TEAM : 32);
                 if (lane == i) v[d] = vi;
                 if (lane > i && act) bk -= tkd * vi;
             }
@@ -1518,13 +1528,13 @@ struct QPT {
 #ifndef QP_EXACT
         if constexpr (TEAM > 32) { solve_Tt_blocked(r, u); return; }
 #endif
-        if (TEAM == 32 && nAC <= 32) {  // register form, see solve_T
+        if (TEAM <= 32 && nAC <= TEAM) {  // register form, see solve_T
             const bool act = lane < nAC;
             double rk = act ? r[nFR - 1 - lane] : 0.0;
             const double piv = act ? T_(lane, nFR - 1 - lane) : 1.0, ri = 1.0 / piv;
             QP_U1 for (int i = nAC - 1; i >= 0; i--) {
                 const double tik = (lane < i) ? T_(i, nFR - 1 - lane) : 0.0;
-                const double ui = __shfl_sync(0xffffffffu, quot(rk, piv, ri), i);
+                const double ui = __shfl_sync(team_mask<TEAM>(), quot(rk, piv, ri), i, TEAM <= 32 ? TEAM : 32);
                 if (lane == i) u[i] = ui;
                 if (lane < i) rk -= tik * ui;
             }
@@ -2109,10 +2119,10 @@ __device__ __forceinline__ void qp_instance_store(signed char* st, int mode, int
 // WPS = warps per SM the register allocation is capped for: 16 (<= 128 registers; measured: 20 or 24 warps lose everywhere) or
 // 32 (<= 64 registers, a few spills): 15-20 % faster on QPs small enough that shared memory lets 32 warps be resident
 // (nV <~ 20), slower on the larger ones where shared memory caps the occupancy anyway -- capi.cu picks per problem size.
-static __device__ __forceinline__ void qp_solve_one(const QPKernelArgs& A, const int b, const int team_id, const int lane);
-template <int CTA_THREADS, int WPS>
+template <int TEAM> static __device__ __forceinline__ void qp_solve_one(const QPKernelArgs& A, const int b, const int team_id, const int lane);
+template <int CTA_THREADS, int WPS, int TEAM = 32>
 __global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solve_kernel(const __grid_constant__ QPKernelArgs A) {
-    constexpr int TEAMS = CTA_THREADS / 32;
+    constexpr int TEAMS = CTA_THREADS / TEAM;
     // stage the launch arguments and the 16-bit pattern once per CTA
     {
         const int* src = reinterpret_cast<const int*>(&A);
@@ -2127,23 +2137,23 @@ __global__ void __launch_bounds__(CTA_THREADS, (WPS * 32) / CTA_THREADS) qp_solv
     }
     __syncthreads();
 
-    const int team_id = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
+    const int team_id = threadIdx.x / TEAM;
+    const int lane = threadIdx.x & (TEAM - 1);
     if (A.rescue) {
         // rescue launch (small fixed grid): the instances the main launch listed as overflowing its factor capacity, re-solved
         // from their pre-solve state with full-size factors.  Usually the list is empty and every warp leaves at once.
         const int count = *A.ncap;
-        for (int k = blockIdx.x * TEAMS + team_id; k < count; k += gridDim.x * TEAMS) { qp_solve_one(A, A.caplist[k], team_id, lane); __syncwarp(); }
+        for (int k = blockIdx.x * TEAMS + team_id; k < count; k += gridDim.x * TEAMS) { qp_solve_one<TEAM>(A, A.caplist[k], team_id, lane); __syncwarp(team_mask<TEAM>()); }
         return;
     }
     const int b = blockIdx.x * TEAMS + team_id;
     if (b >= A.batch) return;
     if (A.mask && !A.mask[b]) return;
-    qp_solve_one(A, b, team_id, lane);
+    qp_solve_one<TEAM>(A, b, team_id, lane);
 }
 
-// one QP on the calling warp (slice `team_id` of the CTA's shared memory)
-static __device__ __forceinline__ void qp_solve_one(const QPKernelArgs& A, const int b, const int team_id, const int lane) {
+// one QP on the calling team of TEAM <= 32 lanes (slice `team_id` of the CTA's shared memory)
+template <int TEAM> static __device__ __forceinline__ void qp_solve_one(const QPKernelArgs& A, const int b, const int team_id, const int lane) {
     const int nV = A.nV, nC = A.nC, cap = A.cap, ld = A.ld;
     double* slice = qp_smem + (size_t)team_id * A.slice_doubles;
     int* hdr = reinterpret_cast<int*>(slice);
@@ -2153,64 +2163,64 @@ static __device__ __forceinline__ void qp_solve_one(const QPKernelArgs& A, const
     if (A.inst_state) {
         int oms, nms;
         mode = qp_instance_mode(A.inst_state + 8 * (size_t)b, A.rescue != 0, oms, nms);
-        __syncwarp();  // every lane has read the state
+        __syncwarp(team_mask<TEAM>());  // every lane has read the state
         if (lane == 0 && !A.rescue) qp_instance_store(A.inst_state + 8 * (size_t)b, mode, oms, nms);
     }
     int status = 0;
     if (mode != MODE_COLD) {
         // restore the pre-solve image: everything but the factors verbatim, then Q (nFR x nFR), R (nZ x nZ), T (nAC x nFR)
         const double* st = A.state + (size_t)b * A.state_doubles;
-        for (int i = lane; i < A.oP; i += 32) slice[i] = st[i];
-        __syncwarp();
+        for (int i = lane; i < A.oP; i += TEAM) slice[i] = st[i];
+        __syncwarp(team_mask<TEAM>());
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
         if (!hdr[3]) mode = MODE_COLD;  // previous solve did not end optimal: plain re-init (handle_error)
         else if (nFR > cap) status = ST_CAPACITY;
         else {
             const double *Qp = st + A.oP, *Rp = Qp + nFR * nFR, *Tp = Rp + nZ * nZ;
-            for (int k = lane; k < nFR * nFR; k += 32) Q[(k / nFR) * ld + (k % nFR)] = Qp[k];
-            for (int k = lane; k < nZ * nZ; k += 32) R_(k / nZ, k % nZ) = Rp[k];
-            for (int k = lane; k < nAC * nFR; k += 32) T_(k / nFR, k % nFR) = Tp[k];
+            for (int k = lane; k < nFR * nFR; k += TEAM) Q[(k / nFR) * ld + (k % nFR)] = Qp[k];
+            for (int k = lane; k < nZ * nZ; k += TEAM) R_(k / nZ, k % nZ) = Rp[k];
+            for (int k = lane; k < nAC * nFR; k += TEAM) T_(k / nFR, k % nFR) = Tp[k];
         }
-        __syncwarp();
+        __syncwarp(team_mask<TEAM>());
     }
     if (mode != MODE_HOT_FIXED) {
         const double* av = A.Aval + (size_t)b * A.zA;
-        for (int i = lane; i < A.zA; i += 32) slice[A.oAv + i] = av[i];
+        for (int i = lane; i < A.zA; i += TEAM) slice[A.oAv + i] = av[i];
         if (A.has_H && !A.is_lp) {
             const double* hv = A.Hval + (size_t)b * A.zH;
-            for (int i = lane; i < A.zH; i += 32) slice[A.oHv + i] = hv[i];
+            for (int i = lane; i < A.zH; i += TEAM) slice[A.oHv + i] = hv[i];
         }
     }
     {  // target data of the homotopy
         const double *gN = A.gN + (size_t)b * nV, *lbN = A.lbN + (size_t)b * nV, *ubN = A.ubN + (size_t)b * nV;
         const double *lbAN = A.lbAN + (size_t)b * nC, *ubAN = A.ubAN + (size_t)b * nC;
         // |v| > 1e20 is clamped to qpOASES's infinity, as the oracle does
-        for (int i = lane; i < nV; i += 32) {
+        for (int i = lane; i < nV; i += TEAM) {
             slice[A.ogN + i] = gN[i];
             slice[A.olbN + i] = fmin(fmax(lbN[i], -QP_INFTY), QP_INFTY);
             slice[A.oubN + i] = fmin(fmax(ubN[i], -QP_INFTY), QP_INFTY);
         }
-        for (int i = lane; i < nC; i += 32) {
+        for (int i = lane; i < nC; i += TEAM) {
             slice[A.olbAN + i] = fmin(fmax(lbAN[i], -QP_INFTY), QP_INFTY);
             slice[A.oubAN + i] = fmin(fmax(ubAN[i], -QP_INFTY), QP_INFTY);
         }
     }
-    __syncwarp();
+    __syncwarp(team_mask<TEAM>());
 
     int iters = 0, total_iters = 0;
     PROF_T0
     if (status != ST_CAPACITY) {
         if (mode == MODE_HOT_VARIED) {
-            if (QPT<32>::refactorise()) mode = MODE_COLD;  // projected Hessian of the kept set not PD: cold start
-            else QPT<32>::drift_correction();
+            if (QPT<TEAM>::refactorise()) mode = MODE_COLD;  // projected Hessian of the kept set not PD: cold start
+            else QPT<TEAM>::drift_correction();
         }
-        if (mode == MODE_COLD) QPT<32>::cold_start_state();
-        status = QPT<32>::homotopy(A.max_iter, iters);
+        if (mode == MODE_COLD) QPT<TEAM>::cold_start_state();
+        status = QPT<TEAM>::homotopy(A.max_iter, iters);
         total_iters += iters;
         if (status != ST_OPTIMAL && status != ST_CAPACITY && mode != MODE_COLD) {
             // one-retry recovery of handle_error (src/qpOASESInterface.cpp:746-754): plain re-init
-            QPT<32>::cold_start_state();
-            status = QPT<32>::homotopy(A.max_iter, iters);
+            QPT<TEAM>::cold_start_state();
+            status = QPT<TEAM>::homotopy(A.max_iter, iters);
             total_iters += iters;
         }
     }
@@ -2219,16 +2229,16 @@ static __device__ __forceinline__ void qp_solve_one(const QPKernelArgs& A, const
         return;
     }
     PROF_ADD(PR_TOTAL);
-    QPT<32>::epilogue(b, status, total_iters);
+    QPT<TEAM>::epilogue(b, status, total_iters);
     PROF_ADD(PR_EPILOGUE);
     if ((A.flags & FLAG_KEEP_STATE) && A.state) {
         double* st = A.state + (size_t)b * A.state_doubles;
-        for (int i = lane; i < A.oP; i += 32) st[i] = slice[i];
+        for (int i = lane; i < A.oP; i += TEAM) st[i] = slice[i];
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
         double *Qp = st + A.oP, *Rp = Qp + nFR * nFR, *Tp = Rp + nZ * nZ;
-        for (int k = lane; k < nFR * nFR; k += 32) Qp[k] = Q[(k / nFR) * ld + (k % nFR)];
-        for (int k = lane; k < nZ * nZ; k += 32) Rp[k] = R_(k / nZ, k % nZ);
-        for (int k = lane; k < nAC * nFR; k += 32) Tp[k] = T_(k / nFR, k % nFR);
+        for (int k = lane; k < nFR * nFR; k += TEAM) Qp[k] = Q[(k / nFR) * ld + (k % nFR)];
+        for (int k = lane; k < nZ * nZ; k += TEAM) Rp[k] = R_(k / nZ, k % nZ);
+        for (int k = lane; k < nAC * nFR; k += TEAM) Tp[k] = T_(k / nFR, k % nFR);
     }
 }
 

@@ -82,6 +82,9 @@ typedef struct {
     int factor_cap;      /* capacity of the TQ/Cholesky factors = max. simultaneously free variables held in shared
                             memory: 0 = auto (n + m/2 + 2 for nV = n + 2m), -1 = nV.  Instances that need more are
                             re-solved with capacity nV by a rescue launch: the value affects speed, not results. */
+    int debug_force_error_branch; /* test hook, 0 in production: every solve runs handle_error's infeasible branch after its first
+                            attempt (re-init from the slack-feasible guess x0 = [0; max(0, lbA); -min(0, ubA)],
+                            src/qpOASESInterface.cpp:716-729), which a feasible l1-penalty QP otherwise never reaches */
 } sqpb200_options;
 
 void sqpb200_default_options(sqpb200_options* o);
@@ -183,6 +186,17 @@ int sqpb200_kkt_residuals_recompute(sqpb200_handle h, double* out, int loc);
 /* ---- stand-alone batched SpMV / SpMTV on the handle's CSC matrices (SpHbMat::times,
  * transposed_times; src/SpHbMat.cpp:659-737).  x[batch][ncol or nrow], y[batch][nrow or ncol]. */
 int sqpb200_spmv(sqpb200_handle h, int which, int transpose, const double* x, double* y, int loc);
+
+/* ---- batched Vector operations (row A2 of SURVEY.md 8a: src/Vector.cpp:94-135, 174-184, 237-251; Utils oneNorm / infNorm,
+ * src/Utils.cpp:65-83) on [batch][n] arrays, no handle needed.  Reductions sum in the reference's index order per instance, so
+ * results are bit-identical with Vector::getOneNorm / getInfNorm / times.
+ * sqpb200_vector_reduce: op 0 = getOneNorm, 1 = getInfNorm, 2 = times (dot product with y); out[batch].
+ * sqpb200_vector_elementwise (in place on x): op 0 = add_vector (x += y), 1 = subtract_vector (x -= y), 2 = subtract_vector_to
+ * (x = y - x), 3 = addNumber (x += alpha), 4 = copy_vector (x = y), 5 = scale (x *= alpha). */
+int sqpb200_vector_reduce(int device, int op, long long batch, int n, const double* x, const double* y, double* out, int loc,
+                          void* stream);
+int sqpb200_vector_elementwise(int device, int op, long long batch, int n, double* x, const double* y, double alpha, int loc,
+                               void* stream);
 
 /* ---- stand-alone segmented triplet -> CSC assembly over `nmat` independent matrices in one
  * launch (rows A4/A5 as a batched device sort/scan).  seg[nmat+1] are offsets into the 1-based

@@ -123,6 +123,10 @@ typedef struct {
 } orc_qp_options;
 
 void orc_qp_default_options(orc_qp_options* o);
+/* qpOASESInterface::handle_error (src/qpOASESInterface.cpp:686-758): to be called when the last solve did not end OPTIMAL.
+ * Returns the new status; *iters_added = iterations the recovery adds to Stats::qp_iter.  force_guess != 0 (test hook) takes
+ * the infeasible branch (init from x0 = [0; max(0, lbA); -min(0, ubA)]) whatever the status. */
+int orc_qp_handle_error(orc_qp* q, const orc_qp_options* opt, int force_guess, int* iters_added);
 /* deviation study (process-global, tests only): flags 1 = true division, 2 = ratio test as num < t*den, 4 = maxDualJump cap;
  * refine_steps = numRefinementSteps.  (0, 0) = the shipped behaviour. */
 void orc_qp_set_variant(int flags, int refine_steps);

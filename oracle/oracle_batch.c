@@ -44,8 +44,10 @@ static void* batch_worker(void* arg) {
                                  J->g + (size_t)b * nV, J->Ap, J->Ai, J->Av + (size_t)b * J->Av_stride, J->lb + (size_t)b * nV,
                                  J->ub + (size_t)b * nV, J->lbA + (size_t)b * nC, J->ubA + (size_t)b * nC, J->is_lp);
             double o;
-            int it;
-            orc_qp_get_solution(q, J->x ? J->x + (size_t)b * nV : NULL, J->y ? J->y + (size_t)b * (nV + nC) : NULL, &o, &it);
+            int it, it1 = 0;
+            orc_qp_get_solution(q, NULL, NULL, NULL, &it);
+            if (st != ORC_QP_OPTIMAL) { st = orc_qp_handle_error(q, &opt, 0, &it1); it += it1; } /* optimizeQP -> handle_error */
+            orc_qp_get_solution(q, J->x ? J->x + (size_t)b * nV : NULL, J->y ? J->y + (size_t)b * (nV + nC) : NULL, &o, NULL);
             if (J->obj) J->obj[b] = o;
             if (J->status) J->status[b] = st;
             if (J->iters) J->iters[b] = it;

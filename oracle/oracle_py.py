@@ -221,6 +221,12 @@ class OracleQP:
     def flops(self):
         return self.L.orc_qp_get_flops(self.h)
 
+    def handle_error(self, force_guess=False):
+        """qpOASESInterface::handle_error after a solve that did not end OPTIMAL; returns (status, iterations added)."""
+        it = C.c_int(0)
+        st = self.L.orc_qp_handle_error(self.h, C.byref(self.opt), int(force_guess), C.byref(it))
+        return st, it.value
+
 
 def solve_batch(nV, nC, A, H, g, lb, ub, lbA, ubA, is_lp=False, max_iter=1000, nthreads=0, Avals=None, Hvals=None):
     """Cold-start solve of a batch on the host cores (OpenMP, one oracle object per thread).

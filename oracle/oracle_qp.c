@@ -76,6 +76,7 @@ struct orc_qp {
     double *dx, *dy, *dAx, *t1, *t2, *t3, *w, *a, *yv, *zv, *xiC, *xiB, *dg, *dlb, *dub, *dlbA, *dubA;
     int status, iters, initialised, ramp_offset, max_nFR;
     int fell_back; /* last hotstart_matrices could not keep the working set and ran the cold start itself */
+    int last_cold; /* the last solve was an init (cold or from a guess), not a hot start */
     double flops;
     int verbose;
 };
@@ -755,9 +756,73 @@ static int cold_start(orc_qp* q, const orc_qp_options* opt) {
         q->y[nV + i] = 0.0; q->sC[i] = 0; q->posAC[i] = -1; q->Ax[i] = 0.0;
         q->lbA[i] = -QP_BOUND_RELAX; q->ubA[i] = QP_BOUND_RELAX;
     }
+    q->last_cold = 1;
     q->status = homotopy(q, opt);
     q->initialised = 1;
     return q->status;
+}
+
+/* init(H, g, A, lb, ub, lbA, ubA, nWSR, 0, x0) of handle_error's infeasible branch (src/qpOASESInterface.cpp:716-729, 690-701):
+ * primal guess x0 = [0; max(0, lbA); -min(0, ubA)] (the slack-feasible point of the l1-penalty QP), y = 0; working set read
+ * off x0 and A x0 with boundTolerance = 1e6*EPS (bounds first, then the constraints in index order, linearly dependent ones
+ * left out); auxiliary data relaxed by boundRelaxation; then the homotopy to the real data. */
+static int guess_start(orc_qp* q, const orc_qp_options* opt) {
+    int nV = q->nV, nC = q->nC, o1 = nV - 2 * nC, o2 = nV - nC;
+    const double TOL = 1.0e6 * QP_EPS;
+    q->nFR = 0; q->nAC = 0; q->ramp_offset = 0; q->last_cold = 1;
+    for (int i = 0; i < nV; i++) { q->x[i] = 0.0; q->y[i] = 0.0; }
+    for (int i = 0; i < nC; i++) {
+        q->x[o1 + i] = fmax(0.0, q->lbAN[i]); q->x[o2 + i] = -fmin(0.0, q->ubAN[i]);
+        q->y[nV + i] = 0.0; q->sC[i] = 0; q->posAC[i] = -1;
+    }
+    mulA(q, q->x, q->Ax);
+    for (int i = 0; i < nV; i++) {
+        double xi = q->x[i];
+        int st = (xi <= q->lbN[i] + TOL) ? -1 : ((xi >= q->ubN[i] - TOL) ? 1 : 0);
+        q->sB[i] = st; q->posFR[i] = -1;
+        q->lb[i] = (st < 0) ? xi : xi - QP_BOUND_RELAX;
+        q->ub[i] = (st > 0) ? xi : xi + QP_BOUND_RELAX;
+    }
+    for (int i = 0; i < nC; i++) { q->lbA[i] = q->Ax[i] - QP_BOUND_RELAX; q->ubA[i] = q->Ax[i] + QP_BOUND_RELAX; }
+    for (int i = 0; i < nV; i++) if (q->sB[i] == 0) { q->FR[q->nFR] = i; q->posFR[i] = q->nFR; q->nFR++; }
+    if (q->nFR > q->max_nFR) q->max_nFR = q->nFR;
+    for (int i = 0; i < q->nFR; i++)
+        for (int j = 0; j < q->nFR; j++) q->Q[(size_t)i * nV + j] = (i == j) ? 1.0 : 0.0;
+    for (int i = 0; i < nC; i++) {
+        double ax = q->Ax[i];
+        int st = (ax <= q->lbAN[i] + TOL) ? -1 : ((ax >= q->ubAN[i] - TOL) ? 1 : 0);
+        if (st == 0 || q->nAC >= q->nFR) continue;
+        double z2, a2;
+        constraint_w(q, i, &z2, &a2);
+        if (!(z2 > QP_EPS_LI * QP_EPS_LI * a2) || a2 == 0.0) continue;
+        add_constraint(q, i, st);
+        if (st < 0) q->lbA[i] = ax; else q->ubA[i] = ax;
+    }
+    mulAT(q, q->y + nV, q->t2);
+    mulH(q, q->x, q->t1);
+    for (int i = 0; i < nV; i++) q->g[i] = q->t2[i] + q->y[i] - q->t1[i];
+    q->initialised = 1;
+    if (recompute_R(q)) { q->iters = 0; q->status = ORC_QPERROR_INTERNAL_ERROR; return q->status; }
+    q->status = homotopy(q, opt);
+    return q->status;
+}
+
+/* qpOASESInterface::handle_error (src/qpOASESInterface.cpp:686-758) on top of this solver; the backend restatements call it
+ * whenever a solve did not end OPTIMAL (after a hot start AND after an init, :160-162, :217-219).  Infeasible (or
+ * force_guess, a test hook): re-init from the slack-feasible guess.  Otherwise a plain re-init -- which after a failed init
+ * repeats the same deterministic solve, so only its iteration count is added again (the reference adds nWSR of both runs to
+ * Stats::qp_iter, :752-753).  Returns the status; *iters_added = iterations of the recovery attempt. */
+int orc_qp_handle_error(orc_qp* q, const orc_qp_options* opt, int force_guess, int* iters_added) {
+    int st;
+    if (q->fell_back && !force_guess) { /* the cold start run inside hotstart_matrices already was the recovery attempt */
+        if (iters_added) *iters_added = 0;
+        return q->status;
+    }
+    if ((q->status == ORC_QPERROR_INFEASIBLE || force_guess) && q->nV >= 2 * q->nC) st = guess_start(q, opt);
+    else if (!q->last_cold) st = cold_start(q, opt);
+    else st = q->status;
+    if (iters_added) *iters_added = q->iters;
+    return st;
 }
 
 int orc_qp_init(orc_qp* q, const orc_qp_options* opt, const int* H_colptr, const int* H_rowidx,
@@ -773,6 +838,7 @@ int orc_qp_init(orc_qp* q, const orc_qp_options* opt, const int* H_colptr, const
     build_dense_A(q);
     set_targets(q, g, lb, ub, lbA, ubA);
     q->flops = 0.0;
+    q->fell_back = 0;
     return cold_start(q, opt);
 }
 
@@ -780,6 +846,7 @@ int orc_qp_hotstart(orc_qp* q, const orc_qp_options* opt, const double* g, const
                     const double* ub, const double* lbA, const double* ubA) {
     if (!q->initialised) return ORC_QPERROR_NOTINITIALISED;
     set_targets(q, g, lb, ub, lbA, ubA);
+    q->last_cold = 0; q->fell_back = 0;
     q->status = homotopy(q, opt);
     return q->status;
 }
@@ -823,6 +890,7 @@ int orc_qp_hotstart_matrices(orc_qp* q, const orc_qp_options* opt, const double*
     }
     mulA(q, q->x, q->Ax);
     drift_correction(q);
+    q->last_cold = 0;
     q->status = homotopy(q, opt);
     return q->status;
 }

@@ -126,11 +126,10 @@ static void backend_solve(backend* b) {
         st = (mode == 1) ? orc_qp_hotstart(b->solver, &o, b->g, b->lb, b->ub, b->lbA, b->ubA)
                          : orc_qp_hotstart_matrices(b->solver, &o, Hv, b->Av, b->g, b->lb, b->ub, b->lbA, b->ubA);
         orc_qp_get_solution(b->solver, NULL, NULL, NULL, &its);
-        if (st != ORC_QP_OPTIMAL && !(mode == 2 && orc_qp_get_fell_back(b->solver))) { /* handle_error: plain re-init */
-            st = orc_qp_init(b->solver, &o, Hp, Hi, Hv, b->g, b->Ap, b->Ai, b->Av, b->lb, b->ub, b->lbA, b->ubA, b->is_lp);
-            orc_qp_get_solution(b->solver, NULL, NULL, NULL, &it1);
-            its += it1;
-        }
+    }
+    if (st != ORC_QP_OPTIMAL) { /* handle_error (:160-162, :217-219), after an init as well as after a hot start */
+        st = orc_qp_handle_error(b->solver, &o, 0, &it1);
+        its += it1;
     }
     b->inited = (st == ORC_QP_OPTIMAL);
     orc_qp_get_solution(b->solver, b->x, b->y, &b->obj, NULL);

@@ -26,7 +26,7 @@ EXPORTS = [
     "sqpb200_set_vectors", "sqpb200_get_vectors", "sqpb200_qphandler_bounds", "sqpb200_qphandler_g",
     "sqpb200_solve", "sqpb200_get_solution", "sqpb200_get_working_set", "sqpb200_kkt_residuals",
     "sqpb200_kkt_residuals_recompute", "sqpb200_spmv", "sqpb200_assemble_csc_batched", "sqpb200_launch_count",
-    "sqpb200_solve_config", "sqpb200_last_solve_ms", "sqpb200_get_profile", "sqpb200_io_layout", "sqpb200_solve_host",
+    "sqpb200_solve_config", "sqpb200_last_solve_ms", "sqpb200_get_profile", "sqpb200_io_layout", "sqpb200_solve_host", "sqpb200_vector_reduce", "sqpb200_vector_elementwise",
     "sqpb200_nlp_compile", "sqpb200_nlp_cubin_size", "sqpb200_nlp_load", "sqpb200_nlp_eval", "sqpb200_nlp_destroy",
     "sqpb200_nlp_launch_count", "sqpb200_nlp_last_error",
     "sqpb200_sqp_phase", "sqpb200_sqp_optimize", "sqpb200_reset", "sqpb200_solve_device_mask", "sqpb200_device_buffers", "sqpb200_solve_per_instance",
@@ -36,7 +36,7 @@ EXPORTS = [
 class Options(C.Structure):
     _fields_ = [("qp_maxiter", C.c_int), ("lp_maxiter", C.c_int), ("enable_flipping", C.c_int),
                 ("enable_ramping", C.c_int), ("enable_drift", C.c_int), ("team_size", C.c_int),
-                ("keep_state", C.c_int), ("factor_cap", C.c_int)]
+                ("keep_state", C.c_int), ("factor_cap", C.c_int), ("debug_force_error_branch", C.c_int)]
 
 
 _LIB = None
@@ -58,6 +58,8 @@ def lib():
         L.sqpb200_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.sqpb200_io_layout.argtypes = [C.c_void_p] * 5
         L.sqpb200_reset.argtypes = [C.c_void_p]
+        L.sqpb200_vector_reduce.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sqpb200_vector_elementwise.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
         L.sqpb200_sqp_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
         L.sqpb200_solve_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -131,6 +131,7 @@ void sqpb200_default_options(sqpb200_options* o) {
     o->team_size = 0;
     o->keep_state = 1;
     o->factor_cap = 0;
+    o->debug_force_error_branch = 0;
 }
 
 const char* sqpb200_version(void) { return "sqpb200 0.1 (sm_100a)"; }
@@ -217,6 +218,15 @@ int sqpb200_destroy(sqpb200_handle h) {
 
 int sqpb200_set_stream(sqpb200_handle h, void* s) {
     if (!h) return SQPB200_ERR_INVALID;
+    if ((cudaStream_t)s == h->stream) return 0;
+    // work already queued on the old stream (arena memset, uploads, an in-flight solve) is ordered before anything the new
+    // stream will run: the new stream waits on an event recorded at the tail of the old one (no host synchronisation)
+    CK(cudaSetDevice(h->device));
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, h->stream));
+    CK(cudaStreamWaitEvent((cudaStream_t)s, ev, 0));
+    CK(cudaEventDestroy(ev));
     h->stream = (cudaStream_t)s;
     return 0;
 }
@@ -259,15 +269,24 @@ static int run_assembly(sqpb200_handle h, cudaStream_t stream, int nmat, const i
         pad_off[m + 1] = pad_off[m] + P;
         cp_off[m + 1] = cp_off[m] + ncol[m] + 1;
     }
+    // one checked allocation behind every scratch array (each sub-array 256-byte aligned), freed on every exit path
     int *dseg, *dncol, *dcpoff, *drow, *dcol, *dpad, *dcolptr, *drowidx, *dorder;
     uint64_t* dscr;
-    auto A = [&](void** p, size_t b) { return cudaMalloc(p, b ? b : 4); };
+    char* pool = nullptr;
     cudaError_t e = cudaSuccess;
-    e = A((void**)&dseg, (nmat + 1) * 4); if (e) goto fail0;
-    A((void**)&dncol, nmat * 4); A((void**)&dcpoff, (nmat + 1) * 4); A((void**)&dpad, (nmat + 1) * 4);
-    A((void**)&drow, (size_t)ztot * 4); A((void**)&dcol, (size_t)ztot * 4);
-    A((void**)&dcolptr, (size_t)cp_off[nmat] * 4); A((void**)&drowidx, (size_t)ztot * 4); A((void**)&dorder, (size_t)ztot * 4);
-    e = A((void**)&dscr, (size_t)pad_off[nmat] * 8); if (e) goto fail0;
+    {
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += ((bytes ? bytes : 4) + 255) / 256 * 256; return o; };
+        const size_t o_seg = take((size_t)(nmat + 1) * 4), o_ncol = take((size_t)nmat * 4), o_cp = take((size_t)(nmat + 1) * 4),
+                     o_pad = take((size_t)(nmat + 1) * 4), o_row = take((size_t)ztot * 4), o_col = take((size_t)ztot * 4),
+                     o_colptr = take((size_t)cp_off[nmat] * 4), o_rowidx = take((size_t)ztot * 4), o_order = take((size_t)ztot * 4),
+                     o_scr = take((size_t)pad_off[nmat] * 8);
+        e = cudaMalloc((void**)&pool, off);
+        if (e != cudaSuccess) { *err = cudaGetErrorString(e); return SQPB200_ERR_NOMEM; }
+        dseg = (int*)(pool + o_seg); dncol = (int*)(pool + o_ncol); dcpoff = (int*)(pool + o_cp); dpad = (int*)(pool + o_pad);
+        drow = (int*)(pool + o_row); dcol = (int*)(pool + o_col); dcolptr = (int*)(pool + o_colptr); drowidx = (int*)(pool + o_rowidx);
+        dorder = (int*)(pool + o_order); dscr = (uint64_t*)(pool + o_scr);
+    }
     cudaMemcpyAsync(dseg, seg, (nmat + 1) * 4, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(dncol, ncol, nmat * 4, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(dcpoff, cp_off.data(), (nmat + 1) * 4, cudaMemcpyHostToDevice, stream);
@@ -294,13 +313,9 @@ static int run_assembly(sqpb200_handle h, cudaStream_t stream, int nmat, const i
         if (ms) *ms = t;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
-    cudaFree(dseg); cudaFree(dncol); cudaFree(dcpoff); cudaFree(dpad); cudaFree(drow); cudaFree(dcol);
-    cudaFree(dcolptr); cudaFree(drowidx); cudaFree(dorder); cudaFree(dscr);
+    cudaFree(pool);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return SQPB200_ERR_CUDA; }
     return 0;
-fail0:
-    *err = cudaGetErrorString(e);
-    return SQPB200_ERR_CUDA;
 }
 
 int sqpb200_assemble_csc_batched(int device, int nmat, const int* seg, const int* ncol, const int* row1,
@@ -457,6 +472,60 @@ int sqpb200_get_structure(sqpb200_handle h, int which, int* colptr, int* rowidx,
 int sqpb200_get_nnz(sqpb200_handle h, int which) {
     if (!h) return SQPB200_ERR_INVALID;
     return which == SQPB200_MAT_A ? h->zA : h->zH;
+}
+
+// ------------------------------------------------------------------------------ batched Vector operations (row A2)
+int sqpb200_vector_reduce(int device, int op, long long batch, int n, const double* x, const double* y, double* out, int loc, void* stream_) {
+    if (batch <= 0 || n < 0 || !x || !out || op < 0 || op > 2 || (op == 2 && !y)) return SQPB200_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return SQPB200_ERR_CUDA;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const double *dx = x, *dy = y;
+    double *dout = out, *tmp = nullptr;
+    const size_t bytes = (size_t)batch * (size_t)(n > 0 ? n : 1) * 8;
+    if (loc == SQPB200_LOC_HOST) {
+        if (cudaMalloc((void**)&tmp, bytes * (op == 2 ? 2 : 1) + (size_t)batch * 8) != cudaSuccess) return SQPB200_ERR_NOMEM;
+        double* p = tmp;
+        if (n > 0) cudaMemcpyAsync(p, x, bytes, cudaMemcpyHostToDevice, stream);
+        dx = p; p += (size_t)batch * (n > 0 ? n : 1);
+        if (op == 2) { if (n > 0) cudaMemcpyAsync(p, y, bytes, cudaMemcpyHostToDevice, stream); dy = p; p += (size_t)batch * (n > 0 ? n : 1); }
+        dout = p;
+    }
+    long long g = (batch + 63) / 64;
+    if (g > 148LL * 32) g = 148LL * 32;
+    vector_reduce_kernel<<<(int)g, 64, 0, stream>>>(batch, n, op, dx, dy, dout);
+    cudaError_t e = cudaGetLastError();
+    if (loc == SQPB200_LOC_HOST) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, (size_t)batch * 8, cudaMemcpyDeviceToHost, stream);
+        cudaError_t e2 = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) e = e2;
+        cudaFree(tmp);
+    }
+    return e == cudaSuccess ? 0 : SQPB200_ERR_CUDA;
+}
+
+int sqpb200_vector_elementwise(int device, int op, long long batch, int n, double* x, const double* y, double alpha, int loc, void* stream_) {
+    if (batch <= 0 || n < 0 || !x || op < 0 || op > 5 || ((op <= 2 || op == 4) && !y)) return SQPB200_ERR_INVALID;
+    if (n == 0) return 0;
+    if (cudaSetDevice(device) != cudaSuccess) return SQPB200_ERR_CUDA;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long total = batch * n;
+    double *dx = x, *tmp = nullptr;
+    const double* dy = y;
+    if (loc == SQPB200_LOC_HOST) {
+        if (cudaMalloc((void**)&tmp, (size_t)total * 16) != cudaSuccess) return SQPB200_ERR_NOMEM;
+        cudaMemcpyAsync(tmp, x, (size_t)total * 8, cudaMemcpyHostToDevice, stream);
+        dx = tmp;
+        if (y) { cudaMemcpyAsync(tmp + total, y, (size_t)total * 8, cudaMemcpyHostToDevice, stream); dy = tmp + total; }
+    }
+    vector_elementwise_kernel<<<grid_for(total, 256), 256, 0, stream>>>(total, op, dx, dy, alpha);
+    cudaError_t e = cudaGetLastError();
+    if (loc == SQPB200_LOC_HOST) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(x, dx, (size_t)total * 8, cudaMemcpyDeviceToHost, stream);
+        cudaError_t e2 = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) e = e2;
+        cudaFree(tmp);
+    }
+    return e == cudaSuccess ? 0 : SQPB200_ERR_CUDA;
 }
 
 // ------------------------------------------------------------------------------ values
@@ -795,7 +864,8 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
     fill_dims(h, a, h->large ? h->nV : h->cfg_main.cap);
     a.max_iter = maxiter > 0 ? maxiter : (is_lp ? h->opt.lp_maxiter : h->opt.qp_maxiter);
     a.flags = (h->opt.enable_flipping ? FLAG_FLIPPING : 0) | (h->opt.enable_ramping ? FLAG_RAMPING : 0) |
-              (h->opt.enable_drift ? FLAG_DRIFT : 0) | (h->opt.keep_state ? FLAG_KEEP_STATE : 0);
+              (h->opt.enable_drift ? FLAG_DRIFT : 0) | (h->opt.keep_state ? FLAG_KEEP_STATE : 0) |
+              (h->opt.debug_force_error_branch ? FLAG_FORCE_GUESS : 0);
     a.mode = mode;
     a.Ap = h->dAp; a.Ai = h->dAi; a.Arp = h->dArp; a.Aci = h->dAci; a.Aperm = h->dAperm;
     a.Hp = h->dHp; a.Hi = h->dHi;

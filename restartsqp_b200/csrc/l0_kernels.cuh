@@ -148,6 +148,62 @@ __global__ void __launch_bounds__(256) broadcast_rows_kernel(long long total, in
 }
 
 // ------------------------------------------------------------------------------------------
+// A2: batched Vector operations (src/Vector.cpp:94-135, 174-184, 237-251; Utils oneNorm / infNorm src/Utils.cpp:65-83).
+// Reductions run in the reference's index order per instance (bit-identical).  A CTA of 64 threads owns 64 instances: the
+// rows move through shared memory in tiles of 32 columns (coalesced loads, conflict-free lane-per-row reads), so HBM sees
+// every element once at full line width although each instance is summed sequentially.
+// op: 0 getOneNorm, 1 getInfNorm, 2 times (dot product with y)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) vector_reduce_kernel(long long batch, int n, int op, const double* __restrict__ x,
+                                                             const double* __restrict__ y, double* __restrict__ out) {
+    __shared__ double tx[64][33];
+    __shared__ double ty[64][33];
+    const int tid = threadIdx.x, l = tid & 31, w = tid >> 5;
+    for (long long b0 = (long long)blockIdx.x * 64; b0 < batch; b0 += (long long)gridDim.x * 64) {
+        double acc = 0.0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            __syncthreads();
+            for (int r = w; r < 64; r += 2) {  // warp w loads rows w, w+4, ...: 32 consecutive doubles of one instance
+                const long long b = b0 + r;
+                const int j = j0 + l;
+                if (b < batch && j < n) { tx[r][l] = x[b * n + j]; if (op == 2) ty[r][l] = y[b * n + j]; }
+            }
+            __syncthreads();
+            if (b0 + tid < batch) {
+                const int jm = (n - j0 < 32) ? n - j0 : 32;
+                for (int j = 0; j < jm; j++) {
+                    const double v = tx[tid][j];
+                    if (op == 0) acc = __dadd_rn(acc, fabs(v));
+                    else if (op == 1) { const double a = (v < 0) ? -v : v; if (a > acc) acc = a; }
+                    else acc = __dadd_rn(acc, __dmul_rn(v, ty[tid][j]));
+                }
+            }
+        }
+        if (b0 + tid < batch) out[b0 + tid] = acc;
+    }
+}
+// elementwise: 0 add_vector (x += y), 1 subtract_vector (x -= y), 2 subtract_vector_to (x = y - x), 3 addNumber (x += alpha),
+// 4 copy_vector (x = y), 5 scale (x *= alpha)
+__global__ void __launch_bounds__(256) vector_elementwise_kernel(long long total, int op, double* __restrict__ x,
+                                                                  const double* __restrict__ y, double alpha) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        const double v = x[t];
+        double r;
+        switch (op) {
+        case 0: r = __dadd_rn(v, y[t]); break;
+        case 1: r = __dsub_rn(v, y[t]); break;
+        case 2: r = __dsub_rn(y[t], v); break;
+        case 3: r = __dadd_rn(v, alpha); break;
+        case 4: r = y[t]; break;
+        default: r = __dmul_rn(v, alpha); break;
+        }
+        x[t] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // A7: batched SpMV / SpMTV on a shared pattern.  One thread per (instance, output entry):
 // out[b][o] = sum_{k in [ptr[o], ptr[o+1])} val[b][perm ? perm[k] : k] * x[b][idx[k]],
 // accumulated in k order = the reference's storage order for that output entry.

@@ -110,6 +110,7 @@ int sqpb200_nlp_eval(sqpb200_nlp h, int which, int B, const double* x, const dou
     cudaStream_t stream = (cudaStream_t)stream_;
     cudaSetDevice(h->device);
     const size_t n = h->n, m = h->m, zJ = h->zJ, zH = h->zH, Bz = (size_t)B;
+    if (which == 1 && m && !lam) return SQPB200_ERR_INVALID;  // the Lagrangian Hessian needs multipliers (host and device mode)
     const double *dx = x, *dlam = lam;
     double *df = f, *dc = c, *dg = grad, *dj = jac, *dh = hess;
     size_t off[8];

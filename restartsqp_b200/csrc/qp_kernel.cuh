@@ -50,7 +50,8 @@ namespace sqpb200 {
 enum { ST_OPTIMAL = 20, ST_INTERNAL = 21, ST_INFEASIBLE = 22, ST_UNBOUNDED = 23, ST_NOTINIT = 25, ST_HOMOTOPY = 28,
        ST_CAPACITY = 31 /* internal: factor capacity exceeded, instance is re-solved by the rescue launch */ };
 enum { MODE_COLD = 0, MODE_HOT_FIXED = 1, MODE_HOT_VARIED = 2 };
-enum { FLAG_FLIPPING = 1, FLAG_RAMPING = 2, FLAG_DRIFT = 4, FLAG_KEEP_STATE = 8 };
+enum { FLAG_FLIPPING = 1, FLAG_RAMPING = 2, FLAG_DRIFT = 4, FLAG_KEEP_STATE = 8,
+       FLAG_FORCE_GUESS = 16 /* test hook: take handle_error's infeasible branch whatever the first attempt returned */ };
 
 struct QPKernelArgs {
     int batch, nV, nC;
@@ -2006,6 +2007,80 @@ struct QPT {
         return recompute_R();
     }
 
+    // handle_error's infeasible branch (src/qpOASESInterface.cpp:716-729, 690-701): init with the primal guess
+    // x0 = [0; max(0, lbA); -min(0, ubA)] (the slack-feasible point of the l1-penalty QP), y = 0; working set read off x0 and
+    // A x0 with boundTolerance = 1e6*EPS (bounds first, then the constraints in index order, linearly dependent ones left out);
+    // auxiliary data relaxed by boundRelaxation.  Returns 0, 1 (projected Hessian not positive definite) or 2 (factor capacity).
+    static __device__ QP_FN int guess_start_state() {
+        QP_CTX
+        double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA), *Q = V_(Q);
+        const double *lbN = V_(lbN), *ubN = V_(ubN), *lbAN = V_(lbAN), *ubAN = V_(ubAN);
+        short *sB = sB_, *sC = sC_, *FR = FR_, *posFR = posFR_, *posAC = posAC_;
+        const double TOL = 1.0e6 * QP_EPS;
+        const int o1 = nV - 2 * nC, o2 = nV - nC;
+        QP_U1 for (int i = lane; i < nV; i += TEAM) { x[i] = 0.0; y[i] = 0.0; }
+        SYNC();
+        QP_U1 for (int i = lane; i < nC; i += TEAM) {
+            x[o1 + i] = fmax(0.0, lbAN[i]); x[o2 + i] = -fmin(0.0, ubAN[i]);
+            y[nV + i] = 0.0; sC[i] = 0; posAC[i] = -1;
+        }
+        SYNC();
+        mulA(x, Ax);
+        QP_U1 for (int i = lane; i < nV; i += TEAM) {
+            const double xi = x[i];
+            const int st = (xi <= lbN[i] + TOL) ? -1 : ((xi >= ubN[i] - TOL) ? 1 : 0);
+            sB[i] = (short)st; posFR[i] = -1;
+            lb[i] = (st < 0) ? xi : xi - QP_BOUND_RELAX;
+            ub[i] = (st > 0) ? xi : xi + QP_BOUND_RELAX;
+        }
+        QP_U1 for (int i = lane; i < nC; i += TEAM) { lbA[i] = Ax[i] - QP_BOUND_RELAX; ubA[i] = Ax[i] + QP_BOUND_RELAX; }
+        SYNC();
+        if (lane == 0) {
+            int nf = 0;
+            QP_U1 for (int i = 0; i < nV; i++) if (sB[i] == 0) { if (nf < cap) FR[nf] = (short)i; posFR[i] = (short)nf; nf++; }
+            hdr[0] = nf; hdr[1] = 0; hdr[2] = 0;
+            if (nf > hdr[6]) hdr[6] = nf;
+        }
+        SYNC();
+        const int nFR = hdr[0];
+        if (nFR > cap) return 2;
+        QP_U1 for (int k = lane; k < nFR * nFR; k += TEAM) { const int i = k / nFR, j = k % nFR; Q[i * ld + j] = (i == j) ? 1.0 : 0.0; }
+        SYNC();
+        QP_U1 for (int i = 0; i < nC; i++) {
+            const double ax = Ax[i];
+            const int st = (ax <= lbAN[i] + TOL) ? -1 : ((ax >= ubAN[i] - TOL) ? 1 : 0);
+            if (st == 0 || hdr[1] >= hdr[0]) continue;
+            double z2, a2;
+            constraint_w(i, z2, a2);
+            if (!(z2 > QP_EPS_LI * QP_EPS_LI * a2) || a2 == 0.0) continue;
+            add_constraint(i, st);
+            if (lane == 0) { if (st < 0) lbA[i] = ax; else ubA[i] = ax; }
+            SYNC();
+        }
+        stationarity_gradient();
+        return recompute_R() ? 1 : 0;
+    }
+    // qpOASESInterface::handle_error (src/qpOASESInterface.cpp:686-758), called when a solve did not end OPTIMAL -- after an init
+    // as well as after a hot start (:160-162, :217-219).  `cold`: the failed attempt was an init.  Infeasible: re-init from the
+    // slack-feasible guess.  Otherwise plain re-init; after a failed init that repeats the same deterministic solve, so only its
+    // iteration count is added again (the reference adds nWSR of both runs to Stats::qp_iter, :752-753).
+    static __device__ __forceinline__ int handle_error(int status, bool cold, int max_iter, int last_iters, int& total_iters) {
+        QP_CTX
+        int iters = 0;
+        if ((status == ST_INFEASIBLE || (sA.flags & FLAG_FORCE_GUESS)) && nV >= 2 * nC) {
+            const int e = guess_start_state();
+            if (e == 2) return ST_CAPACITY;
+            if (e == 1) return ST_INTERNAL;
+            status = homotopy(max_iter, iters);
+            total_iters += iters;
+        } else if (!cold) {
+            cold_start_state();
+            status = homotopy(max_iter, iters);
+            total_iters += iters;
+        } else total_iters += last_iters;
+        return status;
+    }
+
     // ---------------------------------------------------------------- epilogue: objective + test_optimality
     static __device__ QP_FN void epilogue(int b, int status, int total_iters) {
         QP_CTX
@@ -2210,19 +2285,16 @@ template <int TEAM> static __device__ __forceinline__ void qp_solve_one(const QP
     int iters = 0, total_iters = 0;
     PROF_T0
     if (status != ST_CAPACITY) {
+        bool fell_back = false;  // the kept working set could not be refactorised: the cold start below is the recovery attempt
         if (mode == MODE_HOT_VARIED) {
-            if (QPT<TEAM>::refactorise()) mode = MODE_COLD;  // projected Hessian of the kept set not PD: cold start
+            if (QPT<TEAM>::refactorise()) { mode = MODE_COLD; fell_back = true; }  // projected Hessian of the kept set not PD
             else QPT<TEAM>::drift_correction();
         }
         if (mode == MODE_COLD) QPT<TEAM>::cold_start_state();
         status = QPT<TEAM>::homotopy(A.max_iter, iters);
         total_iters += iters;
-        if (status != ST_OPTIMAL && status != ST_CAPACITY && mode != MODE_COLD) {
-            // one-retry recovery of handle_error (src/qpOASESInterface.cpp:746-754): plain re-init
-            QPT<TEAM>::cold_start_state();
-            status = QPT<TEAM>::homotopy(A.max_iter, iters);
-            total_iters += iters;
-        }
+        if (status != ST_CAPACITY && ((status != ST_OPTIMAL && !fell_back) || (A.flags & FLAG_FORCE_GUESS)))
+            status = QPT<TEAM>::handle_error(status, mode == MODE_COLD, A.max_iter, iters, total_iters);
     }
     if (status == ST_CAPACITY) {  // left to the rescue launch (full capacity), which restarts from the pre-solve state
         if (lane == 0) { A.status[b] = ST_CAPACITY; A.iters[b] = 0; if (A.ncap) A.caplist[atomicAdd(A.ncap, 1)] = b; }
@@ -2316,18 +2388,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) qp_solve_large_kernel(const __
     int iters = 0, total_iters = 0, status;
     const int lane = tid;
     PROF_T0
+    bool fell_back = false;
     if (mode == MODE_HOT_VARIED) {
-        if (S::refactorise()) mode = MODE_COLD;
+        if (S::refactorise()) { mode = MODE_COLD; fell_back = true; }
         else S::drift_correction();
     }
     if (mode == MODE_COLD) S::cold_start_state();
     status = S::homotopy(A.max_iter, iters);
     total_iters += iters;
-    if (status != ST_OPTIMAL && mode != MODE_COLD) {
-        S::cold_start_state();
-        status = S::homotopy(A.max_iter, iters);
-        total_iters += iters;
-    }
+    if ((status != ST_OPTIMAL && !fell_back) || (A.flags & FLAG_FORCE_GUESS))
+        status = S::handle_error(status, mode == MODE_COLD, A.max_iter, iters, total_iters);
     PROF_ADD(PR_TOTAL);
     S::epilogue(b, status, total_iters);
     PROF_ADD(PR_EPILOGUE);

@@ -59,13 +59,17 @@ def random_l1_qp(rng, n, m, convex=True, rho=None, dens=1.0):
     return dict(nV=nV, nC=nC, n=n, m=m, H=H, A=A, g=g, lb=lb, ub=ub, lbA=lbA, ubA=ubA)
 
 
-def oracle_solve(orc, p, is_lp=False, max_iter=1000, Acsc=None, Hcsc=None):
+def oracle_solve(orc, p, is_lp=False, max_iter=1000, Acsc=None, Hcsc=None, force_error_branch=False):
     """Solve one QP with the CPU oracle; returns dict(x,y,obj,iters,status,wb,wc)."""
     Acsc = csc(p["A"]) if Acsc is None else Acsc
     Hcsc = (None if is_lp else csc(p["H"])) if Hcsc is None else Hcsc
     s = orc.OracleQP(p["nV"], p["nC"], max_iter=max_iter)
     st = s.init(Hcsc, p["g"], Acsc, p["lb"], p["ub"], p["lbA"], p["ubA"], is_lp=is_lp)
-    x, y, obj, it = s.solution()
+    it = s.solution()[3]
+    if st != 20 or force_error_branch:  # optimizeQP -> handle_error (src/qpOASESInterface.cpp:160-162, 686-758)
+        st, added = s.handle_error(force_guess=force_error_branch)
+        it += added
+    x, y, obj, _ = s.solution()
     wb, wc = s.working_set()
     return dict(x=x, y=y, obj=obj, iters=it, status=st, wb=wb, wc=wc, solver=s)
 

@@ -115,10 +115,9 @@ class OracleQPInterface:
             else:
                 st = s.hotstart(*args) if mode == "fixed" else s.hotstart_matrices(None if self.is_lp else self.Hv[b], self.Av[b], *args)
                 its = s.solution()[3]
-                fell_back = mode == "varied" and bool(orc.lib().orc_qp_get_fell_back(s.h))
-                if st != 20 and not fell_back:  # one-retry recovery: plain re-init (already done inside when the kept set could not be refactorised)
-                    st = s.init(Hcsc, args[0], Acsc, *args[1:], is_lp=self.is_lp)
-                    its += s.solution()[3]
+            if st != 20:  # handle_error (src/qpOASESInterface.cpp:686-758), after an init as well as after a hot start
+                st, added = s.handle_error()
+                its += added
             self.inited[b] = (st == 20)
             x, y, obj, _ = s.solution()
             self.x[b], self.y[b], self.obj[b], self.status[b], self.iters[b] = x, y, obj, st, its

@@ -199,3 +199,27 @@ def test_randomised_l0_stress(gpu_lib):
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "l0_stress.py"), "25", "11"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert " 0 mismatches" in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("n", [1, 7, 32, 69, 200])
+def test_batched_vector_ops_bit_exact(gpu_lib, n):
+    """Row A2: batched Vector::getOneNorm / getInfNorm / times and the in-place elementwise operations (src/Vector.cpp:94-135,
+    174-184, 237-251) through the C ABI; sums in the reference's index order -> bit-identical with a sequential evaluation."""
+    import ctypes as C
+    rng = np.random.default_rng(n)
+    B = 1000
+    x = rng.standard_normal((B, n)) * 10.0 ** rng.integers(-3, 4, size=(B, n))
+    y = rng.standard_normal((B, n))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    out = np.empty(B)
+    # sequential left-to-right sums (np.cumsum adds in index order)
+    assert gpu_lib.sqpb200_vector_reduce(0, 0, B, n, p(x), None, p(out), capi.LOC_HOST, None) == 0
+    assert np.array_equal(out, np.cumsum(np.abs(x), axis=1)[:, -1])
+    assert gpu_lib.sqpb200_vector_reduce(0, 1, B, n, p(x), None, p(out), capi.LOC_HOST, None) == 0
+    assert np.array_equal(out, np.abs(x).max(axis=1))
+    assert gpu_lib.sqpb200_vector_reduce(0, 2, B, n, p(x), p(y), p(out), capi.LOC_HOST, None) == 0
+    assert np.array_equal(out, np.cumsum(x * y, axis=1)[:, -1])
+    for op, want in ((0, x + y), (1, x - y), (2, y - x), (3, x + 0.25), (4, y), (5, x * 0.25)):
+        z = x.copy()
+        assert gpu_lib.sqpb200_vector_elementwise(0, op, B, n, p(z), p(y), 0.25, capi.LOC_HOST, None) == 0
+        assert np.array_equal(z, want), op

@@ -438,3 +438,57 @@ def test_randomised_parity_stress(gpu_lib):
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "qp_stress.py"), "14", "7"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert " 0 mismatches" in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("team", [0, 32, 1024])
+def test_handle_error_infeasible_branch_forced(gpu_lib, team):
+    """handle_error's infeasible branch (src/qpOASESInterface.cpp:716-729): re-init from the slack-feasible guess
+    x0 = [0; max(0, lbA); -min(0, ubA)].  A feasible l1-penalty QP never reports INFEASIBLE, so the test hook
+    debug_force_error_branch sends every instance through the branch after its first attempt.  The result must be (a) what the
+    oracle's restatement of the same branch gives (bitwise on the warp kernels) and (b) the unique solution of the strictly convex
+    QP, i.e. what the plain cold start found -- the branch is a different path to the same point."""
+    rng = np.random.default_rng(515 + team)
+    n, m, B = 6, 5, 24
+    base = H.random_l1_qp(rng, n, m, convex=True, dens=0.8)
+    nV, nC = base["nV"], base["nC"]
+    Ac, Hc = H.csc(base["A"]), H.csc(base["H"])
+    g = np.tile(base["g"], (B, 1)); g[:, :n] += rng.standard_normal((B, n))
+    t = lambda v: np.ascontiguousarray(np.tile(v, (B, 1)))
+    lb, ub, lbA, ubA = t(base["lb"]), t(base["ub"]), t(base["lbA"]), t(base["ubA"])
+    shift = 0.5 * rng.standard_normal((B, m))
+    lbA = np.where(lbA > -1e17, lbA + shift, lbA); ubA = np.where(ubA < 1e17, ubA + shift, ubA)
+    s = r.CudaQPInterface(nV=nV, nC=nC, qptype=r.QPType.QP, batch=B, team_size=team, debug_force_error_branch=True)
+    s.set_csc(capi.MAT_A, *Ac); s.set_csc(capi.MAT_H, *Hc)
+    s.set_g(g); s.set_lb(lb); s.set_ub(ub); s.set_lbA(lbA); s.set_ubA(ubA)
+    s.optimizeQP()
+    assert (s.get_status() == 20).all() and s.test_optimality().all()
+    x = s.get_optimal_solution()
+    y = np.concatenate([s.get_multipliers_bounds(), s.get_multipliers_constr()], axis=1)
+    it = s.get_iterations()
+    for b in range(B):
+        p = dict(nV=nV, nC=nC, g=g[b], lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b])
+        o = H.oracle_solve(orc, p, Acsc=Ac, Hcsc=Hc, force_error_branch=True)
+        plain = H.oracle_solve(orc, p, Acsc=Ac, Hcsc=Hc)
+        assert o["status"] == 20
+        if team != 1024:
+            assert int(it[b]) == o["iters"] and np.array_equal(x[b], o["x"]) and np.array_equal(y[b], o["y"])
+        assert relerr(x[b], plain["x"]) <= RTOL and relerr(y[b], plain["y"]) <= 10 * RTOL
+        assert o["iters"] > plain["iters"]  # both attempts are counted (Stats::qp_iter, :752-753)
+    s.close()
+
+
+def test_failed_cold_start_counts_its_iterations_twice(gpu_lib):
+    """src/qpOASESInterface.cpp:160-162, 746-754: a failed init is followed by handle_error's plain re-init -- the same
+    deterministic solve again -- and the working-set changes of both runs are added to Stats::qp_iter."""
+    q = [f for f in FIX if f["name"] == "QORE_hs107"][0]
+    nV, nC = q["nV"], q["nC"]
+    tile = lambda k, n_: np.array(q[k], dtype=np.float64).reshape(1, n_)
+    A = (q["A_colptr"], q["A_rowidx"], np.array(q["A_val"]))
+    Hc = (q["H_colptr"], q["H_rowidx"], np.array(q["H_val"]))
+    s = solve_batch_csc(nV, nC, A, Hc, tile("g", nV), tile("lb", nV), tile("ub", nV), tile("lbA", nC), tile("ubA", nC), team_size=32)
+    so = orc.OracleQP(nV, nC)
+    st = so.init(Hc, q["g"], A, q["lb"], q["ub"], q["lbA"], q["ubA"])
+    single = so.solution()[3]
+    assert st != 20 and int(s.get_status()[0]) == st
+    assert int(s.get_iterations()[0]) == 2 * single
+    s.close()

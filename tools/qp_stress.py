@@ -51,9 +51,9 @@ for case in range(ncase):
                 else:
                     so = o.hotstart(g[b], lb[b], ub[b], lbA[b], ubA[b]) if step < 3 else o.hotstart_matrices(None if is_lp else Hv[b], Av[b], g[b], lb[b], ub[b], lbA[b], ubA[b])
                     ito = o.solution()[3]
-                    if so != 20 and not (step == 3 and orc.lib().orc_qp_get_fell_back(o.h)):
-                        so = o.init(None if is_lp else (Hc[0], Hc[1], Hv[b]), g[b], (Ac[0], Ac[1], Av[b]), lb[b], ub[b], lbA[b], ubA[b], is_lp=is_lp)
-                        ito += o.solution()[3]
+                if so != 20:  # handle_error, after an init as well as after a hot start
+                    so, added = o.handle_error()
+                    ito += added
                 xo, yo, _, _ = o.solution()
                 tot += 1
                 if team != 1024:  # warp kernel: bit for bit

@@ -17,6 +17,8 @@ program as a CUDA kernel body (one thread per instance) for a device-resident ou
 import math
 import os
 
+import re
+
 import numpy as np
 
 from .sqp_types import NLPInfo
@@ -127,6 +129,8 @@ class Graph:
         ca = self.cval(a)
         if ca is not None:
             try:
+                if op == "ncdf":
+                    return self.const(0.5 * math.erfc(-ca * 0.7071067811865476))
                 return self.const(getattr(math, {"abs": "fabs"}.get(op, op))(ca))
             except (ValueError, OverflowError):
                 pass
@@ -200,6 +204,8 @@ class Graph:
                 r = self.neg(self.div(du, self.un("sqrt", self.sub(self.ONE, self.mul(u, u)))))
             elif op == "abs":
                 r = self.mul(self.div(u, a), du)
+            elif op == "ncdf":  # standard normal distribution function: Phi'(u) = exp(-u^2/2) / sqrt(2 pi)
+                r = self.mul(self.mul(self.const(0.3989422804014327), self.un("exp", self.mul(self.const(-0.5), self.mul(u, u)))), du)
             else:
                 raise NotImplementedError(op)
         memo[key] = r
@@ -236,9 +242,22 @@ class _Tokens:
         return self.pos < len(self.lines)
 
 
-def _read_expr(tok, G, defined):
+# Imported functions (F segments).  The reference's HS models declare one, `myerf` (hs068, hs069), implemented by an AMPL function
+# library that is not part of the reference; Hock-Schittkowski 68 / 69 define it as the standard normal distribution function
+# Phi (with it the tabulated solution of hs068 satisfies x3 = 2 Phi(-x2) to all printed digits).
+_IMPORTED = {"myerf": "ncdf"}
+
+
+def _read_expr(tok, G, defined, funcs=None):
     ln = tok.next().strip()
     k = ln[0]
+    if k == "f":
+        idx, nargs = (int(t) for t in ln[1:].split())
+        args = [_read_expr(tok, G, defined, funcs) for _ in range(nargs)]
+        name = (funcs or {}).get(idx)
+        if name not in _IMPORTED or nargs != 1:
+            raise NotImplementedError("imported function %r with %d arguments" % (name, nargs))
+        return G.un(_IMPORTED[name], args[0])
     if k == "n":
         return G.const(float(ln[1:]))
     if k == "v":
@@ -247,14 +266,14 @@ def _read_expr(tok, G, defined):
     if k == "o":
         op = int(ln[1:])
         if op in _BIN:
-            a = _read_expr(tok, G, defined)
-            b = _read_expr(tok, G, defined)
+            a = _read_expr(tok, G, defined, funcs)
+            b = _read_expr(tok, G, defined, funcs)
             return getattr(G, _BIN[op])(a, b)
         if op in _UN:
-            return G.un(_UN[op], _read_expr(tok, G, defined))
+            return G.un(_UN[op], _read_expr(tok, G, defined, funcs))
         if op == 54:
             cnt = int(tok.next().strip())
-            return G.sum([_read_expr(tok, G, defined) for _ in range(cnt)])
+            return G.sum([_read_expr(tok, G, defined, funcs) for _ in range(cnt)])
         raise NotImplementedError("nl opcode o%d" % op)
     raise NotImplementedError("nl expression token %r" % ln)
 
@@ -291,8 +310,7 @@ class NLModel:
         hdr = [tok.next().split() for _ in range(10)]
         self.name = os.path.splitext(os.path.basename(path))[0]
         self.n, self.m, self.n_obj = int(hdr[1][0]), int(hdr[1][1]), int(hdr[1][2])
-        if int(hdr[5][1]) != 0:
-            raise NotImplementedError("imported functions (F segments)")
+        funcs = {}
         self.nzJ = int(hdr[7][0])
         G = self.G = Graph()
         n, m = self.n, self.m
@@ -308,14 +326,16 @@ class NLModel:
         while tok.more():
             ln = tok.next().strip()
             k, rest = ln[0], ln[1:].split()
-            if k == "C":
-                self.con_nl[int(rest[0])] = _read_expr(tok, G, defined)
+            if k == "F":
+                funcs[int(rest[0])] = rest[3]
+            elif k == "C":
+                self.con_nl[int(rest[0])] = _read_expr(tok, G, defined, funcs)
             elif k == "O":
                 if int(rest[0]) == 0:
                     self.obj_sense = int(rest[1])
-                    self.obj_nl = _read_expr(tok, G, defined)
+                    self.obj_nl = _read_expr(tok, G, defined, funcs)
                 else:
-                    _read_expr(tok, G, defined)
+                    _read_expr(tok, G, defined, funcs)
             elif k == "V":
                 idx, nlin = int(rest[0]), int(rest[1])
                 e = G.ZERO
@@ -323,7 +343,7 @@ class NLModel:
                     f = tok.next().split()
                     j = int(f[0])
                     e = G.add(e, G.mul(G.const(float(f[1])), defined[j] if j in defined else G.var(j)))
-                defined[idx] = G.add(e, _read_expr(tok, G, defined))
+                defined[idx] = G.add(e, _read_expr(tok, G, defined, funcs))
             elif k == "r":
                 self.c_l, self.c_u = _read_bounds(tok, m)
             elif k == "b":
@@ -359,9 +379,13 @@ class NLModel:
 
 _NP_FUN = {"sqrt": "np.sqrt", "sin": "np.sin", "cos": "np.cos", "log": "np.log", "exp": "np.exp", "abs": "np.abs", "tan": "np.tan",
            "atan": "np.arctan", "tanh": "np.tanh", "sinh": "np.sinh", "cosh": "np.cosh", "log10": "np.log10", "acos": "np.arccos",
-           "asin": "np.arcsin"}
+           "asin": "np.arcsin", "ncdf": "_ncdf"}
 _C_FUN = {"abs": "fabs"}
 _INFIX = {"add": "+", "sub": "-", "mul": "*", "div": "/"}
+_MATH_NAMES = ("pow", "sqrt", "sin", "cos", "log", "exp", "tan", "atan", "tanh", "sinh", "cosh", "log10", "acos", "asin")
+_MATH_CALL = re.compile(r"(?<![A-Za-z0-9_])(%s)\(" % "|".join(_MATH_NAMES))
+_MATH_WRAPPERS = (["static __device__ __noinline__ double nl_pow(double a, double b) { return pow(a, b); }"] +
+                  ["static __device__ __noinline__ double nl_%s(double a) { return %s(a); }" % (f, f) for f in _MATH_NAMES if f != "pow"])
 
 
 def _emit(G, roots, lang):
@@ -417,6 +441,64 @@ def _emit(G, roots, lang):
     return lines, name
 
 
+def _emit_chunked_cuda(G, roots, tag, chunk, n):
+    """The straight-line program of `roots` cut into consecutive pieces of `chunk` statements, each a __noinline__ device
+    function: NVRTC's time grows much faster than linearly with the length of one function (hs105, 20 k statements in one
+    kernel: 47 s), while the sum over pieces of a few thousand statements stays linear.  Values that cross a piece boundary go
+    through a per-thread scratch array T (local memory); evaluation order and arithmetic are exactly those of the one-piece
+    program.  Returns (source lines of the device functions, body lines of the kernel after `b` / bounds check, name_of(root))."""
+    lines, name = _emit(G, roots, "c")
+    # transcendental functions through __noinline__ wrappers (emitted once by cuda_source): inlined, every pow() is a few hundred
+    # instructions and the kernels of hs025 / hs105 reach 5 MB of SASS
+    lines = [_MATH_CALL.sub(lambda mo: "nl_" + mo.group(1) + "(", ln) for ln in lines]
+    order = []  # compute nodes in emission order: _emit names them t<node id>
+    for ln in lines:
+        order.append(int(ln.split()[2][1:]))
+    pos = {a: i // chunk for i, a in enumerate(order)}
+    npieces = (len(order) + chunk - 1) // chunk
+    last_use = {}  # node -> last piece that reads it (npieces = the kernel epilogue)
+    for a in order:
+        t = G.nodes[a]
+        for k in t[1:]:
+            if k in pos and pos[a] > last_use.get(k, -1):
+                last_use[k] = pos[a]
+    for r_ in roots:
+        if r_ in pos:
+            last_use[r_] = npieces
+    cross = [a for a in order if last_use.get(a, -1) > pos[a]]
+    tidx = {a: i for i, a in enumerate(cross)}
+    funcs, calls = [], []
+    for pc in range(npieces):
+        seg = order[pc * chunk:(pc + 1) * chunk]
+        segset = set(seg)
+        ins, xs = [], set()
+        for a in seg:
+            for k in G.nodes[a][1:]:
+                tk = G.nodes[k]
+                if tk[0] == "var":
+                    xs.add(tk[1])
+                elif k in pos and k not in segset and k not in ins:
+                    ins.append(k)
+        fn = "nlp_piece_%s_%d" % (tag, pc)
+        funcs.append("static __device__ __noinline__ void %s(const double* __restrict__ xv, double* __restrict__ T) {" % fn)
+        funcs += ["    const double x%d = xv[%d];" % (j, j) for j in sorted(xs)]
+        funcs += ["    const double t%d = T[%d];" % (k, tidx[k]) for k in ins]
+        funcs += ["    " + lines[i] for i in range(pc * chunk, min((pc + 1) * chunk, len(order)))]
+        funcs += ["    T[%d] = t%d;" % (tidx[a], a) for a in seg if a in tidx]
+        funcs += ["}", ""]
+        calls.append("    %s(xv, T);" % fn)
+    body = ["    double xv[%d];" % max(n, 1), "    double T[%d];" % max(len(cross), 1)]
+    body += ["    for (int j = 0; j < %d; j++) xv[j] = x[(size_t)b * %d + j];" % (n, n)] + calls
+    rname = {}
+    for r_ in roots:
+        if r_ in tidx:
+            rname[r_] = "T[%d]" % tidx[r_]
+        else:
+            nm = name[r_]
+            rname[r_] = ("xv[%s]" % nm[1:]) if G.nodes[r_][0] == "var" else nm
+    return funcs, body, rname
+
+
 class AmplNLP:
     """The SQPTNLP-shaped view of an NLModel, batched over instances (x is [batch][n])."""
 
@@ -462,7 +544,7 @@ class AmplNLP:
     # ---- code generation
     def _compile(self):
         G, n, m = self.model.G, self.n, self.m
-        src = ["import numpy as np", ""]
+        src = ["import numpy as np", "from scipy.special import ndtr as _ncdf", ""]
 
         def fun(name, roots, extra_args, body_tail):
             lines, nm = _emit(G, roots, "py")
@@ -501,13 +583,40 @@ class AmplNLP:
         exec(compile(self.source, "<nl:%s>" % self.name, "exec"), ns)
         self._f, self._c, self._g, self._j, self._h = ns["eval_f"], ns["eval_c"], ns["eval_grad"], ns["eval_jac"], ns["eval_hess"]
 
-    def cuda_source(self):
+    CUDA_PIECE = 1500  # statements per device function of the chunked form (large DAGs)
+
+    def cuda_source(self, piece=None):
         """The same straight-line programs as two CUDA kernels, one thread per instance, instance-major outputs:
         nlp_eval_fc (f, c at trial points) and nlp_eval_all (f, c, grad f, Jacobian and Lagrangian-Hessian triplet
-        values).  Compiled at run time by sqpb200_nlp_compile (NVRTC, sm_100a, --fmad=false)."""
+        values).  Compiled at run time by sqpb200_nlp_compile (NVRTC, sm_100a, --fmad=false).  Programs longer than `piece`
+        statements are cut into __noinline__ device functions of that length (_emit_chunked_cuda)."""
         G, n, m = self.model.G, self.n, self.m
         zJ, zH = len(self.jac_nodes), len(self._hess_terms)
         hroots = [d2 for terms in self._hess_terms for _, d2 in terms]
+        piece = self.CUDA_PIECE if piece is None else piece
+        ncompute = sum(1 for t in G.nodes if t[0] not in ("const", "var"))
+        if ncompute > piece:
+            head = ["    const int b = blockIdx.x * blockDim.x + threadIdx.x;", "    if (b >= B) return;"]
+            f1, b1, n1 = _emit_chunked_cuda(G, [self.f_node] + self.c_nodes, "fc", piece, n)
+            f2, b2, n2 = _emit_chunked_cuda(G, [self.f_node] + self.c_nodes + self.grad_nodes + self.jac_nodes + hroots, "all", piece, n)
+            src = ["// generated by restartsqp_b200/nl_reader.py from %s.nl (chunked: %d statements per device function)" % (self.name, piece)]
+            src += ["static __device__ __forceinline__ double ncdf(double u) { return 0.5 * erfc(-u * 0.7071067811865476); }"]
+            src += _MATH_WRAPPERS + [""] + f1 + f2
+            src += ['extern "C" __global__ void nlp_eval_fc(int B, const double* __restrict__ x, double* __restrict__ f, double* __restrict__ c) {']
+            src += head + b1 + ["    f[b] = %s;" % n1[self.f_node]]
+            src += ["    c[(size_t)b * %d + %d] = %s;" % (m, i, n1[a]) for i, a in enumerate(self.c_nodes)] + ["}", ""]
+            src += ['extern "C" __global__ void nlp_eval_all(int B, const double* __restrict__ x, const double* __restrict__ lam,',
+                    "                                        double* __restrict__ f, double* __restrict__ c, double* __restrict__ grad,",
+                    "                                        double* __restrict__ jac, double* __restrict__ hess) {"]
+            src += head + b2 + ["    f[b] = %s;" % n2[self.f_node]]
+            src += ["    c[(size_t)b * %d + %d] = %s;" % (m, i, n2[a]) for i, a in enumerate(self.c_nodes)]
+            src += ["    grad[(size_t)b * %d + %d] = %s;" % (n, i, n2[a]) for i, a in enumerate(self.grad_nodes)]
+            src += ["    jac[(size_t)b * %d + %d] = %s;" % (zJ, i, n2[a]) for i, a in enumerate(self.jac_nodes)]
+            for e, terms in enumerate(self._hess_terms):
+                parts = [n2[d2] if k == 0 else "lam[(size_t)b * %d + %d] * %s" % (m, k - 1, n2[d2]) for k, d2 in terms]
+                src.append("    hess[(size_t)b * %d + %d] = %s;" % (zH, e, " + ".join(parts)))
+            src.append("}")
+            return "\n".join(src)
 
         def body(roots):
             lines, nm = _emit(G, roots, "c")
@@ -529,6 +638,7 @@ class AmplNLP:
             return out, nm
 
         src = ["// generated by restartsqp_b200/nl_reader.py from %s.nl" % self.name,
+               "static __device__ __forceinline__ double ncdf(double u) { return 0.5 * erfc(-u * 0.7071067811865476); }",
                'extern "C" __global__ void nlp_eval_fc(int B, const double* __restrict__ x, double* __restrict__ f, double* __restrict__ c) {']
         out, nm = body([self.f_node] + self.c_nodes)
         src += out + ["    f[b] = %s;" % nm[self.f_node]]
@@ -568,6 +678,7 @@ class AmplNLP:
             return ["    const double x%d = x[%d];" % (j, j) for j in xs] + ["    " + ln for ln in lines], nm
 
         src = ["#include <math.h>", "/* generated by restartsqp_b200/nl_reader.py from %s.nl */" % self.name,
+               "static double ncdf(double u) { return 0.5 * erfc(-u * 0.7071067811865476); }",
                "void nlp_fc(const double* x, double* f, double* c) {"]
         out, nm = body([self.f_node] + self.c_nodes)
         src += out + ["    *f = %s;" % nm[self.f_node]] + ["    c[%d] = %s;" % (i, nm[a]) for i, a in enumerate(self.c_nodes)] + ["}", ""]
@@ -626,7 +737,7 @@ class DeviceNLP:
     (Eval_f_c for trial points, Eval_all for accepted points).  There is no CPU fallback: constructing it without a CUDA
     device raises."""
 
-    MAX_NODES = 12000  # NVRTC time grows faster than linearly with the length of the straight-line kernel (hs105: 20 k nodes, 47 s)
+    MAX_NODES = 200000  # large DAGs are compiled in pieces (AmplNLP.cuda_source); hs092, the largest HS model, has 121 k nodes
 
     def __init__(self, path, device=0, max_nodes=None):
         import ctypes as C

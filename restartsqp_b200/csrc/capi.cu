@@ -299,7 +299,13 @@ static int run_assembly(sqpb200_handle h, cudaStream_t stream, int nmat, const i
         cudaEventRecord(e0, stream);
         int Pmax = 1;
         for (int m = 0; m < nmat; m++) Pmax = std::max(Pmax, pad_off[m + 1] - pad_off[m]);
-        if (Pmax <= ASM_WARP_KEYS && nmat >= 8)  // many small matrices: one warp each, eight per CTA
+        if (Pmax <= 256 && nmat >= 8) {  // many small matrices: one warp each, keys in registers (shuffle network)
+            const int grid = (nmat + 7) / 8;
+            if (Pmax <= 32) csc_assemble_reg_kernel<1><<<grid, 256, 0, stream>>>(nmat, dseg, dncol, dcpoff, drow, dcol, dcolptr, drowidx, dorder);
+            else if (Pmax <= 64) csc_assemble_reg_kernel<2><<<grid, 256, 0, stream>>>(nmat, dseg, dncol, dcpoff, drow, dcol, dcolptr, drowidx, dorder);
+            else if (Pmax <= 128) csc_assemble_reg_kernel<4><<<grid, 256, 0, stream>>>(nmat, dseg, dncol, dcpoff, drow, dcol, dcolptr, drowidx, dorder);
+            else csc_assemble_reg_kernel<8><<<grid, 256, 0, stream>>>(nmat, dseg, dncol, dcpoff, drow, dcol, dcolptr, drowidx, dorder);
+        } else if (Pmax <= ASM_WARP_KEYS && nmat >= 8)  // up to 512 keys: the network in the warp's shared-memory slice
             csc_assemble_warp_kernel<<<(nmat + 7) / 8, 256, (size_t)8 * Pmax * 8, stream>>>(nmat, Pmax, dseg, dncol, dcpoff, drow, dcol, dpad, dcolptr, drowidx, dorder);
         else
             csc_assemble_kernel<<<nmat, 256, 0, stream>>>(nmat, dseg, dncol, dcpoff, drow, dcol, dpad, dscr, dcolptr, drowidx, dorder);

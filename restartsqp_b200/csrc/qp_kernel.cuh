@@ -774,17 +774,19 @@ struct QPT {
     //   qa = q[0]; for j: qb = q[j+1]; q[j] = c qa - s qb; qa = s qa + c qb;  q[cnt-1] = qa
     // Warp w owns 32-row groups; a group moves through shared memory in 32-column tiles (coalesced loads and stores, the
     // chain runs lane-per-row out of the tile).
+    // The chain runs over the logical columns j = 0 .. cnt-1, stored at column base + dir * j (dir = -1: the right-to-left
+    // chains of the removals, whose rotation i acts on (c, c+1) with c decreasing: same recurrence with (c_j, -s_j)).
     static __device__ __forceinline__ void rot_rows(double* M, int ld, int nP, int cnt, const double* cs, const double* sn, int rank = 0,
-                                                    int ncta = 1) {
+                                                    int ncta = 1, int base = 0, int dir = 1) {
         if (cnt <= 0) return;
         const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
         double* tile = qp_smem + (size_t)warp * (32 * 33);
         for (int r0 = (warp + (TEAM / 32) * rank) * 32; r0 < nP; r0 += TEAM * ncta) {
             const int nr = (nP - r0 < 32) ? nP - r0 : 32;
-            double qa = (l < nr) ? M[(size_t)(r0 + l) * ld] : 0.0;
+            double qa = (l < nr) ? M[(size_t)(r0 + l) * ld + base] : 0.0;
             for (int jt = 0; jt < cnt; jt += 32) {
                 // originals of columns jt+1 .. jt+32
-                for (int rr = 0; rr < nr; rr++) { const int j = jt + 1 + l; if (j < cnt) tile[rr * 33 + l] = M[(size_t)(r0 + rr) * ld + j]; }
+                for (int rr = 0; rr < nr; rr++) { const int j = jt + 1 + l; if (j < cnt) tile[rr * 33 + l] = M[(size_t)(r0 + rr) * ld + base + dir * j]; }
                 __syncwarp();
                 if (l < nr) {
                     const int cmax = (cnt - jt < 32) ? cnt - jt : 32;
@@ -798,7 +800,7 @@ struct QPT {
                     }
                 }
                 __syncwarp();
-                for (int rr = 0; rr < nr; rr++) { const int j = jt + l; if (j < cnt) M[(size_t)(r0 + rr) * ld + j] = tile[rr * 33 + l]; }
+                for (int rr = 0; rr < nr; rr++) { const int j = jt + l; if (j < cnt) M[(size_t)(r0 + rr) * ld + base + dir * j] = tile[rr * 33 + l]; }
                 __syncwarp();
             }
         }
@@ -972,18 +974,34 @@ struct QPT {
         const pidx *Hp = pat + sA.pHp, *Hi = pat + sA.pHi;
         const bool has_H = sA.has_H && !sA.is_lp;
         PROF_T0
-        // A: W[p][b] = (H z_b)[FR[p]], entries split over the cluster
-        for (int e = rank * TEAM + lane; e < nFR * nZ; e += cs * TEAM) {
-            const int p = e / nZ, b = e - p * nZ;
-            double s = 0.0;
-            if (has_H) {
-                const int c = FR[p], e1 = Hp[c + 1];
-                for (int h = Hp[c]; h < e1; h++) {
-                    const int pr = posFR[Hi[h]];
-                    if (pr >= 0) s += Hv[h] * Q[(size_t)pr * ld + b];
+        // A: W[p][b] = (H z_b)[FR[p]], entries split over the cluster; a thread owns four columns b, b + 32, b + 64, b + 96 of
+        // one row p so that every index / value load of H's column is shared by four outputs (lanes still walk b: coalesced)
+        {
+            const int nb4 = (nZ + 127) / 128;  // groups of 128 columns
+            const int l32 = lane & 31;
+            for (int e = rank * (TEAM / 32) + (lane >> 5); e < nFR * nb4; e += cs * (TEAM / 32)) {
+                const int p = e / nb4, b0 = (e - p * nb4) * 128 + l32;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                if (has_H) {
+                    const int c = FR[p], e1 = Hp[c + 1];
+                    for (int h = Hp[c]; h < e1; h++) {
+                        const int pr = posFR[Hi[h]];
+                        if (pr >= 0) {
+                            const double hv = Hv[h];
+                            const double* q = Q + (size_t)pr * ld + b0;
+                            if (b0 < nZ) s0 += hv * q[0];
+                            if (b0 + 32 < nZ) s1 += hv * q[32];
+                            if (b0 + 64 < nZ) s2 += hv * q[64];
+                            if (b0 + 96 < nZ) s3 += hv * q[96];
+                        }
+                    }
                 }
+                double* w = W + (size_t)p * ld + b0;
+                if (b0 < nZ) w[0] = s0;
+                if (b0 + 32 < nZ) w[32] = s1;
+                if (b0 + 64 < nZ) w[64] = s2;
+                if (b0 + 96 < nZ) w[96] = s3;
             }
-            W[(size_t)p * ld + b] = s;
         }
         large_sync();
         PROF_ADD(PR_REFAC_W);
@@ -1045,7 +1063,7 @@ struct QPT {
         const int oM = vh[8], nP = vh[9], i0 = vh[10], i1 = vh[11], oA = vh[12], oB = vh[13], flag = vh[14];
         if (cmd == OP_COLSUMS) col_sums(slice + oM, ld, nP, i0, i1, slice + oA, slice + oB, flag ? -1.0 : 1.0, rank, cs);
         else if (cmd == OP_ROWSUMS) row_sums(slice + oM, ld, nP, i0, i1, slice + oA, slice + oB, (flag & 1) ? FR_ : nullptr, (flag & 2) != 0, rank, cs);
-        else if (cmd == OP_ROTROWS) rot_rows(slice + oM, ld, nP, i0, slice + oA, slice + oB, rank, cs);
+        else if (cmd == OP_ROTROWS) rot_rows(slice + oM, ld, nP, i0, slice + oA, slice + oB, rank, cs, i1, flag ? -1 : 1);
     }
     static __device__ __forceinline__ void dist_op(int cmd, int oM, int nP, int i0, int i1, int oA, int oB, int flag) {
         QP_CTX
@@ -1066,10 +1084,10 @@ struct QPT {
         if (sClusterSize > 1 && (long long)nP * (j1 - j0) >= DIST_MIN_ELEMS) dist_op(OP_ROWSUMS, oM, nP, j0, j1, oV, oOut, (via_FR ? 1 : 0) | (accumulate ? 2 : 0));
         else row_sums(slice + oM, ld, nP, j0, j1, slice + oV, slice + oOut, via_FR ? FR_ : nullptr, accumulate);
     }
-    static __device__ __forceinline__ void rot_rows_auto(int oM, int nP, int cnt, int oC, int oS_) {
+    static __device__ __forceinline__ void rot_rows_auto(int oM, int nP, int cnt, int oC, int oS_, int base = 0, int dir = 1) {
         QP_CTX
-        if (sClusterSize > 1 && (long long)nP * cnt >= DIST_MIN_ELEMS) dist_op(OP_ROTROWS, oM, nP, cnt, 0, oC, oS_, 0);
-        else rot_rows(slice + oM, ld, nP, cnt, slice + oC, slice + oS_);
+        if (sClusterSize > 1 && (long long)nP * cnt >= DIST_MIN_ELEMS) dist_op(OP_ROTROWS, oM, nP, cnt, base, oC, oS_, dir < 0 ? 1 : 0);
+        else rot_rows(slice + oM, ld, nP, cnt, slice + oC, slice + oS_, 0, 1, base, dir);
     }
     static __device__ QP_FN int recompute_R_blocked() {
         QP_CTX
@@ -1103,7 +1121,7 @@ struct QPT {
             // strip product: partial sums over k = sl, sl + 8, ... < i0
             double s = 0.0;
             if (c < nb) {
-#pragma unroll 8
+#pragma unroll 16
                 for (int k = sl; k < i0; k += 8) s += R_(k, i0 + c) * z[k];
             }
             red[sl * LT_NB + c] = s;
@@ -1357,18 +1375,27 @@ struct QPT {
                 T_(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
                 T_(ii, cL + 1) = sn * ta + cs * tb;
             }
+#ifndef QP_EXACT
+            if constexpr (TEAM > 32) {  // Q is rotated afterwards, all rotations in one coalesced pass (rot_rows, right to left)
+                if (lane == 0) { V_(t2)[i - k - 1] = cs; V_(t3)[i - k - 1] = -sn; }
+            } else
+#endif
+            {
             QP_U1 for (int p = lane; p < nFR; p += TEAM) {
                 double qa = Q[p * ld + cL], qb = Q[p * ld + cL + 1];
                 Q[p * ld + cL] = cs * qa - sn * qb;
                 Q[p * ld + cL + 1] = sn * qa + cs * qb;
             }
+            }
             SYNC();
         }
-        // shift rows k+1.. up by one (row i -> i-1): sequential over rows, lanes over columns
-        QP_U1 for (int i = k + 1; i < nAC; i++) {
-            QP_U1 for (int j = lane; j < nFR; j += TEAM) T_(i - 1, j) = T_(i, j);
-            SYNC();
-        }
+#ifndef QP_EXACT
+        if constexpr (TEAM > 32) rot_rows_auto(sA.oQ, nFR, nAC - k, sA.ot2, sA.ot3, nFR - 1 - k, -1);
+#endif
+        // shift rows k+1.. up by one (row i -> i-1): every thread moves its own columns, so no barrier between the rows
+        QP_U1 for (int j = lane; j < nFR; j += TEAM)
+            QP_U1 for (int i = k + 1; i < nAC; i++) T_(i - 1, j) = T_(i, j);
+        SYNC();
         if (lane == 0) {
             QP_U1 for (int i = k + 1; i < nAC; i++) { AC[i - 1] = AC[i]; posAC[AC[i - 1]] = (short)(i - 1); }
             sC_[c] = 0; posAC[c] = -1; hdr[1] = nAC - 1;
@@ -1473,13 +1500,23 @@ struct QPT {
                 T_(ii, cL) = (ii == i) ? 0.0 : cs * ta - sn * tb;
                 T_(ii, cL + 1) = sn * ta + cs * tb;
             }
+#ifndef QP_EXACT
+            if constexpr (TEAM > 32) {
+                if (lane == 0) { V_(t2)[i] = cs; V_(t3)[i] = -sn; }
+            } else
+#endif
+            {
             QP_U1 for (int p = lane; p < nFR; p += TEAM) {
                 double qa = Q[p * ld + cL], qb = Q[p * ld + cL + 1];
                 Q[p * ld + cL] = cs * qa - sn * qb;
                 Q[p * ld + cL + 1] = sn * qa + cs * qb;
             }
+            }
             SYNC();
         }
+#ifndef QP_EXACT
+        if constexpr (TEAM > 32) rot_rows_auto(sA.oQ, nFR, nAC + 1, sA.ot2, sA.ot3, nFR - 1, -1);
+#endif
         return 0;
     }
 

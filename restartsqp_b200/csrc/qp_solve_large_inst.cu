@@ -12,12 +12,15 @@ namespace sqpb200 {
 // CTAs per QP: the largest power of two <= 16 that keeps batch * cluster <= SM count, so that a batch smaller than the GPU still
 // fills it (16 is a non-portable cluster size: opt-in attribute, and a fall-back to 8 if the launch is refused).
 // SQPB200_CLUSTER overrides (1, 2, 4, 8, 16).
-static int cluster_for_batch(int batch) {
+static int cluster_for_batch(int batch, int nV) {
     if (const char* e = getenv("SQPB200_CLUSTER")) { int v = atoi(e); if (v >= 1 && v <= 16 && (v & (v - 1)) == 0) return v; }
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // a cluster barrier costs microseconds, and more with 16 CTAs: the non-portable size only pays at nV >= 2048
+    // (measured: n = 64 runs 8.7 ms with 8 CTAs per QP, 10-12 ms with one, 15-19 ms with 16)
+    const int cap = nV < 64 ? 1 : (nV < 2048 ? 8 : 16);
     int cs = 1;
-    while (cs < 16 && (long long)batch * cs * 2 <= sms) cs *= 2;  // 16 = non-portable cluster size (opt-in below), batch <= 9
+    while (cs < cap && (long long)batch * cs * 2 <= sms) cs *= 2;  // 16 = non-portable cluster size (opt-in below), batch <= 9
     return cs;
 }
 
@@ -26,7 +29,7 @@ cudaError_t launch_qp_solve_large(const QPKernelArgs& a, cudaStream_t stream) {
     qp_solve_large_kernel<QP_CTA><<<a.batch, QP_CTA, 0, stream>>>(a);
     return cudaGetLastError();
 #else
-    int cs = cluster_for_batch(a.batch);
+    int cs = cluster_for_batch(a.batch, a.nV);
     const size_t smem = (size_t)QPT<QP_CTA>::LS_TOTAL * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(qp_solve_large_kernel<QP_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -55,11 +58,11 @@ cudaError_t launch_qp_solve_large(const QPKernelArgs& a, cudaStream_t stream) {
 #endif
 }
 int qp_solve_large_threads() { return QP_CTA; }
-int qp_solve_large_cluster(int batch) {
+int qp_solve_large_cluster(int batch, int nV) {
 #ifdef QP_EXACT
-    (void)batch; return 1;
+    (void)batch; (void)nV; return 1;
 #else
-    return cluster_for_batch(batch);
+    return cluster_for_batch(batch, nV);
 #endif
 }
 }  // namespace sqpb200

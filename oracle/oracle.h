@@ -155,6 +155,11 @@ int orc_qp_solve_batch(int B, int nV, int nC, const int* Hp, const int* Hi, cons
 /* flop counter for the roofline model of SURVEY.md section 8(d) */
 double orc_qp_get_flops(const orc_qp* q);
 int orc_qp_get_max_free(const orc_qp* q);
+/* the FIXED <-> VARIED flip of the matrix status (src/qpOASESInterface.cpp:202-207): init(H, g, A, ..., x_qp, y_qp, &bounds), a
+ * fresh init whose auxiliary QP is built from the previous solution, the previous bound statuses and the sign of the previous
+ * constraint multipliers */
+int orc_qp_reinit(orc_qp* q, const orc_qp_options* opt, const double* H_val, const double* A_val, const double* g,
+                  const double* lb, const double* ub, const double* lbA, const double* ubA);
 /* 1 if the last orc_qp_hotstart_matrices already performed the cold re-init of handle_error (src/qpOASESInterface.cpp:746-754) */
 int orc_qp_get_fell_back(const orc_qp* q);
 

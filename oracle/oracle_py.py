@@ -207,6 +207,13 @@ class OracleQP:
         return self.L.orc_qp_hotstart_matrices(self.h, C.byref(self.opt), _dp(hv), _dp(av), _dp(_f64(g)),
                                                _dp(_f64(lb)), _dp(_f64(ub)), _dp(_f64(lbA)), _dp(_f64(ubA)))
 
+    def reinit(self, H_val, A_val, g, lb, ub, lbA, ubA):
+        """the matrix-status flip of optimizeQP (src/qpOASESInterface.cpp:202-207): init from the previous solution"""
+        hv = None if H_val is None else _f64(H_val)
+        av = None if A_val is None else _f64(A_val)
+        return self.L.orc_qp_reinit(self.h, C.byref(self.opt), _dp(hv), _dp(av), _dp(_f64(g)),
+                                    _dp(_f64(lb)), _dp(_f64(ub)), _dp(_f64(lbA)), _dp(_f64(ubA)))
+
     def solution(self):
         x, y = np.zeros(self.nV), np.zeros(self.nV + self.nC)
         obj, it = C.c_double(0), C.c_int(0)

@@ -762,49 +762,77 @@ static int cold_start(orc_qp* q, const orc_qp_options* opt) {
     return q->status;
 }
 
-/* init(H, g, A, lb, ub, lbA, ubA, nWSR, 0, x0) of handle_error's infeasible branch (src/qpOASESInterface.cpp:716-729, 690-701):
- * primal guess x0 = [0; max(0, lbA); -min(0, ubA)] (the slack-feasible point of the l1-penalty QP), y = 0; working set read
- * off x0 and A x0 with boundTolerance = 1e6*EPS (bounds first, then the constraints in index order, linearly dependent ones
- * left out); auxiliary data relaxed by boundRelaxation; then the homotopy to the real data. */
-static int guess_start(orc_qp* q, const orc_qp_options* opt) {
-    int nV = q->nV, nC = q->nC, o1 = nV - 2 * nC, o2 = nV - nC;
-    const double TOL = 1.0e6 * QP_EPS;
-    q->nFR = 0; q->nAC = 0; q->ramp_offset = 0; q->last_cold = 1;
-    for (int i = 0; i < nV; i++) { q->x[i] = 0.0; q->y[i] = 0.0; }
-    for (int i = 0; i < nC; i++) {
-        q->x[o1 + i] = fmax(0.0, q->lbAN[i]); q->x[o2 + i] = -fmin(0.0, q->ubAN[i]);
-        q->y[nV + i] = 0.0; q->sC[i] = 0; q->posAC[i] = -1;
-    }
-    mulA(q, q->x, q->Ax);
+/* Auxiliary QP of an init from a guess (qpOASES QProblem::solveInitialQP as reached from src/qpOASESInterface.cpp:202-207 and
+ * :716-729): x, y, A x and the wanted bound statuses sB are set by the caller, want[i] is the wanted status of constraint i.
+ * Working set: bounds first, then the constraints in index order, linearly dependent ones left out; auxiliary bounds equal to
+ * x / A x on the active side and relaxed by boundRelaxation elsewhere -- except that a constraint left out for dependence
+ * keeps its wanted side tight ("strongly inactive"); gradient from stationarity; projected Cholesky factor. */
+static int aux_qp_from_guess(orc_qp* q, const int* want) {
+    int nV = q->nV, nC = q->nC;
+    q->nFR = 0; q->nAC = 0; q->ramp_offset = 0;
     for (int i = 0; i < nV; i++) {
         double xi = q->x[i];
-        int st = (xi <= q->lbN[i] + TOL) ? -1 : ((xi >= q->ubN[i] - TOL) ? 1 : 0);
-        q->sB[i] = st; q->posFR[i] = -1;
+        int st = q->sB[i];
+        q->posFR[i] = -1;
         q->lb[i] = (st < 0) ? xi : xi - QP_BOUND_RELAX;
         q->ub[i] = (st > 0) ? xi : xi + QP_BOUND_RELAX;
     }
-    for (int i = 0; i < nC; i++) { q->lbA[i] = q->Ax[i] - QP_BOUND_RELAX; q->ubA[i] = q->Ax[i] + QP_BOUND_RELAX; }
+    for (int i = 0; i < nC; i++) { q->sC[i] = 0; q->posAC[i] = -1; }
     for (int i = 0; i < nV; i++) if (q->sB[i] == 0) { q->FR[q->nFR] = i; q->posFR[i] = q->nFR; q->nFR++; }
     if (q->nFR > q->max_nFR) q->max_nFR = q->nFR;
     for (int i = 0; i < q->nFR; i++)
         for (int j = 0; j < q->nFR; j++) q->Q[(size_t)i * nV + j] = (i == j) ? 1.0 : 0.0;
     for (int i = 0; i < nC; i++) {
         double ax = q->Ax[i];
-        int st = (ax <= q->lbAN[i] + TOL) ? -1 : ((ax >= q->ubAN[i] - TOL) ? 1 : 0);
+        int st = want[i];
+        q->lbA[i] = (st < 0) ? ax : ax - QP_BOUND_RELAX;
+        q->ubA[i] = (st > 0) ? ax : ax + QP_BOUND_RELAX;
         if (st == 0 || q->nAC >= q->nFR) continue;
         double z2, a2;
         constraint_w(q, i, &z2, &a2);
         if (!(z2 > QP_EPS_LI * QP_EPS_LI * a2) || a2 == 0.0) continue;
         add_constraint(q, i, st);
-        if (st < 0) q->lbA[i] = ax; else q->ubA[i] = ax;
     }
     mulAT(q, q->y + nV, q->t2);
     mulH(q, q->x, q->t1);
     for (int i = 0; i < nV; i++) q->g[i] = q->t2[i] + q->y[i] - q->t1[i];
     q->initialised = 1;
-    if (recompute_R(q)) { q->iters = 0; q->status = ORC_QPERROR_INTERNAL_ERROR; return q->status; }
+    return recompute_R(q);
+}
+
+/* init(H, g, A, lb, ub, lbA, ubA, nWSR, 0, x0) of handle_error's infeasible branch (src/qpOASESInterface.cpp:716-729, 690-701):
+ * primal guess x0 = [0; max(0, lbA); -min(0, ubA)] (the slack-feasible point of the l1-penalty QP), y = 0; working set read
+ * off x0 and A x0 with boundTolerance = 1e6*EPS; then the homotopy to the real data. */
+static int guess_start(orc_qp* q, const orc_qp_options* opt) {
+    int nV = q->nV, nC = q->nC, o1 = nV - 2 * nC, o2 = nV - nC;
+    const double TOL = 1.0e6 * QP_EPS;
+    int* want = (int*)zalloc(nC ? nC : 1, 4);
+    q->last_cold = 1;
+    for (int i = 0; i < nV; i++) { q->x[i] = 0.0; q->y[i] = 0.0; }
+    for (int i = 0; i < nC; i++) { q->x[o1 + i] = fmax(0.0, q->lbAN[i]); q->x[o2 + i] = -fmin(0.0, q->ubAN[i]); q->y[nV + i] = 0.0; }
+    mulA(q, q->x, q->Ax);
+    for (int i = 0; i < nV; i++) { double xi = q->x[i]; q->sB[i] = (xi <= q->lbN[i] + TOL) ? -1 : ((xi >= q->ubN[i] - TOL) ? 1 : 0); }
+    for (int i = 0; i < nC; i++) { double ax = q->Ax[i]; want[i] = (ax <= q->lbAN[i] + TOL) ? -1 : ((ax >= q->ubAN[i] - TOL) ? 1 : 0); }
+    int bad = aux_qp_from_guess(q, want);
+    free(want);
+    if (bad) { q->iters = 0; q->status = ORC_QPERROR_INTERNAL_ERROR; return q->status; }
     q->status = homotopy(q, opt);
     return q->status;
+}
+
+/* init(H, g, A, lb, ub, lbA, ubA, nWSR, 0, x_qp, y_qp, &bounds) of a FIXED <-> VARIED flip of the matrix status
+ * (src/qpOASESInterface.cpp:202-207): primal and dual guess = the previous solution, bound statuses = the previous ones,
+ * constraint statuses from the sign of the guessed multipliers (y > EPS lower, y < -EPS upper; qpOASES
+ * obtainAuxiliaryWorkingSet with guessedConstraints == 0 and yOpt != 0), new matrices.  1 if the projected Hessian of that
+ * working set is not positive definite (the init fails before its homotopy). */
+static int reinit_state(orc_qp* q) {
+    int nV = q->nV, nC = q->nC;
+    int* want = (int*)zalloc(nC ? nC : 1, 4);
+    for (int i = 0; i < nC; i++) { double yi = q->y[nV + i]; want[i] = (yi > QP_EPS) ? -1 : ((yi < -QP_EPS) ? 1 : 0); }
+    mulA(q, q->x, q->Ax);
+    int bad = aux_qp_from_guess(q, want);
+    free(want);
+    return bad;
 }
 
 /* qpOASESInterface::handle_error (src/qpOASESInterface.cpp:686-758) on top of this solver; the backend restatements call it
@@ -891,6 +919,21 @@ int orc_qp_hotstart_matrices(orc_qp* q, const orc_qp_options* opt, const double*
     mulA(q, q->x, q->Ax);
     drift_correction(q);
     q->last_cold = 0;
+    q->status = homotopy(q, opt);
+    return q->status;
+}
+
+/* the matrix-status flip of optimizeQP (src/qpOASESInterface.cpp:202-207): a fresh init from the previous solution */
+int orc_qp_reinit(orc_qp* q, const orc_qp_options* opt, const double* H_val, const double* A_val, const double* g,
+                  const double* lb, const double* ub, const double* lbA, const double* ubA) {
+    if (!q->initialised) return ORC_QPERROR_NOTINITIALISED;
+    int nV = q->nV;
+    if (q->has_H && H_val) memcpy(q->Hv, H_val, sizeof(double) * q->Hp[nV]);
+    if (A_val) { memcpy(q->Av, A_val, sizeof(double) * q->Ap[nV]); build_dense_A(q); }
+    set_targets(q, g, lb, ub, lbA, ubA);
+    q->fell_back = 0;
+    if (reinit_state(q)) { q->fell_back = 1; return cold_start(q, opt); } /* as hotstart_matrices: the plain re-init of handle_error */
+    q->last_cold = 0; /* a failure is followed by handle_error's plain re-init, a different solve */
     q->status = homotopy(q, opt);
     return q->status;
 }

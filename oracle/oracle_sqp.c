@@ -107,7 +107,7 @@ static void backend_solve(backend* b) {
     orc_qp_options o;
     orc_qp_default_options(&o);
     o.max_iter = b->maxiter;
-    int mode = 0; /* 0 cold, 1 fixed, 2 varied */
+    int mode = 0; /* 0 cold, 1 fixed, 2 varied, 3 status flip: init from the previous solution */
     if (b->first_solved) {
         int varied = b->upd_A || b->upd_H;
         if (b->old_ms == MS_UNDEFINED) b->old_ms = varied ? MS_VARIED : MS_FIXED;
@@ -115,7 +115,7 @@ static void backend_solve(backend* b) {
         if (b->new_ms == MS_UNDEFINED) mode = (b->old_ms == MS_FIXED) ? 1 : 2;
         else if (b->new_ms == MS_FIXED && b->old_ms == MS_FIXED) mode = 1;
         else if (b->new_ms == MS_VARIED && b->old_ms == MS_VARIED) mode = 2;
-        else { mode = 2; b->new_ms = b->old_ms = MS_UNDEFINED; }
+        else { mode = 3; b->new_ms = b->old_ms = MS_UNDEFINED; }
     }
     const int* Hp = b->is_lp ? NULL : b->Hp; const int* Hi = b->is_lp ? NULL : b->Hi; const double* Hv = b->is_lp ? NULL : b->Hv;
     int st, its = 0, it1 = 0;
@@ -124,7 +124,8 @@ static void backend_solve(backend* b) {
         orc_qp_get_solution(b->solver, NULL, NULL, NULL, &its);
     } else {
         st = (mode == 1) ? orc_qp_hotstart(b->solver, &o, b->g, b->lb, b->ub, b->lbA, b->ubA)
-                         : orc_qp_hotstart_matrices(b->solver, &o, Hv, b->Av, b->g, b->lb, b->ub, b->lbA, b->ubA);
+           : (mode == 2) ? orc_qp_hotstart_matrices(b->solver, &o, Hv, b->Av, b->g, b->lb, b->ub, b->lbA, b->ubA)
+                         : orc_qp_reinit(b->solver, &o, Hv, b->Av, b->g, b->lb, b->ub, b->lbA, b->ubA);
         orc_qp_get_solution(b->solver, NULL, NULL, NULL, &its);
     }
     if (st != ORC_QP_OPTIMAL) { /* handle_error (:160-162, :217-219), after an init as well as after a hot start */

@@ -861,8 +861,8 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
         if (h->new_ms == MS_UNDEFINED) mode = (h->old_ms == MS_FIXED) ? MODE_HOT_FIXED : MODE_HOT_VARIED;
         else if (h->new_ms == MS_FIXED && h->old_ms == MS_FIXED) mode = MODE_HOT_FIXED;
         else if (h->new_ms == MS_VARIED && h->old_ms == MS_VARIED) mode = MODE_HOT_VARIED;
-        else {  // status flip: warm re-init with (x, y, working set) :202-207 -> same working set, new factors
-            mode = MODE_HOT_VARIED;
+        else {  // status flip: init(..., x_qp, y_qp, &bounds) :202-207, a fresh init from the previous solution
+            mode = MODE_REINIT;
             h->new_ms = h->old_ms = MS_UNDEFINED;
         }
     }

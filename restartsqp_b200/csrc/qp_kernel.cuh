@@ -49,7 +49,8 @@ namespace sqpb200 {
 
 enum { ST_OPTIMAL = 20, ST_INTERNAL = 21, ST_INFEASIBLE = 22, ST_UNBOUNDED = 23, ST_NOTINIT = 25, ST_HOMOTOPY = 28,
        ST_CAPACITY = 31 /* internal: factor capacity exceeded, instance is re-solved by the rescue launch */ };
-enum { MODE_COLD = 0, MODE_HOT_FIXED = 1, MODE_HOT_VARIED = 2 };
+enum { MODE_COLD = 0, MODE_HOT_FIXED = 1, MODE_HOT_VARIED = 2,
+       MODE_REINIT = 3 /* FIXED <-> VARIED flip of the matrix status: init from the previous solution (src/qpOASESInterface.cpp:202-207) */ };
 enum { FLAG_FLIPPING = 1, FLAG_RAMPING = 2, FLAG_DRIFT = 4, FLAG_KEEP_STATE = 8,
        FLAG_FORCE_GUESS = 16 /* test hook: take handle_error's infeasible branch whatever the first attempt returned */ };
 
@@ -2044,33 +2045,29 @@ struct QPT {
         return recompute_R();
     }
 
-    // handle_error's infeasible branch (src/qpOASESInterface.cpp:716-729, 690-701): init with the primal guess
-    // x0 = [0; max(0, lbA); -min(0, ubA)] (the slack-feasible point of the l1-penalty QP), y = 0; working set read off x0 and
-    // A x0 with boundTolerance = 1e6*EPS (bounds first, then the constraints in index order, linearly dependent ones left out);
-    // auxiliary data relaxed by boundRelaxation.  Returns 0, 1 (projected Hessian not positive definite) or 2 (factor capacity).
-    static __device__ QP_FN int guess_start_state() {
+    // Auxiliary QP of an init from a guess (qpOASES solveInitialQP as reached from src/qpOASESInterface.cpp:202-207 and :716-729).
+    // The caller has set x, y, A x, the wanted bound statuses sB and the wanted constraint statuses (as doubles in dy[nV..]).
+    // Working set: bounds first, then the constraints in index order, linearly dependent ones left out; auxiliary bounds tight
+    // on the active side and relaxed by boundRelaxation elsewhere -- a constraint left out for dependence keeps its wanted side
+    // tight; gradient from stationarity.  Returns 0, 1 (projected Hessian not positive definite) or 2 (factor capacity).
+    static __device__ QP_FN int aux_qp_from_guess() {
         QP_CTX
-        double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA), *Q = V_(Q);
-        const double *lbN = V_(lbN), *ubN = V_(ubN), *lbAN = V_(lbAN), *ubAN = V_(ubAN);
+        double *x = V_(x), *Ax = V_(Ax), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA), *Q = V_(Q);
+        const double* want = V_(dy) + nV;
         short *sB = sB_, *sC = sC_, *FR = FR_, *posFR = posFR_, *posAC = posAC_;
-        const double TOL = 1.0e6 * QP_EPS;
-        const int o1 = nV - 2 * nC, o2 = nV - nC;
-        QP_U1 for (int i = lane; i < nV; i += TEAM) { x[i] = 0.0; y[i] = 0.0; }
-        SYNC();
-        QP_U1 for (int i = lane; i < nC; i += TEAM) {
-            x[o1 + i] = fmax(0.0, lbAN[i]); x[o2 + i] = -fmin(0.0, ubAN[i]);
-            y[nV + i] = 0.0; sC[i] = 0; posAC[i] = -1;
-        }
-        SYNC();
-        mulA(x, Ax);
         QP_U1 for (int i = lane; i < nV; i += TEAM) {
             const double xi = x[i];
-            const int st = (xi <= lbN[i] + TOL) ? -1 : ((xi >= ubN[i] - TOL) ? 1 : 0);
-            sB[i] = (short)st; posFR[i] = -1;
+            const int st = sB[i];
+            posFR[i] = -1;
             lb[i] = (st < 0) ? xi : xi - QP_BOUND_RELAX;
             ub[i] = (st > 0) ? xi : xi + QP_BOUND_RELAX;
         }
-        QP_U1 for (int i = lane; i < nC; i += TEAM) { lbA[i] = Ax[i] - QP_BOUND_RELAX; ubA[i] = Ax[i] + QP_BOUND_RELAX; }
+        QP_U1 for (int i = lane; i < nC; i += TEAM) {
+            const double ax = Ax[i], st = want[i];
+            sC[i] = 0; posAC[i] = -1;
+            lbA[i] = (st < 0.0) ? ax : ax - QP_BOUND_RELAX;
+            ubA[i] = (st > 0.0) ? ax : ax + QP_BOUND_RELAX;
+        }
         SYNC();
         if (lane == 0) {
             int nf = 0;
@@ -2084,18 +2081,46 @@ struct QPT {
         QP_U1 for (int k = lane; k < nFR * nFR; k += TEAM) { const int i = k / nFR, j = k % nFR; Q[i * ld + j] = (i == j) ? 1.0 : 0.0; }
         SYNC();
         QP_U1 for (int i = 0; i < nC; i++) {
-            const double ax = Ax[i];
-            const int st = (ax <= lbAN[i] + TOL) ? -1 : ((ax >= ubAN[i] - TOL) ? 1 : 0);
+            const int st = (int)want[i];
             if (st == 0 || hdr[1] >= hdr[0]) continue;
             double z2, a2;
             constraint_w(i, z2, a2);
             if (!(z2 > QP_EPS_LI * QP_EPS_LI * a2) || a2 == 0.0) continue;
             add_constraint(i, st);
-            if (lane == 0) { if (st < 0) lbA[i] = ax; else ubA[i] = ax; }
-            SYNC();
         }
         stationarity_gradient();
         return recompute_R() ? 1 : 0;
+    }
+    // handle_error's infeasible branch (src/qpOASESInterface.cpp:716-729, 690-701): init with the primal guess
+    // x0 = [0; max(0, lbA); -min(0, ubA)] (the slack-feasible point of the l1-penalty QP), y = 0; working set read off x0 and
+    // A x0 with boundTolerance = 1e6*EPS.
+    static __device__ QP_FN int guess_start_state() {
+        QP_CTX
+        double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *want = V_(dy) + nV;
+        const double *lbN = V_(lbN), *ubN = V_(ubN), *lbAN = V_(lbAN), *ubAN = V_(ubAN);
+        short* sB = sB_;
+        const double TOL = 1.0e6 * QP_EPS;
+        const int o1 = nV - 2 * nC, o2 = nV - nC;
+        QP_U1 for (int i = lane; i < nV; i += TEAM) { x[i] = 0.0; y[i] = 0.0; }
+        SYNC();
+        QP_U1 for (int i = lane; i < nC; i += TEAM) { x[o1 + i] = fmax(0.0, lbAN[i]); x[o2 + i] = -fmin(0.0, ubAN[i]); y[nV + i] = 0.0; }
+        SYNC();
+        mulA(x, Ax);
+        QP_U1 for (int i = lane; i < nV; i += TEAM) { const double xi = x[i]; sB[i] = (short)((xi <= lbN[i] + TOL) ? -1 : ((xi >= ubN[i] - TOL) ? 1 : 0)); }
+        QP_U1 for (int i = lane; i < nC; i += TEAM) { const double ax = Ax[i]; want[i] = (ax <= lbAN[i] + TOL) ? -1.0 : ((ax >= ubAN[i] - TOL) ? 1.0 : 0.0); }
+        SYNC();
+        return aux_qp_from_guess();
+    }
+    // The matrix-status flip (src/qpOASESInterface.cpp:202-207): init(H, g, A, ..., x_qp, y_qp, &bounds) -- primal and dual guess
+    // = the previous solution, bound statuses = the previous ones, constraint statuses from the sign of the guessed multipliers
+    // (y > EPS lower, y < -EPS upper: qpOASES obtainAuxiliaryWorkingSet with yOpt and without guessedConstraints), new matrices.
+    static __device__ QP_FN int reinit_start_state() {
+        QP_CTX
+        double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *want = V_(dy) + nV;
+        QP_U1 for (int i = lane; i < nC; i += TEAM) { const double yi = y[nV + i]; want[i] = (yi > QP_EPS) ? -1.0 : ((yi < -QP_EPS) ? 1.0 : 0.0); }
+        SYNC();
+        mulA(x, Ax);
+        return aux_qp_from_guess();
     }
     // qpOASESInterface::handle_error (src/qpOASESInterface.cpp:686-758), called when a solve did not end OPTIMAL -- after an init
     // as well as after a hot start (:160-162, :217-219).  `cold`: the failed attempt was an init.  Infeasible: re-init from the
@@ -2217,7 +2242,7 @@ __device__ __forceinline__ int qp_instance_mode(const signed char* st, bool resc
         if (new_ms < 0) mode = (old_ms == 0) ? MODE_HOT_FIXED : MODE_HOT_VARIED;
         else if (new_ms == 0 && old_ms == 0) mode = MODE_HOT_FIXED;
         else if (new_ms == 1 && old_ms == 1) mode = MODE_HOT_VARIED;
-        else { mode = MODE_HOT_VARIED; new_ms = old_ms = -1; }  // status flip: warm re-init with the kept working set (:202-207)
+        else { mode = MODE_REINIT; new_ms = old_ms = -1; }  // status flip: init from the previous solution (:202-207)
     }
     return mode;
 }
@@ -2326,12 +2351,18 @@ template <int TEAM> static __device__ __forceinline__ void qp_solve_one(const QP
         if (mode == MODE_HOT_VARIED) {
             if (QPT<TEAM>::refactorise()) { mode = MODE_COLD; fell_back = true; }  // projected Hessian of the kept set not PD
             else QPT<TEAM>::drift_correction();
+        } else if (mode == MODE_REINIT) {
+            const int e = QPT<TEAM>::reinit_start_state();
+            if (e == 2) status = ST_CAPACITY;
+            else if (e) { mode = MODE_COLD; fell_back = true; }  // that init fails before its homotopy: plain re-init
         }
-        if (mode == MODE_COLD) QPT<TEAM>::cold_start_state();
-        status = QPT<TEAM>::homotopy(A.max_iter, iters);
-        total_iters += iters;
-        if (status != ST_CAPACITY && ((status != ST_OPTIMAL && !fell_back) || (A.flags & FLAG_FORCE_GUESS)))
-            status = QPT<TEAM>::handle_error(status, mode == MODE_COLD, A.max_iter, iters, total_iters);
+        if (status != ST_CAPACITY) {
+            if (mode == MODE_COLD) QPT<TEAM>::cold_start_state();
+            status = QPT<TEAM>::homotopy(A.max_iter, iters);
+            total_iters += iters;
+            if (status != ST_CAPACITY && ((status != ST_OPTIMAL && !fell_back) || (A.flags & FLAG_FORCE_GUESS)))
+                status = QPT<TEAM>::handle_error(status, mode == MODE_COLD, A.max_iter, iters, total_iters);
+        }
     }
     if (status == ST_CAPACITY) {  // left to the rescue launch (full capacity), which restarts from the pre-solve state
         if (lane == 0) { A.status[b] = ST_CAPACITY; A.iters[b] = 0; if (A.ncap) A.caplist[atomicAdd(A.ncap, 1)] = b; }
@@ -2429,6 +2460,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) qp_solve_large_kernel(const __
     if (mode == MODE_HOT_VARIED) {
         if (S::refactorise()) { mode = MODE_COLD; fell_back = true; }
         else S::drift_correction();
+    } else if (mode == MODE_REINIT) {
+        if (S::reinit_start_state()) { mode = MODE_COLD; fell_back = true; }
     }
     if (mode == MODE_COLD) S::cold_start_state();
     status = S::homotopy(A.max_iter, iters);

@@ -99,7 +99,7 @@ class OracleQPInterface:
             elif self.new_ms == MS_VARIED and self.old_ms == MS_VARIED:
                 mode = "varied"
             else:
-                mode = "varied"
+                mode = "reinit"  # status flip: init from the previous solution (:202-207)
                 self.new_ms = self.old_ms = MS_UNDEFINED
         for b in range(self.batch):
             if active_mask is not None and not active_mask[b]:
@@ -113,7 +113,8 @@ class OracleQPInterface:
                 st = s.init(Hcsc, args[0], Acsc, *args[1:], is_lp=self.is_lp)
                 its = s.solution()[3]
             else:
-                st = s.hotstart(*args) if mode == "fixed" else s.hotstart_matrices(None if self.is_lp else self.Hv[b], self.Av[b], *args)
+                margs = (None if self.is_lp else self.Hv[b], self.Av[b]) + args
+                st = s.hotstart(*args) if mode == "fixed" else (s.hotstart_matrices(*margs) if mode == "varied" else s.reinit(*margs))
                 its = s.solution()[3]
             if st != 20:  # handle_error (src/qpOASESInterface.cpp:686-758), after an init as well as after a hot start
                 st, added = s.handle_error()

@@ -187,18 +187,22 @@ def test_hotstart_fixed_and_varied(gpu_lib, team):
         st = oracles[b].hotstart(g2[b], lb[b], ub[b], lbA2[b], ubA2[b])
         x, y, obj, it = oracles[b].solution(); wb, wc = oracles[b].working_set()
         check_against_oracle(s, b, dict(x=x, y=y, obj=obj, iters=it, status=st, wb=wb, wc=wc), nV)
-    # 2) new matrix values -> VARIED hot start (first a status flip, handled as a warm re-init)
-    Hv2 = np.tile(Hc[2], (B, 1)) * 1.1
+    # 2) new matrix values: the FIXED -> VARIED flip is an init from the previous solution (:202-207), the solve after it a
+    #    VARIED hot start, hotstart(H, g, A, ...) (:184-188)
+    Hv2 = np.tile(Hc[2], (B, 1))
     Av2 = np.tile(Ac[2], (B, 1))
-    s.set_csc_values(capi.MAT_H, Hv2); s.set_csc_values(capi.MAT_A, Av2)
-    s.optimizeQP()
-    for b in range(B):
-        st = oracles[b].hotstart_matrices(Hv2[b], Av2[b], g2[b], lb[b], ub[b], lbA2[b], ubA2[b])
-        x, y, obj, it = oracles[b].solution(); wb, wc = oracles[b].working_set()
-        check_against_oracle(s, b, dict(x=x, y=y, obj=obj, iters=it, status=st, wb=wb, wc=wc), nV)
-        p = dict(nV=nV, nC=nC, g=g2[b], lb=lb[b], ub=ub[b], lbA=lbA2[b], ubA=ubA2[b])
-        cold = H.oracle_solve(orc, p, Acsc=Ac, Hcsc=(Hc[0], Hc[1], Hv2[b]))
-        assert relerr(s.get_optimal_solution()[b], cold["x"]) <= RTOL
+    for k, call in enumerate(("reinit", "hotstart_matrices", "hotstart_matrices")):
+        Hv2 = Hv2 * 1.1
+        g2 = g2.copy(); g2[:, :n] += 0.1 * rng.standard_normal((B, n))
+        s.set_csc_values(capi.MAT_H, Hv2); s.set_csc_values(capi.MAT_A, Av2); s.set_g(g2)
+        s.optimizeQP()
+        for b in range(B):
+            st = getattr(oracles[b], call)(Hv2[b], Av2[b], g2[b], lb[b], ub[b], lbA2[b], ubA2[b])
+            x, y, obj, it = oracles[b].solution(); wb, wc = oracles[b].working_set()
+            check_against_oracle(s, b, dict(x=x, y=y, obj=obj, iters=it, status=st, wb=wb, wc=wc), nV)
+            p = dict(nV=nV, nC=nC, g=g2[b], lb=lb[b], ub=ub[b], lbA=lbA2[b], ubA=ubA2[b])
+            cold = H.oracle_solve(orc, p, Acsc=Ac, Hcsc=(Hc[0], Hc[1], Hv2[b]))
+            assert relerr(s.get_optimal_solution()[b], cold["x"]) <= RTOL
     s.close()
 
 

@@ -167,3 +167,38 @@ def test_hotstart_vectors_and_matrices():
         p3["H"] = Hd
         r_cold2 = H.oracle_solve(orc, p3, Acsc=Ac, Hcsc=Hc2)
         assert np.abs(x_hot2 - r_cold2["x"]).max() < 1e-8
+
+
+def test_reinit_from_previous_solution():
+    """The matrix-status flip of optimizeQP (src/qpOASESInterface.cpp:202-207): init(H, g, A, ..., x_qp, y_qp, &bounds).  On a
+    strictly convex QP it reaches the point a cold start reaches on the new data; with unchanged data the guess is already
+    optimal (no working-set change); and the working set it ends in satisfies the KKT test."""
+    rng = np.random.default_rng(11)
+    done = 0
+    for _ in range(12):
+        n, m = int(rng.integers(2, 7)), int(rng.integers(1, 5))
+        p = H.random_l1_qp(rng, n, m)
+        Ac, Hc = H.csc(p["A"]), H.csc(p["H"])
+        r0 = H.oracle_solve(orc, p, Acsc=Ac, Hcsc=Hc)
+        if r0["status"] != 20:
+            continue
+        s = r0["solver"]
+        args = (p["g"], p["lb"], p["ub"], p["lbA"], p["ubA"])
+        assert s.reinit(Hc[2], Ac[2], *args) == 20
+        x1, y1, _, it1 = s.solution()
+        assert it1 == 0 and np.abs(x1 - r0["x"]).max() < 1e-10 and np.abs(y1 - r0["y"]).max() < 1e-8
+        Hv2 = Hc[2] * 1.2
+        Av2 = Ac[2] * (1.0 + 0.05 * rng.standard_normal(len(Ac[2])) * (np.abs(np.abs(Ac[2]) - 1.0) > 1e-12))
+        g2 = p["g"] + np.concatenate([0.3 * rng.standard_normal(n), np.zeros(2 * m)])
+        assert s.reinit(Hv2, Av2, g2, *args[1:]) == 20
+        x2, y2, _, _ = s.solution()
+        A2, H2 = (Ac[0], Ac[1], Av2), (Hc[0], Hc[1], Hv2)
+        cold = H.oracle_solve(orc, dict(p, g=g2), Acsc=A2, Hcsc=H2)
+        assert np.abs(x2 - cold["x"]).max() < 1e-8
+        wb, wc = s.working_set()
+        Ax = orc.csc_times(p["nC"], p["nV"], *A2, x2)
+        Wb, Wc = orc.translate_working_set(wb, wc, x2, Ax, *args[1:])
+        ok, res = orc.kkt_residuals(p["nV"], p["nC"], A2, H2, g2, *args[1:], x2, y2, Wb, Wc)
+        assert ok, res
+        done += 1
+    assert done >= 8

@@ -29,11 +29,11 @@ for case in range(ncase):
         if not is_lp: s.set_csc(capi.MAT_H, *Hc)
         Av, Hv = t(Ac[2]), t(Hc[2])
         sol = [orc.OracleQP(nV, nC, max_iter=100 if is_lp else 1000) for _ in range(B)]
-        for step in range(4):
+        for step in range(5):  # init, 2 x hotstart (FIXED), init from the previous solution (FIXED -> VARIED flip), hotstart with matrices
             if step in (1, 2):
                 g = g.copy(); g[:, :n] += 0.3 * rng.standard_normal((B, n)) * (0.0 if is_lp else 1.0)
                 if m: lbA = np.where(lbA > -1e17, lbA + 0.2 * rng.standard_normal((B, m)), lbA); ubA = np.maximum(ubA, lbA)
-            if step == 3:
+            if step >= 3:
                 Av = Av * (1.0 + 0.05 * rng.standard_normal(Av.shape) * (np.abs(np.abs(Av) - 1.0) > 1e-12))
                 s.set_csc_values(capi.MAT_A, Av)
                 if not is_lp:
@@ -49,7 +49,7 @@ for case in range(ncase):
                     so = o.init(None if is_lp else (Hc[0], Hc[1], Hv[b]), g[b], (Ac[0], Ac[1], Av[b]), lb[b], ub[b], lbA[b], ubA[b], is_lp=is_lp)
                     ito = o.solution()[3]
                 else:
-                    so = o.hotstart(g[b], lb[b], ub[b], lbA[b], ubA[b]) if step < 3 else o.hotstart_matrices(None if is_lp else Hv[b], Av[b], g[b], lb[b], ub[b], lbA[b], ubA[b])
+                    so = o.hotstart(g[b], lb[b], ub[b], lbA[b], ubA[b]) if step < 3 else (o.reinit if step == 3 else o.hotstart_matrices)(None if is_lp else Hv[b], Av[b], g[b], lb[b], ub[b], lbA[b], ubA[b])
                     ito = o.solution()[3]
                 if so != 20:  # handle_error, after an init as well as after a hot start
                     so, added = o.handle_error()

@@ -840,6 +840,11 @@ int sqpb200_device_buffers(sqpb200_handle h, void** out) {
     out[0] = h->dx; out[1] = h->dy; out[2] = h->dobj; out[3] = h->dstatus; out[4] = h->diters; out[5] = h->dkkt;
     return 0;
 }
+// SQPB200_LARGE_RECOMPUTE=1: the one-QP-per-cluster kernel recomputes R after every addition instead of updating it
+static bool large_recompute() {
+    static const bool v = [] { const char* e = getenv("SQPB200_LARGE_RECOMPUTE"); return e && e[0] == '1'; }();
+    return v;
+}
 static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask, bool mask_on_device, signed char* inst_state) {
     if (!h) return SQPB200_ERR_INVALID;
     CK(cudaSetDevice(h->device));
@@ -871,7 +876,7 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
     a.max_iter = maxiter > 0 ? maxiter : (is_lp ? h->opt.lp_maxiter : h->opt.qp_maxiter);
     a.flags = (h->opt.enable_flipping ? FLAG_FLIPPING : 0) | (h->opt.enable_ramping ? FLAG_RAMPING : 0) |
               (h->opt.enable_drift ? FLAG_DRIFT : 0) | (h->opt.keep_state ? FLAG_KEEP_STATE : 0) |
-              (h->opt.debug_force_error_branch ? FLAG_FORCE_GUESS : 0);
+              (h->opt.debug_force_error_branch ? FLAG_FORCE_GUESS : 0) | (large_recompute() ? FLAG_NO_CARRY : 0);
     a.mode = mode;
     a.Ap = h->dAp; a.Ai = h->dAi; a.Arp = h->dArp; a.Aci = h->dAci; a.Aperm = h->dAperm;
     a.Hp = h->dHp; a.Hi = h->dHi;

@@ -52,7 +52,8 @@ enum { ST_OPTIMAL = 20, ST_INTERNAL = 21, ST_INFEASIBLE = 22, ST_UNBOUNDED = 23,
 enum { MODE_COLD = 0, MODE_HOT_FIXED = 1, MODE_HOT_VARIED = 2,
        MODE_REINIT = 3 /* FIXED <-> VARIED flip of the matrix status: init from the previous solution (src/qpOASESInterface.cpp:202-207) */ };
 enum { FLAG_FLIPPING = 1, FLAG_RAMPING = 2, FLAG_DRIFT = 4, FLAG_KEEP_STATE = 8,
-       FLAG_FORCE_GUESS = 16 /* test hook: take handle_error's infeasible branch whatever the first attempt returned */ };
+       FLAG_FORCE_GUESS = 16 /* test hook: take handle_error's infeasible branch whatever the first attempt returned */,
+       FLAG_NO_CARRY = 32 /* one-QP-per-cluster kernel: recompute R after every addition (as the warp kernel does) instead of updating it */ };
 
 struct QPKernelArgs {
     int batch, nV, nC;
@@ -777,17 +778,31 @@ struct QPT {
     // chain runs lane-per-row out of the tile).
     // The chain runs over the logical columns j = 0 .. cnt-1, stored at column base + dir * j (dir = -1: the right-to-left
     // chains of the removals, whose rotation i acts on (c, c+1) with c decreasing: same recurrence with (c_j, -s_j)).
+    // tri: M is upper triangular (row r zero left of column r), so the chain of a row group starts at its first fill-in.
+    // Groups of 32 rows, or of 16 / 8 while that leaves warps without work (the chain then runs on the first lanes only).
     static __device__ __forceinline__ void rot_rows(double* M, int ld, int nP, int cnt, const double* cs, const double* sn, int rank = 0,
-                                                    int ncta = 1, int base = 0, int dir = 1) {
+                                                    int ncta = 1, int base = 0, int dir = 1, bool tri = false) {
         if (cnt <= 0) return;
-        const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+        const int warp = threadIdx.x >> 5, l = threadIdx.x & 31, nwarps = (TEAM / 32) * ncta;
+        int G = 32;
+        while (G > 8 && (nP + G - 1) / G < nwarps) G >>= 1;
         double* tile = qp_smem + (size_t)warp * (32 * 33);
-        for (int r0 = (warp + (TEAM / 32) * rank) * 32; r0 < nP; r0 += TEAM * ncta) {
-            const int nr = (nP - r0 < 32) ? nP - r0 : 32;
-            double qa = (l < nr) ? M[(size_t)(r0 + l) * ld + base] : 0.0;
-            for (int jt = 0; jt < cnt; jt += 32) {
-                // originals of columns jt+1 .. jt+32
-                for (int rr = 0; rr < nr; rr++) { const int j = jt + 1 + l; if (j < cnt) tile[rr * 33 + l] = M[(size_t)(r0 + rr) * ld + base + dir * j]; }
+        for (int r0 = (warp + (TEAM / 32) * rank) * G; r0 < nP; r0 += nwarps * G) {
+            const int nr = (nP - r0 < G) ? nP - r0 : G;
+            const int jt0 = (tri && r0 > 0) ? ((r0 - 1) & ~31) : 0;
+            double qa = (l < nr) ? M[(size_t)(r0 + l) * ld + base + dir * jt0] : 0.0;
+            for (int jt = jt0; jt < cnt; jt += 32) {
+                // originals of columns jt+1 .. jt+32: eight independent loads in flight per lane
+                {
+                    const int j = jt + 1 + l;
+                    for (int rr0 = 0; rr0 < nr; rr0 += 8) {
+                        double v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) v[u] = (rr0 + u < nr && j < cnt) ? M[(size_t)(r0 + rr0 + u) * ld + base + dir * j] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 8; u++) tile[(rr0 + u) * 33 + l] = v[u];
+                    }
+                }
                 __syncwarp();
                 if (l < nr) {
                     const int cmax = (cnt - jt < 32) ? cnt - jt : 32;
@@ -894,6 +909,55 @@ struct QPT {
     // Elimination with the block in registers (thread (r0, j) owns rows r0, r0 + 8, ... of column j): per pivot the owners
     // publish the finished (unscaled) row, one barrier, and every thread updates its own entries with a_ki a_kj / a_kk; the
     // square roots are taken afterwards for all rows at once, so the pivot chain is one division + one barrier long.
+    // X = D^{-1} for the upper triangular 64 x 64 block D in shared memory (leading dimension LT_D_LD; entries outside the
+    // leading nb x nb part are taken as the identity), by recursive doubling: the eight 8 x 8 diagonal blocks by substitution
+    // (one thread per column), then X12 = -X11 (D12 X22) for block pairs of size 8, 16, 32 -- every element of a product by its
+    // own thread, two barriers per level instead of one warp-synchronous step per row of the block.  T: scratch, same shape.
+    static __device__ __forceinline__ void tri_inv_block(const double* D, double* X, double* T, int nb) {
+        const int tid = threadIdx.x;
+        for (int k = tid; k < LT_NB * LT_NB; k += TEAM) { const int i = k >> 6, j = k & 63; X[i * LT_D_LD + j] = (i == j && i >= nb) ? 1.0 : 0.0; }
+        __syncthreads();
+        if (tid < nb) {
+            const int c = tid, g0 = c & ~7;
+            X[c * LT_D_LD + c] = 1.0 / D[c * LT_D_LD + c];
+            for (int r = c - 1; r >= g0; r--) {
+                double sacc = 0.0;
+                for (int l = r + 1; l <= c; l++) sacc += D[r * LT_D_LD + l] * X[l * LT_D_LD + c];
+                X[r * LT_D_LD + c] = -sacc / D[r * LT_D_LD + r];
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int sz = 8; sz < LT_NB; sz <<= 1) {
+            const int lg = (sz == 8) ? 3 : ((sz == 16) ? 4 : 5);
+            // T = D12 X22 (X22 upper triangular: k <= j)
+            for (int e = tid; e < 32 * sz; e += TEAM) {
+                const int j = e & (sz - 1), i = (e >> lg) & (sz - 1), pr = e >> (2 * lg), a0 = pr * 2 * sz, b0 = a0 + sz;
+                double s0 = 0.0, s1 = 0.0;
+                int k = 0;
+                for (; k + 1 <= j; k += 2) {
+                    s0 += D[(a0 + i) * LT_D_LD + b0 + k] * X[(b0 + k) * LT_D_LD + b0 + j];
+                    s1 += D[(a0 + i) * LT_D_LD + b0 + k + 1] * X[(b0 + k + 1) * LT_D_LD + b0 + j];
+                }
+                if (k <= j) s0 += D[(a0 + i) * LT_D_LD + b0 + k] * X[(b0 + k) * LT_D_LD + b0 + j];
+                T[(a0 + i) * LT_D_LD + b0 + j] = (a0 + i < nb && b0 + j < nb) ? s0 + s1 : 0.0;
+            }
+            __syncthreads();
+            // X12 = -X11 T (X11 upper triangular: k >= i)
+            for (int e = tid; e < 32 * sz; e += TEAM) {
+                const int j = e & (sz - 1), i = (e >> lg) & (sz - 1), pr = e >> (2 * lg), a0 = pr * 2 * sz, b0 = a0 + sz;
+                double s0 = 0.0, s1 = 0.0;
+                int k = i;
+                for (; k + 1 < sz; k += 2) {
+                    s0 += X[(a0 + i) * LT_D_LD + a0 + k] * T[(a0 + k) * LT_D_LD + b0 + j];
+                    s1 += X[(a0 + i) * LT_D_LD + a0 + k + 1] * T[(a0 + k + 1) * LT_D_LD + b0 + j];
+                }
+                if (k < sz) s0 += X[(a0 + i) * LT_D_LD + a0 + k] * T[(a0 + k) * LT_D_LD + b0 + j];
+                X[(a0 + i) * LT_D_LD + b0 + j] = -(s0 + s1);
+            }
+            __syncthreads();
+        }
+    }
     static __device__ __forceinline__ int diag_block(int i0, int nb) {
         QP_CTX
         double *RT = V_(RT), *W = V_(W);
@@ -938,24 +1002,14 @@ struct QPT {
             }
         }
         __syncthreads();
-        // inverse of the (upper triangular) factor, column c by 8 threads (c = tid / 8): x_c = 1 / R_cc,
-        // x_r = -(sum_{l = r+1..c} R_rl x_l) / R_rr; columns are independent, so only warp-level synchronisation
-        {
-            const int c = tid >> 3, sub = tid & 7;
-            if (c < nb && sub == 0) DI[c * LT_D_LD + c] = sc[64 + c];
-            __syncwarp();
-            for (int r = nb - 2; r >= 0; r--) {  // uniform trip count; columns c <= r idle
-                double sacc = 0.0;
-                if (c < nb && r < c)
-                    for (int l = r + 1 + sub; l <= c; l += 8) sacc += D[r * LT_D_LD + l] * DI[l * LT_D_LD + c];
-                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-                sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
-                if (c < nb && r < c && sub == 0) DI[r * LT_D_LD + c] = -sacc * sc[64 + r];
-                __syncwarp();
-            }
+        // inverse of the (upper triangular) factor
+        if (nb < LT_NB) {  // the last block: identity outside the leading nb x nb part
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const int i = r0 + 8 * q; if (i < j && j >= nb) D[i * LT_D_LD + j] = 0.0; }
+            if (tid >= nb && tid < LT_NB) D[tid * LT_D_LD + tid] = 1.0;
+            __syncthreads();
         }
-        __syncthreads();
+        tri_inv_block(D, DI, qp_smem, nb);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             const int i = r0 + 8 * q;
@@ -1056,7 +1110,7 @@ struct QPT {
     }
     // ---- operations the leader shares with its helper CTAs: arguments go through the slice header (ints 4..15), offsets are
     // in doubles from the slice base.  Worth two cluster barriers only when the operand is large.
-    enum { OP_REFAC = 1, OP_EXIT = 2, OP_COLSUMS = 3, OP_ROWSUMS = 4, OP_ROTROWS = 5 };
+    enum { OP_REFAC = 1, OP_EXIT = 2, OP_COLSUMS = 3, OP_ROWSUMS = 4, OP_ROTROWS = 5, OP_DINV = 6 };
     static constexpr int DIST_MIN_ELEMS = 1 << 17;  // below ~1 MB of factor data the leader works alone
     static __device__ __forceinline__ void run_op(int cmd, int rank, int cs) {
         QP_CTX
@@ -1064,7 +1118,8 @@ struct QPT {
         const int oM = vh[8], nP = vh[9], i0 = vh[10], i1 = vh[11], oA = vh[12], oB = vh[13], flag = vh[14];
         if (cmd == OP_COLSUMS) col_sums(slice + oM, ld, nP, i0, i1, slice + oA, slice + oB, flag ? -1.0 : 1.0, rank, cs);
         else if (cmd == OP_ROWSUMS) row_sums(slice + oM, ld, nP, i0, i1, slice + oA, slice + oB, (flag & 1) ? FR_ : nullptr, (flag & 2) != 0, rank, cs);
-        else if (cmd == OP_ROTROWS) rot_rows(slice + oM, ld, nP, i0, slice + oA, slice + oB, rank, cs, i1, flag ? -1 : 1);
+        else if (cmd == OP_ROTROWS) rot_rows(slice + oM, ld, nP, i0, slice + oA, slice + oB, rank, cs, i1, (flag & 1) ? -1 : 1, (flag & 2) != 0);
+        else if (cmd == OP_DINV) dinv_blocks(nP, rank, cs);
     }
     static __device__ __forceinline__ void dist_op(int cmd, int oM, int nP, int i0, int i1, int oA, int oB, int flag) {
         QP_CTX
@@ -1085,11 +1140,118 @@ struct QPT {
         if (sClusterSize > 1 && (long long)nP * (j1 - j0) >= DIST_MIN_ELEMS) dist_op(OP_ROWSUMS, oM, nP, j0, j1, oV, oOut, (via_FR ? 1 : 0) | (accumulate ? 2 : 0));
         else row_sums(slice + oM, ld, nP, j0, j1, slice + oV, slice + oOut, via_FR ? FR_ : nullptr, accumulate);
     }
-    static __device__ __forceinline__ void rot_rows_auto(int oM, int nP, int cnt, int oC, int oS_, int base = 0, int dir = 1) {
+    static __device__ __forceinline__ void rot_rows_auto(int oM, int nP, int cnt, int oC, int oS_, int base = 0, int dir = 1, bool tri = false) {
         QP_CTX
-        if (sClusterSize > 1 && (long long)nP * cnt >= DIST_MIN_ELEMS) dist_op(OP_ROTROWS, oM, nP, cnt, base, oC, oS_, dir < 0 ? 1 : 0);
-        else rot_rows(slice + oM, ld, nP, cnt, slice + oC, slice + oS_, 0, 1, base, dir);
+        if (sClusterSize > 1 && (long long)nP * cnt >= DIST_MIN_ELEMS) dist_op(OP_ROTROWS, oM, nP, cnt, base, oC, oS_, (dir < 0 ? 1 : 0) | (tri ? 2 : 0));
+        else rot_rows(slice + oM, ld, nP, cnt, slice + oC, slice + oS_, 0, 1, base, dir, tri);
     }
+    // ---- Cholesky factor of the projected Hessian carried through an addition (one-QP-per-cluster kernel only).  The warp
+    // kernel and the oracle recompute R after every addition, as qpOASES does under setToReliable
+    // (enableCholeskyRefactorisation = 1); that is O(nZ^3) per working-set change.  Here the addition's rotation chain G (the
+    // one that was just applied to the null-space columns of Q) is applied to the columns of R, the last column is dropped
+    // (Z loses it) and the upper Hessenberg rest is brought back to triangular form by row rotations: R_new'R_new =
+    // (Z G)'H(Z G) restricted to the kept columns, the same matrix a recomputation factorises, in O(nZ^2) (qpOASES's own
+    // update under its default options).  A full recomputation still runs every REFAC_EVERY additions, after an exchange
+    // step (R is one column short there) and after a flipped bound.
+    static constexpr int REFAC_EVERY = 64;
+    // inverses of the 64 x 64 diagonal blocks of R (n x n) into W, block b by CTA b % cs
+    static __device__ __forceinline__ void dinv_blocks(int n, int rank, int cs) {
+        QP_CTX
+        const double* RT = V_(RT);
+        double* W = V_(W);
+        double* D = qp_smem + LS_D;
+        double* DI = qp_smem + LS_DI;
+        const int tid = threadIdx.x, j = tid & 63, r0 = tid >> 6;
+        for (int i0 = rank * LT_NB; i0 < n; i0 += cs * LT_NB) {
+            const int nb = (n - i0 < LT_NB) ? n - i0 : LT_NB;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int i = r0 + 8 * q;
+                D[i * LT_D_LD + j] = (i < nb && j < nb && i <= j) ? R_(i0 + i, i0 + j) : ((i == j) ? 1.0 : 0.0);
+            }
+            __syncthreads();
+            tri_inv_block(D, DI, qp_smem, nb);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int i = r0 + 8 * q;
+                if (i < nb && j < nb) W[(size_t)(i0 + i) * ld + j] = DI[i * LT_D_LD + j];
+            }
+            __syncthreads();
+        }
+    }
+    // rows 0..nZ-1, columns 0..nZ-2 of R hold an upper Hessenberg matrix: row rotation k (rows k, k+1) removes (k+1, k).
+    // A thread owns the columns tid, tid + TEAM, ... and carries "its" entries of the running row k+1 in registers; the rows
+    // k+1 .. k+4 are in flight in four register sets (the loop is unrolled by four so that the sets rotate without moves: an
+    // L2 round trip per rotation otherwise); one barrier per rotation (the owner of column k publishes (c, s) through shared
+    // memory).
+    template <int NQ>
+    static __device__ __noinline__ void retriangularise(int nZ) {
+        QP_CTX
+        double* RT = V_(RT);
+        double* sc = qp_smem + LS_RED;
+        const int tid = threadIdx.x, m = nZ - 1;
+        const int nact = (m < TEAM) ? ((m + 31) & ~31) : TEAM;
+        if (tid >= nact) { __syncthreads(); return; }
+        double cur[NQ], buf[4][NQ];  // buf[r & 3]: row r
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const int j = tid + TEAM * q;
+            cur[q] = (j < m) ? R_(0, j) : 0.0;
+#pragma unroll
+            for (int r = 1; r <= 4; r++) buf[r & 3][q] = (j < m && j + 1 >= r && r < nZ) ? R_(r, j) : 0.0;
+        }
+        for (int k0 = 0; k0 < m; k0 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int k = k0 + u;
+                if (k >= m) break;
+                double* nxt = buf[(u + 1) & 3];  // row k+1 (k0 is a multiple of four)
+                if (tid == (k & (TEAM - 1))) {
+                    double a = 0.0, b = 0.0;
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) if (q == k / TEAM) { a = cur[q]; b = nxt[q]; }
+                    const double h2 = a * a + b * b;
+                    double* o = sc + 2 * (k & 1);
+                    if (h2 > 0.0) { const double ih = rsqrt(h2); o[0] = a * ih; o[1] = b * ih; } else { o[0] = 1.0; o[1] = 0.0; }
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(nact) : "memory");  // the warps that own a column
+                const double c = sc[2 * (k & 1)], sn = sc[2 * (k & 1) + 1];
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    const int j = tid + TEAM * q;
+                    if (j >= k && j < m) {
+                        const double a = cur[q], b = nxt[q];
+                        R_(k, j) = c * a + sn * b;
+                        if (j == k) { R_(k + 1, k) = 0.0; cur[q] = 0.0; }
+                        else cur[q] = c * b - sn * a;
+                    }
+                    nxt[q] = (j + 1 >= k + 5 && j < m && k + 5 < nZ) ? R_(k + 5, j) : 0.0;  // row k+5 takes the place of row k+1
+                }
+                // row k + 32 towards L2, one 128-byte line per thread
+                if (k + 32 < nZ && tid * 16 < m && tid * 16 + 16 > k + 30) asm volatile("prefetch.global.L2 [%0];" ::"l"(&R_(k + 32, tid * 16)));
+            }
+        }
+        __syncthreads();
+    }
+    // R (nZ x nZ) -> factor of the working set that has just lost its last null-space column; (c_j, s_j) of the addition's chain
+    // are still in t2 / t3
+    static __device__ __noinline__ void update_R_after_add(int nZ) {
+        QP_CTX
+        const int m = nZ - 1;
+        if (m <= 0) return;
+        PROF_T0
+        rot_rows_auto(sA.oRT, nZ, nZ, sA.ot2, sA.ot3, 0, 1, true);
+        PROF_ADD(PR_REFAC_W);  // (profile build: the three slots of the recomputation show the update's steps)
+        if (m <= TEAM) retriangularise<1>(nZ);
+        else if (m <= 2 * TEAM) retriangularise<2>(nZ);
+        else if (m <= 4 * TEAM) retriangularise<4>(nZ);
+        else retriangularise<8>(nZ);
+        PROF_ADD(PR_REFAC_M);
+        if (sClusterSize > 1 && m > TEAM) dist_op(OP_DINV, 0, m, 0, 0, 0, 0, 0);
+        else dinv_blocks(m, 0, 1);
+        PROF_ADD(PR_REFAC_CHOL);
+    }
+    static constexpr int UPDATE_MAX_NZ = 8 * TEAM;
     static __device__ QP_FN int recompute_R_blocked() {
         QP_CTX
         if (lane == 0) hdr[4] = 1;  // command: refactorise
@@ -1333,15 +1495,18 @@ struct QPT {
         SYNC();
         return r;
     }
-    static __device__ QP_FN void add_constraint(int c, int status) {
+    // carry_R (one-QP-per-cluster kernel): R is valid for the current working set and is updated instead of recomputed
+    static __device__ QP_FN void add_constraint(int c, int status, bool carry_R = false) {
         QP_CTX
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
         double *Q = V_(Q), *RT = V_(RT);
         const double *t2 = V_(t2), *t3 = V_(t3), *w = V_(w);
         double r = rotation_chain(nZ);
 #ifndef QP_EXACT
-        if constexpr (TEAM > 32) rot_rows_auto(sA.oQ, nFR, nZ, sA.ot2, sA.ot3);
-        else
+        if constexpr (TEAM > 32) {
+            rot_rows_auto(sA.oQ, nFR, nZ, sA.ot2, sA.ot3);
+            if (carry_R) update_R_after_add(nZ);  // before the new row of T below: with nFR == cap it lands on row nZ-1 of R
+        } else
 #endif
         {
         QP_U1 for (int p = lane; p < nFR; p += TEAM) {
@@ -1424,7 +1589,7 @@ struct QPT {
         SYNC();
         return z2;
     }
-    static __device__ QP_FN void add_bound(int v, int status) {
+    static __device__ QP_FN void add_bound(int v, int status, bool carry_R = false) {
         QP_CTX
         const int nFR = hdr[0], nAC = hdr[1], nZ = nFR - nAC;
         double *Q = V_(Q), *RT = V_(RT);
@@ -1433,8 +1598,10 @@ struct QPT {
         const int p = posFR[v];
         rotation_chain(nFR);
 #ifndef QP_EXACT
-        if constexpr (TEAM > 32) rot_rows_auto(sA.oQ, nFR, nFR, sA.ot2, sA.ot3);
-        else
+        if constexpr (TEAM > 32) {
+            rot_rows_auto(sA.oQ, nFR, nFR, sA.ot2, sA.ot3);
+            if (carry_R) update_R_after_add(nZ);  // the first nZ-1 rotations of the chain act inside the null space
+        } else
 #endif
         {
         QP_U1 for (int pp = lane; pp < nFR; pp += TEAM) {
@@ -1839,6 +2006,7 @@ struct QPT {
         QP_CTX
         const int nT = nV + nC;
         const int flags = sA.flags;
+        int carried = 0;  // additions since R was last recomputed (one-QP-per-cluster kernel)
         double *x = V_(x), *y = V_(y), *Ax = V_(Ax), *g = V_(g), *lb = V_(lb), *ub = V_(ub), *lbA = V_(lbA), *ubA = V_(ubA);
         double *dx = V_(dx), *dy = V_(dy), *dAx = V_(dAx), *w = V_(w), *a = V_(a);
         const double *gN = V_(gN), *lbN = V_(lbN), *ubN = V_(ubN), *lbAN = V_(lbAN), *ubAN = V_(ubAN);
@@ -1975,6 +2143,12 @@ struct QPT {
                     PROF_RESET
                 }
             } else {
+                // one-QP-per-cluster kernel: R is carried through the addition (update_R_after_add) unless an exchange step left
+                // it one column short or REFAC_EVERY updates have accumulated
+                bool carry = false;
+#ifndef QP_EXACT
+                if constexpr (TEAM > 32) carry = !sA.is_lp && carried < REFAC_EVERY && hdr[0] - hdr[1] <= UPDATE_MAX_NZ && !(sA.flags & FLAG_NO_CARRY);
+#endif
                 if (bc_isbound) {
                     double z2 = bound_w(bc_idx);
                     PROF_ADD(PR_WVEC);
@@ -1982,9 +2156,10 @@ struct QPT {
                         int e_ = ensure_li(-1, bc_idx, bc_status);
                         if (e_) { iters = it; return e_ == 2 ? ST_CAPACITY : ST_INFEASIBLE; }
                         bound_w(bc_idx);
+                        carry = false;
                         PROF_ADD(PR_ENSURE_LI);
                     }
-                    add_bound(bc_idx, bc_status);
+                    add_bound(bc_idx, bc_status, carry);
                     PROF_ADD(PR_ADD);
                 } else {
                     double z2, a2;
@@ -1994,12 +2169,17 @@ struct QPT {
                         int e_ = ensure_li(bc_idx, -1, bc_status);
                         if (e_) { iters = it; return e_ == 2 ? ST_CAPACITY : ST_INFEASIBLE; }
                         constraint_w(bc_idx, z2, a2);
+                        carry = false;
                         PROF_ADD(PR_ENSURE_LI);
                     }
-                    add_constraint(bc_idx, bc_status);
+                    add_constraint(bc_idx, bc_status, carry);
                     PROF_ADD(PR_ADD);
                 }
-                if (recompute_R()) { iters = it; return ST_INTERNAL; }
+                if (carry) carried++;
+                else {
+                    if (recompute_R()) { iters = it; return ST_INTERNAL; }
+                    carried = 0;
+                }
                 PROF_RESET
             }
             if (tau <= QP_EPS && (flags & FLAG_RAMPING)) ramping();

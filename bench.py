@@ -212,6 +212,17 @@ def run_gpu(args, rank, world, local_rank):
         h2d += lay["in_bytes"] + Av.numel() * 8 + Hv.numel() * 8
         d2h += lay["out_bytes"]
         groups.append(dict(q=q, s=s, inb=inb, outb=outb, Av=Av, Hv=Hv, lay=lay, nV=d["nV"], nC=d["nC"]))
+    # End-to-end path, double-buffered: a second handle per dumped QP (own device arena, own stream, own pinned result block,
+    # the same pinned inputs), so that the uploads of step k+1 run while step k is being solved, as a host that replays a stream
+    # of batches would arrange it.  Every step still uploads all its inputs and downloads all its results.
+    groups_b = []
+    if args.e2e_overlap:
+        for gr in groups:
+            q = gr["q"]
+            s2 = r.CudaQPInterface(nV=gr["nV"], nC=gr["nC"], qptype=r.QPType.QP, batch=B, device=local_rank, keep_state=False, team_size=args.team)
+            s2.set_csc(capi.MAT_A, q["A_colptr"], q["A_rowidx"], gr["Av"].numpy())
+            s2.set_csc(capi.MAT_H, q["H_colptr"], q["H_rowidx"], gr["Hv"].numpy())
+            groups_b.append(dict(gr, s=s2, outb=torch.zeros(gr["lay"]["out_bytes"], dtype=torch.uint8).pin_memory()))
     torch.cuda.synchronize()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     # one CUDA stream per dumped QP: the independent solve launches of a step overlap, so small groups fill the
@@ -248,6 +259,41 @@ def run_gpu(args, rank, world, local_rank):
             gr["s"].solve_host(r.QPType.QP, gr["inb"].data_ptr(), gr["Av"].data_ptr(), gr["Hv"].data_ptr(), gr["outb"].data_ptr())
         join()
 
+    streams_b = [torch.cuda.Stream() for _ in groups_b]
+    for gr, st in zip(groups_b, streams_b):
+        gr["s"].set_stream(st.cuda_stream)
+
+    def run_e2e_overlapped(n):
+        """n steps; step k goes to handle set k % 2.  All streams start after the current stream and are joined at the end."""
+        ev = torch.cuda.Event()
+        ev.record()
+        for st in (streams or []) + streams_b:
+            st.wait_event(ev)
+        for k in range(n):
+            for gr in (groups if k % 2 == 0 else groups_b):
+                gr["s"].solve_host(r.QPType.QP, gr["inb"].data_ptr(), gr["Av"].data_ptr(), gr["Hv"].data_ptr(), gr["outb"].data_ptr())
+        cur = torch.cuda.current_stream()
+        for st in (streams or []) + streams_b:
+            cur.wait_stream(st)
+
+    def timed_e2e_overlapped(steps, warmup):
+        run_e2e_overlapped(warmup)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_e2e_overlapped(steps)
+        e1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def timed(fn, steps, warmup, collect_kernel_ms=False):
         for _ in range(warmup):
             fn()
@@ -283,12 +329,15 @@ def run_gpu(args, rank, world, local_rank):
     cal = [gr["s"].last_solve_ms() for gr in groups]
     order = sorted(range(len(groups)), key=lambda i: -cal[i])
     groups[:] = [groups[i] for i in order]
+    if groups_b:
+        groups_b[:] = [groups_b[i] for i in order]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     use_streams(True)
     ms_res, launches, _ = timed(step_resident, args.steps, args.warmup)
-    ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    ms_e2e_serial, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))  # one step at a time (L2 flush + join between steps)
+    ms_e2e = timed_e2e_overlapped(args.steps, max(4, args.warmup)) if (groups_b and streams) else ms_e2e_serial
     clocks = sampler.stop() if rank == 0 else None  # sampled every 20 ms across both timed regions (and their warm-ups)
     # serial pass on the default stream, only to attribute device time to the solve kernel (per-launch CUDA events)
     torch.cuda.synchronize()
@@ -401,7 +450,11 @@ def run_gpu(args, rank, world, local_rank):
                        "team_size": args.team or "auto", "streams": len(streams) if streams else 1},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "api": "sqpb200_solve_host (CudaQPInterface.solve_host): per dumped QP one upload of the vector block, one each of the A and H "
-                           "values, the solve, one download of the result block"},
+                           "values, the solve, one download of the result block",
+                    "overlap": ("two handles per dumped QP alternate, so the copies of step k+1 overlap the solves of step k; every step uploads all "
+                                "inputs and downloads all results") if (groups_b and streams) else "none",
+                    "serial": {"value": qps_step * args.steps / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial / args.steps,
+                               "note": "one step at a time: L2 flush and a join of all streams between steps"}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d QPs (passes over %d replicas of each of the %d dumped QPs) in %.1f s" % (n, B, len(fixtures), t)},
@@ -648,6 +701,7 @@ def main():
     ap.add_argument("--team", type=int, default=0, help="threads per QP (0 = auto)")
     ap.add_argument("--extras", type=int, default=1, help="1: the other BASELINE configs on rank 0 when run on one GPU; 2: also under torchrun; 0: off")
     ap.add_argument("--strong", type=int, default=1000000, help="instances of the strong-scaling block (configs[4]); 0: off")
+    ap.add_argument("--e2e-overlap", type=int, default=1, help="1: the end-to-end path alternates two handle sets (consecutive steps overlap); 0: one step at a time")
     ap.add_argument("--streams", type=int, default=1, help="1: one CUDA stream per dumped QP (overlapping launches), 0: default stream")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -1111,7 +1111,10 @@ struct QPT {
     // ---- operations the leader shares with its helper CTAs: arguments go through the slice header (ints 4..15), offsets are
     // in doubles from the slice base.  Worth two cluster barriers only when the operand is large.
     enum { OP_REFAC = 1, OP_EXIT = 2, OP_COLSUMS = 3, OP_ROWSUMS = 4, OP_ROTROWS = 5, OP_DINV = 6 };
-    static constexpr int DIST_MIN_ELEMS = 1 << 17;  // below ~1 MB of factor data the leader works alone
+#ifndef QP_DIST_MIN_ELEMS
+#define QP_DIST_MIN_ELEMS (1 << 17)
+#endif
+    static constexpr int DIST_MIN_ELEMS = QP_DIST_MIN_ELEMS;  // below ~1 MB of factor data the leader works alone
     static __device__ __forceinline__ void run_op(int cmd, int rank, int cs) {
         QP_CTX
         volatile int* vh = hdr;
@@ -1153,7 +1156,10 @@ struct QPT {
     // (Z G)'H(Z G) restricted to the kept columns, the same matrix a recomputation factorises, in O(nZ^2) (qpOASES's own
     // update under its default options).  A full recomputation still runs every REFAC_EVERY additions, after an exchange
     // step (R is one column short there) and after a flipped bound.
-    static constexpr int REFAC_EVERY = 64;
+#ifndef QP_REFAC_EVERY
+#define QP_REFAC_EVERY 64
+#endif
+    static constexpr int REFAC_EVERY = QP_REFAC_EVERY;
     // inverses of the 64 x 64 diagonal blocks of R (n x n) into W, block b by CTA b % cs
     static __device__ __forceinline__ void dinv_blocks(int n, int rank, int cs) {
         QP_CTX
@@ -1184,7 +1190,7 @@ struct QPT {
     // k+1 .. k+4 are in flight in four register sets (the loop is unrolled by four so that the sets rotate without moves: an
     // L2 round trip per rotation otherwise); one barrier per rotation (the owner of column k publishes (c, s) through shared
     // memory).
-    template <int NQ>
+    template <int NQ, int DEPTH>
     static __device__ __noinline__ void retriangularise(int nZ) {
         QP_CTX
         double* RT = V_(RT);
@@ -1192,20 +1198,20 @@ struct QPT {
         const int tid = threadIdx.x, m = nZ - 1;
         const int nact = (m < TEAM) ? ((m + 31) & ~31) : TEAM;
         if (tid >= nact) { __syncthreads(); return; }
-        double cur[NQ], buf[4][NQ];  // buf[r & 3]: row r
+        double cur[NQ], buf[DEPTH][NQ];  // buf[r % DEPTH]: row r
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
             const int j = tid + TEAM * q;
             cur[q] = (j < m) ? R_(0, j) : 0.0;
 #pragma unroll
-            for (int r = 1; r <= 4; r++) buf[r & 3][q] = (j < m && j + 1 >= r && r < nZ) ? R_(r, j) : 0.0;
+            for (int r = 1; r <= DEPTH; r++) buf[r % DEPTH][q] = (j < m && j + 1 >= r && r < nZ) ? R_(r, j) : 0.0;
         }
-        for (int k0 = 0; k0 < m; k0 += 4) {
+        for (int k0 = 0; k0 < m; k0 += DEPTH) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < DEPTH; u++) {
                 const int k = k0 + u;
                 if (k >= m) break;
-                double* nxt = buf[(u + 1) & 3];  // row k+1 (k0 is a multiple of four)
+                double* nxt = buf[(u + 1) % DEPTH];  // row k+1 (k0 is a multiple of DEPTH)
                 if (tid == (k & (TEAM - 1))) {
                     double a = 0.0, b = 0.0;
 #pragma unroll
@@ -1221,14 +1227,97 @@ struct QPT {
                     const int j = tid + TEAM * q;
                     if (j >= k && j < m) {
                         const double a = cur[q], b = nxt[q];
-                        R_(k, j) = c * a + sn * b;
+                        R_(k, j) = fma(c, a, sn * b);
                         if (j == k) { R_(k + 1, k) = 0.0; cur[q] = 0.0; }
-                        else cur[q] = c * b - sn * a;
+                        else cur[q] = fma(c, b, -sn * a);
                     }
-                    nxt[q] = (j + 1 >= k + 5 && j < m && k + 5 < nZ) ? R_(k + 5, j) : 0.0;  // row k+5 takes the place of row k+1
+                    // row k + 1 + DEPTH takes the place of row k + 1
+                    nxt[q] = (j >= k + DEPTH && j < m && k + 1 + DEPTH < nZ) ? R_(k + 1 + DEPTH, j) : 0.0;
                 }
                 // row k + 32 towards L2, one 128-byte line per thread
                 if (k + 32 < nZ && tid * 16 < m && tid * 16 + 16 > k + 30) asm volatile("prefetch.global.L2 [%0];" ::"l"(&R_(k + 32, tid * 16)));
+            }
+        }
+        __syncthreads();
+    }
+    // The same elimination with four rotations per barrier (m <= 4 * TEAM): a thread owns the four adjacent columns
+    // 4 tid .. 4 tid + 3, so the owner of columns k0 .. k0+3 forms the rotations k0 .. k0+3 one after the other out of its own
+    // registers (applying each to its four columns before the next) and publishes all four at once; the other threads then
+    // apply the four rotations to their columns.  Rows k0+5 .. k0+8 are loaded while the group k0 is processed.
+    static __device__ __noinline__ void retriangularise4(int nZ) {
+        QP_CTX
+        double* RT = V_(RT);
+        double* sc = qp_smem + LS_RED;  // (c, s) of a group: 8 doubles, double-buffered
+        const int tid = threadIdx.x, m = nZ - 1, j0 = 4 * tid;
+        const int nact = (((m + 3) >> 2) + 31) & ~31;  // threads that own a column < m, whole warps
+        if (tid >= nact) { __syncthreads(); return; }
+        const bool full = j0 + 3 < m;
+        auto load4 = [&](int r, double (&v)[4]) {
+            if (r > m || j0 >= m || j0 + 4 < r) { v[0] = v[1] = v[2] = v[3] = 0.0; return; }  // row r is zero left of column r-1
+            const double* p = &R_(r, j0);
+            if (full) { const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2); v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+            else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) v[q] = (j0 + q < m) ? p[q] : 0.0;
+            }
+        };
+        auto store4 = [&](int r, const double (&v)[4]) {
+            if (j0 >= m || j0 + 3 < r) return;  // nothing on or right of the diagonal
+            double* p = &R_(r, j0);
+            if (full) { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]); }
+            else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (j0 + q < m) p[q] = v[q];
+            }
+        };
+        double cur[4], rows[2][4][4];  // rows[g & 1][u]: row k0 + 1 + u of group g = k0 / 4
+        load4(0, cur);
+#pragma unroll
+        for (int u = 0; u < 4; u++) load4(1 + u, rows[0][u]);
+        for (int kk = 0; kk < m; kk += 8) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int k0 = kk + 4 * h;
+                if (k0 >= m) break;
+                double (&rw)[4][4] = rows[h];
+#pragma unroll
+                for (int u = 0; u < 4; u++) load4(k0 + 5 + u, rows[h ^ 1][u]);
+                // rows k0 + 33 .. k0 + 36 towards L2, one 128-byte line per thread
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (k0 + 33 + u <= m && tid * 16 < m && tid * 16 + 16 > k0 + 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(&R_(k0 + 33 + u, tid * 16)));
+                double* o = sc + 8 * ((k0 >> 2) & 1);
+                const bool owner = (tid == (k0 >> 2));
+                if (owner) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (k0 + u < m) {
+                            const double a = cur[u], b = rw[u][u], h2 = a * a + b * b;
+                            double c = 1.0, sn = 0.0;
+                            if (h2 > 0.0) { const double ih = rsqrt(h2); c = a * ih; sn = b * ih; }
+                            o[2 * u] = c; o[2 * u + 1] = sn;
+                            double top[4];
+#pragma unroll
+                            for (int v = 0; v < 4; v++) { top[v] = fma(c, cur[v], sn * rw[u][v]); cur[v] = fma(c, rw[u][v], -sn * cur[v]); }
+                            cur[u] = 0.0;
+                            store4(k0 + u, top);
+                        }
+                    }
+                    if (k0 + 4 <= m) R_(k0 + 4, k0 + 3) = 0.0;  // the last eliminated entry lies in the next group's first row
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(nact) : "memory");
+                if (!owner && j0 > k0) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (k0 + u < m) {
+                            const double c = o[2 * u], sn = o[2 * u + 1];
+                            double top[4];
+#pragma unroll
+                            for (int v = 0; v < 4; v++) { top[v] = fma(c, cur[v], sn * rw[u][v]); cur[v] = fma(c, rw[u][v], -sn * cur[v]); }
+                            store4(k0 + u, top);
+                        }
+                    }
+                }
             }
         }
         __syncthreads();
@@ -1242,10 +1331,12 @@ struct QPT {
         PROF_T0
         rot_rows_auto(sA.oRT, nZ, nZ, sA.ot2, sA.ot3, 0, 1, true);
         PROF_ADD(PR_REFAC_W);  // (profile build: the three slots of the recomputation show the update's steps)
-        if (m <= TEAM) retriangularise<1>(nZ);
-        else if (m <= 2 * TEAM) retriangularise<2>(nZ);
-        else if (m <= 4 * TEAM) retriangularise<4>(nZ);
-        else retriangularise<8>(nZ);
+#ifndef QP_RETRI_DEPTH
+#define QP_RETRI_DEPTH 4
+#endif
+        if (m <= TEAM) retriangularise<1, QP_RETRI_DEPTH>(nZ);
+        else if (m <= 4 * TEAM) retriangularise4(nZ);
+        else retriangularise<8, 4>(nZ);
         PROF_ADD(PR_REFAC_M);
         if (sClusterSize > 1 && m > TEAM) dist_op(OP_DINV, 0, m, 0, 0, 0, 0, 0);
         else dinv_blocks(m, 0, 1);

@@ -16,9 +16,11 @@ static int cluster_for_batch(int batch, int nV) {
     if (const char* e = getenv("SQPB200_CLUSTER")) { int v = atoi(e); if (v >= 1 && v <= 16 && (v & (v - 1)) == 0) return v; }
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // a cluster barrier costs microseconds, and more with 16 CTAs: the non-portable size only pays at nV >= 2048
-    // (measured: n = 64 runs 8.7 ms with 8 CTAs per QP, 10-12 ms with one, 15-19 ms with 16)
-    const int cap = nV < 64 ? 1 : (nV < 2048 ? 8 : 16);
+    // Every shared primitive costs two cluster barriers, and since R is carried through additions the refactorisation (the
+    // one phase that scales with the CTA count) is rare.  Measured (ms; CTAs per QP in brackets): nV = 128 x 8: 8.5 [1], 8.5 [2],
+    // 9.7 [4]; nV = 512 x 16: 92 [1], 91 [2], 87 [4], 161 [8]; nV = 1024 x 16: 371 [2], 326 [4], 546 [8]; nV = 2048 x 16:
+    // 2854 [2], 2330 [4], 3263 [8]; nV = 4096 x 4: 13312 [4], 11548 [8], 10817 [16] (non-portable size).
+    const int cap = nV < 64 ? 1 : (nV <= 256 ? 2 : (nV <= 2048 ? 4 : (nV <= 3072 ? 8 : 16)));
     int cs = 1;
     while (cs < cap && (long long)batch * cs * 2 <= sms) cs *= 2;  // 16 = non-portable cluster size (opt-in below), batch <= 9
     return cs;

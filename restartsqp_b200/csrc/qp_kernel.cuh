@@ -732,43 +732,60 @@ struct QPT {
         for (int k = 0; k < TEAM / 32; k++) t += sRedT[k];
         return t;
     }
-    // out[j] = sgn * sum_{p < nP} M[p * ld + j] * v[p] for j0 <= j < j1 (columns over the lanes, the p range cut into 8 slices)
+    // out[j] = sgn * sum_{p < nP} M[p * ld + j] * v[p] for j0 <= j < j1: blocks of 64 columns (even-aligned), a lane on two adjacent
+    // columns (one 16-byte load per row), warp w on the rows w, w + 16, ...; eight loads in flight per lane
     static __device__ __forceinline__ void col_sums(const double* M, int ld, int nP, int j0, int j1, const double* v, double* out, double sgn,
                                                     int rank = 0, int cs = 1) {
-        double* red = qp_smem + LS_RED;
-        const int tid = threadIdx.x, c = tid & 63, sl = tid >> 6;
-        for (int jb = j0 + 64 * rank; jb < j1; jb += 64 * cs) {
-            const int j = jb + c;
+        double* red16 = qp_smem;  // [16][64] (the tile ring is idle outside the refactorisation)
+        const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+        for (int jb = (j0 & ~1) + 64 * rank; jb < j1; jb += 64 * cs) {
+            const int j = jb + 2 * l;
             double s0 = 0.0, s1 = 0.0;
             if (j < j1) {
-                int pp = sl;
-#pragma unroll 4
-                for (; pp + 8 < nP; pp += 16) { s0 += M[(size_t)pp * ld + j] * v[pp]; s1 += M[(size_t)(pp + 8) * ld + j] * v[pp + 8]; }
-                if (pp < nP) s0 += M[(size_t)pp * ld + j] * v[pp];
+                const double* base = M + j;
+#pragma unroll 8
+                for (int pp = warp; pp < nP; pp += TEAM / 32) {
+                    const double2 m = *reinterpret_cast<const double2*>(base + (size_t)pp * ld);
+                    const double vp = v[pp];
+                    s0 += m.x * vp; s1 += m.y * vp;
+                }
             }
-            red[sl * 64 + c] = s0 + s1;
+            red16[warp * 64 + 2 * l] = s0; red16[warp * 64 + 2 * l + 1] = s1;
             __syncthreads();
-            if (tid < 64 && jb + tid < j1) {
+            if (tid < 64 && jb + tid >= j0 && jb + tid < j1) {
                 double t = 0.0;
 #pragma unroll
-                for (int q = 0; q < 8; q++) t += red[q * 64 + tid];
+                for (int q = 0; q < TEAM / 32; q++) t += red16[q * 64 + tid];
                 out[jb + tid] = sgn * t;
             }
             __syncthreads();
         }
     }
-    // s_p = sum_{j0 <= j < j1} M[p * ld + j] * v[j] for p < nP, one warp per row; out[idx ? idx[p] : p] (+)= s_p
+    // s_p = sum_{j0 <= j < j1} M[p * ld + j] * v[j] for p < nP, a warp on four rows at a time, a lane on two adjacent columns
+    // (16-byte loads); out[idx ? idx[p] : p] (+)= s_p
     static __device__ __forceinline__ void row_sums(const double* M, int ld, int nP, int j0, int j1, const double* v, double* out,
                                                     const short* idx, bool accumulate, int rank = 0, int cs = 1) {
-        const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
-        for (int pr = warp + (TEAM / 32) * rank; pr < nP; pr += (TEAM / 32) * cs) {
-            const double* row = M + (size_t)pr * ld;
-            double s0 = 0.0;
-#pragma unroll 4
-            for (int j = j0 + l; j < j1; j += 32) s0 += row[j] * v[j];
+        const int warp = threadIdx.x >> 5, l = threadIdx.x & 31, ja = j0 & ~1;
+        for (int pr = (warp + (TEAM / 32) * rank) * 4; pr < nP; pr += (TEAM / 32) * cs * 4) {
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+            for (int j = ja + 2 * l; j < j1; j += 64) {
+                const bool lo = j >= j0, hi = j + 1 < j1;
+                const double v0 = lo ? v[j] : 0.0, v1 = hi ? v[j + 1] : 0.0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            if (l == 0) { const int k = idx ? idx[pr] : pr; out[k] = accumulate ? out[k] + s0 : s0; }
+                for (int q = 0; q < 4; q++)
+                    if (pr + q < nP) {
+                        const double2 m = *reinterpret_cast<const double2*>(M + (size_t)(pr + q) * ld + j);
+                        s4[q] += (lo ? m.x * v0 : 0.0) + (hi ? m.y * v1 : 0.0);
+                    }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                double sq = s4[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                if (l == 0 && pr + q < nP) { const int k = idx ? idx[pr + q] : pr + q; out[k] = accumulate ? out[k] + sq : sq; }
+            }
         }
         __syncthreads();
     }
@@ -917,13 +934,15 @@ struct QPT {
         const int tid = threadIdx.x;
         for (int k = tid; k < LT_NB * LT_NB; k += TEAM) { const int i = k >> 6, j = k & 63; X[i * LT_D_LD + j] = (i == j && i >= nb) ? 1.0 : 0.0; }
         __syncthreads();
+        if (tid < nb) X[tid * LT_D_LD + tid] = 1.0 / D[tid * LT_D_LD + tid];
+        __syncthreads();
         if (tid < nb) {
             const int c = tid, g0 = c & ~7;
-            X[c * LT_D_LD + c] = 1.0 / D[c * LT_D_LD + c];
             for (int r = c - 1; r >= g0; r--) {
                 double sacc = 0.0;
+#pragma unroll 4
                 for (int l = r + 1; l <= c; l++) sacc += D[r * LT_D_LD + l] * X[l * LT_D_LD + c];
-                X[r * LT_D_LD + c] = -sacc / D[r * LT_D_LD + r];
+                X[r * LT_D_LD + c] = -sacc * X[r * LT_D_LD + r];
             }
         }
         __syncthreads();
@@ -933,27 +952,33 @@ struct QPT {
             // T = D12 X22 (X22 upper triangular: k <= j)
             for (int e = tid; e < 32 * sz; e += TEAM) {
                 const int j = e & (sz - 1), i = (e >> lg) & (sz - 1), pr = e >> (2 * lg), a0 = pr * 2 * sz, b0 = a0 + sz;
-                double s0 = 0.0, s1 = 0.0;
+                const double* dr = D + (a0 + i) * LT_D_LD + b0;
+                const double* xc = X + b0 * LT_D_LD + b0 + j;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 int k = 0;
-                for (; k + 1 <= j; k += 2) {
-                    s0 += D[(a0 + i) * LT_D_LD + b0 + k] * X[(b0 + k) * LT_D_LD + b0 + j];
-                    s1 += D[(a0 + i) * LT_D_LD + b0 + k + 1] * X[(b0 + k + 1) * LT_D_LD + b0 + j];
+#pragma unroll 2
+                for (; k + 3 <= j; k += 4) {
+                    s0 += dr[k] * xc[k * LT_D_LD]; s1 += dr[k + 1] * xc[(k + 1) * LT_D_LD];
+                    s2 += dr[k + 2] * xc[(k + 2) * LT_D_LD]; s3 += dr[k + 3] * xc[(k + 3) * LT_D_LD];
                 }
-                if (k <= j) s0 += D[(a0 + i) * LT_D_LD + b0 + k] * X[(b0 + k) * LT_D_LD + b0 + j];
-                T[(a0 + i) * LT_D_LD + b0 + j] = (a0 + i < nb && b0 + j < nb) ? s0 + s1 : 0.0;
+                for (; k <= j; k++) s0 += dr[k] * xc[k * LT_D_LD];
+                T[(a0 + i) * LT_D_LD + b0 + j] = (a0 + i < nb && b0 + j < nb) ? (s0 + s1) + (s2 + s3) : 0.0;
             }
             __syncthreads();
             // X12 = -X11 T (X11 upper triangular: k >= i)
             for (int e = tid; e < 32 * sz; e += TEAM) {
                 const int j = e & (sz - 1), i = (e >> lg) & (sz - 1), pr = e >> (2 * lg), a0 = pr * 2 * sz, b0 = a0 + sz;
-                double s0 = 0.0, s1 = 0.0;
+                const double* xr = X + (a0 + i) * LT_D_LD + a0;
+                const double* tc = T + a0 * LT_D_LD + b0 + j;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 int k = i;
-                for (; k + 1 < sz; k += 2) {
-                    s0 += X[(a0 + i) * LT_D_LD + a0 + k] * T[(a0 + k) * LT_D_LD + b0 + j];
-                    s1 += X[(a0 + i) * LT_D_LD + a0 + k + 1] * T[(a0 + k + 1) * LT_D_LD + b0 + j];
+#pragma unroll 2
+                for (; k + 3 < sz; k += 4) {
+                    s0 += xr[k] * tc[k * LT_D_LD]; s1 += xr[k + 1] * tc[(k + 1) * LT_D_LD];
+                    s2 += xr[k + 2] * tc[(k + 2) * LT_D_LD]; s3 += xr[k + 3] * tc[(k + 3) * LT_D_LD];
                 }
-                if (k < sz) s0 += X[(a0 + i) * LT_D_LD + a0 + k] * T[(a0 + k) * LT_D_LD + b0 + j];
-                X[(a0 + i) * LT_D_LD + b0 + j] = -(s0 + s1);
+                for (; k < sz; k++) s0 += xr[k] * tc[k * LT_D_LD];
+                X[(a0 + i) * LT_D_LD + b0 + j] = -((s0 + s1) + (s2 + s3));
             }
             __syncthreads();
         }
@@ -1112,9 +1137,9 @@ struct QPT {
     // in doubles from the slice base.  Worth two cluster barriers only when the operand is large.
     enum { OP_REFAC = 1, OP_EXIT = 2, OP_COLSUMS = 3, OP_ROWSUMS = 4, OP_ROTROWS = 5, OP_DINV = 6 };
 #ifndef QP_DIST_MIN_ELEMS
-#define QP_DIST_MIN_ELEMS (1 << 17)
+#define QP_DIST_MIN_ELEMS (1 << 16)
 #endif
-    static constexpr int DIST_MIN_ELEMS = QP_DIST_MIN_ELEMS;  // below ~1 MB of factor data the leader works alone
+    static constexpr int DIST_MIN_ELEMS = QP_DIST_MIN_ELEMS;  // below ~0.5 MB of factor data the leader works alone (measured: 1 << 16 beats 1 << 17 by 3-6 %, 1 << 19 loses 10-20 %)
     static __device__ __forceinline__ void run_op(int cmd, int rank, int cs) {
         QP_CTX
         volatile int* vh = hdr;
@@ -1338,7 +1363,7 @@ struct QPT {
         else if (m <= 4 * TEAM) retriangularise4(nZ);
         else retriangularise<8, 4>(nZ);
         PROF_ADD(PR_REFAC_M);
-        if (sClusterSize > 1 && m > TEAM) dist_op(OP_DINV, 0, m, 0, 0, 0, 0, 0);
+        if (sClusterSize > 1 && m > LT_NB) dist_op(OP_DINV, 0, m, 0, 0, 0, 0, 0);
         else dinv_blocks(m, 0, 1);
         PROF_ADD(PR_REFAC_CHOL);
     }
@@ -1368,32 +1393,44 @@ struct QPT {
         double* RT = V_(RT);
         const double* W = V_(W);
         double* red = qp_smem + LS_RED;
+        double* red16 = qp_smem;  // [16][64]: the tile ring is idle during the substitutions
         double* tv = qp_smem + LS_TV;
-        const int tid = threadIdx.x, c = tid & 63, sl = tid >> 6;
+        const int tid = threadIdx.x, c = tid & 63, sl = tid >> 6, warp = tid >> 5, l = tid & 31;
         for (int i0 = 0; i0 < n; i0 += LT_NB) {
             const int nb = (n - i0 < LT_NB) ? n - i0 : LT_NB;
-            // strip product: partial sums over k = sl, sl + 8, ... < i0
-            double s = 0.0;
-            if (c < nb) {
-#pragma unroll 16
-                for (int k = sl; k < i0; k += 8) s += R_(k, i0 + c) * z[k];
+            // the block inverse goes to registers first: its loads are in flight during the strip product
+            double dreg[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const int k = sl + 8 * q; dreg[q] = (c < nb && k <= c) ? W[(size_t)(i0 + k) * ld + c] : 0.0; }
+            // strip product: a lane owns the columns i0 + 2l, i0 + 2l + 1 (one 16-byte load per row), warp w the rows w, w + 16, ...
+            {
+                double s0 = 0.0, s1 = 0.0;
+                if (2 * l < nb) {
+                    const double* base = &R_(0, i0 + 2 * l);
+#pragma unroll 8
+                    for (int k = warp; k < i0; k += TEAM / 32) {
+                        const double2 v = *reinterpret_cast<const double2*>(base + (size_t)k * ld);
+                        const double zk = z[k];
+                        s0 += v.x * zk; s1 += v.y * zk;
+                    }
+                }
+                if (l < 32) { red16[warp * LT_NB + 2 * l] = s0; red16[warp * LT_NB + 2 * l + 1] = s1; }
             }
-            red[sl * LT_NB + c] = s;
             __syncthreads();
             if (tid < LT_NB) {
                 double tsum = 0.0;
 #pragma unroll
-                for (int q = 0; q < 8; q++) tsum += red[q * LT_NB + tid];
+                for (int q = 0; q < TEAM / 32; q++) tsum += red16[q * LT_NB + tid];
                 tv[tid] = (tid < nb) ? z[i0 + tid] - tsum : 0.0;
             }
             __syncthreads();
             // u_c = sum_{k <= c} Dinv[k][c] t_k
-            s = 0.0;
-            if (c < nb) {
-#pragma unroll 8
-                for (int k = sl; k <= c; k += 8) s += W[(size_t)(i0 + k) * ld + c] * tv[k];
+            {
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) s += dreg[q] * tv[sl + 8 * q];
+                red[sl * LT_NB + c] = s;
             }
-            red[sl * LT_NB + c] = s;
             __syncthreads();
             if (tid < nb) {
                 double u = 0.0;
@@ -1414,13 +1451,24 @@ struct QPT {
         const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
         for (int i0 = ((n - 1) >> 6) << 6; i0 >= 0; i0 -= LT_NB) {
             const int nb = (n - i0 < LT_NB) ? n - i0 : LT_NB, i1 = i0 + nb;
-            {   // the warp's four rows (warp, warp + 16, ...) together: four independent load streams per lane
+            // the warp's rows of the block inverse first (row r: columns r + l, r + l + 32), in flight during the strip product
+            double dreg[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int r = warp + (TEAM / 32) * q;
+#pragma unroll
+                for (int h = 0; h < 2; h++) { const int cc = r + l + 32 * h; dreg[q][h] = (r < nb && cc < nb) ? W[(size_t)(i0 + r) * ld + cc] : 0.0; }
+            }
+            {   // the warp's four rows (warp, warp + 16, ...) together, a lane on the columns k, k + 1 (16-byte loads; i1 is even)
                 double s4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 2
-                for (int k = i1 + l; k < n; k += 32) {
-                    const double zk = z[k];
+                for (int k = i1 + 2 * l; k < n; k += 64) {
+                    const double zk = z[k], zk1 = (k + 1 < n) ? z[k + 1] : 0.0;
 #pragma unroll
-                    for (int q = 0; q < 4; q++) { const int r = warp + (TEAM / 32) * q; if (r < nb) s4[q] += R_(i0 + r, k) * zk; }
+                    for (int q = 0; q < 4; q++) {
+                        const int r = warp + (TEAM / 32) * q;
+                        if (r < nb) { const double2 v = *reinterpret_cast<const double2*>(&R_(i0 + r, k)); s4[q] += v.x * zk + ((k + 1 < n) ? v.y * zk1 : 0.0); }
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -1432,12 +1480,15 @@ struct QPT {
                 }
             }
             __syncthreads();
-            for (int r = warp; r < nb; r += TEAM / 32) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int r = warp + (TEAM / 32) * q;
                 double s = 0.0;
-                for (int cc = r + l; cc < nb; cc += 32) s += W[(size_t)(i0 + r) * ld + cc] * tv[cc];
+#pragma unroll
+                for (int h = 0; h < 2; h++) { const int cc = r + l + 32 * h; if (r < nb && cc < nb) s += dreg[q][h] * tv[cc]; }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (l == 0) z[i0 + r] = s;
+                if (l == 0 && r < nb) z[i0 + r] = s;
             }
             __syncthreads();
         }

@@ -1359,6 +1359,9 @@ struct QPT {
 #ifndef QP_RETRI_DEPTH
 #define QP_RETRI_DEPTH 4
 #endif
+        // (a panel variant -- one warp eliminating 32 columns out of registers, then all threads applying the 32 rotations to
+        // their columns -- measured no faster: the chain of dependent FP64 operations per rotation, ~0.3 us, is what bounds all
+        // three forms)
         if (m <= TEAM) retriangularise<1, QP_RETRI_DEPTH>(nZ);
         else if (m <= 4 * TEAM) retriangularise4(nZ);
         else retriangularise<8, 4>(nZ);

@@ -85,6 +85,10 @@ typedef struct {
     int debug_force_error_branch; /* test hook, 0 in production: every solve runs handle_error's infeasible branch after its first
                             attempt (re-init from the slack-feasible guess x0 = [0; max(0, lbA); -min(0, ubA)],
                             src/qpOASESInterface.cpp:716-729), which a feasible l1-penalty QP otherwise never reaches */
+    int refactorise_every; /* one-QP-per-cluster kernel (team_size 1024) only.  0 (default): the projected Cholesky factor is carried
+                            through an addition by rotations and recomputed every 64th addition; 1: recomputed after every
+                            addition, as qpOASES does under setToReliable (enableCholeskyRefactorisation = 1) and as the warp
+                            kernel always does.  Same matrix either way; O(nZ^2) against O(nZ^3) per working-set change. */
 } sqpb200_options;
 
 void sqpb200_default_options(sqpb200_options* o);

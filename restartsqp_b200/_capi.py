@@ -36,7 +36,8 @@ EXPORTS = [
 class Options(C.Structure):
     _fields_ = [("qp_maxiter", C.c_int), ("lp_maxiter", C.c_int), ("enable_flipping", C.c_int),
                 ("enable_ramping", C.c_int), ("enable_drift", C.c_int), ("team_size", C.c_int),
-                ("keep_state", C.c_int), ("factor_cap", C.c_int), ("debug_force_error_branch", C.c_int)]
+                ("keep_state", C.c_int), ("factor_cap", C.c_int), ("debug_force_error_branch", C.c_int),
+                ("refactorise_every", C.c_int)]
 
 
 _LIB = None

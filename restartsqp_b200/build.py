@@ -23,8 +23,9 @@ TEAMS = [(32, 128, 16), (32, 64, 16), (32, 32, 16), (32, 128, 32),
          (16, 128, 16), (8, 128, 16)]
 LARGE_CTA = int(os.environ.get("SQPB200_LARGE_CTA", "512"))  # threads of the one-QP-per-CTA kernel (large QPs)
 QP_EXTRA_FLAGS = os.environ.get("SQPB200_QP_FLAGS", "").split()
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC"]
+# SQPB200_FMAD=true: experiment only -- contraction into FMA breaks the bit-for-bit agreement of the warp kernel with the oracle
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=" + os.environ.get("SQPB200_FMAD", "false"), "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():

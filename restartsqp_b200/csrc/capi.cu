@@ -132,6 +132,7 @@ void sqpb200_default_options(sqpb200_options* o) {
     o->keep_state = 1;
     o->factor_cap = 0;
     o->debug_force_error_branch = 0;
+    o->refactorise_every = 0;
 }
 
 const char* sqpb200_version(void) { return "sqpb200 0.1 (sm_100a)"; }
@@ -876,7 +877,7 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
     a.max_iter = maxiter > 0 ? maxiter : (is_lp ? h->opt.lp_maxiter : h->opt.qp_maxiter);
     a.flags = (h->opt.enable_flipping ? FLAG_FLIPPING : 0) | (h->opt.enable_ramping ? FLAG_RAMPING : 0) |
               (h->opt.enable_drift ? FLAG_DRIFT : 0) | (h->opt.keep_state ? FLAG_KEEP_STATE : 0) |
-              (h->opt.debug_force_error_branch ? FLAG_FORCE_GUESS : 0) | (large_recompute() ? FLAG_NO_CARRY : 0);
+              (h->opt.debug_force_error_branch ? FLAG_FORCE_GUESS : 0) | ((large_recompute() || h->opt.refactorise_every == 1) ? FLAG_NO_CARRY : 0);
     a.mode = mode;
     a.Ap = h->dAp; a.Ai = h->dAi; a.Arp = h->dArp; a.Aci = h->dAci; a.Aperm = h->dAperm;
     a.Hp = h->dHp; a.Hi = h->dHi;

@@ -28,7 +28,7 @@ class CudaQPInterface:
     """Batched QP/LP backend.  nV = nVar_QP, nC = nConstr_QP (src/qpOASESInterface.cpp:46-47)."""
 
     def __init__(self, nlp_info=None, qptype=QPType.QP, options=None, batch=1, device=0, nV=None, nC=None,
-                 team_size=0, keep_state=True, factor_cap=0, debug_force_error_branch=False):
+                 team_size=0, keep_state=True, factor_cap=0, debug_force_error_branch=False, refactorise_every=0):
         self.L = capi.lib()
         self.options = options if options is not None else Options()
         if nlp_info is not None:  # constructor (NLPInfo, QPType, options): src/qpOASESInterface.cpp:35-50
@@ -40,6 +40,7 @@ class CudaQPInterface:
         o.qp_maxiter, o.lp_maxiter = self.options.qp_maxiter, self.options.lp_maxiter
         o.team_size, o.keep_state, o.factor_cap = team_size, int(keep_state), int(factor_cap)
         o.debug_force_error_branch = int(bool(debug_force_error_branch))
+        o.refactorise_every = int(refactorise_every)
         self.h = C.c_void_p()
         rc = self.L.sqpb200_create(self.batch, self.nV_, self.nC_, int(self.qptype), device, C.byref(o), C.byref(self.h))
         if rc < 0:

@@ -315,8 +315,8 @@ def test_factor_capacity_rescue_path(gpu_lib, cap):
 @pytest.mark.parametrize("name", ["QORE_hs104", "QORE_hs107", "QORE_hs116"])
 def test_dumped_qp_on_cta_per_qp_kernel(gpu_lib, name):
     """The one-QP-per-CTA kernel (slice in global memory) runs the same active-set code with the refactorisation on the
-    FP64 tensor cores (DMMA accumulates in a different order than the oracle's scalar sums; -DQP_EXACT builds the bit-exact
-    scalar variant).  Its gate is north_star's: same status, and where the oracle solves the QP the same objective to 1e-8 and
+    FP64 tensor cores (DMMA accumulates in a different order than the oracle's scalar sums, and the factor is updated rather
+    than recomputed after most additions; -DQP_EXACT builds the bit-exact scalar variant).  Its gate is north_star's: same status, and where the oracle solves the QP the same objective to 1e-8 and
     a KKT point by the reference's own test.  On the rho = 1e8 scaled dump (hs104) the homotopy path is rounding-sensitive,
     so iteration counts may differ while the solution does not; the well-scaled hs116 must keep the oracle's working set."""
     q = [f for f in FIX if f["name"] == name][0]
@@ -360,6 +360,34 @@ def test_synthetic_large_config4(gpu_lib, n, B, checked):
         o = H.oracle_solve(orc, p, Acsc=d["Ac"], Hcsc=d["Hc"], max_iter=100000)
         check_against_oracle(s, b, o, nV)
     s.close()
+
+
+@pytest.mark.parametrize("n,B", [(96, 6), (200, 4)])
+def test_cluster_kernel_factor_update_equals_recomputation(gpu_lib, n, B):
+    """The one-QP-per-cluster kernel carries the projected Cholesky factor through additions (column rotations, row
+    re-triangularisation, block inverses) and recomputes it every 64th addition; with refactorise_every = 1 it recomputes it
+    after every addition, which is what qpOASES does under setToReliable and what the warp kernel and the oracle do.  Both are
+    factors of the same matrix: same working sets and iteration counts, x and y to 1e-10, and both equal to the oracle."""
+    d = H.synthetic_large_qp(n, batch=B)
+    nV, nC = d["nV"], d["nC"]
+    res = []
+    for every in (0, 1):
+        s = r.CudaQPInterface(nV=nV, nC=nC, qptype=r.QPType.QP, batch=B, team_size=1024, refactorise_every=every)
+        s.set_csc(capi.MAT_A, *d["Ac"]); s.set_csc(capi.MAT_H, *d["Hc"])
+        s.set_g(d["g"]); s.set_lb(d["lb"]); s.set_ub(d["ub"]); s.set_lbA(d["lbA"]); s.set_ubA(d["ubA"])
+        s.optimizeQP()
+        assert (s.get_status() == 20).all() and s.test_optimality().all()
+        y = np.concatenate([s.get_multipliers_bounds(), s.get_multipliers_constr()], axis=1)
+        res.append((s.get_optimal_solution().copy(), y, s.get_iterations().copy(), s.get_working_set(translated=False)))
+        if every == 0:
+            o = H.oracle_solve(orc, dict(nV=nV, nC=nC, g=d["g"][0], lb=d["lb"][0], ub=d["ub"][0], lbA=d["lbA"][0], ubA=d["ubA"][0]),
+                               Acsc=d["Ac"], Hcsc=d["Hc"], max_iter=100000)
+            check_against_oracle(s, 0, o, nV)
+        s.close()
+    (x0, y0, it0, ws0), (x1, y1, it1, ws1) = res
+    assert (it0 == it1).all() and it0.min() > n // 2
+    assert (ws0[0] == ws1[0]).all() and (ws0[1] == ws1[1]).all()
+    assert relerr(x0, x1) <= 1e-10 and relerr(y0, y1) <= 1e-9
 
 
 def _dense_case(nV, nC, Hd, A, g, lb, ub, lbA, ubA):

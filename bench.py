@@ -662,9 +662,22 @@ def run_l0(device, peak):
         timed(lambda: L.sqpb200_qphandler_bounds(s.h, 0, n, m, p(delta), p(xl), p(xu), p(xk), p(cl), p(cu), p(ck), capi.LOC_DEVICE)))
     row("qphandler_g", 8 * (n + 1 + nV) * B, timed(lambda: L.sqpb200_qphandler_g(s.h, n, m, p(gr), p(rho), capi.LOC_DEVICE)))
     o5 = torch.empty(B, 5, dtype=torch.float64, device=dev)
-    row("kkt_test", (8 * (zA + zH + 5 * nV + 2 * nC + (nV + nC)) + 2 * (nV + nC) + 4 * (nV + nC) + 40) * B,
-        timed(lambda: L.sqpb200_kkt_residuals_recompute(s.h, p(o5), capi.LOC_DEVICE)))
+    kkt_bytes = 8 * (zA + zH + 5 * nV + 2 * nC + (nV + nC)) + 2 * (nV + nC) + 4 * (nV + nC) + 40
+    row("kkt_test", kkt_bytes * B, timed(lambda: L.sqpb200_kkt_residuals_recompute(s.h, p(o5), capi.LOC_DEVICE)))
+    out["kkt_test"]["data"] = "random vectors, x = y = 0 (dense violation terms)"
     s.close()
+    # the same kernel where test_optimality runs it: at the solutions of the dumped hs116 QP (replicated and perturbed)
+    Bk = 1 << 16
+    d = make_batch(q, Bk, 4242)
+    sk = r.CudaQPInterface(nV=nV, nC=nC, qptype=r.QPType.QP, batch=Bk, device=device, keep_state=False)
+    sk.set_csc(capi.MAT_A, q["A_colptr"], q["A_rowidx"], d["Av"]); sk.set_csc(capi.MAT_H, q["H_colptr"], q["H_rowidx"], d["Hv"])
+    sk.set_g(d["g"]); sk.set_lb(d["lb"]); sk.set_ub(d["ub"]); sk.set_lbA(d["lbA"]); sk.set_ubA(d["ubA"])
+    sk._solve(r.QPType.QP, None, None, 0)
+    o5k = torch.empty(Bk, 5, dtype=torch.float64, device=dev)
+    row("kkt_test_at_solution", kkt_bytes * Bk, timed(lambda: L.sqpb200_kkt_residuals_recompute(sk.h, p(o5k), capi.LOC_DEVICE)))
+    out["kkt_test_at_solution"]["data"] = "2^16 perturbed replicas of the dumped hs116 QP, after the solve (the state test_optimality sees)"
+    out["kkt_test_at_solution"]["kkt_error_max"] = float(o5k[:, 4].max().item())
+    sk.close()
     # value scatter through `order` (A6) and segmented assembly (A4/A5) on the Jacobian triplets of the same shape
     jr, jc = [], []
     for c in range(n):

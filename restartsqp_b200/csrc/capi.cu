@@ -846,6 +846,10 @@ static bool large_recompute() {
     static const bool v = [] { const char* e = getenv("SQPB200_LARGE_RECOMPUTE"); return e && e[0] == '1'; }();
     return v;
 }
+static bool flip_as_hotstart() {
+    static const bool v = [] { const char* e = getenv("SQPB200_FLIP_AS_HOTSTART"); return e && e[0] == '1'; }();
+    return v;
+}
 static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned char* active_mask, bool mask_on_device, signed char* inst_state) {
     if (!h) return SQPB200_ERR_INVALID;
     CK(cudaSetDevice(h->device));
@@ -877,7 +881,7 @@ static int solve_impl(sqpb200_handle h, int mode_qp, int maxiter, const unsigned
     a.max_iter = maxiter > 0 ? maxiter : (is_lp ? h->opt.lp_maxiter : h->opt.qp_maxiter);
     a.flags = (h->opt.enable_flipping ? FLAG_FLIPPING : 0) | (h->opt.enable_ramping ? FLAG_RAMPING : 0) |
               (h->opt.enable_drift ? FLAG_DRIFT : 0) | (h->opt.keep_state ? FLAG_KEEP_STATE : 0) |
-              (h->opt.debug_force_error_branch ? FLAG_FORCE_GUESS : 0) | ((large_recompute() || h->opt.refactorise_every == 1) ? FLAG_NO_CARRY : 0);
+              (h->opt.debug_force_error_branch ? FLAG_FORCE_GUESS : 0) | ((large_recompute() || h->opt.refactorise_every == 1) ? FLAG_NO_CARRY : 0) | (flip_as_hotstart() ? FLAG_FLIP_AS_HOTSTART : 0);
     a.mode = mode;
     a.Ap = h->dAp; a.Ai = h->dAi; a.Arp = h->dArp; a.Aci = h->dAci; a.Aperm = h->dAperm;
     a.Hp = h->dHp; a.Hi = h->dHi;

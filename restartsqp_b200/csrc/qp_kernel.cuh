@@ -53,7 +53,8 @@ enum { MODE_COLD = 0, MODE_HOT_FIXED = 1, MODE_HOT_VARIED = 2,
        MODE_REINIT = 3 /* FIXED <-> VARIED flip of the matrix status: init from the previous solution (src/qpOASESInterface.cpp:202-207) */ };
 enum { FLAG_FLIPPING = 1, FLAG_RAMPING = 2, FLAG_DRIFT = 4, FLAG_KEEP_STATE = 8,
        FLAG_FORCE_GUESS = 16 /* test hook: take handle_error's infeasible branch whatever the first attempt returned */,
-       FLAG_NO_CARRY = 32 /* one-QP-per-cluster kernel: recompute R after every addition (as the warp kernel does) instead of updating it */ };
+       FLAG_NO_CARRY = 32 /* one-QP-per-cluster kernel: recompute R after every addition (as the warp kernel does) instead of updating it */,
+       FLAG_FLIP_AS_HOTSTART = 64 /* experiment (SQPB200_FLIP_AS_HOTSTART=1): the matrix-status flip as a hot start with new matrices, round 1's approximation */ };
 
 struct QPKernelArgs {
     int batch, nV, nC;
@@ -2628,6 +2629,7 @@ template <int TEAM> static __device__ __forceinline__ void qp_solve_one(const QP
         __syncwarp(team_mask<TEAM>());  // every lane has read the state
         if (lane == 0 && !A.rescue) qp_instance_store(A.inst_state + 8 * (size_t)b, mode, oms, nms);
     }
+    if (mode == MODE_REINIT && (A.flags & FLAG_FLIP_AS_HOTSTART)) mode = MODE_HOT_VARIED;
     int status = 0;
     if (mode != MODE_COLD) {
         // restore the pre-solve image: everything but the factors verbatim, then Q (nFR x nFR), R (nZ x nZ), T (nAC x nFR)

@@ -176,6 +176,34 @@ def test_device_loop_second_order_correction_equals_host_loop(gpu_lib, name):
     alg.close(); dev.close()
 
 
+@pytest.mark.parametrize("name", ["hs006", "hs043", "hs100"])
+def test_device_loop_second_order_correction_equals_mirror_on_cpu_oracle(gpu_lib, name):
+    """Second-order correction against a CPU path that shares no QP arithmetic with the kernels: the numpy mirror of
+    Algorithm::Optimize with every QP / LP solved by the C oracle (tests/oracle_backend.py: the backend's state machine around
+    oracle_qp.c), the NLP evaluated by the same NVRTC evaluator.  Handle-level init / hotstart decisions on both sides
+    (per_instance_modes=False).  Identical exit flags, outer and QP iteration counts, penalty parameters, radii and iterates."""
+    import os
+    from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
+    from restartsqp_b200.sqp_device import DeviceBatchedSQP
+    from oracle_backend import OracleQPInterface
+    from test_hs_suite import HS_DIR, perturbed_starts
+    dev = DeviceNLP(AmplNLP(os.path.join(HS_DIR, name + ".nl")))
+    B = 24
+    X = perturbed_starts(dev.host, B, 2)
+    opt = r.Options(iter_max=120, second_order_correction=True)
+    mk = lambda info, qptype: r.QPhandler(info, qptype, opt, batch=B, backend=OracleQPInterface(info, qptype, opt, batch=B), refresh_ubA=True)
+    res_h = BatchedSQP(dev, x0=X, options=opt, make_handler=mk).Optimize()
+    alg = DeviceBatchedSQP(dev, x0=X, options=r.Options(iter_max=120, second_order_correction=True), per_instance_modes=False)
+    res_d = alg.Optimize()
+    res_off = DeviceBatchedSQP(dev, x0=X, options=r.Options(iter_max=120), per_instance_modes=False).Optimize()
+    assert (res_d.exitflag == res_h.exitflag).all() and (res_d.iters == res_h.iters).all() and (res_d.qp_iter == res_h.qp_iter).all()
+    assert (res_d.rho == res_h.rho).all() and (res_d.delta == res_h.delta).all()
+    fin = np.isfinite(res_h.x).all(axis=1)
+    assert np.array_equal(res_d.x[fin], res_h.x[fin])
+    assert (res_d.qp_iter != res_off.qp_iter).any()  # the correction was actually taken somewhere
+    alg.close(); dev.close()
+
+
 @pytest.mark.parametrize("name", ["hs015", "hs043", "hs071", "hs083", "hs093", "hs106", "hs108", "hs113", "hs116", "hs118"])
 def test_device_loop_per_instance_modes_equal_the_c_oracle(gpu_lib, name):
     """Default mode of DeviceBatchedSQP: the backend's init/hotstart state machine runs per instance inside the solve kernel, i.e.

@@ -797,37 +797,44 @@ struct QPT {
     // The chain runs over the logical columns j = 0 .. cnt-1, stored at column base + dir * j (dir = -1: the right-to-left
     // chains of the removals, whose rotation i acts on (c, c+1) with c decreasing: same recurrence with (c_j, -s_j)).
     // tri: M is upper triangular (row r zero left of column r), so the chain of a row group starts at its first fill-in.
-    // Groups of 32 rows, or of 16 / 8 while that leaves warps without work (the chain then runs on the first lanes only).
+    // Groups of 16 rows (8 while that leaves warps without work); the chain runs on the first lanes.  The 16 row loads of the
+    // next tile are issued before the chain of the current one, so a warp always has a tile in flight (a solve is bound by
+    // load latency: with loads only between the chains an SM moved ~11 GB/s here).
     static __device__ __forceinline__ void rot_rows(double* M, int ld, int nP, int cnt, const double* cs, const double* sn, int rank = 0,
                                                     int ncta = 1, int base = 0, int dir = 1, bool tri = false) {
         if (cnt <= 0) return;
         const int warp = threadIdx.x >> 5, l = threadIdx.x & 31, nwarps = (TEAM / 32) * ncta;
-        int G = 32;
+        constexpr int GM = 16;
+        int G = GM;
         while (G > 8 && (nP + G - 1) / G < nwarps) G >>= 1;
-        double* tile = qp_smem + (size_t)warp * (32 * 33);
+        double* tile = qp_smem + (size_t)warp * (GM * 33 + 64);
+        double* rotc = tile + GM * 33;  // (c, s) of the tile's 32 rotations: the chain must not wait for global loads
         for (int r0 = (warp + (TEAM / 32) * rank) * G; r0 < nP; r0 += nwarps * G) {
             const int nr = (nP - r0 < G) ? nP - r0 : G;
             const int jt0 = (tri && r0 > 0) ? ((r0 - 1) & ~31) : 0;
             double qa = (l < nr) ? M[(size_t)(r0 + l) * ld + base + dir * jt0] : 0.0;
+            double v[GM], cj, sj;
+            // originals of columns jt+1 .. jt+32 of the group's rows, and the rotations jt .. jt+31
+            auto issue = [&](int jt) {
+                const int j = jt + 1 + l;
+#pragma unroll
+                for (int u = 0; u < GM; u++) v[u] = (u < nr && j < cnt) ? M[(size_t)(r0 + u) * ld + base + dir * j] : 0.0;
+                cj = (j < cnt) ? cs[j - 1] : 1.0; sj = (j < cnt) ? sn[j - 1] : 0.0;
+            };
+            issue(jt0);
             for (int jt = jt0; jt < cnt; jt += 32) {
-                // originals of columns jt+1 .. jt+32: eight independent loads in flight per lane
-                {
-                    const int j = jt + 1 + l;
-                    for (int rr0 = 0; rr0 < nr; rr0 += 8) {
-                        double v[8];
 #pragma unroll
-                        for (int u = 0; u < 8; u++) v[u] = (rr0 + u < nr && j < cnt) ? M[(size_t)(r0 + rr0 + u) * ld + base + dir * j] : 0.0;
-#pragma unroll
-                        for (int u = 0; u < 8; u++) tile[(rr0 + u) * 33 + l] = v[u];
-                    }
-                }
+                for (int u = 0; u < GM; u++) tile[u * 33 + l] = v[u];
+                rotc[l] = cj; rotc[32 + l] = sj;
                 __syncwarp();
+                if (jt + 32 < cnt) issue(jt + 32);
                 if (l < nr) {
                     const int cmax = (cnt - jt < 32) ? cnt - jt : 32;
+#pragma unroll 4
                     for (int c = 0; c < cmax; c++) {
                         const int j = jt + c;
                         if (j + 1 < cnt) {
-                            const double co = cs[j], si = sn[j], qb = tile[l * 33 + c];
+                            const double co = rotc[c], si = rotc[32 + c], qb = tile[l * 33 + c];
                             tile[l * 33 + c] = co * qa - si * qb;
                             qa = si * qa + co * qb;
                         } else tile[l * 33 + c] = qa;

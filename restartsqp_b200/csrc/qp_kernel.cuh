@@ -829,16 +829,19 @@ struct QPT {
                 __syncwarp();
                 if (jt + 32 < cnt) issue(jt + 32);
                 if (l < nr) {
-                    const int cmax = (cnt - jt < 32) ? cnt - jt : 32;
-#pragma unroll 4
-                    for (int c = 0; c < cmax; c++) {
-                        const int j = jt + c;
-                        if (j + 1 < cnt) {
-                            const double co = rotc[c], si = rotc[32 + c], qb = tile[l * 33 + c];
-                            tile[l * 33 + c] = co * qa - si * qb;
-                            qa = si * qa + co * qb;
-                        } else tile[l * 33 + c] = qa;
+                    const int cmax = (cnt - jt < 32) ? cnt - jt : 32;       // columns of this tile
+                    const int crot = (cnt - 1 - jt < 32) ? cnt - 1 - jt : 32;  // rotations of this tile (the last column has none)
+                    double* tl = tile + l * 33;
+                    int c = 0;
+                    for (; c + 8 <= crot; c += 8) {  // operands of eight rotations first, then the dependent chain (s qa + c qb)
+                        double co[8], si[8], qb[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) { co[u] = rotc[c + u]; si[u] = rotc[32 + c + u]; qb[u] = tl[c + u]; }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) { tl[c + u] = co[u] * qa - si[u] * qb[u]; qa = si[u] * qa + co[u] * qb[u]; }
                     }
+                    for (; c < crot; c++) { const double co = rotc[c], si = rotc[32 + c], qb = tl[c]; tl[c] = co * qa - si * qb; qa = si * qa + co * qb; }
+                    if (c < cmax) tl[c] = qa;
                 }
                 __syncwarp();
                 for (int rr = 0; rr < nr; rr++) { const int j = jt + l; if (j < cnt) M[(size_t)(r0 + rr) * ld + base + dir * j] = tile[rr * 33 + l]; }

@@ -235,7 +235,10 @@ __shared__ int sRedP[32];
 #define T_(i, j) RT[(cap - 1 - (i)) * ld + (j)]
 // inner sequential sums: not unrolled in the warp kernel (instruction-cache footprint), unrolled 8x in the CTA kernel so
 // that the loads of consecutive terms overlap (the additions stay in order: no reassociation without fast-math)
-#define DOT_UNROLL _Pragma("unroll (TEAM <= 32 ? 1 : 8)")
+#ifndef QP_DOT_UNROLL_N
+#define QP_DOT_UNROLL_N 1
+#endif
+#define DOT_UNROLL _Pragma("unroll (TEAM <= 32 ? QP_DOT_UNROLL_N : 8)")
 #define SYNC() do { if (TEAM <= 32) __syncwarp(team_mask<TEAM>()); else __syncthreads(); } while (0)
 
 template <int TEAM>

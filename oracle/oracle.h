@@ -178,6 +178,7 @@ typedef struct {
     int iter_max, penalty_update, penalty_iter_max, qp_maxiter, lp_maxiter;
     double eta_c, eta_s, eta_e, gamma_c, gamma_e, delta, delta_min, delta_max, tol, penalty_update_tol, rho, rho_max,
         increase_parm, eps1, eps1_change_parm, eps2, opt_prim_fea_tol, opt_dual_fea_tol, opt_compl_tol, opt_stat_tol;
+    int second_order_correction; /* Options::second_order_correction (src/Options.cpp:26), off by default */
 } orc_sqp_problem;
 /* Algorithm::initialization + Optimize for one starting point (src/Algorithm.cpp:55-168, 438-472). */
 int orc_sqp_solve(const orc_sqp_problem* P, const double* x0, const double* lam0, double* x_out, double* f_out,

@@ -264,7 +264,8 @@ class _SqpProblem(C.Structure):
                 [(k, C.c_int) for k in ("iter_max", "penalty_update", "penalty_iter_max", "qp_maxiter", "lp_maxiter")] +
                 [(k, C.c_double) for k in ("eta_c", "eta_s", "eta_e", "gamma_c", "gamma_e", "delta", "delta_min", "delta_max", "tol",
                                            "penalty_update_tol", "rho", "rho_max", "increase_parm", "eps1", "eps1_change_parm", "eps2",
-                                           "opt_prim_fea_tol", "opt_dual_fea_tol", "opt_compl_tol", "opt_stat_tol")])
+                                           "opt_prim_fea_tol", "opt_dual_fea_tol", "opt_compl_tol", "opt_stat_tol")] +
+                [("second_order_correction", C.c_int)])
 
 
 class SqpOracle:
@@ -301,6 +302,7 @@ class SqpOracle:
         for k in ("eta_c", "eta_s", "eta_e", "gamma_c", "gamma_e", "delta", "delta_min", "delta_max", "tol", "penalty_update_tol", "rho", "rho_max",
                   "increase_parm", "eps1", "eps1_change_parm", "eps2", "opt_prim_fea_tol", "opt_dual_fea_tol", "opt_compl_tol", "opt_stat_tol"):
             setattr(P, k, float(getattr(o, k)))
+        P.second_order_correction = int(bool(getattr(o, "second_order_correction", False)))
         self.lam0 = _f64(nlp.Get_starting_point()[1])
 
     def solve_batch(self, x0, nthreads=0):

@@ -326,6 +326,45 @@ int orc_sqp_solve(const orc_sqp_problem* P, const double* x0, const double* lam0
             for (int i = 0; i < m; i++) S.neg_lam[i] = -S.lam_c[i];
             P->all(S.x_k, S.neg_lam, &f_tmp, c_tmp, S.grad, S.jac, S.hess);
             S.updA = S.updH = S.updBounds = S.updG = 1;
+        } else if (P->second_order_correction) {
+            /* second_order_correction (src/Algorithm.cpp:1140-1211): the QP again around the trial point with the gradient
+             * H_k p_k + g_k; its solution s_k is added to p_k and the ratio test repeated with the SOC QP's own objective as the
+             * predicted reduction (ratio_test reads get_obj_QP(), :728); p_k and the QP data are restored otherwise. */
+            backend* q = S.qp;
+            memcpy(S.g_new, S.p_k, sizeof(double) * n); /* p_k_tmp (g_new is free until the next accepted step) */
+            for (int i = 0; i < n; i++) S.diff[i] = 0.0;
+            for (int k = 0; k < P->zH; k++) { /* symmetric-half triplet product in storage order, src/SpTripletMat.cpp:237-258 */
+                const int i = P->H_row1[k] - 1, j = P->H_col1[k] - 1;
+                S.diff[i] += S.hess[k] * S.p_k[j];
+                if (i != j) S.diff[j] += S.hess[k] * S.p_k[i];
+            }
+            for (int i = 0; i < n; i++) S.diff[i] = S.diff[i] + S.grad[i];
+            orc_qp_g(P->n, P->m, S.diff, -1.0, q->g);
+            orc_qp_bounds(3, P->n, P->m, S.delta, P->x_l, P->x_u, S.x_trial, P->c_l, P->c_u, S.c_trial, q->lb, q->ub, q->lbA, q->ubA);
+            int accepted = 0;
+            if (solve_qp(&S)) {
+                for (int i = 0; i < n; i++) { S.p_k[i] = S.p_k[i] + q->x[i]; S.x_trial[i] = S.x_k[i] + S.p_k[i]; }
+                P->fc(S.x_trial, &S.f_trial, S.c_trial);
+                S.infea_trial = cal_infea(P, S.c_trial);
+                const double Q1_x = S.f_k + S.rho * S.infea, Q1_t = S.f_trial + S.rho * S.infea_trial;
+                S.actual_red = Q1_x - Q1_t;
+                S.pred_red = S.rho * S.infea - q->obj;
+                accepted = S.actual_red >= P->eta_s * S.pred_red && S.actual_red >= -P->tol;
+            }
+            if (!accepted) memcpy(S.p_k, S.g_new, sizeof(double) * n);
+            /* QP data back to the current point (the reference does this after a rejected correction; after an accepted one the
+             * next setupQP rewrites gradient and bounds anyway) */
+            orc_qp_g(P->n, P->m, S.grad, -1.0, q->g);
+            orc_qp_bounds(3, P->n, P->m, S.delta, P->x_l, P->x_u, S.x_k, P->c_l, P->c_u, S.c_k, q->lb, q->ub, q->lbA, q->ubA);
+            if (accepted) {
+                S.infea = S.infea_trial; S.f_k = S.f_trial;
+                memcpy(S.x_k, S.x_trial, sizeof(double) * n);
+                memcpy(S.c_k, S.c_trial, sizeof(double) * m);
+                get_multipliers(&S);
+                for (int i = 0; i < m; i++) S.neg_lam[i] = -S.lam_c[i];
+                P->all(S.x_k, S.neg_lam, &f_tmp, c_tmp, S.grad, S.jac, S.hess);
+                S.updA = S.updH = S.updBounds = S.updG = 1;
+            }
         }
         S.iter += 1;
         get_multipliers(&S);

@@ -228,6 +228,30 @@ def test_device_loop_per_instance_modes_equal_the_c_oracle(gpu_lib, name):
     alg.close(); dev.close()
 
 
+@pytest.mark.parametrize("name", ["hs015", "hs043", "hs113"])
+def test_device_loop_second_order_correction_equals_the_c_oracle(gpu_lib, name):
+    """The same with the opt-in second-order correction (src/Algorithm.cpp:1140-1211) on both sides: per-instance state machines
+    in the solve kernels against one independent solve per instance in oracle/oracle_sqp.c."""
+    import os
+    from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
+    from restartsqp_b200.sqp_device import DeviceBatchedSQP
+    from oracle import oracle_py as orc
+    from test_hs_suite import HS_DIR, perturbed_starts
+    host = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+    dev = DeviceNLP(host)
+    X = perturbed_starts(host, 96, 4)
+    alg = DeviceBatchedSQP(dev, x0=X, options=r.Options(iter_max=150, second_order_correction=True))
+    res_d = alg.Optimize()
+    res_c = orc.SqpOracle(host, r.Options(iter_max=150, second_order_correction=True)).solve_batch(X)
+    res_off = orc.SqpOracle(host, r.Options(iter_max=150)).solve_batch(X)
+    assert (res_d.exitflag == res_c["exitflag"]).all(), (res_d.exitflag, res_c["exitflag"])
+    assert (res_d.iters == res_c["iters"]).all() and (res_d.qp_iter == res_c["qp_iter"]).all()
+    fin = np.isfinite(res_c["x"]).all(axis=1)
+    assert np.array_equal(res_d.x[fin], res_c["x"][fin]) and np.array_equal(res_d.obj[fin], res_c["obj"][fin])
+    assert (res_c["qp_iter"] != res_off["qp_iter"]).any()  # the correction was taken somewhere
+    alg.close(); dev.close()
+
+
 @pytest.mark.parametrize("name,soc", [("hs071", False), ("hs100", False), ("hs043", True), ("hs116", False)])
 def test_cxx_sequenced_loop_equals_python_sequenced_loop(gpu_lib, name, soc):
     """sqpb200_sqp_optimize (the whole of Algorithm::Optimize behind one C call) against the same launch sequence issued from

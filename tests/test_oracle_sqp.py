@@ -41,3 +41,30 @@ def test_c_oracle_reaches_known_optimum(name):
     res = orc.SqpOracle(nlp, r.Options()).solve_batch(perturbed_starts(nlp, 3, 0), nthreads=2)
     assert (res["exitflag"] == 0).all()
     assert abs(res["obj"][0] - F_STAR[name]) <= 1e-3 * max(1.0, abs(F_STAR[name]))
+
+
+@pytest.mark.parametrize("name", ["hs006", "hs015", "hs043", "hs113"])
+def test_c_oracle_second_order_correction_equals_numpy_mirror(name):
+    """second_order_correction (src/Algorithm.cpp:1140-1211, opt-in) in oracle_sqp.c against the numpy mirror, single instance,
+    every QP / LP of both by the C oracle of the backend: identical exit flags, outer and QP iteration counts and iterates; the
+    correction must actually be taken somewhere (the QP iteration counts differ from a run without it)."""
+    nlp = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+    X = perturbed_starts(nlp, 6, 2)
+    res_c = orc.SqpOracle(nlp, r.Options(iter_max=150, second_order_correction=True)).solve_batch(X)
+    res_off = orc.SqpOracle(nlp, r.Options(iter_max=150)).solve_batch(X)
+    compared = 0
+    for b in range(X.shape[0]):
+        o1 = r.Options(iter_max=150, second_order_correction=True)
+        mk = lambda info, qt: r.QPhandler(info, qt, o1, batch=1, backend=OracleQPInterface(info, qt, o1, batch=1), refresh_ubA=True)
+        try:
+            r1 = BatchedSQP(nlp, x0=X[b:b + 1], options=o1, make_handler=mk).Optimize()
+        except (r.QP_NOT_OPTIMAL, r.LP_NOT_OPTIMAL):
+            continue
+        assert int(r1.exitflag[0]) == int(res_c["exitflag"][b])
+        assert int(r1.iters[0]) == int(res_c["iters"][b]) and int(r1.qp_iter[0]) == int(res_c["qp_iter"][b])
+        if np.isfinite(r1.x[0]).all():
+            assert np.array_equal(r1.x[0], res_c["x"][b]) and r1.obj[0] == res_c["obj"][b]
+        compared += 1
+    assert compared >= 3
+    if name in ("hs006", "hs043"):
+        assert (res_c["qp_iter"] != res_off["qp_iter"]).any()

@@ -1,9 +1,14 @@
 // qp_kernel.cuh -- batched FP64 active-set QP/LP solver for sm_100a (row D of SURVEY.md 8a).
 //
-// One QP per warp; a CTA hosts CTA_THREADS/32 QPs.  Everything a QP needs for the whole solve lives in
-// that warp's slice of shared memory: the factors (Q of the TQ factorisation; T and the projected Cholesky
-// factor R packed into one array), current and target homotopy data, iterate and work vectors, matrix
-// values and the working-set index lists.  The sparsity pattern (shared by the batch) is staged once per
+// One solver template, QPT<TEAM>, three ways to run it:
+//   * TEAM = 32: one QP per warp, a CTA hosts CTA_THREADS/32 QPs (qp_solve_kernel);
+//   * TEAM = 16 / 8: sub-warp teams for QPs with nV <= 16 / <= 8 (two / four QPs per warp, team-masked barriers and shuffles);
+//   * TEAM = 512: one QP per thread-block cluster (qp_solve_large_kernel, QPs too large for shared memory): the slice lives in
+//     global memory, rank 0 of the cluster runs the method and the other CTAs take their share of the refactorisation (TMA-staged
+//     FP64 DMMA tiles) and of the large O(n^2) primitives; the projected Cholesky factor is carried through additions.
+// For TEAM <= 32 everything a QP needs for the whole solve lives in the team's slice of shared memory: the factors (Q of the
+// TQ factorisation; T and the projected Cholesky factor R packed into one array), current and target homotopy data, iterate and
+// work vectors, matrix values and the working-set index lists.  The sparsity pattern (shared by the batch) is staged once per
 // CTA as 16-bit indices, and the launch arguments are copied to static shared memory, so the solver's
 // out-of-line functions carry no per-thread state at all: no local-memory traffic, no global loads inside
 // the active-set loop.  HBM is touched only for the compulsory input (matrix values, g, bounds), the output
@@ -13,7 +18,8 @@
 // (call sites src/qpOASESInterface.cpp:155-206, 231-268, 221-222, 843-844, options :765): same
 // steps, thresholds and tie-breaks as the CPU oracle (oracle/oracle_qp.c), which is only a
 // checker and is never called from here.  The library is compiled with -fmad=false and every sum
-// below runs in the oracle's order, so results are bit-identical with the oracle.
+// below runs in the oracle's order, so the results of the warp and sub-warp kernels are bit-identical with the oracle (the
+// cluster kernel sums on the tensor cores and updates its factor: same working sets, 1e-8).
 //
 // Parallelisation inside the warp (32 lanes):
 //   * sparse products: one lane per output entry (CSC columns for H and A', a CSR view for A),
@@ -27,9 +33,9 @@
 //   * ratio tests: lane-local scan in index order + (ratio, position) lexicographic min reduction,
 //     which reproduces the sequential "first index wins ties" rule.
 //
-// A multi-warp-per-QP variant (named-barrier teams of 64..256 threads) was prototyped this round; with
+// A multi-warp-per-QP variant inside one CTA (named-barrier teams of 64..256 threads) was prototyped in round 1; with
 // out-of-line functions CTA-level barriers lost synchronisation intermittently on sm_100a / CUDA 12.9 and
-// the inlined build deadlocked at large grids, so only the warp variant is shipped.
+// the inlined build deadlocked at large grids, so between the warp and the whole CTA there is no intermediate team size.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

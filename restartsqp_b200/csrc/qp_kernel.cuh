@@ -244,11 +244,12 @@ __shared__ int sRedP[32];
 #ifndef QP_DOT_UNROLL_N
 #define QP_DOT_UNROLL_N 1
 #endif
-#define DOT_UNROLL _Pragma("unroll (TEAM <= 32 ? QP_DOT_UNROLL_N : 8)")
+#define DOT_UNROLL _Pragma("unroll (TEAM <= 32 ? DOT_N_SMALL : 8)")
 #define SYNC() do { if (TEAM <= 32) __syncwarp(team_mask<TEAM>()); else __syncthreads(); } while (0)
 
 template <int TEAM>
 struct QPT {
+    static constexpr int DOT_N_SMALL = QP_DOT_UNROLL_N;  // a macro is not expanded inside the pragma's string
     typedef typename PatIdx<TEAM>::type pidx;
     // ---------------------------------------------------------------- sparse products
     static __device__ QP_FN void mulH(const double* v, double* out) {  // out = (H + reg I) v (H symmetric: column gather)

@@ -243,6 +243,9 @@ const char* sqpb200_nlp_last_error(void);
  * as phases of one kernel, one thread per instance, over SoA state that never leaves the device.  The caller owns every
  * array (device memory) and sequences phases, QP/LP solves (sqpb200_solve_device_mask) and NLP evaluations (sqpb200_nlp_eval
  * with device pointers). */
+/* exit flag of an instance whose QP data did not change since its last solve (no Update_* flag raised): the reference's setupQP
+ * throws QP_UNCHANGED there (src/Algorithm.cpp:651-670) and nothing catches it; 7 is not a value of the reference's Exitflag */
+#define SQPB200_EXIT_QP_UNCHANGED 7
 #define SQPB200_PH_FLAGS 0
 #define SQPB200_PH_AFTER_QP 1
 #define SQPB200_PH_LP_AFTER 2

@@ -26,7 +26,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { EX_OPTIMAL = 0, EX_EXCEED_MAX_ITER = 2, EX_TRUST_REGION_TOO_SMALL = 4, EX_UNKNOWN = -99 };
+enum { EX_OPTIMAL = 0, EX_EXCEED_MAX_ITER = 2, EX_TRUST_REGION_TOO_SMALL = 4, EX_UNKNOWN = -99,
+       EX_QP_UNCHANGED = 7 /* not a value of the reference's Exitflag: setupQP throws QP_UNCHANGED there (src/Algorithm.cpp:651-670) */ };
 enum { CT_BOUNDED = 5, CT_EQUAL = -5, CT_BOUNDED_ABOVE = 9, CT_BOUNDED_BELOW = 1, CT_UNBOUNDED = 0 };
 enum { MS_UNDEFINED = -1, MS_FIXED = 0, MS_VARIED = 1 };
 
@@ -230,6 +231,9 @@ static void setup_qp(sqp* S) {
         S->first = 0;
         return;
     }
+    /* no Update_* flag raised since the last solve: the reference throws QP_UNCHANGED (src/Algorithm.cpp:651-670), which nothing
+     * catches; the run ends here with its own exit flag instead of re-solving the same QP until iter_max */
+    if (!(S->updA || S->updH || S->updBounds || S->updDelta || S->updPenalty || S->updG)) { S->exitflag = EX_QP_UNCHANGED; return; }
     if (S->updA) backend_set_A(q, P->zJ, P->J_row1, P->J_col1, S->jac);
     if (S->updH) backend_set_H(q, P->zH, P->H_row1, P->H_col1, S->hess);
     if (S->updBounds) orc_qp_bounds(3, P->n, P->m, S->delta, P->x_l, P->x_u, S->x_k, P->c_l, P->c_u, S->c_k, q->lb, q->ub, q->lbA, q->ubA);
@@ -305,6 +309,7 @@ int orc_sqp_solve(const orc_sqp_problem* P, const double* x0, const double* lam0
     double* c_tmp = zal(m, 8);
     while (S.iter < P->iter_max && S.exitflag == EX_UNKNOWN) {
         setup_qp(&S);
+        if (S.exitflag != EX_UNKNOWN) break;
         if (!solve_qp(&S)) break;
         for (int i = 0; i < n; i++) S.p_k[i] = S.qp->x[i];
         update_penalty_parameter(&S);

@@ -23,7 +23,8 @@
 
 namespace {
 
-enum { EX_OPTIMAL = 0, EX_EXCEED_MAX_ITER = 2, EX_TRUST_REGION_TOO_SMALL = 4, EX_UNKNOWN = -99 };
+enum { EX_OPTIMAL = 0, EX_EXCEED_MAX_ITER = 2, EX_TRUST_REGION_TOO_SMALL = 4, EX_UNKNOWN = -99,
+       EX_QP_UNCHANGED = SQPB200_EXIT_QP_UNCHANGED };
 enum { CT_BOUNDED = 5, CT_EQUAL = -5, CT_BOUNDED_ABOVE = 9, CT_BOUNDED_BELOW = 1, CT_UNBOUNDED = 0 };
 enum { UP_A = 1, UP_H = 2, UP_BOUNDS = 4, UP_DELTA = 8, UP_PENALTY = 16, UP_G = 32 };
 
@@ -92,7 +93,10 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
     const int n = S.n, m = S.m, nV = n + 2 * m;
     switch (phase) {
     case SQPB200_PH_FLAGS: {
-        const bool a = S.iter[b] < S.iter_max && S.exitflag[b] == EX_UNKNOWN;
+        bool a = S.iter[b] < S.iter_max && S.exitflag[b] == EX_UNKNOWN;
+        // no Update_* flag raised since the instance's last solve: the reference throws QP_UNCHANGED (src/Algorithm.cpp:651-670),
+        // which nothing catches; here the instance ends with its own exit flag instead of re-solving the same QP until iter_max
+        if (a && S.iter[b] > 0 && S.upd[b] == 0) { S.exitflag[b] = EX_QP_UNCHANGED; a = false; }
         S.active[b] = a ? 1 : 0;
         if (a) {
             atomicAdd(&S.counters[0], 1);

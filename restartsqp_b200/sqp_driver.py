@@ -197,6 +197,12 @@ class BatchedSQP:
             self.first_ = False
             return
         a = active
+        # no Update_* flag raised since the instance's last solve: the reference throws QP_UNCHANGED (src/Algorithm.cpp:651-670),
+        # which nothing catches; here the instance ends with its own exit flag instead of re-solving the same QP until iter_max
+        unchanged = a & ~(self.Update_A | self.Update_H | self.Update_bounds | self.Update_delta | self.Update_penalty | self.Update_g)
+        if unchanged.any():
+            self.exitflag_[unchanged] = int(Exitflag.QP_UNCHANGED)
+            a = a & ~unchanged
         if (self.Update_A & a).any():
             qp.update_A(self._jac())
         if (self.Update_H & a).any():
@@ -451,6 +457,9 @@ class BatchedSQP:
             if not active.any():
                 break
             self.setupQP(active)
+            active = active & (self.exitflag_ == UNK)
+            if not active.any():
+                break
             active = self._solveQP(active)
             self.p_k_[active] = self.myQP_.get_optimal_solution()[:, :n][active]   # get_search_direction :609
             self.update_penalty_parameter(active)

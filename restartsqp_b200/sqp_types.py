@@ -24,6 +24,7 @@ class Exitflag(enum.IntEnum):  # Types.hpp:51-73
     TRUST_REGION_TOO_SMALL = 4
     STEP_LARGER_THAN_TRUST_REGION = 5
     EXCEED_TIME_LIMITS = 6
+    QP_UNCHANGED = 7  # not in Types.hpp: Algorithm::setupQP throws QP_UNCHANGED there (src/Algorithm.cpp:651-670); a batch cannot abort
     QP_OPTIMAL = 20
     QPERROR_INTERNAL_ERROR = 21
     QPERROR_INFEASIBLE = 22

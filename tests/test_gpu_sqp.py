@@ -252,6 +252,32 @@ def test_device_loop_second_order_correction_equals_the_c_oracle(gpu_lib, name):
     alg.close(); dev.close()
 
 
+def test_device_loop_qp_unchanged_guard(gpu_lib):
+    """setupQP's QP_UNCHANGED guard (src/Algorithm.cpp:651-670) in the device loop (PH_FLAGS): an instance whose QP data did not
+    change since its last solve ends with Exitflag.QP_UNCHANGED instead of re-solving the same QP until iter_max.  hs105 gets
+    there after one iteration from most perturbed starts; against the C oracle instance by instance (exp / log are evaluated by
+    NVRTC and by libm: agreement on nearly all starts, not bit for bit)."""
+    import os
+    from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
+    from restartsqp_b200.sqp_device import DeviceBatchedSQP
+    from oracle import oracle_py as orc
+    from test_hs_suite import HS_DIR, perturbed_starts
+    host = AmplNLP(os.path.join(HS_DIR, "hs105.nl"))
+    dev = DeviceNLP(host)
+    X = perturbed_starts(host, 64, 1)
+    U = int(r.Exitflag.QP_UNCHANGED)
+    for pim in (True, False):
+        alg = DeviceBatchedSQP(dev, x0=X, options=r.Options(iter_max=50), per_instance_modes=pim)
+        res_d = alg.Optimize()
+        alg.close()
+        assert (res_d.exitflag == U).sum() >= 32 and (res_d.iters[res_d.exitflag == U] < 50).all()
+        if pim:
+            res_c = orc.SqpOracle(host, r.Options(iter_max=50)).solve_batch(X)
+            same = (res_d.exitflag == res_c["exitflag"]) & (res_d.iters == res_c["iters"])
+            assert same.mean() >= 0.9, same.mean()
+    dev.close()
+
+
 @pytest.mark.parametrize("name,soc", [("hs071", False), ("hs100", False), ("hs043", True), ("hs116", False)])
 def test_cxx_sequenced_loop_equals_python_sequenced_loop(gpu_lib, name, soc):
     """sqpb200_sqp_optimize (the whole of Algorithm::Optimize behind one C call) against the same launch sequence issued from

@@ -68,3 +68,22 @@ def test_c_oracle_second_order_correction_equals_numpy_mirror(name):
     assert compared >= 3
     if name in ("hs006", "hs043"):
         assert (res_c["qp_iter"] != res_off["qp_iter"]).any()
+
+
+def test_qp_unchanged_guard_of_setupQP():
+    """Algorithm::setupQP throws QP_UNCHANGED when no Update_* flag was raised since the last solve (src/Algorithm.cpp:651-670): a
+    rejected step whose ratio neither shrinks nor grows the radius (possible when the predicted reduction is not positive).  hs105
+    gets there after its first iteration from most perturbed starts.  The C oracle and the numpy mirror end such an instance with
+    Exitflag.QP_UNCHANGED (7, not a value of the reference's enum) instead of re-solving the same QP until iter_max."""
+    nlp = AmplNLP(os.path.join(HS_DIR, "hs105.nl"))
+    X = perturbed_starts(nlp, 8, 1)
+    res_c = orc.SqpOracle(nlp, r.Options(iter_max=50)).solve_batch(X)
+    unch = res_c["exitflag"] == int(r.Exitflag.QP_UNCHANGED)
+    assert unch.sum() >= 4 and (res_c["iters"][unch] >= 1).all() and (res_c["iters"][unch] < 50).all()
+    agree = 0
+    for b in np.nonzero(unch)[0][:4]:
+        o1 = r.Options(iter_max=50)
+        mk = lambda info, qt: r.QPhandler(info, qt, o1, batch=1, backend=OracleQPInterface(info, qt, o1, batch=1), refresh_ubA=True)
+        r1 = BatchedSQP(nlp, x0=X[b:b + 1], options=o1, make_handler=mk).Optimize()
+        agree += int(r1.exitflag[0]) == int(r.Exitflag.QP_UNCHANGED) and int(r1.iters[0]) == int(res_c["iters"][b])
+    assert agree >= 3  # libm and numpy evaluate hs105's exp / log differently in the last bits: not every start has to agree

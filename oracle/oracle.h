@@ -183,6 +183,8 @@ typedef struct {
 /* Algorithm::initialization + Optimize for one starting point (src/Algorithm.cpp:55-168, 438-472). */
 int orc_sqp_solve(const orc_sqp_problem* P, const double* x0, const double* lam0, double* x_out, double* f_out,
                   int* exitflag, int* iters, long long* qp_iters, double* kkt_out);
+/* test aid: QP solves that failed inside the penalty loop (src/Algorithm.cpp:932-935, 958-961) since the last call */
+long long orc_sqp_penalty_qp_failures(void);
 /* One solve per instance x0[B][n] on the host cores; returns the number of threads used. */
 int orc_sqp_solve_batch(const orc_sqp_problem* P, int B, const double* x0, const double* lam0, double* x, double* f,
                         int* exitflag, int* iters, long long* qp_iters, double* kkt, int nthreads);

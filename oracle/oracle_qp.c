@@ -952,7 +952,8 @@ void orc_qp_get_solution(const orc_qp* q, double* x, double* y, double* obj, int
             free(hx);
         }
         for (int i = 0; i < nV; i++) s += q->gN[i] * q->x[i];
-        *obj = s;
+        /* getObjVal() of a problem that is not solved is INFTY (qpOASES QProblemB::getObjVal; src/qpOASESInterface.cpp:324-327) */
+        *obj = (q->status == ORC_QP_OPTIMAL) ? s : QP_INFTY;
     }
     if (iters) *iters = q->iters;
 }

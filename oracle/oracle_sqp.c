@@ -156,7 +156,7 @@ typedef struct {
     int *bound_type, *cons_type;
     int exitflag, iter, pen_trial;
     long long qp_iter;
-    int updA, updH, updBounds, updDelta, updPenalty, updG, first;
+    int updA, updH, updBounds, updDelta, updPenalty, updG, first, lp_failed;
     backend *qp, *lp;
 } sqp;
 
@@ -243,6 +243,10 @@ static void setup_qp(sqp* S) {
     S->updA = S->updH = S->updBounds = S->updDelta = S->updPenalty = S->updG = 0;
 }
 
+/* test aid (process-global): how many QP solves failed inside the penalty loop since the last call */
+static long long g_pen_qp_failures = 0;
+long long orc_sqp_penalty_qp_failures(void) { long long v = g_pen_qp_failures; g_pen_qp_failures = 0; return v; }
+
 static void update_penalty_parameter(sqp* S) {
     const orc_sqp_problem* P = S->P;
     if (!P->penalty_update) return;
@@ -256,7 +260,7 @@ static void update_penalty_parameter(sqp* S) {
     backend_set_A(lp, P->zJ, P->J_row1, P->J_col1, S->jac);
     backend_solve(lp);
     S->qp_iter += lp->iters;
-    if (lp->status != ORC_QP_OPTIMAL) { S->exitflag = lp->status; return; }
+    if (lp->status != ORC_QP_OPTIMAL) { S->exitflag = lp->status; S->lp_failed = 1; return; } /* LP_NOT_OPTIMAL leaves Optimize, :900-906 */
     const double infea_infty = slack_norm(P, lp->x);
     const int feasible_lp = infea_infty <= P->penalty_update_tol;
     int need = 1;
@@ -269,9 +273,12 @@ static void update_penalty_parameter(sqp* S) {
         S->pen_trial += 1;
         orc_qp_g(P->n, P->m, NULL, rho_trial, S->qp->g);
         if (solve_qp(S)) S->infea_model = slack_norm(P, S->qp->x);
-        else { need = 0; }
+        else __sync_fetch_and_add(&g_pen_qp_failures, 1);
+        /* else: QP_NOT_OPTIMAL inside the loop only leaves the loop (:932-935, :958-961); the acceptance test below then sees
+         * the objective of an unsolved QP (INFTY) and takes its failure branch, and Optimize runs the rest of the iteration
+         * (trial point, ratio test, iter++, check_optimality) before its loop condition ends the solve */
     }
-    if (need && rho_trial > S->rho && S->exitflag == EX_UNKNOWN) {
+    if (need && rho_trial > S->rho) {
         const double qp_obj = S->qp->obj;
         if (rho_trial * S->infea - qp_obj >= P->eps2 * rho_trial * (S->infea - S->infea_model)) {
             S->eps1 += (1 - S->eps1) * P->eps1_change_parm;
@@ -313,7 +320,7 @@ int orc_sqp_solve(const orc_sqp_problem* P, const double* x0, const double* lam0
         if (!solve_qp(&S)) break;
         for (int i = 0; i < n; i++) S.p_k[i] = S.qp->x[i];
         update_penalty_parameter(&S);
-        if (S.exitflag != EX_UNKNOWN) break;
+        if (S.lp_failed) break;
         /* get_trial_point_info */
         double norm_p = 0.0;
         for (int i = 0; i < n; i++) { S.x_trial[i] = S.x_k[i] + S.p_k[i]; norm_p = fmax(norm_p, fabs(S.p_k[i])); }
@@ -331,7 +338,7 @@ int orc_sqp_solve(const orc_sqp_problem* P, const double* x0, const double* lam0
             for (int i = 0; i < m; i++) S.neg_lam[i] = -S.lam_c[i];
             P->all(S.x_k, S.neg_lam, &f_tmp, c_tmp, S.grad, S.jac, S.hess);
             S.updA = S.updH = S.updBounds = S.updG = 1;
-        } else if (P->second_order_correction) {
+        } else if (P->second_order_correction && S.exitflag == EX_UNKNOWN) {
             /* second_order_correction (src/Algorithm.cpp:1140-1211): the QP again around the trial point with the gradient
              * H_k p_k + g_k; its solution s_k is added to p_k and the ratio test repeated with the SOC QP's own objective as the
              * predicted reduction (ratio_test reads get_obj_QP(), :728); p_k and the QP data are restored otherwise. */

@@ -2514,7 +2514,9 @@ struct QPT {
             double obj = 0.0;
             QP_U1 for (int i = 0; i < nV; i++) obj += 0.5 * x[i] * t1[i];
             QP_U1 for (int i = 0; i < nV; i++) obj += gN[i] * x[i];
-            sA.obj[b] = obj; sA.status[b] = status; sA.iters[b] = total_iters;
+            // getObjVal() of a problem that is not solved is INFTY (qpOASES QProblemB::getObjVal; the reference passes it on,
+            // src/qpOASESInterface.cpp:324-327)
+            sA.obj[b] = (status == ST_OPTIMAL) ? obj : QP_INFTY; sA.status[b] = status; sA.iters[b] = total_iters;
             // qpOASESInterface::get_working_set + test_optimality (src/qpOASESInterface.cpp:835-895, 498-684),
             // evaluated against the target data the caller supplied.
             double primal = 0.0, dual = 0.0, compl_ = 0.0, stat = 0.0;

@@ -138,7 +138,7 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
         if (!S.need[b]) break;
         S.qp_iter[b] += S.lp_iters[b];
         const int st = S.lp_status[b];
-        if (st != SQPB200_QP_OPTIMAL) { S.exitflag[b] = st; S.need[b] = 0; break; }
+        if (st != SQPB200_QP_OPTIMAL) { S.exitflag[b] = st; S.need[b] = 0; break; }  // LP_NOT_OPTIMAL leaves Optimize (:900-906)
         const double* x = S.lp_x + (size_t)b * nV;
         double s = 0.0;
         for (int i = n; i < nV; i++) s = s + fabs(x[i]);
@@ -169,8 +169,11 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
         const int st = S.qp_status[b];
         const bool ok = (S.qp_kkt[(size_t)b * 5 + 4] <= 1.0e-6) && st == SQPB200_QP_OPTIMAL;
         if (!ok) {
+            // QP_NOT_OPTIMAL inside the penalty loop only leaves the loop (:932-935, :958-961): the acceptance test of
+            // PH_PEN_FINAL then sees the objective of an unsolved QP (INFTY) and takes its failure branch, and the instance runs
+            // the rest of the iteration (trial point, ratio test, iter++, check_optimality) before PH_FLAGS ends its solve
             S.exitflag[b] = (st == SQPB200_QP_OPTIMAL) ? SQPB200_QPERROR_INTERNAL_ERROR : st;
-            S.need[b] = 0;
+            S.need[b] = 2;
             break;
         }
         const double* x = S.qp_x + (size_t)b * nV;
@@ -180,7 +183,7 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
         break;
     }
     case SQPB200_PH_PEN_FINAL: {
-        if (!(S.need[b] && S.rho_trial[b] > S.rho[b] && S.exitflag[b] == EX_UNKNOWN)) break;
+        if (!(S.need[b] && S.rho_trial[b] > S.rho[b] && (S.exitflag[b] == EX_UNKNOWN || S.need[b] == 2))) break;
         const double rt = S.rho_trial[b], qp_obj = S.qp_obj[b];
         const bool succ = rt * S.infea[b] - qp_obj >= S.eps2 * rt * (S.infea[b] - S.infea_model[b]);
         if (succ) {
@@ -195,7 +198,7 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
         break;
     }
     case SQPB200_PH_TRIAL: {
-        if (S.active[b] && S.exitflag[b] != EX_UNKNOWN) S.active[b] = 0;
+        if (S.active[b] && S.exitflag[b] != EX_UNKNOWN && S.need[b] != 2) S.active[b] = 0;
         if (!S.active[b]) break;
         double np_ = 0.0;  // norm_p_k_ = ||p_k||_inf, recorded before any second-order correction is added (:98, :1181)
         for (int i = 0; i < n; i++) {

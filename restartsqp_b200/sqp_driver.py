@@ -151,6 +151,7 @@ class BatchedSQP:
         self.bound_cons_type_ = classify_single_constraint(self.x_l_, self.x_u_)
         self.infea_measure_ = self.cal_infea(self.c_k_)                              # :472
         self.exitflag_ = np.full(B, int(Exitflag.UNKNOWN), dtype=np.int32)
+        self.lp_failed_ = np.zeros(B, dtype=bool)
         self.iter_ = np.zeros(B, dtype=np.int64)
         self.qp_iter_ = np.zeros(B, dtype=np.int64)
         self.penalty_change_trial_ = np.zeros(B, dtype=np.int64)
@@ -296,6 +297,7 @@ class BatchedSQP:
         lp_status = lp.get_status()
         lp_fail = need & (lp_status != int(Exitflag.QP_OPTIMAL))
         self.exitflag_[lp_fail] = lp_status[lp_fail]
+        self.lp_failed_ |= lp_fail  # LP_NOT_OPTIMAL leaves Optimize (:900-906)
         need = need & ~lp_fail
         infea_infty = lp.get_infea_measure_model()
         feasible_lp = infea_infty <= o.penalty_update_tol
@@ -313,8 +315,9 @@ class BatchedSQP:
             self.myQP_.update_penalty(rho_trial)  # rho_trial == rho_ for every instance that never entered the loop
             ok = self._solveQP(go)
             self.infea_measure_model_[ok] = self.myQP_.get_infea_measure_model()[ok]
-            need = need & ~(go & ~ok)
-        changed = need & (rho_trial > self.rho_) & (self.exitflag_ == int(Exitflag.UNKNOWN))
+            # QP_NOT_OPTIMAL inside the loop only leaves the loop (:932-935, :958-961): the acceptance test below then sees the
+            # objective of an unsolved QP (INFTY) and takes its failure branch, and Optimize runs the rest of the iteration
+        changed = need & (rho_trial > self.rho_)
         if changed.any():
             qp_obj = self.myQP_.get_objective()
             succ = changed & (rho_trial * self.infea_measure_ - qp_obj >=
@@ -463,12 +466,12 @@ class BatchedSQP:
             active = self._solveQP(active)
             self.p_k_[active] = self.myQP_.get_optimal_solution()[:, :n][active]   # get_search_direction :609
             self.update_penalty_parameter(active)
-            active = active & (self.exitflag_ == UNK)
+            active = active & ~self.lp_failed_
             self.norm_p_k_ = np.abs(self.p_k_).max(axis=1) if self.nVar_ else np.zeros(self.batch)
             self.get_trial_point_info(active)
             acc = self.ratio_test(active)
             if o.second_order_correction:
-                self.second_order_correction(active & ~acc)
+                self.second_order_correction(active & ~acc)  # (instances whose exit flag is already set are skipped inside)
             self.iter_[active] += 1
             self.check_optimality(active)
             still = active & (self.exitflag_ == UNK)

@@ -87,3 +87,37 @@ def test_qp_unchanged_guard_of_setupQP():
         r1 = BatchedSQP(nlp, x0=X[b:b + 1], options=o1, make_handler=mk).Optimize()
         agree += int(r1.exitflag[0]) == int(r.Exitflag.QP_UNCHANGED) and int(r1.iters[0]) == int(res_c["iters"][b])
     assert agree >= 3  # libm and numpy evaluate hs105's exp / log differently in the last bits: not every start has to agree
+
+
+@pytest.mark.parametrize("name", ["hs099", "hs108"])
+def test_qp_failure_inside_the_penalty_loop_runs_the_rest_of_the_iteration(name):
+    """QP_NOT_OPTIMAL inside update_penalty_parameter only leaves its while loop (src/Algorithm.cpp:932-935, 958-961): the
+    acceptance test then sees the objective of an unsolved QP (getObjVal() = INFTY) and takes its failure branch, and Optimize
+    still runs the trial point, the ratio test, iter++ and check_optimality before its loop condition ends the solve.  Instances
+    that take this path (found with the oracle's counter): C oracle == numpy mirror on the oracle-backed backend, bit for bit."""
+    import ctypes as C
+    L = orc.lib()
+    L.orc_sqp_penalty_qp_failures.restype = C.c_longlong
+    nlp = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+    X = perturbed_starts(nlp, 64, 4)
+    so = orc.SqpOracle(nlp, r.Options(iter_max=150))
+    hit = compared = 0
+    for b in range(X.shape[0]):
+        L.orc_sqp_penalty_qp_failures()
+        res_c = so.solve_batch(X[b:b + 1], nthreads=1)
+        if L.orc_sqp_penalty_qp_failures() == 0:
+            continue
+        hit += 1
+        assert 20 < int(res_c["exitflag"][0]) <= 30 or int(res_c["exitflag"][0]) == 0  # the QP's error code, or OPTIMAL by check_optimality
+        o1 = r.Options(iter_max=150)
+        mk = lambda info, qt: r.QPhandler(info, qt, o1, batch=1, backend=OracleQPInterface(info, qt, o1, batch=1), refresh_ubA=True)
+        try:
+            r1 = BatchedSQP(nlp, x0=X[b:b + 1], options=o1, make_handler=mk).Optimize()
+        except (r.QP_NOT_OPTIMAL, r.LP_NOT_OPTIMAL):
+            continue
+        assert int(r1.exitflag[0]) == int(res_c["exitflag"][0]) and int(r1.iters[0]) == int(res_c["iters"][0])
+        assert int(r1.qp_iter[0]) == int(res_c["qp_iter"][0])
+        if np.isfinite(r1.x[0]).all():
+            assert np.array_equal(r1.x[0], res_c["x"][0])
+        compared += 1
+    assert hit >= 1 and compared >= 1

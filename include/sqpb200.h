@@ -320,6 +320,42 @@ int sqpb200_solve_per_instance(sqpb200_handle h, int mode, int maxiter, const un
 /* device pointers of the handle's result arrays: out[0..5] = x, y, obj, status, iters, kkt */
 int sqpb200_device_buffers(sqpb200_handle h, void** out);
 
+/* ---- QORE layout: the wire format of the reference's QORE backend -- compressed-row matrices and bounds
+ * stacked as lb = [lb_x ; lb_Ax], ub = [ub_x ; ub_Ax] of length nV + nC (include/sqphot/QOREInterface.hpp:30-252;
+ * src/QOREInterface.cpp:89-90 QPSetData(A_->RowIndex(), A_->ColIndex(), A_->MatVal(), H_->...), :102 QPOptimize(lb_, ub_, g_),
+ * :120-122 "primalsol" / "dualsol" of length nV + nC, :441 "workingset"; the QPhandler side is src/QPhandler.cpp:225-260,
+ * 369-383).  A handle whose structure was given this way solves on the same kernels: the column-compressed pattern the solver
+ * works on is derived once, values move through a precomputed position map on the device.
+ *
+ * sqpb200_set_structure_A_csr / _H_csr: first call of QOREInterface::set_A / set_H (src/QOREInterface.cpp:643-659) ->
+ * SpHbMat(..., isCompressedRow = true)::setStructure (src/SpHbMat.cpp:238-250, 324-337): same arguments as
+ * sqpb200_set_structure_A / _H, same device sort with the key (row, column, counter); later sqpb200_set_values_A / _H calls take
+ * triplet-ordered values as before.  Return the number of entries or a negative error. */
+int sqpb200_set_structure_A_csr(sqpb200_handle h, int zJ, const int* row1, const int* col1, int I_len,
+                                const int* I_irow, const int* I_jcol, const int* I_size, const double* I_value);
+int sqpb200_set_structure_H_csr(sqpb200_handle h, int zH, const int* row1, const int* col1, int is_symmetric);
+/* Direct compressed-row structure: the data constructor QOREInterface(H, A, g, lb, ub, options) of the replay driver
+ * (src/QOREInterface.cpp:36-60, test/QPsolvers_testers.cpp:74-75, 172-175).  rowptr[nrow+1], colidx[nnz], 0-based, entries of a
+ * row in ascending column order.  Values then arrive in this storage order through sqpb200_set_values_csr. */
+int sqpb200_set_structure_csr(sqpb200_handle h, int which, int nnz, const int* rowptr, const int* colidx);
+/* rowptr[nrow+1], colidx[nnz], order[nnz] (triplet entry -> storage position; any pointer may be NULL) of a handle whose
+ * structure was set through one of the three calls above. */
+int sqpb200_get_structure_csr(sqpb200_handle h, int which, int* rowptr, int* colidx, int* order);
+/* vals[batch][nnz] in compressed-row storage order (broadcast != 0: vals[nnz] shared by all instances); raises Update_A / Update_H
+ * like QOREInterface::set_A / set_H (matrix_change_flag_, src/QOREInterface.cpp:647, 656). */
+int sqpb200_set_values_csr(sqpb200_handle h, int which, const double* vals, int loc, int broadcast);
+int sqpb200_get_values_csr(sqpb200_handle h, int which, double* vals, int loc);
+/* Stacked bounds lb[batch][nV+nC], ub[batch][nV+nC] (either may be NULL): bulk form of QOREInterface::set_lb / set_ub
+ * (include/sqphot/QOREInterface.hpp; written by src/QPhandler.cpp:225-260, 369-383).  Entries [0, nV) are the variable bounds,
+ * [nV, nV+nC) the constraint bounds.  broadcast != 0: one row shared by all instances. */
+int sqpb200_set_bounds_stacked(sqpb200_handle h, const double* lb, const double* ub, int loc, int broadcast);
+int sqpb200_get_bounds_stacked(sqpb200_handle h, double* lb, double* ub, int loc);
+/* Results in QORE's layout (src/QOREInterface.cpp:120-122, 441): primal[batch][nV+nC] = [x ; A x], dual[batch][nV+nC] = [bound
+ * multipliers ; constraint multipliers], workingset[batch][nV+nC] (int32) in QORE's sign convention as the reference decodes it
+ * (src/QOREInterface.cpp:440-492: -1 = active at the upper bound, +1 = active at the lower bound, 0 = inactive).  Any pointer
+ * may be NULL. */
+int sqpb200_get_solution_stacked(sqpb200_handle h, double* primal, double* dual, int* workingset, int loc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,6 +113,36 @@ def csc_from_entries(ncol, er, ec, ev):
     return colptr, rowidx, val, order
 
 
+def csr_from_entries(nrow, er, ec, ev):
+    """Compressed-row branch of SpHbMat::setStructure (src/SpHbMat.cpp:238-250, 324-337): the same sort with the roles of
+    row and column exchanged, key (row, col, counter).  Returns (rowptr, colidx, val, order)."""
+    return csc_from_entries(nrow, ec, er, ev)
+
+
+def assemble_A_csr(nrow, ncol, row1, col1, val, iinfo):
+    """QOREInterface::set_A -> SpHbMat(nnz, nCon, nVar, isCompressedRow = true)::setStructure(rhs, I_info)
+    (src/QOREInterface.cpp:643-650, :205)."""
+    row1, col1, val = _i32(row1), _i32(col1), _f64(val)
+    irow, jcol, size, ival = iinfo
+    zJ = len(row1)
+    z = zJ + int(size.sum())
+    er, ec, ev = np.zeros(z, np.int32), np.zeros(z, np.int32), np.zeros(z)
+    n = lib().orc_expand_A(zJ, _ip(row1), _ip(col1), _dp(val), len(size), _ip(irow), _ip(jcol), _ip(size),
+                           _dp(ival), _ip(er), _ip(ec), _dp(ev))
+    assert n == z
+    return csr_from_entries(nrow, er, ec, ev)
+
+
+def assemble_H_csr(n, row1, col1, val, symmetric=True):
+    """QOREInterface::set_H -> SpHbMat(nVar, nVar, isCompressedRow = true)::setStructure(rhs)
+    (src/QOREInterface.cpp:652-659, :212)."""
+    row1, col1, val = _i32(row1), _i32(col1), _f64(val)
+    zH = len(row1)
+    er, ec, ev = np.zeros(2 * zH, np.int32), np.zeros(2 * zH, np.int32), np.zeros(2 * zH)
+    z = lib().orc_expand_H(zH, _ip(row1), _ip(col1), _dp(val), int(symmetric), _ip(er), _ip(ec), _dp(ev))
+    return csr_from_entries(n, er[:z].copy(), ec[:z].copy(), ev[:z].copy())
+
+
 def setmatval_A(order, jac_val, csc_val):
     out = _f64(csc_val).copy()
     jac_val = _f64(jac_val)

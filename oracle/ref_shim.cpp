@@ -126,4 +126,66 @@ double ref_vector_inf_norm(const double* x, int n) { Vector v(n, x); return v.ge
 double ref_const_INF(void) { return INF; }
 double ref_const_sqrt_m_eps(void) { return sqrt_m_eps; }
 
+// ---- compressed-row ("QORE layout") branch of the same routines: what QOREInterface::set_A / set_H build
+// (src/QOREInterface.cpp:643-659 on SpHbMat(..., isCompressedRow = true), include/sqphot/QOREInterface.hpp) and what
+// QPSetData receives (src/QOREInterface.cpp:89-90: A_->RowIndex() = row pointers, A_->ColIndex() = column of each entry).
+static void export_csr(const SpHbMat& m, int* rowptr, int* colidx, double* val, int* order) {
+    for (int i = 0; i <= m.RowNum(); i++) rowptr[i] = m.RowIndex(i);
+    for (int i = 0; i < m.EntryNum(); i++) {
+        colidx[i] = m.ColIndex(i);
+        if (val) val[i] = m.MatVal(i);
+        order[i] = m.order(i);
+    }
+}
+
+// SpHbMat::setStructure(rhs, I_info) (src/SpHbMat.cpp:196-268), compressed-row branch (:238-250), optionally followed by
+// SpHbMat::setMatVal(rhs2, I_info).
+int ref_assemble_A_csr(int nrow, int ncol, int zJ, const int* row1, const int* col1, const double* val,
+                       int I_len, int* I_irow, int* I_jcol, int* I_size, double* I_value,
+                       const double* val_refresh, int* rowptr, int* colidx, double* out_val, int* order) {
+    IdentityInfo info;
+    info.length = I_len; info.irow = I_irow; info.jcol = I_jcol; info.size = I_size; info.value = I_value;
+    int zI = 0;
+    for (int i = 0; i < I_len; i++) zI += I_size[i];
+    auto t = make_triplet(nrow, ncol, zJ, row1, col1, val, false);
+    SpHbMat hb(zJ + zI, nrow, ncol, true);
+    hb.setStructure(t, info);
+    if (val_refresh) {
+        auto t2 = make_triplet(nrow, ncol, zJ, row1, col1, val_refresh, false);
+        hb.setMatVal(t2, info);
+    }
+    export_csr(hb, rowptr, colidx, out_val, order);
+    return hb.EntryNum();
+}
+
+// SpHbMat::setStructure(rhs) (src/SpHbMat.cpp:284-355), compressed-row branch (:324-337), lazily allocated as in
+// QOREInterface::allocate_memory (src/QOREInterface.cpp:212).
+int ref_assemble_H_csr(int n, int zH, const int* row1, const int* col1, const double* val, int symmetric,
+                       const double* val_refresh, int* rowptr, int* colidx, double* out_val, int* order) {
+    auto t = make_triplet(n, n, zH, row1, col1, val, symmetric != 0);
+    SpHbMat hb(n, n, true);
+    hb.setStructure(t);
+    if (val_refresh) {
+        auto t2 = make_triplet(n, n, zH, row1, col1, val_refresh, symmetric != 0);
+        hb.setMatVal(t2);
+    }
+    export_csr(hb, rowptr, colidx, out_val, order);
+    return hb.EntryNum();
+}
+
+// SpHbMat::times (src/SpHbMat.cpp:698-737) on a compressed-row matrix.
+void ref_csr_times(int nrow, int ncol, int nnz, const int* rowptr, const int* colidx,
+                   const double* val, const double* x, double* y) {
+    auto m = std::make_shared<SpHbMat>(nnz, nrow, ncol, true);
+    for (int i = 0; i <= nrow; i++) m->setRowIndexAt(i, rowptr[i]);
+    for (int i = 0; i < nnz; i++) {
+        m->setColIndexAt(i, colidx[i]);
+        m->setMatValAt(i, val[i]);
+    }
+    auto p = std::make_shared<Vector>(ncol, x);
+    auto r = std::make_shared<Vector>(nrow);
+    if (nnz > 0) m->times(p, r);
+    std::memcpy(y, r->values(), sizeof(double) * nrow);
+}
+
 }  // extern "C"

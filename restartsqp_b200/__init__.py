@@ -7,9 +7,10 @@ from .sqp_types import (ActiveType, Exitflag, IdentityInfo, NLPInfo, Options, QP
                         QP_NOT_OPTIMAL, LP_NOT_OPTIMAL, QP_INTERNAL_ERROR, INVALID_WORKING_SET, INF)
 from . import _capi as capi
 from .qp_interface import CudaQPInterface
+from .qore_layout import CudaQOREInterface
 from .qp_handler import QPhandler
 from .sqp_driver import BatchedSQP, HS071
 
 __all__ = ["ActiveType", "Exitflag", "IdentityInfo", "NLPInfo", "Options", "QPType", "Solver", "SpTripletMat",
            "Stats", "QP_NOT_OPTIMAL", "LP_NOT_OPTIMAL", "QP_INTERNAL_ERROR", "INVALID_WORKING_SET", "INF", "capi",
-           "CudaQPInterface", "QPhandler", "BatchedSQP", "HS071"]
+           "CudaQPInterface", "CudaQOREInterface", "QPhandler", "BatchedSQP", "HS071"]

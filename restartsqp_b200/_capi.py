@@ -30,6 +30,10 @@ EXPORTS = [
     "sqpb200_nlp_compile", "sqpb200_nlp_cubin_size", "sqpb200_nlp_load", "sqpb200_nlp_eval", "sqpb200_nlp_destroy",
     "sqpb200_nlp_launch_count", "sqpb200_nlp_last_error",
     "sqpb200_sqp_phase", "sqpb200_sqp_optimize", "sqpb200_reset", "sqpb200_solve_device_mask", "sqpb200_device_buffers", "sqpb200_solve_per_instance",
+    # QORE layout: compressed-row matrices, stacked bounds / primal / dual / working set
+    "sqpb200_set_structure_A_csr", "sqpb200_set_structure_H_csr", "sqpb200_set_structure_csr", "sqpb200_get_structure_csr",
+    "sqpb200_set_values_csr", "sqpb200_get_values_csr", "sqpb200_set_bounds_stacked", "sqpb200_get_bounds_stacked",
+    "sqpb200_get_solution_stacked",
 ]
 
 
@@ -59,6 +63,15 @@ def lib():
         L.sqpb200_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.sqpb200_io_layout.argtypes = [C.c_void_p] * 5
         L.sqpb200_reset.argtypes = [C.c_void_p]
+        L.sqpb200_set_structure_A_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        L.sqpb200_set_structure_H_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.sqpb200_set_structure_csr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.sqpb200_get_structure_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sqpb200_set_values_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.sqpb200_get_values_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.sqpb200_set_bounds_stacked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.sqpb200_get_bounds_stacked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.sqpb200_get_solution_stacked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.sqpb200_vector_reduce.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sqpb200_vector_elementwise.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
         L.sqpb200_sqp_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -41,6 +41,12 @@ struct sqpb200_handle_s {
     std::vector<double> A_init;
     int *dAp = nullptr, *dAi = nullptr, *dArp = nullptr, *dAci = nullptr, *dAperm = nullptr, *dAsrc = nullptr;
     int *dHp = nullptr, *dHi = nullptr, *dHsrc = nullptr;
+    // QORE layout (compressed-row view given by the caller, sqpb200_set_structure_*_csr): row pointers, column indices, triplet ->
+    // storage position, and the position maps between the two storage orders (q2c[compressed-row position] = compressed-column
+    // position, c2q its inverse), resident for the device-side value moves
+    struct CsrView { bool set = false; std::vector<int> rp, ci, order, q2c, c2q; int *dq2c = nullptr, *dc2q = nullptr; } qA, qH;
+    void* qscratch = nullptr;  // [batch][nC] doubles (A x) + [batch][nV+nC] int32 (working set) of sqpb200_get_solution_stacked
+    size_t qscratch_bytes = 0;
     // data
     double *dAval = nullptr, *dHval = nullptr;
     double *dg = nullptr, *dlb = nullptr, *dub = nullptr, *dlbA = nullptr, *dubA = nullptr;
@@ -209,6 +215,8 @@ int sqpb200_destroy(sqpb200_handle h) {
     void* ptrs[] = {h->dAp, h->dAi, h->dArp, h->dAci, h->dAperm, h->dAsrc, h->dHp, h->dHi, h->dHsrc, h->dAval, h->dHval,
                     h->arena, h->dstate, h->stage, h->dgpat, h->dgwork, h->dprof, h->dmaxfr, h->dncap};
     for (void* p : ptrs) if (p) cudaFree(p);
+    void* qptrs[] = {h->qA.dq2c, h->qA.dc2q, h->qH.dq2c, h->qH.dc2q, h->qscratch};
+    for (void* p : qptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_maxfr) cudaEventDestroy(h->ev_maxfr);
@@ -1164,3 +1172,282 @@ int sqpb200_spmv(sqpb200_handle h, int which, int transpose, const double* x, do
     return 0;
 }
 
+// ------------------------------------------------------------------------------ QORE layout (compressed-row matrices, stacked bounds)
+// The reference's QORE backend keeps A and H row-compressed and one lb / ub pair of length nV + nC (src/QOREInterface.cpp:89-102,
+// 191-219).  These entry points accept and return that layout; the solve kernels keep working on the column-compressed pattern,
+// which is derived here once per structure (host, O(nnz)), and values move between the two storage orders through position
+// maps on the device (scatter_values_kernel in its gather form).
+__global__ void qore_workingset_kernel(long long total, int nV, int nC, const signed char* __restrict__ wsB,
+                                       const signed char* __restrict__ wsC, int* __restrict__ out) {
+    // QORE's sign is the opposite of qpOASES's: src/QOREInterface.cpp:445-458 reads -1 as "at the upper bound" where
+    // src/qpOASESInterface.cpp:848-861 reads +1
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int ld = nV + nC;
+    for (; t < total; t += stride) {
+        const long long b = t / ld;
+        const int i = (int)(t - b * ld);
+        const int w = i < nV ? (int)wsB[b * nV + i] : (int)wsC[b * nC + (i - nV)];
+        out[t] = -w;
+    }
+}
+
+// compressed-row (rp, ci) -> compressed-column (cp, ri) plus the position map q2c; entries with equal keys keep their order
+static void csr_to_csc(int nrow, int ncol, const std::vector<int>& rp, const std::vector<int>& ci, std::vector<int>& cp,
+                       std::vector<int>& ri, std::vector<int>& q2c) {
+    const int z = (int)ci.size();
+    cp.assign(ncol + 1, 0); ri.assign(z, 0); q2c.assign(z, 0);
+    for (int e = 0; e < z; e++) cp[ci[e] + 1]++;
+    for (int c = 0; c < ncol; c++) cp[c + 1] += cp[c];
+    std::vector<int> fill(cp.begin(), cp.end() - 1);
+    for (int r = 0; r < nrow; r++)
+        for (int e = rp[r]; e < rp[r + 1]; e++) { const int pos = fill[ci[e]]++; ri[pos] = r; q2c[e] = pos; }
+}
+
+static int finish_csr_view(sqpb200_handle h, sqpb200_handle_s::CsrView& q) {
+    const int z = (int)q.ci.size();
+    q.c2q.assign(z, 0);
+    for (int e = 0; e < z; e++) q.c2q[q.q2c[e]] = e;
+    if (upload_vec(h, &q.dq2c, q.q2c) || upload_vec(h, &q.dc2q, q.c2q)) return SQPB200_ERR_CUDA;
+    q.set = true;
+    return 0;
+}
+
+static int finish_structure_H(sqpb200_handle h) {
+    int rc = 0;
+    rc |= upload_vec(h, &h->dHp, h->Hp); rc |= upload_vec(h, &h->dHi, h->Hi); rc |= upload_vec(h, &h->dHsrc, h->Hsrc);
+    if (rc) return SQPB200_ERR_CUDA;
+    if (h->dHval) { CK(cudaFree(h->dHval)); h->dHval = nullptr; }
+    if (dev_alloc(h, &h->dHval, (size_t)h->batch * h->zH)) return SQPB200_ERR_CUDA;
+    h->H_set = true;
+    h->cfg_cap_key = -1;
+    return 0;
+}
+
+int sqpb200_set_structure_A_csr(sqpb200_handle h, int zJ, const int* row1, const int* col1, int I_len, const int* I_irow,
+                                const int* I_jcol, const int* I_size, const double* I_value) {
+    if (!h || zJ < 0) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    // entry list of SpHbMat::setStructure(rhs, I_info), src/SpHbMat.cpp:203-227
+    std::vector<int> er, ec;
+    std::vector<double> ev;
+    for (int i = 0; i < zJ; i++) { er.push_back(row1[i]); ec.push_back(col1[i]); ev.push_back(0.0); }
+    for (int b = 0; b < I_len; b++)
+        for (int j = 0; j < I_size[b]; j++) { er.push_back(I_irow[b] + j); ec.push_back(I_jcol[b] + j); ev.push_back(I_value[b]); }
+    const int z = (int)er.size();
+    for (int i = 0; i < z; i++)
+        if (er[i] < 1 || er[i] > h->nC || ec[i] < 1 || ec[i] > h->nV) { h->err = "triplet index out of range"; return SQPB200_ERR_INVALID; }
+    if (h->nV >= (1 << 21)) { h->err = "matrix too large for packed keys"; return SQPB200_ERR_TOO_LARGE; }
+    // compressed-row branch (:238-250): the device sort with the roles of row and column exchanged, key (row, column, counter)
+    auto& q = h->qA;
+    q.rp.assign(h->nC + 1, 0); q.ci.assign(z, 0); q.order.assign(z, 0);
+    int seg[2] = {0, z}, nrow[1] = {h->nC};
+    if (z > 0) {
+        int rc = run_assembly(h, h->stream, 1, seg, nrow, ec.data(), er.data(), q.rp.data(), q.ci.data(), q.order.data(), nullptr, &h->err);
+        h->launches++;
+        if (rc) return rc;
+    }
+    h->zA = z; h->zJ = zJ;
+    csr_to_csc(h->nC, h->nV, q.rp, q.ci, h->Ap, h->Ai, q.q2c);
+    h->Aorder.assign(z, 0); h->Asrc.assign(z, -1); h->A_init.assign(z, 0.0);
+    for (int i = 0; i < z; i++) {
+        h->Aorder[i] = q.q2c[q.order[i]];
+        if (i < zJ) h->Asrc[h->Aorder[i]] = i;
+        else h->A_init[h->Aorder[i]] = ev[i];
+    }
+    int rc = finish_structure_A(h);
+    if (!rc) rc = finish_csr_view(h, q);
+    return rc ? rc : z;
+}
+
+int sqpb200_set_structure_H_csr(sqpb200_handle h, int zH, const int* row1, const int* col1, int is_symmetric) {
+    if (!h || zH < 0) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    // entry list of SpHbMat::setStructure(rhs), src/SpHbMat.cpp:296-309
+    std::vector<int> er, ec, srct;
+    for (int i = 0; i < zH; i++) {
+        er.push_back(row1[i]); ec.push_back(col1[i]); srct.push_back(i);
+        if (is_symmetric && row1[i] != col1[i]) { er.push_back(col1[i]); ec.push_back(row1[i]); srct.push_back(i); }
+    }
+    const int z = (int)er.size();
+    for (int i = 0; i < z; i++)
+        if (er[i] < 1 || er[i] > h->nV || ec[i] < 1 || ec[i] > h->nV) { h->err = "triplet index out of range"; return SQPB200_ERR_INVALID; }
+    if (h->nV >= (1 << 21)) { h->err = "matrix too large for packed keys"; return SQPB200_ERR_TOO_LARGE; }
+    auto& q = h->qH;
+    q.rp.assign(h->nV + 1, 0); q.ci.assign(z, 0); q.order.assign(z, 0);
+    int seg[2] = {0, z}, nrow[1] = {h->nV};
+    if (z > 0) {  // compressed-row branch (:324-337)
+        int rc = run_assembly(h, h->stream, 1, seg, nrow, ec.data(), er.data(), q.rp.data(), q.ci.data(), q.order.data(), nullptr, &h->err);
+        h->launches++;
+        if (rc) return rc;
+    }
+    h->zH = z; h->zHt = zH;
+    csr_to_csc(h->nV, h->nV, q.rp, q.ci, h->Hp, h->Hi, q.q2c);
+    h->Horder.assign(z, 0); h->Hsrc.assign(z, -1);
+    for (int i = 0; i < z; i++) { h->Horder[i] = q.q2c[q.order[i]]; h->Hsrc[h->Horder[i]] = srct[i]; }
+    int rc = finish_structure_H(h);
+    if (!rc) rc = finish_csr_view(h, q);
+    return rc ? rc : z;
+}
+
+int sqpb200_set_structure_csr(sqpb200_handle h, int which, int nnz, const int* rowptr, const int* colidx) {
+    if (!h || nnz < 0 || !rowptr || (nnz > 0 && !colidx) || (which != SQPB200_MAT_A && which != SQPB200_MAT_H)) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const bool isA = which == SQPB200_MAT_A;
+    const int nrow = isA ? h->nC : h->nV;
+    if (rowptr[0] != 0 || rowptr[nrow] != nnz) { h->err = "rowptr[0] != 0 or rowptr[nrow] != nnz"; return SQPB200_ERR_INVALID; }
+    for (int r = 0; r < nrow; r++)
+        if (rowptr[r + 1] < rowptr[r]) { h->err = "rowptr not monotone"; return SQPB200_ERR_INVALID; }
+    for (int e = 0; e < nnz; e++)
+        if (colidx[e] < 0 || colidx[e] >= h->nV) { h->err = "column index out of range"; return SQPB200_ERR_INVALID; }
+    auto& q = isA ? h->qA : h->qH;
+    q.rp.assign(rowptr, rowptr + nrow + 1); q.ci.assign(colidx, colidx + nnz); q.order.resize(nnz);
+    for (int e = 0; e < nnz; e++) q.order[e] = e;
+    int rc;
+    if (isA) {
+        h->zA = nnz; h->zJ = nnz;
+        csr_to_csc(nrow, h->nV, q.rp, q.ci, h->Ap, h->Ai, q.q2c);
+        h->Aorder = q.q2c; h->Asrc.assign(nnz, 0); h->A_init.clear();
+        for (int e = 0; e < nnz; e++) h->Asrc[q.q2c[e]] = e;
+        rc = finish_structure_A(h);
+    } else {
+        h->zH = nnz; h->zHt = nnz;
+        csr_to_csc(nrow, h->nV, q.rp, q.ci, h->Hp, h->Hi, q.q2c);
+        h->Horder = q.q2c; h->Hsrc.assign(nnz, 0);
+        for (int e = 0; e < nnz; e++) h->Hsrc[q.q2c[e]] = e;
+        rc = finish_structure_H(h);
+    }
+    if (!rc) rc = finish_csr_view(h, q);
+    return rc ? rc : nnz;
+}
+
+int sqpb200_get_structure_csr(sqpb200_handle h, int which, int* rowptr, int* colidx, int* order) {
+    if (!h) return SQPB200_ERR_INVALID;
+    const auto& q = which == SQPB200_MAT_A ? h->qA : h->qH;
+    if (!q.set) { h->err = "structure was not given in compressed-row form"; return SQPB200_ERR_STATE; }
+    if (rowptr) std::copy(q.rp.begin(), q.rp.end(), rowptr);
+    if (colidx) std::copy(q.ci.begin(), q.ci.end(), colidx);
+    if (order) std::copy(q.order.begin(), q.order.end(), order);
+    return 0;
+}
+
+int sqpb200_set_values_csr(sqpb200_handle h, int which, const double* vals, int loc, int broadcast) {
+    if (!h || !vals) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const bool isA = which == SQPB200_MAT_A;
+    const auto& q = isA ? h->qA : h->qH;
+    if (!q.set || (isA ? !h->A_set : !h->H_set)) { h->err = "structure was not given in compressed-row form"; return SQPB200_ERR_STATE; }
+    const int z = isA ? h->zA : h->zH;
+    if (z > 0) {
+        const size_t bytes = (size_t)(broadcast ? 1 : h->batch) * z * 8;
+        if (loc == SQPB200_LOC_HOST && ensure_stage(h, bytes)) return SQPB200_ERR_CUDA;
+        const void* din;
+        if (to_device(h, vals, bytes, loc, 0, &din)) return SQPB200_ERR_CUDA;
+        const long long total = (long long)h->batch * z;
+        // out[b][compressed-column position] = in[b][c2q[position]]
+        scatter_values_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(total, z, z, q.dc2q, (const double*)din, broadcast,
+                                                                           isA ? h->dAval : h->dHval);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    if (h->first_solved) { if (isA) h->upd_A = true; else h->upd_H = true; }
+    return 0;
+}
+
+int sqpb200_get_values_csr(sqpb200_handle h, int which, double* vals, int loc) {
+    if (!h || !vals) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const bool isA = which == SQPB200_MAT_A;
+    const auto& q = isA ? h->qA : h->qH;
+    if (!q.set) { h->err = "structure was not given in compressed-row form"; return SQPB200_ERR_STATE; }
+    const int z = isA ? h->zA : h->zH;
+    if (z == 0) return 0;
+    const size_t bytes = (size_t)h->batch * z * 8;
+    double* dout = vals;
+    if (loc == SQPB200_LOC_HOST) { if (ensure_stage(h, bytes)) return SQPB200_ERR_CUDA; dout = (double*)h->stage; }
+    const long long total = (long long)h->batch * z;
+    scatter_values_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(total, z, z, q.dq2c, isA ? h->dAval : h->dHval, 0, dout);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (loc == SQPB200_LOC_HOST) CK(cudaMemcpyAsync(vals, dout, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sqpb200_set_bounds_stacked(sqpb200_handle h, const double* lb, const double* ub, int loc, int broadcast) {
+    if (!h) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int nV = h->nV, nC = h->nC;
+    const size_t ld = (size_t)(nV + nC) * 8;
+    const cudaMemcpyKind kind = loc == SQPB200_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const double* src[2] = {lb, ub};
+    double* dx[2] = {h->dlb, h->dub};
+    double* dc[2] = {h->dlbA, h->dubA};
+    const int wx[2] = {SQPB200_VEC_LB, SQPB200_VEC_UB}, wc[2] = {SQPB200_VEC_LBA, SQPB200_VEC_UBA};
+    for (int k = 0; k < 2; k++) {
+        if (!src[k]) continue;
+        if (broadcast) {  // one row for every instance: the broadcast path of the split setters
+            int rc = sqpb200_set_vectors(h, wx[k], src[k], 0, nV, loc, 1);
+            if (!rc && nC > 0) rc = sqpb200_set_vectors(h, wc[k], src[k] + nV, 0, nC, loc, 1);
+            if (rc) return rc;
+        } else {  // two strided DMA copies per vector: rows of nV + nC doubles split at nV
+            CK(cudaMemcpy2DAsync(dx[k], (size_t)nV * 8, src[k], ld, (size_t)nV * 8, h->batch, kind, h->stream));
+            if (nC > 0) CK(cudaMemcpy2DAsync(dc[k], (size_t)nC * 8, src[k] + nV, ld, (size_t)nC * 8, h->batch, kind, h->stream));
+        }
+    }
+    if (h->first_solved && (lb || ub)) h->upd_bounds = true;  // Update_bounds, as the per-entry setters raise it
+    return 0;
+}
+
+int sqpb200_get_bounds_stacked(sqpb200_handle h, double* lb, double* ub, int loc) {
+    if (!h) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int nV = h->nV, nC = h->nC;
+    const size_t ld = (size_t)(nV + nC) * 8;
+    const cudaMemcpyKind kind = loc == SQPB200_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    double* dst[2] = {lb, ub};
+    const double* dx[2] = {h->dlb, h->dub};
+    const double* dc[2] = {h->dlbA, h->dubA};
+    for (int k = 0; k < 2; k++) {
+        if (!dst[k]) continue;
+        CK(cudaMemcpy2DAsync(dst[k], ld, dx[k], (size_t)nV * 8, (size_t)nV * 8, h->batch, kind, h->stream));
+        if (nC > 0) CK(cudaMemcpy2DAsync(dst[k] + nV, ld, dc[k], (size_t)nC * 8, (size_t)nC * 8, h->batch, kind, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sqpb200_get_solution_stacked(sqpb200_handle h, double* primal, double* dual, int* workingset, int loc) {
+    if (!h) return SQPB200_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int nV = h->nV, nC = h->nC;
+    const size_t B = h->batch, ld = (size_t)(nV + nC);
+    const cudaMemcpyKind kind = loc == SQPB200_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    const size_t ax_bytes = ((B * nC * 8 + 255) / 256) * 256, need = ax_bytes + B * ld * 4 + 256;
+    if (need > h->qscratch_bytes) {
+        if (h->qscratch) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->qscratch)); h->qscratch = nullptr; h->qscratch_bytes = 0; }
+        CK(cudaMalloc(&h->qscratch, need));
+        h->qscratch_bytes = need;
+    }
+    double* dAx = (double*)h->qscratch;
+    int* dws = (int*)((char*)h->qscratch + ax_bytes);
+    if (primal) {  // "primalsol" = [x ; A x] (src/QOREInterface.cpp:120; its test_optimality reads x_qp_(nV + i) as the activity)
+        CK(cudaMemcpy2DAsync(primal, ld * 8, h->dx, (size_t)nV * 8, (size_t)nV * 8, B, kind, h->stream));
+        if (nC > 0) {
+            if (!h->A_set) { h->err = "structure of A not set"; return SQPB200_ERR_STATE; }
+            int rc = sqpb200_spmv(h, SQPB200_MAT_A, 0, h->dx, dAx, SQPB200_LOC_DEVICE);
+            if (rc) return rc;
+            CK(cudaMemcpy2DAsync(primal + nV, ld * 8, dAx, (size_t)nC * 8, (size_t)nC * 8, B, kind, h->stream));
+        }
+    }
+    if (copy_out(h, dual, h->dy, B * ld * 8, loc)) return SQPB200_ERR_CUDA;  // "dualsol": already stacked (:303-305 of the qpOASES twin)
+    if (workingset) {
+        const long long total = (long long)(B * ld);
+        qore_workingset_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(total, nV, nC, h->dwsB, h->dwsC, dws);
+        h->launches++;
+        CK(cudaGetLastError());
+        if (copy_out(h, workingset, dws, B * ld * 4, loc)) return SQPB200_ERR_CUDA;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}

@@ -9,7 +9,8 @@ import numpy as np
 
 from . import _capi as capi
 from .qp_interface import CudaQPInterface
-from .sqp_types import (IdentityInfo, NLPInfo, Options, QPType, Stats, SpTripletMat, QP_NOT_OPTIMAL, SQRT_M_EPS,
+from .qore_layout import CudaQOREInterface
+from .sqp_types import (IdentityInfo, NLPInfo, Options, QPType, Solver, Stats, SpTripletMat, QP_NOT_OPTIMAL, SQRT_M_EPS,
                         ActiveType)
 
 
@@ -27,8 +28,17 @@ class QPhandler:
                                       size=np.array([m, m], np.int32), value=np.array([1.0, -1.0]))
         # the backend switch of src/QPhandler.cpp:58-76; `backend` lets a caller plug another object with the
         # CudaQPInterface method set (the tests plug the CPU oracle there to check the host logic without a GPU)
-        self.solverInterface_ = backend if backend is not None else CudaQPInterface(nlp_info, qptype, self.options, batch=batch,
-                                                                                    device=device, **kw)
+        # QPsolverChoice == QORE selects the QORE-layout member of the family (row-compressed matrices, stacked bounds:
+        # CudaQOREInterface), every other choice the qpOASES-layout one; both run on the same CUDA kernels
+        choice = self.options.LPsolverChoice if QPType(qptype) == QPType.LP else self.options.QPsolverChoice
+        self.QPsolverChoice_ = Solver.QORE if isinstance(backend, CudaQOREInterface) or (backend is None and choice == Solver.QORE) \
+            else choice
+        if backend is not None:
+            self.solverInterface_ = backend
+        elif self.QPsolverChoice_ == Solver.QORE:
+            self.solverInterface_ = CudaQOREInterface(nlp_info, qptype, self.options, batch=batch, device=device, **kw)
+        else:
+            self.solverInterface_ = CudaQPInterface(nlp_info, qptype, self.options, batch=batch, device=device, **kw)
         self.qptype = QPType(qptype)
         # False: update_bounds leaves ubA stale exactly like the reference's non-QORE branch;
         # True: both sides are refreshed, as its QORE branch does.  The batched SQP driver needs True to make progress
@@ -61,9 +71,10 @@ class QPhandler:
     def set_bounds(self, delta, x_l, x_u, x_k, c_l, c_u, c_k):
         self._bounds(0, delta, x_l, x_u, x_k, c_l, c_u, c_k)
 
-    # -- src/QPhandler.cpp:342-419 (lbA refreshed, ubA not: SURVEY.md 8a quirk 2)
+    # -- src/QPhandler.cpp:342-419 (qpOASES branch: lbA refreshed, ubA not; QORE branch :369-383: both sides)
     def update_bounds(self, delta, x_l, x_u, x_k, c_l, c_u, c_k):
-        self._bounds(3 if self.refresh_ubA else 1, delta, x_l, x_u, x_k, c_l, c_u, c_k)
+        both = self.refresh_ubA or self.QPsolverChoice_ == Solver.QORE
+        self._bounds(3 if both else 1, delta, x_l, x_u, x_k, c_l, c_u, c_k)
 
     # -- src/QPhandler.cpp:533-567
     def update_delta(self, delta, x_l, x_u, x_k):
@@ -159,6 +170,9 @@ class QPhandler:
             out[at_lo] = int(ActiveType.ACTIVE_BELOW)
             out[at_lo & at_hi] = int(ActiveType.ACTIVE_BOTH_SIDE)
             return out
+        if self.QPsolverChoice_ == Solver.QORE:  # :626-638: constraint bounds are the tail of the stacked lb / ub
+            nV = self.nVar_QP_
+            return classify(Ax, lb[:, nV:], ub[:, nV:]), classify(x, lb[:, :nV], ub[:, :nV])
         ubA = si.getUbA()
         return classify(Ax, ubA, ubA), classify(x, lb, ub)
 

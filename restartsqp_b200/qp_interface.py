@@ -34,7 +34,7 @@ class CudaQPInterface:
         if nlp_info is not None:  # constructor (NLPInfo, QPType, options): src/qpOASESInterface.cpp:35-50
             nC = nlp_info.nCon
             nV = nlp_info.nVar + 2 * nlp_info.nCon
-        self.nV_, self.nC_, self.batch, self.qptype = int(nV), int(nC), int(batch), QPType(qptype)
+        self.nV_, self.nC_, self.batch, self.qptype, self.device = int(nV), int(nC), int(batch), QPType(qptype), int(device)
         o = capi.Options()
         self.L.sqpb200_default_options(C.byref(o))
         o.qp_maxiter, o.lp_maxiter = self.options.qp_maxiter, self.options.lp_maxiter
@@ -138,6 +138,91 @@ class CudaQPInterface:
             v = np.zeros(1)
         p, loc = capi.ptr(v)
         _check(self.h, self.L.sqpb200_set_values_csc(self.h, which, p, loc, int(v.ndim == 1)), "set_values_csc")
+
+    # ------------------------------------------------------------------ QORE layout (compressed-row matrices, stacked vectors)
+    def set_A_csr(self, rhs: SpTripletMat, I_info: IdentityInfo = None):
+        """QOREInterface::set_A (src/QOREInterface.cpp:643-650): the first call builds the compressed-row structure
+        (SpHbMat(..., isCompressedRow = true)::setStructure, src/SpHbMat.cpp:238-250), later calls refresh values."""
+        if not self._A_set:
+            r, c = capi.i32(rhs.RowIndex), capi.i32(rhs.ColIndex)
+            if I_info is None:
+                I_info = IdentityInfo(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0))
+            ir, jc, sz, val = capi.i32(I_info.irow), capi.i32(I_info.jcol), capi.i32(I_info.size), capi.f64(I_info.value)
+            _check(self.h, self.L.sqpb200_set_structure_A_csr(self.h, len(r), r.ctypes.data_as(C.c_void_p),
+                                                              c.ctypes.data_as(C.c_void_p), len(sz),
+                                                              ir.ctypes.data_as(C.c_void_p), jc.ctypes.data_as(C.c_void_p),
+                                                              sz.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p)),
+                   "set_structure_A_csr")
+            self._A_set = True
+        self.set_A(rhs, I_info)  # values: triplet order, scattered on the device
+
+    def set_H_csr(self, rhs: SpTripletMat):
+        """QOREInterface::set_H (src/QOREInterface.cpp:652-659)."""
+        if not self._H_set:
+            r, c = capi.i32(rhs.RowIndex), capi.i32(rhs.ColIndex)
+            _check(self.h, self.L.sqpb200_set_structure_H_csr(self.h, len(r), r.ctypes.data_as(C.c_void_p),
+                                                              c.ctypes.data_as(C.c_void_p), int(rhs.isSymmetric)),
+                   "set_structure_H_csr")
+            self._H_set = True
+        self.set_H(rhs)
+
+    def set_csr(self, which, rowptr, colidx, vals):
+        """Data-constructor path of the QORE backend (src/QOREInterface.cpp:36-60): compressed-row arrays given directly."""
+        rp, ci = capi.i32(rowptr), capi.i32(colidx)
+        _check(self.h, self.L.sqpb200_set_structure_csr(self.h, which, len(ci), rp.ctypes.data_as(C.c_void_p),
+                                                        ci.ctypes.data_as(C.c_void_p)), "set_structure_csr")
+        if which == capi.MAT_A:
+            self._A_set = True
+        else:
+            self._H_set = True
+        self.set_csr_values(which, vals)
+
+    def set_csr_values(self, which, vals):
+        v = capi.f64(vals)
+        if v.shape[-1] == 0:
+            v = np.zeros(1)
+        p, loc = capi.ptr(v)
+        _check(self.h, self.L.sqpb200_set_values_csr(self.h, which, p, loc, int(v.ndim == 1)), "set_values_csr")
+
+    def get_csr(self, which):
+        """Compressed-row arrays as QPSetData receives them (src/QOREInterface.cpp:89-90): RowIndex = row pointers,
+        ColIndex = column of each entry, MatVal[batch][nnz] in that storage order, order = triplet entry -> position."""
+        nnz = self.L.sqpb200_get_nnz(self.h, which)
+        nrow = self.nC_ if which == capi.MAT_A else self.nV_
+        rp, ci, od = np.zeros(nrow + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz, np.int32)
+        _check(self.h, self.L.sqpb200_get_structure_csr(self.h, which, rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p),
+                                                        od.ctypes.data_as(C.c_void_p)), "get_structure_csr")
+        vals = np.zeros((self.batch, nnz))
+        if nnz:
+            _check(self.h, self.L.sqpb200_get_values_csr(self.h, which, vals.ctypes.data_as(C.c_void_p), capi.LOC_HOST), "get_values_csr")
+        return dict(RowIndex=rp, ColIndex=ci, order=od, MatVal=vals)
+
+    def set_bounds_stacked(self, lb=None, ub=None):
+        """lb / ub [nV+nC] (shared) or [batch][nV+nC]: variable bounds first, then constraint bounds."""
+        arrs = [None if a is None else capi.f64(a) for a in (lb, ub)]
+        given = [a for a in arrs if a is not None]
+        if not given:
+            return
+        assert all(a.ndim == given[0].ndim and a.shape[-1] == self.nV_ + self.nC_ for a in given)
+        (pl, l1), (pu, l2) = capi.ptr(arrs[0]), capi.ptr(arrs[1])
+        _check(self.h, self.L.sqpb200_set_bounds_stacked(self.h, pl, pu, l1 if arrs[0] is not None else l2, int(given[0].ndim == 1)),
+               "set_bounds_stacked")
+
+    def get_bounds_stacked(self):
+        lb, ub = np.empty((self.batch, self.nV_ + self.nC_)), np.empty((self.batch, self.nV_ + self.nC_))
+        _check(self.h, self.L.sqpb200_get_bounds_stacked(self.h, lb.ctypes.data_as(C.c_void_p), ub.ctypes.data_as(C.c_void_p),
+                                                         capi.LOC_HOST), "get_bounds_stacked")
+        return lb, ub
+
+    def get_solution_stacked(self, want=("primal", "dual", "workingset")):
+        """(primal [x ; A x], dual [bound ; constraint multipliers], workingset in QORE's sign) as [batch][nV+nC] arrays."""
+        n = self.nV_ + self.nC_
+        pr = np.empty((self.batch, n)) if "primal" in want else None
+        du = np.empty((self.batch, n)) if "dual" in want else None
+        ws = np.empty((self.batch, n), np.int32) if "workingset" in want else None
+        pp = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in (pr, du, ws)]
+        _check(self.h, self.L.sqpb200_get_solution_stacked(self.h, *pp, capi.LOC_HOST), "get_solution_stacked")
+        return pr, du, ws
 
     # ------------------------------------------------------------------ batched QPhandler data kernels
     def qphandler_bounds(self, mode, n, m, delta, x_l, x_u, x_k, c_l=None, c_u=None, c_k=None):
@@ -307,6 +392,16 @@ class CudaQPInterface:
         py, _ = capi.ptr(y)
         _check(self.h, self.L.sqpb200_spmv(self.h, which, int(transpose), px, py, loc), "spmv")
         return y
+
+    def vector_times(self, a, b):
+        """Batched Vector::times (src/Vector.cpp:237-251): out[batch] = sum_i a[b][i] * b[b][i] in index order, on the device."""
+        a, b = capi.f64(a), capi.f64(b)
+        out = np.empty(a.shape[0])
+        (pa, loc), (pb, _) = capi.ptr(a), capi.ptr(b)
+        rc = self.L.sqpb200_vector_reduce(self.device, 2, a.shape[0], a.shape[1], pa, pb, out.ctypes.data_as(C.c_void_p), loc, None)
+        if rc < 0:
+            raise capi.SqpB200Error("vector_reduce failed (%d)" % rc)
+        return out
 
     def launch_count(self):
         return int(self.L.sqpb200_launch_count(self.h))

@@ -244,9 +244,14 @@ class BatchedSQP:
         si = self.myQP_.solverInterface_
         if not hasattr(si, "getA"):
             return
-        A, Hm = si.getA(), si.getH()
         os.makedirs(self.dump_dir_, exist_ok=True)
         name = getattr(self.nlp_, "name", type(self.nlp_).__name__)
+        if hasattr(si, "get_primal_stacked"):  # QORE-layout backend: its own WriteQPDataToFile writes exactly this file
+            for b in idx[: self.dump_left_]:
+                si.WriteQPDataToFile(os.path.join(self.dump_dir_, "QORE_%s_inst%dqpdata.log" % (name, int(b))), int(b))
+                self.dump_left_ -= 1
+            return
+        A, Hm = si.getA(), si.getH()
         lb, ub, lbA, ubA, g = si.getLb(), si.getUb(), si.getLbA(), si.getUbA(), si.getG()
         for b in idx[: self.dump_left_]:
             q = dict(nV=si.nV_, nC=si.nC_, lb=lb[b], ub=ub[b], lbA=lbA[b], ubA=ubA[b], g=g[b],

@@ -14,6 +14,8 @@ Writes
   l0_golden.json    outputs of the reference's own L0 code (oracle/_ref/libref_l0.so): CSC index
                     arrays, `order`, refreshed values, SpMV / SpMTV results and norms for the HS071
                     shaped probe of SURVEY.md section 8c and for seeded random matrices.
+  qore_golden.json  the same triplets through the reference's compressed-row SpHbMat (the QORE layout of
+                    src/QOREInterface.cpp:89-90, 643-659): row pointers, column indices, `order`, values.
 """
 import ctypes as C
 import glob
@@ -199,7 +201,48 @@ def make_l0_golden():
           cases[0]["A_order"], "H.colptr =", cases[0]["H_colptr"])
 
 
+def make_qore_golden():
+    """qore_golden.json: the compressed-row arrays the reference's QOREInterface hands to QPSetData
+    (src/QOREInterface.cpp:89-90): SpHbMat(..., isCompressedRow = true)::setStructure / setMatVal run on the triplets of
+    every l0_golden.json case (row pointers, column indices, `order`, values before and after a refresh) and
+    SpHbMat::times on the compressed-row matrix."""
+    R = orc.ref_lib()
+    assert R is not None and hasattr(R, "ref_assemble_A_csr"), "build oracle/_ref first (make -C oracle ref)"
+    src = json.load(open(os.path.join(OUT, "l0_golden.json")))["cases"]
+    cases = []
+    for c in src:
+        n, m = c["n"], c["m"]
+        nV, nC = n + 2 * m, m
+        jr, jc, jv, jv2 = orc._i32(c["J_row1"]), orc._i32(c["J_col1"]), orc._f64(c["J_val"]), orc._f64(c["J_val2"])
+        hr, hc, hv, hv2 = orc._i32(c["H_row1"]), orc._i32(c["H_col1"]), orc._f64(c["H_val"]), orc._f64(c["H_val2"])
+        irow, jcol, size, ival = [a.copy() for a in orc.identity_info(n, m)]
+        z = len(jr) + 2 * m
+        Arp, Aci, Ao = np.zeros(nC + 1, np.int32), np.zeros(z, np.int32), np.zeros(z, np.int32)
+        Av0, Av1 = np.zeros(z), np.zeros(z)
+        for vref, out in ((None, Av0), (dp(jv2), Av1)):
+            R.ref_assemble_A_csr(nC, nV, len(jr), ip(jr), ip(jc), dp(jv), 2, ip(irow), ip(jcol), ip(size), dp(ival), vref,
+                                 ip(Arp), ip(Aci), dp(out), ip(Ao))
+        zmax = 2 * len(hr)
+        Hrp, Hci, Ho = np.zeros(nV + 1, np.int32), np.zeros(zmax, np.int32), np.zeros(zmax, np.int32)
+        Hv0, Hv1 = np.zeros(zmax), np.zeros(zmax)
+        for vref, out in ((None, Hv0), (dp(hv2), Hv1)):
+            zh = R.ref_assemble_H_csr(nV, len(hr), ip(hr), ip(hc), dp(hv), 1, vref, ip(Hrp), ip(Hci), dp(out), ip(Ho))
+        x = orc._f64(c["x"])
+        Ax, Hx = np.zeros(nC), np.zeros(nV)
+        R.ref_csr_times(nC, nV, z, ip(Arp), ip(Aci), dp(Av0), dp(x), dp(Ax))
+        R.ref_csr_times(nV, nV, zh, ip(Hrp), ip(Hci[:zh].copy()), dp(Hv0[:zh].copy()), dp(x), dp(Hx))
+        cases.append(dict(name=c["name"], n=n, m=m, A_rowptr=Arp.tolist(), A_colidx=Aci.tolist(), A_order=Ao.tolist(),
+                          A_val=Av0.tolist(), A_val2=Av1.tolist(), H_rowptr=Hrp.tolist(), H_colidx=Hci[:zh].tolist(),
+                          H_order=Ho[:zh].tolist(), H_val=Hv0[:zh].tolist(), H_val2=Hv1[:zh].tolist(), Ax=Ax.tolist(),
+                          Hx=Hx.tolist()))
+    with open(os.path.join(OUT, "qore_golden.json"), "w") as f:
+        json.dump(dict(generator="tests/golden/make_golden.py (reference compressed-row SpHbMat via oracle/_ref/libref_l0.so; "
+                                 "inputs = the triplets of l0_golden.json)", cases=cases), f)
+    print("qore_golden.json:", len(cases), "cases; hs071 A.rowptr =", cases[0]["A_rowptr"], "A.order =", cases[0]["A_order"])
+
+
 if __name__ == "__main__":
     orc.build()
     make_qp_fixtures()
     make_l0_golden()
+    make_qore_golden()

@@ -18,6 +18,12 @@ def load_l0_golden():
         return json.load(f)["cases"]
 
 
+def load_qore_golden():
+    """Compressed-row (QORE layout) arrays of the reference's SpHbMat for the triplets of l0_golden.json, case by case."""
+    with open(os.path.join(GOLDEN, "qore_golden.json")) as f:
+        return json.load(f)["cases"]
+
+
 def is_symmetric_fixture(q):
     nV = q["nV"]
     H = sp.csc_matrix((q["H_val"], q["H_rowidx"], q["H_colptr"]), shape=(nV, nV)).toarray()

@@ -26,6 +26,7 @@ class OracleQPInterface:
         self.kkt = np.zeros((B, 5))
         self.wb, self.wc = np.zeros((B, nV), np.int32), np.zeros((B, nC), np.int32)
         self.A = self.H = None
+        self.qA = self.qH = None
         self.solvers = [orc.OracleQP(nV, nC, max_iter=self.maxiter) for _ in range(B)]
         self.inited = np.zeros(B, bool)
         self.first_solved = False
@@ -75,11 +76,105 @@ class OracleQPInterface:
         if rho is not None:
             self.g[:, n:] = np.asarray(rho)[:, None]
 
-    def set_g(self, v): self.g[:] = v
-    def set_lb(self, v): self.lb[:] = v
-    def set_ub(self, v): self.ub[:] = v
-    def set_lbA(self, v): self.lbA[:] = v
-    def set_ubA(self, v): self.ubA[:] = v
+    @staticmethod
+    def _put(arr, a0, a1):
+        if a1 is None:
+            arr[:] = a0        # vector form
+        else:
+            arr[:, int(a0)] = a1  # (location, value) form
+
+    def set_g(self, a0, a1=None): self._put(self.g, a0, a1)
+    def set_lb(self, a0, a1=None): self._put(self.lb, a0, a1)
+    def set_ub(self, a0, a1=None): self._put(self.ub, a0, a1)
+    def set_lbA(self, a0, a1=None): self._put(self.lbA, a0, a1)
+    def set_ubA(self, a0, a1=None): self._put(self.ubA, a0, a1)
+
+    # ---- QORE layout (the twin of the sqpb200_*_csr / *_stacked entry points): row-compressed views, stacked vectors
+    def _csr_view(self, rp, ci, ncol):
+        """Position map between the row- and the column-compressed storage of one pattern (stable for equal keys)."""
+        rp, ci = np.asarray(rp, np.int64), np.asarray(ci, np.int64)
+        rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+        q2c = np.empty(len(ci), np.int64)
+        q2c[np.lexsort((np.arange(len(ci)), rows, ci))] = np.arange(len(ci))
+        cp = np.zeros(ncol + 1, np.int32)
+        np.add.at(cp, ci + 1, 1)
+        cp = np.cumsum(cp).astype(np.int32)
+        ri = np.empty(len(ci), np.int32)
+        ri[q2c] = rows
+        return cp, ri, q2c
+
+    def set_A_csr(self, rhs, I_info=None):
+        if self.A is None:
+            self.qA = dict(zip(("rp", "ci", "val", "order"), orc.assemble_A_csr(
+                self.nC_, self.nV_, rhs.RowIndex, rhs.ColIndex, np.zeros(len(rhs.RowIndex)),
+                (I_info.irow, I_info.jcol, I_info.size, I_info.value))))
+            self.qA["q2c"] = self._csr_view(self.qA["rp"], self.qA["ci"], self.nV_)[2]
+        self.set_A(rhs, I_info)
+
+    def set_H_csr(self, rhs):
+        if self.H is None:
+            self.qH = dict(zip(("rp", "ci", "val", "order"), orc.assemble_H_csr(
+                self.nV_, rhs.RowIndex, rhs.ColIndex, np.zeros(len(rhs.RowIndex)), rhs.isSymmetric)))
+            self.qH["q2c"] = self._csr_view(self.qH["rp"], self.qH["ci"], self.nV_)[2]
+        self.set_H(rhs)
+
+    def set_csr(self, which, rowptr, colidx, vals):
+        cp, ri, q2c = self._csr_view(rowptr, colidx, self.nV_)
+        q = dict(rp=np.asarray(rowptr, np.int32), ci=np.asarray(colidx, np.int32), order=np.arange(len(colidx), dtype=np.int32), q2c=q2c)
+        if which == 0:
+            self.qA, self.A = q, dict(p=cp, i=ri, order=q2c.astype(np.int32), zJ=len(colidx))
+            self.Av = np.zeros((self.batch, len(colidx)))
+        else:
+            self.qH, self.H = q, dict(p=cp, i=ri, order=q2c.astype(np.int32), r=None, c=None, sym=False)
+            self.Hv = np.zeros((self.batch, len(colidx)))
+        self.set_csr_values(which, vals)
+
+    def set_csr_values(self, which, vals):
+        q = self.qA if which == 0 else self.qH
+        v = self._bvals(vals, len(q["ci"]))
+        (self.Av if which == 0 else self.Hv)[:, q["q2c"]] = v
+        if self.first_solved:
+            if which == 0:
+                self.upd_A = True
+            else:
+                self.upd_H = True
+
+    def get_csr(self, which):
+        q = self.qA if which == 0 else self.qH
+        vals = (self.Av if which == 0 else self.Hv)[:, q["q2c"]]
+        return dict(RowIndex=np.asarray(q["rp"], np.int32), ColIndex=np.asarray(q["ci"], np.int32),
+                    order=np.asarray(q["order"], np.int32), MatVal=vals.copy())
+
+    def set_bounds_stacked(self, lb=None, ub=None):
+        nV = self.nV_
+        if lb is not None:
+            lb = np.broadcast_to(np.asarray(lb, dtype=np.float64), (self.batch, nV + self.nC_))
+            self.lb[:], self.lbA[:] = lb[:, :nV], lb[:, nV:]
+        if ub is not None:
+            ub = np.broadcast_to(np.asarray(ub, dtype=np.float64), (self.batch, nV + self.nC_))
+            self.ub[:], self.ubA[:] = ub[:, :nV], ub[:, nV:]
+
+    def get_bounds_stacked(self):
+        return np.hstack([self.lb, self.lbA]), np.hstack([self.ub, self.ubA])
+
+    def spmv(self, which, x, transpose=False):
+        out = []
+        for b in range(self.batch):
+            if which == 0:
+                out.append(orc.csc_times(self.nC_, self.nV_, self.A["p"], self.A["i"], self.Av[b], x[b], transpose=transpose))
+            else:
+                out.append(orc.csc_times(self.nV_, self.nV_, self.H["p"], self.H["i"], self.Hv[b], x[b]))
+        return np.array(out).reshape(self.batch, -1)
+
+    def vector_times(self, a, b):
+        out = np.zeros(len(a))
+        for i in range(np.shape(a)[1]):  # index order of Vector::times
+            out = out + np.asarray(a)[:, i] * np.asarray(b)[:, i]
+        return out
+
+    def get_solution_stacked(self, want=("primal", "dual", "workingset")):
+        Ax = self.spmv(0, self.x) if self.nC_ else np.zeros((self.batch, 0))
+        return np.hstack([self.x, Ax]), self.y.copy(), -np.hstack([self.wb, self.wc]).astype(np.int32)
 
     # ---- solve: the init/hotstart decision of src/qpOASESInterface.cpp:141-211 per handle
     def _solve(self, active_mask):

@@ -25,6 +25,21 @@ def test_adapter_compiles_against_reference_headers():
     assert r.returncode == 0, r.stderr
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/include"), reason="needs the reference headers")
+def test_qore_layout_adapter_compiles_against_reference_headers():
+    cmd = ["g++", "-std=c++11", "-fsyntax-only", "-w", "-I" + os.path.join(ROOT, "oracle", "stubs"), "-I/root/reference/include",
+           "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "restartsqp_b200", "csrc", "adapter", "CudaQOREInterface.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_qore_layout_adapter_implements_every_pure_virtual():
+    hpp = open(os.path.join(ROOT, "restartsqp_b200", "csrc", "adapter", "CudaQOREInterface.hpp")).read()
+    assert hpp.count("override") >= 30  # the 30 pure virtuals of include/sqphot/QPsolverInterface.hpp:43-194
+    for ref in ("include/sqphot/QOREInterface.hpp:30-252", "src/QPhandler.cpp:225-260"):
+        assert ref in hpp
+
+
 def test_adapter_implements_every_pure_virtual():
     hpp = open(os.path.join(ROOT, "restartsqp_b200", "csrc", "adapter", "CudaQPInterface.hpp")).read()
     for name in ["getLb", "getUb", "getLbA", "getUbA", "getG", "getH", "getA", "optimizeQP", "optimizeLP", "get_optimal_solution",
@@ -90,4 +105,43 @@ def test_cpp_plugin_matches_oracle_on_hs071(gpu_lib):
     x2, y2, obj2, it2 = o["solver"].solution()
     assert int(out["hot_status"][0]) == st == 20
     assert np.array(out["hot_x"], float).tolist() == x2.tolist()
+    assert int(out["hot_qp_iter"][0]) == o["iters"] + it2
+
+
+@pytest.mark.gpu
+def test_cpp_qore_layout_plugin_matches_oracle_on_hs071(gpu_lib):
+    """The QORE-layout plugin (CudaQOREInterface.cpp) driven like QPhandler's QORE branch: x_qp = [x ; A x], one stacked
+    multiplier vector, QORE's working-set sign, row-compressed getA(); same numbers as the oracle, bit for bit."""
+    if not os.path.exists(DRIVER):
+        pytest.skip("oracle/_ref/adapter_hs071 not built (needs /root/reference at build time)")
+    p = subprocess.run([DRIVER, "qore"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = {}
+    for line in p.stdout.strip().splitlines():
+        k, *v = line.split()
+        out[k] = v
+    prob, A, Hh = hs071_first_qp(1.0)
+    o = H.oracle_solve(orc, prob, Acsc=A[:3], Hcsc=Hh[:3])
+    assert int(out["status"][0]) == 20 == o["status"] and int(out["kkt_ok"][0]) == 1 and int(out["getLbA_threw"][0]) == 1
+    assert int(out["qp_iter"][0]) == o["iters"]
+    Ax = orc.csc_times(2, 8, A[0], A[1], A[2], o["x"])
+    assert np.array(out["x"], float).tolist() == o["x"].tolist() + Ax.tolist()  # [x ; A x], bit-identical
+    assert np.array(out["y"], float).tolist() == o["y"].tolist()
+    assert float(out["obj"][0]) == o["obj"]
+    assert [int(t) for t in out["ws"]] == (-np.concatenate([o["wb"], o["wc"]])).tolist()  # QORE: -1 upper, +1 lower
+    Wb, Wc = orc.translate_working_set(o["wb"], o["wc"], o["x"], Ax, prob["lb"], prob["ub"], prob["lbA"], prob["ubA"])
+    assert [int(t) for t in out["Wb"]] == Wb.tolist() and [int(t) for t in out["Wc"]] == Wc.tolist()
+    # getA() is the reference's compressed-row matrix of the same triplets
+    jr, jc = [1, 2] * 4, [1, 1, 2, 2, 3, 3, 4, 4]
+    xk = np.array([1.0, 5.0, 5.0, 1.0])
+    J = np.array([[xk[1] * xk[2] * xk[3], xk[0] * xk[2] * xk[3], xk[0] * xk[1] * xk[3], xk[0] * xk[1] * xk[2]], 2 * xk])
+    rp, ci, v, _ = orc.assemble_A_csr(2, 8, jr, jc, np.array([J[a - 1, b - 1] for a, b in zip(jr, jc)]), orc.identity_info(4, 2))
+    assert [int(t) for t in out["A_rowptr"]] == rp.tolist() and [int(t) for t in out["A_colidx"]] == ci.tolist()
+    assert np.array(out["A_val"], float).tolist() == v.tolist()
+    assert np.array(out["lb"], float).tolist() == prob["lb"].tolist() + prob["lbA"].tolist()
+    prob2, _, _ = hs071_first_qp(0.5)
+    st = o["solver"].hotstart(prob2["g"], prob2["lb"], prob2["ub"], prob2["lbA"], prob2["ubA"])
+    x2, y2, obj2, it2 = o["solver"].solution()
+    assert int(out["hot_status"][0]) == st == 20
+    assert np.array(out["hot_x"], float)[:8].tolist() == x2.tolist()
     assert int(out["hot_qp_iter"][0]) == o["iters"] + it2

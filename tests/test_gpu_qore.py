@@ -1,0 +1,204 @@
+"""GPU parity of the QORE-layout entry points (include/sqpb200.h: sqpb200_set_structure_*_csr, sqpb200_set_values_csr,
+sqpb200_set_bounds_stacked, sqpb200_get_solution_stacked) and of the host class on top of them (restartsqp_b200/qore_layout.py,
+mirror of include/sqphot/QOREInterface.hpp).  Index arrays are compared bit for bit with the compressed-row arrays the
+reference's own SpHbMat builds (tests/golden/qore_golden.json); a QP given in the QORE layout must come back with exactly the
+numbers the same QP gives in the qpOASES layout, since both run on the same kernels."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import restartsqp_b200 as r
+from restartsqp_b200 import capi, qp_dump
+from restartsqp_b200.qore_layout import CudaQOREInterface, replay_qore
+from restartsqp_b200.sqp_types import SQRT_M_EPS
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+L0 = {c["name"]: c for c in H.load_l0_golden()}
+QORE = H.load_qore_golden()
+
+
+def identity(n, m):
+    return r.IdentityInfo(irow=np.array([1, 1], np.int32), jcol=np.array([n + 1, n + m + 1], np.int32),
+                          size=np.array([m, m], np.int32), value=np.array([1.0, -1.0]))
+
+
+@pytest.mark.parametrize("q", QORE, ids=[c["name"] for c in QORE])
+def test_device_csr_assembly_bit_exact_with_reference(gpu_lib, q):
+    c = L0[q["name"]]
+    n, m = c["n"], c["m"]
+    nV, nC = n + 2 * m, m
+    s = CudaQOREInterface(r.NLPInfo(nCon=m, nVar=n), r.QPType.QP, batch=3)
+    J = r.SpTripletMat(np.array(c["J_row1"], np.int32), np.array(c["J_col1"], np.int32), np.array(c["J_val"]), nC, nV, False)
+    Hm = r.SpTripletMat(np.array(c["H_row1"], np.int32), np.array(c["H_col1"], np.int32), np.array(c["H_val"]), nV, nV, True)
+    s.set_A(J, identity(n, m))
+    s.set_H(Hm)
+    A, Hh = s.getA(), s.getH()
+    assert A["RowIndex"].tolist() == q["A_rowptr"] and A["ColIndex"].tolist() == q["A_colidx"] and A["order"].tolist() == q["A_order"]
+    assert Hh["RowIndex"].tolist() == q["H_rowptr"] and Hh["ColIndex"].tolist() == q["H_colidx"] and Hh["order"].tolist() == q["H_order"]
+    for b in range(3):
+        assert A["MatVal"][b].tolist() == q["A_val"] and Hh["MatVal"][b].tolist() == q["H_val"]
+    # the column-compressed pattern the kernels work on is the one the qpOASES-layout path builds from the same triplets
+    Ac, Hc = s.inner.getA(), s.inner.getH()
+    assert Ac["ColIndex"].tolist() == c["A_colptr"] and Ac["RowIndex"].tolist() == c["A_rowidx"] and Ac["order"].tolist() == c["A_order"]
+    assert Hc["ColIndex"].tolist() == c["H_colptr"] and Hc["RowIndex"].tolist() == c["H_rowidx"] and Hc["order"].tolist() == c["H_order"]
+    assert Ac["MatVal"][2].tolist() == c["A_val"] and Hc["MatVal"][0].tolist() == c["H_cscval"]
+    # later calls refresh values (per-instance values)
+    J.MatVal = np.stack([np.array(c["J_val2"]), np.array(c["J_val"]), 2.0 * np.array(c["J_val2"])])
+    Hm.MatVal = np.stack([np.array(c["H_val2"]), np.array(c["H_val"]), 2.0 * np.array(c["H_val2"])])
+    s.set_A(J, None)
+    s.set_H(Hm)
+    A, Hh = s.getA(), s.getH()
+    assert A["MatVal"][0].tolist() == q["A_val2"] and A["MatVal"][1].tolist() == q["A_val"]
+    assert Hh["MatVal"][0].tolist() == q["H_val2"] and Hh["MatVal"][1].tolist() == q["H_val"]
+    # values handed over in compressed-row order land where the triplet path put them
+    s.set_csr_values(capi.MAT_A, np.array(q["A_val"]))
+    s.set_csr_values(capi.MAT_H, np.stack([np.array(q["H_val"])] * 3))
+    assert s.inner.getA()["MatVal"][1].tolist() == c["A_val"] and s.inner.getH()["MatVal"][2].tolist() == c["H_cscval"]
+    # products on the handle are the reference's compressed-row products (bit-identical with its column-compressed ones)
+    x = np.tile(np.array(c["x"]), (3, 1))
+    if nC:
+        assert s.spmv(capi.MAT_A, x)[0].tolist() == q["Ax"]
+    assert s.spmv(capi.MAT_H, x)[2].tolist() == q["Hx"]
+    s.close()
+
+
+def test_stacked_bounds_round_trip(gpu_lib):
+    nV, nC, B = 5, 2, 4
+    rng = np.random.default_rng(0)
+    s = CudaQOREInterface(nV=nV, nC=nC, batch=B)
+    lb, ub = rng.standard_normal((B, nV + nC)), rng.standard_normal((B, nV + nC))
+    s.set_lb(lb); s.set_ub(ub)
+    assert (s.getLb() == lb).all() and (s.getUb() == ub).all()
+    assert (s.inner.getLb() == lb[:, :nV]).all() and (s.inner.getUbA() == ub[:, nV:]).all()
+    s.set_lb(np.arange(7.0))  # one row for every instance
+    assert (s.getLb() == np.arange(7.0)).all() and (s.getUb() == ub).all()
+    s.set_lb(1, -4.0); s.set_ub(6, np.array([1.0, 2.0, 3.0, 4.0])); s.set_lb(5, 0.5)
+    s.set_lbA(0, 99.0)  # no-op in this layout
+    got = s.getLb()
+    assert got[3].tolist() == [0, -4, 2, 3, 4, 0.5, 6] and s.getUb()[:, 6].tolist() == [1, 2, 3, 4]
+    s.reset_constraints()
+    assert not s.getLb().any() and not s.getUb().any()
+    s.close()
+
+
+def both_layouts(p, B, g):
+    nV, nC = p["nV"], p["nC"]
+    Acsr, Hcsr = sp.csr_matrix(p["A"]), sp.csr_matrix(p["H"])
+    Acsr.sort_indices(); Hcsr.sort_indices()
+    q = CudaQOREInterface(nV=nV, nC=nC, batch=B)
+    q.set_csr(capi.MAT_A, Acsr.indptr, Acsr.indices, Acsr.data)
+    q.set_csr(capi.MAT_H, Hcsr.indptr, Hcsr.indices, Hcsr.data)
+    q.set_g(g)
+    q.set_lb(np.concatenate([p["lb"], p["lbA"]])); q.set_ub(np.concatenate([p["ub"], p["ubA"]]))
+    o = r.CudaQPInterface(nV=nV, nC=nC, batch=B)
+    o.set_csc(capi.MAT_A, *H.csc(p["A"]))
+    o.set_csc(capi.MAT_H, *H.csc(p["H"]))
+    o.set_g(g); o.set_lb(p["lb"]); o.set_ub(p["ub"]); o.set_lbA(p["lbA"]); o.set_ubA(p["ubA"])
+    return q, o
+
+
+def reference_translation(ws, primal, lb, ub, nV):
+    """src/QOREInterface.cpp:440-492, entry by entry."""
+    W = np.zeros(len(ws), np.int32)
+    for i in range(len(ws)):
+        if i < nV:
+            near_lb, near_ub = abs(primal[i] - lb[i]) < SQRT_M_EPS, abs(primal[i] - ub[i]) < SQRT_M_EPS
+        else:
+            near_lb, near_ub = abs(float(primal[i] - lb[i] < SQRT_M_EPS)) != 0, abs(float(primal[i] - ub[i] < SQRT_M_EPS)) != 0
+        if ws[i] == -1:
+            W[i] = -99 if near_lb else 1
+        elif ws[i] == 1:
+            W[i] = -99 if near_ub else -1
+    return W
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_qore_layout_solves_equal_qpoases_layout_solves(gpu_lib, seed):
+    rng = np.random.default_rng(900 + seed)
+    n, m, B = int(rng.integers(2, 12)), int(rng.integers(0, 8)), 16
+    p = H.random_l1_qp(rng, n, m)
+    nV, nC = p["nV"], p["nC"]
+    g = np.tile(p["g"], (B, 1))
+    g[:, :n] += 0.3 * rng.standard_normal((B, n))
+    q, o = both_layouts(p, B, g)
+    q.optimizeQP(); o.optimizeQP()
+    assert (q.get_status() == 20).all() and (o.get_status() == 20).all()
+    pr = q.get_primal_stacked()
+    x = o.get_optimal_solution()
+    assert (pr[:, :nV] == x).all()
+    if nC:
+        assert (pr[:, nV:] == o.spmv(capi.MAT_A, x)).all()
+    assert (q.get_multipliers_bounds() == o.get_multipliers_bounds()).all()
+    assert (q.get_multipliers_constr() == o.get_multipliers_constr()).all()
+    assert (q.get_iterations() == o.get_iterations()).all()
+    wc, wb = o.get_working_set(translated=False)
+    raw = q.get_working_set_raw()
+    assert (raw == -np.hstack([wb, wc])).all()  # QORE: -1 upper, +1 lower
+    Wc, Wb = q.get_working_set()
+    Wc_o, Wb_o = o.get_working_set(translated=True)
+    assert (Wc == Wc_o).all() and (Wb == Wb_o).all()  # both translations keep the same misplaced parenthesis
+    lb, ub = q.getLb(), q.getUb()
+    for b in range(0, B, 5):
+        W = reference_translation(raw[b], pr[b], lb[b], ub[b], nV)
+        assert (Wb[b] == W[:nV]).all() and (Wc[b] == W[nV:]).all()
+    ko, kq = o.get_optimality_status(), q.get_optimality_status()
+    assert (kq["KKT_error"] == ko["KKT_error"]).all() and q.test_optimality().all()
+    obj = o.get_obj_value()
+    assert np.abs(q.get_obj_value() - obj).max() <= 1e-9 * max(1.0, np.abs(obj).max())
+    # hot start after new bounds and new matrix values, both layouts
+    g2 = g + 0.05 * rng.standard_normal(g.shape)
+    q.set_g(g2); o.set_g(g2)
+    Acsr = sp.csr_matrix(p["A"]); Acsr.sort_indices()
+    q.set_csr_values(capi.MAT_A, Acsr.data * 1.0); o.set_csc_values(capi.MAT_A, H.csc(p["A"])[2])
+    q.optimizeQP(); o.optimizeQP()
+    assert (q.get_status() == o.get_status()).all() and (q.get_iterations() == o.get_iterations()).all()
+    assert (q.get_optimal_solution() == o.get_optimal_solution()).all()
+    q.close(); o.close()
+
+
+def test_replay_of_the_dumped_qps_in_their_own_layout(gpu_lib, tmp_path):
+    """The 18 `.log` dumps are QORE-layout files (src/QOREInterface.cpp:582-598): written back to that layout and replayed through
+    the QORE data constructor they solve exactly like the converted fixtures do through the qpOASES-layout constructor."""
+    fixtures = [f for f in H.load_qp_fixtures() if f["source"] == "log" and H.is_symmetric_fixture(f) and f["name"] != "QORE_hs107"]
+    assert len(fixtures) >= 10
+    for f in fixtures:
+        path = str(tmp_path / (f["name"] + "qpdata.log"))
+        qp_dump.write_qore_log(path, f)
+        q = replay_qore(path, batch=2)
+        o = qp_dump.replay(f, batch=2)
+        q.optimizeQP(); o.optimizeQP()
+        assert (q.get_status() == o.get_status()).all(), f["name"]
+        assert (q.get_iterations() == o.get_iterations()).all(), f["name"]
+        assert (q.get_optimal_solution() == o.get_optimal_solution()).all(), f["name"]
+        assert (q.get_multipliers_constr() == o.get_multipliers_constr()).all(), f["name"]
+        out = str(tmp_path / "out.log")
+        q.WriteQPDataToFile(out, instance=1)
+        assert open(out).read() == open(path).read(), f["name"]
+        q.close(); o.close()
+
+
+def test_device_sqp_loop_through_the_qore_layout(gpu_lib):
+    """Algorithm::Optimize with QPsolverChoice = QORE (src/QPhandler.cpp:63-64): the device-resident loop on QORE-layout
+    handles gives the iterates of the default layout, bit for bit."""
+    import os
+    from restartsqp_b200.sqp_device import DeviceBatchedSQP
+    from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
+    from test_hs_suite import HS_DIR, perturbed_starts
+    res = {}
+    for name in ("hs071", "hs043"):
+        host = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+        X = perturbed_starts(host, 64, 7)
+        for choice in (r.Solver.CUDA_B200, r.Solver.QORE):
+            opt = r.Options(iter_max=120)
+            opt.QPsolverChoice = opt.LPsolverChoice = choice
+            dev = DeviceNLP(host)
+            alg = DeviceBatchedSQP(dev, x0=X, options=opt)
+            if choice == r.Solver.QORE:
+                assert isinstance(alg.myQP_.solverInterface_, CudaQOREInterface) and isinstance(alg.myLP_.solverInterface_, CudaQOREInterface)
+            res[choice] = alg.Optimize()
+            alg.close()
+            dev.close()
+        a, b = res[r.Solver.CUDA_B200], res[r.Solver.QORE]
+        assert (a.exitflag == b.exitflag).all() and ((a.exitflag == 0).mean() > 0.9 or name != "hs071"), name
+        assert (a.iters == b.iters).all() and (a.qp_iter == b.qp_iter).all() and (a.x == b.x).all(), name

@@ -53,13 +53,32 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+# the C++ batched host driver (csrc/driver): BatchedAlgorithm + its command-line front end, linked against the library
+DRIVER = os.path.join(LIBDIR, "batched_sqp")
+DRIVER_SRC = [os.path.join(CSRC, "driver", f) for f in ("BatchedAlgorithm.cpp", "batched_sqp_main.cpp")]
+DRIVER_DEPS = DRIVER_SRC + [os.path.join(CSRC, "driver", "BatchedAlgorithm.hpp"), HEADERS[-1]]
+
+
 def is_stale():
-    return _stale(LIB, [u[0] for u in _units()] + HEADERS + [os.path.abspath(__file__)])
+    return _stale(LIB, [u[0] for u in _units()] + HEADERS + [os.path.abspath(__file__)]) or _stale(DRIVER, DRIVER_DEPS + [LIB])
+
+
+def build_driver(force=False):
+    """g++-level C++ (no device code): compiled by nvcc's host compiler, linked with libsqpb200.so and the CUDA runtime."""
+    if not force and not _stale(DRIVER, DRIVER_DEPS + [LIB]):
+        return DRIVER
+    cmd = [_nvcc(), "-O2", "-std=c++17", "-I" + os.path.join(os.path.dirname(HERE), "include"), "-o", DRIVER] + DRIVER_SRC + [
+        "-L" + LIBDIR, "-lsqpb200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("driver build failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return DRIVER
 
 
 def build(force=False, verbose=False):
     """Compile the CUDA extension if it is missing or older than its sources.  Returns the .so path."""
-    if not force and not is_stale():
+    if not force and not _stale(LIB, [u[0] for u in _units()] + HEADERS + [os.path.abspath(__file__)]):
+        build_driver()
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
@@ -83,6 +102,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print("\n".join(logs))
+    build_driver(force=True)
     return LIB
 
 

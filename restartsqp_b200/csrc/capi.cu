@@ -177,7 +177,7 @@ int sqpb200_create(int batch, int nV, int nC, int qptype, int device, const sqpb
         const size_t o_mask = take(B);
         if (cudaMalloc(&h->arena, off) != cudaSuccess) { h->arena = nullptr; rc = 1; }
         else {
-            cudaMemsetAsync(h->arena, 0, off, h->stream);
+            if (cudaMemsetAsync(h->arena, 0, off, h->stream) != cudaSuccess) rc = 1;
             char* a = (char*)h->arena;
             // the vectors (g .. ubA) and the results (x .. iters) are two contiguous blocks: one copy each way per solve
             h->in_off[0] = o_g; h->in_off[1] = o_lb; h->in_off[2] = o_ub; h->in_off[3] = o_lbA; h->in_off[4] = o_ubA; h->in_bytes = o_x;
@@ -190,20 +190,19 @@ int sqpb200_create(int batch, int nV, int nC, int qptype, int device, const sqpb
             h->dwsB = (signed char*)(a + o_wsB); h->dwsC = (signed char*)(a + o_wsC); h->dmask = (unsigned char*)(a + o_mask);
         }
     }
-    if (rc) { *out = h; return SQPB200_ERR_CUDA; }
-    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+    if (rc) { h->err = "allocation of the vector arena failed"; *out = h; return SQPB200_ERR_CUDA; }
+    if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) { h->err = "cudaEventCreate failed"; *out = h; return SQPB200_ERR_CUDA; }
     if (cudaMalloc((void**)&h->dmaxfr, sizeof(int)) == cudaSuccess && cudaMallocHost((void**)&h->maxfr_host, sizeof(int)) == cudaSuccess &&
         cudaEventCreateWithFlags(&h->ev_maxfr, cudaEventDisableTiming) == cudaSuccess) {
-        cudaMemset(h->dmaxfr, 0, sizeof(int));
         *h->maxfr_host = 0;
-        if (cudaMalloc((void**)&h->dncap, (size_t)(batch + 1) * sizeof(int)) != cudaSuccess) { h->err = "allocation failed"; *out = h; return SQPB200_ERR_CUDA; }
-        cudaMemset(h->dncap, 0, (size_t)(batch + 1) * sizeof(int));
+        if (cudaMemset(h->dmaxfr, 0, sizeof(int)) != cudaSuccess || cudaMalloc((void**)&h->dncap, (size_t)(batch + 1) * sizeof(int)) != cudaSuccess ||
+            cudaMemset(h->dncap, 0, (size_t)(batch + 1) * sizeof(int)) != cudaSuccess) { h->err = "allocation failed"; *out = h; return SQPB200_ERR_CUDA; }
     } else { h->err = "allocation of the capacity counter failed"; *out = h; return SQPB200_ERR_CUDA; }
     if (cudaMalloc((void**)&h->dprof, 16 * sizeof(long long)) == cudaSuccess) cudaMemset(h->dprof, 0, 16 * sizeof(long long));
     else h->dprof = nullptr;
     // status = NOTINITIALISED until the first solve
     std::vector<int> st(batch, SQPB200_QPERROR_NOTINITIALISED);
-    cudaMemcpy(h->dstatus, st.data(), B * sizeof(int), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(h->dstatus, st.data(), B * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "initialising the status array failed"; *out = h; return SQPB200_ERR_CUDA; }
     *out = h;
     return 0;
 }

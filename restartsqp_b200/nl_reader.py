@@ -731,6 +731,26 @@ class AmplNLP:
             return self._h(self._x(x), np.ascontiguousarray(np.atleast_2d(lam), dtype=np.float64))
 
 
+def write_model_file(nlp, path, x0=None):
+    """Hand a model to the C++ batched driver (restartsqp_b200/csrc/driver/batched_sqp_main.cpp -> BatchedAlgorithm): sizes,
+    bounds, starting point, 1-based sparsity patterns, the starting points [B][n] and the CUDA source of the batched evaluator.
+    Doubles are written as C99 hex floats: the hand-over is exact."""
+    h = nlp if isinstance(nlp, AmplNLP) else AmplNLP(nlp)
+    xl, xu, cl, cu = h.Get_bounds_info()
+    xs, ls = h.Get_starting_point()
+    x0 = np.atleast_2d(np.asarray(xs if x0 is None else x0, dtype=np.float64))
+    hx = lambda a: " ".join(("inf" if v == np.inf else "-inf" if v == -np.inf else float(v).hex()) for v in np.asarray(a, dtype=np.float64).ravel())
+    ints = lambda a: " ".join(str(int(v)) for v in a)
+    with open(path, "w") as f:
+        f.write("%d %d %d %d %d\n" % (h.n, h.m, len(h.J_row1), len(h.H_row1), x0.shape[0]))
+        for a in (xl, xu, cl, cu, xs, np.asarray(ls, dtype=np.float64).reshape(-1)[:h.m]):
+            f.write(hx(a) + "\n")
+        for a in (h.J_row1, h.J_col1, h.H_row1, h.H_col1):
+            f.write(ints(a) + "\n")
+        f.write(hx(x0) + "\n---SOURCE---\n")
+        f.write(h.cuda_source())
+
+
 class DeviceNLP:
     """AmplNLP whose evaluations run on the GPU: the generated CUDA source is compiled with NVRTC through the C ABI
     (sqpb200_nlp_compile / _load / _eval).  Same SQPTNLP-shaped interface plus the fused calls the batched driver prefers

@@ -575,6 +575,26 @@ def run_extras(device, hbm_peak):
         ex["sqp_hs071_1e6"] = sqp_case("hs071", 0, 1000000, reps=2)
     except Exception as e:
         ex["sqp_hs071"] = {"error": repr(e)[:200]}
+    try:  # the same 10^4 HS071 solves through the C++ host driver (csrc/driver/BatchedAlgorithm.cpp + batched_sqp), no Python in the loop
+        import subprocess
+        import tempfile
+        from restartsqp_b200.nl_reader import write_model_file
+        exe = os.path.join(ROOT, "restartsqp_b200", "lib", "batched_sqp")
+        host = AmplNLP(os.path.join(ROOT, "tests", "golden", "hs_nl", "hs071.nl"))
+        with tempfile.TemporaryDirectory() as td:
+            mf = os.path.join(td, "hs071.model")
+            write_model_file(host, mf, perturbed_starts(host, 10000, 0))
+            p = subprocess.run([exe, mf, "--quiet", "--repeat", "3"], capture_output=True, text=True, timeout=120)
+        if p.returncode != 0:
+            raise RuntimeError((p.stdout + p.stderr)[-200:])
+        t = p.stdout.strip().splitlines()[-1].split()
+        kv = dict(zip(t[1::2], t[2::2]))
+        ex["sqp_hs071_cpp_driver"] = {"metric": "SQP solves/sec", "instances": int(kv["instances"]), "optimal": int(kv["optimal"]),
+                                      "value": float(kv["solves_per_s"]), "unit": "solves/s", "optimize_ms": float(kv["optimize_ms"]),
+                                      "note": "restartsqp_b200/lib/batched_sqp: BatchedAlgorithm::Optimize of the third batch on one object, "
+                                              "CUDA events around the call (starts already uploaded by reset)"}
+    except Exception as e:
+        ex["sqp_hs071_cpp_driver"] = {"error": repr(e)[:200]}
     try:  # configs[2]: a slice of the HS suite, 10^4 perturbed starts per problem, CPU figure per problem
         rows, tg, tc, ninst, nopt = {}, 0.0, 0.0, 0, 0
         for k, name in enumerate(HS_SLICE):

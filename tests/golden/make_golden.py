@@ -14,6 +14,7 @@ Writes
   l0_golden.json    outputs of the reference's own L0 code (oracle/_ref/libref_l0.so): CSC index
                     arrays, `order`, refreshed values, SpMV / SpMTV results and norms for the HS071
                     shaped probe of SURVEY.md section 8c and for seeded random matrices.
+  qp_fixtures_qore.json  the 18 `.log` dumps unconverted (QORE layout, explicit zeros kept): inputs of the QORE data constructor.
   qore_golden.json  the same triplets through the reference's compressed-row SpHbMat (the QORE layout of
                     src/QOREInterface.cpp:89-90, 643-659): row pointers, column indices, `order`, values.
 """
@@ -201,6 +202,26 @@ def make_l0_golden():
           cases[0]["A_order"], "H.colptr =", cases[0]["H_colptr"])
 
 
+def make_qore_raw_fixtures():
+    """qp_fixtures_qore.json: the 18 `.log` dumps as they are (QORE layout: stacked bounds, row-compressed A and H with their
+    explicit zeros), i.e. what test/QPsolvers_testers.cpp:48-150 reads and hands to the QORE data constructor (:74-75, 172-175)
+    before it converts a copy for qpOASES.  Inputs only."""
+    qps = []
+    for p in sorted(glob.glob(REF + "/test/unsolved_QP_data/*.log")):
+        it = iter(open(p).read().split())
+        nV, nC, zA, zH = (int(next(it)) for _ in range(4))
+        f = lambda n: [float(next(it)) for _ in range(n)]
+        i = lambda n: [int(next(it)) for _ in range(n)]
+        lb, ub, g = f(nV + nC), f(nV + nC), f(nV)
+        A_rp, A_ci, A_v = i(nC + 1), i(zA), f(zA)
+        H_rp, H_ci, H_v = i(nV + 1), i(zH), f(zH)
+        qps.append(dict(name=os.path.basename(p).replace("qpdata.log", ""), nV=nV, nC=nC, lb=lb, ub=ub, g=g, A_rowptr=A_rp,
+                        A_colidx=A_ci, A_val=A_v, H_rowptr=H_rp, H_colidx=H_ci, H_val=H_v))
+    with open(os.path.join(OUT, "qp_fixtures_qore.json"), "w") as fo:
+        json.dump(dict(generator="tests/golden/make_golden.py (test/unsolved_QP_data/*.log, unconverted)", qps=qps), fo)
+    print("qp_fixtures_qore.json:", len(qps), "QPs; explicit zeros in H:", {q["name"]: sum(1 for v in q["H_val"] if v == 0.0) for q in qps})
+
+
 def make_qore_golden():
     """qore_golden.json: the compressed-row arrays the reference's QOREInterface hands to QPSetData
     (src/QOREInterface.cpp:89-90): SpHbMat(..., isCompressedRow = true)::setStructure / setMatVal run on the triplets of
@@ -246,3 +267,4 @@ if __name__ == "__main__":
     make_qp_fixtures()
     make_l0_golden()
     make_qore_golden()
+    make_qore_raw_fixtures()

@@ -24,6 +24,12 @@ def load_qore_golden():
         return json.load(f)["cases"]
 
 
+def load_qore_raw_fixtures():
+    """The 18 `.log` dumps unconverted (QORE layout, explicit zeros kept): inputs of the QORE data constructor."""
+    with open(os.path.join(GOLDEN, "qp_fixtures_qore.json")) as f:
+        return json.load(f)["qps"]
+
+
 def is_symmetric_fixture(q):
     nV = q["nV"]
     H = sp.csc_matrix((q["H_val"], q["H_rowidx"], q["H_colptr"]), shape=(nV, nV)).toarray()

@@ -178,6 +178,33 @@ def test_replay_of_the_dumped_qps_in_their_own_layout(gpu_lib, tmp_path):
         q.close(); o.close()
 
 
+def test_replay_driver_both_arms_agree(gpu_lib):
+    """test/QPsolvers_testers.cpp solves each dumped QP twice: unconverted with the QORE-layout backend (:172-200) and, converted
+    through the dense matrix, with the qpOASES-layout backend (:206-229).  Same two arms on the GPU, 64 perturbed replicas each:
+    identical status, iteration counts and working sets, solutions equal to the last bits (the unconverted matrices keep
+    explicit zeros and, in hs104, entries of 1e-17 that the conversion drops)."""
+    raw = {q["name"]: q for q in H.load_qore_raw_fixtures()}
+    fixtures = [f for f in H.load_qp_fixtures() if f["source"] == "log" and H.is_symmetric_fixture(f) and f["name"] != "QORE_hs107"]
+    assert len(fixtures) >= 10
+    B = 64
+    rng = np.random.default_rng(1234)
+    for f in fixtures:
+        q_raw = raw[f["name"]]
+        g = np.tile(np.array(f["g"]), (B, 1))
+        g[1:] *= 1.0 + 1.0e-3 * rng.uniform(-1.0, 1.0, (B - 1, f["nV"]))  # SURVEY.md 8d config 2 perturbation, replica 0 exact
+        q = replay_qore(q_raw, batch=B)
+        o = qp_dump.replay(f, batch=B)
+        q.set_g(g); o.set_g(g)
+        q.inner.optimizeQP(); o.optimizeQP()
+        assert (q.inner.get_status() == o.get_status()).all(), f["name"]
+        assert (q.get_iterations() == o.get_iterations()).all(), f["name"]
+        wc, wb = o.get_working_set(translated=False)
+        assert (q.get_working_set_raw() == -np.hstack([wb, wc])).all(), f["name"]
+        x = o.get_optimal_solution()
+        assert np.abs(q.get_optimal_solution() - x).max() <= 1e-12 * max(1.0, np.abs(x).max()), f["name"]
+        q.close(); o.close()
+
+
 def test_device_sqp_loop_through_the_qore_layout(gpu_lib):
     """Algorithm::Optimize with QPsolverChoice = QORE (src/QPhandler.cpp:63-64): the device-resident loop on QORE-layout
     handles gives the iterates of the default layout, bit for bit."""

@@ -15,7 +15,7 @@ from restartsqp_b200.qore_layout import CudaQOREInterface, read_qore_log_raw, re
 from restartsqp_b200.sqp_driver import BatchedSQP, HS071
 from restartsqp_b200.sqp_types import SQRT_M_EPS
 from oracle_backend import OracleQPInterface
-from helpers import load_l0_golden, load_qore_golden, load_qp_fixtures, random_l1_qp, is_symmetric_fixture
+from helpers import load_l0_golden, load_qore_golden, load_qp_fixtures, load_qore_raw_fixtures, random_l1_qp, is_symmetric_fixture, oracle_solve
 
 L0 = {c["name"]: c for c in load_l0_golden()}
 
@@ -207,3 +207,26 @@ def test_sqp_loop_through_the_qore_layout_equals_the_qpoases_layout():
     assert (res_q.exitflag == res_p.exitflag).all() and (res_q.exitflag == 0).all()
     assert (res_q.iters == res_p.iters).all() and (res_q.qp_iter == res_p.qp_iter).all()
     assert (res_q.x == res_p.x).all()
+
+
+RAW = load_qore_raw_fixtures()
+
+
+@pytest.mark.parametrize("q", RAW, ids=[q["name"] for q in RAW])
+def test_replay_driver_both_arms_agree(q):
+    """test/QPsolvers_testers.cpp solves each dumped QP twice: as it is with the QORE-layout backend (:172-200) and, converted
+    through the dense matrix (entries with |v| <= 1e-16 dropped, :206-218), with the qpOASES-layout backend (:220-229), and
+    prints the two side by side.  Same two arms on the oracle twin: identical status, iteration count and working set; the
+    solutions agree to the last bits (the unconverted matrices keep explicit zeros and, in hs104, entries of 1e-17)."""
+    from oracle import oracle_py as orc
+    f = [c for c in load_qp_fixtures() if c["name"] == q["name"]][0]
+    s = replay_qore(q, batch=1, backend=OracleQPInterface(nV=q["nV"], nC=q["nC"], batch=1))
+    s.inner.optimizeQP()  # no exception for the reference's own failure case (hs107)
+    o = oracle_solve(orc, dict(nV=f["nV"], nC=f["nC"], g=np.array(f["g"]), lb=np.array(f["lb"]), ub=np.array(f["ub"]),
+                               lbA=np.array(f["lbA"]), ubA=np.array(f["ubA"])),
+                     Acsc=(np.array(f["A_colptr"], np.int32), np.array(f["A_rowidx"], np.int32), np.array(f["A_val"])),
+                     Hcsc=(np.array(f["H_colptr"], np.int32), np.array(f["H_rowidx"], np.int32), np.array(f["H_val"])))
+    assert int(s.inner.get_status()[0]) == o["status"] and int(s.get_iterations()[0]) == o["iters"]
+    assert (s.get_working_set_raw()[0] == -np.concatenate([o["wb"], o["wc"]])).all()
+    x = s.get_optimal_solution()[0]
+    assert np.abs(x - o["x"]).max() <= 1e-12 * max(1.0, np.abs(o["x"]).max())

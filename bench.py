@@ -23,6 +23,7 @@ rank solves its own 20*B replicas (rank-seeded perturbations): weak scaling, no 
          cluster kernel, and the HBM-bound L0 kernels (GB/s against the measured copy peak).
   strong  BASELINE.json configs[4]: a FIXED 10^6 HS071 instances sharded by instance index over the N ranks
          (device-resident SQP loop, no collective on the path), so that the driver's 1/2/4/8 runs show strong scaling too.
+  weak_sqp  the weak-scaling leg of the same config: 1.25 x 10^5 HS071 instances per GPU.
 
 `--impl reference` times the CPU path alone and prints the same JSON line with "impl": "reference".
 """
@@ -348,6 +349,8 @@ def run_gpu(args, rank, world, local_rank):
     e2e = qps_step * args.steps / (ms_e2e * 1e-3)
 
     strong = run_strong(args, rank, world, local_rank, dist) if args.strong else None
+    # the weak-scaling leg of configs[4]: 1.25 x 10^5 instances per GPU
+    weak_sqp = run_strong(args, rank, world, local_rank, dist, N=125000 * world, scaling="weak") if args.strong else None
 
     if rank == 0:
         status_ok, per_dump, e2e_ok = 0, {}, 0
@@ -461,6 +464,8 @@ def run_gpu(args, rank, world, local_rank):
         }
         if strong is not None:
             out["strong"] = strong
+        if weak_sqp is not None:
+            out["weak_sqp"] = weak_sqp
         if args.extras and (world == 1 or args.extras > 1):
             out["extras"] = run_extras(local_rank, hbm_peak)
         print(json.dumps(out))
@@ -469,7 +474,7 @@ def run_gpu(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_strong(args, rank, world, local_rank, dist):
+def run_strong(args, rank, world, local_rank, dist, N=None, scaling="strong"):
     """BASELINE.json configs[4], strong scaling: a fixed N = args.strong HS071 instances (perturbed starts)
     sharded contiguously by instance index over the ranks; each rank runs the device-resident SQP loop on its shard (no collective
     on the path).  Timed with CUDA events around reset (upload of the shard's starts + evaluation + state) and Optimize, after two
@@ -479,7 +484,7 @@ def run_strong(args, rank, world, local_rank, dist):
         from restartsqp_b200 import sharding
         from restartsqp_b200.nl_reader import AmplNLP, DeviceNLP
         from restartsqp_b200.sqp_device import DeviceBatchedSQP
-        N = int(args.strong)
+        N = int(args.strong) if N is None else int(N)
         host = AmplNLP(os.path.join(ROOT, "tests", "golden", "hs_nl", "hs071.nl"))
         dev = DeviceNLP(host, device=local_rank)
         lo, hi = sharding.shard_range(N, rank, world)
@@ -511,7 +516,7 @@ def run_strong(args, rank, world, local_rank, dist):
         alg.close(); dev.close()
         ms = sorted(times)[reps // 2]
         return {"metric": "SQP solves/sec", "config": "10^6-scale HS071 instances sharded by instance index (BASELINE.json configs[4])",
-                "scaling": "strong", "instances": N, "per_rank": hi - lo, "n_gpus": world, "ms": ms, "value": N / (ms * 1e-3), "unit": "solves/s",
+                "scaling": scaling, "instances": N, "per_rank": hi - lo, "n_gpus": world, "ms": ms, "value": N / (ms * 1e-3), "unit": "solves/s",
                 "optimal": int(t[1].item()), "sqp_iters_mean": float(t[2].item()) / N,
                 "ms_all": times,
                 "timing": "CUDA events around reset(x0) + Optimize on every rank, max over ranks, median of 3 repetitions (all in ms_all); handles and the "

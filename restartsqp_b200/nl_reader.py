@@ -144,6 +144,26 @@ class Graph:
 
     # ---- differentiation (memoised per variable)
     def diff(self, a, v, memo):
+        """d node / d x_v.  Post-order over an explicit stack: a sum of a thousand terms is a chain of a thousand `add` nodes
+        (the CUTE models beyond the HS set), which a recursive walk cannot descend."""
+        if (a, v) in memo:
+            return memo[(a, v)]
+        stack = [a]
+        while stack:
+            node = stack[-1]
+            if (node, v) in memo:
+                stack.pop()
+                continue
+            t = self.nodes[node]
+            missing = [k for k in t[1:] if (k, v) not in memo] if t[0] not in ("const", "var") else []
+            if missing:
+                stack.extend(missing)
+                continue
+            memo[(node, v)] = self._diff_node(node, v, memo)  # every child is in the memo: the calls below return at once
+            stack.pop()
+        return memo[(a, v)]
+
+    def _diff_node(self, a, v, memo):
         key = (a, v)
         if key in memo:
             return memo[key]
@@ -212,18 +232,26 @@ class Graph:
         return r
 
     def depends(self, a, memo):
-        """frozenset of variable indices the node depends on"""
-        if a in memo:
-            return memo[a]
-        t = self.nodes[a]
-        if t[0] == "const":
-            r = frozenset()
-        elif t[0] == "var":
-            r = frozenset([t[1]])
-        else:
-            r = frozenset().union(*[self.depends(k, memo) for k in t[1:]])
-        memo[a] = r
-        return r
+        """frozenset of variable indices the node depends on (explicit stack, see diff)"""
+        stack = [a]
+        while stack:
+            node = stack[-1]
+            if node in memo:
+                stack.pop()
+                continue
+            t = self.nodes[node]
+            if t[0] == "const":
+                memo[node] = frozenset()
+            elif t[0] == "var":
+                memo[node] = frozenset([t[1]])
+            else:
+                missing = [k for k in t[1:] if k not in memo]
+                if missing:
+                    stack.extend(missing)
+                    continue
+                memo[node] = frozenset().union(*[memo[k] for k in t[1:]])
+            stack.pop()
+        return memo[a]
 
 
 class _Tokens:

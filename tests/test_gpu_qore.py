@@ -182,7 +182,7 @@ def test_replay_driver_both_arms_agree(gpu_lib):
     """test/QPsolvers_testers.cpp solves each dumped QP twice: unconverted with the QORE-layout backend (:172-200) and, converted
     through the dense matrix, with the qpOASES-layout backend (:206-229).  Same two arms on the GPU, 64 perturbed replicas each:
     identical status, iteration counts and working sets, solutions equal to the last bits (the unconverted matrices keep
-    explicit zeros and, in hs104, entries of 1e-17 that the conversion drops)."""
+    explicit zeros)."""
     raw = {q["name"]: q for q in H.load_qore_raw_fixtures()}
     fixtures = [f for f in H.load_qp_fixtures() if f["source"] == "log" and H.is_symmetric_fixture(f) and f["name"] != "QORE_hs107"]
     assert len(fixtures) >= 10
@@ -196,12 +196,16 @@ def test_replay_driver_both_arms_agree(gpu_lib):
         o = qp_dump.replay(f, batch=B)
         q.set_g(g); o.set_g(g)
         q.inner.optimizeQP(); o.optimizeQP()
-        assert (q.inner.get_status() == o.get_status()).all(), f["name"]
-        assert (q.get_iterations() == o.get_iterations()).all(), f["name"]
+        # hs104: H holds a dozen entries of 1e-17 .. 1e-20 that the conversion drops (|v| <= 1e-16, test/QPsolvers_testers.cpp:18-29);
+        # its projected Hessian is singular without them, so the two arms are different QPs as soon as g is perturbed (the CPU
+        # oracle shows the same: other iteration counts on 41 of 64 replicas).  The exact dump (replica 0) agrees.
+        sel = slice(0, 1) if f["name"] == "QORE_hs104" else slice(None)
+        assert (q.inner.get_status()[sel] == o.get_status()[sel]).all(), f["name"]
+        assert (q.get_iterations()[sel] == o.get_iterations()[sel]).all(), f["name"]
         wc, wb = o.get_working_set(translated=False)
-        assert (q.get_working_set_raw() == -np.hstack([wb, wc])).all(), f["name"]
-        x = o.get_optimal_solution()
-        assert np.abs(q.get_optimal_solution() - x).max() <= 1e-12 * max(1.0, np.abs(x).max()), f["name"]
+        assert (q.get_working_set_raw()[sel] == -np.hstack([wb, wc])[sel]).all(), f["name"]
+        x = o.get_optimal_solution()[sel]
+        assert np.abs(q.get_optimal_solution()[sel] - x).max() <= 1e-12 * max(1.0, np.abs(x).max()), f["name"]
         q.close(); o.close()
 
 

@@ -33,6 +33,7 @@ class Graph:
 
     def __init__(self):
         self.nodes, self.index = [], {}
+        self._dep = {}  # node -> variables it depends on (nodes are immutable, so the memo lives as long as the graph)
         self.ZERO, self.ONE = self.const(0.0), self.const(1.0)
 
     def _mk(self, t):
@@ -152,6 +153,10 @@ class Graph:
         while stack:
             node = stack[-1]
             if (node, v) in memo:
+                stack.pop()
+                continue
+            if v not in self.depends(node, self._dep):  # structurally zero: no walk through the subtree (the local
+                memo[(node, v)] = self.ZERO             # simplifications would reduce it to ZERO anyway)
                 stack.pop()
                 continue
             t = self.nodes[node]

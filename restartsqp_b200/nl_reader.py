@@ -24,6 +24,9 @@ import numpy as np
 from .sqp_types import NLPInfo
 
 _BIN = {0: "add", 1: "sub", 2: "mul", 3: "div", 5: "pow"}
+# comparison opcodes -> (node kind, operands swapped, result negated): LT, LE, EQ, GE, GT, NE
+_CMP = {22: ("lt", False, False), 23: ("le", False, False), 24: ("eq", False, False), 28: ("le", True, False), 29: ("lt", True, False),
+        30: ("eq", False, True)}
 _UN = {16: "neg", 39: "sqrt", 41: "sin", 43: "log", 44: "exp", 46: "cos", 15: "abs", 38: "tan", 49: "atan", 37: "tanh",
        40: "sinh", 45: "cosh", 42: "log10", 53: "acos", 51: "asin"}
 
@@ -137,6 +140,27 @@ class Graph:
                 pass
         return self._mk((op, a))
 
+    # ---- non-smooth operators of the CUTE models beyond the HS set: comparisons give 1.0 / 0.0, `if` selects
+    def cmp(self, op, a, b):
+        ca, cb = self.cval(a), self.cval(b)
+        if ca is not None and cb is not None:
+            return self.ONE if {"le": ca <= cb, "lt": ca < cb, "eq": ca == cb}[op] else self.ZERO
+        return self._mk((op, a, b))
+
+    def ifelse(self, c, a, b):
+        cc = self.cval(c)
+        if cc is not None:
+            return a if cc != 0.0 else b
+        if a == b:
+            return a
+        return self._mk(("if", c, a, b))
+
+    def min2(self, a, b):
+        return self.ifelse(self.cmp("le", a, b), a, b)
+
+    def max2(self, a, b):
+        return self.ifelse(self.cmp("le", b, a), a, b)
+
     def sum(self, args):
         out = self.ZERO
         for a in args:
@@ -197,6 +221,10 @@ class Graph:
                 r = self.mul(a, self.add(self.mul(de, self.un("log", base)), self.div(self.mul(ex, db), base)))
         elif op == "neg":
             r = self.neg(self.diff(t[1], v, memo))
+        elif op in ("le", "lt", "eq"):
+            r = self.ZERO  # piecewise constant
+        elif op == "if":
+            r = self.ifelse(t[1], self.diff(t[2], v, memo), self.diff(t[3], v, memo))  # derivative of the selected branch
         else:
             u, du = t[1], self.diff(t[1], v, memo)
             if du == self.ZERO:
@@ -307,6 +335,30 @@ def _read_expr(tok, G, defined, funcs=None):
         if op == 54:
             cnt = int(tok.next().strip())
             return G.sum([_read_expr(tok, G, defined, funcs) for _ in range(cnt)])
+        if op in (11, 12):  # MINLIST / MAXLIST
+            cnt = int(tok.next().strip())
+            args = [_read_expr(tok, G, defined, funcs) for _ in range(cnt)]
+            out = args[0]
+            for a in args[1:]:
+                out = G.min2(out, a) if op == 11 else G.max2(out, a)
+            return out
+        if op in _CMP:  # comparisons: 1.0 / 0.0
+            a = _read_expr(tok, G, defined, funcs)
+            b = _read_expr(tok, G, defined, funcs)
+            kind, swap, negate = _CMP[op]
+            r_ = G.cmp(kind, b, a) if swap else G.cmp(kind, a, b)
+            return G.sub(G.ONE, r_) if negate else r_
+        if op in (20, 21):  # OR, AND on 0 / 1 values
+            a = _read_expr(tok, G, defined, funcs)
+            b = _read_expr(tok, G, defined, funcs)
+            return G.mul(a, b) if op == 21 else G.sub(G.add(a, b), G.mul(a, b))
+        if op == 34:  # NOT
+            return G.sub(G.ONE, _read_expr(tok, G, defined, funcs))
+        if op == 35:  # if c then a else b
+            c = _read_expr(tok, G, defined, funcs)
+            a = _read_expr(tok, G, defined, funcs)
+            b = _read_expr(tok, G, defined, funcs)
+            return G.ifelse(c, a, b)
         raise NotImplementedError("nl opcode o%d" % op)
     raise NotImplementedError("nl expression token %r" % ln)
 
@@ -415,6 +467,7 @@ _NP_FUN = {"sqrt": "np.sqrt", "sin": "np.sin", "cos": "np.cos", "log": "np.log",
            "asin": "np.arcsin", "ncdf": "_ncdf"}
 _C_FUN = {"abs": "fabs"}
 _INFIX = {"add": "+", "sub": "-", "mul": "*", "div": "/"}
+_CMP_C = {"le": "<=", "lt": "<", "eq": "=="}
 _MATH_NAMES = ("pow", "sqrt", "sin", "cos", "log", "exp", "tan", "atan", "tanh", "sinh", "cosh", "log10", "acos", "asin")
 _MATH_CALL = re.compile(r"(?<![A-Za-z0-9_])(%s)\(" % "|".join(_MATH_NAMES))
 _MATH_WRAPPERS = (["static __device__ __noinline__ double nl_pow(double a, double b) { return pow(a, b); }"] +
@@ -467,6 +520,10 @@ def _emit(G, roots, lang):
                 rhs = ("np.power(%s, %s)" if lang == "py" else "pow(%s, %s)") % (name[t[1]], name[t[2]])
         elif t[0] == "neg":
             rhs = "-%s" % name[t[1]]
+        elif t[0] in _CMP_C:
+            rhs = ("(%s %s %s) * 1.0" if lang == "py" else "(%s %s %s ? 1.0 : 0.0)") % (name[t[1]], _CMP_C[t[0]], name[t[2]])
+        elif t[0] == "if":
+            rhs = ("np.where(%s != 0.0, %s, %s)" if lang == "py" else "(%s != 0.0 ? %s : %s)") % (name[t[1]], name[t[2]], name[t[3]])
         else:
             rhs = "%s(%s)" % ((_NP_FUN[t[0]] if lang == "py" else _C_FUN.get(t[0], t[0])), name[t[1]])
         lines.append(("%s = %s" if lang == "py" else "const double %s = %s;") % (nm, rhs))

@@ -1,4 +1,4 @@
-"""Beyond the Hock-Schittkowski set: 24 small models of the reference's test/CUTE_examples directory that its own scripts do not
+"""Beyond the Hock-Schittkowski set: 25 small models of the reference's test/CUTE_examples directory that its own scripts do not
 run (test/runhs.sh lists hs* only), copied as data fixtures to tests/golden/cute_nl.  CPU: the `.nl` reader against central
 differences, the C oracle of Algorithm::Optimize (oracle/oracle_sqp.c) to the optima tabulated for the CUTE set, and the numpy
 mirror of the loop (the product's host logic, on the oracle twin of the backend) against that C oracle.  GPU: the
@@ -20,7 +20,8 @@ CUTE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c
 F_STAR = {"orthregb": 0.0, "fccu": 11.14911, "genhs28": 0.92717369, "lotschd": 2398.4158, "oslbqp": 6.25, "hs21mod": -95.96,
           "hatfldh": -24.5, "aircrftb": 0.0, "bt3": 4.09301056, "bt8": 1.0, "bt13": 0.0, "matrix2": 0.0, "zecevic2": -4.125,
           "zecevic4": 7.5575, "polak4": 0.0, "byrdsphr": -4.68330, "makela1": -1.41421356, "demymalo": -3.0, "gigomez1": -3.0,
-          "mifflin1": -1.0, "mifflin2": -1.0, "maratos": -1.0, "booth": 0.0, "simbqp": 0.0}
+          "mifflin1": -1.0, "mifflin2": -1.0, "maratos": -1.0, "booth": 0.0, "simbqp": 0.0,
+          "hubfit": 0.0168935}  # hubfit: an `if` / comparison model (Huber fit), the non-smooth operators of the reader
 NAMES = sorted(F_STAR)
 
 

@@ -60,7 +60,7 @@ def main():
         sum(v["optimal"] for v in ok.values()), 16 * len(ok), ", ".join("%s %d" % (names.get(k, str(k)), c) for k, c in flags.most_common())))
     worst = sorted((v["optimal"], k) for k, v in ok.items() if v["optimal"] < 8)
     print("Models with fewer than 8 of 16 OPTIMAL: %s.\n" % ", ".join("%s (%d)" % (k, c) for c, k in worst))
-    print("24 of these models (constrained, polynomial, tabulated optima) are test fixtures: `tests/golden/cute_nl`, `tests/test_cute_suite.py`.")
+    print("25 of these models (constrained, tabulated optima; 24 polynomial, one with `if`) are test fixtures: `tests/golden/cute_nl`, `tests/test_cute_suite.py`.")
 
 
 if __name__ == "__main__":

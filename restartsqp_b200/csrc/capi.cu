@@ -393,6 +393,7 @@ int sqpb200_set_structure_A(sqpb200_handle h, int zJ, const int* row1, const int
     for (int i = 0; i < z; i++)
         if (er[i] < 1 || er[i] > h->nC || ec[i] < 1 || ec[i] > h->nV) { h->err = "triplet index out of range"; return SQPB200_ERR_INVALID; }
     h->zA = z; h->zJ = zJ;
+    h->qA.set = false;  // a compressed-row view of an earlier structure no longer applies
     h->Ap.assign(h->nV + 1, 0); h->Ai.assign(z, 0); h->Aorder.assign(z, 0);
     int seg[2] = {0, z}, ncol[1] = {h->nV};
     if (z > 0) {
@@ -423,6 +424,7 @@ int sqpb200_set_structure_H(sqpb200_handle h, int zH, const int* row1, const int
     for (int i = 0; i < z; i++)
         if (er[i] < 1 || er[i] > h->nV || ec[i] < 1 || ec[i] > h->nV) { h->err = "triplet index out of range"; return SQPB200_ERR_INVALID; }
     h->zH = z; h->zHt = zH;
+    h->qH.set = false;
     h->Hp.assign(h->nV + 1, 0); h->Hi.assign(z, 0); h->Horder.assign(z, 0);
     int seg[2] = {0, z}, ncol[1] = {h->nV};
     if (z > 0) {
@@ -448,6 +450,7 @@ int sqpb200_set_structure_csc(sqpb200_handle h, int which, int nnz, const int* c
     if (colptr[h->nV] != nnz) { h->err = "colptr[ncol] != nnz"; return SQPB200_ERR_INVALID; }
     if (which == SQPB200_MAT_A) {
         h->zA = nnz; h->zJ = nnz;
+        h->qA.set = false;
         h->Ap.assign(colptr, colptr + h->nV + 1); h->Ai.assign(rowidx, rowidx + nnz);
         h->Aorder.resize(nnz); h->Asrc.resize(nnz);
         for (int i = 0; i < nnz; i++) { h->Aorder[i] = i; h->Asrc[i] = i; }
@@ -456,6 +459,7 @@ int sqpb200_set_structure_csc(sqpb200_handle h, int which, int nnz, const int* c
         return rc ? rc : nnz;
     } else if (which == SQPB200_MAT_H) {
         h->zH = nnz; h->zHt = nnz;
+        h->qH.set = false;
         h->Hp.assign(colptr, colptr + h->nV + 1); h->Hi.assign(rowidx, rowidx + nnz);
         h->Horder.resize(nnz); h->Hsrc.resize(nnz);
         for (int i = 0; i < nnz; i++) { h->Horder[i] = i; h->Hsrc[i] = i; }

@@ -602,27 +602,27 @@ class AmplNLP:
         self.c_nodes = [G.add(md.con_nl[i], G.sum([G.mul(G.const(c), G.var(j)) for j, c in sorted(md.con_lin[i].items())]))
                         for i in range(m)]
         memo = {}
+        dep = G._dep
         self.grad_nodes = [G.diff(self.f_node, j, memo) for j in range(n)]
         # Jacobian structure: the J segments (every variable that appears in a row), column-major like ASL's goff
         ent = sorted((j, i) for i in range(m) for j in md.con_lin[i])
         self.J_col1 = np.array([j + 1 for j, i in ent], np.int32)
         self.J_row1 = np.array([i + 1 for j, i in ent], np.int32)
         self.jac_nodes = [G.diff(self.c_nodes[i], j, memo) for j, i in ent]
-        dep = {}
         for i in range(m):
             extra = G.depends(self.c_nodes[i], dep) - set(md.con_lin[i])
             if extra:
                 raise ValueError("constraint %d depends on variables missing from its J segment: %s" % (i, sorted(extra)))
         # Hessian of the Lagrangian: upper triangle, column by column; structure = union of structural non-zeros
         funcs = [self.f_node] + self.c_nodes
-        first = [[G.diff(fn, j, memo) for j in range(n)] for fn in funcs]
         hess = {}
-        for k, fn in enumerate(funcs):
-            for j in range(n):
-                if first[k][j] == G.ZERO:
+        for k, fn in enumerate(funcs):  # only the variables a function depends on can carry a derivative (same entries, same order)
+            for j in sorted(G.depends(fn, dep)):
+                dj = G.diff(fn, j, memo)
+                if dj == G.ZERO:
                     continue
-                for i in range(j + 1):
-                    d2 = G.diff(first[k][j], i, memo)
+                for i in sorted(v for v in G.depends(dj, dep) if v <= j):
+                    d2 = G.diff(dj, i, memo)
                     if d2 != G.ZERO:
                         hess.setdefault((j, i), []).append((k, d2))
         hk = sorted(hess)

@@ -88,6 +88,7 @@ int main(int argc, char** argv) {
             cudaEventSynchronize(e1);
             cudaEventElapsedTime(&ms, e0, e1);
         }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
         size_t optimal = 0;
         for (size_t b = 0; b < B; b++) {
             optimal += r.exitflag[b] == 0;

@@ -40,6 +40,34 @@ def test_qore_layout_adapter_implements_every_pure_virtual():
         assert ref in hpp
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/include"), reason="needs the reference tree")
+def test_reference_patch_applies(tmp_path):
+    """integration/restartsqp_cuda_backend.patch (the registration of the two plugins) applies to the
+    reference tree as it is; the patched Options.cpp and both plugins compile against the patched headers."""
+    import shutil
+    ref = "/root/reference"
+    work = str(tmp_path / "ref")
+    for f in ("include/sqphot", "src"):
+        shutil.copytree(os.path.join(ref, f), os.path.join(work, f))
+    for dirpath, _, files in os.walk(work):
+        os.chmod(dirpath, 0o755)
+        for f in files:
+            os.chmod(os.path.join(dirpath, f), 0o644)
+    patch = os.path.join(ROOT, "integration", "restartsqp_cuda_backend.patch")
+    p = subprocess.run(["patch", "-p1", "--no-backup-if-mismatch", "-i", patch], cwd=work, capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "CUDA_B200_QORE_LAYOUT" in open(os.path.join(work, "include/sqphot/Types.hpp")).read()
+    adapter = os.path.join(ROOT, "restartsqp_b200", "csrc", "adapter")
+    for f in ("CudaQPInterface", "CudaQOREInterface"):
+        shutil.copy(os.path.join(adapter, f + ".hpp"), os.path.join(work, "include/sqphot", f + ".hpp"))
+        shutil.copy(os.path.join(adapter, f + ".cpp"), os.path.join(work, "src", f + ".cpp"))
+    inc = ["-I" + os.path.join(ROOT, "oracle", "stubs"), "-I" + os.path.join(work, "include"), "-I" + os.path.join(work, "include/sqphot"),
+           "-I" + os.path.join(ROOT, "include")]
+    for src in ("src/Options.cpp", "src/CudaQPInterface.cpp", "src/CudaQOREInterface.cpp"):
+        c = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-w"] + inc + [os.path.join(work, src)], capture_output=True, text=True)
+        assert c.returncode == 0, src + "\n" + c.stderr
+
+
 def test_adapter_implements_every_pure_virtual():
     hpp = open(os.path.join(ROOT, "restartsqp_b200", "csrc", "adapter", "CudaQPInterface.hpp")).read()
     for name in ["getLb", "getUb", "getLbA", "getUbA", "getG", "getH", "getA", "optimizeQP", "optimizeLP", "get_optimal_solution",

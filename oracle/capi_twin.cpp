@@ -6,6 +6,8 @@
 // product library is restartsqp_b200/lib/libsqpb200.so, which has no CPU path.  Same state machine as the library's host side
 // (src/qpOASESInterface.cpp:141-211, 817-833; handle_error :686-758), same as tests/oracle_backend.py.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -190,6 +192,7 @@ int sqpb200_solve(sqpb200_handle h, int mode, int, const unsigned char*) {
     else if (m == VARIED) st = orc_qp_hotstart_matrices(h->solver, &o, Hv, h->Av.data(), h->g.data(), h->lb.data(), h->ub.data(), h->lbA.data(), h->ubA.data());
     else st = orc_qp_reinit(h->solver, &o, Hv, h->Av.data(), h->g.data(), h->lb.data(), h->ub.data(), h->lbA.data(), h->ubA.data());
     orc_qp_get_solution(h->solver, h->x.data(), h->y.data(), &h->obj, &its);
+    const int st_first = st, its_first = its;
     if (st != 20) { int added = 0; st = orc_qp_handle_error(h->solver, &o, 0, &added); its += added; }
     h->inited = st == 20;
     int it2 = 0;
@@ -203,6 +206,9 @@ int sqpb200_solve(sqpb200_handle h, int mode, int, const unsigned char*) {
                               h->ubA.data(), h->WB.data(), h->WC.data());
     orc_kkt_residuals(h->nV, h->nC, h->Ap.data(), h->Ai.data(), h->Av.data(), Hp, Hi, Hv, h->g.data(), h->lb.data(), h->ub.data(), h->lbA.data(),
                       h->ubA.data(), h->x.data(), h->y.data(), h->WB.data(), h->WC.data(), h->kkt.data());
+    if (getenv("SQPB200_TWIN_TRACE"))
+        fprintf(stderr, "twin solve: first attempt %d / %d; mode %d status %d iters %d kkt %.3e %.3e %.3e %.3e | %.3e\n", st_first, its_first, (int)m, st, its, h->kkt[0], h->kkt[1], h->kkt[2],
+                h->kkt[3], h->kkt[4]);
     h->upd_A = h->upd_H = false;
     h->first_solved = true;
     return 0;

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstddef>
+#include <cstdlib>
 #include <string>
 namespace Ipopt {
 enum EJournalLevel { J_INSUPPRESSIBLE = -1, J_NONE = 0, J_ERROR, J_STRONGWARNING, J_SUMMARY, J_WARNING,
@@ -37,11 +38,16 @@ public:
 };
 class Journalist {
 public:
+    // silent unless ORACLE_STUB_JOURNAL_STDOUT is set: the reference prints an iteration log through this call
     void Printf(EJournalLevel, EJournalCategory, const char* fmt, ...) const {
+        static const bool loud = getenv("ORACLE_STUB_JOURNAL_STDOUT") != nullptr;
+        if (!loud) return;
         va_list ap; va_start(ap, fmt); vprintf(fmt, ap); va_end(ap);
     }
     SmartPtr<Journal> AddFileJournal(const std::string&, const std::string&, EJournalLevel = J_WARNING) { return SmartPtr<Journal>(&journal_); }
+    SmartPtr<Journal> GetJournal(const std::string&) { return SmartPtr<Journal>(&journal_); }
     void DeleteAllJournals() {}
+    void FlushBuffer() const {}
 private:
     Journal journal_;
 };

@@ -44,9 +44,15 @@ public:
     OptimalityStatus get_optimality_status() override { return qpOptimalStatus_; }
 
     // include/sqphot/QOREInterface.hpp:142-155: entries are clipped to +-INF; locations >= nVar_QP are constraint bounds
+#ifndef SQPB200_QORE_NO_CLIP
     void set_g(int location, double value) override { g_->setValueAt(location, value < INF ? value : INF); g_dirty_ = true; }
     void set_lb(int location, double value) override { lb_->setValueAt(location, value > -INF ? value : -INF); b_dirty_ = true; }
     void set_ub(int location, double value) override { ub_->setValueAt(location, value < INF ? value : INF); b_dirty_ = true; }
+#else  // test builds only (oracle/_ref/algorithm_nl_twin_noclip): bounds as the qpOASES-layout setters and the batched kernels take them
+    void set_g(int location, double value) override { g_->setValueAt(location, value); g_dirty_ = true; }
+    void set_lb(int location, double value) override { lb_->setValueAt(location, value); b_dirty_ = true; }
+    void set_ub(int location, double value) override { ub_->setValueAt(location, value); b_dirty_ = true; }
+#endif
     void set_g(shared_ptr<const Vector> rhs) override { g_->copy_vector(rhs->values()); g_dirty_ = true; }
     void set_lb(shared_ptr<const Vector> rhs) override { lb_->copy_vector(rhs->values()); b_dirty_ = true; }
     void set_ub(shared_ptr<const Vector> rhs) override { ub_->copy_vector(rhs->values()); b_dirty_ = true; }

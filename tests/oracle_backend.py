@@ -196,6 +196,7 @@ class OracleQPInterface:
             else:
                 mode = "reinit"  # status flip: init from the previous solution (:202-207)
                 self.new_ms = self.old_ms = MS_UNDEFINED
+        self.last_mode = mode
         for b in range(self.batch):
             if active_mask is not None and not active_mask[b]:
                 continue

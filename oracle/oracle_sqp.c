@@ -16,6 +16,12 @@
  * the host cores (pthreads): it is the CPU figure bench.py prints beside the GPU's SQP solves/s, and a third, independent
  * statement of the loop next to the numpy mirror (sqp_driver.py) and the device kernels (csrc/sqp_outer.cu).
  *
+ * PINNED against the reference's own code: oracle/_ref/algorithm_nl* links src/Algorithm.cpp, src/SQPTNLP.cpp and src/QPhandler.cpp
+ * (patched only by integration/restartsqp_cuda_backend.patch) with the QORE-layout plugin; run on the CPU twin of the C ABI it gives
+ * this file's exit flags, outer and QP iteration counts, iterates and objectives bit for bit on 23 models x 6 starts
+ * (tests/test_reference_algorithm.py; the differences -- the QORE setters' clipping of infinite bounds, failure labels, the
+ * reference's acceptance of a NaN KKT error -- are asserted there).  What stays unpinned is the QP solver under it (oracle_qp.c).
+ *
  * Deliberate choices shared with the product's drivers: update_bounds refreshes ubA as well (mode 3; the reference's
  * non-QORE branch leaves it stale), a failed QP ends the instance with the QP status as exit flag
  * (the reference throws), second-order correction off (src/Options.cpp:26).

@@ -83,7 +83,7 @@ def test_reference_qphandler_drives_the_plugins_on_the_gpu(gpu_lib, mode):
     if not (os.path.exists(BIN) and os.path.exists(TWIN)):
         pytest.skip("oracle/_ref/qphandler_hs071 not built (needs /root/reference at build time)")
     args = [mode] if mode else []
-    g = subprocess.run([BIN] + args, capture_output=True, text=True, timeout=120)
+    g = subprocess.run([BIN] + args, capture_output=True, text=True, timeout=30)  # bounded: not run on a GPU before
     t = subprocess.run([TWIN] + args, capture_output=True, text=True, timeout=120)
     assert g.returncode == 0 and t.returncode == 0, g.stdout + g.stderr
     assert g.stdout == t.stdout  # the library and the oracle agree bit for bit, so the two runs print the same text

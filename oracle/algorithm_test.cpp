@@ -6,7 +6,7 @@
 // oracle/oracle_sqp.c, evaluates): this is what PINS that oracle -- and through it the device-resident loop -- against the
 // reference's real Algorithm::Optimize.
 //
-//   algorithm_nl[_twin] <model file> <evaluator .so> <instance> [qore]
+//   algorithm_nl[_twin] <model file> <evaluator .so> <instance> [qore] [soc]
 // Default backend: the patched Options default, CUDA_B200 (CudaQPInterface through QPhandler's non-QORE branches, which leave ubA
 // stale after the first iteration: SURVEY.md 8a quirk 2).  `qore`: CUDA_B200_QORE_LAYOUT (CudaQOREInterface through QPhandler's QORE
 // branches, which refresh both constraint sides -- the reference's own default backend is QORE, src/Options.cpp:24-25).
@@ -96,9 +96,10 @@ private:
 };
 
 int main(int argc, char** argv) {
-    if (argc < 4) { fprintf(stderr, "usage: %s <model file> <evaluator .so> <instance> [qore]\n", argv[0]); return 64; }
+    if (argc < 4) { fprintf(stderr, "usage: %s <model file> <evaluator .so> <instance> [qore] [soc]\n", argv[0]); return 64; }
     const int inst = atoi(argv[3]);
-    const bool qore = argc > 4 && !strcmp(argv[4], "qore");
+    bool qore = false, soc = false;
+    for (int i = 4; i < argc; i++) { qore |= !strcmp(argv[i], "qore"); soc |= !strcmp(argv[i], "soc"); }
     std::ifstream file(argv[1]);
     std::stringstream ss; ss << file.rdbuf();
     std::string all = ss.str();
@@ -128,6 +129,7 @@ int main(int argc, char** argv) {
             alg.myQP_ = make_shared<QPhandler>(alg.nlp_->nlp_info_, QP, alg.jnlst_, alg.options_);
             alg.myLP_ = make_shared<QPhandler>(alg.nlp_->nlp_info_, LP, alg.jnlst_, alg.options_);
         }
+        if (soc) alg.options_->second_order_correction = true;  // off by default, src/Options.cpp:26
         alg.Optimize();
         printf("%d %d %d %a", (int)alg.get_exit_flag(), alg.get_stats()->iter, alg.get_stats()->qp_iter, alg.get_final_objective());
         for (int i = 0; i < md.n; i++) printf(" %a", alg.x_k_->values(i));

@@ -89,6 +89,31 @@ def test_reference_optimize_with_the_plugin_as_shipped(name, tmp_path):
 
 
 @needs_ref
+def test_reference_second_order_correction_equals_the_oracle(tmp_path):
+    """The opt-in second-order correction (src/Algorithm.cpp:1140-1211) of the reference's real code against the oracle's: same exit
+    flags, outer and QP iteration counts on 7 models x 6 starts (on five of them the correction changes the run); the iterates
+    agree bit for bit except for one hs100 run that differs by one unit in the last place in two components (not traced yet)."""
+    exact = total = 0
+    for name in ["hs006", "hs043", "hs100", "hs015", "hs113", "hs071", "hs038"]:
+        h = AmplNLP(os.path.join(HS_DIR, name + ".nl"))
+        X = perturbed_starts(h, B, 4)
+        res = orc.SqpOracle(h, r.Options(second_order_correction=True)).solve_batch(X)
+        model = str(tmp_path / (name + ".model"))
+        write_model_file(h, model, X)
+        ev = sorted(glob.glob(os.path.join(ROOT, "oracle", "_gen", "nlp_%s_*.so" % name)), key=os.path.getmtime)[-1]
+        for k in range(B):
+            p = subprocess.run([NOCLIP, model, ev, str(k), "qore", "soc"], capture_output=True, text=True, timeout=300)
+            assert p.returncode == 0, (name, k, p.stdout)
+            t = p.stdout.split()
+            x = np.array([float.fromhex(v) for v in t[4:]])
+            assert (int(t[0]), int(t[1]), int(t[2])) == (int(res["exitflag"][k]), int(res["iters"][k]), int(res["qp_iter"][k])), (name, k)
+            assert np.abs(x - res["x"][k]).max() <= 1e-14 * max(1.0, np.abs(x).max()), (name, k)
+            exact += int(np.array_equal(x, res["x"][k]))
+            total += 1
+    assert total == 42 and exact >= 41
+
+
+@needs_ref
 def test_clipped_far_bounds_change_qp_iterations_not_results(tmp_path):
     """hs015 (non-convex, one-sided constraints): with the bounds clipped to 1e18 two of six runs take other QP iterations
     (flipped bounds land on the far bound's value) and arrive at the same iterates."""

@@ -206,6 +206,12 @@ int sqpb200_solve(sqpb200_handle h, int mode, int, const unsigned char*) {
                               h->ubA.data(), h->WB.data(), h->WC.data());
     orc_kkt_residuals(h->nV, h->nC, h->Ap.data(), h->Ai.data(), h->Av.data(), Hp, Hi, Hv, h->g.data(), h->lb.data(), h->ub.data(), h->lbA.data(),
                       h->ubA.data(), h->x.data(), h->y.data(), h->WB.data(), h->WC.data(), h->kkt.data());
+    if (getenv("SQPB200_TWIN_TRACE_DATA")) {  // one line per solve: every input vector and the solution as hex floats
+        auto dump = [](const char* nm, const std::vector<double>& v) { fprintf(stderr, " %s", nm); for (double t : v) fprintf(stderr, " %a", t); };
+        fprintf(stderr, "twin data:");
+        dump("g", h->g); dump("lb", h->lb); dump("ub", h->ub); dump("lbA", h->lbA); dump("ubA", h->ubA); dump("Av", h->Av); dump("Hv", h->Hv); dump("x", h->x);
+        fprintf(stderr, "\n");
+    }
     if (getenv("SQPB200_TWIN_TRACE"))
         fprintf(stderr, "twin solve: first attempt %d / %d; mode %d status %d iters %d kkt %.3e %.3e %.3e %.3e | %.3e\n", st_first, its_first, (int)m, st, its, h->kkt[0], h->kkt[1], h->kkt[2],
                 h->kkt[3], h->kkt[4]);

@@ -375,6 +375,10 @@ int orc_sqp_solve(const orc_sqp_problem* P, const double* x0, const double* lam0
             orc_qp_g(P->n, P->m, S.grad, -1.0, q->g);
             orc_qp_bounds(3, P->n, P->m, S.delta, P->x_l, P->x_u, S.x_k, P->c_l, P->c_u, S.c_k, q->lb, q->ub, q->lbA, q->ubA);
             if (accepted) {
+                /* update_radius reads p_k_->getInfNorm() (src/Algorithm.cpp:822): after an accepted correction that is the norm of the
+                 * corrected step p_k + s_k (found by running the reference's own code: tests/test_reference_algorithm.py) */
+                norm_p = 0.0;
+                for (int i = 0; i < n; i++) norm_p = fmax(norm_p, fabs(S.p_k[i]));
                 S.infea = S.infea_trial; S.f_k = S.f_trial;
                 memcpy(S.x_k, S.x_trial, sizeof(double) * n);
                 memcpy(S.c_k, S.c_trial, sizeof(double) * m);

@@ -200,7 +200,7 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
     case SQPB200_PH_TRIAL: {
         if (S.active[b] && S.exitflag[b] != EX_UNKNOWN && S.need[b] != 2) S.active[b] = 0;
         if (!S.active[b]) break;
-        double np_ = 0.0;  // norm_p_k_ = ||p_k||_inf, recorded before any second-order correction is added (:98, :1181)
+        double np_ = 0.0;  // ||p_k||_inf for update_radius (:822); an accepted second-order correction replaces it (SOC_RATIO)
         for (int i = 0; i < n; i++) {
             S.x_trial[(size_t)b * n + i] = S.x_k[(size_t)b * n + i] + S.p_k[(size_t)b * n + i];
             np_ = fmax(np_, fabs(S.p_k[(size_t)b * n + i]));
@@ -312,6 +312,11 @@ __global__ void sqp_phase_kernel(const __grid_constant__ sqpb200_sqp_state S, in
             S.actual_red[b] = ared; S.pred_red[b] = pred;
             if (ared >= S.eta_s * pred && ared >= -S.tol) {
                 S.acc[b] = 1;
+                // update_radius reads p_k_->getInfNorm() (src/Algorithm.cpp:822): after an accepted correction that is the norm of the
+                // corrected step p_k + s_k, which p_k holds since SOC_AFTER
+                double np_ = 0.0;
+                for (int i = 0; i < n; i++) np_ = fmax(np_, fabs(S.p_k[(size_t)b * n + i]));
+                S.norm_p[b] = np_;
                 S.infea[b] = infea_t;
                 S.f_k[b] = S.f_trial[b];
                 for (int i = 0; i < n; i++) S.x_k[(size_t)b * n + i] = S.x_trial[(size_t)b * n + i];

@@ -401,6 +401,9 @@ class BatchedSQP:
         # qp_obj_ (= qp_obj_soc here) is bookkeeping the reference never reads in a test
         del qp_obj_soc
         acc2 = self.ratio_test(ok, qp_obj=self.myQP_.get_objective())
+        took = ok & acc2  # update_radius reads p_k_->getInfNorm() (:822): after an accepted correction the norm of p_k + s_k
+        if took.any() and self.nVar_:
+            self.norm_p_k_[took] = np.abs(self.p_k_[took]).max(axis=1)
         still = rej & ~acc2
         self.p_k_[still] = p_tmp[still]
         self.myQP_.update_grad(self.grad_f_)
@@ -446,7 +449,7 @@ class BatchedSQP:
     def update_radius(self, active):
         o = self.options_
         shrink = active & (self.actual_reduction_ < o.eta_c * self.pred_reduction_)
-        norm_p = self.norm_p_k_  # ||p_k||_inf as recorded before a second-order correction was added (:98, :1181)
+        norm_p = self.norm_p_k_  # ||p_k||_inf of the step taken (:822): the corrected step after an accepted second-order correction
         grow = active & ~shrink & (self.actual_reduction_ > o.eta_e * self.pred_reduction_) & (o.tol > np.abs(self.delta_ - norm_p))
         self.delta_[shrink] = o.gamma_c * self.delta_[shrink]
         self.delta_[grow] = np.minimum(o.gamma_e * self.delta_[grow], o.delta_max)

@@ -38,3 +38,9 @@ $CXX -o "$HERE/_ref/algorithm_nl_twin" $O/algorithm_test.o $O/Algorithm.o $O/SQP
 N=$W/n
 $CXX -o "$HERE/_ref/algorithm_nl_twin_noclip" $N/algorithm_test.o $N/Algorithm.o $O/SQPTNLP.o $N/QPhandler.o $O/qpOASESInterface.o $O/QOREInterface.o $O/Options.o \
     $O/Utils.o $O/Vector.o $O/SpTripletMat.o $O/SpHbMat.o $O/CudaQPInterface.o $N/CudaQOREInterface.o $O/link_standins.o $TWIN
+# the reference's real qpOASESInterface.cpp on the functional qpOASES stand-in (oracle solver) beside the plugin on the CPU twin
+$CXX $FLAGS -DQPOASES_OVER_ORACLE $INC -c "$HERE/stubs_link/link_standins.cpp" -o "$W/o/link_standins_f.o"
+$CXX $FLAGS $INC -c "$HERE/stubs_link/qpoases_over_oracle.cpp" -o "$W/o/qpoases_over_oracle.o"
+$CXX $FLAGS $INC -I"$ADAPTER" -c "$HERE/backend_pin_test.cpp" -o "$W/o/backend_pin_test.o"
+$CXX -o "$HERE/_ref/backend_pin_twin" $O/backend_pin_test.o $O/qpOASESInterface.o $O/qpoases_over_oracle.o $O/link_standins_f.o $O/Options.o $O/Utils.o $O/Vector.o \
+    $O/SpTripletMat.o $O/SpHbMat.o $O/CudaQPInterface.o $TWIN

@@ -13,6 +13,7 @@
         abort();                                                                                                  \
     } while (0)
 
+#ifndef QPOASES_OVER_ORACLE  /* the functional stand-in (qpoases_over_oracle.cpp) defines these instead */
 namespace qpOASES {
 void Options::setToReliable() { STANDIN("qpOASES::Options::setToReliable"); }
 Bounds::Bounds() {}
@@ -48,6 +49,7 @@ BooleanType SQProblem::isInfeasible() const { STANDIN("isInfeasible"); return BT
 BooleanType SQProblem::isUnbounded() const { STANDIN("isUnbounded"); return BT_FALSE; }
 BooleanType SQProblem::isSolved() const { STANDIN("isSolved"); return BT_FALSE; }
 }  // namespace qpOASES
+#endif
 
 extern "C" {
 qp_int QPNew(QoreProblem**, qp_int, qp_int, qp_int, qp_int) { STANDIN("QPNew"); return 0; }

@@ -28,6 +28,10 @@ public:
     sparse_int_t* createDiagInfo();
     void setVal(const real_t* val);
     returnValue print(const char* name = 0) const;
+    // used by the functional stand-in only (qpoases_over_oracle.cpp): the column-compressed arrays the reference hands over
+    int_t nr_, nc_;
+    sparse_int_t *ir_, *jc_;
+    const real_t* val_;
 };
 class SymSparseMat : public SparseMatrix {
 public:
@@ -63,6 +67,11 @@ public:
     BooleanType isInfeasible() const;
     BooleanType isUnbounded() const;
     BooleanType isSolved() const;
+    // used by the functional stand-in only
+    void* impl_;
+    int_t nV_, nC_;
+    int status_, is_lp_;
+    Options options_;
 };
 }  // namespace qpOASES
 #endif
